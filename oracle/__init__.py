@@ -1,0 +1,79 @@
+"""oracle/ — CPU restatement of the reference hot path.  TEST INFRASTRUCTURE ONLY.
+
+Who may import this package: ``tests/``, ``__graft_entry__.smoke()``, and ``bench.py``'s
+``cpu_baseline`` leg / ``--impl reference`` arm.  The product package
+``dl_image_segmentation_b200`` never imports it and has no CPU fallback.
+
+What it restates (reference = harry-gibson/dl_image_segmentation, paths under
+``/root/reference/dl_segmentation_utils``):
+
+=====================  ==========================================================================
+``partition``          ``_img_to_tf_mp.py:102-122,167-170,213-226`` (seeded shuffle, linspace ranges,
+                       shard names); same code in ``_img_to_tf_threaded.py:163-170,236-239,297-314``
+``example_proto``      ``_tfrecord_image_translation.py:7-211`` (feature wrappers + ``convert_to_example``)
+                       and ``:216-415`` (templates + the five ``parse_*_proto``)
+``tfrecord``           ``tf.io.TFRecordWriter`` / ``TFRecordDataset`` call sites
+                       (``_img_to_tf_mp.py:119,141,150``; ``parse_tfrecords.ipynb`` cell 4)
+``imagecodecs``        ``load_image_rasterio`` (``_img_to_tf_mp.py:22-75``) and ``_process_image``
+                       (``_img_to_tf_threaded.py:75-121``): TIFF (LZW / DEFLATE / none) and PNG decode
+``composite``          ``_descartes_img_chips.py:562-567`` (np.ma median) and ``:461-469,603-626``
+                       (date/cloud filter, stable descending sort, painter's mosaic), ``:516`` dstack
+``normalise``          north-star row A17 (cast, per-band normalise, one-hot, integer band statistics)
+``translate``          the whole worker loop ``_img_to_tf_mp.py:78-157`` on top of the pieces above
+=====================  ==========================================================================
+
+PARITY STATUS — **parity unpinned by the reference**: the reference ships no tests, golden
+vectors or fixtures and none of its dependencies (tensorflow, rasterio/GDAL,
+descarteslabs) can be imported in the build container, so it cannot be executed to make
+fixtures either.  The arithmetic it delegates lives in un-pinned third-party libraries
+(conda_env_cpu.yml:5-12).  The oracle is therefore pinned from the outside instead:
+RFC 3720 B.4 CRC-32C vectors; ``google.protobuf`` (dynamic ``tensorflow.Example`` descriptor,
+deterministic serialisation); ``zlib``; libtiff 4.7.1 through ``cv2`` and ``Pillow``; libpng through
+``Pillow``; and ``numpy.ma.median`` itself (NumPy is the real implementation the reference calls).
+Those checks live in ``tests/test_oracle_*.py`` and the committed vectors in ``tests/golden/``.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libb2oracle.so")
+_SRC = os.path.join(_HERE, "csrc", "b2oracle.c")
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/csrc/b2oracle.c with gcc (no GPU, no CUDA)."""
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+        os.makedirs(os.path.dirname(_SO), exist_ok=True)
+        subprocess.check_call(["gcc", "-O3", "-msse4.2", "-fPIC", "-shared", "-o", _SO, _SRC])
+    return _SO
+
+
+_lib = None
+
+
+def clib():
+    global _lib
+    if _lib is None:
+        L = ctypes.CDLL(build())
+        u8p, u64p = ctypes.c_void_p, ctypes.c_void_p
+        L.orc_crc32c.restype = ctypes.c_uint32
+        L.orc_crc32c.argtypes = [u8p, ctypes.c_size_t]
+        L.orc_crc32c_sw.restype = ctypes.c_uint32
+        L.orc_crc32c_sw.argtypes = [u8p, ctypes.c_size_t]
+        L.orc_mask_crc.restype = ctypes.c_uint32
+        L.orc_mask_crc.argtypes = [ctypes.c_uint32]
+        L.orc_masked_crc32c.restype = ctypes.c_uint32
+        L.orc_masked_crc32c.argtypes = [u8p, ctypes.c_size_t]
+        L.orc_tfrecord_frame.restype = None
+        L.orc_tfrecord_frame.argtypes = [u8p, ctypes.c_uint64, u8p]
+        L.orc_tfrecord_scan.restype = ctypes.c_int64
+        L.orc_tfrecord_scan.argtypes = [u8p, ctypes.c_uint64, u64p, u64p, ctypes.c_int64, ctypes.c_int]
+        L.orc_lzw_decode.restype = ctypes.c_int64
+        L.orc_lzw_decode.argtypes = [u8p, ctypes.c_size_t, u8p, ctypes.c_size_t]
+        L.orc_hdiff_undo.restype = None
+        L.orc_hdiff_undo.argtypes = [u8p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
+        L.orc_png_unfilter.restype = ctypes.c_int
+        L.orc_png_unfilter.argtypes = [u8p, u8p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int]
+        _lib = L
+    return _lib

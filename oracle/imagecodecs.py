@@ -1,0 +1,212 @@
+"""Chip decode: TIFF (LZW / DEFLATE / none) and PNG (oracle; test infrastructure only).
+
+Stands in for the two decode calls of the reference:
+  * ``load_image_rasterio`` ``_img_to_tf_mp.py:43-75`` — ``MemoryFile(bytes).open().read()`` (GDAL ->
+    libtiff / libpng) then ``reshape_as_image`` ``(B,H,W)->(H,W,B)`` ``:69``; ``decode=False`` keeps the file
+    bytes and only reads height/width/count ``:51-53``.
+  * ``_process_image`` ``_img_to_tf_threaded.py:87-121`` — ``tf.image.decode_png`` ``:59``.
+GDAL/TF are not installable; the codecs are restated from the public specs (TIFF 6.0 sections 2, 13, 14;
+PNG sections 5, 9; RFC 1950/1951 via the real ``zlib``).  Chip format written by the reference:
+``_descartes_img_chips.py:781-797`` (GTiff, COMPRESS=LZW, TILED=TRUE -> 256x256 tiles, pixel
+interleaved, predictor 1).  Tests cross-check against libtiff (cv2, Pillow) and libpng (Pillow).
+"""
+import struct
+import zlib
+
+import numpy as np
+
+from . import clib
+
+_TYPE_SIZE = {1: 1, 2: 1, 3: 2, 4: 4, 5: 8, 6: 1, 7: 1, 8: 2, 9: 4, 10: 8, 11: 4, 12: 8, 16: 8}
+_TYPE_FMT = {1: "B", 2: "c", 3: "H", 4: "I", 6: "b", 7: "B", 8: "h", 9: "i", 11: "f", 12: "d", 16: "Q"}
+
+
+class DecodeError(Exception):
+    pass
+
+
+def parse_tiff(blob: bytes) -> dict:
+    """First IFD of a classic TIFF -> dict of the tags the decoder needs."""
+    if len(blob) < 8:
+        raise DecodeError("short TIFF")
+    bo = {b"II": "<", b"MM": ">"}.get(blob[:2])
+    if bo is None:
+        raise DecodeError("not a TIFF")
+    magic, ifd = struct.unpack(bo + "HI", blob[2:8])
+    if magic != 42:
+        raise DecodeError("BigTIFF / unknown magic %d" % magic)
+    (n,) = struct.unpack(bo + "H", blob[ifd:ifd + 2])
+    tags = {}
+    for i in range(n):
+        e = ifd + 2 + 12 * i
+        tag, typ, cnt = struct.unpack(bo + "HHI", blob[e:e + 8])
+        sz = _TYPE_SIZE.get(typ)
+        if sz is None:
+            continue
+        nb = sz * cnt
+        off = e + 8 if nb <= 4 else struct.unpack(bo + "I", blob[e + 8:e + 12])[0]
+        raw = blob[off:off + nb]
+        if len(raw) < nb:
+            raise DecodeError("tag %d data out of range" % tag)
+        if typ == 5 or typ == 10:
+            vals = struct.unpack(bo + ("II" if typ == 5 else "ii") * cnt, raw)
+        elif typ == 2:
+            vals = raw
+        else:
+            vals = struct.unpack(bo + _TYPE_FMT[typ] * cnt, raw)
+        tags[tag] = vals
+    g = lambda t, d=None: tags[t][0] if t in tags else d
+    info = dict(
+        byteorder=bo, width=g(256), height=g(257), compression=g(259, 1), photometric=g(262, 1),
+        spp=g(277, 1), planar=g(284, 1), predictor=g(317, 1), fill_order=g(266, 1),
+        bps=tags.get(258, (1,)), sample_format=tags.get(339, (1,)), tags=tags)
+    if info["width"] is None or info["height"] is None:
+        raise DecodeError("missing size tags")
+    if 322 in tags:
+        info.update(tiled=True, block_w=g(322), block_h=g(323), offsets=tags[324], counts=tags[325])
+    else:
+        rps = min(g(278, info["height"]), info["height"])
+        info.update(tiled=False, block_w=info["width"], block_h=rps, offsets=tags[273], counts=tags[279])
+    if len(set(info["bps"])) != 1 or len(set(info["sample_format"])) != 1:
+        raise DecodeError("mixed per-band sample types")
+    info["nodata"] = tags[42113].rstrip(b"\0").decode() if 42113 in tags else None
+    return info
+
+
+def _dtype(bps, fmt):
+    try:
+        return {(8, 1): np.uint8, (8, 2): np.int8, (16, 1): np.uint16, (16, 2): np.int16, (32, 1): np.uint32,
+                (32, 2): np.int32, (32, 3): np.float32, (64, 3): np.float64}[(bps, fmt)]
+    except KeyError:
+        raise DecodeError("unsupported sample type bps=%d fmt=%d" % (bps, fmt))
+
+
+def lzw_decode(src: bytes, nbytes: int) -> bytes:
+    out = np.zeros(nbytes, dtype=np.uint8)
+    s = np.frombuffer(src, dtype=np.uint8)
+    n = clib().orc_lzw_decode(s.ctypes.data, s.size, out.ctypes.data, nbytes)
+    if n != nbytes:
+        raise DecodeError("LZW stream produced %d of %d bytes" % (n, nbytes))
+    return out.tobytes()
+
+
+def decode_tiff(blob: bytes) -> np.ndarray:
+    t = parse_tiff(blob)
+    W, H, spp = t["width"], t["height"], t["spp"]
+    bps, fmt = t["bps"][0], t["sample_format"][0]
+    dt = np.dtype(_dtype(bps, fmt))
+    bpsamp = dt.itemsize
+    if t["fill_order"] != 1:
+        raise DecodeError("FillOrder 2 unsupported")
+    if t["predictor"] not in (1, 2):
+        raise DecodeError("predictor %d unsupported" % t["predictor"])
+    planes = spp if t["planar"] == 2 else 1
+    spb = 1 if t["planar"] == 2 else spp            # samples per pixel inside one block
+    bw, bh = t["block_w"], t["block_h"]
+    across = (W + bw - 1) // bw
+    down = (H + bh - 1) // bh
+    if len(t["offsets"]) < across * down * planes:
+        raise DecodeError("too few blocks")
+    out = np.zeros((H, W, spp), dtype=dt)
+    for p in range(planes):
+        for by in range(down):
+            for bx in range(across):
+                k = (p * down + by) * across + bx
+                rows = bh if t["tiled"] else min(bh, H - by * bh)
+                nbytes = rows * bw * spb * bpsamp
+                raw = blob[t["offsets"][k]:t["offsets"][k] + t["counts"][k]]
+                if len(raw) != t["counts"][k]:
+                    raise DecodeError("block %d out of file" % k)
+                c = t["compression"]
+                if c == 5:
+                    dec = lzw_decode(raw, nbytes)
+                elif c in (8, 32946):
+                    try:
+                        dec = zlib.decompress(raw)
+                    except zlib.error as e:
+                        raise DecodeError(str(e))
+                    if len(dec) < nbytes:
+                        raise DecodeError("short deflate block")
+                    dec = dec[:nbytes]
+                elif c == 1:
+                    if len(raw) < nbytes:
+                        raise DecodeError("short raw block")
+                    dec = raw[:nbytes]
+                else:
+                    raise DecodeError("compression %d unsupported" % c)
+                arr = np.frombuffer(dec, dtype=dt.newbyteorder(t["byteorder"])).astype(dt).reshape(rows, bw * spb).copy()
+                if t["predictor"] == 2:
+                    if dt.kind == "f":
+                        raise DecodeError("predictor 2 on float")
+                    clib().orc_hdiff_undo(arr.ctypes.data, rows, bw * spb, spb, bpsamp)
+                arr = arr.reshape(rows, bw, spb)
+                y0, x0 = by * bh, bx * bw
+                hh, ww = min(rows, H - y0), min(bw, W - x0)
+                if t["planar"] == 2:
+                    out[y0:y0 + hh, x0:x0 + ww, p] = arr[:hh, :ww, 0]
+                else:
+                    out[y0:y0 + hh, x0:x0 + ww, :] = arr[:hh, :ww, :]
+    return out
+
+
+_PNG_SIG = b"\x89PNG\r\n\x1a\n"
+
+
+def parse_png(blob: bytes) -> dict:
+    if blob[:8] != _PNG_SIG:
+        raise DecodeError("not a PNG")
+    p, idat, ihdr = 8, [], None
+    while p + 8 <= len(blob):
+        (n,) = struct.unpack(">I", blob[p:p + 4])
+        typ = blob[p + 4:p + 8]
+        body = blob[p + 8:p + 8 + n]
+        if len(body) != n:
+            raise DecodeError("truncated chunk")
+        if typ == b"IHDR":
+            ihdr = struct.unpack(">IIBBBBB", body)
+        elif typ == b"IDAT":
+            idat.append(body)
+        elif typ == b"IEND":
+            break
+        p += 12 + n
+    if ihdr is None:
+        raise DecodeError("no IHDR")
+    w, h, depth, ctype, comp, flt, inter = ihdr
+    return dict(width=w, height=h, depth=depth, color_type=ctype, interlace=inter, idat=b"".join(idat))
+
+
+def decode_png(blob: bytes) -> np.ndarray:
+    """8-bit grey / RGB / grey+alpha / RGBA, non-interlaced -> (H,W,C) uint8 (decode_png with channels=0)."""
+    t = parse_png(blob)
+    ch = {0: 1, 2: 3, 4: 2, 6: 4}.get(t["color_type"])
+    if t["depth"] != 8 or ch is None or t["interlace"]:
+        raise DecodeError("PNG flavour out of scope (depth %d, colour type %d)" % (t["depth"], t["color_type"]))
+    h, rb = t["height"], t["width"] * ch
+    try:
+        raw = zlib.decompress(t["idat"])
+    except zlib.error as e:
+        raise DecodeError(str(e))
+    if len(raw) < h * (rb + 1):
+        raise DecodeError("short PNG stream")
+    src = np.frombuffer(raw, dtype=np.uint8, count=h * (rb + 1))
+    dst = np.zeros(h * rb, dtype=np.uint8)
+    if clib().orc_png_unfilter(src.ctypes.data, dst.ctypes.data, h, rb, ch) != 0:
+        raise DecodeError("bad PNG filter type")
+    return dst.reshape(h, t["width"], ch)
+
+
+def decode_image(blob: bytes) -> np.ndarray:
+    if blob[:8] == _PNG_SIG:
+        return decode_png(blob)
+    if blob[:2] in (b"II", b"MM"):
+        return decode_tiff(blob)
+    raise DecodeError("unknown image format")
+
+
+def image_shape(blob: bytes):
+    """(height, width, bands) from the header only — load_image_rasterio(decode=False), :51-53."""
+    if blob[:8] == _PNG_SIG:
+        t = parse_png(blob)
+        return t["height"], t["width"], {0: 1, 2: 3, 4: 2, 6: 4}[t["color_type"]]
+    t = parse_tiff(blob)
+    return t["height"], t["width"], t["spp"]

@@ -1,0 +1,90 @@
+"""Whole-job restatements used as the CPU baseline (oracle; test infrastructure only).
+
+``images_to_tfrecords``  = ``process_dataset_mp`` ``_img_to_tf_mp.py:233-275`` with the worker loop
+``_process_image_files_mp_worker :78-157`` (per shard: writer, per chip: two ``load_image_rasterio``
+calls ``:128-131``, key assert ``:132``, skip on exception ``:133-136``, ``convert_to_example`` ``:138``,
+``writer.write(SerializeToString())`` ``:141``) and the same joblib fan-out ``:180``.
+``parse_shards``         = ``TFRecordDataset(...).map(parse_fn, 8)`` ``parse_tfrecords.ipynb`` cells 4, 30
+followed by the north-star cast / normalise / one-hot.
+"""
+import os
+
+import numpy as np
+
+from . import example_proto, imagecodecs, normalise, partition, tfrecord
+
+
+def load_image(path, parse_dltile_filename=True, decode=True):
+    """load_image_rasterio (_img_to_tf_mp.py:22-75) -> (data, h, w, bands, tile_key)."""
+    with open(path, "rb") as f:
+        blob = f.read()
+    if decode:
+        arr = imagecodecs.decode_image(blob)
+        h, w, b = arr.shape
+        data = arr
+    else:
+        h, w, b = imagecodecs.image_shape(blob)
+        data = blob
+    return data, h, w, b, partition.tile_key(path, parse_dltile_filename)
+
+
+def build_record(img_path, lbl_path, dltile_from_filename=True, store_as_array=True):
+    ib, ih, iw, ibands, ikey = load_image(img_path, dltile_from_filename, store_as_array)
+    lb, lh, lw, _, lkey = load_image(lbl_path, dltile_from_filename, store_as_array)
+    assert ikey == lkey
+    ex = example_proto.convert_to_example(ib, lb, ih, iw, ibands, lh, lw, ikey)
+    return ex.SerializeToString(deterministic=True)
+
+
+def _worker(proc_index, ranges, name, img_files, lbl_files, out_dir, num_shards, dltile, store_as_array, quiet=True):
+    num_proc = len(ranges)
+    assert not num_shards % num_proc
+    per = num_shards // num_proc
+    sr = np.linspace(ranges[proc_index][0], ranges[proc_index][1], per + 1).astype(int)
+    written = 0
+    for s in range(per):
+        shard = proc_index * per + s
+        path = os.path.join(out_dir, partition.shard_name(name, shard, num_shards))
+        os.makedirs(out_dir, exist_ok=True)
+        with tfrecord.TFRecordWriter(path) as w:
+            for i in range(int(sr[s]), int(sr[s + 1])):
+                try:
+                    rec = build_record(img_files[i], lbl_files[i], dltile, store_as_array)
+                except Exception as e:                      # :133-136
+                    if not quiet:
+                        print(e)
+                        print("SKIPPED: Unexpected eror while decoding %s." % img_files[i])
+                    continue
+                w.write(rec)
+                written += 1
+    return written
+
+
+def images_to_tfrecords(name, directory, out_directory, num_shards, num_proc=None, dltile_from_filename=True,
+                        file_ext="tif", store_as_array=True, n_jobs=None, limit=None):
+    """n_jobs = OS processes actually used (the reference uses num_proc of them)."""
+    from joblib import Parallel, delayed
+    if not num_proc:
+        num_proc = num_shards
+    imgs, lbls = partition.find_image_files(directory, file_ext)
+    if limit is not None:
+        imgs, lbls = imgs[:limit], lbls[:limit]
+    ranges = partition.worker_ranges(len(imgs), num_proc)
+    args = [(p, ranges, name, imgs, lbls, out_directory, num_shards, dltile_from_filename, store_as_array)
+            for p in range(len(ranges))]
+    res = Parallel(n_jobs=n_jobs or num_proc)(__import__("joblib").delayed(_worker)(*a) for a in args)
+    return sum(res)
+
+
+def parse_records_norm_onehot(records, mean, std, num_classes):
+    """records: list of Example bytes (uint8 arrays stored as BytesList) -> (N,H,W,C) f32, (N,H,W,K) f32."""
+    imgs, hots = [], []
+    for r in records:
+        img, tgt, _ = example_proto.parse_8bit_array_proto(r)
+        imgs.append(normalise.normalise(img, mean, std))
+        hots.append(normalise.one_hot(tgt, num_classes))
+    return np.stack(imgs), np.stack(hots)
+
+
+def parse_shard_bytes(buf, mean, std, num_classes, verify=True):
+    return parse_records_norm_onehot(tfrecord.read_records(buf, verify), mean, std, num_classes)
