@@ -1,0 +1,232 @@
+"""TFRecord Example builder and parsers — B200 drop-in for the reference module of the same name.
+
+Mirrors ``dl_segmentation_utils/_tfrecord_image_translation.py``: same function names, argument
+meaning and (image, target, identifier) return convention; ``tf.Tensor`` results become CUDA
+``torch.Tensor`` (DLPack-exportable).  All byte movement and arithmetic (protobuf field location,
+payload scatter, CRC, widening to float32, decode) runs in libb2chips.so; this file only marshals.
+
+Reference behaviour kept (file:line in the reference):
+  * BytesList iff both payloads are ``bytes`` / uint8 arrays, otherwise FloatList(float32) for BOTH
+    (``:160-197``); eight keys (``:199-209``); identifier utf-8 bytes (``:208``).
+  * ``parse_8bit_array_proto`` asserts payload length == h*w*c (``:307-308,313``);
+    ``parse_higher_dtype_array_proto`` returns float32 (``:403-407``); the rgb / gdal parsers return the
+    target as (H,W,1) and ``..._wrapped`` casts both to float32 (``:328-329``).
+  * A missing or mistyped key raises (TF: InvalidArgumentError from parse_single_example, ``:249,394``).
+Serialisation order is the deterministic (sorted-key) one — see DESIGN.md.
+"""
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import B2Error
+
+FixedLenFeature = namedtuple("FixedLenFeature", ["shape", "dtype"])
+FixedLenSequenceFeature = namedtuple("FixedLenSequenceFeature", ["shape", "dtype", "allow_missing"])
+
+# plain-Python descriptions of the two parse templates (reference :216-225 and :231-241)
+featuretemplate_bytestring_imagechip = {
+    "image/image_data": FixedLenFeature([], "string"),
+    "image/height": FixedLenFeature([], "int64"),
+    "image/width": FixedLenFeature([], "int64"),
+    "image/channels": FixedLenFeature([], "int64"),
+    "target/target_data": FixedLenFeature([], "string"),
+    "target/height": FixedLenFeature([], "int64"),
+    "target/width": FixedLenFeature([], "int64"),
+    "identifier": FixedLenFeature([], "string"),
+}
+featuretemplate_ndarray_imagechip = {
+    "image/image_data": FixedLenSequenceFeature([], "float32", True),
+    "image/height": FixedLenFeature([], "int64"),
+    "image/width": FixedLenFeature([], "int64"),
+    "image/channels": FixedLenFeature([], "int64"),
+    "target/target_data": FixedLenSequenceFeature([], "float32", True),
+    "target/height": FixedLenFeature([], "int64"),
+    "target/width": FixedLenFeature([], "int64"),
+    "identifier": FixedLenFeature([], "string"),
+}
+
+
+class InvalidArgumentError(B2Error):
+    """parse_single_example could not satisfy the template (missing / mistyped / multi-valued key)."""
+
+
+def _is_uint8(x):
+    if isinstance(x, np.ndarray):
+        return x.dtype == np.uint8
+    if isinstance(x, torch.Tensor):
+        return x.dtype == torch.uint8
+    return False
+
+
+def _is_array(x):
+    return isinstance(x, (np.ndarray, torch.Tensor))
+
+
+class Example:
+    """What convert_to_example returns: holds the payloads, serialises on the GPU on demand."""
+
+    def __init__(self, img_data, target_data, dims, identifier, as_bytes):
+        self.img_data, self.target_data = img_data, target_data
+        self.dims, self.identifier, self.as_bytes = dims, identifier, as_bytes
+
+    def build_item(self, device=None):
+        h, w, c, th, tw = self.dims
+        img = ops.to_device(self.img_data, device).reshape(-1)
+        tgt = ops.to_device(self.target_data, device).reshape(-1)
+        if self.as_bytes:                       # raw bytes or uint8 array: stored verbatim
+            img, tgt = img.view(torch.uint8), tgt.view(torch.uint8)
+        return dict(img=img, tgt=tgt, kind=1 if self.as_bytes else 2, h=h, w=w, c=c, th=th, tw=tw,
+                    identifier=self.identifier)
+
+    def SerializeToString(self, deterministic=True, device=None):
+        out, offs, total = ops.build_records([self.build_item(device)], device)
+        return bytes(out[12:total - 4].cpu().numpy())
+
+
+def convert_to_example(img_data, target_data, img_h, img_w, img_b, target_h, target_w, identifier):
+    """Wrap image + target (+ dims + identifier) as a tf.train.Example (reference :55-211)."""
+    image_is_bytes = isinstance(img_data, bytes) or (_is_array(img_data) and _is_uint8(img_data))
+    target_is_bytes = isinstance(target_data, bytes) or (_is_array(target_data) and _is_uint8(target_data) and image_is_bytes)
+    as_bytes = image_is_bytes and target_is_bytes
+    if not as_bytes:
+        for name, d in (("img_data", img_data), ("target_data", target_data)):
+            if isinstance(d, bytes):
+                # reference: tf.train.FloatList(value=[<bytes>]) raises TypeError
+                raise TypeError("%s is bytes but the pair is not storable as BytesList (reference :192-197)" % name)
+    ident = identifier if isinstance(identifier, bytes) else str(identifier).encode("utf-8")
+    return Example(img_data, target_data, (int(img_h), int(img_w), int(img_b), int(target_h), int(target_w)), ident, as_bytes)
+
+
+# ------------------------------------------------------------------------------------------- parsing
+def _open_single(example_proto, device=None):
+    """One serialized Example (bytes / uint8 tensor) -> ShardIndex with a single un-framed record."""
+    ctx = ops.get_ctx(device)
+    buf = ops.to_device(example_proto, ctx.device)
+    n = int(buf.numel())
+    rec_off = torch.zeros((1,), dtype=torch.int64, device=ctx.device)
+    rec_len = torch.full((1,), n, dtype=torch.int64, device=ctx.device)
+    import ctypes
+
+    from . import _lib
+    index_dev = torch.empty((ctypes.sizeof(_lib.ExampleIndex),), dtype=torch.uint8, device=ctx.device)
+    _lib.check(_lib.lib().b2_tfrecord_index(ctx.handle, _lib.ptr(buf), _lib.ptr(rec_off), _lib.ptr(rec_len), 1,
+                                            _lib.ptr(index_dev), ctx.stream()))
+    index = index_dev.cpu().numpy().view(np.dtype(_lib.EXAMPLE_INDEX_DTYPE))
+    return ops.ShardIndex(buf, n, 1, rec_off, rec_len, index_dev, index, np.array([n], dtype=np.uint64))
+
+
+def check_index(idx, want_kind):
+    """Raise what parse_single_example would for this template."""
+    bad = np.nonzero(idx["status"] != 0)[0]
+    if len(bad):
+        raise InvalidArgumentError("record %d: %s" % (bad[0], "malformed Example" if idx["status"][bad[0]] == 1
+                                                     else "a required feature is missing, mistyped or multi-valued"))
+    wrong = np.nonzero((idx["img_kind"] != want_kind) | (idx["tgt_kind"] != want_kind))[0]
+    if len(wrong):
+        raise InvalidArgumentError("record %d: image/target data are not stored as %s" %
+                                   (wrong[0], "BytesList" if want_kind == 1 else "FloatList"))
+
+
+def parse_records_raw(si, want_kind, verify_crc, first=0, count=None):
+    """Shared body of the array parsers over records [first, first+count) of a ShardIndex.
+
+    Returns (img_buf, tgt_buf, idx): payload bytes as stored, one row per record."""
+    count = si.n - first if count is None else count
+    idx = si.index[first:first + count]
+    check_index(idx, want_kind)
+    img_buf, tgt_buf, status = ops.parse_shard(si, "raw", verify_crc=verify_crc, first=first, count=count)
+    st = status.cpu().numpy()
+    if (st == 1).any():
+        raise ops.DataLossError("corrupted record #%d (data CRC mismatch)" % (first + int(np.nonzero(st == 1)[0][0])))
+    if (st != 0).any():
+        raise B2Error("parse failed with status %d" % int(st[st != 0][0]))
+    return img_buf, tgt_buf, idx
+
+
+def _identifier(si, r):
+    o, l = int(si.index[r]["id_off"]), int(si.index[r]["id_len"])
+    return bytes(si.shard[o:o + l].cpu().numpy())
+
+
+def rows_to_arrays_8bit(img_buf, tgt_buf, idx):
+    out = []
+    for k in range(len(idx)):
+        h, w, c = int(idx["height"][k]), int(idx["width"][k]), int(idx["channels"][k])
+        th, tw = int(idx["tgt_height"][k]), int(idx["tgt_width"][k])
+        il, tl = int(idx["img_len"][k]), int(idx["tgt_len"][k])
+        assert il == h * w * c, "Decoded shape is %r - does not match" % ((il,),)      # reference :307-308
+        assert tl == th * tw                                                             # reference :313
+        out.append((img_buf[k, :il].view(h, w, c), tgt_buf[k, :tl].view(th, tw)))
+    return out
+
+
+def rows_to_arrays_f32(img_buf, tgt_buf, idx):
+    out = []
+    for k in range(len(idx)):
+        h, w, c = int(idx["height"][k]), int(idx["width"][k]), int(idx["channels"][k])
+        th, tw = int(idx["tgt_height"][k]), int(idx["tgt_width"][k])
+        il, tl = int(idx["img_len"][k]), int(idx["tgt_len"][k])
+        if il != 4 * h * w * c or tl != 4 * th * tw:
+            raise InvalidArgumentError("Input to reshape is a tensor with %d values, but the requested shape has %d"
+                                       % (il // 4, h * w * c))
+        out.append((img_buf[k, :il].view(torch.float32).view(h, w, c), tgt_buf[k, :tl].view(torch.float32).view(th, tw)))
+    return out
+
+
+def _parse_byteslist_proto(example_proto, device=None):
+    """(img_bytes, (h,w,c), target_bytes, (th,tw), identifier) with the blobs as uint8 CUDA tensors (reference :244-266)."""
+    si = _open_single(example_proto, device)
+    img_buf, tgt_buf, idx = parse_records_raw(si, 1, verify_crc=False)
+    r = idx[0]
+    return (img_buf[0, :int(r["img_len"])], (int(r["height"]), int(r["width"]), int(r["channels"])),
+            tgt_buf[0, :int(r["tgt_len"])], (int(r["tgt_height"]), int(r["tgt_width"])), _identifier(si, 0))
+
+
+def parse_8bit_array_proto(example_proto, device=None):
+    """8-bit arrays stored as bytes strings -> (uint8 (H,W,C), uint8 (H,W), identifier)  (reference :296-316)."""
+    si = _open_single(example_proto, device)
+    img_buf, tgt_buf, idx = parse_records_raw(si, 1, verify_crc=False)
+    (img, tgt), = rows_to_arrays_8bit(img_buf, tgt_buf, idx)
+    return img, tgt, _identifier(si, 0)
+
+
+def parse_higher_dtype_array_proto(example_proto, device=None):
+    """FloatList arrays -> (float32 (H,W,C), float32 (H,W), identifier)  (reference :389-415)."""
+    si = _open_single(example_proto, device)
+    img_buf, tgt_buf, idx = parse_records_raw(si, 2, verify_crc=False)
+    (img, tgt), = rows_to_arrays_f32(img_buf, tgt_buf, idx)
+    return img, tgt, _identifier(si, 0)
+
+
+def _decode_pair(img_blob, tgt_blob, device=None):
+    from . import _codec
+    (img, tgt), status = _codec.decode_blobs([img_blob, tgt_blob], device=device)
+    for s, name in zip(status, ("image", "target")):
+        if s != 0:
+            raise InvalidArgumentError("could not decode %s data (codec status %d)" % (name, s))
+    return img, tgt
+
+
+def parse_encoded_rgb_img_proto(example_proto, device=None):
+    """PNG-encoded payloads -> (uint8 (H,W,3), uint8 (H,W,1), identifier)  (reference :269-293, tf.io.decode_image)."""
+    ib, _, tb, _, ident = _parse_byteslist_proto(example_proto, device)
+    img, tgt = _decode_pair(ib, tb, device)
+    return img, tgt, ident
+
+
+def parse_encoded_gdal_proto_eager(example_proto, device=None):
+    """GDAL-readable payloads (GeoTIFF LZW/DEFLATE, PNG) -> native dtype (H,W,B), (H,W,1)  (reference :349-386)."""
+    ib, ishp, tb, tshp, ident = _parse_byteslist_proto(example_proto, device)
+    img, tgt = _decode_pair(ib, tb, device)
+    assert tuple(img.shape) == tuple(ishp)                                              # reference :377
+    assert tgt.shape[0] == tshp[0] and tgt.shape[1] == tshp[1]                          # reference :383-384
+    return img, tgt, ident
+
+
+def parse_encoded_gdal_proto_wrapped(example_proto, device=None):
+    """As _eager but always float32 (reference :319-346)."""
+    from . import _codec
+    img, tgt, ident = parse_encoded_gdal_proto_eager(example_proto, device)
+    return _codec.to_float32(img), _codec.to_float32(tgt), ident

@@ -1,0 +1,343 @@
+// composite.cu — K3: per-pixel compositors over a (T,H,W,B) time stack.
+//
+//   K3a  masked median            replaces np.ma.median(np.ma.masked_where(...), axis=0)
+//                                 (_descartes_img_chips.py:562-567)
+//   K3b  nearest-date mosaic      replaces filter + stable descending sort + SceneCollection.mosaic
+//                                 (_descartes_img_chips.py:461-469, 603-626)
+//
+// Both are pure streaming kernels bounded by HBM bandwidth: every stack element is read exactly once
+// (K3a) or at most once (K3b), straight from global memory with fully coalesced vector loads — there is
+// no reuse, so no shared-memory staging.
+#include <math.h>
+
+#include "common.cuh"
+#include "median_net.inc"
+
+namespace b2 {
+
+// ------------------------------------------------------------------------------------------------ K3a
+//
+// A thread owns NV packed u16x2 registers = 2*NV consecutive bands of ONE pixel and keeps the whole
+// time series in registers (P slots, P = T rounded up to a power of two).  Invalid entries (cloud,
+// nodata, or padding slots t >= T) are replaced by sentinels, alternating 0xFFFF, 0x0000, 0xFFFF ...
+// per (pixel, band).  With m invalid entries that puts floor(m/2) zeros below and ceil(m/2) 0xFFFFs
+// above the n = P - m valid values, so the valid values occupy ranks [floor(m/2), floor(m/2)+n) and their
+// middle element(s) always sit at ranks P/2-1 (n odd) or P/2-1 and P/2 (n even).  Ties between a
+// sentinel and a genuine 0 / 0xFFFF are harmless because equal keys are interchangeable.  A pruned
+// selection network (median_net.inc) then extracts just those two ranks: no sort, no dynamic indexing.
+//
+// kNodata: per-(t,pixel,band) mask in addition to the per-(t,pixel) validity byte.
+template <int P, int NV, bool kNodata>
+__global__ void __launch_bounds__(256)
+median_kernel(const uint16_t* __restrict__ stack, const uint8_t* __restrict__ valid,
+              const uint8_t* __restrict__ nodata, int T, uint64_t hw, int B, uint64_t n_groups,
+              double* __restrict__ out, uint8_t* __restrict__ out_mask) {
+    constexpr int VEC = 2 * NV;  // u16 elements per thread
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const uint64_t e0 = g * VEC;            // first element (pixel*B + band) of this thread
+    const uint64_t pix = e0 / (uint64_t)B;
+    const uint64_t plane = hw * (uint64_t)B;  // elements per scene
+
+    uint32_t v[NV][P];
+    uint32_t tg[NV], cnt[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        tg[k] = 0xFFFFFFFFu;  // next sentinel per half: 0xFFFF first
+        cnt[k] = 0;
+    }
+    // issue every load of the series before touching any of them
+    uint32_t raw[P][NV];
+    uint32_t vb[P];
+    uint32_t nd[P][NV];
+#pragma unroll
+    for (int t = 0; t < P; t++) {
+        if (t < T) {
+            const uint16_t* src = stack + (uint64_t)t * plane + e0;
+            if (NV == 1) {
+                raw[t][0] = __ldg(reinterpret_cast<const uint32_t*>(src));
+            } else if (NV == 2) {
+                uint2 q = __ldg(reinterpret_cast<const uint2*>(src));
+                raw[t][0] = q.x;
+                raw[t][NV > 1 ? 1 : 0] = q.y;
+            } else {
+                uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
+                raw[t][0] = q.x;
+                raw[t][NV > 1 ? 1 : 0] = q.y;
+                raw[t][NV > 2 ? 2 : 0] = q.z;
+                raw[t][NV > 3 ? 3 : 0] = q.w;
+            }
+            vb[t] = __ldg(valid + (uint64_t)t * hw + pix);
+            if (kNodata) {
+                const uint8_t* np_ = nodata + (uint64_t)t * plane + e0;
+#pragma unroll
+                for (int k = 0; k < NV; k++) {
+                    uint32_t two = __ldg(reinterpret_cast<const uint16_t*>(np_ + 2 * k));
+                    nd[t][k] = ((two & 0xFFu) ? 0x0000FFFFu : 0u) | ((two & 0xFF00u) ? 0xFFFF0000u : 0u);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < P; t++) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            uint32_t im;  // per half: 0xFFFF where the entry is invalid
+            uint32_t x;
+            if (t < T) {
+                im = vb[t] ? 0u : 0xFFFFFFFFu;
+                if (kNodata) im |= nd[t][k];
+                x = raw[t][k];
+            } else {
+                im = 0xFFFFFFFFu;
+                x = 0;
+            }
+            v[k][t] = (x & ~im) | (tg[k] & im);
+            tg[k] ^= im;
+            cnt[k] += (~im) & 0x00010001u;
+        }
+    }
+    double res[VEC];
+    uint32_t msk = 0;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        MedNet<P>::run(v[k]);
+        const uint32_t lo = v[k][P / 2 - 1], hi = v[k][P / 2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t n = (cnt[k] >> (16 * h)) & 0xFFFFu;
+            const uint32_t a = (lo >> (16 * h)) & 0xFFFFu, b = (hi >> (16 * h)) & 0xFFFFu;
+            // n odd -> the single middle (rank P/2-1); n even -> mean of the two middles; exact in double
+            const uint32_t sum2 = (n & 1u) ? 2u * a : a + b;
+            res[2 * k + h] = n ? 0.5 * (double)sum2 : 0.0;
+            msk |= (n ? 0u : 1u) << (8 * (2 * k + h));
+        }
+    }
+    double* o = out + e0;
+#pragma unroll
+    for (int k = 0; k < NV; k++) st_cs(reinterpret_cast<double2*>(o) + k, make_double2(res[2 * k], res[2 * k + 1]));
+    if (NV == 1) {
+        *reinterpret_cast<uint16_t*>(out_mask + e0) = (uint16_t)msk;
+    } else if (NV == 2) {
+        *reinterpret_cast<uint32_t*>(out_mask + e0) = msk;
+    }
+}
+
+// NV == 4 needs a 64-bit mask word; kept as a separate tiny overload to keep the kernel above simple.
+// Generic fallback: any T, any B, one thread per (pixel, band); rank-counting selection straight from
+// global memory (two passes over the series, no local arrays).  Used when T > 32 or B is odd.
+__global__ void __launch_bounds__(256)
+median_generic_kernel(const uint16_t* __restrict__ stack, const uint8_t* __restrict__ valid,
+                      const uint8_t* __restrict__ nodata, int T, uint64_t hw, int B, uint64_t n_elems,
+                      double* __restrict__ out, uint8_t* __restrict__ out_mask) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_elems) return;
+    const uint64_t pix = e / (uint64_t)B;
+    const uint64_t plane = hw * (uint64_t)B;
+    int n = 0;
+    for (int t = 0; t < T; t++) {
+        bool ok = valid[(uint64_t)t * hw + pix] != 0;
+        if (nodata) ok = ok && nodata[(uint64_t)t * plane + e] == 0;
+        n += ok;
+    }
+    if (n == 0) {
+        out[e] = 0.0;
+        out_mask[e] = 1;
+        return;
+    }
+    const int r_lo = (n - 1) / 2, r_hi = n / 2;
+    uint32_t a = 0, b = 0;
+    for (int t = 0; t < T; t++) {
+        bool ok = valid[(uint64_t)t * hw + pix] != 0;
+        if (nodata) ok = ok && nodata[(uint64_t)t * plane + e] == 0;
+        if (!ok) continue;
+        const uint32_t x = stack[(uint64_t)t * plane + e];
+        int less = 0, leq = 0;  // rank interval of x among the valid values, ties broken by index
+        for (int u = 0; u < T; u++) {
+            bool ok2 = valid[(uint64_t)u * hw + pix] != 0;
+            if (nodata) ok2 = ok2 && nodata[(uint64_t)u * plane + e] == 0;
+            if (!ok2) continue;
+            const uint32_t y = stack[(uint64_t)u * plane + e];
+            less += (y < x) || (y == x && u < t);
+            leq += 1;
+        }
+        (void)leq;
+        if (less == r_lo) a = x;
+        if (less == r_hi) b = x;
+    }
+    out[e] = 0.5 * (double)(a + b);
+    out_mask[e] = 0;
+}
+
+template <int P, int NV>
+static void launch_median(const uint16_t* stack, const uint8_t* valid, const uint8_t* nodata, int T, uint64_t hw,
+                          int B, double* out, uint8_t* mask, cudaStream_t s) {
+    const uint64_t n_groups = hw * (uint64_t)B / (2 * NV);
+    const unsigned grid = (unsigned)((n_groups + 255) / 256);
+    if (nodata)
+        median_kernel<P, NV, true><<<grid, 256, 0, s>>>(stack, valid, nodata, T, hw, B, n_groups, out, mask);
+    else
+        median_kernel<P, NV, false><<<grid, 256, 0, s>>>(stack, valid, nodata, T, hw, B, n_groups, out, mask);
+}
+
+template <int NV>
+static bool dispatch_median(int P, const uint16_t* stack, const uint8_t* valid, const uint8_t* nodata, int T,
+                            uint64_t hw, int B, double* out, uint8_t* mask, cudaStream_t s) {
+    switch (P) {
+        case 2: launch_median<2, NV>(stack, valid, nodata, T, hw, B, out, mask, s); return true;
+        case 4: launch_median<4, NV>(stack, valid, nodata, T, hw, B, out, mask, s); return true;
+        case 8: launch_median<8, NV>(stack, valid, nodata, T, hw, B, out, mask, s); return true;
+        case 16: launch_median<16, NV>(stack, valid, nodata, T, hw, B, out, mask, s); return true;
+        case 32: launch_median<32, NV>(stack, valid, nodata, T, hw, B, out, mask, s); return true;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------ K3b
+//
+// One CTA column per chip (blockIdx.y).  Prologue: the first T threads evaluate the search filter and
+// rank the eligible scenes by (|day - ref| ascending, index descending) — the reverse of the painting
+// order, so order[0] is the scene painted last, i.e. the one that wins wherever it is valid.
+// Main loop: one thread per pixel walks `order`, probing one validity byte per scene (coalesced across
+// the warp) and stops at the first valid scene; only that scene's pixel is read.  Filtered-out scenes
+// are never touched, so the kernel moves far fewer bytes than the dense T-deep definition.
+template <int PB>  // bytes per pixel (all bands), 0 = runtime
+__global__ void __launch_bounds__(256)
+mosaic_kernel(const void* const* __restrict__ stacks, const uint8_t* const* __restrict__ valids,
+              const int32_t* __restrict__ scene_day, const float* __restrict__ scene_cf, int32_t ref_day,
+              int32_t min_day, int32_t max_day, float max_cf, int T, uint32_t hw, int pb_runtime,
+              uint8_t* __restrict__ out, uint8_t* __restrict__ out_mask, int16_t* __restrict__ src_index,
+              int32_t* __restrict__ n_eligible) {
+    extern __shared__ int32_t sm[];  // key[T], order[T], n
+    int32_t* key = sm;
+    int32_t* order = sm + T;
+    __shared__ int32_t n_el;
+    const int chip = blockIdx.y;
+    const int pb = PB ? PB : pb_runtime;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const int32_t d = scene_day[(size_t)chip * T + t];
+        const float cf = scene_cf[(size_t)chip * T + t];
+        bool ok = d >= min_day && d < max_day;
+        if (!isnan(max_cf)) ok = ok && (cf < max_cf);
+        const int64_t diff = (int64_t)d - (int64_t)ref_day;
+        const int64_t ad = diff < 0 ? -diff : diff;
+        key[t] = ok ? (int32_t)(ad > 0x7FFFFFFE ? 0x7FFFFFFE : ad) : -1;
+    }
+    if (threadIdx.x == 0) n_el = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const int32_t k = key[t];
+        if (k >= 0) {
+            int r = 0;
+            for (int u = 0; u < T; u++) {
+                const int32_t ku = key[u];
+                r += (ku >= 0) && (ku < k || (ku == k && u > t));
+            }
+            order[r] = t;
+            atomicAdd(&n_el, 1);
+        }
+    }
+    __syncthreads();
+    const int ne = n_el;
+    if (n_eligible && blockIdx.x == 0 && threadIdx.x == 0) n_eligible[chip] = ne;
+    const uint8_t* vchip = valids[chip];
+    const uint8_t* schip = static_cast<const uint8_t*>(stacks[chip]);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
+        int sel = -1;
+        for (int k = 0; k < ne; k++) {
+            const int t = order[k];
+            if (__ldg(vchip + (size_t)t * hw + p)) {
+                sel = t;
+                break;
+            }
+        }
+        uint8_t* o = out + ((size_t)chip * hw + p) * pb;
+        const uint8_t* s = schip + ((size_t)(sel < 0 ? 0 : sel) * hw + p) * pb;
+        if (PB == 16) {
+            uint4 v = sel < 0 ? make_uint4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uint4*>(s));
+            *reinterpret_cast<uint4*>(o) = v;
+        } else if (PB == 8) {
+            uint2 v = sel < 0 ? make_uint2(0, 0) : __ldg(reinterpret_cast<const uint2*>(s));
+            *reinterpret_cast<uint2*>(o) = v;
+        } else if (PB == 4) {
+            uint32_t v = sel < 0 ? 0u : __ldg(reinterpret_cast<const uint32_t*>(s));
+            *reinterpret_cast<uint32_t*>(o) = v;
+        } else if (PB == 2) {
+            uint16_t v = sel < 0 ? (uint16_t)0 : __ldg(reinterpret_cast<const uint16_t*>(s));
+            *reinterpret_cast<uint16_t*>(o) = v;
+        } else {
+            for (int i = 0; i < pb; i++) o[i] = sel < 0 ? (uint8_t)0 : s[i];
+        }
+        out_mask[(size_t)chip * hw + p] = sel < 0;
+        if (src_index) src_index[(size_t)chip * hw + p] = (int16_t)sel;
+    }
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_median_composite_u16(b2_ctx* ctx, const uint16_t* stack, const uint8_t* valid, const uint8_t* nodata,
+                                       int T, int H, int W, int B, double* out, uint8_t* out_mask, b2_stream stream) {
+    B2_REQUIRE(ctx && stack && valid && out && out_mask, "b2_median_composite_u16: NULL argument");
+    B2_REQUIRE(T >= 1 && H >= 1 && W >= 1 && B >= 1, "b2_median_composite_u16: T,H,W,B must be positive");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint64_t hw = (uint64_t)H * W;
+    int P = 2;
+    while (P < T) P <<= 1;
+    const bool aligned = (reinterpret_cast<uintptr_t>(stack) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
+                         (reinterpret_cast<uintptr_t>(out_mask) % 4 == 0) &&
+                         (!nodata || reinterpret_cast<uintptr_t>(nodata) % 4 == 0);
+    bool done = false;
+    if (P <= 32 && aligned) {
+        // 4 bands per thread (64-bit loads) when the band count allows, else 2
+        if (B % 4 == 0 && P <= 16)
+            done = dispatch_median<2>(P, stack, valid, nodata, T, hw, B, out, out_mask, s);
+        else if (B % 2 == 0)
+            done = dispatch_median<1>(P, stack, valid, nodata, T, hw, B, out, out_mask, s);
+    }
+    if (!done) {
+        const uint64_t n = hw * (uint64_t)B;
+        median_generic_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(stack, valid, nodata, T, hw, B, n, out, out_mask);
+    }
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b2_nearest_date_mosaic(b2_ctx* ctx, const void* const* stacks, const uint8_t* const* valids,
+                                      const int32_t* scene_day, const float* scene_cf, int32_t ref_day,
+                                      int32_t min_day, int32_t max_day, float max_cf, int n_chips, int T, int H,
+                                      int W, int B, int elem_bytes, void* out, uint8_t* out_mask,
+                                      int16_t* src_index, int32_t* n_eligible, b2_stream stream) {
+    B2_REQUIRE(ctx && stacks && valids && scene_day && scene_cf && out && out_mask, "b2_nearest_date_mosaic: NULL argument");
+    B2_REQUIRE(n_chips >= 1 && n_chips <= 65535, "b2_nearest_date_mosaic: n_chips must be in [1,65535] per call");
+    B2_REQUIRE(T >= 1 && T <= 4096 && H >= 1 && W >= 1 && B >= 1, "b2_nearest_date_mosaic: bad T/H/W/B");
+    B2_REQUIRE(elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4 || elem_bytes == 8,
+               "b2_nearest_date_mosaic: elem_bytes must be 1, 2, 4 or 8");
+    B2_REQUIRE((uint64_t)H * W < (1ull << 31), "b2_nearest_date_mosaic: chip too large");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint32_t hw = (uint32_t)H * W;
+    const int pb = B * elem_bytes;
+    // enough CTAs per chip to fill the machine when n_chips is small, one per 1024 pixels at most
+    unsigned per_chip = (hw + 1023) / 1024;
+    const unsigned want = (unsigned)((ctx->sm_count * 8 + n_chips - 1) / n_chips);
+    if (per_chip > want) per_chip = want > 0 ? want : 1;
+    dim3 grid(per_chip, n_chips);
+    const size_t smem = 2 * (size_t)T * sizeof(int32_t);
+    const bool al = reinterpret_cast<uintptr_t>(out) % 16 == 0;  // per-chip stack alignment is the caller's contract
+#define B2_MOSAIC(PBV)                                                                                              \
+    mosaic_kernel<PBV><<<grid, 256, smem, s>>>(stacks, valids, scene_day, scene_cf, ref_day, min_day, max_day, max_cf, \
+                                               T, hw, pb, static_cast<uint8_t*>(out), out_mask, src_index, n_eligible)
+    if (al && pb == 16) B2_MOSAIC(16);
+    else if (al && pb == 8) B2_MOSAIC(8);
+    else if (al && pb == 4) B2_MOSAIC(4);
+    else if (al && pb == 2) B2_MOSAIC(2);
+    else B2_MOSAIC(0);
+#undef B2_MOSAIC
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}

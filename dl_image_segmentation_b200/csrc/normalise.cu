@@ -1,0 +1,208 @@
+// normalise.cu — K4: fused cast + per-band normalise + label one-hot, and exact integer band statistics.
+//
+// North-star row A17.  Not present in the reference (nearest analogue: per-band-max display
+// scaling, parse_tfrecords.ipynb cell 21); the definition is the oracle's (oracle/normalise.py):
+//     x_hat = (float32(x) - mean[c]) / std[c]        IEEE float32 subtract and divide
+//     onehot[..., k] = (label == k) ? 1.0f : 0.0f    out-of-range labels give an all-zero row (tf.one_hot)
+// Both kernels are elementwise streams bounded by HBM bandwidth; they are write-dominated (4x and 4K x the
+// input bytes), so every store is a coalesced 128-bit streaming store.
+#include "common.cuh"
+
+namespace b2 {
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v) { return (float)v; }
+
+// One thread per output float4 of the image: elements [4g, 4g+4) of the flattened (n_pixels*C) array.
+template <typename T>
+__global__ void __launch_bounds__(256)
+normalise_kernel(const T* __restrict__ img, const float* __restrict__ mean, const float* __restrict__ stdv,
+                 uint64_t n_elems, int C, float* __restrict__ out) {
+    __shared__ float s_mean[64], s_std[64];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        s_mean[c] = mean[c];
+        s_std[c] = stdv[c];
+    }
+    __syncthreads();
+    const uint64_t groups = (n_elems + 3) >> 2;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t e0 = 4 * g;
+        uint32_t c = (uint32_t)(e0 % (uint64_t)C);
+        float f[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float x = (e0 + k < n_elems) ? to_f32(img[e0 + k]) : 0.0f;
+            f[k] = __fdiv_rn(x - s_mean[c], s_std[c]);
+            c = (c + 1 == (uint32_t)C) ? 0 : c + 1;
+        }
+        if (e0 + 4 <= n_elems) {
+            st_cs(reinterpret_cast<float4*>(out) + g, make_float4(f[0], f[1], f[2], f[3]));
+        } else {
+            for (uint64_t e = e0; e < n_elems; e++) out[e] = f[e - e0];
+        }
+    }
+}
+
+template <typename L>
+__device__ __forceinline__ bool label_is(L lab, uint32_t k);
+template <>
+__device__ __forceinline__ bool label_is<uint8_t>(uint8_t lab, uint32_t k) { return (uint32_t)lab == k; }
+template <>
+__device__ __forceinline__ bool label_is<float>(float lab, uint32_t k) { return lab == (float)k; }
+
+// One thread per output float4 of the one-hot tensor: floats [4g, 4g+4) of the flattened (n_pixels*K) array.
+template <typename L>
+__global__ void __launch_bounds__(256)
+onehot_kernel(const L* __restrict__ label, uint64_t n_pixels, int K, float* __restrict__ out) {
+    const uint64_t n_fl = n_pixels * (uint64_t)K;
+    const uint64_t groups = (n_fl + 3) >> 2;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t f0 = 4 * g;
+        uint64_t l = f0 / (uint64_t)K;
+        uint32_t c = (uint32_t)(f0 - l * (uint64_t)K);
+        float f[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            f[k] = (l < n_pixels && label_is<L>(__ldg(label + l), c)) ? 1.0f : 0.0f;
+            if (++c == (uint32_t)K) {
+                c = 0;
+                l++;
+            }
+        }
+        if (f0 + 4 <= n_fl) {
+            st_cs(reinterpret_cast<float4*>(out) + g, make_float4(f[0], f[1], f[2], f[3]));
+        } else {
+            for (uint64_t e = f0; e < n_fl; e++) out[e] = f[e - f0];
+        }
+    }
+}
+
+// Band statistics.  Thread-private 64-bit accumulators per band (B <= kMaxB), warp-shuffle + shared-memory
+// reduction, then one 64-bit atomic per (CTA, band, counter).  x*x is split at bit 16 so that the global
+// accumulators cannot overflow 2^64 for any realistic dataset.
+constexpr int kMaxB = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+stats_kernel(const T* __restrict__ img, const uint8_t* __restrict__ valid, uint64_t n_pixels, int B,
+             unsigned long long* __restrict__ acc) {
+    unsigned long long cnt = 0, sum[kMaxB], sq[kMaxB];
+#pragma unroll
+    for (int b = 0; b < kMaxB; b++) sum[b] = sq[b] = 0;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pixels; p += (uint64_t)gridDim.x * blockDim.x) {
+        if (valid && !valid[p]) continue;
+        cnt++;
+        const T* px = img + p * (uint64_t)B;
+#pragma unroll
+        for (int b = 0; b < kMaxB; b++) {
+            if (b < B) {
+                const unsigned long long x = (unsigned long long)px[b];
+                sum[b] += x;
+                sq[b] += x * x;
+            }
+        }
+    }
+    __shared__ unsigned long long red[8][2 * kMaxB + 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) red[wid][2 * kMaxB] = cnt;
+#pragma unroll
+    for (int b = 0; b < kMaxB; b++) {
+        if (b < B) {
+            unsigned long long s = sum[b], q = sq[b];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                q += __shfl_xor_sync(0xffffffffu, q, o);
+            }
+            if (lane == 0) {
+                red[wid][b] = s;
+                red[wid][kMaxB + b] = q;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < B) {
+        const int b = threadIdx.x;
+        unsigned long long n = 0, s = 0, q = 0;
+        for (int w = 0; w < 8; w++) {
+            n += red[w][2 * kMaxB];
+            s += red[w][b];
+            q += red[w][kMaxB + b];
+        }
+        // per-CTA q < 2^64 is guaranteed (<= 2^32 per pixel, a CTA sees far fewer than 2^32 pixels)
+        atomicAdd(acc + 4 * b + 0, n);
+        atomicAdd(acc + 4 * b + 1, s);
+        atomicAdd(acc + 4 * b + 2, q & 0xFFFFull);
+        atomicAdd(acc + 4 * b + 3, q >> 16);
+    }
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+static unsigned stream_grid(const b2_ctx* ctx, uint64_t items) {
+    uint64_t blocks = (items + 255) / 256;
+    const uint64_t cap = (uint64_t)ctx->sm_count * 32;  // several waves of resident CTAs, grid-stride beyond
+    if (blocks > cap) blocks = cap;
+    return (unsigned)(blocks ? blocks : 1);
+}
+
+extern "C" int b2_normalise_onehot(b2_ctx* ctx, const void* img, int img_dtype, const void* label, int label_dtype,
+                                   const float* mean, const float* stdv, uint64_t n_pixels, int C, int K,
+                                   float* img_out, float* onehot_out, b2_stream stream) {
+    B2_REQUIRE(ctx, "b2_normalise_onehot: NULL ctx");
+    B2_REQUIRE(!img_out || (img && mean && stdv && C >= 1 && C <= 64), "b2_normalise_onehot: image path needs img, mean, std, 1<=C<=64");
+    B2_REQUIRE(!onehot_out || (label && K >= 1), "b2_normalise_onehot: one-hot path needs label and K>=1");
+    B2_REQUIRE((reinterpret_cast<uintptr_t>(img_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(onehot_out) & 15) == 0,
+               "b2_normalise_onehot: outputs must be 16-byte aligned");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (img_out && n_pixels) {
+        const uint64_t n = n_pixels * (uint64_t)C;
+        const unsigned grid = stream_grid(ctx, (n + 3) / 4);
+        switch (img_dtype) {
+            case B2_U8: normalise_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(img), mean, stdv, n, C, img_out); break;
+            case B2_U16: normalise_kernel<uint16_t><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(img), mean, stdv, n, C, img_out); break;
+            case B2_I16: normalise_kernel<int16_t><<<grid, 256, 0, s>>>(static_cast<const int16_t*>(img), mean, stdv, n, C, img_out); break;
+            case B2_F32: normalise_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(img), mean, stdv, n, C, img_out); break;
+            default: return fail("b2_normalise_onehot: img_dtype must be u8, u16, i16 or f32");
+        }
+        ctx->launches++;
+        B2_CUDA(cudaGetLastError());
+    }
+    if (onehot_out && n_pixels) {
+        const unsigned grid = stream_grid(ctx, (n_pixels * (uint64_t)K + 3) / 4);
+        if (label_dtype == B2_U8)
+            onehot_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(label), n_pixels, K, onehot_out);
+        else if (label_dtype == B2_F32)
+            onehot_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(label), n_pixels, K, onehot_out);
+        else
+            return fail("b2_normalise_onehot: label_dtype must be u8 or f32");
+        ctx->launches++;
+        B2_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" int b2_band_stats(b2_ctx* ctx, const void* img, int dtype, const uint8_t* valid, uint64_t n_pixels, int B,
+                             uint64_t* acc, b2_stream stream) {
+    B2_REQUIRE(ctx && img && acc, "b2_band_stats: NULL argument");
+    B2_REQUIRE(B >= 1 && B <= kMaxB, "b2_band_stats: 1 <= B <= 16");
+    if (n_pixels == 0) return 0;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const unsigned grid = stream_grid(ctx, n_pixels);
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(acc);
+    if (dtype == B2_U8)
+        stats_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(img), valid, n_pixels, B, a);
+    else if (dtype == B2_U16)
+        stats_kernel<uint16_t><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(img), valid, n_pixels, B, a);
+    else
+        return fail("b2_band_stats: dtype must be u8 or u16");
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,371 @@
+"""Device operators: thin, typed Python wrappers over the C ABI (include/b2chips.h).
+
+Everything here takes and returns CUDA tensors (torch is the allocator / stream provider only) and
+enqueues on torch's current stream.  No function in this module computes on the CPU.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import B2Error, check, get_ctx, lib, ptr
+
+_NP2B2 = {np.dtype("uint8"): _lib.B2_U8, np.dtype("uint16"): _lib.B2_U16, np.dtype("int16"): _lib.B2_I16,
+          np.dtype("uint32"): _lib.B2_U32, np.dtype("int32"): _lib.B2_I32, np.dtype("float32"): _lib.B2_F32,
+          np.dtype("float64"): _lib.B2_F64, np.dtype("int8"): _lib.B2_I8}
+_T2NP = {torch.uint8: "uint8", torch.int8: "int8", torch.int16: "int16", torch.int32: "int32",
+         torch.float32: "float32", torch.float64: "float64"}
+for _n in ("uint16", "uint32"):
+    if hasattr(torch, _n):
+        _T2NP[getattr(torch, _n)] = _n
+
+
+class DataLossError(B2Error):
+    """A TFRecord frame or data CRC did not verify (TensorFlow raises tf.errors.DataLossError)."""
+
+
+def b2_dtype(t) -> int:
+    if isinstance(t, torch.Tensor):
+        return _NP2B2[np.dtype(_T2NP[t.dtype])]
+    return _NP2B2[np.dtype(t.dtype)]
+
+
+def to_device(x, device=None, dtype=None):
+    """numpy array / bytes / torch tensor -> contiguous CUDA tensor (no arithmetic, just a copy)."""
+    ctx = get_ctx(device)
+    if isinstance(x, (bytes, bytearray, memoryview)):
+        x = np.frombuffer(x, dtype=np.uint8)
+    if isinstance(x, np.ndarray):
+        if dtype is not None:
+            x = x.astype(dtype, copy=False)
+        if not x.flags.writeable:
+            x = x.copy()
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if not isinstance(x, torch.Tensor):
+        raise TypeError("expected bytes, numpy array or torch tensor, got %r" % type(x))
+    return x.to(ctx.device, non_blocking=True).contiguous()
+
+
+# --------------------------------------------------------------------------------------------- K3
+def median_composite(stack, valid, nodata=None, device=None):
+    """(T,H,W,B) uint16 + (T,H,W[,1]) uint8 -> ((H,W,B) float64, (H,W,B) bool mask).  b2_median_composite_u16."""
+    ctx = get_ctx(device)
+    stack = to_device(stack, ctx.device)
+    valid = to_device(valid, ctx.device)
+    if b2_dtype(stack) != _lib.B2_U16:
+        raise B2Error("median_composite: stack must be uint16 (got %s)" % stack.dtype)
+    if valid.dim() == 4:
+        if valid.shape[-1] != 1:
+            raise B2Error("median_composite: valid must be (T,H,W) or (T,H,W,1)")
+        valid = valid[..., 0].contiguous()
+    if valid.dtype == torch.bool:
+        valid = valid.to(torch.uint8)
+    T, H, W, B = stack.shape
+    if tuple(valid.shape) != (T, H, W) or valid.dtype != torch.uint8:
+        raise B2Error("median_composite: valid must be uint8 of shape (T,H,W)")
+    nd = None
+    if nodata is not None:
+        nd = to_device(nodata, ctx.device)
+        if nd.dtype == torch.bool:
+            nd = nd.to(torch.uint8)
+        if tuple(nd.shape) != (T, H, W, B) or nd.dtype != torch.uint8:
+            raise B2Error("median_composite: nodata mask must be uint8/bool of shape (T,H,W,B)")
+    out = torch.empty((H, W, B), dtype=torch.float64, device=ctx.device)
+    mask = torch.empty((H, W, B), dtype=torch.uint8, device=ctx.device)
+    check(lib().b2_median_composite_u16(ctx.handle, ptr(stack), ptr(valid), ptr(nd), T, H, W, B, ptr(out), ptr(mask),
+                                        ctx.stream()))
+    return out, mask.view(torch.bool)
+
+
+_I32_MIN, _I32_MAX = -(1 << 31), (1 << 31) - 1
+
+
+def nearest_date_mosaic(stacks, valids, scene_day, scene_cf, ref_day, min_day=None, max_day=None, max_cf=None,
+                        device=None, want_src=True, ptr_tables=None):
+    """Batched nearest-to-reference-date mosaic.  b2_nearest_date_mosaic.
+
+    stacks: (N,T,H,W,B) tensor or list of N (T,H,W,B) tensors; valids: (N,T,H,W) / list of (T,H,W) uint8;
+    scene_day (N,T) int32; scene_cf (N,T) float32.  Returns out (N,H,W,B), mask (N,H,W) bool,
+    src (N,H,W) int16 or None, n_eligible (N,) int32 — all on the device.
+    """
+    ctx = get_ctx(device)
+    if isinstance(stacks, (list, tuple)):
+        st = [to_device(s, ctx.device) for s in stacks]
+        va = [to_device(v, ctx.device) for v in valids]
+    else:
+        s_all = to_device(stacks, ctx.device)
+        v_all = to_device(valids, ctx.device)
+        st = [s_all[i] for i in range(s_all.shape[0])]
+        va = [v_all[i] for i in range(v_all.shape[0])]
+    n = len(st)
+    T, H, W, B = st[0].shape
+    for s, v in zip(st, va):
+        if tuple(s.shape) != (T, H, W, B) or s.dtype != st[0].dtype or not s.is_contiguous():
+            raise B2Error("nearest_date_mosaic: all stacks must be contiguous with one shape and dtype")
+        if tuple(v.shape) != (T, H, W) or v.dtype != torch.uint8 or not v.is_contiguous():
+            raise B2Error("nearest_date_mosaic: valids must be contiguous uint8 (T,H,W)")
+    day = to_device(np.ascontiguousarray(scene_day, dtype=np.int32) if not isinstance(scene_day, torch.Tensor) else scene_day, ctx.device)
+    cf = to_device(np.ascontiguousarray(scene_cf, dtype=np.float32) if not isinstance(scene_cf, torch.Tensor) else scene_cf, ctx.device)
+    if tuple(day.shape) != (n, T) or tuple(cf.shape) != (n, T) or day.dtype != torch.int32 or cf.dtype != torch.float32:
+        raise B2Error("nearest_date_mosaic: scene_day / scene_cf must be (N,T) int32 / float32")
+    if ptr_tables is None:
+        sp = torch.tensor([s.data_ptr() for s in st], dtype=torch.int64).to(ctx.device)
+        vp = torch.tensor([v.data_ptr() for v in va], dtype=torch.int64).to(ctx.device)
+    else:
+        sp, vp = ptr_tables
+    eb = st[0].element_size()
+    out = torch.empty((n, H, W, B), dtype=st[0].dtype, device=ctx.device)
+    mask = torch.empty((n, H, W), dtype=torch.uint8, device=ctx.device)
+    src = torch.empty((n, H, W), dtype=torch.int16, device=ctx.device) if want_src else None
+    nel = torch.empty((n,), dtype=torch.int32, device=ctx.device)
+    check(lib().b2_nearest_date_mosaic(
+        ctx.handle, ptr(sp), ptr(vp), ptr(day), ptr(cf), int(ref_day),
+        _I32_MIN if min_day is None else int(min_day), _I32_MAX if max_day is None else int(max_day),
+        float("nan") if max_cf is None else float(max_cf), n, T, H, W, B, eb, ptr(out), ptr(mask), ptr(src), ptr(nel),
+        ctx.stream()))
+    return out, mask.view(torch.bool), src, nel
+
+
+# --------------------------------------------------------------------------------------------- K4
+def normalise_onehot(img, label, mean, std, num_classes, device=None):
+    """(N,H,W,C) u8/u16/i16/f32 + (N,H,W) u8/f32 -> ((N,H,W,C) f32, (N,H,W,K) f32).  b2_normalise_onehot."""
+    ctx = get_ctx(device)
+    img_out = hot = None
+    stream = ctx.stream()
+    n_pix = None
+    if img is not None:
+        img = to_device(img, ctx.device)
+        C = img.shape[-1]
+        mean_d = to_device(np.asarray(mean, dtype=np.float32) if not isinstance(mean, torch.Tensor) else mean, ctx.device)
+        std_d = to_device(np.asarray(std, dtype=np.float32) if not isinstance(std, torch.Tensor) else std, ctx.device)
+        if mean_d.numel() != C or std_d.numel() != C:
+            raise B2Error("normalise_onehot: mean/std must have one entry per band")
+        img_out = torch.empty(img.shape, dtype=torch.float32, device=ctx.device)
+        n_pix = img.numel() // C
+        check(lib().b2_normalise_onehot(ctx.handle, ptr(img), b2_dtype(img), None, 0, ptr(mean_d), ptr(std_d), n_pix, C, 1,
+                                        ptr(img_out), None, stream))
+    if label is not None:
+        label = to_device(label, ctx.device)
+        if label.dim() >= 3 and label.shape[-1] == 1 and img is not None and label.dim() == img.dim():
+            label = label[..., 0].contiguous()
+        hot = torch.empty(tuple(label.shape) + (int(num_classes),), dtype=torch.float32, device=ctx.device)
+        check(lib().b2_normalise_onehot(ctx.handle, None, 0, ptr(label), b2_dtype(label), None, None, label.numel(), 1,
+                                        int(num_classes), None, ptr(hot), stream))
+    return img_out, hot
+
+
+def band_stats(img, valid=None, acc=None, device=None):
+    """Accumulate exact integer band statistics into acc (B,4) [int64 storage of uint64 counters]."""
+    ctx = get_ctx(device)
+    img = to_device(img, ctx.device)
+    B = img.shape[-1]
+    if acc is None:
+        acc = torch.zeros((B, 4), dtype=torch.int64, device=ctx.device)
+    v = None
+    if valid is not None:
+        v = to_device(valid, ctx.device)
+        if v.dtype == torch.bool:
+            v = v.to(torch.uint8)
+    check(lib().b2_band_stats(ctx.handle, ptr(img), b2_dtype(img), ptr(v), img.numel() // B, B, ptr(acc), ctx.stream()))
+    return acc
+
+
+def stats_to_python(acc):
+    """(B,4) device counters -> list of (n, sum, sumsq) exact Python ints."""
+    a = acc.cpu().numpy().view(np.uint64)
+    return [(int(r[0]), int(r[1]), int(r[2]) + 65536 * int(r[3])) for r in a]
+
+
+def mean_std_from_stats(stats):
+    """Exact integer stats -> float32 mean/std (population), each one correctly-rounded float64 division."""
+    mean, std = [], []
+    for n, s, ss in stats:
+        if n == 0:
+            mean.append(0.0)
+            std.append(1.0)
+        else:
+            mean.append(s / n)
+            std.append(math.sqrt((ss * n - s * s) / (n * n)))
+    return np.asarray(mean, dtype=np.float64).astype(np.float32), np.asarray(std, dtype=np.float64).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------- K2
+def crc32c(data, offsets, lens, device=None):
+    """CRC-32C of byte ranges of a device buffer -> uint32 numpy array (host)."""
+    ctx = get_ctx(device)
+    data = to_device(data, ctx.device)
+    offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+    ln = np.ascontiguousarray(lens, dtype=np.uint64)
+    n = len(offs)
+    out = torch.empty((max(n, 1),), dtype=torch.int32, device=ctx.device)
+    od = to_device(offs.view(np.int64), ctx.device)
+    ld = to_device(ln.view(np.int64), ctx.device)
+    check(lib().b2_crc32c(ctx.handle, ptr(data), ptr(od), ptr(ld), n, int(ln.max()) if n else 0, ptr(out), ctx.stream()))
+    return out[:n].cpu().numpy().view(np.uint32)
+
+
+class ShardIndex:
+    """A shard resident on the device plus its frame table and per-record feature locations."""
+
+    def __init__(self, shard, nbytes, n, rec_off, rec_len, index_dev, index, lens_host):
+        self.shard, self.nbytes, self.n = shard, nbytes, n
+        self.rec_off, self.rec_len, self.index_dev, self.index = rec_off, rec_len, index_dev, index
+        self.max_len = int(lens_host.max()) if n else 0
+        self.lens_host = lens_host
+
+    def identifiers(self, shard_host=None):
+        """identifier bytes of every record (small D2H gathers)."""
+        out = []
+        for r in self.index:
+            o, l = int(r["id_off"]), int(r["id_len"])
+            out.append(bytes(self.shard[o:o + l].cpu().numpy()) if shard_host is None else bytes(shard_host[o:o + l]))
+        return out
+
+
+def open_shard(data, device=None, with_index=True, nbytes=None):
+    """Upload (if needed), walk the frames and locate the features.  One small D2H read-back (the tables)."""
+    ctx = get_ctx(device)
+    shard = to_device(data, ctx.device)
+    if shard.dtype != torch.uint8 or shard.dim() != 1:
+        raise B2Error("open_shard: shard must be a flat uint8 buffer")
+    nbytes = int(shard.numel()) if nbytes is None else int(nbytes)
+    cap = 1 << 12
+    while True:
+        rec_off = torch.empty((cap,), dtype=torch.int64, device=ctx.device)
+        rec_len = torch.empty((cap,), dtype=torch.int64, device=ctx.device)
+        res = torch.zeros((2,), dtype=torch.int64, device=ctx.device)
+        check(lib().b2_tfrecord_scan(ctx.handle, ptr(shard), nbytes, cap, ptr(rec_off), ptr(rec_len), ptr(res), ctx.stream()))
+        n, st = (int(v) for v in res.cpu())
+        if st == 2:
+            cap *= 16
+            continue
+        if st != 0:
+            raise DataLossError("corrupted record #%d (bad frame or length CRC)" % n)
+        break
+    lens_host = rec_len[:n].cpu().numpy().astype(np.uint64) if n else np.zeros(0, np.uint64)
+    index_dev = index = None
+    if with_index and n:
+        index_dev = torch.empty((n * ctypes.sizeof(_lib.ExampleIndex),), dtype=torch.uint8, device=ctx.device)
+        check(lib().b2_tfrecord_index(ctx.handle, ptr(shard), ptr(rec_off), ptr(rec_len), n, ptr(index_dev), ctx.stream()))
+        index = index_dev.cpu().numpy().view(np.dtype(_lib.EXAMPLE_INDEX_DTYPE))
+    elif with_index:
+        index = np.zeros(0, np.dtype(_lib.EXAMPLE_INDEX_DTYPE))
+    return ShardIndex(shard, nbytes, n, rec_off, rec_len, index_dev, index, lens_host)
+
+
+def _align16(x):
+    return (int(x) + 15) & ~15
+
+
+def parse_shard(si: ShardIndex, mode, verify_crc=True, mean=None, std=None, num_classes=None, first=0, count=None,
+                out=None):
+    """Run the fused parse kernel over records [first, first+count).  Returns (img_buf, tgt_buf, status_dev).
+
+    mode 'raw': img_buf (count, img_stride) uint8 holding each record's payload bytes as stored;
+    mode 'norm_onehot': img_buf (count, img_len) float32, tgt_buf (count, tgt_len*K) float32;
+    mode 'none': CRC verification only.
+    """
+    ctx = get_ctx(si.shard.device)
+    count = si.n - first if count is None else count
+    if count <= 0:
+        return None, None, None
+    idx = si.index[first:first + count]
+    sink = _lib.ParseSink()
+    sink.verify_crc = 1 if verify_crc else 0
+    img_buf = tgt_buf = None
+    if mode == "none":
+        sink.mode = _lib.SINK_NONE
+    elif mode == "raw":
+        sink.mode = _lib.SINK_RAW
+        istr, tstr = _align16(max(1, idx["img_len"].max())), _align16(max(1, idx["tgt_len"].max()))
+        img_buf, tgt_buf = out if out is not None else (
+            torch.empty((count, istr), dtype=torch.uint8, device=ctx.device),
+            torch.empty((count, tstr), dtype=torch.uint8, device=ctx.device))
+        sink.img_out, sink.img_stride = img_buf.data_ptr(), img_buf.stride(0)
+        sink.tgt_out, sink.tgt_stride = tgt_buf.data_ptr(), tgt_buf.stride(0)
+    elif mode == "norm_onehot":
+        sink.mode = _lib.SINK_NORM_ONEHOT
+        K = int(num_classes)
+        C = int(idx["channels"][0])
+        il, tl = int(idx["img_len"].max()), int(idx["tgt_len"].max())
+        if (il * 4) % 16 or (tl * K * 4) % 16:
+            il, tl = _align16(il), _align16(tl)
+        img_buf, tgt_buf = out if out is not None else (
+            torch.empty((count, il), dtype=torch.float32, device=ctx.device),
+            torch.empty((count, tl * K), dtype=torch.float32, device=ctx.device))
+        mean_d = to_device(np.asarray(mean, dtype=np.float32) if not isinstance(mean, torch.Tensor) else mean, ctx.device)
+        std_d = to_device(np.asarray(std, dtype=np.float32) if not isinstance(std, torch.Tensor) else std, ctx.device)
+        if mean_d.numel() != C or std_d.numel() != C:
+            raise B2Error("parse_shard: mean/std must have %d entries" % C)
+        sink.img_out, sink.img_stride = img_buf.data_ptr(), img_buf.stride(0) * 4
+        sink.tgt_out, sink.tgt_stride = tgt_buf.data_ptr(), tgt_buf.stride(0) * 4
+        sink.mean, sink.std, sink.channels, sink.num_classes = mean_d.data_ptr(), std_d.data_ptr(), C, K
+        sink._keep = (mean_d, std_d)
+    else:
+        raise ValueError(mode)
+    status = torch.empty((count,), dtype=torch.int32, device=ctx.device)
+    esz = ctypes.sizeof(_lib.ExampleIndex)
+    index_ptr = ctypes.c_void_p(si.index_dev.data_ptr() + first * esz) if si.index_dev is not None else None
+    check(lib().b2_tfrecord_parse(
+        ctx.handle, ptr(si.shard), si.nbytes, ctypes.c_void_p(si.rec_off.data_ptr() + 8 * first),
+        ctypes.c_void_p(si.rec_len.data_ptr() + 8 * first), index_ptr, count,
+        int(si.lens_host[first:first + count].max()), ctypes.byref(sink), ptr(status), ctx.stream()))
+    return img_buf, tgt_buf, status
+
+
+def example_layout(kind, img_bytes, tgt_bytes, img_h, img_w, img_c, tgt_h, tgt_w, identifier: bytes):
+    """Host-side protobuf scaffold around the two payloads -> (scaffold bytes, piece_len[3], example_len)."""
+    cap = 256 + len(identifier)
+    buf = (ctypes.c_uint8 * cap)()
+    pl = (ctypes.c_uint32 * 3)()
+    el = ctypes.c_uint64()
+    idb = (ctypes.c_uint8 * max(1, len(identifier))).from_buffer_copy(identifier or b"\0")
+    check(lib().b2_example_layout(kind, int(img_bytes), int(tgt_bytes), int(img_h), int(img_w), int(img_c), int(tgt_h),
+                                  int(tgt_w), ctypes.cast(idb, ctypes.c_void_p), len(identifier),
+                                  ctypes.cast(buf, ctypes.c_void_p), cap, pl, ctypes.byref(el)))
+    total = pl[0] + pl[1] + pl[2]
+    return bytes(buf[:total]), (pl[0], pl[1], pl[2]), int(el.value)
+
+
+def build_records(items, device=None):
+    """Serialise + frame records on the device.
+
+    items: list of dicts with keys img (CUDA tensor), tgt (CUDA tensor), kind (1 bytes / 2 float),
+    h, w, c, th, tw, identifier (bytes).  Returns (out uint8 CUDA tensor holding the framed records back to
+    back, offsets list, total bytes).
+    """
+    ctx = get_ctx(device)
+    n = len(items)
+    descs = np.zeros(n, dtype=np.dtype(_lib.BUILD_DESC_DTYPE))
+    assert descs.dtype.itemsize == ctypes.sizeof(_lib.BuildDesc)
+    scaf = bytearray()
+    pos = 0
+    offsets = []
+    max_rec = 0
+    keep = []
+    for i, it in enumerate(items):
+        img, tgt, kind = it["img"], it["tgt"], int(it["kind"])
+        keep += [img, tgt]
+        ib = img.numel() * (img.element_size() if kind == 1 else 4)
+        tb = tgt.numel() * (tgt.element_size() if kind == 1 else 4)
+        sc, pl, el = example_layout(kind, ib, tb, it["h"], it["w"], it["c"], it["th"], it["tw"], it["identifier"])
+        d = descs[i]
+        d["out_off"], d["example_len"], d["scaffold_off"] = pos, el, len(scaf)
+        d["piece_len"] = pl
+        d["src_dtype"], d["tgt_dtype"], d["kind"] = b2_dtype(img), b2_dtype(tgt), kind
+        d["img_src"], d["img_count"] = img.data_ptr(), img.numel() * (img.element_size() if kind == 1 else 1)
+        d["tgt_src"], d["tgt_count"] = tgt.data_ptr(), tgt.numel() * (tgt.element_size() if kind == 1 else 1)
+        scaf += sc
+        offsets.append(pos)
+        pos += el + 16
+        max_rec = max(max_rec, el + 16)
+    out = torch.empty((_align16(pos) + 16,), dtype=torch.uint8, device=ctx.device)
+    descs_d = to_device(descs.view(np.uint8), ctx.device)
+    scaf_d = to_device(bytes(scaf) if scaf else b"\0", ctx.device)
+    for s in range(0, n, 65535):
+        m = min(65535, n - s)
+        check(lib().b2_tfrecord_build(ctx.handle, ctypes.c_void_p(descs_d.data_ptr() + s * descs.dtype.itemsize), m,
+                                      max_rec, ptr(scaf_d), ptr(out), ctx.stream()))
+    return out, offsets, pos

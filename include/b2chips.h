@@ -1,0 +1,170 @@
+/*
+ * b2chips.h — C ABI of libb2chips.so: the B200 (sm_100a) replacement for the native calls that
+ * harry-gibson/dl_image_segmentation's hot path reaches through TensorFlow, rasterio/GDAL/libtiff,
+ * libpng/zlib and numpy.ma.  The reference has no FFI of its own (it is pure Python,
+ * dl_segmentation_utils/__init__.py:1-15); every entry point below therefore cites the reference
+ * CALL SITE whose third-party native work it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  Every function returns 0 on success, non-zero on misuse or
+ *     CUDA failure; b2_last_error() then returns a thread-local message.
+ *   - All *_dev pointers are device memory owned by the caller; the library allocates nothing but a
+ *     per-context workspace.  Work is enqueued on `stream` (a cudaStream_t passed as void*); nothing
+ *     synchronises the host unless stated.
+ *   - Per-item failures (a corrupt chip, a bad CRC) are DATA: they come back in a status array, as the
+ *     reference's skip-and-continue loop expects (_img_to_tf_mp.py:127-136).
+ *   - One b2_ctx per (process, device), used by one host thread at a time (one writer per worker,
+ *     _img_to_tf_mp.py:119).
+ */
+#ifndef B2CHIPS_H
+#define B2CHIPS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_VERSION 100 /* 0.1.0 */
+
+typedef struct b2_ctx b2_ctx;
+typedef void* b2_stream; /* cudaStream_t */
+
+/* element types (numpy names) */
+enum { B2_U8 = 0, B2_U16 = 1, B2_I16 = 2, B2_U32 = 3, B2_I32 = 4, B2_F32 = 5, B2_F64 = 6, B2_I8 = 7 };
+
+/* ------------------------------------------------------------------ context */
+int b2_version(void);
+const char* b2_last_error(void);
+int b2_ctx_create(int device, b2_ctx** out);
+int b2_ctx_destroy(b2_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t b2_ctx_launch_count(const b2_ctx* ctx);
+int b2_ctx_sm_count(const b2_ctx* ctx);
+
+/* ------------------------------------------------------------------ K3: compositors
+ * b2_median_composite_u16 replaces np.repeat + np.ma.masked_where + np.ma.median(axis=0)
+ *   (_descartes_img_chips.py:562-567).  stack (T,H,W,B) u16 bands-innermost; valid (T,H,W) u8, 0 = masked;
+ *   nodata (T,H,W,B) u8 or NULL, non-zero = masked (the pre-existing mask np.ma.masked_where ORs with).
+ *   out (H,W,B) float64: middle value, or mean of the two middles; out_mask (H,W,B) u8 = 1 and out = 0.0
+ *   where no scene is valid.
+ */
+int b2_median_composite_u16(b2_ctx* ctx, const uint16_t* stack_dev, const uint8_t* valid_dev,
+                            const uint8_t* nodata_dev, int T, int H, int W, int B,
+                            double* out_dev, uint8_t* out_mask_dev, b2_stream stream);
+
+/* b2_nearest_date_mosaic replaces the filter + sort + SceneCollection.mosaic of create_img_array_for_tile
+ *   (_descartes_img_chips.py:603-626, key function :461-469).  For each of n_chips chips:
+ *   scene t is eligible iff min_day <= scene_day[t] < max_day and (max_cf is NaN or scene_cf[t] < max_cf);
+ *   out pixel = stack[t*] with t* the eligible scene, valid at that pixel, of least |scene_day - ref_day|,
+ *   ties to the HIGHER scene index (stable descending sort, painted last).  INT32_MIN / INT32_MAX disable
+ *   the date bounds.  stacks_dev / valids_dev: device arrays of n_chips device pointers to (T,H,W,B) and
+ *   (T,H,W) u8.  scene_day_dev / scene_cf_dev: (n_chips,T).  out (n_chips,H,W,B) same element type;
+ *   out_mask (n_chips,H,W) u8 = 1 where no valid scene (out = 0); src_index (n_chips,H,W) int16 or NULL;
+ *   n_eligible (n_chips) int32 or NULL — 0 means the reference returns None (:614-615).
+ */
+int b2_nearest_date_mosaic(b2_ctx* ctx, const void* const* stacks_dev, const uint8_t* const* valids_dev,
+                           const int32_t* scene_day_dev, const float* scene_cf_dev,
+                           int32_t ref_day, int32_t min_day, int32_t max_day, float max_cf,
+                           int n_chips, int T, int H, int W, int B, int elem_bytes,
+                           void* out_dev, uint8_t* out_mask_dev, int16_t* src_index_dev,
+                           int32_t* n_eligible_dev, b2_stream stream);
+
+/* ------------------------------------------------------------------ K4: cast / normalise / one-hot / statistics
+ * North-star row A17 (not in the reference; nearest analogue parse_tfrecords.ipynb cell 21).
+ *   img (N,H,W,C) of img_dtype; label (N,H,W) of label_dtype (B2_U8 or B2_F32); mean/std (C) float32.
+ *   img_out = (float(x) - mean[c]) / std[c]  (IEEE float32);  onehot_out (N,H,W,K) = label==k ? 1 : 0.
+ *   Either output may be NULL.
+ */
+int b2_normalise_onehot(b2_ctx* ctx, const void* img_dev, int img_dtype, const void* label_dev, int label_dtype,
+                        const float* mean_dev, const float* std_dev, uint64_t n_pixels, int C, int K,
+                        float* img_out_dev, float* onehot_out_dev, b2_stream stream);
+
+/* Exact integer per-band statistics: acc (B,4) uint64 += { n, sum x, sum (x*x & 0xFFFF), sum (x*x >> 16) } over
+ *   pixels with valid != 0 (valid NULL = all).  dtype B2_U8 or B2_U16.  Accumulates (caller zeroes acc). */
+int b2_band_stats(b2_ctx* ctx, const void* img_dev, int dtype, const uint8_t* valid_dev, uint64_t n_pixels, int B,
+                  uint64_t* acc_dev, b2_stream stream);
+
+/* ------------------------------------------------------------------ K2: TFRecord framing, CRC-32C, Example payloads
+ * Replace tf.io.TFRecordWriter.write / TFRecordDataset (framing + masked CRC-32C), Example.SerializeToString,
+ * tf.io.parse_single_example, tf.io.decode_raw and tf.reshape
+ *   (_img_to_tf_mp.py:119,141; _tfrecord_image_translation.py:211,249,306-314,394-407; parse_tfrecords.ipynb cell 4).
+ */
+
+/* CRC-32C (unmasked) of n byte ranges of one device buffer. */
+int b2_crc32c(b2_ctx* ctx, const uint8_t* data_dev, const uint64_t* offsets_dev, const uint64_t* lens_dev, int n,
+              uint64_t max_len, uint32_t* crc_out_dev, b2_stream stream);
+
+/* Walk the frames of one shard exactly as RecordReader does.  rec_offsets/rec_lens (capacity max_records) receive
+ * the offset and length of each record's DATA.  result_dev[0] = number of records found, result_dev[1] = 0 ok,
+ * 1 = corrupt/truncated frame or bad length-CRC at record result_dev[0], 2 = capacity exceeded.
+ * shard_dev must be 16-byte aligned. */
+int b2_tfrecord_scan(b2_ctx* ctx, const uint8_t* shard_dev, uint64_t nbytes, uint64_t max_records,
+                     uint64_t* rec_offsets_dev, uint64_t* rec_lens_dev, int64_t* result_dev, b2_stream stream);
+
+typedef struct {
+    uint64_t img_off, img_len; /* payload of image/image_data, offset from shard start, length in bytes      */
+    uint64_t tgt_off, tgt_len; /* payload of target/target_data                                              */
+    uint64_t id_off, id_len;   /* identifier bytes                                                           */
+    int32_t img_kind, tgt_kind; /* 1 = BytesList (one value), 2 = FloatList (packed float32), 0 = absent     */
+    int32_t height, width, channels, tgt_height, tgt_width;
+    int32_t status; /* 0 ok; 1 malformed protobuf; 2 required key missing / wrong type / not exactly one value */
+} b2_example_index;
+
+/* Locate the eight features of each Example (any key order, unknown fields skipped, last duplicate wins). */
+int b2_tfrecord_index(b2_ctx* ctx, const uint8_t* shard_dev, const uint64_t* rec_offsets_dev,
+                      const uint64_t* rec_lens_dev, int n, b2_example_index* index_out_dev, b2_stream stream);
+
+enum { B2_SINK_NONE = 0, B2_SINK_RAW = 1, B2_SINK_NORM_ONEHOT = 2 };
+typedef struct {
+    int32_t mode;        /* B2_SINK_NONE: CRC only.  RAW: payload bytes copied as stored (uint8 arrays; packed
+                            little-endian float32 == float arrays).  NORM_ONEHOT: uint8 image -> normalised float32,
+                            uint8 target -> one-hot float32 (K classes).                                      */
+    int32_t verify_crc;  /* non-zero: compute each record's data CRC and compare with the stored masked CRC   */
+    void* img_out;       /* record i lands at img_out + i*img_stride (bytes)                                  */
+    uint64_t img_stride;
+    void* tgt_out;
+    uint64_t tgt_stride;
+    const float* mean;   /* (channels) device, NORM_ONEHOT only                                               */
+    const float* std;
+    int32_t channels;
+    int32_t num_classes;
+} b2_parse_sink;
+
+/* One fused pass over the records: CRC verify + payload scatter/cast.  status_dev[i]: 0 ok, 1 data-CRC mismatch
+ * (TF: DataLossError), 2 index status != 0, 3 payload larger than its output stride. */
+int b2_tfrecord_parse(b2_ctx* ctx, const uint8_t* shard_dev, uint64_t shard_nbytes, const uint64_t* rec_offsets_dev,
+                      const uint64_t* rec_lens_dev, const b2_example_index* index_dev, int n,
+                      uint64_t max_record_len, const b2_parse_sink* sink, int32_t* status_dev, b2_stream stream);
+
+/* Host-side: the protobuf bytes around the two payloads for convert_to_example's eight keys in sorted
+ * (deterministic) order (_tfrecord_image_translation.py:199-211).  kind 1 = BytesList, 2 = FloatList.
+ * Writes three scaffold pieces (before image payload, between the payloads, after target payload) into
+ * scaffold[cap]; returns total Example length in *example_len and piece lengths in piece_len[3]. */
+int b2_example_layout(int kind, uint64_t img_payload_bytes, uint64_t tgt_payload_bytes,
+                      int64_t img_h, int64_t img_w, int64_t img_c, int64_t tgt_h, int64_t tgt_w,
+                      const uint8_t* identifier, uint64_t identifier_len,
+                      uint8_t* scaffold, uint64_t cap, uint32_t piece_len[3], uint64_t* example_len);
+
+typedef struct {
+    uint64_t out_off;       /* where the framed record starts in out_dev                                      */
+    uint64_t example_len;   /* length of the Example (frame adds 16)                                          */
+    uint64_t scaffold_off;  /* offset of this record's three scaffold pieces (concatenated) in scaffold_dev  */
+    uint32_t piece_len[3];
+    int32_t src_dtype;      /* element type of img_src (B2_U8 .. B2_F32); B2_U8 also covers raw file bytes   */
+    int32_t tgt_dtype;
+    int32_t kind;           /* 1 BytesList (bytes copied), 2 FloatList (elements widened to float32)         */
+    const void* img_src;    /* device */
+    uint64_t img_count;     /* elements (bytes for kind 1)                                                    */
+    const void* tgt_src;
+    uint64_t tgt_count;
+} b2_build_desc;
+
+/* Serialise + frame n records: header (length + masked CRC), Example bytes, footer (masked data CRC). */
+int b2_tfrecord_build(b2_ctx* ctx, const b2_build_desc* descs_dev, int n, uint64_t max_record_bytes,
+                      const uint8_t* scaffold_dev, uint8_t* out_dev, b2_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2CHIPS_H */
