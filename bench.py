@@ -141,7 +141,8 @@ def run_ours(args, rank, world):
     out = (torch.empty((RECS_PER_SHARD, H * W * C), dtype=torch.float32, device=dev),
            torch.empty((RECS_PER_SHARD, H * W * K), dtype=torch.float32, device=dev))
     pinned = [s.cpu().pin_memory() for s in shards]
-    stage = [torch.empty_like(shards[0]) for _ in range(2)]
+    big = max(int(s.numel()) for s in shards)
+    stage = [torch.empty((big,), dtype=torch.uint8, device=dev) for _ in range(2)]
     ev = lambda: torch.cuda.Event(enable_timing=True)
     kern_events = []
 
@@ -161,7 +162,7 @@ def run_ours(args, rank, world):
     def step_e2e():
         last = None
         for i, p in enumerate(pinned):
-            buf = stage[i & 1]
+            buf = stage[i & 1][:p.numel()]
             buf.copy_(p, non_blocking=True)                                   # H2D of the shard
             si = ops.open_shard(buf, dev)                                     # D2H: frame table + feature index
             _, _, st = ops.parse_shard(si, "norm_onehot", verify_crc=True, mean=mean_d, std=std_d, num_classes=K, out=out)

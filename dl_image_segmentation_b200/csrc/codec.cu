@@ -1,0 +1,927 @@
+// codec.cu — K1: chip decode on the GPU.  TIFF-LZW, DEFLATE (zlib-wrapped: TIFF compression 8/32946 and PNG
+// IDAT), PNG un-filter, TIFF predictor 2 / byte order / planar / tile assembly; plus the host-side header
+// parsers (TIFF IFD, PNG chunks) that plan the device work.
+//
+// Replaces (reference call sites): rasterio MemoryFile(...).open().read() -> GDAL -> libtiff / libpng
+//     _img_to_tf_mp.py:45-48, _tfrecord_image_translation.py:320-326,369-381
+//   tf.image.decode_png / tf.io.decode_image -> libpng + zlib
+//     _img_to_tf_threaded.py:59, _tfrecord_image_translation.py:283,289
+//   reshape_as_image (B,H,W)->(H,W,B)  _img_to_tf_mp.py:69  (output is written HWC directly)
+// Chip format: _descartes_img_chips.py:781-797 (GTiff, COMPRESS=LZW, TILED=TRUE).
+//
+// Entropy decode is serial inside a stream, so parallelism is one WARP per compressed stream (tile, strip or PNG
+// zlib stream) with thousands of streams in flight, and the warp's 32 lanes are used inside the stream:
+//   LZW    : 32 codes per round.  Inside a Clear-delimited segment the code widths depend only on the code index,
+//            so all 32 bit positions are known up front; string lengths resolve through the "entry k = output of
+//            code k plus one byte" identity (LZW is LZ77 with implicit back references), a warp scan gives the
+//            output offsets, and the bytes are produced in parallel by chasing each byte to its literal.
+//   DEFLATE: every lane decodes the same Huffman symbols (uniform control flow, no broadcasts), literals are
+//            gathered 32 at a time into one coalesced store, and LZ77 matches are copied by the whole warp.
+//   PNG    : anti-diagonal wavefront, one lane per scanline of a 32-row band (left / up / up-left dependencies).
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b2 {
+
+enum { CODEC_RAW = 1, CODEC_LZW = 5, CODEC_ZLIB = 8 };
+
+__device__ __forceinline__ void set_status(int32_t* status, int image, int code) {
+    if (status) atomicMax(status + image, code);
+}
+
+// ================================================================================================ LZW
+// bits consumed by the first k codes of a segment (k = number of codes after the Clear)
+__device__ __forceinline__ uint32_t lzw_cum_bits(uint32_t k) {
+    if (k <= 254) return 9 * k;
+    if (k <= 766) return 2286 + 10 * (k - 254);
+    if (k <= 1790) return 7406 + 11 * (k - 766);
+    return 18670 + 12 * (k - 1790);
+}
+__device__ __forceinline__ uint32_t lzw_width(uint32_t k) { return k < 254 ? 9 : (k < 766 ? 10 : (k < 1790 ? 11 : 12)); }
+
+constexpr int kLzwWarps = 4;
+constexpr int kLzwMaxCodes = 3840;  // code positions per segment (entries 258..4095 -> at most 3838 + slack)
+
+struct LzwWarpSmem {
+    uint32_t offs[kLzwMaxCodes + 40];  // offs[k] = output offset of code position k of the current segment
+    uint32_t b_off[33];                // this round: output offset of each lane's string (+ end sentinel)
+    int32_t b_src[32];                 // >=0: source offset in dst ; <0: literal value = -1 - b_src
+};
+
+__global__ void __launch_bounds__(kLzwWarps * 32)
+lzw_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ streams, const int* __restrict__ order,
+           int n_streams, uint8_t* __restrict__ scratch, int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    LzwWarpSmem* sm = reinterpret_cast<LzwWarpSmem*>(smem_raw) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int wi = blockIdx.x * kLzwWarps + (threadIdx.x >> 5);
+    if (wi >= n_streams) return;
+    const b2_stream_desc sd = streams[order ? order[wi] : wi];
+    if (sd.codec != CODEC_LZW) return;
+    const uint8_t* src = blob + sd.src_off;
+    uint8_t* dst = scratch + sd.dst_off;
+    const uint32_t src_bits = sd.src_len * 8u, dst_len = sd.dst_len;
+    uint32_t bitpos = 0, n = 0, out = 0;
+    int err = 0;
+    bool done = false;
+    while (!done && out < dst_len) {
+        // ---- fetch: one big-endian word per lane covering [bitpos .. bitpos + 32*12) bits
+        const uint32_t w0 = bitpos >> 5;
+        uint32_t wbe = 0;
+        {
+            const uint32_t bo = (w0 + lane) * 4;
+            if (bo + 4 <= sd.src_len) {
+                const uint8_t* p = src + bo;
+                wbe = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+            } else {
+                for (uint32_t j = 0; j < 4; j++)
+                    if (bo + j < sd.src_len) wbe |= (uint32_t)src[bo + j] << (24 - 8 * j);
+            }
+        }
+        const uint32_t k = n + lane;                                   // code index inside the segment
+        const uint32_t my_bit = bitpos + lzw_cum_bits(k) - lzw_cum_bits(n);
+        const uint32_t wd = lzw_width(k);
+        const uint32_t rel = my_bit - (w0 << 5);
+        const uint32_t hi = __shfl_sync(0xffffffffu, wbe, (rel >> 5) & 31);
+        const uint32_t lo = __shfl_sync(0xffffffffu, wbe, ((rel >> 5) + 1) & 31);
+        const uint64_t win = ((uint64_t)hi << 32) | lo;
+        uint32_t code = (uint32_t)((win << (rel & 31)) >> (64 - wd));
+        const bool in_input = (my_bit + wd <= src_bits) && ((rel >> 5) + 1 < 32);
+        const bool avail = in_input && (k < kLzwMaxCodes);
+        if (!avail) code = 257;                                        // running out of input behaves like EOI
+        const bool is_ctl = (code == 256) || (code == 257);
+        const uint32_t ctl_mask = __ballot_sync(0xffffffffu, is_ctl);
+        const int m = ctl_mask ? (__ffs(ctl_mask) - 1) : 32;           // ordinary codes this round
+        // ---- lengths
+        uint32_t len = 0;
+        int32_t dep = -1;                                              // lane this string's length depends on
+        bool bad = false;
+        uint32_t e = 0;
+        if (lane < m) {
+            if (code < 256) {
+                len = 1;
+            } else {
+                e = code - 258;
+                if (k == 0 || e + 1 > k) bad = true;                   // first code after Clear must be a literal; entry must exist
+                else if (e < n) len = sm->offs[e + 1] - sm->offs[e] + 1;
+                else dep = (int32_t)(e - n);
+            }
+        }
+        if (__ballot_sync(0xffffffffu, bad)) { err = 2; break; }
+        for (int it = 0; it < 32; it++) {
+            const uint32_t pend = __ballot_sync(0xffffffffu, dep >= 0);
+            if (!pend) break;
+            const uint32_t ld = __shfl_sync(0xffffffffu, len, dep >= 0 ? dep : 0);
+            const bool dep_ready = dep >= 0 && !((pend >> dep) & 1u);
+            if (dep_ready) {
+                len = ld + 1;
+                dep = -1 - dep;                                        // remember the lane (as -1-lane) for the source offset
+            }
+        }
+        // ---- offsets (inclusive warp scan)
+        uint32_t incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t my_off = out + incl - len;
+        uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        int32_t srcv;
+        if (lane < m) {
+            if (code < 256) srcv = -1 - (int32_t)code;
+            else if (e < n) srcv = (int32_t)sm->offs[e];
+            else srcv = 0;  // fixed below from the producing lane's offset
+        } else srcv = -1;
+        {
+            const int dl = (dep < -1 || (dep == -1 && false)) ? (-1 - dep) : 0;
+            const uint32_t so = __shfl_sync(0xffffffffu, my_off, dl);
+            if (lane < m && code >= 256 && e >= n) srcv = (int32_t)so;
+        }
+        if (lane < m) sm->offs[k] = my_off;
+        if (lane == 0) sm->offs[n + m] = out + tot;
+        sm->b_off[lane] = (lane < m) ? my_off : (out + tot);
+        sm->b_src[lane] = srcv;
+        if (lane == 0) sm->b_off[32] = out + tot;
+        __syncwarp();
+        if (tot > dst_len - out) tot = dst_len - out;                  // libtiff truncates the last string
+        // ---- bytes: each output byte chases its chain down to a literal or to already-written output
+        for (uint32_t base = 0; base < tot; base += 32) {
+            const uint32_t idx = base + lane;
+            if (idx < tot) {
+                uint32_t p = out + idx;
+                uint32_t val = 0;
+                for (int hop = 0; hop < 64; hop++) {
+                    int lo_l = 0, hi_l = m;                            // owner = last lane with b_off <= p
+                    while (hi_l - lo_l > 1) {
+                        const int mid = (lo_l + hi_l) >> 1;
+                        if (sm->b_off[mid] <= p) lo_l = mid; else hi_l = mid;
+                    }
+                    const int32_t s = sm->b_src[lo_l];
+                    if (s < 0) { val = (uint32_t)(-1 - s); break; }
+                    const uint32_t q = (uint32_t)s + (p - sm->b_off[lo_l]);
+                    if (q < out) { val = dst[q]; break; }
+                    p = q;
+                }
+                dst[out + idx] = (uint8_t)val;
+            }
+        }
+        __syncwarp();
+        out += tot;
+        bitpos += lzw_cum_bits(n + m) - lzw_cum_bits(n);
+        n += m;
+        if (m < 32) {                                                  // a control code stopped the round
+            const uint32_t cc = __shfl_sync(0xffffffffu, code, m);
+            const uint32_t cw = __shfl_sync(0xffffffffu, wd, m);
+            if (cc == 256) { bitpos += cw; n = 0; }
+            else done = true;
+        }
+    }
+    if (err == 0 && out < dst_len) err = 1;                            // stream ended early / table overflow
+    if (err && lane == 0) set_status(status, sd.image, 10 + err);
+}
+
+// ================================================================================================ DEFLATE
+struct InfWarpSmem {
+    uint16_t lit_lut[1024];   // (symbol << 4) | length, 0 = not a short code
+    uint16_t dist_lut[256];
+    uint16_t lit_count[16], dist_count[16];
+    uint16_t lit_sym[288], dist_sym[32];
+    uint8_t lens[320];
+    uint16_t cl_lut[128];
+};
+constexpr int kInfWarps = 4;
+
+struct BitReader {
+    const uint8_t* src;
+    uint32_t len, pos;
+    uint64_t buf;
+    int cnt;
+    __device__ __forceinline__ void refill() {
+        while (cnt <= 32) {
+            uint32_t w = 0;
+            if (pos + 4 <= len) {
+                w = (uint32_t)src[pos] | ((uint32_t)src[pos + 1] << 8) | ((uint32_t)src[pos + 2] << 16) | ((uint32_t)src[pos + 3] << 24);
+            } else {
+                for (uint32_t j = 0; j < 4; j++)
+                    if (pos + j < len) w |= (uint32_t)src[pos + j] << (8 * j);
+            }
+            buf |= (uint64_t)w << cnt;
+            pos += 4;
+            cnt += 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1)); }
+    __device__ __forceinline__ void drop(int n) { buf >>= n; cnt -= n; }
+    __device__ __forceinline__ uint32_t take(int n) { uint32_t v = peek(n); drop(n); return v; }
+    // true once more bits were consumed than the stream holds
+    __device__ __forceinline__ bool overrun() const { return (int64_t)pos * 8 - cnt > (int64_t)len * 8; }
+};
+
+// Build LUT (root_bits) + canonical count/symbol arrays from code lengths lens[0..n).  Warp-cooperative.
+// Returns false for an over-subscribed code.
+__device__ bool build_huffman(const uint8_t* lens, int n, uint16_t* lut, int root_bits, uint16_t* count, uint16_t* syms, int lane) {
+    for (int i = lane; i < (1 << root_bits); i += 32) lut[i] = 0;
+    if (lane < 16) count[lane] = 0;
+    __syncwarp();
+    // counts and canonical first codes (serial: tiny)
+    uint32_t first[16], offs[16];
+    if (lane == 0) {
+        for (int i = 0; i < n; i++) count[lens[i]]++;
+        count[0] = 0;
+    }
+    __syncwarp();
+    int left = 1;
+    uint32_t code = 0, off = 0;
+    bool ok = true;
+    for (int l = 1; l < 16; l++) {
+        left = (left << 1) - (int)count[l];
+        if (left < 0) ok = false;
+        first[l] = code;
+        offs[l] = off;
+        code = (code + count[l]) << 1;
+        off += count[l];
+    }
+    if (!ok) return false;
+    // symbols sorted by (length, value); rank inside a length = number of earlier symbols of the same length
+    for (int s = lane; s < n; s += 32) {
+        const int l = lens[s];
+        if (!l) continue;
+        int rank = 0;
+        for (int t = 0; t < s; t++) rank += (lens[t] == l);
+        syms[offs[l] + rank] = (uint16_t)s;
+        if (l <= root_bits) {
+            uint32_t c = first[l] + rank;                     // canonical code, MSB first
+            uint32_t r = __brev(c) >> (32 - l);               // as it appears in the LSB-first bit stream
+            for (uint32_t i = r; i < (1u << root_bits); i += (1u << l)) lut[i] = (uint16_t)((s << 4) | l);
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
+// canonical bit-by-bit decode for codes longer than the LUT root (puff-style)
+__device__ __forceinline__ int decode_slow(BitReader& br, const uint16_t* count, const uint16_t* syms) {
+    int code = 0, first = 0, index = 0;
+    for (int l = 1; l < 16; l++) {
+        code |= (int)br.take(1);
+        const int c = count[l];
+        if (code - c < first) return syms[index + (code - first)];
+        index += c;
+        first += c;
+        first <<= 1;
+        code <<= 1;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ int decode_sym(BitReader& br, const uint16_t* lut, int root_bits, const uint16_t* count, const uint16_t* syms) {
+    br.refill();
+    const uint16_t e = lut[br.peek(root_bits)];
+    if (e) {
+        br.drop(e & 15);
+        return e >> 4;
+    }
+    return decode_slow(br, count, syms);
+}
+
+__constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+__global__ void __launch_bounds__(kInfWarps * 32)
+inflate_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ streams, const int* __restrict__ order,
+               int n_streams, uint8_t* __restrict__ scratch, int32_t* __restrict__ status) {
+    __shared__ InfWarpSmem smem[kInfWarps];
+    InfWarpSmem* sm = smem + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int wi = blockIdx.x * kInfWarps + (threadIdx.x >> 5);
+    if (wi >= n_streams) return;
+    const b2_stream_desc sd = streams[order ? order[wi] : wi];
+    if (sd.codec != CODEC_ZLIB) return;
+    uint8_t* dst = scratch + sd.dst_off;
+    const uint32_t dst_len = sd.dst_len;
+    BitReader br{blob + sd.src_off, sd.src_len, 0, 0, 0};
+    int err = 0;
+    uint32_t out = 0;
+    // zlib header (RFC 1950)
+    br.refill();
+    {
+        const uint32_t cmf = br.take(8), flg = br.take(8);
+        if ((cmf & 15) != 8 || ((cmf << 8) | flg) % 31 != 0 || (flg & 0x20)) err = 1;
+    }
+    uint32_t npend = 0, mylit = 0;        // literals gathered for one coalesced store
+    bool last = false;
+    while (!err && !last) {
+        br.refill();
+        last = br.take(1);
+        const uint32_t type = br.take(2);
+        if (type == 0) {                  // stored
+            br.drop(br.cnt & 7);
+            br.refill();
+            const uint32_t ln = br.take(16), nln = br.take(16);
+            if ((ln ^ 0xFFFFu) != nln) { err = 2; break; }
+            // flush pending literals first
+            if (npend) { if (lane < npend) dst[out + lane] = (uint8_t)mylit; out += npend; npend = 0; }
+            if (ln > dst_len - out) { err = 3; break; }
+            // bytes still in the bit buffer belong to the stored data
+            const uint32_t start = br.pos - (uint32_t)(br.cnt >> 3);
+            if (start + ln > br.len) { err = 4; break; }
+            for (uint32_t i = lane; i < ln; i += 32) dst[out + i] = br.src[start + i];
+            out += ln;
+            br.pos = start + ln;
+            br.buf = 0;
+            br.cnt = 0;
+            __syncwarp();
+            continue;
+        }
+        if (type == 3) { err = 5; break; }
+        int nlit, ndist;
+        if (type == 1) {                  // fixed Huffman
+            for (int i = lane; i < 288; i += 32) sm->lens[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
+            for (int i = lane; i < 30; i += 32) sm->lens[288 + i] = 5;
+            nlit = 288;
+            ndist = 30;
+            __syncwarp();
+        } else {                          // dynamic Huffman
+            br.refill();
+            nlit = (int)br.take(5) + 257;
+            ndist = (int)br.take(5) + 1;
+            const int ncl = (int)br.take(4) + 4;
+            if (nlit > 286 || ndist > 30) { err = 6; break; }
+            __shared__ uint8_t cl_lens_all[kInfWarps][19];
+            uint8_t* cl_lens = cl_lens_all[threadIdx.x >> 5];
+            if (lane < 19) cl_lens[lane] = 0;
+            __syncwarp();
+            for (int i = 0; i < ncl; i++) {
+                br.refill();
+                const uint32_t v = br.take(3);
+                if (lane == 0) cl_lens[c_cl_order[i]] = (uint8_t)v;
+            }
+            __syncwarp();
+            __shared__ uint16_t cl_cnt_all[kInfWarps][16], cl_sym_all[kInfWarps][19];
+            if (!build_huffman(cl_lens, 19, sm->cl_lut, 7, cl_cnt_all[threadIdx.x >> 5], cl_sym_all[threadIdx.x >> 5], lane)) { err = 7; break; }
+            int idx = 0;
+            int prev = 0;
+            while (idx < nlit + ndist) {
+                br.refill();
+                const uint16_t e = sm->cl_lut[br.peek(7)];
+                if (!e) { err = 8; break; }
+                br.drop(e & 15);
+                const int sym = e >> 4;
+                int rep = 1, val = sym;
+                if (sym == 16) { if (idx == 0) { err = 9; break; } val = prev; rep = 3 + (int)br.take(2); }
+                else if (sym == 17) { val = 0; rep = 3 + (int)br.take(3); }
+                else if (sym == 18) { val = 0; rep = 11 + (int)br.take(7); }
+                if (idx + rep > nlit + ndist) { err = 10; break; }
+                // lens layout: [0,nlit) literal/length, [288, 288+ndist) distance
+                for (int j = lane; j < rep; j += 32) {
+                    const int t = idx + j;
+                    sm->lens[t < nlit ? t : 288 + (t - nlit)] = (uint8_t)val;
+                }
+                idx += rep;
+                prev = val;
+            }
+            if (err) break;
+            __syncwarp();
+            if (sm->lens[256] == 0) { err = 11; break; }
+        }
+        if (!build_huffman(sm->lens, nlit, sm->lit_lut, 10, sm->lit_count, sm->lit_sym, lane)) { err = 12; break; }
+        if (!build_huffman(sm->lens + 288, ndist, sm->dist_lut, 8, sm->dist_count, sm->dist_sym, lane)) { err = 13; break; }
+        // ---- symbols
+        while (true) {
+            const int sym = decode_sym(br, sm->lit_lut, 10, sm->lit_count, sm->lit_sym);
+            if (sym < 0) { err = 14; break; }
+            if (sym < 256) {
+                if (lane == npend) mylit = (uint32_t)sym;
+                if (++npend == 32) {
+                    if (out + 32 > dst_len) { err = 3; break; }
+                    dst[out + lane] = (uint8_t)mylit;
+                    out += 32;
+                    npend = 0;
+                    __syncwarp();
+                }
+                continue;
+            }
+            if (npend) {
+                if (out + npend > dst_len) { err = 3; break; }
+                if (lane < npend) dst[out + lane] = (uint8_t)mylit;
+                out += npend;
+                npend = 0;
+                __syncwarp();
+            }
+            if (sym == 256) break;
+            const int li = sym - 257;
+            if (li >= 29) { err = 15; break; }
+            br.refill();
+            const uint32_t mlen = c_len_base[li] + br.take(c_len_extra[li]);
+            const int ds = decode_sym(br, sm->dist_lut, 8, sm->dist_count, sm->dist_sym);
+            if (ds < 0 || ds >= 30) { err = 16; break; }
+            br.refill();
+            const uint32_t dist = c_dist_base[ds] + br.take(c_dist_extra[ds]);
+            if (dist > out) { err = 17; break; }
+            if (mlen > dst_len - out) { err = 3; break; }
+            // overlapped copies repeat the last `dist` bytes periodically: every source byte is already written
+            for (uint32_t i = lane; i < mlen; i += 32) dst[out + i] = dst[out - dist + (dist >= mlen ? i : i % dist)];
+            out += mlen;
+            __syncwarp();
+            if (br.overrun()) { err = 18; break; }
+        }
+    }
+    if (!err && npend) {
+        if (out + npend > dst_len) err = 3;
+        else { if (lane < npend) dst[out + lane] = (uint8_t)mylit; out += npend; }
+    }
+    if (!err && out < dst_len) err = 19;          // fewer bytes than the image needs
+    if (err && lane == 0) set_status(status, sd.image, 20 + err);
+}
+
+// ================================================================================================ raw copy
+__global__ void __launch_bounds__(256)
+rawcopy_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ streams, int n_streams,
+               uint8_t* __restrict__ scratch, int32_t* __restrict__ status) {
+    const int si = blockIdx.y;
+    if (si >= n_streams) return;
+    const b2_stream_desc sd = streams[si];
+    if (sd.codec != CODEC_RAW) return;
+    if (sd.src_len < sd.dst_len) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) set_status(status, sd.image, 31);
+        return;
+    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < sd.dst_len; i += gridDim.x * blockDim.x)
+        scratch[sd.dst_off + i] = blob[sd.src_off + i];
+}
+
+// ================================================================================================ PNG un-filter
+// One warp per image.  Rows are processed in bands of 32; lane L owns row band*32+L and runs x = step - L, so
+// the row above is always exactly one pixel ahead: `up` arrives by shuffle from lane L-1, `up-left` is the `up`
+// of the previous step, `left` is the lane's own previous result.
+__global__ void __launch_bounds__(128)
+png_unfilter_kernel(const uint8_t* __restrict__ scratch, const b2_image_desc* __restrict__ imgs, int n_images,
+                    uint8_t* __restrict__ out, int32_t* __restrict__ status) {
+    const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wi >= n_images) return;
+    const b2_image_desc im = imgs[wi];
+    if (im.format != 2) return;
+    if (status && status[wi] != 0) return;
+    const int bpp = im.samples, w = im.width, h = im.height;
+    const size_t rb = (size_t)w * bpp;
+    const uint8_t* src = scratch + im.scratch_off;
+    uint8_t* dst = out + im.out_off;
+    bool bad = false;
+    for (int band = 0; band < h; band += 32) {
+        const int row = band + lane;
+        const bool live = row < h;
+        const uint8_t* srow = src + (size_t)(live ? row : 0) * (rb + 1);
+        const int ft = live ? srow[0] : 0;
+        if (live && ft > 4) bad = true;
+        uint32_t left[4] = {0, 0, 0, 0}, upl[4] = {0, 0, 0, 0}, cur[4] = {0, 0, 0, 0};
+        const uint8_t* prow = (band > 0) ? dst + (size_t)(band - 1) * rb : nullptr;  // row above the band (lane 0)
+        for (int step = 0; step < w + 31; step++) {
+            const int x = step - lane;
+            const bool act = live && x >= 0 && x < w;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if (c >= bpp) break;
+                uint32_t up = __shfl_up_sync(0xffffffffu, cur[c], 1);     // lane L-1's pixel x (computed last step)
+                if (lane == 0) up = (prow && x >= 0 && x < w) ? prow[(size_t)x * bpp + c] : 0;
+                if (act) {
+                    const uint32_t raw = srow[1 + (size_t)x * bpp + c];
+                    const uint32_t a = left[c], b = up, cc = upl[c];
+                    uint32_t pred;
+                    if (ft == 0) pred = 0;
+                    else if (ft == 1) pred = a;
+                    else if (ft == 2) pred = b;
+                    else if (ft == 3) pred = (a + b) >> 1;
+                    else {
+                        const int p = (int)a + (int)b - (int)cc;
+                        const int pa = abs(p - (int)a), pb = abs(p - (int)b), pc = abs(p - (int)cc);
+                        pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : cc);
+                    }
+                    const uint32_t v = (raw + pred) & 0xFFu;
+                    dst[(size_t)row * rb + (size_t)x * bpp + c] = (uint8_t)v;
+                    left[c] = v;
+                    upl[c] = b;
+                    cur[c] = v;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (__ballot_sync(0xffffffffu, bad) && lane == 0) set_status(status, wi, 41);
+}
+
+// ================================================================================================ TIFF assembly
+// predictor 2 undo, in place on the decoded block scratch: one warp per block row, one channel at a time,
+// chunked warp scan (each lane sums a run of pixels, exclusive scan across lanes, then rewrites its run).
+template <typename T>
+__device__ __forceinline__ T load_sample(const uint8_t* p, bool swap) {
+    T v;
+    memcpy(&v, p, sizeof(T));
+    if (swap) {
+        if (sizeof(T) == 2) v = (T)__byte_perm((uint32_t)v, 0, 0x0001);
+        else if (sizeof(T) == 4) v = (T)__byte_perm((uint32_t)v, 0, 0x0123);
+    }
+    return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+hdiff_undo_kernel(uint8_t* __restrict__ scratch, const b2_image_desc* __restrict__ imgs, int img_index,
+                  const int32_t* __restrict__ status) {
+    const b2_image_desc im = imgs[img_index];
+    if (status && status[img_index] != 0) return;
+    const int planes = im.planar == 2 ? im.samples : 1;
+    const int spb = im.planar == 2 ? 1 : im.samples;
+    const long long rows_total = (long long)im.blocks_across * im.blocks_down * planes * im.block_h;
+    const long long wrow = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wrow >= rows_total) return;
+    const long long blk = wrow / im.block_h;
+    const int ry = (int)(wrow % im.block_h);
+    uint8_t* base = scratch + im.scratch_off + (uint64_t)blk * im.block_bytes + (uint64_t)ry * im.block_w * spb * sizeof(T);
+    const bool swap = im.big_endian && sizeof(T) > 1;
+    const int bw = im.block_w;
+    const int per = (bw + 31) / 32;
+    const int x0 = lane * per, x1 = min(bw, x0 + per);
+    for (int c = 0; c < spb; c++) {
+        T sum = 0;
+        for (int x = x0; x < x1; x++) sum += load_sample<T>(base + ((size_t)x * spb + c) * sizeof(T), swap);
+        T incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const T t = (T)__shfl_up_sync(0xffffffffu, (uint32_t)incl, o);
+            if (lane >= o) incl += t;
+        }
+        T run = incl - sum;
+        for (int x = x0; x < x1; x++) {
+            uint8_t* p = base + ((size_t)x * spb + c) * sizeof(T);
+            run += load_sample<T>(p, swap);
+            T v = run;                                             // store back in FILE byte order; assemble swaps once
+            if (swap) {
+                if (sizeof(T) == 2) v = (T)__byte_perm((uint32_t)v, 0, 0x0001);
+                else if (sizeof(T) == 4) v = (T)__byte_perm((uint32_t)v, 0, 0x0123);
+            }
+            memcpy(p, &v, sizeof(T));
+        }
+    }
+}
+
+// gather decoded blocks into the final (H,W,samples) array: crop edge blocks, interleave planes, fix byte order
+__global__ void __launch_bounds__(256)
+assemble_kernel(const uint8_t* __restrict__ scratch, const b2_image_desc* __restrict__ imgs, int n_images,
+                uint8_t* __restrict__ out, const int32_t* __restrict__ status) {
+    const int ii = blockIdx.y;
+    if (ii >= n_images) return;
+    const b2_image_desc im = imgs[ii];
+    if (im.format != 1) return;
+    if (status && status[ii] != 0) return;
+    const int bs = im.bytes_per_sample;
+    const int S = im.samples, Wd = im.width, Hd = im.height;
+    const uint8_t* src = scratch + im.scratch_off;
+    uint8_t* dst = out + im.out_off;
+    const bool fast = (im.planar == 1) && !(im.big_endian && bs > 1);
+    if (fast) {
+        // row segments are contiguous in both layouts: copy bytes; one loop index = one output byte-quad
+        const uint64_t rowbytes = (uint64_t)Wd * S * bs;
+        const uint64_t total = rowbytes * Hd;
+        const uint64_t blk_rowbytes = (uint64_t)im.block_w * S * bs;
+        for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < total; i += (uint64_t)gridDim.x * blockDim.x * 4) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint64_t o = i + j;
+                if (o >= total) break;
+                const uint32_t y = (uint32_t)(o / rowbytes);
+                const uint64_t xb = o - (uint64_t)y * rowbytes;
+                const uint32_t bx = (uint32_t)(xb / blk_rowbytes), by = y / im.block_h;
+                const uint64_t inb = xb - (uint64_t)bx * blk_rowbytes;
+                const uint64_t so = ((uint64_t)by * im.blocks_across + bx) * im.block_bytes + (uint64_t)(y - by * im.block_h) * blk_rowbytes + inb;
+                v |= (uint32_t)src[so] << (8 * j);
+            }
+            if (i + 4 <= total && ((reinterpret_cast<uintptr_t>(dst) + i) & 3) == 0) {
+                *reinterpret_cast<uint32_t*>(dst + i) = v;
+            } else {
+                for (int j = 0; j < 4 && i + j < total; j++) dst[i + j] = (uint8_t)(v >> (8 * j));
+            }
+        }
+        return;
+    }
+    const uint64_t n_samples = (uint64_t)Wd * Hd * S;
+    const int spb = im.planar == 2 ? 1 : S;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_samples; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(i % S);
+        const uint64_t pix = i / S;
+        const uint32_t x = (uint32_t)(pix % Wd), y = (uint32_t)(pix / Wd);
+        const uint32_t bx = x / im.block_w, by = y / im.block_h;
+        const uint32_t plane = im.planar == 2 ? c : 0, cc = im.planar == 2 ? 0 : c;
+        const uint64_t blk = ((uint64_t)plane * im.blocks_down + by) * im.blocks_across + bx;
+        const uint64_t so = blk * im.block_bytes + (((uint64_t)(y - by * im.block_h) * im.block_w + (x - bx * im.block_w)) * spb + cc) * bs;
+        const uint8_t* p = src + so;
+        uint8_t* q = dst + i * bs;
+        if (im.big_endian) for (int j = 0; j < bs; j++) q[j] = p[bs - 1 - j];
+        else for (int j = 0; j < bs; j++) q[j] = p[j];
+    }
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_decode_streams(b2_ctx* ctx, const uint8_t* blob, const b2_stream_desc* streams, int n_streams,
+                                 uint32_t codec_mask, uint32_t max_raw_len, uint8_t* scratch, int32_t* status, b2_stream stream) {
+    B2_REQUIRE(ctx && blob && streams && scratch && status, "b2_decode_streams: NULL argument");
+    if (n_streams <= 0) return 0;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (codec_mask & 1u) {   // LZW
+        const size_t smem = sizeof(LzwWarpSmem) * kLzwWarps;
+        static bool attr_set[64] = {false};
+        if (!attr_set[ctx->device & 63]) {
+            B2_CUDA(cudaFuncSetAttribute(lzw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set[ctx->device & 63] = true;
+        }
+        lzw_kernel<<<(n_streams + kLzwWarps - 1) / kLzwWarps, kLzwWarps * 32, smem, s>>>(blob, streams, nullptr, n_streams, scratch, status);
+        ctx->launches++;
+        B2_CUDA(cudaGetLastError());
+    }
+    if (codec_mask & 2u) {   // zlib / DEFLATE
+        inflate_kernel<<<(n_streams + kInfWarps - 1) / kInfWarps, kInfWarps * 32, 0, s>>>(blob, streams, nullptr, n_streams, scratch, status);
+        ctx->launches++;
+        B2_CUDA(cudaGetLastError());
+    }
+    if (codec_mask & 4u) {   // uncompressed
+        unsigned gx = (max_raw_len + 256 * 16 - 1) / (256 * 16);
+        if (gx < 1) gx = 1;
+        if (gx > 64) gx = 64;
+        for (int s0 = 0; s0 < n_streams; s0 += 65535) {
+            const int m = n_streams - s0 < 65535 ? n_streams - s0 : 65535;
+            rawcopy_kernel<<<dim3(gx, m), 256, 0, s>>>(blob, streams + s0, m, scratch, status);
+            ctx->launches++;
+        }
+        B2_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" int b2_assemble_images(b2_ctx* ctx, uint8_t* scratch, const b2_image_desc* imgs_dev, const b2_image_desc* imgs_host,
+                                  int n_images, uint8_t* out, int32_t* status, b2_stream stream) {
+    B2_REQUIRE(ctx && scratch && imgs_dev && imgs_host && out && status, "b2_assemble_images: NULL argument");
+    if (n_images <= 0) return 0;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    bool any_png = false, any_tiff = false;
+    uint64_t max_bytes = 0;
+    for (int i = 0; i < n_images; i++) {
+        const b2_image_desc& im = imgs_host[i];
+        if (im.format == 2) any_png = true;
+        if (im.format == 1) {
+            any_tiff = true;
+            const uint64_t nb = (uint64_t)im.width * im.height * im.samples * im.bytes_per_sample;
+            if (nb > max_bytes) max_bytes = nb;
+            if (im.predictor == 2) {
+                const int planes = im.planar == 2 ? im.samples : 1;
+                const long long rows = (long long)im.blocks_across * im.blocks_down * planes * im.block_h;
+                const unsigned grid = (unsigned)((rows * 32 + 127) / 128);
+                switch (im.bytes_per_sample) {
+                    case 1: hdiff_undo_kernel<uint8_t><<<grid, 128, 0, s>>>(scratch, imgs_dev, i, status); break;
+                    case 2: hdiff_undo_kernel<uint16_t><<<grid, 128, 0, s>>>(scratch, imgs_dev, i, status); break;
+                    case 4: hdiff_undo_kernel<uint32_t><<<grid, 128, 0, s>>>(scratch, imgs_dev, i, status); break;
+                    default: return fail("b2_assemble_images: predictor 2 needs 8/16/32-bit samples");
+                }
+                ctx->launches++;
+            }
+        }
+    }
+    B2_CUDA(cudaGetLastError());
+    if (any_tiff) {
+        unsigned gx = (unsigned)((max_bytes / 4 + 255) / 256);
+        if (gx < 1) gx = 1;
+        if (gx > 256) gx = 256;
+        for (int s0 = 0; s0 < n_images; s0 += 65535) {
+            const int m = n_images - s0 < 65535 ? n_images - s0 : 65535;
+            assemble_kernel<<<dim3(gx, m), 256, 0, s>>>(scratch, imgs_dev + s0, m, out, status + s0);
+            ctx->launches++;
+        }
+        B2_CUDA(cudaGetLastError());
+    }
+    if (any_png) {
+        png_unfilter_kernel<<<(n_images * 32 + 127) / 128, 128, 0, s>>>(scratch, imgs_dev, n_images, out, status);
+        ctx->launches++;
+        B2_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+// ================================================================================================ host parsers
+namespace {
+struct Rd {
+    const uint8_t* b;
+    uint64_t n;
+    bool be;
+    bool ok(uint64_t o, uint64_t k) const { return o <= n && k <= n - o; }
+    uint16_t u16(uint64_t o) const { return be ? (uint16_t)((b[o] << 8) | b[o + 1]) : (uint16_t)(b[o] | (b[o + 1] << 8)); }
+    uint32_t u32(uint64_t o) const {
+        return be ? ((uint32_t)b[o] << 24) | ((uint32_t)b[o + 1] << 16) | ((uint32_t)b[o + 2] << 8) | b[o + 3]
+                  : (uint32_t)b[o] | ((uint32_t)b[o + 1] << 8) | ((uint32_t)b[o + 2] << 16) | ((uint32_t)b[o + 3] << 24);
+    }
+};
+const int kTypeSize[17] = {0, 1, 1, 2, 4, 8, 1, 1, 2, 4, 8, 4, 8, 0, 0, 0, 8};
+
+struct TiffTags {
+    uint32_t width = 0, height = 0, compression = 1, spp = 1, planar = 1, predictor = 1, fill_order = 1;
+    uint32_t bps = 1, fmt = 1, tile_w = 0, tile_h = 0, rps = 0;
+    bool mixed = false, has_size = false;
+    uint64_t off_pos = 0, off_cnt = 0, cnt_pos = 0, cnt_cnt = 0;
+    int off_type = 0, cnt_type = 0;
+    bool has_nodata = false;
+    double nodata = 0;
+};
+
+// value i of an IFD entry of SHORT/LONG type
+uint32_t entry_val(const Rd& r, int type, uint64_t pos, uint64_t i) { return type == 3 ? r.u16(pos + 2 * i) : r.u32(pos + 4 * i); }
+
+int parse_tiff(const uint8_t* blob, uint64_t size, TiffTags& t, Rd& r) {
+    if (size < 8) return 2;
+    r.b = blob; r.n = size;
+    if (blob[0] == 'I' && blob[1] == 'I') r.be = false;
+    else if (blob[0] == 'M' && blob[1] == 'M') r.be = true;
+    else return 2;
+    if (r.u16(2) != 42) return 3;                       // BigTIFF / unknown
+    const uint64_t ifd = r.u32(4);
+    if (!r.ok(ifd, 2)) return 2;
+    const uint32_t n = r.u16(ifd);
+    if (!r.ok(ifd + 2, (uint64_t)n * 12)) return 2;
+    bool hw = false, hh = false;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint64_t e = ifd + 2 + 12ull * i;
+        const uint32_t tag = r.u16(e), type = r.u16(e + 2), cnt = r.u32(e + 4);
+        if (type == 0 || type > 16 || kTypeSize[type] == 0) continue;
+        const uint64_t nb = (uint64_t)kTypeSize[type] * cnt;
+        const uint64_t pos = nb <= 4 ? e + 8 : r.u32(e + 8);
+        if (!r.ok(pos, nb)) return 2;
+        auto v0 = [&]() -> uint32_t { return (type == 3) ? r.u16(pos) : (type == 4 ? r.u32(pos) : (type == 1 ? blob[pos] : 0)); };
+        switch (tag) {
+            case 256: t.width = v0(); hw = true; break;
+            case 257: t.height = v0(); hh = true; break;
+            case 258:
+                t.bps = v0();
+                for (uint32_t k = 1; k < cnt; k++) if (entry_val(r, type, pos, k) != t.bps) t.mixed = true;
+                break;
+            case 259: t.compression = v0(); break;
+            case 266: t.fill_order = v0(); break;
+            case 277: t.spp = v0(); break;
+            case 278: t.rps = v0(); break;
+            case 284: t.planar = v0(); break;
+            case 317: t.predictor = v0(); break;
+            case 322: t.tile_w = v0(); break;
+            case 323: t.tile_h = v0(); break;
+            case 339:
+                t.fmt = v0();
+                for (uint32_t k = 1; k < cnt; k++) if (entry_val(r, type, pos, k) != t.fmt) t.mixed = true;
+                break;
+            case 273: case 324: t.off_pos = pos; t.off_cnt = cnt; t.off_type = type; break;
+            case 279: case 325: t.cnt_pos = pos; t.cnt_cnt = cnt; t.cnt_type = type; break;
+            case 42113: {
+                std::string s(reinterpret_cast<const char*>(blob + pos), (size_t)nb);
+                t.has_nodata = true;
+                t.nodata = atof(s.c_str());
+            } break;
+            default: break;
+        }
+    }
+    t.has_size = hw && hh;
+    return 0;
+}
+
+int tiff_dtype(uint32_t bps, uint32_t fmt) {
+    if (bps == 8) return fmt == 2 ? B2_I8 : (fmt == 1 ? B2_U8 : -1);
+    if (bps == 16) return fmt == 1 ? B2_U16 : (fmt == 2 ? B2_I16 : -1);
+    if (bps == 32) return fmt == 1 ? B2_U32 : (fmt == 2 ? B2_I32 : (fmt == 3 ? B2_F32 : -1));
+    if (bps == 64) return fmt == 3 ? B2_F64 : -1;
+    return -1;
+}
+const uint8_t kPngSig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+}  // namespace
+
+// Header-only probe: what load_image_rasterio(decode=False) reads (_img_to_tf_mp.py:51-53) plus what the
+// decoder needs.  info->status: 0 ok, 2 corrupt header, 3 unsupported flavour.
+extern "C" int b2_image_probe(const uint8_t* blob, uint64_t size, b2_image_info* info) {
+    B2_REQUIRE(blob && info, "b2_image_probe: NULL argument");
+    memset(info, 0, sizeof(*info));
+    if (size >= 8 && memcmp(blob, kPngSig, 8) == 0) {
+        info->format = 2;
+        uint64_t p = 8;
+        bool ihdr = false;
+        int n_idat = 0;
+        while (p + 8 <= size) {
+            const uint64_t n = ((uint64_t)blob[p] << 24) | (blob[p + 1] << 16) | (blob[p + 2] << 8) | blob[p + 3];
+            if (p + 12 + n > size) { info->status = 2; return 0; }
+            if (memcmp(blob + p + 4, "IHDR", 4) == 0 && n >= 13) {
+                const uint8_t* d = blob + p + 8;
+                info->width = (int32_t)(((uint32_t)d[0] << 24) | (d[1] << 16) | (d[2] << 8) | d[3]);
+                info->height = (int32_t)(((uint32_t)d[4] << 24) | (d[5] << 16) | (d[6] << 8) | d[7]);
+                const int depth = d[8], ct = d[9], inter = d[12];
+                info->samples = ct == 0 ? 1 : (ct == 2 ? 3 : (ct == 4 ? 2 : (ct == 6 ? 4 : 0)));
+                info->dtype = B2_U8;
+                if (depth != 8 || info->samples == 0 || inter != 0) info->status = 3;
+                ihdr = true;
+            } else if (memcmp(blob + p + 4, "IDAT", 4) == 0) {
+                n_idat++;
+            } else if (memcmp(blob + p + 4, "IEND", 4) == 0) {
+                break;
+            }
+            p += 12 + n;
+        }
+        if (!ihdr || info->width <= 0 || info->height <= 0) { info->status = 2; return 0; }
+        info->n_blocks = n_idat;          // IDAT chunks to concatenate
+        info->block_w = info->width;
+        info->block_h = info->height;
+        info->blocks_across = info->blocks_down = 1;
+        info->planar = 1;
+        info->predictor = 1;
+        info->compression = 8;
+        info->block_bytes = (uint64_t)info->height * ((uint64_t)info->width * info->samples + 1);
+        if (n_idat == 0 && info->status == 0) info->status = 2;
+        return 0;
+    }
+    TiffTags t;
+    Rd r{};
+    const int pe = parse_tiff(blob, size, t, r);
+    if (pe) { info->status = pe; return 0; }
+    info->format = 1;
+    info->width = (int32_t)t.width;
+    info->height = (int32_t)t.height;
+    info->samples = (int32_t)t.spp;
+    info->dtype = tiff_dtype(t.bps, t.fmt);
+    info->compression = (int32_t)t.compression;
+    info->predictor = (int32_t)t.predictor;
+    info->planar = (int32_t)t.planar;
+    info->big_endian = r.be ? 1 : 0;
+    info->tiled = t.tile_w ? 1 : 0;
+    info->has_nodata = t.has_nodata;
+    info->nodata = t.nodata;
+    if (!t.has_size || t.width == 0 || t.height == 0 || t.spp == 0) { info->status = 2; return 0; }
+    if (info->dtype < 0 || t.mixed || t.fill_order != 1 || (t.planar != 1 && t.planar != 2) ||
+        !(t.compression == 1 || t.compression == 5 || t.compression == 8 || t.compression == 32946) ||
+        !(t.predictor == 1 || (t.predictor == 2 && t.bps <= 32 && t.fmt != 3))) {
+        info->status = 3;
+        return 0;
+    }
+    if (t.tile_w) { info->block_w = (int32_t)t.tile_w; info->block_h = (int32_t)t.tile_h; }
+    else { info->block_w = (int32_t)t.width; info->block_h = (int32_t)((t.rps == 0 || t.rps > t.height) ? t.height : t.rps); }
+    if (info->block_w <= 0 || info->block_h <= 0) { info->status = 2; return 0; }
+    info->blocks_across = (info->width + info->block_w - 1) / info->block_w;
+    info->blocks_down = (info->height + info->block_h - 1) / info->block_h;
+    const int planes = t.planar == 2 ? (int)t.spp : 1;
+    info->n_blocks = info->blocks_across * info->blocks_down * planes;
+    const uint64_t spb = t.planar == 2 ? 1 : t.spp;
+    info->block_bytes = (uint64_t)info->block_w * info->block_h * spb * (t.bps / 8);
+    if (t.off_cnt < (uint64_t)info->n_blocks || t.cnt_cnt < (uint64_t)info->n_blocks ||
+        (t.off_type != 3 && t.off_type != 4) || (t.cnt_type != 3 && t.cnt_type != 4)) { info->status = 2; return 0; }
+    return 0;
+}
+
+// Offsets / byte counts of the compressed blocks (TIFF tiles or strips, in file order) or of the IDAT chunk
+// payloads (PNG).  decoded_len[i] = bytes block i must produce (short last strip handled).
+extern "C" int b2_image_blocks(const uint8_t* blob, uint64_t size, const b2_image_info* info, uint64_t* offsets,
+                               uint64_t* counts, uint64_t* decoded_len, int cap) {
+    B2_REQUIRE(blob && info && offsets && counts && decoded_len, "b2_image_blocks: NULL argument");
+    B2_REQUIRE(info->status == 0, "b2_image_blocks: image was not probed successfully");
+    B2_REQUIRE(cap >= info->n_blocks, "b2_image_blocks: capacity too small");
+    if (info->format == 2) {
+        uint64_t p = 8;
+        int k = 0;
+        while (p + 8 <= size) {
+            const uint64_t n = ((uint64_t)blob[p] << 24) | (blob[p + 1] << 16) | (blob[p + 2] << 8) | blob[p + 3];
+            if (memcmp(blob + p + 4, "IDAT", 4) == 0 && k < cap) { offsets[k] = p + 8; counts[k] = n; decoded_len[k] = 0; k++; }
+            else if (memcmp(blob + p + 4, "IEND", 4) == 0) break;
+            p += 12 + n;
+        }
+        if (k) decoded_len[0] = info->block_bytes;
+        return 0;
+    }
+    TiffTags t;
+    Rd r{};
+    if (parse_tiff(blob, size, t, r)) return fail("b2_image_blocks: corrupt TIFF");
+    const uint64_t spb = t.planar == 2 ? 1 : t.spp;
+    const int per_plane = info->blocks_across * info->blocks_down;
+    for (int i = 0; i < info->n_blocks; i++) {
+        offsets[i] = entry_val(r, t.off_type, t.off_pos, i);
+        counts[i] = entry_val(r, t.cnt_type, t.cnt_pos, i);
+        if (!r.ok(offsets[i], counts[i])) return fail("b2_image_blocks: block outside the file");
+        uint64_t rows = info->block_h;
+        if (!info->tiled) {
+            const int by = (i % per_plane) / info->blocks_across;
+            const uint64_t left = (uint64_t)info->height - (uint64_t)by * info->block_h;
+            if (left < rows) rows = left;
+        }
+        decoded_len[i] = rows * info->block_w * spb * (t.bps / 8);
+    }
+    return 0;
+}
