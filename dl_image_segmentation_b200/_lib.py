@@ -84,6 +84,11 @@ _lock = threading.Lock()
 def register_signatures(extra):
     """Later modules (codec) add their entry points here before the library is first loaded."""
     SIGNATURES.update(extra)
+    if _lib is not None:
+        for name, (res, args) in extra.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
 
 
 def lib():

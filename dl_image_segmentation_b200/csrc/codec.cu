@@ -52,7 +52,7 @@ struct LzwWarpSmem {
 
 __global__ void __launch_bounds__(kLzwWarps * 32)
 lzw_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ streams, const int* __restrict__ order,
-           int n_streams, uint8_t* __restrict__ scratch, int32_t* __restrict__ status) {
+           int n_streams, uint8_t* scratch, int32_t* __restrict__ status) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     LzwWarpSmem* sm = reinterpret_cast<LzwWarpSmem*>(smem_raw) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -136,7 +136,7 @@ lzw_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ 
             else srcv = 0;  // fixed below from the producing lane's offset
         } else srcv = -1;
         {
-            const int dl = (dep < -1 || (dep == -1 && false)) ? (-1 - dep) : 0;
+            const int dl = dep < 0 ? (-1 - dep) : 0;                   // producing lane of an in-batch reference
             const uint32_t so = __shfl_sync(0xffffffffu, my_off, dl);
             if (lane < m && code >= 256 && e >= n) srcv = (int32_t)so;
         }
@@ -153,7 +153,7 @@ lzw_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ 
             if (idx < tot) {
                 uint32_t p = out + idx;
                 uint32_t val = 0;
-                for (int hop = 0; hop < 64; hop++) {
+                for (;;) {                                             // p strictly decreases: always terminates
                     int lo_l = 0, hi_l = m;                            // owner = last lane with b_off <= p
                     while (hi_l - lo_l > 1) {
                         const int mid = (lo_l + hi_l) >> 1;
@@ -295,7 +295,7 @@ __constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 
 
 __global__ void __launch_bounds__(kInfWarps * 32)
 inflate_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ streams, const int* __restrict__ order,
-               int n_streams, uint8_t* __restrict__ scratch, int32_t* __restrict__ status) {
+               int n_streams, uint8_t* scratch, int32_t* __restrict__ status) {
     __shared__ InfWarpSmem smem[kInfWarps];
     InfWarpSmem* sm = smem + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -414,7 +414,7 @@ inflate_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restric
                 npend = 0;
                 __syncwarp();
             }
-            if (sym == 256) break;
+            if (sym == 256) { if (br.overrun()) err = 18; break; }
             const int li = sym - 257;
             if (li >= 29) { err = 15; break; }
             br.refill();

@@ -164,6 +164,59 @@ typedef struct {
 int b2_tfrecord_build(b2_ctx* ctx, const b2_build_desc* descs_dev, int n, uint64_t max_record_bytes,
                       const uint8_t* scaffold_dev, uint8_t* out_dev, b2_stream stream);
 
+/* ------------------------------------------------------------------ K1: chip decode (TIFF LZW / DEFLATE / none, PNG)
+ * Replace rasterio MemoryFile(...).open().read() -> GDAL -> libtiff/libpng (_img_to_tf_mp.py:45-48,
+ * _tfrecord_image_translation.py:320-326,369-381) and tf.image.decode_png / tf.io.decode_image
+ * (_img_to_tf_threaded.py:59, _tfrecord_image_translation.py:283,289), including reshape_as_image
+ * (_img_to_tf_mp.py:69): the output is written (H,W,bands) directly.
+ */
+typedef struct {
+    int32_t format;      /* 1 TIFF, 2 PNG                                                                     */
+    int32_t width, height, samples; /* what src.width / src.height / src.count return (_img_to_tf_mp.py:51-53) */
+    int32_t dtype;       /* B2_U8 ...                                                                         */
+    int32_t compression; /* TIFF tag 259 (1 none, 5 LZW, 8/32946 DEFLATE); 8 for PNG                          */
+    int32_t predictor, planar, big_endian, tiled;
+    int32_t block_w, block_h, blocks_across, blocks_down;
+    int32_t n_blocks;    /* TIFF: tiles/strips (all planes); PNG: number of IDAT chunks                       */
+    int32_t status;      /* 0 ok, 2 corrupt header, 3 flavour out of scope                                    */
+    int32_t has_nodata, pad_;
+    double nodata;       /* GDAL_NODATA tag 42113 (_descartes_img_chips.py:794-795)                           */
+    uint64_t block_bytes; /* decoded bytes of one full block (PNG: h * (1 + w*samples) filtered bytes)        */
+} b2_image_info;
+
+/* Host-side header parse (TIFF IFD / PNG chunks); never touches the GPU. */
+int b2_image_probe(const uint8_t* blob, uint64_t size, b2_image_info* info);
+/* Host-side: offset / byte count / decoded length of each compressed block (TIFF) or IDAT payload (PNG). */
+int b2_image_blocks(const uint8_t* blob, uint64_t size, const b2_image_info* info, uint64_t* offsets,
+                    uint64_t* counts, uint64_t* decoded_len, int cap);
+
+typedef struct {         /* one compressed stream = one warp of work                                          */
+    uint64_t src_off;    /* offset in blob_dev                                                                */
+    uint64_t dst_off;    /* offset in scratch_dev                                                             */
+    uint32_t src_len;
+    uint32_t dst_len;    /* bytes the stream must decode to                                                   */
+    int32_t codec;       /* 1 stored, 5 LZW, 8 zlib                                                           */
+    int32_t image;       /* owning image: failures are reported in status_dev[image]                          */
+} b2_stream_desc;
+
+typedef struct {         /* one image to assemble from its decoded blocks                                     */
+    uint64_t scratch_off; /* first decoded block (blocks consecutive, block_bytes apart)                      */
+    uint64_t out_off;    /* where the (H,W,samples) array starts in out_dev                                   */
+    uint64_t block_bytes;
+    int32_t format, width, height, samples, bytes_per_sample, predictor, planar, big_endian;
+    int32_t block_w, block_h, blocks_across, blocks_down;
+} b2_image_desc;
+
+/* codec_mask: bit0 LZW, bit1 zlib, bit2 stored streams present.  status_dev (one int32 per image) must be
+ * zeroed by the caller; non-zero afterwards = that image failed to decode (skip it, _img_to_tf_mp.py:133-136). */
+int b2_decode_streams(b2_ctx* ctx, const uint8_t* blob_dev, const b2_stream_desc* streams_dev, int n_streams,
+                      uint32_t codec_mask, uint32_t max_raw_len, uint8_t* scratch_dev, int32_t* status_dev,
+                      b2_stream stream);
+/* TIFF: predictor-2 undo, byte order, plane interleave, edge-tile crop -> (H,W,samples).  PNG: un-filter. */
+int b2_assemble_images(b2_ctx* ctx, uint8_t* scratch_dev, const b2_image_desc* images_dev,
+                       const b2_image_desc* images_host, int n_images, uint8_t* out_dev, int32_t* status_dev,
+                       b2_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,150 @@
+"""-m gpu: K1 chip decode (TIFF LZW / DEFLATE / stored, PNG inflate + un-filter) through the C ABI vs the oracle.
+
+Bit-exact on every pixel.  Inputs come from three independent encoders: libtiff via cv2, libpng via Pillow,
+and the synthetic writers (GDAL-style tiled LZW, planar, big-endian, chosen PNG filters / deflate block types).
+"""
+import zlib
+
+import cv2
+import numpy as np
+import pytest
+
+import synthetic as syn
+from oracle import imagecodecs as oic
+
+pytestmark = pytest.mark.gpu
+
+
+def _decode(dev, blobs):
+    from dl_image_segmentation_b200 import _codec
+    arrays, status = _codec.decode_blobs(blobs, device=dev)
+    return [None if a is None else a.cpu().numpy() for a in arrays], list(status)
+
+
+def _check(dev, blobs, wants=None):
+    got, status = _decode(dev, blobs)
+    for i, b in enumerate(blobs):
+        want = oic.decode_image(b) if wants is None else wants[i]
+        assert status[i] == 0, (i, status[i])
+        assert got[i].dtype == want.dtype and got[i].shape == want.shape, (i, got[i].dtype, got[i].shape, want.shape)
+        np.testing.assert_array_equal(got[i], want, err_msg="image %d" % i)
+
+
+def test_gdal_style_tiled_lzw_chip_pairs(dev):
+    blobs, wants = [], []
+    for i in range(3):
+        img, lab, _ = syn.cfg3_chip(i)
+        blobs += [syn.tiff_bytes(img, tile=256), syn.tiff_bytes(lab, tile=256, nodata=255)]
+        wants += [img, lab[:, :, None]]
+    _check(dev, blobs, wants)
+
+
+def test_libtiff_encoded_strips_predictor2(dev):
+    img, lab, _ = syn.cfg3_chip(7, size=200)
+    ok, enc = cv2.imencode(".tif", img[..., [2, 1, 0, 3]], [cv2.IMWRITE_TIFF_COMPRESSION, 5])
+    ok2, encl = cv2.imencode(".tif", lab, [cv2.IMWRITE_TIFF_COMPRESSION, 5])
+    ok3, enc8 = cv2.imencode(".tif", (img[..., :3] >> 6).astype(np.uint8), [cv2.IMWRITE_TIFF_COMPRESSION, 5])
+    assert ok and ok2 and ok3
+    _check(dev, [enc.tobytes(), encl.tobytes(), enc8.tobytes()],
+           [img, lab[:, :, None], (img[..., :3] >> 6).astype(np.uint8)[..., ::-1]])
+
+
+@pytest.mark.parametrize("kw", [
+    dict(tile=None, predictor=2), dict(tile=128, predictor=2, planar=2), dict(tile=256, compression="deflate"),
+    dict(tile=None, compression="none", big_endian=True), dict(tile=256, big_endian=True, predictor=2),
+    dict(tile=64, planar=2), dict(tile=None, rows_per_strip=7, compression="deflate", predictor=2),
+    dict(tile=32, compression="none"), dict(tile=None, rows_per_strip=1000)])
+def test_tiff_variants(dev, kw):
+    img, lab, _ = syn.cfg3_chip(11, size=300)
+    img = img[:300, :280]
+    _check(dev, [syn.tiff_bytes(img, **kw), syn.tiff_bytes(lab[:77, :130], **kw)], [img, lab[:77, :130, None]])
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int16, np.uint32, np.float32, np.float64])
+def test_tiff_dtypes(dev, dtype):
+    rng = np.random.default_rng(8)
+    base = syn.smooth_field(rng, 150, 170)
+    img = (np.stack([base, base[::-1], base.T[:150, :170] if False else base * 0.5], -1) * 1000).astype(dtype)
+    kws = [dict(tile=64), dict(tile=None, compression="deflate")]
+    if np.issubdtype(dtype, np.integer):
+        kws.append(dict(tile=64, predictor=2, big_endian=True))
+    _check(dev, [syn.tiff_bytes(img, **kw) for kw in kws], [img] * len(kws))
+
+
+def test_lzw_pathological_streams(dev):
+    rng = np.random.default_rng(9)
+    cases = [np.zeros((256, 256), np.uint8),                                     # one long run: KwKwK chains
+             np.full((100, 300), 7, np.uint8),
+             rng.integers(0, 256, (256, 256), dtype=np.uint8),                   # incompressible: all literals, many Clears
+             np.tile(np.arange(256, dtype=np.uint8), (256, 1)),                  # periodic
+             np.repeat(rng.integers(0, 4, (64, 64), dtype=np.uint8), 4, axis=1), # short runs
+             rng.integers(0, 2, (301, 257), dtype=np.uint8),
+             np.zeros((1, 1), np.uint8), np.arange(5, dtype=np.uint8).reshape(1, 5)]
+    blobs = [syn.tiff_bytes(c, tile=None, rows_per_strip=c.shape[0]) for c in cases] + \
+            [syn.tiff_bytes(c, tile=256) for c in cases[:4]]
+    _check(dev, blobs, [c[:, :, None] for c in cases] + [c[:, :, None] for c in cases[:4]])
+
+
+def test_png_pillow_chip_pairs(dev):
+    blobs, wants = [], []
+    for i in range(4):
+        img, lab, _ = syn.cfg1_chip(i)
+        blobs += [syn.png_bytes(img), syn.png_bytes(lab)]
+        wants += [img, lab[:, :, None]]
+    _check(dev, blobs, wants)
+
+
+@pytest.mark.parametrize("filters", [(0,), (1,), (2,), (3,), (4,), (0, 1, 2, 3, 4), (4, 3, 4, 1)])
+@pytest.mark.parametrize("channels", [1, 2, 3, 4])
+def test_png_each_filter_and_colour_type(dev, filters, channels):
+    rng = np.random.default_rng(channels)
+    img = np.stack([(syn.smooth_field(rng, 70, 93) * 255).astype(np.uint8) for _ in range(channels)], -1)
+    img[::7] = rng.integers(0, 256, img[::7].shape, dtype=np.uint8)
+    _check(dev, [syn.png_bytes_manual(img, filter_types=filters, idat_chunk=997)], [img])
+
+
+def test_png_deflate_block_types(dev):
+    img, lab, _ = syn.cfg1_chip(3, size=96)
+    blobs = [syn.png_bytes_manual(img, zlevel=0),                                 # stored blocks
+             syn.png_bytes_manual(img, strategy=zlib.Z_FIXED),                    # fixed Huffman
+             syn.png_bytes_manual(img, zlevel=9),                                 # dynamic Huffman
+             syn.png_bytes_manual(lab, zlevel=1), syn.png_bytes_manual(np.zeros((300, 500, 3), np.uint8)),   # long matches
+             syn.png_bytes_manual(lab, strategy=zlib.Z_HUFFMAN_ONLY), syn.png_bytes_manual(lab, strategy=zlib.Z_RLE)]
+    _check(dev, blobs)
+
+
+def test_corrupt_chips_are_skipped_not_fatal(dev):
+    img, lab, _ = syn.cfg3_chip(1, size=128)
+    good = syn.tiff_bytes(img, tile=64)
+    png = syn.png_bytes(syn.cfg1_chip(0, size=64)[0])
+    trunc = good[:len(good) // 2]
+    garb = bytearray(good)
+    garb[len(good) // 2:len(good) // 2 + 400] = bytes(400)
+    badpng = bytearray(png)
+    badpng[60:90] = bytes(30)
+    blobs = [good, trunc, bytes(garb), b"not an image at all", png, bytes(badpng), png[:100], good]
+    got, status = _decode(dev, blobs)
+    assert status[0] == 0 and status[4] == 0 and status[7] == 0
+    np.testing.assert_array_equal(got[0], img)
+    np.testing.assert_array_equal(got[7], img)
+    for i in (1, 3, 6):
+        assert status[i] != 0 and got[i] is None
+    for i, b in ((2, bytes(garb)), (5, bytes(badpng))):          # payload damage: either flagged, or decodes like the oracle
+        try:
+            want = oic.decode_image(b)
+        except oic.DecodeError:
+            want = None
+        if status[i] == 0 and want is not None:
+            np.testing.assert_array_equal(got[i], want)
+
+
+def test_probe_header_only(dev):
+    from dl_image_segmentation_b200 import _codec
+    img, lab, _ = syn.cfg3_chip(0, size=100)
+    i1 = _codec.probe(syn.tiff_bytes(img, tile=64, nodata=None))
+    assert (i1.height, i1.width, i1.samples, i1.status) == (100, 100, 4, 0)
+    i2 = _codec.probe(syn.tiff_bytes(lab, nodata=255))
+    assert (i2.height, i2.width, i2.samples, i2.has_nodata, i2.nodata) == (100, 100, 1, 1, 255.0)
+    i3 = _codec.probe(syn.png_bytes(syn.cfg1_chip(0, size=40)[0]))
+    assert (i3.height, i3.width, i3.samples, i3.format) == (40, 40, 3, 2)
+    assert _codec.probe(b"garbage").status != 0

@@ -1,0 +1,118 @@
+#!/usr/bin/env python3
+"""Per-kernel roofline micro-benchmarks (CUDA events, inputs >> L2, >= 3 warm-ups).
+
+    python tools/kbench.py [median] [mosaic] [parse] [build] [stats] [norm] [decode] ...
+
+Prints one JSON line per kernel: algorithmic bytes per launch / event time vs MEASURED_PEAKS.json hbm_gbs.
+Used for development and for the ncu captures under profiles/; bench.py stays the headline number.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from dl_image_segmentation_b200 import _lib, ops  # noqa: E402
+
+PEAK = 6450.9
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timeit(fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn(0)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(iters):
+        fn(i)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def report(name, ms, algo_bytes, extra=None):
+    gbs = algo_bytes / (ms / 1e3) / 1e9
+    d = {"kernel": name, "ms": round(ms, 4), "algorithmic_bytes": int(algo_bytes), "GB/s": round(gbs, 1),
+         "frac_of_measured_hbm": round(gbs / PEAK, 4)}
+    if extra:
+        d.update(extra)
+    print(json.dumps(d), flush=True)
+
+
+def bench_median(dev, n_tiles=8, iters=16):
+    T, H, W, B = 16, 1024, 1024, 8
+    g = torch.Generator(device=dev)
+    g.manual_seed(1004)
+    stacks = [torch.randint(0, 10001, (T, H, W, B), dtype=torch.int32, device=dev, generator=g).to(torch.int16).view(torch.uint16)
+              for _ in range(n_tiles)]
+    valids = [(torch.rand((T, H, W), device=dev, generator=g) > 0.4).to(torch.uint8) for _ in range(n_tiles)]
+    ctx = _lib.get_ctx(dev)
+    out = torch.empty((H, W, B), dtype=torch.float64, device=dev)
+    mask = torch.empty((H, W, B), dtype=torch.uint8, device=dev)
+
+    def fn(i):
+        s, v = stacks[i % n_tiles], valids[i % n_tiles]
+        _lib.check(_lib.lib().b2_median_composite_u16(ctx.handle, _lib.ptr(s), _lib.ptr(v), None, T, H, W, B,
+                                                      _lib.ptr(out), _lib.ptr(mask), ctx.stream()))
+    ms = timeit(fn, iters)
+    algo = T * H * W * B * 2 + T * H * W + H * W * B * 8 + H * W * B
+    report("median_kernel<16,NV=2> cfg4 (16,1024,1024,8)", ms, algo, {"tiles_per_s": round(1e3 / ms, 1), "Gpix_per_s": round(H * W / ms / 1e6, 3)})
+
+
+def bench_mosaic(dev, pool=256, chips=4096, iters=5):
+    import synthetic as syn
+    T, H, W, B = 32, 256, 256, 4
+    g = torch.Generator(device=dev)
+    g.manual_seed(1005)
+    stacks = torch.randint(0, 10001, (pool, T, H, W, B), dtype=torch.int32, device=dev, generator=g).to(torch.int16).view(torch.uint16)
+    # spatially coherent validity (clouds are blobs): coarse noise upsampled
+    coarse = torch.rand((pool * T, 1, 16, 16), device=dev, generator=g)
+    valids = (torch.nn.functional.interpolate(coarse, size=(H, W), mode="bilinear") > 0.33).to(torch.uint8).reshape(pool, T, H, W)
+    days = np.stack([syn.cfg5_scene_meta(c)[0] for c in range(chips)])
+    cfs = np.stack([syn.cfg5_scene_meta(c)[1] for c in range(chips)])
+    day_d, cf_d = ops.to_device(days, dev), ops.to_device(cfs, dev)
+    sp = torch.tensor([stacks[c % pool].data_ptr() for c in range(chips)], dtype=torch.int64).to(dev)
+    vp = torch.tensor([valids[c % pool].data_ptr() for c in range(chips)], dtype=torch.int64).to(dev)
+    ctx = _lib.get_ctx(dev)
+    out = torch.empty((chips, H, W, B), dtype=torch.uint16, device=dev)
+    mask = torch.empty((chips, H, W), dtype=torch.uint8, device=dev)
+    src = torch.empty((chips, H, W), dtype=torch.int16, device=dev)
+    nel = torch.empty((chips,), dtype=torch.int32, device=dev)
+    f = syn.CFG5_FILTER
+
+    def fn(i):
+        _lib.check(_lib.lib().b2_nearest_date_mosaic(ctx.handle, _lib.ptr(sp), _lib.ptr(vp), _lib.ptr(day_d), _lib.ptr(cf_d),
+                                                     f["ref_day"], f["min_day"], f["max_day"], f["max_cf"], chips, T, H, W, B, 2,
+                                                     _lib.ptr(out), _lib.ptr(mask), None, _lib.ptr(nel), ctx.stream()))
+    ms = timeit(fn, iters)
+    dense = chips * (T * H * W * B * 2 + T * H * W + H * W * B * 2 + H * W)
+    # bytes actually touched: one pixel read + probes of eligible scenes until the first valid one (estimated from src)
+    _lib.check(_lib.lib().b2_nearest_date_mosaic(ctx.handle, _lib.ptr(sp), _lib.ptr(vp), _lib.ptr(day_d), _lib.ptr(cf_d),
+                                                 f["ref_day"], f["min_day"], f["max_day"], f["max_cf"], chips, T, H, W, B, 2,
+                                                 _lib.ptr(out), _lib.ptr(mask), _lib.ptr(src), _lib.ptr(nel), ctx.stream()))
+    touched_min = chips * (H * W * B * 2 * 2 + H * W + H * W)
+    report("mosaic_kernel<8> cfg5 T=32 256x256x4 u16, %d chips" % chips, ms, dense,
+           {"chips_per_s": round(chips / ms * 1e3, 1), "note": "dense-equivalent bytes; the kernel skips filtered/occluded scenes",
+            "GB/s_min_touched": round(touched_min / (ms / 1e3) / 1e9, 1), "mean_eligible": float(nel.float().mean().cpu())})
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    which = sys.argv[1:] or ["median", "mosaic"]
+    if "median" in which:
+        bench_median(dev)
+    if "mosaic" in which:
+        bench_mosaic(dev)
+
+
+if __name__ == "__main__":
+    main()
