@@ -141,35 +141,33 @@ def run_ours(args, rank, world):
     out = (torch.empty((RECS_PER_SHARD, H * W * C), dtype=torch.float32, device=dev),
            torch.empty((RECS_PER_SHARD, H * W * K), dtype=torch.float32, device=dev))
     pinned = [s.cpu().pin_memory() for s in shards]
-    big = max(int(s.numel()) for s in shards)
-    stage = [torch.empty((big,), dtype=torch.uint8, device=dev) for _ in range(2)]
     ev = lambda: torch.cuda.Event(enable_timing=True)
     kern_events = []
 
     def step_resident(record_kernel=False):
-        bad = 0
-        for s in shards:
-            si = ops.open_shard(s, dev)
-            if record_kernel:
+        st = None
+        if record_kernel:                      # per-launch events need the un-pipelined order
+            for s in shards:
+                si = ops.open_shard(s, dev)
                 a, b = ev(), ev()
                 a.record()
-            _, _, st = ops.parse_shard(si, "norm_onehot", verify_crc=True, mean=mean_d, std=std_d, num_classes=K, out=out)
-            if record_kernel:
+                _, _, st = ops.parse_shard(si, "norm_onehot", verify_crc=True, mean=mean_d, std=std_d, num_classes=K, out=out)
                 b.record()
                 kern_events.append((a, b))
+            return st
+        for _, _, st, _ in ops.iter_parsed_shards(shards, "norm_onehot", verify_crc=True, mean=mean_d, std=std_d,
+                                                  num_classes=K, out=out, device=dev):
+            pass
         return st
 
     def step_e2e():
-        last = None
-        for i, p in enumerate(pinned):
-            buf = stage[i & 1][:p.numel()]
-            buf.copy_(p, non_blocking=True)                                   # H2D of the shard
-            si = ops.open_shard(buf, dev)                                     # D2H: frame table + feature index
-            _, _, st = ops.parse_shard(si, "norm_onehot", verify_crc=True, mean=mean_d, std=std_d, num_classes=K, out=out)
-            last = st.cpu()                                                   # D2H: per-record status
-            if int(last.abs().sum()):
-                raise RuntimeError("parse status != 0")
-        return last
+        bad = torch.zeros((), dtype=torch.int32, device=dev)
+        for _, _, st, _ in ops.iter_parsed_shards(pinned, "norm_onehot", verify_crc=True, mean=mean_d, std=std_d,
+                                                  num_classes=K, out=out, device=dev):
+            bad += st.abs().sum().to(torch.int32)
+        if int(bad.cpu()):                                                    # D2H: job status
+            raise RuntimeError("parse status != 0")
+        return bad
 
     def timed(fn, steps, warmup, **kw):
         for _ in range(warmup):
@@ -196,8 +194,9 @@ def run_ours(args, rank, world):
 
     sampler = ClockSampler(local)
     sampler.start()
-    ms, launches = timed(step_resident, args.steps, args.warmup, record_kernel=True)
+    ms, launches = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop()
+    timed(step_resident, 2, 0, record_kernel=True)          # per-launch CUDA events of the dominant kernel
     st = step_resident()
     assert not st.cpu().numpy().any(), "parse status != 0"
     e2e_steps = max(1, min(args.steps, 5))

@@ -65,7 +65,7 @@ def _align(x, a=256):
     return (int(x) + a - 1) // a * a
 
 
-def decode_blobs(blobs, device=None):
+def decode_blobs(blobs, device=None, timings=None):
     """Decode a batch of encoded chips on the GPU.
 
     blobs: list of bytes / uint8 arrays (host).  Returns (arrays, status): arrays[i] is an (H,W,bands) CUDA
@@ -140,8 +140,18 @@ def decode_blobs(blobs, device=None):
     scratch = torch.empty((max(scratch_pos, 16),), dtype=torch.uint8, device=ctx.device)
     out = torch.empty((max(out_pos, 16),), dtype=torch.uint8, device=ctx.device)
     st_d = torch.from_numpy(status.copy()).to(ctx.device)
+    if timings is not None:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
     check(lib().b2_decode_streams(ctx.handle, ptr(blob_d), ptr(sd_d), len(sd), mask, max_raw, ptr(scratch), ptr(st_d), ctx.stream()))
+    if timings is not None:
+        ev[1].record()
     check(lib().b2_assemble_images(ctx.handle, ptr(scratch), ptr(im_d), images.ctypes.data, n, ptr(out), ptr(st_d), ctx.stream()))
+    if timings is not None:
+        ev[2].record()
+        torch.cuda.synchronize()
+        timings.update(decode_ms=ev[0].elapsed_time(ev[1]), assemble_ms=ev[1].elapsed_time(ev[2]),
+                       compressed_bytes=int(sum(int(s[2]) for s in streams)), decoded_bytes=int(out_pos), streams=len(streams))
     status = st_d.cpu().numpy()
     for i, info in enumerate(infos):
         if status[i] != 0:

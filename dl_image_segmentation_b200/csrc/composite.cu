@@ -9,6 +9,7 @@
 // (K3a) or at most once (K3b), straight from global memory with fully coalesced vector loads — there is
 // no reuse, so no shared-memory staging.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "median_net.inc"
@@ -17,7 +18,7 @@ namespace b2 {
 
 // ------------------------------------------------------------------------------------------------ K3a
 //
-// A thread owns NV packed u16x2 registers = 2*NV consecutive bands of ONE pixel and keeps the whole
+// A thread owns ONE packed u16x2 register per scene = two consecutive bands of one pixel, and keeps the whole
 // time series in registers (P slots, P = T rounded up to a power of two).  Invalid entries (cloud,
 // nodata, or padding slots t >= T) are replaced by sentinels, alternating 0xFFFF, 0x0000, 0xFFFF ...
 // per (pixel, band).  With m invalid entries that puts floor(m/2) zeros below and ceil(m/2) 0xFFFFs
@@ -26,104 +27,83 @@ namespace b2 {
 // sentinel and a genuine 0 / 0xFFFF are harmless because equal keys are interchangeable.  A pruned
 // selection network (median_net.inc) then extracts just those two ranks: no sort, no dynamic indexing.
 //
-// kNodata: per-(t,pixel,band) mask in addition to the per-(t,pixel) validity byte.
-template <int P, int NV, bool kNodata>
-__global__ void __launch_bounds__(256)
+// GPP = threads per pixel (B/2).  When it is a power of two the GPP threads of a pixel sit in one warp and
+// SHARE the validity column: each loads P/GPP of the T bytes and the bit masks are OR-ed with warp shuffles,
+// which removes (GPP-1)/GPP of the byte loads and their registers.  GPP = 0: every thread loads all T bytes.
+// All loads of a thread are issued back to back before any is consumed (T + T/GPP independent requests).
+template <int P, int GPP, bool kNodata>
+__global__ void __launch_bounds__(256, (P <= 16 ? (kNodata ? 4 : 6) : 2))
 median_kernel(const uint16_t* __restrict__ stack, const uint8_t* __restrict__ valid,
               const uint8_t* __restrict__ nodata, int T, uint64_t hw, int B, uint64_t n_groups,
               double* __restrict__ out, uint8_t* __restrict__ out_mask) {
-    constexpr int VEC = 2 * NV;  // u16 elements per thread
-    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_groups) return;
-    const uint64_t e0 = g * VEC;            // first element (pixel*B + band) of this thread
-    const uint64_t pix = e0 / (uint64_t)B;
-    const uint64_t plane = hw * (uint64_t)B;  // elements per scene
+    const uint64_t g_raw = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = g_raw < n_groups;
+    const uint64_t g = live ? g_raw : n_groups - 1;   // keep every lane alive for the shuffles
+    const uint64_t e0 = g * 2;                        // first element (pixel*B + band) of this thread
+    const uint64_t pix = GPP ? g / GPP : e0 / (uint64_t)B;
+    const uint64_t plane = hw * (uint64_t)B;          // elements per scene
 
-    uint32_t v[NV][P];
-    uint32_t tg[NV], cnt[NV];
+    uint32_t v[P];
 #pragma unroll
-    for (int k = 0; k < NV; k++) {
-        tg[k] = 0xFFFFFFFFu;  // next sentinel per half: 0xFFFF first
-        cnt[k] = 0;
+    for (int t = 0; t < P; t++) v[t] = (t < T) ? __ldg(reinterpret_cast<const uint32_t*>(stack + (uint64_t)t * plane + e0)) : 0u;
+    uint32_t vmask = 0;                               // bit t set = scene t usable at this pixel
+    if (GPP) {
+        constexpr int kPer = GPP ? (P + GPP - 1) / GPP : P;
+        const int sub = (int)(g % (GPP ? GPP : 1));
+        uint32_t vb[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+            const int t = sub + j * GPP;
+            vb[j] = (t < T) ? __ldg(valid + (uint64_t)t * hw + pix) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < kPer; j++) vmask |= (vb[j] ? 1u : 0u) << (sub + j * GPP);
+#pragma unroll
+        for (int o = 1; o < GPP; o <<= 1) vmask |= __shfl_xor_sync(0xffffffffu, vmask, o);
+    } else {
+        uint32_t vb[P];
+#pragma unroll
+        for (int t = 0; t < P; t++) vb[t] = (t < T) ? __ldg(valid + (uint64_t)t * hw + pix) : 0u;
+#pragma unroll
+        for (int t = 0; t < P; t++) vmask |= (vb[t] ? 1u : 0u) << t;
     }
-    // issue every load of the series before touching any of them
-    uint32_t raw[P][NV];
-    uint32_t vb[P];
-    uint32_t nd[P][NV];
+    uint32_t ndm[kNodata ? P : 1];                    // per half 0xFFFF where the (t,band) sample is nodata
+    if (kNodata) {
 #pragma unroll
-    for (int t = 0; t < P; t++) {
-        if (t < T) {
-            const uint16_t* src = stack + (uint64_t)t * plane + e0;
-            if (NV == 1) {
-                raw[t][0] = __ldg(reinterpret_cast<const uint32_t*>(src));
-            } else if (NV == 2) {
-                uint2 q = __ldg(reinterpret_cast<const uint2*>(src));
-                raw[t][0] = q.x;
-                raw[t][NV > 1 ? 1 : 0] = q.y;
-            } else {
-                uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
-                raw[t][0] = q.x;
-                raw[t][NV > 1 ? 1 : 0] = q.y;
-                raw[t][NV > 2 ? 2 : 0] = q.z;
-                raw[t][NV > 3 ? 3 : 0] = q.w;
-            }
-            vb[t] = __ldg(valid + (uint64_t)t * hw + pix);
-            if (kNodata) {
-                const uint8_t* np_ = nodata + (uint64_t)t * plane + e0;
-#pragma unroll
-                for (int k = 0; k < NV; k++) {
-                    uint32_t two = __ldg(reinterpret_cast<const uint16_t*>(np_ + 2 * k));
-                    nd[t][k] = ((two & 0xFFu) ? 0x0000FFFFu : 0u) | ((two & 0xFF00u) ? 0xFFFF0000u : 0u);
-                }
-            }
+        for (int t = 0; t < P; t++) {
+            const uint32_t two = (t < T) ? __ldg(reinterpret_cast<const uint16_t*>(nodata + (uint64_t)t * plane + e0)) : 0u;
+            ndm[t] = ((two & 0xFFu) ? 0x0000FFFFu : 0u) | ((two & 0xFF00u) ? 0xFFFF0000u : 0u);
         }
     }
+    uint32_t tg = 0xFFFFFFFFu, cnt = 0;               // next sentinel per half (0xFFFF first); valid count per half
 #pragma unroll
     for (int t = 0; t < P; t++) {
-#pragma unroll
-        for (int k = 0; k < NV; k++) {
-            uint32_t im;  // per half: 0xFFFF where the entry is invalid
-            uint32_t x;
-            if (t < T) {
-                im = vb[t] ? 0u : 0xFFFFFFFFu;
-                if (kNodata) im |= nd[t][k];
-                x = raw[t][k];
-            } else {
-                im = 0xFFFFFFFFu;
-                x = 0;
-            }
-            v[k][t] = (x & ~im) | (tg[k] & im);
-            tg[k] ^= im;
-            cnt[k] += (~im) & 0x00010001u;
-        }
+        uint32_t im = ((vmask >> t) & 1u) ? 0u : 0xFFFFFFFFu;     // per half: 0xFFFF where the entry is invalid
+        if (kNodata) im |= ndm[t];
+        v[t] = (v[t] & ~im) | (tg & im);
+        tg ^= im;
+        cnt += (~im) & 0x00010001u;
     }
-    double res[VEC];
+    MedNet<P>::run(v);
+    const uint32_t lo = v[P / 2 - 1], hi = v[P / 2];
+    double res[2];
     uint32_t msk = 0;
 #pragma unroll
-    for (int k = 0; k < NV; k++) {
-        MedNet<P>::run(v[k]);
-        const uint32_t lo = v[k][P / 2 - 1], hi = v[k][P / 2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const uint32_t n = (cnt[k] >> (16 * h)) & 0xFFFFu;
-            const uint32_t a = (lo >> (16 * h)) & 0xFFFFu, b = (hi >> (16 * h)) & 0xFFFFu;
-            // n odd -> the single middle (rank P/2-1); n even -> mean of the two middles; exact in double
-            const uint32_t sum2 = (n & 1u) ? 2u * a : a + b;
-            res[2 * k + h] = n ? 0.5 * (double)sum2 : 0.0;
-            msk |= (n ? 0u : 1u) << (8 * (2 * k + h));
-        }
+    for (int h = 0; h < 2; h++) {
+        const uint32_t n = (cnt >> (16 * h)) & 0xFFFFu;
+        const uint32_t a = (lo >> (16 * h)) & 0xFFFFu, b = (hi >> (16 * h)) & 0xFFFFu;
+        // n odd -> the single middle (rank P/2-1); n even -> mean of the two middles
+        const uint32_t sum2 = (n & 1u) ? 2u * a : a + b;
+        // sum2 / 2 exactly, without an int->double conversion: 2^51 + sum2/2 is representable (ulp 0.5)
+        res[h] = n ? __hiloint2double(0x43200000, (int)sum2) - 2251799813685248.0 : 0.0;
+        msk |= (n ? 0u : 1u) << (8 * h);
     }
-    double* o = out + e0;
-#pragma unroll
-    for (int k = 0; k < NV; k++) st_cs(reinterpret_cast<double2*>(o) + k, make_double2(res[2 * k], res[2 * k + 1]));
-    if (NV == 1) {
+    if (live) {
+        st_cs(reinterpret_cast<double2*>(out + e0), make_double2(res[0], res[1]));
         *reinterpret_cast<uint16_t*>(out_mask + e0) = (uint16_t)msk;
-    } else if (NV == 2) {
-        *reinterpret_cast<uint32_t*>(out_mask + e0) = msk;
     }
 }
 
-// NV == 4 needs a 64-bit mask word; kept as a separate tiny overload to keep the kernel above simple.
 // Generic fallback: any T, any B, one thread per (pixel, band); rank-counting selection straight from
 // global memory (two passes over the series, no local arrays).  Used when T > 32 or B is odd.
 __global__ void __launch_bounds__(256)
@@ -169,26 +149,38 @@ median_generic_kernel(const uint16_t* __restrict__ stack, const uint8_t* __restr
     out_mask[e] = 0;
 }
 
-template <int P, int NV>
+template <int P, int GPP>
 static void launch_median(const uint16_t* stack, const uint8_t* valid, const uint8_t* nodata, int T, uint64_t hw,
                           int B, double* out, uint8_t* mask, cudaStream_t s) {
-    const uint64_t n_groups = hw * (uint64_t)B / (2 * NV);
+    const uint64_t n_groups = hw * (uint64_t)B / 2;
     const unsigned grid = (unsigned)((n_groups + 255) / 256);
     if (nodata)
-        median_kernel<P, NV, true><<<grid, 256, 0, s>>>(stack, valid, nodata, T, hw, B, n_groups, out, mask);
+        median_kernel<P, GPP, true><<<grid, 256, 0, s>>>(stack, valid, nodata, T, hw, B, n_groups, out, mask);
     else
-        median_kernel<P, NV, false><<<grid, 256, 0, s>>>(stack, valid, nodata, T, hw, B, n_groups, out, mask);
+        median_kernel<P, GPP, false><<<grid, 256, 0, s>>>(stack, valid, nodata, T, hw, B, n_groups, out, mask);
 }
 
-template <int NV>
+template <int P>
+static void dispatch_gpp(int gpp, const uint16_t* stack, const uint8_t* valid, const uint8_t* nodata, int T,
+                         uint64_t hw, int B, double* out, uint8_t* mask, cudaStream_t s) {
+    switch (gpp) {
+        case 1: launch_median<P, 1>(stack, valid, nodata, T, hw, B, out, mask, s); break;
+        case 2: launch_median<P, 2>(stack, valid, nodata, T, hw, B, out, mask, s); break;
+        case 4: launch_median<P, 4>(stack, valid, nodata, T, hw, B, out, mask, s); break;
+        case 8: launch_median<P, 8>(stack, valid, nodata, T, hw, B, out, mask, s); break;
+        default: launch_median<P, 0>(stack, valid, nodata, T, hw, B, out, mask, s); break;
+    }
+}
+
 static bool dispatch_median(int P, const uint16_t* stack, const uint8_t* valid, const uint8_t* nodata, int T,
                             uint64_t hw, int B, double* out, uint8_t* mask, cudaStream_t s) {
+    const int gpp = B / 2;
     switch (P) {
-        case 2: launch_median<2, NV>(stack, valid, nodata, T, hw, B, out, mask, s); return true;
-        case 4: launch_median<4, NV>(stack, valid, nodata, T, hw, B, out, mask, s); return true;
-        case 8: launch_median<8, NV>(stack, valid, nodata, T, hw, B, out, mask, s); return true;
-        case 16: launch_median<16, NV>(stack, valid, nodata, T, hw, B, out, mask, s); return true;
-        case 32: launch_median<32, NV>(stack, valid, nodata, T, hw, B, out, mask, s); return true;
+        case 2: dispatch_gpp<2>(gpp, stack, valid, nodata, T, hw, B, out, mask, s); return true;
+        case 4: dispatch_gpp<4>(gpp, stack, valid, nodata, T, hw, B, out, mask, s); return true;
+        case 8: dispatch_gpp<8>(gpp, stack, valid, nodata, T, hw, B, out, mask, s); return true;
+        case 16: dispatch_gpp<16>(gpp, stack, valid, nodata, T, hw, B, out, mask, s); return true;
+        case 32: dispatch_gpp<32>(gpp, stack, valid, nodata, T, hw, B, out, mask, s); return true;
     }
     return false;
 }
@@ -290,13 +282,7 @@ extern "C" int b2_median_composite_u16(b2_ctx* ctx, const uint16_t* stack, const
                          (reinterpret_cast<uintptr_t>(out_mask) % 4 == 0) &&
                          (!nodata || reinterpret_cast<uintptr_t>(nodata) % 4 == 0);
     bool done = false;
-    if (P <= 32 && aligned) {
-        // 4 bands per thread (64-bit loads) when the band count allows, else 2
-        if (B % 4 == 0 && P <= 16)
-            done = dispatch_median<2>(P, stack, valid, nodata, T, hw, B, out, out_mask, s);
-        else if (B % 2 == 0)
-            done = dispatch_median<1>(P, stack, valid, nodata, T, hw, B, out, out_mask, s);
-    }
+    if (P <= 32 && aligned && B % 2 == 0) done = dispatch_median(P, stack, valid, nodata, T, hw, B, out, out_mask, s);
     if (!done) {
         const uint64_t n = hw * (uint64_t)B;
         median_generic_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(stack, valid, nodata, T, hw, B, n, out, out_mask);

@@ -166,6 +166,15 @@ __device__ __forceinline__ void sink_raw(const uint32_t* buf32, const uint8_t* b
     }
 }
 
+// Dynamic shared memory of the NORM_ONEHOT sink:
+//   lut  : C*256 floats, lut[c*256+v] = (float(v) - mean[c]) / std[c] computed ONCE per CTA with IEEE division —
+//          the per-pixel work is then one shared-memory lookup, and the result is bit-identical to dividing.
+//   hot  : per warp, labels_per_iter*K floats kept at zero; a label sets ONE float to 1.0f, the warp streams the
+//          block out with coalesced 128-bit stores and clears that float again.  No per-element compare/select.
+constexpr int kLutMaxC = 8;
+constexpr int kHotMaxK = 32;
+__host__ __device__ inline int hot_labels_per_iter(int K) { return K <= 16 ? 64 : 32; }
+
 template <int kMode>
 __global__ void __launch_bounds__(kTileThreads)
 parse_kernel(const ParseArgs a) {
@@ -173,6 +182,8 @@ parse_kernel(const ParseArgs a) {
     __shared__ CrcSmem cs;
     __shared__ uint32_t red[kTileThreads / 32];
     __shared__ float s_mean[64], s_std[64];
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    const int tid = threadIdx.x;
     const int r = blockIdx.y;
     const uint32_t tile = blockIdx.x;
     const uint64_t d0 = a.rec_off[r], len = a.rec_len[r];
@@ -181,21 +192,46 @@ parse_kernel(const ParseArgs a) {
     const uint64_t ts = A + (uint64_t)tile * kTile, te = ts + kTile;
     if (len == 0 || ts >= d1) return;
     if (a.sink.verify_crc) load_crc_tables(&cs, a.tab);
-    if (kMode == B2_SINK_NORM_ONEHOT) {
-        for (int c = threadIdx.x; c < a.sink.channels && c < 64; c += blockDim.x) {
-            s_mean[c] = a.sink.mean[c];
-            s_std[c] = a.sink.std[c];
+    b2_example_index ix;
+    bool sink_ok = false;
+    const int C = a.sink.channels, K = a.sink.num_classes;
+    const bool use_lut = C <= kLutMaxC, use_hot = K <= kHotMaxK;
+    float* lut = reinterpret_cast<float*>(dyn_smem);
+    float* hot_all = lut + (use_lut ? C * 256 : 0);
+    if (kMode != B2_SINK_NONE && a.index != nullptr) {
+        ix = a.index[r];
+        sink_ok = ix.status == 0;
+    }
+    bool has_img = false, has_tgt = false;
+    if (kMode == B2_SINK_NORM_ONEHOT && sink_ok) {
+        sink_ok = ix.img_kind == 1 && ix.tgt_kind == 1 && ix.img_len * 4 <= a.sink.img_stride &&
+                  ix.tgt_len * (uint64_t)K * 4 <= a.sink.tgt_stride && ix.img_len < (1ull << 31) &&
+                  ix.tgt_len * (uint64_t)K < (1ull << 31);
+        has_img = sink_ok && a.sink.img_out && ix.img_len && ix.img_off < te && ix.img_off + ix.img_len > ts;
+        has_tgt = sink_ok && a.sink.tgt_out && ix.tgt_len && ix.tgt_off < te && ix.tgt_off + ix.tgt_len > ts;
+        if (has_img) {
+            if (use_lut) {
+                for (int i = tid; i < C * 256; i += kTileThreads)
+                    lut[i] = __fdiv_rn((float)(i & 255) - a.sink.mean[i >> 8], a.sink.std[i >> 8]);
+            } else {
+                for (int c = tid; c < C && c < 64; c += kTileThreads) {
+                    s_mean[c] = a.sink.mean[c];
+                    s_std[c] = a.sink.std[c];
+                }
+            }
+        }
+        if (has_tgt && use_hot) {
+            const int nfl = hot_labels_per_iter(K) * K * (kTileThreads / 32);
+            for (int i = tid; i < nfl; i += kTileThreads) hot_all[i] = 0.0f;
         }
     }
     stage_tile(buf4, a.shard, ts, a.nbytes < d1 ? a.nbytes : d1);
     __syncthreads();
     if (a.sink.verify_crc) {
         const uint32_t c = tile_crc(buf4, &cs, a.tab, ts, d0, d1, tile == 0, red);
-        if (threadIdx.x == 0) a.tilecrc[(size_t)r * a.tiles_x + tile] = c;
+        if (tid == 0) a.tilecrc[(size_t)r * a.tiles_x + tile] = c;
     }
-    if (kMode == B2_SINK_NONE || a.index == nullptr) return;
-    const b2_example_index ix = a.index[r];
-    if (ix.status != 0) return;
+    if (kMode == B2_SINK_NONE || !sink_ok) return;
     const uint32_t* buf32 = reinterpret_cast<const uint32_t*>(buf4);
     const uint8_t* buf8 = reinterpret_cast<const uint8_t*>(buf4);
     if (kMode == B2_SINK_RAW) {
@@ -207,24 +243,25 @@ parse_kernel(const ParseArgs a) {
         return;
     }
     // ---- NORM_ONEHOT: uint8 image -> (x-mean)/std float32 ; uint8 target -> one-hot float32
-    const int C = a.sink.channels, K = a.sink.num_classes;
-    if (ix.img_kind != 1 || ix.tgt_kind != 1) return;
-    if (ix.img_len * 4 > a.sink.img_stride || ix.tgt_len * (uint64_t)K * 4 > a.sink.tgt_stride) return;
-    if (ix.img_len >= (1ull << 31) || ix.tgt_len * (uint64_t)K >= (1ull << 31)) return;   // 32-bit index maths below
-    if (a.sink.img_out && ix.img_len && ix.img_off < te && ix.img_off + ix.img_len > ts) {
+    if (has_img) {
         float* dst = reinterpret_cast<float*>(static_cast<uint8_t*>(a.sink.img_out) + (uint64_t)r * a.sink.img_stride);
         const uint64_t po = ix.img_off;
         const uint32_t pl = (uint32_t)ix.img_len;
         const uint64_t lo = po > ts ? po : ts, hi = (po + pl < te) ? po + pl : te;
+        // float4 group g = image bytes [4g, 4g+4); owned by the tile that holds its first byte
         const uint32_t g_lo = (uint32_t)((lo - po + 3) >> 2), g_hi = (uint32_t)((hi - po + 3) >> 2), full = pl >> 2;
         const uint32_t base = (uint32_t)(po - ts);  // wraps when po < ts; base + 4g is back in [0, kTile)
-        for (uint32_t g = g_lo + threadIdx.x; g < g_hi; g += blockDim.x) {
+        uint32_t g = g_lo + tid;
+        uint32_t c0 = (4u * g) % (uint32_t)C;
+        const uint32_t cstep = (4u * kTileThreads) % (uint32_t)C;
+        for (; g < g_hi; g += kTileThreads) {
             const uint32_t x = smem_u32_unaligned(buf32, base + 4 * g);
-            uint32_t c = (4 * g) % (uint32_t)C;
             float f[4];
+            uint32_t c = c0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                f[k] = __fdiv_rn((float)((x >> (8 * k)) & 0xFFu) - s_mean[c], s_std[c]);
+                const uint32_t v = (x >> (8 * k)) & 0xFFu;
+                f[k] = use_lut ? lut[(c << 8) + v] : __fdiv_rn((float)v - s_mean[c], s_std[c]);
                 c = (c + 1 == (uint32_t)C) ? 0 : c + 1;
             }
             if (g < full) {
@@ -232,35 +269,72 @@ parse_kernel(const ParseArgs a) {
             } else {
                 for (uint32_t b = 4 * g; b < pl; b++) dst[b] = f[b - 4 * g];
             }
+            c0 += cstep;
+            if (c0 >= (uint32_t)C) c0 -= (uint32_t)C;
         }
     }
-    if (a.sink.tgt_out && ix.tgt_len && ix.tgt_off < te && ix.tgt_off + ix.tgt_len > ts) {
+    if (has_tgt) {
         float* dst = reinterpret_cast<float*>(static_cast<uint8_t*>(a.sink.tgt_out) + (uint64_t)r * a.sink.tgt_stride);
         const uint64_t po = ix.tgt_off;
         const uint32_t pl = (uint32_t)ix.tgt_len;
         const uint64_t lo = po > ts ? po : ts, hi = (po + pl < te) ? po + pl : te;
-        // float4 group g holds one-hot floats [4g, 4g+4); it is owned by the tile holding label floor(4g/K)
-        const uint32_t nfl = pl * (uint32_t)K;
-        const uint32_t g_lo = (uint32_t)(((lo - po) * K + 3) >> 2), g_hi = (uint32_t)(((hi - po) * K + 3) >> 2), full = nfl >> 2;
         const uint32_t base = (uint32_t)(po - ts);
-        for (uint32_t g = g_lo + threadIdx.x; g < g_hi; g += blockDim.x) {
-            const uint32_t f0 = 4 * g;
-            uint32_t l = f0 / (uint32_t)K;
-            uint32_t c = f0 - l * (uint32_t)K;
-            float f[4];
+        if (use_hot) {
+            // work unit = 4 labels (4K floats: always a whole number of float4s, 16-byte aligned in the output);
+            // a unit belongs to the tile holding its first label, later labels may sit in the 32-byte halo
+            const uint32_t j_lo = (uint32_t)((lo - po + 3) >> 2), j_hi = (uint32_t)((hi - po + 3) >> 2);
+            const uint32_t L_beg = 4 * j_lo, L_end = (4 * j_hi < pl) ? 4 * j_hi : pl;
+            const int Lw = hot_labels_per_iter(K);
+            const int warp = tid >> 5, lane = tid & 31;
+            float* hot = hot_all + warp * Lw * K;
+            for (uint32_t L0 = L_beg + warp * Lw; L0 < L_end; L0 += (kTileThreads / 32) * Lw) {
+                const uint32_t nl = (L_end - L0 < (uint32_t)Lw) ? L_end - L0 : (uint32_t)Lw;
+                uint32_t slot[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t lab = (l < pl) ? buf8[base + l] : 0xFFFFFFFFu;
-                f[k] = (lab == c) ? 1.0f : 0.0f;
-                if (++c == (uint32_t)K) {
-                    c = 0;
-                    l++;
+                for (int i = 0; i < 2; i++) {
+                    const uint32_t li = lane + 32 * i;
+                    if (li < nl) {
+                        const uint32_t lab = buf8[base + L0 + li];
+                        if (lab < (uint32_t)K) {
+                            slot[i] = li * K + lab;
+                            hot[slot[i]] = 1.0f;
+                        }
+                    }
                 }
+                __syncwarp();
+                const uint32_t nfl = nl * K, nf4 = nfl >> 2;
+                float4* o4 = reinterpret_cast<float4*>(dst + (size_t)L0 * K);
+                const float4* h4 = reinterpret_cast<const float4*>(hot);
+                for (uint32_t i = lane; i < nf4; i += 32) st_cs(o4 + i, h4[i]);
+                if (lane < (nfl & 3)) dst[(size_t)L0 * K + 4 * nf4 + lane] = hot[4 * nf4 + lane];
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+                    if (slot[i] != 0xFFFFFFFFu) hot[slot[i]] = 0.0f;
             }
-            if (g < full) {
-                st_cs(reinterpret_cast<float4*>(dst) + g, make_float4(f[0], f[1], f[2], f[3]));
-            } else {
-                for (uint32_t b = f0; b < nfl; b++) dst[b] = f[b - f0];
+        } else {
+            // generic path (K > 32): float4 group g holds one-hot floats [4g, 4g+4), owned by the tile of label 4g/K
+            const uint32_t nfl = pl * (uint32_t)K;
+            const uint32_t g_lo = (uint32_t)(((lo - po) * K + 3) >> 2), g_hi = (uint32_t)(((hi - po) * K + 3) >> 2), full = nfl >> 2;
+            for (uint32_t g = g_lo + tid; g < g_hi; g += kTileThreads) {
+                const uint32_t f0 = 4 * g;
+                uint32_t l = f0 / (uint32_t)K;
+                uint32_t c = f0 - l * (uint32_t)K;
+                float f[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t lab = (l < pl) ? buf8[base + l] : 0xFFFFFFFFu;
+                    f[k] = (lab == c) ? 1.0f : 0.0f;
+                    if (++c == (uint32_t)K) {
+                        c = 0;
+                        l++;
+                    }
+                }
+                if (g < full) {
+                    st_cs(reinterpret_cast<float4*>(dst) + g, make_float4(f[0], f[1], f[2], f[3]));
+                } else {
+                    for (uint32_t b = f0; b < nfl; b++) dst[b] = f[b - f0];
+                }
             }
         }
     }
@@ -763,7 +837,17 @@ static int launch_parse(b2_ctx* ctx, const ParseArgs& pa, int n, uint32_t tiles_
     switch (pa.sink.mode) {
         case B2_SINK_NONE: parse_kernel<B2_SINK_NONE><<<grid, kTileThreads, 0, s>>>(pa); break;
         case B2_SINK_RAW: parse_kernel<B2_SINK_RAW><<<grid, kTileThreads, 0, s>>>(pa); break;
-        default: parse_kernel<B2_SINK_NORM_ONEHOT><<<grid, kTileThreads, 0, s>>>(pa); break;
+        default: {
+            const int C = pa.sink.channels, K = pa.sink.num_classes;
+            size_t dyn = (C <= kLutMaxC ? (size_t)C * 256 * sizeof(float) : 0) +
+                         (K <= kHotMaxK ? (size_t)hot_labels_per_iter(K) * K * (kTileThreads / 32) * sizeof(float) : 0);
+            static bool attr_set[64] = {false};
+            if (!attr_set[ctx->device & 63]) {
+                B2_CUDA(cudaFuncSetAttribute(parse_kernel<B2_SINK_NORM_ONEHOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+                attr_set[ctx->device & 63] = true;
+            }
+            parse_kernel<B2_SINK_NORM_ONEHOT><<<grid, kTileThreads, dyn, s>>>(pa);
+        } break;
     }
     ctx->launches++;
     B2_CUDA(cudaGetLastError());

@@ -369,3 +369,54 @@ def build_records(items, device=None):
         check(lib().b2_tfrecord_build(ctx.handle, ctypes.c_void_p(descs_d.data_ptr() + s * descs.dtype.itemsize), m,
                                       max_rec, ptr(scaf_d), ptr(out), ctx.stream()))
     return out, offsets, pos
+
+
+def iter_parsed_shards(shards, mode, verify_crc=True, mean=None, std=None, num_classes=None, out=None, device=None):
+    """Parse a sequence of shards with a one-ahead software pipeline.
+
+    shards: iterable of uint8 tensors (CUDA-resident, or pinned host tensors which are uploaded here).  While the
+    fused parse kernel of shard k runs on the caller's stream, the upload + frame scan + feature index of shard k+1
+    (and the small D2H read-back of its tables) proceed on a side stream, so the host never stalls the GPU.
+    Yields (img_buf, tgt_buf, status_dev, ShardIndex) per shard.  `out` = optional (img_buf, tgt_buf) to reuse.
+    """
+    ctx = get_ctx(device)
+    main = torch.cuda.current_stream(ctx.device)
+    side = _side_stream(ctx.device)
+    if isinstance(mean, np.ndarray) or isinstance(mean, (list, tuple)):
+        mean = to_device(np.asarray(mean, dtype=np.float32), ctx.device)
+    if isinstance(std, np.ndarray) or isinstance(std, (list, tuple)):
+        std = to_device(np.asarray(std, dtype=np.float32), ctx.device)
+
+    def prefetch(s):
+        with torch.cuda.stream(side):
+            si = open_shard(s, ctx.device)
+        for t in (si.shard, si.rec_off, si.rec_len, si.index_dev):
+            if t is not None:
+                t.record_stream(main)
+        return si
+
+    it = iter(shards)
+    try:
+        nxt = prefetch(next(it))
+    except StopIteration:
+        return
+    while nxt is not None:
+        si = nxt
+        main.wait_stream(side)
+        res = parse_shard(si, mode, verify_crc=verify_crc, mean=mean, std=std, num_classes=num_classes, out=out)
+        try:
+            nxt = prefetch(next(it))
+        except StopIteration:
+            nxt = None
+        yield res + (si,)
+
+
+_side = {}
+
+
+def _side_stream(device):
+    s = _side.get(device.index)
+    if s is None:
+        # high priority: the tiny scan/index kernels must slip in between the CTAs of a running parse kernel
+        s = _side[device.index] = torch.cuda.Stream(device, priority=-1)
+    return s

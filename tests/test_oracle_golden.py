@@ -1,0 +1,218 @@
+"""CPU tests: pin the oracle against the committed golden vectors (tests/golden, made by gen_golden.py from
+libtiff / libpng / zlib / google.protobuf / numpy.ma and the RFC 3720 + TFRecord known answers) and against
+the live third-party codecs in this image."""
+import io
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import synthetic as syn
+from oracle import composite as ocomp
+from oracle import example_proto as oep
+from oracle import imagecodecs as oic
+from oracle import normalise as onorm
+from oracle import partition as opart
+from oracle import tfrecord as otfr
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+VEC = json.load(open(os.path.join(G, "vectors.json")))
+
+
+def _g(name):
+    p = os.path.join(G, name)
+    return np.load(p) if name.endswith(".npy") else open(p, "rb").read()
+
+
+def test_crc32c_rfc3720_vectors():
+    for v in VEC["crc32c"]:
+        data = bytes.fromhex(v["hex"])
+        assert otfr.crc32c(data) == v["crc"] == otfr.crc32c_py(data)
+        assert otfr.masked_crc32c(data) == v["masked"]
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 7, 8, 9, 63, 64, 65, 4097):
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert otfr.crc32c(d) == otfr.crc32c_py(d)
+
+
+def test_tfrecord_frame_vectors_and_scan():
+    for v in VEC["frames"]:
+        assert otfr.frame(bytes.fromhex(v["data_hex"])).hex() == v["frame_hex"]
+    recs = [b"", b"abc", bytes(range(16)), b"x" * 1000]
+    buf = b"".join(otfr.frame(r) for r in recs)
+    assert otfr.read_records(buf) == recs
+    bad = bytearray(buf)
+    bad[-6] ^= 1
+    with pytest.raises(otfr.DataLossError):
+        otfr.read_records(bytes(bad))
+    assert otfr.read_records(bytes(bad), verify=False)[-1] != recs[-1]
+    with pytest.raises(otfr.DataLossError):
+        otfr.scan(buf[:-1])
+
+
+def test_example_bytes_match_google_protobuf():
+    img8, lab8 = _g("chip8_img.npy"), _g("chip8_lab.npy")
+    img16, lab16 = _g("chip16_img.npy"), _g("chip16_lab.npy")
+    h, w, c = img8.shape
+    s = oep.convert_to_example(img8, lab8, h, w, c, h, w, VEC["example"]["key8"]).SerializeToString()
+    assert s == _g("example_bytes.bin")
+    h, w, c = img16.shape
+    s16 = oep.convert_to_example(img16, lab16, h, w, c, h, w, VEC["example"]["key16"]).SerializeToString()
+    assert s16 == _g("example_float.bin")
+    # and back
+    i, t, ident = oep.parse_8bit_array_proto(_g("example_bytes.bin"))
+    assert np.array_equal(i, img8) and np.array_equal(t, lab8) and ident == VEC["example"]["key8"].encode()
+    i, t, ident = oep.parse_higher_dtype_array_proto(_g("example_float.bin"))
+    assert i.dtype == np.float32 and np.array_equal(i, img16.astype(np.float32)) and np.array_equal(t, lab16.astype(np.float32))
+    with pytest.raises(oep.ParseError):
+        oep.parse_8bit_array_proto(_g("example_float.bin"))
+
+
+def test_convert_to_example_type_dispatch():
+    img8, lab8 = _g("chip8_img.npy"), _g("chip8_lab.npy")
+    f = oep.parse_example(oep.convert_to_example(img8, lab8, 24, 24, 3, 24, 24, "k").SerializeToString())
+    assert f["image/image_data"][0] == "bytes" and f["target/target_data"][0] == "bytes"
+    # uint8 label next to a uint16 image is forced to FloatList (reference :184-197)
+    f = oep.parse_example(oep.convert_to_example(img8.astype(np.uint16), lab8, 24, 24, 3, 24, 24, "k").SerializeToString())
+    assert f["image/image_data"][0] == "float" and f["target/target_data"][0] == "float"
+    f = oep.parse_example(oep.convert_to_example(b"raw-img", b"raw-lab", 1, 2, 3, 1, 2, "k").SerializeToString())
+    assert f["image/image_data"] == ("bytes", [b"raw-img"]) and f["identifier"] == ("bytes", [b"k"])
+    assert sorted(f) == sorted(oep.KEYS)
+    # payload sizes of SURVEY.md Appendix B (22-byte key)
+    key22 = "448:32:10.0:43:-38:349"
+    assert len(key22) == 22
+    big = oep.convert_to_example(np.zeros((256, 256, 3), np.uint8), np.zeros((256, 256), np.uint8), 256, 256, 3, 256, 256, key22)
+    assert len(big.SerializeToString()) == 262381
+    bigf = oep.convert_to_example(np.zeros((512, 512, 4), np.uint16), np.zeros((512, 512), np.uint8), 512, 512, 4, 512, 512, key22)
+    assert len(bigf.SerializeToString()) == 5243122
+
+
+def test_tiff_and_png_decode_against_golden_files():
+    img, lab = _g("tiff_img.npy"), _g("tiff_lab.npy")
+    assert np.array_equal(oic.decode_image(_g("libtiff_cv2_lzw_u16x4.tif")), img)          # libtiff-encoded, strips, predictor 2
+    assert np.array_equal(oic.decode_image(_g("libtiff_pil_lzw_u8.tif"))[..., 0], lab)
+    assert np.array_equal(oic.decode_image(_g("libtiff_pil_deflate_u8.tif"))[..., 0], lab)
+    assert np.array_equal(oic.decode_image(_g("gdalstyle_tiled_lzw_u16x4.tif")), img)      # GDAL layout: 64x64 tiles, predictor 1
+    assert np.array_equal(oic.decode_image(_g("gdalstyle_tiled_lzw_label.tif"))[..., 0], lab)
+    assert oic.parse_tiff(_g("gdalstyle_tiled_lzw_label.tif"))["nodata"] == "255"
+    assert np.array_equal(oic.decode_image(_g("libpng_rgb.png")), _g("png_img.npy"))
+    assert np.array_equal(oic.decode_image(_g("libpng_label.png"))[..., 0], _g("png_lab.npy"))
+    assert oic.image_shape(_g("libpng_rgb.png")) == (64, 64, 3)
+    assert oic.image_shape(_g("gdalstyle_tiled_lzw_u16x4.tif")) == (96, 96, 4)
+
+
+def test_decoders_against_live_libtiff_and_libpng():
+    import cv2
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    img, lab, _ = syn.cfg3_chip(9, size=130)
+    for arr in (img, (img >> 4).astype(np.uint8)[..., :3], lab):
+        ok, enc = cv2.imencode(".tif", arr if arr.ndim == 2 else arr[..., [2, 1, 0, 3][:arr.shape[2]] if arr.shape[2] == 4 else [2, 1, 0]],
+                               [cv2.IMWRITE_TIFF_COMPRESSION, 5])
+        assert ok
+        got = oic.decode_image(enc.tobytes())
+        assert np.array_equal(got if arr.ndim == 3 else got[..., 0], arr)
+    # our writers are readable by libtiff / libpng (so the GPU tests' inputs are legitimate files)
+    for kw in (dict(tile=64), dict(tile=None, predictor=2), dict(tile=64, compression="deflate"), dict(tile=None, big_endian=True)):
+        b = syn.tiff_bytes(lab, **kw)
+        assert np.array_equal(np.array(Image.open(io.BytesIO(b))), lab), kw
+        assert np.array_equal(oic.decode_image(b)[..., 0], lab)
+    noise = rng.integers(0, 256, (70, 50, 3), dtype=np.uint8)
+    for ft in ((0,), (1,), (2,), (3,), (4,), (0, 1, 2, 3, 4)):
+        b = syn.png_bytes_manual(noise, filter_types=ft, idat_chunk=333)
+        assert np.array_equal(np.array(Image.open(io.BytesIO(b))), noise)
+        assert np.array_equal(oic.decode_image(b), noise)
+    with pytest.raises(oic.DecodeError):
+        oic.decode_image(b"nope")
+    with pytest.raises(oic.DecodeError):
+        oic.decode_image(syn.tiff_bytes(lab, tile=64)[:600])
+
+
+def test_median_against_numpy_ma_golden():
+    stack, valid = _g("median_stack.npy"), _g("median_valid.npy")
+    ref = ocomp.median_composite(stack, valid)
+    assert ref.dtype == np.float64
+    assert np.array_equal(ref.filled(0.0), _g("median_out.npy"))
+    assert np.array_equal(np.ma.getmaskarray(ref), _g("median_mask.npy"))
+    for kat in VEC["median_kat"]:
+        v = np.array([int(c) for c in kat["valid"]], np.uint8).reshape(4, 1, 1)
+        r = ocomp.median_composite(np.array(kat["values"], np.uint16).reshape(4, 1, 1, 1), v)
+        if kat["median"] is None:
+            assert np.ma.getmaskarray(r).all()
+        else:
+            assert float(r[0, 0, 0]) == kat["median"]
+    r = ocomp.median_composite(np.array([65535, 65534], np.uint16).reshape(2, 1, 1, 1), np.ones((2, 1, 1), np.uint8))
+    assert float(r[0, 0, 0]) == 65534.5
+
+
+def test_nearest_date_rules():
+    rng = np.random.default_rng(1)
+    T, H, W, B = 6, 5, 4, 2
+    stack = rng.integers(1, 100, (T, H, W, B), dtype=np.uint16)
+    valid = np.ones((T, H, W), np.uint8)
+    days = [10, 20, 20, 30, 40, 50]
+    cf = [0.1, 0.2, 0.3, 0.5, 0.1, 0.0]
+    out, mask, src = ocomp.nearest_date_mosaic(stack, valid, days, cf, 20)
+    assert (src == 2).all()                                   # tie at distance 0 -> later scene
+    out, mask, src = ocomp.nearest_date_mosaic(stack, valid, days, cf, 25)
+    assert (src == 3).all()                                   # 20,20,30 all at distance 5 -> last of them
+    out, mask, src = ocomp.nearest_date_mosaic(stack, valid, days, cf, 25, max_cf=0.5)
+    assert (src == 2).all()                                   # strict < drops scene 3
+    out, mask, src = ocomp.nearest_date_mosaic(stack, valid, days, cf, 45, min_day=20, max_day=40)
+    assert (src == 3).all()                                   # end exclusive: day 40 is out
+    assert ocomp.nearest_date_mosaic(stack, valid, days, cf, 25, min_day=60) is None
+    valid[3] = 0
+    valid[2, 0, 0] = 0
+    out, mask, src = ocomp.nearest_date_mosaic(stack, valid, days, cf, 25)
+    assert src[0, 0] == 1 and src[1, 1] == 2 and np.array_equal(out[0, 0], stack[1, 0, 0])
+    valid[:, 4, 3] = 0
+    out, mask, src = ocomp.nearest_date_mosaic(stack, valid, days, cf, 25)
+    assert mask[4, 3] and not out[4, 3].any() and src[4, 3] == -1
+
+
+def test_partition_shuffle_and_names(tmp_path):
+    assert opart.tile_key(VEC["identifier"]["path"]) == VEC["identifier"]["key"]
+    idx = list(range(20))
+    random.seed(12345)
+    random.shuffle(idx)
+    assert idx == VEC["shuffle20"]
+    assert opart.worker_ranges(6000, 12) == [[500 * i, 500 * (i + 1)] for i in range(12)]
+    plan = opart.shard_plan(6000, 12, 12)
+    assert plan == [(s, 500 * s, 500 * (s + 1)) for s in range(12)]
+    # benchmark sizes give worker-count-invariant shard boundaries
+    for n, S, gs in ((6000, 24, (1, 2, 3, 4, 6, 8, 12, 24)), (1024, 16, (1, 2, 4, 8, 16))):
+        ref = opart.shard_plan(n, S, 1)
+        for g in gs:
+            assert opart.shard_plan(n, S, g) == ref
+    assert opart.shard_plan(103, 12, 4) != opart.shard_plan(103, 12, 1)        # awkward N: boundaries move, as in the reference
+    assert opart.shard_plan(1000003, 16, 8) != opart.shard_plan(1000003, 16, 1)
+    assert opart.shard_name("train", 2, 10) == "train-00002-of-00010"
+    for sub in ("images", "labels"):
+        os.makedirs(tmp_path / sub)
+        for k in range(7):
+            (tmp_path / sub / ("1#2#%d.tif" % k)).write_bytes(b"x")
+    a, b = opart.find_image_files(str(tmp_path), "tif")
+    assert [os.path.basename(x) for x in a] == [os.path.basename(x) for x in b] and len(a) == 7
+    a2, _ = opart.find_image_files(str(tmp_path), "tif")
+    assert a == a2
+
+
+def test_normalise_onehot_and_stats_definitions():
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 256, (2, 5, 6, 3), dtype=np.uint8)
+    lab = rng.integers(0, 12, (2, 5, 6), dtype=np.uint8)
+    lab[0, 0, 0] = 255
+    mean, std = np.array([1.5, 100.0, 200.25], np.float32), np.array([2.0, 3.0, 0.5], np.float32)
+    x = onorm.normalise(img, mean, std)
+    assert x.dtype == np.float32 and x[1, 2, 3, 1] == np.float32((np.float32(img[1, 2, 3, 1]) - mean[1]) / std[1])
+    h = onorm.one_hot(lab, 10)
+    assert h.shape == (2, 5, 6, 10) and h.dtype == np.float32 and not h[0, 0, 0].any()
+    assert (h.sum(-1) == (lab < 10)).all()
+    st = onorm.band_stats(img)
+    flat = img.reshape(-1, 3).astype(np.int64)
+    assert st == [(60, int(flat[:, b].sum()), int((flat[:, b] ** 2).sum())) for b in range(3)]
+    m, s = onorm.mean_std_from_stats(st)
+    np.testing.assert_allclose(m, flat.mean(0), rtol=1e-6)
+    np.testing.assert_allclose(s, flat.std(0), rtol=1e-6)

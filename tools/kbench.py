@@ -104,6 +104,74 @@ def bench_mosaic(dev, pool=256, chips=4096, iters=5):
             "GB/s_min_touched": round(touched_min / (ms / 1e3) / 1e9, 1), "mean_eligible": float(nel.float().mean().cpu())})
 
 
+def bench_decode(dev, kind, n_distinct=16, reps=16):
+    import time
+
+    import synthetic as syn
+    from dl_image_segmentation_b200 import _codec
+    blobs = []
+    for i in range(n_distinct):
+        if kind == "lzw":
+            img, lab, _ = syn.cfg3_chip(i)
+            blobs += [syn.tiff_bytes(img, tile=256), syn.tiff_bytes(lab, tile=256, nodata=255)]
+        elif kind == "lzw_strips_pred2":
+            img, lab, _ = syn.cfg3_chip(i)
+            blobs += [syn.tiff_bytes(img, tile=None, predictor=2, photometric=2), syn.tiff_bytes(lab, tile=None, predictor=2)]
+        elif kind == "deflate":
+            img, lab, _ = syn.cfg3_chip(i)
+            blobs += [syn.tiff_bytes(img, tile=256, compression="deflate"), syn.tiff_bytes(lab, tile=256, compression="deflate")]
+        else:
+            img, lab, _ = syn.cfg1_chip(i)
+            blobs += [syn.png_bytes(img), syn.png_bytes(lab)]
+    batch = blobs * reps
+    best = None
+    for it in range(4):
+        tm = {}
+        t0 = time.time()
+        arrays, status = _codec.decode_blobs(batch, device=dev, timings=tm)
+        torch.cuda.synchronize()
+        tm["wall_ms"] = (time.time() - t0) * 1e3
+        assert not status.any()
+        if best is None or tm["decode_ms"] + tm["assemble_ms"] < best["decode_ms"] + best["assemble_ms"]:
+            best = tm
+    pairs = len(batch) // 2
+    ms = best["decode_ms"] + best["assemble_ms"]
+    algo = best["compressed_bytes"] + best["decoded_bytes"]
+    report("decode %s: %d chip pairs (%d streams)" % (kind, pairs, best["streams"]), ms, algo,
+           {"chip_pairs_per_s": round(pairs / ms * 1e3, 1), "decode_ms": round(best["decode_ms"], 3),
+            "assemble_ms": round(best["assemble_ms"], 3), "decoded_GB/s": round(best["decoded_bytes"] / ms / 1e6, 1),
+            "wall_ms_incl_host_parse_and_h2d": round(best["wall_ms"], 1)})
+
+
+def bench_parse(dev, n_shards=8):
+    """Variants of the fused parse kernel on cfg2 shards + write-only / copy bandwidth references."""
+    sys.path.insert(0, ROOT)
+    import bench as B
+    B.N_SHARDS = n_shards
+    shards = B.make_shards_on_device(dev, 7)
+    sis = [ops.open_shard(s, dev) for s in shards]
+    mean = ops.to_device(np.array([127.0, 128.0, 126.5], np.float32), dev)
+    std = ops.to_device(np.array([73.0, 74.0, 72.5], np.float32), dev)
+    out = (torch.empty((B.RECS_PER_SHARD, B.H * B.W * B.C), dtype=torch.float32, device=dev),
+           torch.empty((B.RECS_PER_SHARD, B.H * B.W * B.K), dtype=torch.float32, device=dev))
+    rec = shards[0].numel() // B.RECS_PER_SHARD
+    n = B.RECS_PER_SHARD
+    img_b, hot_b = B.H * B.W * B.C * 4, B.H * B.W * B.K * 4
+    for name, mode, verify, algo in (
+            ("parse crc-only", "none", True, n * rec),
+            ("parse norm+onehot no-crc", "norm_onehot", False, n * (rec + img_b + hot_b)),
+            ("parse norm+onehot +crc", "norm_onehot", True, n * (rec + img_b + hot_b)),
+            ("parse raw +crc", "raw", True, n * (rec + B.H * B.W * (B.C + 1)))):
+        def fn(i):
+            ops.parse_shard(sis[i % n_shards], mode, verify_crc=verify, mean=mean, std=std, num_classes=B.K,
+                            out=out if mode == "norm_onehot" else None)
+        report(name, timeit(fn, 16), algo)
+    big = torch.empty((1 << 30,), dtype=torch.uint8, device=dev)
+    big2 = torch.empty((1 << 30,), dtype=torch.uint8, device=dev)
+    report("reference: torch zero_ 1 GiB (write-only)", timeit(lambda i: big.zero_(), 10), 1 << 30)
+    report("reference: torch copy_ 1 GiB (read+write)", timeit(lambda i: big2.copy_(big), 10), 2 << 30)
+
+
 def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -112,6 +180,11 @@ def main():
         bench_median(dev)
     if "mosaic" in which:
         bench_mosaic(dev)
+    if "parse" in which:
+        bench_parse(dev)
+    for kind in ("lzw", "lzw_strips_pred2", "deflate", "png"):
+        if kind in which or "decode" in which:
+            bench_decode(dev, kind)
 
 
 if __name__ == "__main__":
