@@ -70,6 +70,10 @@ SIGNATURES = {
     "b2_crc32c": (_i, [_vp, _vp, _vp, _vp, _i, _u64, _vp, _vp]),
     "b2_tfrecord_scan": (_i, [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp]),
     "b2_tfrecord_index": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "b2_tfrecord_table_bytes": (_u64, [_u64, _u64]),
+    "b2_tfrecord_table_layout": (_i, [_u64, _u64, ctypes.POINTER(_u64)]),
+    "b2_tfrecord_open": (_i, [_vp, _vp, _u64, _u64, _vp, _vp]),
+    "b2_tfrecord_parse_table": (_i, [_vp, _vp, _u64, _u64, _vp, ctypes.POINTER(ParseSink), _vp, _vp]),
     "b2_tfrecord_parse": (_i, [_vp, _vp, _u64, _vp, _vp, _vp, _i, _u64, ctypes.POINTER(ParseSink), _vp, _vp]),
     "b2_example_layout": (_i, [_i, _u64, _u64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                ctypes.c_int64, _vp, _u64, _vp, _u64, ctypes.POINTER(ctypes.c_uint32),

@@ -17,6 +17,7 @@ struct CrcTables {
     uint32_t xinvb[16];      // xinvb[r]  = x^(-8 r)
     uint32_t x2n[64];        // x^(2^k) for x2n pow
     uint32_t xtile;          // x^(8*8192): advance by one tile
+    uint32_t tpow[2048];     // tpow[j] = x^(8*8192*j): advance by j tiles (records up to 16 MiB; beyond -> xpow8)
 };
 
 }  // namespace b2

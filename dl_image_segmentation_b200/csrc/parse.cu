@@ -1,0 +1,684 @@
+// parse.cu — K2b + K4: the fused per-record pass over an opened TFRecord shard.
+//
+// Replaces (reference call sites): TFRecordDataset's data-CRC check     parse_tfrecords.ipynb cell 4
+//                                   tf.io.parse_single_example / decode_raw / reshape
+//                                                                        _tfrecord_image_translation.py:249,306-314,394-407
+//                                   cast -> per-band normalise, label -> one-hot (north-star row A17)
+//
+// Work decomposition.  Record data is cut into 8 KiB tiles on a 16-byte aligned grid anchored at the record's
+// (aligned-down) data start.  A 256-thread CTA owns a run of `q` consecutive tiles.  For every tile
+//   * one elected thread issues a TMA bulk copy (cp.async.bulk, SASS UBLKCP) of the tile + 32-byte halo into one
+//     of two shared-memory buffers and arms an mbarrier; the copy of tile i+1 overlaps the work on tile i,
+//   * the CTA computes the tile's CRC-32C partial from shared memory (the bytes cross HBM exactly once),
+//   * the payload sinks read the same shared-memory tile: raw copy, or uint8 -> (x-mean)/std float32 with
+//     128-bit streaming stores, and label -> one-hot through per-warp shared-memory blocks that are pushed to
+//     HBM with TMA bulk stores (cp.async.bulk.global.shared::cta): a label costs ONE 4-byte shared-memory write,
+//     the 4*K output bytes per label never pass through registers,
+//   * thread 0 advances the tile's CRC partial to the end of the record (one GF(2)[x] multiplication by a
+//     tabulated power of x), XORs it into the record's accumulator and counts the tile; the CTA that completes
+//     a record un-advances the zero padding, compares with the stored masked CRC and writes the record's status.
+// There is no second kernel and no per-tile workspace.
+//
+// CRC-32C without a CRC instruction: the pure CRC (zero init) is linear over GF(2), so
+//   * thread i CRCs its two 16-byte vectors (tile offsets 16 i and 16 i + 4096) with slice-by-4 table steps whose
+//     "advance" also skips the gap between them,
+//   * one multiplication by x^(8*(4080-16 i)) moves its partial to the end of the tile,
+//   * partials XOR together (warp shuffles, then 8 words of shared memory) into one word per tile.
+// The 0xFFFFFFFF init is XORed into the first four data bytes.
+#include <cstring>
+
+#include "tfrecord_common.cuh"
+
+namespace b2 {
+
+constexpr int kBufBytes = kTile + 128;   // tile + 32-byte halo, rounded so the second buffer stays 128-byte aligned
+constexpr int kHotMaxK = 32;             // one-hot through shared-memory blocks + bulk stores up to this many classes
+constexpr int kHotLabels = 256;          // labels per block (one per thread): one bulk store moves 1024*K bytes
+
+// ---------------------------------------------------------------- PTX: mbarrier + bulk async copies (TMA, 1-D)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------- arguments
+struct ParseArgs {
+    const uint8_t* shard;
+    uint64_t nbytes;                 // bytes that may be read from shard; ~0 = unknown (never read past a range end)
+    const uint64_t* rec_off;
+    const uint64_t* rec_len;
+    const b2_example_index* index;   // NULL: CRC only
+    b2_parse_sink sink;
+    const CrcTables* tab;
+    // tile -> record map.  Opened shard: tile2rec / tile_start / hdr (device-resident counts).  Otherwise uniform:
+    // tile w belongs to record w / tiles_x.
+    const uint32_t* tile2rec;
+    const uint32_t* tile_start;
+    const int64_t* hdr;
+    uint32_t tiles_x, n;
+    uint32_t q;                      // consecutive tiles per CTA
+    uint32_t* crc_acc;               // per record, zero on entry, zero again on exit
+    uint32_t* done;
+    int32_t* status;                 // per-record status (parse) ...
+    uint32_t* crc_out;               // ... or raw CRCs (b2_crc32c)
+    int64_t* n_bad;                  // hdr[4] of an opened shard, or NULL
+};
+
+struct __align__(16) TileJob {
+    uint64_t ts, d0, d1;
+    uint64_t img_off, img_len, tgt_off, tgt_len;
+    uint32_t r, tile, nt, cb, tail, flags;   // flags: 1 valid, 2 sink ok
+};
+
+__device__ __forceinline__ uint32_t tile_power(const CrcTables* tab, uint32_t j) {
+    return j < 2048 ? __ldg(&tab->tpow[j]) : xpow8(tab, (uint64_t)j * kTile);
+}
+
+// thread 0: describe tile w and start its copy into buf
+template <int kMode>
+__device__ __forceinline__ void make_job(const ParseArgs& a, uint32_t w, TileJob* j, uint8_t* buf, uint64_t* bar) {
+    uint32_t r, tile;
+    if (a.tile2rec) {
+        r = a.tile2rec[w];
+        tile = w - a.tile_start[r];
+    } else {
+        r = w / a.tiles_x;
+        tile = w - r * a.tiles_x;
+    }
+    const uint64_t d0 = a.rec_off[r], len = a.rec_len[r];
+    const uint32_t nt = record_tiles(d0, len);
+    j->r = r;
+    j->tile = tile;
+    j->nt = nt;
+    if (tile >= nt) {
+        j->flags = 0;
+        return;
+    }
+    const uint64_t d1 = d0 + len, ts = (d0 & ~15ull) + (uint64_t)tile * kTile, te = ts + kTile;
+    j->ts = ts;
+    j->d0 = d0;
+    j->d1 = d1;
+    uint32_t flags = 1;
+    j->img_off = j->img_len = j->tgt_off = j->tgt_len = 0;
+    if (kMode != B2_SINK_NONE && a.index != nullptr) {
+        const b2_example_index* ix = a.index + r;
+        bool ok = ix->status == 0;
+        const uint64_t il = ix->img_len, tl = ix->tgt_len;
+        if (kMode == B2_SINK_RAW) ok = ok && il <= a.sink.img_stride && tl <= a.sink.tgt_stride;
+        if (kMode == B2_SINK_NORM_ONEHOT) {
+            const uint64_t K = (uint64_t)a.sink.num_classes;
+            ok = ok && ix->img_kind == 1 && ix->tgt_kind == 1 && il * 4 <= a.sink.img_stride && tl * K * 4 <= a.sink.tgt_stride &&
+                 il < (1ull << 31) && tl * K < (1ull << 31);
+        }
+        if (ok) {
+            flags |= 2;
+            j->img_off = ix->img_off;
+            j->img_len = il;
+            j->tgt_off = ix->tgt_off;
+            j->tgt_len = tl;
+        }
+    }
+    j->flags = flags;
+    // bytes to stage: [ts, min(te + 32, d1)), never touching shard[lim...]
+    const uint64_t lim = a.nbytes != ~0ull ? a.nbytes : d1;
+    uint64_t want = (d1 + 15) & ~15ull;
+    if (want > te + 32) want = te + 32;
+    uint32_t cb, tail = 0;
+    if (len == 0) {
+        cb = 0;
+    } else if (want <= lim) {
+        cb = (uint32_t)(want - ts);
+    } else {
+        cb = (uint32_t)((lim - ts) & ~15ull);
+        const uint64_t end = d1 < lim ? d1 : lim;
+        tail = end > ts + cb ? (uint32_t)(end - ts - cb) : 0;
+    }
+    j->cb = cb;
+    j->tail = tail;
+    if (cb) {
+        mbar_expect_tx(bar, cb);
+        bulk_g2s(buf, a.shard + ts, cb, bar);
+    }
+}
+
+// raw byte copy of payload range [po, po+pl) (absolute) into dst, for the part owned by tile [ts, te)
+__device__ __forceinline__ void sink_raw(const uint32_t* buf32, const uint8_t* buf8, uint64_t ts, uint64_t te,
+                                         uint64_t po, uint64_t pl, uint8_t* dst) {
+    if (pl == 0 || po >= te || po + pl <= ts) return;
+    const bool al = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    const uint64_t lo = po > ts ? po : ts, hi = (po + pl < te) ? po + pl : te;  // absolute bytes in this tile
+    if (al) {
+        // 16-byte destination groups whose FIRST byte lies in the tile; last partial group done bytewise
+        const uint64_t g_lo = (lo - po + 15) >> 4, g_hi = (hi - po + 15) >> 4;
+        const uint64_t full = pl >> 4;
+        for (uint64_t g = g_lo + threadIdx.x; g < g_hi; g += blockDim.x) {
+            const uint32_t o = (uint32_t)(po + 16 * g - ts);
+            if (g < full) {
+                uint4 v;
+                v.x = smem_u32_unaligned(buf32, o);
+                v.y = smem_u32_unaligned(buf32, o + 4);
+                v.z = smem_u32_unaligned(buf32, o + 8);
+                v.w = smem_u32_unaligned(buf32, o + 12);
+                st_cs(reinterpret_cast<uint4*>(dst + 16 * g), v);
+            } else {
+                for (uint64_t b = 16 * g; b < pl; b++) dst[b] = buf8[o + (b - 16 * g)];
+            }
+        }
+    } else {
+        for (uint64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) dst[p - po] = buf8[p - ts];
+    }
+}
+
+// (x - mean) / std, bit-identical with IEEE division.  Fast path: q = d * r, corrected by one residual step
+// (r = correctly rounded 1/std): 3 FP32 instructions instead of the ~10 of a full division.  Whether the fast path
+// reproduces the division for EVERY byte value of EVERY band is checked once per CTA (256*C cases); if any case
+// differs (or std is 0 / non-finite) the whole launch uses the division.
+__device__ __forceinline__ float norm_fast(float d, float sd, float rc) {
+    const float q = __fmul_rn(d, rc);
+    const float rem = __fmaf_rn(-q, sd, d);
+    return __fmaf_rn(rem, rc, q);
+}
+
+__device__ inline void finalize_record(const ParseArgs& a, const TileJob& j) {
+    const uint32_t r = j.r;
+    const uint64_t d0 = j.d0, len = j.d1 - j.d0;
+    const bool want_crc = a.sink.verify_crc || a.crc_out;
+    uint32_t crc = 0;
+    if (want_crc) {
+        if (len < 4) {   // the init XOR does not fit in the message: bytewise
+            uint32_t s = 0xFFFFFFFFu;
+            for (uint64_t i = 0; i < len; i++) s = (s >> 8) ^ __ldg(&a.tab->t4[3][(s ^ a.shard[d0 + i]) & 0xff]);
+            crc = ~s;
+            atomicExch(&a.crc_acc[r], 0u);
+        } else {
+            uint32_t acc = atomicExch(&a.crc_acc[r], 0u);
+            // acc sits at the end of the last tile; un-advance by the zero padding after the record end
+            const uint64_t pad = (d0 & ~15ull) + (uint64_t)j.nt * kTile - j.d1;
+            acc = multmodp(__ldg(&a.tab->xinv16[pad >> 4]), acc);
+            acc = multmodp(__ldg(&a.tab->xinvb[pad & 15]), acc);
+            crc = ~acc;
+        }
+    }
+    a.done[r] = 0;
+    if (a.crc_out) {
+        a.crc_out[r] = crc;
+        return;
+    }
+    int32_t st = 0;
+    if (a.sink.verify_crc) {
+        uint32_t stored = ~mask_crc(crc);
+        if (a.nbytes == ~0ull || j.d1 + 4 <= a.nbytes) {
+            stored = 0;
+            for (int k = 0; k < 4; k++) stored |= (uint32_t)a.shard[j.d1 + k] << (8 * k);
+        }
+        if (stored != mask_crc(crc)) st = 1;
+    }
+    if (st == 0 && a.index && a.sink.mode != B2_SINK_NONE) {
+        const b2_example_index* ix = a.index + r;
+        if (ix->status != 0) st = 2;
+        else if (a.sink.mode == B2_SINK_RAW) {
+            if (ix->img_len > a.sink.img_stride || ix->tgt_len > a.sink.tgt_stride) st = 3;
+        } else {
+            const uint64_t K = (uint64_t)a.sink.num_classes;
+            if (ix->img_kind != 1 || ix->tgt_kind != 1) st = 2;
+            else if (ix->img_len * 4 > a.sink.img_stride || ix->tgt_len * K * 4 > a.sink.tgt_stride ||
+                     ix->img_len >= (1ull << 31) || ix->tgt_len * K >= (1ull << 31)) st = 3;
+        }
+    }
+    a.status[r] = st;
+    if (st != 0 && a.n_bad) atomicAdd(reinterpret_cast<unsigned long long*>(a.n_bad), 1ull);
+}
+
+// a(x)*b(x) mod P, fully unrolled and branch-free (5 instructions per bit instead of the rolled loop's 11)
+__device__ __forceinline__ uint32_t multmodp_fast(uint32_t a, uint32_t b) {
+    uint32_t p = 0;
+#pragma unroll
+    for (int k = 31; k >= 0; k--) {
+        if (a & (1u << k)) p ^= b;
+        b = (b & 1u) ? (b >> 1) ^ kPoly : (b >> 1);
+    }
+    return p;
+}
+
+// Per-thread running CRC state over the tiles of one record.  A thread owns vectors i and i+256 of every tile; the
+// distance from the end of one of its vectors to the start of its next one is always 4080 bytes, inside a tile and
+// from one tile to the next, so the same "consume 4 bytes and skip 4080" table step chains them all and the
+// expensive per-thread alignment (one GF(2)[x] multiplication) is paid once per run of tiles, not once per tile.
+// On return the state sits at (tile end + 16 i): run_flush() un-advances by 16 i.
+__device__ __forceinline__ uint32_t crc_tile_step(uint32_t s, const uint4* buf4, const CrcSmem* cs, const TileJob& j,
+                                                  bool interior) {
+    const int i = threadIdx.x;
+    uint4 v0 = buf4[i], v1 = buf4[i + 256];
+    if (!interior) {
+        v0 = mask_vec(v0, j.ts + 16ull * i, j.d0, j.d1);
+        v1 = mask_vec(v1, j.ts + 4096 + 16ull * i, j.d0, j.d1);
+        if (j.tile == 0 && i < 2) {  // init XOR lives in the first 4 data bytes, i.e. inside vectors 0/1 of tile 0
+            uint32_t w[4] = {v0.x, v0.y, v0.z, v0.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint64_t p = j.ts + 16ull * i + 4 * q + k;
+                    if (p >= j.d0 && p < j.d0 + 4) w[q] ^= 0xFFu << (8 * k);
+                }
+            v0 = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    s = adv4(cs->t4, s ^ v0.x);
+    s = adv4(cs->t4, s ^ v0.y);
+    s = adv4(cs->t4, s ^ v0.z);
+    s = adv4(cs->s, s ^ v0.w);
+    s = adv4(cs->t4, s ^ v1.x);
+    s = adv4(cs->t4, s ^ v1.y);
+    s = adv4(cs->t4, s ^ v1.z);
+    s = adv4(cs->s, s ^ v1.w);
+    return s;
+}
+
+struct Run {             // consecutive tiles of one record handled by this CTA (uniform across the CTA)
+    uint32_t r, nt, last_tile, tiles;
+    uint64_t d0, d1;
+    bool open;
+};
+
+// Close a run: fold the per-thread CRC states into the record accumulator, count the tiles, finalise the record
+// if this was its last outstanding run.  Called by all threads (contains __syncthreads).
+__device__ __forceinline__ void run_flush(const ParseArgs& a, Run& run, uint32_t& s, bool want_crc, uint32_t* red) {
+    const int tid = threadIdx.x;
+    const bool crc = want_crc && run.d1 - run.d0 >= 4;
+    if (crc) {
+        uint32_t t = multmodp_fast(__ldg(&a.tab->xinv16[tid]), s);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) t ^= __shfl_xor_sync(0xffffffffu, t, o);
+        if ((tid & 31) == 0) red[tid >> 5] = t;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (crc) {
+            uint32_t c = 0;
+#pragma unroll
+            for (int k = 0; k < kTileThreads / 32; k++) c ^= red[k];
+            c = multmodp_fast(tile_power(a.tab, run.nt - 1 - run.last_tile), c);
+            if (c) atomicXor(&a.crc_acc[run.r], c);
+        }
+        __threadfence();
+        const uint32_t old = atomicAdd(&a.done[run.r], run.tiles);
+        if (old + run.tiles == run.nt) {
+            __threadfence();
+            TileJob j;
+            j.r = run.r;
+            j.nt = run.nt;
+            j.d0 = run.d0;
+            j.d1 = run.d1;
+            finalize_record(a, j);
+        }
+    }
+    if (crc) __syncthreads();   // red[] may be rewritten by the next flush
+    s = 0;
+    run.open = false;
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(kTileThreads, kMode == B2_SINK_NORM_ONEHOT ? 4 : 6)
+fused_parse_kernel(const ParseArgs a) {
+    extern __shared__ __align__(128) uint8_t dyn[];
+    __shared__ CrcSmem cs;
+    __shared__ uint32_t red[kTileThreads / 32];
+    __shared__ TileJob job[2];
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ float s_mean[64], s_std[64], s_rcp[64];
+    __shared__ int s_exact_div;
+    const int tid = threadIdx.x;
+    const uint64_t total = a.hdr ? (uint64_t)a.hdr[2] : (uint64_t)a.n * a.tiles_x;
+    const uint64_t w0 = (uint64_t)blockIdx.x * a.q;
+    if (w0 >= total) return;
+    const uint32_t nq = (uint32_t)(total - w0 < a.q ? total - w0 : a.q);
+    const bool want_crc = a.sink.verify_crc || a.crc_out;
+    const int C = a.sink.channels, K = a.sink.num_classes;
+    const bool use_hot = K <= kHotMaxK;
+    float* hot_all = reinterpret_cast<float*>(dyn + 2 * kBufBytes);
+
+    if (want_crc) load_crc_tables(&cs, a.tab);
+    if (kMode == B2_SINK_NORM_ONEHOT) {
+        if (tid == 0) s_exact_div = 0;
+        for (int c = tid; c < C; c += kTileThreads) {
+            s_mean[c] = a.sink.mean[c];
+            s_std[c] = a.sink.std[c];
+            s_rcp[c] = __frcp_rn(a.sink.std[c]);
+        }
+        if (use_hot)
+            for (int i = tid; i < 2 * kHotLabels * K; i += kTileThreads) hot_all[i] = 0.0f;
+    }
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (kMode == B2_SINK_NORM_ONEHOT) {
+        int bad = 0;
+        for (int i = tid; i < C * 256; i += kTileThreads) {
+            const int c = i >> 8;
+            const float d = __fsub_rn((float)(i & 255), s_mean[c]);
+            bad |= __float_as_uint(norm_fast(d, s_std[c], s_rcp[c])) != __float_as_uint(__fdiv_rn(d, s_std[c]));
+        }
+        if (bad) s_exact_div = 1;
+    }
+    if (tid == 0) make_job<kMode>(a, (uint32_t)w0, &job[0], dyn, &bar[0]);
+    __syncthreads();
+    const bool exact_div = kMode == B2_SINK_NORM_ONEHOT && s_exact_div != 0;
+    // image loop stride: the largest S <= 256 with 4 S a multiple of C, so that a thread's four bytes always fall on
+    // the same four bands and their constants stay in registers
+    uint32_t img_S = kTileThreads;
+    if (kMode == B2_SINK_NORM_ONEHOT) {
+        const uint32_t m = (C % 4 == 0) ? C / 4 : ((C % 2 == 0) ? C / 2 : C);
+        img_S = kTileThreads - (kTileThreads % m);
+    }
+    uint32_t phase = 0;
+    uint32_t s = 0;                       // running CRC state of this thread
+    Run run;
+    run.open = false;
+    uint32_t hot_it = 0;                  // one-hot blocks issued so far (block = hot_it & 1)
+    uint32_t slot0 = 0xFFFFFFFFu, slot1 = 0xFFFFFFFFu;   // the float this thread set in block 0 / 1
+
+    for (uint32_t it = 0; it < nq; it++) {
+        const uint32_t b = it & 1;
+        if (tid == 0 && it + 1 < nq) make_job<kMode>(a, (uint32_t)(w0 + it + 1), &job[b ^ 1], dyn + (b ^ 1) * kBufBytes, &bar[b ^ 1]);
+        const TileJob j = job[b];
+        const bool valid = (j.flags & 1) != 0;
+        if (run.open && (!valid || j.r != run.r)) run_flush(a, run, s, want_crc, red);
+        if (valid) {
+            uint8_t* buf8w = dyn + b * kBufBytes;
+            if (j.cb) {
+                mbar_wait(&bar[b], (phase >> b) & 1);
+                phase ^= 1u << b;
+            }
+            if (j.tail) {
+                if (tid < (int)j.tail) buf8w[j.cb + tid] = a.shard[j.ts + j.cb + tid];
+                __syncthreads();
+            }
+            const uint4* buf4 = reinterpret_cast<const uint4*>(buf8w);
+            const uint32_t* buf32 = reinterpret_cast<const uint32_t*>(buf8w);
+            const uint8_t* buf8 = buf8w;
+            const uint64_t ts = j.ts, te = ts + kTile;
+            if (!run.open) {
+                run.open = true;
+                run.r = j.r;
+                run.nt = j.nt;
+                run.d0 = j.d0;
+                run.d1 = j.d1;
+                run.tiles = 0;
+            }
+            run.tiles++;
+            run.last_tile = j.tile;
+            if (want_crc && j.d1 - j.d0 >= 4) s = crc_tile_step(s, buf4, &cs, j, j.tile != 0 && te <= j.d1);
+            if (kMode == B2_SINK_RAW && (j.flags & 2)) {
+                if (a.sink.img_out)
+                    sink_raw(buf32, buf8, ts, te, j.img_off, j.img_len, static_cast<uint8_t*>(a.sink.img_out) + (uint64_t)j.r * a.sink.img_stride);
+                if (a.sink.tgt_out)
+                    sink_raw(buf32, buf8, ts, te, j.tgt_off, j.tgt_len, static_cast<uint8_t*>(a.sink.tgt_out) + (uint64_t)j.r * a.sink.tgt_stride);
+            }
+            if (kMode == B2_SINK_NORM_ONEHOT && (j.flags & 2)) {
+                // ---- uint8 image -> (x-mean)/std float32
+                if (a.sink.img_out && j.img_len && j.img_off < te && j.img_off + j.img_len > ts && (uint32_t)tid < img_S) {
+                    float* dst = reinterpret_cast<float*>(static_cast<uint8_t*>(a.sink.img_out) + (uint64_t)j.r * a.sink.img_stride);
+                    const uint64_t po = j.img_off;
+                    const uint32_t pl = (uint32_t)j.img_len;
+                    const uint64_t lo = po > ts ? po : ts, hi = (po + pl < te) ? po + pl : te;
+                    // float4 group g = image bytes [4g, 4g+4); owned by the tile that holds its first byte
+                    const uint32_t g_lo = (uint32_t)((lo - po + 3) >> 2), g_hi = (uint32_t)((hi - po + 3) >> 2), full = pl >> 2;
+                    const uint32_t base = (uint32_t)(po - ts);  // wraps when po < ts; base + 4g is back in [0, kTile)
+                    uint32_t g = g_lo + tid;
+                    float mu[4], sd[4], rc[4];
+                    {
+                        uint32_t ch = (4u * g) % (uint32_t)C;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            mu[k] = s_mean[ch];
+                            sd[k] = s_std[ch];
+                            rc[k] = s_rcp[ch];
+                            ch = (ch + 1 == (uint32_t)C) ? 0 : ch + 1;
+                        }
+                    }
+                    for (; g < g_hi; g += img_S) {
+                        const uint32_t x = smem_u32_unaligned(buf32, base + 4 * g);
+                        float f[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            // byte k -> float, exactly: 0x4B000000 | v is 2^23 + v
+                            const float v = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7540 + k)) - 8388608.0f;
+                            const float d = __fsub_rn(v, mu[k]);
+                            f[k] = exact_div ? __fdiv_rn(d, sd[k]) : norm_fast(d, sd[k], rc[k]);
+                        }
+                        if (g < full) {
+                            st_cs(reinterpret_cast<float4*>(dst) + g, make_float4(f[0], f[1], f[2], f[3]));
+                        } else {   // the payload's last 1..3 bytes
+                            if (4 * g + 0 < pl) dst[4 * g + 0] = f[0];
+                            if (4 * g + 1 < pl) dst[4 * g + 1] = f[1];
+                            if (4 * g + 2 < pl) dst[4 * g + 2] = f[2];
+                        }
+                    }
+                }
+                // ---- uint8 target -> one-hot float32
+                if (a.sink.tgt_out && j.tgt_len && j.tgt_off < te && j.tgt_off + j.tgt_len > ts) {
+                    float* dst = reinterpret_cast<float*>(static_cast<uint8_t*>(a.sink.tgt_out) + (uint64_t)j.r * a.sink.tgt_stride);
+                    const uint64_t po = j.tgt_off;
+                    const uint32_t pl = (uint32_t)j.tgt_len;
+                    const uint64_t lo = po > ts ? po : ts, hi = (po + pl < te) ? po + pl : te;
+                    const uint32_t base = (uint32_t)(po - ts);
+                    if (use_hot) {
+                        // The CTA fills a block of kHotLabels*K floats in shared memory — zero except ONE 1.0f per label,
+                        // so a label costs one 4-byte shared-memory write — and thread 0 pushes the block to HBM with a
+                        // single TMA bulk store; two blocks alternate so the store of one overlaps the fill of the other.
+                        // Work unit = 4 labels (4K floats: a whole number of 16-byte groups, 16-byte aligned in the
+                        // output); a unit belongs to the tile holding its first label, later labels may sit in the halo.
+                        const uint32_t j_lo = (uint32_t)((lo - po + 3) >> 2), j_hi = (uint32_t)((hi - po + 3) >> 2);
+                        const uint32_t L_beg = 4 * j_lo, L_end = (4 * j_hi < pl) ? 4 * j_hi : pl;
+                        for (uint32_t L0 = L_beg; L0 < L_end; L0 += kHotLabels, hot_it++) {
+                            const uint32_t hb = hot_it & 1;
+                            float* hot = hot_all + hb * kHotLabels * K;
+                            if (hot_it >= 2) {   // the bulk store that used this block two rounds ago must have read it
+                                if (tid == 0) bulk_wait_read<1>();
+                                __syncthreads();
+                            }
+                            const uint32_t old = hb ? slot1 : slot0;
+                            if (old != 0xFFFFFFFFu) hot[old] = 0.0f;
+                            uint32_t mine = 0xFFFFFFFFu;
+                            if (L0 + tid < L_end) {
+                                const uint32_t lab = buf8[base + L0 + tid];
+                                if (lab < (uint32_t)K) {
+                                    mine = tid * K + lab;
+                                    hot[mine] = 1.0f;
+                                }
+                            }
+                            if (hb) slot1 = mine; else slot0 = mine;
+                            fence_proxy_async();
+                            __syncthreads();
+                            const uint32_t nl = (L_end - L0 < (uint32_t)kHotLabels) ? L_end - L0 : (uint32_t)kHotLabels;
+                            const uint32_t nfl = nl * K, nb16 = (nfl * 4) & ~15u;
+                            if (tid == 0) {
+                                if (nb16) bulk_s2g(dst + (size_t)L0 * K, hot, nb16);
+                                bulk_commit();
+                            }
+                            if ((uint32_t)tid < (nfl & 3)) dst[(size_t)L0 * K + (nfl & ~3u) + tid] = hot[(nfl & ~3u) + tid];
+                        }
+                    } else {
+                        // generic path (K > 32): float4 group g holds one-hot floats [4g, 4g+4), owned by the tile of label 4g/K
+                        const uint32_t nfl = pl * (uint32_t)K;
+                        const uint32_t g_lo = (uint32_t)(((lo - po) * K + 3) >> 2), g_hi = (uint32_t)(((hi - po) * K + 3) >> 2), full = nfl >> 2;
+                        for (uint32_t g = g_lo + tid; g < g_hi; g += kTileThreads) {
+                            const uint32_t f0 = 4 * g;
+                            uint32_t l = f0 / (uint32_t)K;
+                            uint32_t cc = f0 - l * (uint32_t)K;
+                            float f[4];
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const uint32_t lab = (l < pl) ? buf8[base + l] : 0xFFFFFFFFu;
+                                f[k] = (lab == cc) ? 1.0f : 0.0f;
+                                if (++cc == (uint32_t)K) {
+                                    cc = 0;
+                                    l++;
+                                }
+                            }
+                            if (g < full) {
+                                st_cs(reinterpret_cast<float4*>(dst) + g, make_float4(f[0], f[1], f[2], f[3]));
+                            } else {
+                                if (f0 + 0 < nfl) dst[f0 + 0] = f[0];
+                                if (f0 + 1 < nfl) dst[f0 + 1] = f[1];
+                                if (f0 + 2 < nfl) dst[f0 + 2] = f[2];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();   // everyone is done with buffer b and job[b]
+    }
+    if (run.open) run_flush(a, run, s, want_crc, red);
+    if (kMode == B2_SINK_NORM_ONEHOT && tid == 0) bulk_wait_read<0>();   // shared memory must outlive the bulk stores
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+namespace {
+
+struct LaunchCfg {
+    bool ready = false;
+    int ctas_per_sm[3] = {0, 0, 0};
+};
+LaunchCfg g_cfg[64];
+
+size_t dyn_bytes(int mode, int K) {
+    size_t d = 2 * (size_t)kBufBytes;
+    if (mode == B2_SINK_NORM_ONEHOT && K <= kHotMaxK) d += (size_t)2 * kHotLabels * K * sizeof(float);
+    return d;
+}
+
+int launch_fused(b2_ctx* ctx, const ParseArgs& pa, uint64_t max_tiles, cudaStream_t s) {
+    LaunchCfg& cfg = g_cfg[ctx->device & 63];
+    if (!cfg.ready) {
+        B2_CUDA(cudaFuncSetAttribute(fused_parse_kernel<B2_SINK_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        B2_CUDA(cudaFuncSetAttribute(fused_parse_kernel<B2_SINK_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        B2_CUDA(cudaFuncSetAttribute(fused_parse_kernel<B2_SINK_NORM_ONEHOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        cfg.ready = true;
+    }
+    const unsigned grid = (unsigned)((max_tiles + pa.q - 1) / pa.q);
+    const size_t dyn = dyn_bytes(pa.sink.mode, pa.sink.num_classes);
+    switch (pa.sink.mode) {
+        case B2_SINK_NONE: fused_parse_kernel<B2_SINK_NONE><<<grid, kTileThreads, dyn, s>>>(pa); break;
+        case B2_SINK_RAW: fused_parse_kernel<B2_SINK_RAW><<<grid, kTileThreads, dyn, s>>>(pa); break;
+        default: fused_parse_kernel<B2_SINK_NORM_ONEHOT><<<grid, kTileThreads, dyn, s>>>(pa); break;
+    }
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int check_sink(const b2_parse_sink* sink, const char* who) {
+    if (sink->mode == B2_SINK_NORM_ONEHOT) {
+        B2_REQUIRE(sink->mean && sink->std && sink->channels >= 1 && sink->channels <= 64 && sink->num_classes >= 1,
+                   std::string(who) + ": NORM_ONEHOT needs mean/std, 1..64 channels and num_classes >= 1");
+        B2_REQUIRE((reinterpret_cast<uintptr_t>(sink->img_out) & 15) == 0 && (sink->img_stride & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(sink->tgt_out) & 15) == 0 && (sink->tgt_stride & 15) == 0,
+                   std::string(who) + ": NORM_ONEHOT outputs and strides must be 16-byte aligned");
+    } else {
+        B2_REQUIRE(sink->mode == B2_SINK_NONE || sink->mode == B2_SINK_RAW, std::string(who) + ": unknown sink mode");
+    }
+    return 0;
+}
+
+uint32_t tiles_per_cta() {
+    static int q = -1;
+    if (q < 0) {
+        const char* e = getenv("B2_PARSE_TILES_PER_CTA");
+        q = e ? atoi(e) : 2;
+        if (q < 1) q = 1;
+        if (q > 64) q = 64;
+    }
+    return (uint32_t)q;
+}
+
+}  // namespace
+
+extern "C" int b2_tfrecord_parse(b2_ctx* ctx, const uint8_t* shard, uint64_t nbytes, const uint64_t* rec_off,
+                                 const uint64_t* rec_len, const b2_example_index* index, int n,
+                                 uint64_t max_record_len, const b2_parse_sink* sink, int32_t* status,
+                                 b2_stream stream) {
+    B2_REQUIRE(ctx && shard && rec_off && rec_len && sink && status, "b2_tfrecord_parse: NULL argument");
+    B2_REQUIRE(n >= 0 && n <= (1 << 24), "b2_tfrecord_parse: n out of range");
+    B2_REQUIRE((reinterpret_cast<uintptr_t>(shard) & 15) == 0, "b2_tfrecord_parse: shard must be 16-byte aligned");
+    B2_REQUIRE(sink->mode == B2_SINK_NONE || index, "b2_tfrecord_parse: index required for a payload sink");
+    if (int e = check_sink(sink, "b2_tfrecord_parse")) return e;
+    if (n == 0) return 0;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint64_t tx = (max_record_len + 15 + kTile - 1) / kTile;
+    if (!tx) tx = 1;
+    B2_REQUIRE(tx * (uint64_t)n < (1ull << 32), "b2_tfrecord_parse: too many tiles for one call");
+    // per-record accumulators live in the context workspace: calls on one context must be stream-ordered
+    if (int e = ws_reserve(ctx, (size_t)n * 8, s)) return e;
+    B2_CUDA(cudaMemsetAsync(ctx->ws, 0, (size_t)n * 8, s));
+    uint32_t* acc = static_cast<uint32_t*>(ctx->ws);
+    ParseArgs pa{shard, nbytes, rec_off, rec_len, index, *sink, ctx->crc_dev, nullptr, nullptr, nullptr,
+                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(), acc, acc + n, status, nullptr, nullptr};
+    return launch_fused(ctx, pa, tx * (uint64_t)n, s);
+}
+
+extern "C" int b2_tfrecord_parse_table(b2_ctx* ctx, const uint8_t* shard, uint64_t nbytes, uint64_t max_records,
+                                       uint8_t* table, const b2_parse_sink* sink, int32_t* status, b2_stream stream) {
+    B2_REQUIRE(ctx && shard && table && sink && status, "b2_tfrecord_parse_table: NULL argument");
+    B2_REQUIRE(max_records >= 1 && max_records <= (1u << 24), "b2_tfrecord_parse_table: max_records out of range");
+    B2_REQUIRE((reinterpret_cast<uintptr_t>(shard) & 15) == 0 && (reinterpret_cast<uintptr_t>(table) & 15) == 0,
+               "b2_tfrecord_parse_table: shard and table must be 16-byte aligned");
+    if (int e = check_sink(sink, "b2_tfrecord_parse_table")) return e;
+    DeviceGuard g(ctx->device);
+    const TableView v = table_view(table, nbytes, max_records);
+    ParseArgs pa{shard, nbytes, v.rec_off, v.rec_len, v.index, *sink, ctx->crc_dev, v.tile2rec, v.tile_start, v.hdr,
+                 0, 0, tiles_per_cta(), v.crc_acc, v.done, status, nullptr, v.hdr + 4};
+    return launch_fused(ctx, pa, v.cap_tiles, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b2_crc32c(b2_ctx* ctx, const uint8_t* data, const uint64_t* offsets, const uint64_t* lens, int n,
+                         uint64_t max_len, uint32_t* crc_out, b2_stream stream) {
+    B2_REQUIRE(ctx && data && offsets && lens && crc_out, "b2_crc32c: NULL argument");
+    B2_REQUIRE(n >= 0 && n <= (1 << 24), "b2_crc32c: n out of range");
+    B2_REQUIRE((reinterpret_cast<uintptr_t>(data) & 15) == 0, "b2_crc32c: data must be 16-byte aligned");
+    if (n == 0) return 0;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint64_t tx = (max_len + 15 + kTile - 1) / kTile;
+    if (!tx) tx = 1;
+    B2_REQUIRE(tx * (uint64_t)n < (1ull << 32), "b2_crc32c: too many tiles for one call");
+    if (int e = ws_reserve(ctx, (size_t)n * 8, s)) return e;
+    B2_CUDA(cudaMemsetAsync(ctx->ws, 0, (size_t)n * 8, s));
+    uint32_t* acc = static_cast<uint32_t*>(ctx->ws);
+    b2_parse_sink sink;
+    memset(&sink, 0, sizeof(sink));
+    sink.mode = B2_SINK_NONE;
+    sink.verify_crc = 1;
+    ParseArgs pa{data, ~0ull, offsets, lens, nullptr, sink, ctx->crc_dev, nullptr, nullptr, nullptr,
+                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(), acc, acc + n, nullptr, crc_out, nullptr};
+    return launch_fused(ctx, pa, tx * (uint64_t)n, s);
+}

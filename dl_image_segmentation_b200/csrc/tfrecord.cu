@@ -22,513 +22,228 @@
 #include <cstring>
 #include <vector>
 
-#include "common.cuh"
+#include "tfrecord_common.cuh"
 
 namespace b2 {
 
-struct CrcSmem {
-    uint32_t t4[4][256];
-    uint32_t s[4][256];
-};
-
-__device__ __forceinline__ uint32_t adv4(const uint32_t (*t)[256], uint32_t x) {
-    return t[0][x & 0xff] ^ t[1][(x >> 8) & 0xff] ^ t[2][(x >> 16) & 0xff] ^ t[3][x >> 24];
-}
-
-__device__ __forceinline__ void load_crc_tables(CrcSmem* sm, const CrcTables* tab) {
-    const uint32_t* g0 = &tab->t4[0][0];
-    const uint32_t* g1 = &tab->s4096[0][0];
-    uint32_t* d0 = &sm->t4[0][0];
-    uint32_t* d1 = &sm->s[0][0];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-        d0[i] = __ldg(g0 + i);
-        d1[i] = __ldg(g1 + i);
-    }
-}
-
-// zero the bytes of a 16-byte vector at absolute address a that fall outside [lo, hi)
-__device__ __forceinline__ uint4 mask_vec(uint4 v, uint64_t a, uint64_t lo, uint64_t hi) {
-    if (a >= lo && a + 16 <= hi) return v;
-    uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        uint32_t m = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint64_t p = a + 4 * q + j;
-            if (p >= lo && p < hi) m |= 0xFFu << (8 * j);
-        }
-        w[q] &= m;
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-// CRC partial of one staged tile (vectors already zero outside [d0,d1)).  Returns the CTA-wide XOR in thread 0.
-// init_lo/init_hi: absolute range whose bytes get the 0xFF init XOR (d0..d0+4), only relevant for tile 0.
-__device__ __forceinline__ uint32_t tile_crc(const uint4* buf4, const CrcSmem* cs, const CrcTables* tab, uint64_t ts,
-                                             uint64_t d0, uint64_t d1, bool first_tile, uint32_t* red) {
-    const int i = threadIdx.x;
-    uint4 v0 = mask_vec(buf4[i], ts + 16ull * i, d0, d1);
-    uint4 v1 = mask_vec(buf4[i + 256], ts + 4096 + 16ull * i, d0, d1);
-    if (first_tile && i < 2) {  // init XOR lives in the first 4 data bytes, i.e. inside vectors 0/1 of tile 0
-        uint32_t w[4] = {v0.x, v0.y, v0.z, v0.w};
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint64_t p = ts + 16ull * i + 4 * q + j;
-                if (p >= d0 && p < d0 + 4) w[q] ^= 0xFFu << (8 * j);
-            }
-        v0 = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-    uint32_t s = adv4(cs->t4, v0.x);
-    s = adv4(cs->t4, s ^ v0.y);
-    s = adv4(cs->t4, s ^ v0.z);
-    s = adv4(cs->s, s ^ v0.w);
-    s = adv4(cs->t4, s ^ v1.x);
-    s = adv4(cs->t4, s ^ v1.y);
-    s = adv4(cs->t4, s ^ v1.z);
-    s = adv4(cs->t4, s ^ v1.w);
-    s = multmodp(__ldg(&tab->fix[i]), s);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) s ^= __shfl_xor_sync(0xffffffffu, s, o);
-    if ((i & 31) == 0) red[i >> 5] = s;
-    __syncthreads();
-    uint32_t r = 0;
-    if (i == 0) {
-#pragma unroll
-        for (int k = 0; k < kTileThreads / 32; k++) r ^= red[k];
-    }
-    return r;
-}
-
-// stage [ts, ts + kTile + 32) of `base` into shared memory, zero beyond `nbytes`
-__device__ __forceinline__ void stage_tile(uint4* buf4, const uint8_t* base, uint64_t ts, uint64_t nbytes) {
-    for (int k = threadIdx.x; k < kTile / 16 + 2; k += blockDim.x) {
-        const uint64_t a = ts + 16ull * k;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (a + 16 <= nbytes) {
-            v = ld_nc(reinterpret_cast<const uint4*>(base + a));
-        } else if (a < nbytes) {
-            uint32_t w[4] = {0, 0, 0, 0};
-            for (uint64_t p = a; p < nbytes; p++) w[(p - a) >> 2] |= (uint32_t)base[p] << (8 * ((p - a) & 3));
-            v = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-        buf4[k] = v;
-    }
-}
-
-__device__ __forceinline__ uint32_t smem_u32_unaligned(const uint32_t* buf32, uint32_t off) {
-    const uint32_t w0 = buf32[off >> 2], w1 = buf32[(off >> 2) + 1];
-    return __funnelshift_r(w0, w1, (off & 3) * 8);
-}
-
-// ---------------------------------------------------------------------------------------------- parse
-struct ParseArgs {
-    const uint8_t* shard;
-    uint64_t nbytes;
-    const uint64_t* rec_off;
-    const uint64_t* rec_len;
-    const b2_example_index* index;  // may be NULL (CRC-only over raw ranges)
-    b2_parse_sink sink;
-    const CrcTables* tab;
-    uint32_t* tilecrc;  // [n][tiles_x]
-    uint32_t tiles_x;
-};
-
-// raw byte copy of payload range [po, po+pl) (absolute) into dst, for the part owned by tile [ts, te)
-__device__ __forceinline__ void sink_raw(const uint32_t* buf32, const uint8_t* buf8, uint64_t ts, uint64_t te,
-                                         uint64_t po, uint64_t pl, uint8_t* dst) {
-    if (pl == 0 || po >= te || po + pl <= ts) return;
-    const bool al = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
-    const uint64_t lo = po > ts ? po : ts, hi = (po + pl < te) ? po + pl : te;  // absolute bytes in this tile
-    if (al) {
-        // 16-byte destination groups whose FIRST byte lies in the tile; last partial group done bytewise
-        const uint64_t g_lo = (lo - po + 15) >> 4, g_hi = (hi - po + 15) >> 4;
-        const uint64_t full = pl >> 4;
-        for (uint64_t g = g_lo + threadIdx.x; g < g_hi; g += blockDim.x) {
-            const uint32_t o = (uint32_t)(po + 16 * g - ts);
-            if (g < full) {
-                uint4 v;
-                v.x = smem_u32_unaligned(buf32, o);
-                v.y = smem_u32_unaligned(buf32, o + 4);
-                v.z = smem_u32_unaligned(buf32, o + 8);
-                v.w = smem_u32_unaligned(buf32, o + 12);
-                st_cs(reinterpret_cast<uint4*>(dst + 16 * g), v);
-            } else {
-                for (uint64_t b = 16 * g; b < pl; b++) dst[b] = buf8[o + (b - 16 * g)];
-            }
-        }
-        // bytes of the first (partial) group when the payload starts mid-tile are covered: g_lo*16 >= lo-po.
-        // bytes between lo-po and g_lo*16 belong to a group whose first byte is in the previous tile.
-    } else {
-        for (uint64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) dst[p - po] = buf8[p - ts];
-    }
-}
-
-// Dynamic shared memory of the NORM_ONEHOT sink:
-//   lut  : C*256 floats, lut[c*256+v] = (float(v) - mean[c]) / std[c] computed ONCE per CTA with IEEE division —
-//          the per-pixel work is then one shared-memory lookup, and the result is bit-identical to dividing.
-//   hot  : per warp, labels_per_iter*K floats kept at zero; a label sets ONE float to 1.0f, the warp streams the
-//          block out with coalesced 128-bit stores and clears that float again.  No per-element compare/select.
-constexpr int kLutMaxC = 8;
-constexpr int kHotMaxK = 32;
-__host__ __device__ inline int hot_labels_per_iter(int K) { return K <= 16 ? 64 : 32; }
-
-template <int kMode>
-__global__ void __launch_bounds__(kTileThreads)
-parse_kernel(const ParseArgs a) {
-    __shared__ __align__(16) uint4 buf4[kTile / 16 + 2];
-    __shared__ CrcSmem cs;
-    __shared__ uint32_t red[kTileThreads / 32];
-    __shared__ float s_mean[64], s_std[64];
-    extern __shared__ __align__(16) uint8_t dyn_smem[];
-    const int tid = threadIdx.x;
-    const int r = blockIdx.y;
-    const uint32_t tile = blockIdx.x;
-    const uint64_t d0 = a.rec_off[r], len = a.rec_len[r];
-    const uint64_t d1 = d0 + len;
-    const uint64_t A = d0 & ~15ull;
-    const uint64_t ts = A + (uint64_t)tile * kTile, te = ts + kTile;
-    if (len == 0 || ts >= d1) return;
-    if (a.sink.verify_crc) load_crc_tables(&cs, a.tab);
-    b2_example_index ix;
-    bool sink_ok = false;
-    const int C = a.sink.channels, K = a.sink.num_classes;
-    const bool use_lut = C <= kLutMaxC, use_hot = K <= kHotMaxK;
-    float* lut = reinterpret_cast<float*>(dyn_smem);
-    float* hot_all = lut + (use_lut ? C * 256 : 0);
-    if (kMode != B2_SINK_NONE && a.index != nullptr) {
-        ix = a.index[r];
-        sink_ok = ix.status == 0;
-    }
-    bool has_img = false, has_tgt = false;
-    if (kMode == B2_SINK_NORM_ONEHOT && sink_ok) {
-        sink_ok = ix.img_kind == 1 && ix.tgt_kind == 1 && ix.img_len * 4 <= a.sink.img_stride &&
-                  ix.tgt_len * (uint64_t)K * 4 <= a.sink.tgt_stride && ix.img_len < (1ull << 31) &&
-                  ix.tgt_len * (uint64_t)K < (1ull << 31);
-        has_img = sink_ok && a.sink.img_out && ix.img_len && ix.img_off < te && ix.img_off + ix.img_len > ts;
-        has_tgt = sink_ok && a.sink.tgt_out && ix.tgt_len && ix.tgt_off < te && ix.tgt_off + ix.tgt_len > ts;
-        if (has_img) {
-            if (use_lut) {
-                for (int i = tid; i < C * 256; i += kTileThreads)
-                    lut[i] = __fdiv_rn((float)(i & 255) - a.sink.mean[i >> 8], a.sink.std[i >> 8]);
-            } else {
-                for (int c = tid; c < C && c < 64; c += kTileThreads) {
-                    s_mean[c] = a.sink.mean[c];
-                    s_std[c] = a.sink.std[c];
-                }
-            }
-        }
-        if (has_tgt && use_hot) {
-            const int nfl = hot_labels_per_iter(K) * K * (kTileThreads / 32);
-            for (int i = tid; i < nfl; i += kTileThreads) hot_all[i] = 0.0f;
-        }
-    }
-    stage_tile(buf4, a.shard, ts, a.nbytes < d1 ? a.nbytes : d1);
-    __syncthreads();
-    if (a.sink.verify_crc) {
-        const uint32_t c = tile_crc(buf4, &cs, a.tab, ts, d0, d1, tile == 0, red);
-        if (tid == 0) a.tilecrc[(size_t)r * a.tiles_x + tile] = c;
-    }
-    if (kMode == B2_SINK_NONE || !sink_ok) return;
-    const uint32_t* buf32 = reinterpret_cast<const uint32_t*>(buf4);
-    const uint8_t* buf8 = reinterpret_cast<const uint8_t*>(buf4);
-    if (kMode == B2_SINK_RAW) {
-        if (ix.img_len > a.sink.img_stride || ix.tgt_len > a.sink.tgt_stride) return;
-        if (a.sink.img_out)
-            sink_raw(buf32, buf8, ts, te, ix.img_off, ix.img_len, static_cast<uint8_t*>(a.sink.img_out) + (uint64_t)r * a.sink.img_stride);
-        if (a.sink.tgt_out)
-            sink_raw(buf32, buf8, ts, te, ix.tgt_off, ix.tgt_len, static_cast<uint8_t*>(a.sink.tgt_out) + (uint64_t)r * a.sink.tgt_stride);
-        return;
-    }
-    // ---- NORM_ONEHOT: uint8 image -> (x-mean)/std float32 ; uint8 target -> one-hot float32
-    if (has_img) {
-        float* dst = reinterpret_cast<float*>(static_cast<uint8_t*>(a.sink.img_out) + (uint64_t)r * a.sink.img_stride);
-        const uint64_t po = ix.img_off;
-        const uint32_t pl = (uint32_t)ix.img_len;
-        const uint64_t lo = po > ts ? po : ts, hi = (po + pl < te) ? po + pl : te;
-        // float4 group g = image bytes [4g, 4g+4); owned by the tile that holds its first byte
-        const uint32_t g_lo = (uint32_t)((lo - po + 3) >> 2), g_hi = (uint32_t)((hi - po + 3) >> 2), full = pl >> 2;
-        const uint32_t base = (uint32_t)(po - ts);  // wraps when po < ts; base + 4g is back in [0, kTile)
-        uint32_t g = g_lo + tid;
-        uint32_t c0 = (4u * g) % (uint32_t)C;
-        const uint32_t cstep = (4u * kTileThreads) % (uint32_t)C;
-        for (; g < g_hi; g += kTileThreads) {
-            const uint32_t x = smem_u32_unaligned(buf32, base + 4 * g);
-            float f[4];
-            uint32_t c = c0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t v = (x >> (8 * k)) & 0xFFu;
-                f[k] = use_lut ? lut[(c << 8) + v] : __fdiv_rn((float)v - s_mean[c], s_std[c]);
-                c = (c + 1 == (uint32_t)C) ? 0 : c + 1;
-            }
-            if (g < full) {
-                st_cs(reinterpret_cast<float4*>(dst) + g, make_float4(f[0], f[1], f[2], f[3]));
-            } else {
-                for (uint32_t b = 4 * g; b < pl; b++) dst[b] = f[b - 4 * g];
-            }
-            c0 += cstep;
-            if (c0 >= (uint32_t)C) c0 -= (uint32_t)C;
-        }
-    }
-    if (has_tgt) {
-        float* dst = reinterpret_cast<float*>(static_cast<uint8_t*>(a.sink.tgt_out) + (uint64_t)r * a.sink.tgt_stride);
-        const uint64_t po = ix.tgt_off;
-        const uint32_t pl = (uint32_t)ix.tgt_len;
-        const uint64_t lo = po > ts ? po : ts, hi = (po + pl < te) ? po + pl : te;
-        const uint32_t base = (uint32_t)(po - ts);
-        if (use_hot) {
-            // work unit = 4 labels (4K floats: always a whole number of float4s, 16-byte aligned in the output);
-            // a unit belongs to the tile holding its first label, later labels may sit in the 32-byte halo
-            const uint32_t j_lo = (uint32_t)((lo - po + 3) >> 2), j_hi = (uint32_t)((hi - po + 3) >> 2);
-            const uint32_t L_beg = 4 * j_lo, L_end = (4 * j_hi < pl) ? 4 * j_hi : pl;
-            const int Lw = hot_labels_per_iter(K);
-            const int warp = tid >> 5, lane = tid & 31;
-            float* hot = hot_all + warp * Lw * K;
-            for (uint32_t L0 = L_beg + warp * Lw; L0 < L_end; L0 += (kTileThreads / 32) * Lw) {
-                const uint32_t nl = (L_end - L0 < (uint32_t)Lw) ? L_end - L0 : (uint32_t)Lw;
-                uint32_t slot[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-#pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    const uint32_t li = lane + 32 * i;
-                    if (li < nl) {
-                        const uint32_t lab = buf8[base + L0 + li];
-                        if (lab < (uint32_t)K) {
-                            slot[i] = li * K + lab;
-                            hot[slot[i]] = 1.0f;
-                        }
-                    }
-                }
-                __syncwarp();
-                const uint32_t nfl = nl * K, nf4 = nfl >> 2;
-                float4* o4 = reinterpret_cast<float4*>(dst + (size_t)L0 * K);
-                const float4* h4 = reinterpret_cast<const float4*>(hot);
-                for (uint32_t i = lane; i < nf4; i += 32) st_cs(o4 + i, h4[i]);
-                if (lane < (nfl & 3)) dst[(size_t)L0 * K + 4 * nf4 + lane] = hot[4 * nf4 + lane];
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 2; i++)
-                    if (slot[i] != 0xFFFFFFFFu) hot[slot[i]] = 0.0f;
-            }
-        } else {
-            // generic path (K > 32): float4 group g holds one-hot floats [4g, 4g+4), owned by the tile of label 4g/K
-            const uint32_t nfl = pl * (uint32_t)K;
-            const uint32_t g_lo = (uint32_t)(((lo - po) * K + 3) >> 2), g_hi = (uint32_t)(((hi - po) * K + 3) >> 2), full = nfl >> 2;
-            for (uint32_t g = g_lo + tid; g < g_hi; g += kTileThreads) {
-                const uint32_t f0 = 4 * g;
-                uint32_t l = f0 / (uint32_t)K;
-                uint32_t c = f0 - l * (uint32_t)K;
-                float f[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t lab = (l < pl) ? buf8[base + l] : 0xFFFFFFFFu;
-                    f[k] = (lab == c) ? 1.0f : 0.0f;
-                    if (++c == (uint32_t)K) {
-                        c = 0;
-                        l++;
-                    }
-                }
-                if (g < full) {
-                    st_cs(reinterpret_cast<float4*>(dst) + g, make_float4(f[0], f[1], f[2], f[3]));
-                } else {
-                    for (uint32_t b = f0; b < nfl; b++) dst[b] = f[b - f0];
-                }
-            }
-        }
-    }
-}
-
-// x^(8*n) mod P via the x^(2^k) table
-__device__ inline uint32_t xpow8(const CrcTables* tab, uint64_t n) {
-    uint32_t p = 0x80000000u;
-    int k = 3;
-    while (n) {
-        if (n & 1) p = multmodp(__ldg(&tab->x2n[k & 63]), p);
-        n >>= 1;
-        k++;
-    }
-    return p;
-}
-
-// Fold the per-tile partials of one record into its CRC-32C (one warp per record, all lanes return it).
-__device__ inline uint32_t fold_record_crc(const uint32_t* tc, uint32_t nt, uint64_t d0, uint64_t len,
-                                           const uint8_t* base, const CrcTables* tab) {
-    const int lane = threadIdx.x & 31;
-    if (len < 4) {  // the init XOR does not fit in the message: do it bytewise
-        uint32_t s = 0xFFFFFFFFu;
-        for (uint64_t i = 0; i < len; i++) s = (s >> 8) ^ __ldg(&tab->t4[3][(s ^ base[d0 + i]) & 0xff]);
-        return ~s;
-    }
-    const uint32_t q = (nt + 31) / 32;
-    const uint32_t b = lane * q, e = (b + q < nt) ? b + q : nt;
-    const uint32_t xt = tab->xtile;
-    uint32_t s = 0;
-    for (uint32_t t = b; t < e; t++) s = multmodp(xt, s) ^ tc[t];
-    // lane chunks: advance lane's partial past the tiles of the following lanes
-    uint32_t acc = 0;
-    const uint32_t xq = xpow8(tab, (uint64_t)q * kTile);
-    for (int l = 0; l < 32; l++) {
-        const uint32_t sl = __shfl_sync(0xffffffffu, s, l);
-        const uint32_t bl = l * q;
-        if (bl >= nt) break;
-        const uint32_t el = (bl + q < nt) ? bl + q : nt;
-        // Horner across lanes: previous accumulation moves forward by this lane's tile count
-        acc = ((el - bl) == q ? multmodp(xq, acc) : multmodp(xpow8(tab, (uint64_t)(el - bl) * kTile), acc)) ^ sl;
-    }
-    // acc sits at the end of the last tile; un-advance by the zero padding after the record end
-    const uint64_t A = d0 & ~15ull;
-    const uint64_t pad = A + (uint64_t)nt * kTile - (d0 + len);
-    acc = multmodp(__ldg(&tab->xinv16[pad >> 4]), acc);
-    acc = multmodp(__ldg(&tab->xinvb[pad & 15]), acc);
-    return ~acc;
-}
-
-__device__ __forceinline__ uint32_t mask_crc(uint32_t c) { return ((c >> 15) | (c << 17)) + 0xa282ead8u; }
-
-struct FinalArgs {
-    const uint8_t* shard;
-    uint64_t nbytes;
-    const uint64_t* rec_off;
-    const uint64_t* rec_len;
-    const b2_example_index* index;
-    b2_parse_sink sink;
-    const CrcTables* tab;
-    const uint32_t* tilecrc;
-    uint32_t tiles_x;
-    int n;
-    int32_t* status;    // parse: per-record status
-    uint32_t* crc_out;  // b2_crc32c: raw CRCs
-};
-
-__global__ void __launch_bounds__(256) parse_final_kernel(const FinalArgs a) {
-    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (r >= a.n) return;
-    const uint64_t d0 = a.rec_off[r], len = a.rec_len[r];
-    const uint64_t A = d0 & ~15ull;
-    const uint32_t nt = len ? (uint32_t)((d0 + len - A + kTile - 1) / kTile) : 0;
-    uint32_t crc = 0;
-    if (a.sink.verify_crc || a.crc_out) crc = fold_record_crc(a.tilecrc + (size_t)r * a.tiles_x, nt, d0, len, a.shard, a.tab);
-    if (lane != 0) return;
-    if (a.crc_out) {
-        a.crc_out[r] = crc;
-        return;
-    }
-    int32_t st = 0;
-    if (a.sink.verify_crc) {
-        uint32_t stored = 0;
-        if (d0 + len + 4 <= a.nbytes)
-            for (int j = 0; j < 4; j++) stored |= (uint32_t)a.shard[d0 + len + j] << (8 * j);
-        else
-            stored = ~mask_crc(crc);
-        if (stored != mask_crc(crc)) st = 1;
-    }
-    if (st == 0 && a.index && a.sink.mode != B2_SINK_NONE) {
-        const b2_example_index ix = a.index[r];
-        if (ix.status != 0) st = 2;
-        else if (a.sink.mode == B2_SINK_RAW) {
-            if (ix.img_len > a.sink.img_stride || ix.tgt_len > a.sink.tgt_stride) st = 3;
-        } else {
-            if (ix.img_kind != 1 || ix.tgt_kind != 1) st = 2;
-            else if (ix.img_len * 4 > a.sink.img_stride || ix.tgt_len * (uint64_t)a.sink.num_classes * 4 > a.sink.tgt_stride ||
-                     ix.img_len >= (1ull << 31) || ix.tgt_len * (uint64_t)a.sink.num_classes >= (1ull << 31)) st = 3;
-        }
-    }
-    a.status[r] = st;
-}
-
 // ---------------------------------------------------------------------------------------------- scan
-// Frames are a linked list (each length tells where the next header is).  Fast path: if the first record's
-// stride divides the shard, every thread checks "its" header at i*stride; when all lengths agree the
-// sequential walk would visit exactly those offsets (induction), so the result is identical.  Otherwise
-// thread 0 walks the chain.
-__device__ inline uint64_t rd_u64(const uint8_t* p) {
+// Frames are a linked list (each length tells where the next header is), so the walk is inherently serial and,
+// done naively, pays one cold HBM round trip (~1 us) per record.  Records of one shard have nearly the same
+// length (fixed-size chips + a short identifier), so the CTA works in rounds of kScanR records:
+//   1. all threads prefetch, with coalesced 128-bit loads, a +-kScanHW byte window around the PREDICTED position
+//      of each of the next kScanR headers (prediction = position of the current header + k * last stride),
+//   2. thread 0 walks the chain reading lengths from shared memory (falling back to a global read, and ending
+//      the round, when a header lies outside its window) — exactly the positions the sequential reader visits,
+//   3. one thread per visited header verifies its masked length CRC and publishes offset / length.
+// The result (record table, count, status) is identical to RecordReader's sequential walk for any input.
+constexpr int kScanThreads = 512;
+constexpr int kScanR = 64;
+constexpr int kScanHW = 256;
+constexpr int kScanWB = 2 * kScanHW + 32;   // bytes per window (multiple of 16)
+
+__device__ __forceinline__ uint32_t crc_hdr8(uint64_t l, const CrcTables* tab) {
+    uint32_t s = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s = (s >> 8) ^ __ldg(&tab->t4[3][(s ^ (uint32_t)(l >> (8 * i))) & 0xff]);
+    return mask_crc(~s);
+}
+__device__ __forceinline__ uint64_t rd_u64(const uint8_t* p) {
     uint64_t v = 0;
+#pragma unroll
     for (int i = 0; i < 8; i++) v |= (uint64_t)p[i] << (8 * i);
     return v;
 }
-__device__ inline uint32_t rd_u32(const uint8_t* p) {
+__device__ __forceinline__ uint32_t rd_u32(const uint8_t* p) {
     uint32_t v = 0;
+#pragma unroll
     for (int i = 0; i < 4; i++) v |= (uint32_t)p[i] << (8 * i);
     return v;
 }
-__device__ inline bool header_ok(const uint8_t* p, const CrcTables* tab) {
-    uint32_t s = 0xFFFFFFFFu;
-    for (int i = 0; i < 8; i++) s = (s >> 8) ^ __ldg(&tab->t4[3][(s ^ p[i]) & 0xff]);
-    return mask_crc(~s) == rd_u32(p + 8);
-}
+struct ScanOut {
+    uint64_t* offs;
+    uint64_t* lens;
+    int64_t* hdr;          // [0] n, [1] status, [2] total tiles, [3] max len, [4] n_bad (zeroed here)
+    uint32_t* tile_start;  // cap + 1 entries, or NULL (legacy b2_tfrecord_scan)
+    uint32_t* crc_acc;     // cap entries zeroed here, or NULL
+    uint32_t* done;
+    int hdr_words;         // how many int64 of hdr exist (2 legacy, 8 table)
+};
 
-__global__ void __launch_bounds__(1024)
-scan_kernel(const uint8_t* __restrict__ shard, uint64_t nbytes, uint64_t cap, uint64_t* __restrict__ offs,
-            uint64_t* __restrict__ lens, int64_t* __restrict__ result, const CrcTables* __restrict__ tab) {
-    __shared__ int bad;
-    __shared__ uint64_t s_stride;
-    if (threadIdx.x == 0) {
-        bad = 0;
-        s_stride = 0;
-        if (nbytes >= 16) {
-            const uint64_t l0 = rd_u64(shard);
-            if (l0 <= nbytes - 16 && (nbytes % (l0 + 16)) == 0) s_stride = l0 + 16;
+__global__ void __launch_bounds__(kScanThreads)
+scan_kernel(const uint8_t* __restrict__ shard, uint64_t nbytes, uint64_t cap, ScanOut o,
+            const CrcTables* __restrict__ tab) {
+    __shared__ __align__(16) uint8_t win[kScanR][kScanWB];
+    __shared__ uint64_t w_lo[kScanR];            // absolute start of each window
+    __shared__ uint64_t r_pos[kScanR], r_len[kScanR];
+    __shared__ uint64_t s_pos, s_est, s_n;
+    __shared__ int s_m, s_state;                 // records visited this round; 0 continue, 1 clean end, 2 error, 3 cap
+    __shared__ unsigned long long s_first_bad, s_maxlen;
+    __shared__ uint32_t s_warp[kScanThreads / 32];
+    const int tid = threadIdx.x;
+    if (o.crc_acc)
+        for (uint64_t i = tid; i < cap; i += kScanThreads) {
+            o.crc_acc[i] = 0;
+            o.done[i] = 0;
         }
+    if (tid == 0) {
+        s_pos = 0;
+        s_n = 0;
+        s_est = 0;
+        s_state = nbytes == 0 ? 1 : 0;
+        s_first_bad = ~0ull;
+        s_maxlen = 0;
     }
     __syncthreads();
-    const uint64_t stride = s_stride;
-    if (nbytes == 0) {
-        if (threadIdx.x == 0) { result[0] = 0; result[1] = 0; }
-        return;
-    }
-    if (stride) {
-        const uint64_t n = nbytes / stride;
-        if (n <= cap) {
-            for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
-                const uint8_t* h = shard + i * stride;
-                if (rd_u64(h) != stride - 16 || !header_ok(h, tab)) bad = 1;
+    while (s_state == 0) {
+        const uint64_t base = s_pos, n0 = s_n;
+        uint64_t est = s_est;
+        if (est == 0) {                          // first round: learn the stride from the first header (1 round trip)
+            if (tid == 0) {
+                uint64_t e = 0;
+                if (nbytes - base >= 12) {
+                    const uint64_t l = rd_u64(shard + base);
+                    if (l <= nbytes) e = l + 16;
+                }
+                s_est = e ? e : 16;
             }
             __syncthreads();
-            if (!bad) {
-                for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
-                    offs[i] = i * stride + 12;
-                    lens[i] = stride - 16;
-                }
-                if (threadIdx.x == 0) { result[0] = (int64_t)n; result[1] = 0; }
-                return;
-            }
+            est = s_est;
         }
+        // 1. prefetch windows
+        for (int i = tid; i < kScanR * (kScanWB / 16); i += kScanThreads) {
+            const int k = i / (kScanWB / 16), j = i % (kScanWB / 16);
+            const uint64_t c = base + (uint64_t)k * est;   // may overflow for garbage est: harmless, only a prefetch hint
+            const uint64_t lo = c > (uint64_t)kScanHW ? (c - kScanHW) & ~15ull : 0;
+            if (j == 0) w_lo[k] = lo;
+            const uint64_t a = lo + 16ull * j;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (a < nbytes && lo <= nbytes) v = ld16_bounded(shard, a, nbytes);
+            reinterpret_cast<uint4*>(&win[k][0])[j] = v;
+        }
+        __syncthreads();
+        // 2. serial walk over shared memory
+        if (tid == 0) {
+            uint64_t pos = base, n = n0, last_stride = est;
+            int m = 0, state = 0;
+            for (int k = 0; k < kScanR; k++) {
+                if (pos >= nbytes) { state = 1; break; }
+                if (nbytes - pos < 12) { state = 2; break; }
+                const bool in_win = pos >= w_lo[k] && pos + 12 <= w_lo[k] + kScanWB;
+                const uint64_t l = in_win ? rd_u64(&win[k][pos - w_lo[k]]) : rd_u64(shard + pos);
+                const bool bounds_bad = l > nbytes - pos - 12 || nbytes - pos - 12 - l < 4;
+                if (n >= cap) {                  // RecordReader checks this header's CRC and bounds before the count
+                    state = (crc_hdr8(l, tab) != rd_u32(shard + pos + 8) || bounds_bad) ? 2 : 3;
+                    break;
+                }
+                if (bounds_bad) { state = 2; break; }   // status 1 at this record whatever its length CRC says
+                r_pos[m] = pos;
+                r_len[m] = l;
+                m++;
+                n++;
+                last_stride = 16 + l;
+                pos += 16 + l;
+                if (!in_win) break;              // prediction lost: re-anchor the windows
+            }
+            s_m = m;
+            s_pos = pos;
+            s_n = n;
+            s_est = last_stride;
+            s_state = state;
+        }
+        __syncthreads();
+        // 3. parallel header CRC check + publish (entries past a corrupt header are cut off by the final count)
+        const int m = s_m;
+        for (int k = tid; k < m; k += kScanThreads) {
+            const uint64_t pos = r_pos[k], l = r_len[k];
+            if (crc_hdr8(l, tab) != rd_u32(shard + pos + 8)) atomicMin(&s_first_bad, (unsigned long long)(n0 + k));
+            o.offs[n0 + k] = pos + 12;
+            o.lens[n0 + k] = l;
+        }
+        __syncthreads();
+        if (tid == 0 && s_first_bad != ~0ull) {
+            s_n = s_first_bad;
+            s_state = 2;
+        }
+        __syncthreads();
     }
+    const uint64_t n = s_n;
+    const int64_t st = s_state == 1 ? 0 : (s_state == 3 ? 2 : 1);
+    if (tid == 0) {
+        o.hdr[0] = (int64_t)n;
+        o.hdr[1] = st;
+    }
+    if (o.hdr_words < 5) return;
+    // tile prefix over the n records (records past a corruption are not counted)
+    uint64_t maxlen = 0;
+    const uint32_t per = (uint32_t)((n + kScanThreads - 1) / kScanThreads);
+    const uint64_t k0 = (uint64_t)tid * per, k1 = (k0 + per < n) ? k0 + per : n;
+    uint32_t sum = 0;
+    for (uint64_t k = k0; k < k1; k++) {
+        const uint64_t l = o.lens[k];
+        sum += record_tiles(o.offs[k], l);
+        maxlen = l > maxlen ? l : maxlen;
+    }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if ((tid & 31) >= d) inc += t;
+    }
+    if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
+    if (tid == 0) s_maxlen = 0;
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    uint64_t pos = 0, n = 0;
-    int64_t st = 0;
-    while (pos < nbytes) {
-        if (nbytes - pos < 12) { st = 1; break; }
-        const uint64_t l = rd_u64(shard + pos);
-        if (!header_ok(shard + pos, tab)) { st = 1; break; }
-        if (l > nbytes - pos - 12 || nbytes - pos - 12 - l < 4) { st = 1; break; }
-        if (n >= cap) { st = 2; break; }
-        offs[n] = pos + 12;
-        lens[n] = l;
-        n++;
-        pos += 16 + l;
+    uint32_t wbase = 0;
+    for (int w = 0; w < (tid >> 5); w++) wbase += s_warp[w];
+    uint32_t run = wbase + inc - sum;
+    for (uint64_t k = k0; k < k1; k++) {
+        o.tile_start[k] = run;
+        run += record_tiles(o.offs[k], o.lens[k]);
     }
-    result[0] = (int64_t)n;
-    result[1] = st;
+    atomicMax(&s_maxlen, (unsigned long long)maxlen);
+    __syncthreads();
+    if (tid == kScanThreads - 1) {
+        o.tile_start[n] = run;
+        o.hdr[2] = (int64_t)run;
+        o.hdr[3] = (int64_t)s_maxlen;
+        o.hdr[4] = 0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- index
-// One thread per record walks the protobuf structure.  Everything is bounds-checked
-// against the record; a malformed message sets status 1 instead of faulting.
+// One WARP per record walks the protobuf structure.  All 32 lanes execute the same walk over a
+// 512-byte window of the record held in shared memory; when the walk leaves the window the warp reloads it with
+// one coalesced 128-bit load per lane, so a record costs a handful of HBM round trips (its header bytes sit in
+// three clusters: before the image payload, between the payloads, after the target payload) instead of one per
+// byte.  Everything is bounds-checked against the record; a malformed message sets status 1 instead of faulting.
+constexpr int kIdxWarps = 8;
+constexpr int kIdxWin = 512;
+struct Win {
+    const uint8_t* g;
+    uint64_t nbytes;   // bytes that may be read from g
+    uint8_t* s;        // this warp's kIdxWin bytes of shared memory
+    uint64_t lo;       // window = [lo, lo + kIdxWin); ~0 = empty
+};
+__device__ __forceinline__ uint32_t win_byte(Win& w, uint64_t p) {
+    if (p - w.lo >= (uint64_t)kIdxWin) {           // warp-uniform
+        __syncwarp();
+        w.lo = p & ~15ull;
+        const uint64_t a = w.lo + 16ull * (threadIdx.x & 31);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (a < w.nbytes) v = ld16_bounded(w.g, a, w.nbytes);
+        reinterpret_cast<uint4*>(w.s)[threadIdx.x & 31] = v;
+        __syncwarp();
+    }
+    return w.s[p - w.lo];
+}
 struct Cursor {
-    const uint8_t* b;
     uint64_t p, end;
     bool ok;
 };
-__device__ inline uint64_t rd_varint(Cursor& c) {
+__device__ inline uint64_t rd_varint(Win& w, Cursor& c) {
     uint64_t v = 0;
     for (int s = 0; s < 70; s += 7) {
         if (c.p >= c.end) { c.ok = false; return 0; }
-        const uint8_t x = c.b[c.p++];
+        const uint32_t x = win_byte(w, c.p++);
         v |= (uint64_t)(x & 0x7F) << s;
         if (!(x & 0x80)) return v;
     }
@@ -536,20 +251,20 @@ __device__ inline uint64_t rd_varint(Cursor& c) {
     return 0;
 }
 // reads a tag and, for LEN fields, the sub-range; skips other wire types. returns field number (0 on end/error)
-__device__ inline uint32_t next_field(Cursor& c, int& wt, uint64_t& v0, uint64_t& v1) {
+__device__ inline uint32_t next_field(Win& w, Cursor& c, int& wt, uint64_t& v0, uint64_t& v1) {
     if (!c.ok || c.p >= c.end) return 0;
-    const uint64_t tag = rd_varint(c);
+    const uint64_t tag = rd_varint(w, c);
     if (!c.ok) return 0;
     wt = (int)(tag & 7);
     const uint32_t f = (uint32_t)(tag >> 3);
     if (wt == 0) {
-        v0 = rd_varint(c);
+        v0 = rd_varint(w, c);
     } else if (wt == 1) {
         v0 = c.p; v1 = c.p + 8; c.p += 8;
     } else if (wt == 5) {
         v0 = c.p; v1 = c.p + 4; c.p += 4;
     } else if (wt == 2) {
-        const uint64_t n = rd_varint(c);
+        const uint64_t n = rd_varint(w, c);
         if (!c.ok || n > c.end - c.p) { c.ok = false; return 0; }
         v0 = c.p; v1 = c.p + n; c.p += n;
     } else {
@@ -560,56 +275,66 @@ __device__ inline uint32_t next_field(Cursor& c, int& wt, uint64_t& v0, uint64_t
     if (f == 0) { c.ok = false; return 0; }
     return f;
 }
-__device__ inline bool key_is(const uint8_t* b, uint64_t s, uint64_t e, const char* lit, int n) {
+__device__ inline bool key_is(Win& w, uint64_t s, uint64_t e, const char* lit, int n) {
     if (e - s != (uint64_t)n) return false;
     for (int i = 0; i < n; i++)
-        if (b[s + i] != (uint8_t)lit[i]) return false;
+        if (win_byte(w, s + i) != (uint32_t)(uint8_t)lit[i]) return false;
     return true;
 }
 
-__global__ void __launch_bounds__(128)
-index_kernel(const uint8_t* __restrict__ shard, const uint64_t* __restrict__ rec_off,
-             const uint64_t* __restrict__ rec_len, int n, b2_example_index* __restrict__ out) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kIdxWarps * 32)
+index_kernel(const uint8_t* __restrict__ shard, uint64_t nbytes, const uint64_t* __restrict__ rec_off,
+             const uint64_t* __restrict__ rec_len, int n, b2_example_index* __restrict__ out,
+             const int64_t* __restrict__ n_dev, const uint32_t* __restrict__ tile_start, uint32_t* __restrict__ tile2rec) {
+    __shared__ __align__(16) uint8_t s_win[kIdxWarps][kIdxWin];
+    const int r = blockIdx.x * kIdxWarps + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n_dev && (int64_t)r >= n_dev[0]) return;   // opened shard: the record count is only known on the device
     if (r >= n) return;
+    const uint64_t d0 = rec_off[r], dl = rec_len[r];
+    if (tile2rec) {
+        const uint32_t t0 = tile_start[r], t1 = tile_start[r + 1];
+        for (uint32_t t = t0 + lane; t < t1; t += 32) tile2rec[t] = (uint32_t)r;
+    }
+    Win w{shard, nbytes < d0 + dl ? nbytes : d0 + dl, &s_win[threadIdx.x >> 5][0], ~0ull - kIdxWin};
     b2_example_index ix;
     memset(&ix, 0, sizeof(ix));
     int have[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // img, h, w, c, tgt, th, tw, id : 1 ok, -1 wrong type/count
     int64_t dims[5] = {0, 0, 0, 0, 0};
-    Cursor ex{shard, rec_off[r], rec_off[r] + rec_len[r], true};
+    Cursor ex{d0, d0 + dl, true};
     int wt; uint64_t a, b;
-    while (uint32_t f = next_field(ex, wt, a, b)) {
+    while (uint32_t f = next_field(w, ex, wt, a, b)) {
         if (f != 1 || wt != 2) continue;  // Example.features
-        Cursor fs{shard, a, b, true};
+        Cursor fs{a, b, true};
         int wt2; uint64_t a2, b2v;
-        while (uint32_t f2 = next_field(fs, wt2, a2, b2v)) {
+        while (uint32_t f2 = next_field(w, fs, wt2, a2, b2v)) {
             if (f2 != 1 || wt2 != 2) continue;  // Features.feature map entry
-            Cursor en{shard, a2, b2v, true};
+            Cursor en{a2, b2v, true};
             int wt3; uint64_t a3, b3;
             uint64_t ks = 0, ke = 0, vs = 0, ve = 0;
             bool hk = false, hv = false;
-            while (uint32_t f3 = next_field(en, wt3, a3, b3)) {
+            while (uint32_t f3 = next_field(w, en, wt3, a3, b3)) {
                 if (f3 == 1 && wt3 == 2) { ks = a3; ke = b3; hk = true; }
                 else if (f3 == 2 && wt3 == 2) { vs = a3; ve = b3; hv = true; }
             }
             if (!en.ok) { ex.ok = false; break; }
             if (!hk) continue;
             int which = -1;
-            if (key_is(shard, ks, ke, "image/image_data", 16)) which = 0;
-            else if (key_is(shard, ks, ke, "image/height", 12)) which = 1;
-            else if (key_is(shard, ks, ke, "image/width", 11)) which = 2;
-            else if (key_is(shard, ks, ke, "image/channels", 14)) which = 3;
-            else if (key_is(shard, ks, ke, "target/target_data", 18)) which = 4;
-            else if (key_is(shard, ks, ke, "target/height", 13)) which = 5;
-            else if (key_is(shard, ks, ke, "target/width", 12)) which = 6;
-            else if (key_is(shard, ks, ke, "identifier", 10)) which = 7;
+            if (key_is(w, ks, ke, "image/image_data", 16)) which = 0;
+            else if (key_is(w, ks, ke, "image/height", 12)) which = 1;
+            else if (key_is(w, ks, ke, "image/width", 11)) which = 2;
+            else if (key_is(w, ks, ke, "image/channels", 14)) which = 3;
+            else if (key_is(w, ks, ke, "target/target_data", 18)) which = 4;
+            else if (key_is(w, ks, ke, "target/height", 13)) which = 5;
+            else if (key_is(w, ks, ke, "target/width", 12)) which = 6;
+            else if (key_is(w, ks, ke, "identifier", 10)) which = 7;
             if (which < 0) continue;
             // Feature oneof: last member present wins
             int kind = 0; uint64_t ls = 0, le = 0;
             if (hv) {
-                Cursor fe{shard, vs, ve, true};
+                Cursor fe{vs, ve, true};
                 int wt4; uint64_t a4, b4;
-                while (uint32_t f4 = next_field(fe, wt4, a4, b4)) {
+                while (uint32_t f4 = next_field(w, fe, wt4, a4, b4)) {
                     if (wt4 == 2 && f4 >= 1 && f4 <= 3) { kind = (int)f4; ls = a4; le = b4; }
                 }
                 if (!fe.ok) { ex.ok = false; break; }
@@ -617,9 +342,9 @@ index_kernel(const uint8_t* __restrict__ shard, const uint64_t* __restrict__ rec
             // the list message: field 1 repeated
             uint64_t ps = 0, pe = 0; int count = 0; int64_t ival = 0; bool packed_ok = true;
             if (kind) {
-                Cursor li{shard, ls, le, true};
+                Cursor li{ls, le, true};
                 int wt5; uint64_t a5, b5;
-                while (uint32_t f5 = next_field(li, wt5, a5, b5)) {
+                while (uint32_t f5 = next_field(w, li, wt5, a5, b5)) {
                     if (f5 != 1) continue;
                     if (kind == 1) {
                         if (wt5 == 2) { ps = a5; pe = b5; count++; }
@@ -628,8 +353,8 @@ index_kernel(const uint8_t* __restrict__ shard, const uint64_t* __restrict__ rec
                         else if (wt5 == 5) { packed_ok = false; }          // unpacked fixed32: not supported on device
                     } else {
                         if (wt5 == 2) {
-                            Cursor pk{shard, a5, b5, true};
-                            while (pk.ok && pk.p < pk.end) { ival = (int64_t)rd_varint(pk); count++; }
+                            Cursor pk{a5, b5, true};
+                            while (pk.ok && pk.p < pk.end) { ival = (int64_t)rd_varint(w, pk); count++; }
                             if (!pk.ok) li.ok = false;
                         } else if (wt5 == 0) { ival = (int64_t)a5; count++; }
                     }
@@ -659,7 +384,7 @@ index_kernel(const uint8_t* __restrict__ shard, const uint64_t* __restrict__ rec
         for (int k = 0; k < 8; k++)
             if (have[k] != 1) st = 2;
     ix.status = st;
-    out[r] = ix;
+    if (lane == 0) out[r] = ix;
 }
 
 // ---------------------------------------------------------------------------------------------- build
@@ -832,88 +557,13 @@ __global__ void __launch_bounds__(256) build_final_kernel(const BuildArgs a) {
 
 using namespace b2;
 
-static int launch_parse(b2_ctx* ctx, const ParseArgs& pa, int n, uint32_t tiles_x, cudaStream_t s) {
-    dim3 grid(tiles_x, n);
-    switch (pa.sink.mode) {
-        case B2_SINK_NONE: parse_kernel<B2_SINK_NONE><<<grid, kTileThreads, 0, s>>>(pa); break;
-        case B2_SINK_RAW: parse_kernel<B2_SINK_RAW><<<grid, kTileThreads, 0, s>>>(pa); break;
-        default: {
-            const int C = pa.sink.channels, K = pa.sink.num_classes;
-            size_t dyn = (C <= kLutMaxC ? (size_t)C * 256 * sizeof(float) : 0) +
-                         (K <= kHotMaxK ? (size_t)hot_labels_per_iter(K) * K * (kTileThreads / 32) * sizeof(float) : 0);
-            static bool attr_set[64] = {false};
-            if (!attr_set[ctx->device & 63]) {
-                B2_CUDA(cudaFuncSetAttribute(parse_kernel<B2_SINK_NORM_ONEHOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
-                attr_set[ctx->device & 63] = true;
-            }
-            parse_kernel<B2_SINK_NORM_ONEHOT><<<grid, kTileThreads, dyn, s>>>(pa);
-        } break;
-    }
-    ctx->launches++;
-    B2_CUDA(cudaGetLastError());
-    return 0;
-}
-
-extern "C" int b2_tfrecord_parse(b2_ctx* ctx, const uint8_t* shard, uint64_t nbytes, const uint64_t* rec_off,
-                                 const uint64_t* rec_len, const b2_example_index* index, int n,
-                                 uint64_t max_record_len, const b2_parse_sink* sink, int32_t* status,
-                                 b2_stream stream) {
-    B2_REQUIRE(ctx && shard && rec_off && rec_len && sink && status, "b2_tfrecord_parse: NULL argument");
-    B2_REQUIRE(n >= 0 && n <= 65535, "b2_tfrecord_parse: n must be in [0,65535] per call");
-    B2_REQUIRE((reinterpret_cast<uintptr_t>(shard) & 15) == 0, "b2_tfrecord_parse: shard must be 16-byte aligned");
-    B2_REQUIRE(sink->mode == B2_SINK_NONE || index, "b2_tfrecord_parse: index required for a payload sink");
-    if (sink->mode == B2_SINK_NORM_ONEHOT) {
-        B2_REQUIRE(sink->mean && sink->std && sink->channels >= 1 && sink->channels <= 64 && sink->num_classes >= 1,
-                   "b2_tfrecord_parse: NORM_ONEHOT needs mean/std, 1..64 channels and num_classes >= 1");
-        B2_REQUIRE((reinterpret_cast<uintptr_t>(sink->img_out) & 15) == 0 && (sink->img_stride & 15) == 0 &&
-                   (reinterpret_cast<uintptr_t>(sink->tgt_out) & 15) == 0 && (sink->tgt_stride & 15) == 0,
-                   "b2_tfrecord_parse: NORM_ONEHOT outputs and strides must be 16-byte aligned");
-    }
-    if (n == 0) return 0;
-    DeviceGuard g(ctx->device);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const uint32_t tiles_x = (uint32_t)((max_record_len + 15 + kTile - 1) / kTile) + 0;
-    B2_REQUIRE(tiles_x >= 1 || max_record_len == 0, "b2_tfrecord_parse: bad max_record_len");
-    const uint32_t tx = tiles_x ? tiles_x : 1;
-    if (int e = ws_reserve(ctx, (size_t)n * tx * sizeof(uint32_t), s)) return e;
-    ParseArgs pa{shard, nbytes, rec_off, rec_len, index, *sink, ctx->crc_dev, static_cast<uint32_t*>(ctx->ws), tx};
-    if (int e = launch_parse(ctx, pa, n, tx, s)) return e;
-    FinalArgs fa{shard, nbytes, rec_off, rec_len, index, *sink, ctx->crc_dev, static_cast<uint32_t*>(ctx->ws), tx, n, status, nullptr};
-    parse_final_kernel<<<(n * 32 + 255) / 256, 256, 0, s>>>(fa);
-    ctx->launches++;
-    B2_CUDA(cudaGetLastError());
-    return 0;
-}
-
-extern "C" int b2_crc32c(b2_ctx* ctx, const uint8_t* data, const uint64_t* offsets, const uint64_t* lens, int n,
-                         uint64_t max_len, uint32_t* crc_out, b2_stream stream) {
-    B2_REQUIRE(ctx && data && offsets && lens && crc_out, "b2_crc32c: NULL argument");
-    B2_REQUIRE(n >= 0 && n <= 65535, "b2_crc32c: n must be in [0,65535] per call");
-    B2_REQUIRE((reinterpret_cast<uintptr_t>(data) & 15) == 0, "b2_crc32c: data must be 16-byte aligned");
-    if (n == 0) return 0;
-    DeviceGuard g(ctx->device);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    uint32_t tx = (uint32_t)((max_len + 15 + kTile - 1) / kTile);
-    if (!tx) tx = 1;
-    if (int e = ws_reserve(ctx, (size_t)n * tx * sizeof(uint32_t), s)) return e;
-    b2_parse_sink sink;
-    memset(&sink, 0, sizeof(sink));
-    sink.mode = B2_SINK_NONE;
-    sink.verify_crc = 1;
-    ParseArgs pa{data, ~0ull, offsets, lens, nullptr, sink, ctx->crc_dev, static_cast<uint32_t*>(ctx->ws), tx};
-    if (int e = launch_parse(ctx, pa, n, tx, s)) return e;
-    FinalArgs fa{data, ~0ull, offsets, lens, nullptr, sink, ctx->crc_dev, static_cast<uint32_t*>(ctx->ws), tx, n, nullptr, crc_out};
-    parse_final_kernel<<<(n * 32 + 255) / 256, 256, 0, s>>>(fa);
-    ctx->launches++;
-    B2_CUDA(cudaGetLastError());
-    return 0;
-}
-
 extern "C" int b2_tfrecord_scan(b2_ctx* ctx, const uint8_t* shard, uint64_t nbytes, uint64_t max_records,
                                 uint64_t* rec_off, uint64_t* rec_len, int64_t* result, b2_stream stream) {
     B2_REQUIRE(ctx && (shard || nbytes == 0) && rec_off && rec_len && result, "b2_tfrecord_scan: NULL argument");
+    B2_REQUIRE((reinterpret_cast<uintptr_t>(shard) & 15) == 0, "b2_tfrecord_scan: shard must be 16-byte aligned");
     DeviceGuard g(ctx->device);
-    scan_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(shard, nbytes, max_records, rec_off, rec_len, result, ctx->crc_dev);
+    ScanOut o{rec_off, rec_len, result, nullptr, nullptr, nullptr, 2};
+    scan_kernel<<<1, kScanThreads, 0, static_cast<cudaStream_t>(stream)>>>(shard, nbytes, max_records, o, ctx->crc_dev);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;
@@ -923,10 +573,50 @@ extern "C" int b2_tfrecord_index(b2_ctx* ctx, const uint8_t* shard, const uint64
                                  int n, b2_example_index* out, b2_stream stream) {
     B2_REQUIRE(ctx && shard && rec_off && rec_len && out, "b2_tfrecord_index: NULL argument");
     B2_REQUIRE(n >= 0, "b2_tfrecord_index: n < 0");
+    B2_REQUIRE((reinterpret_cast<uintptr_t>(shard) & 15) == 0, "b2_tfrecord_index: shard must be 16-byte aligned");
     if (n == 0) return 0;
     DeviceGuard g(ctx->device);
-    index_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(shard, rec_off, rec_len, n, out);
+    index_kernel<<<(n + kIdxWarps - 1) / kIdxWarps, kIdxWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        shard, ~0ull, rec_off, rec_len, n, out, nullptr, nullptr, nullptr);
     ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" uint64_t b2_tfrecord_table_bytes(uint64_t shard_nbytes, uint64_t max_records) {
+    return table_bytes(shard_nbytes, max_records);
+}
+
+extern "C" int b2_tfrecord_table_layout(uint64_t shard_nbytes, uint64_t max_records, uint64_t offsets[8]) {
+    B2_REQUIRE(offsets, "b2_tfrecord_table_layout: NULL argument");
+    B2_REQUIRE(max_records >= 1 && max_records <= (1u << 24), "b2_tfrecord_table_layout: max_records out of range");
+    const TableView v = table_view(nullptr, shard_nbytes, max_records);
+    offsets[0] = reinterpret_cast<uintptr_t>(v.hdr);
+    offsets[1] = reinterpret_cast<uintptr_t>(v.rec_off);
+    offsets[2] = reinterpret_cast<uintptr_t>(v.rec_len);
+    offsets[3] = reinterpret_cast<uintptr_t>(v.index);
+    offsets[4] = reinterpret_cast<uintptr_t>(v.tile_start);
+    offsets[5] = reinterpret_cast<uintptr_t>(v.tile2rec);
+    offsets[6] = v.cap_tiles;
+    offsets[7] = table_bytes(shard_nbytes, max_records);
+    return 0;
+}
+
+extern "C" int b2_tfrecord_open(b2_ctx* ctx, const uint8_t* shard, uint64_t nbytes, uint64_t max_records, uint8_t* table,
+                                b2_stream stream) {
+    B2_REQUIRE(ctx && (shard || nbytes == 0) && table, "b2_tfrecord_open: NULL argument");
+    B2_REQUIRE(max_records >= 1 && max_records <= (1u << 24), "b2_tfrecord_open: max_records out of range");
+    B2_REQUIRE((reinterpret_cast<uintptr_t>(table) & 15) == 0, "b2_tfrecord_open: table must be 16-byte aligned");
+    B2_REQUIRE((reinterpret_cast<uintptr_t>(shard) & 15) == 0, "b2_tfrecord_open: shard must be 16-byte aligned");
+    B2_REQUIRE(nbytes < (1ull << 44), "b2_tfrecord_open: shard too large");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const TableView v = table_view(table, nbytes, max_records);
+    ScanOut o{v.rec_off, v.rec_len, v.hdr, v.tile_start, v.crc_acc, v.done, 8};
+    scan_kernel<<<1, kScanThreads, 0, s>>>(shard, nbytes, max_records, o, ctx->crc_dev);
+    index_kernel<<<(unsigned)((max_records + kIdxWarps - 1) / kIdxWarps), kIdxWarps * 32, 0, s>>>(
+        shard, nbytes, v.rec_off, v.rec_len, (int)max_records, v.index, v.hdr, v.tile_start, v.tile2rec);
+    ctx->launches += 2;
     B2_CUDA(cudaGetLastError());
     return 0;
 }

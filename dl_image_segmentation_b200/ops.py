@@ -207,13 +207,14 @@ def crc32c(data, offsets, lens, device=None):
 
 
 class ShardIndex:
-    """A shard resident on the device plus its frame table and per-record feature locations."""
+    """A shard resident on the device plus its frame table and per-record feature locations (host copies included)."""
 
-    def __init__(self, shard, nbytes, n, rec_off, rec_len, index_dev, index, lens_host):
+    def __init__(self, shard, nbytes, n, rec_off, rec_len, index_dev, index, lens_host, table=None):
         self.shard, self.nbytes, self.n = shard, nbytes, n
         self.rec_off, self.rec_len, self.index_dev, self.index = rec_off, rec_len, index_dev, index
         self.max_len = int(lens_host.max()) if n else 0
         self.lens_host = lens_host
+        self.table = table
 
     def identifiers(self, shard_host=None):
         """identifier bytes of every record (small D2H gathers)."""
@@ -224,35 +225,105 @@ class ShardIndex:
         return out
 
 
-def open_shard(data, device=None, with_index=True, nbytes=None):
-    """Upload (if needed), walk the frames and locate the features.  One small D2H read-back (the tables)."""
+_layout_cache = {}
+
+
+def table_layout(nbytes, max_records):
+    """(offsets[8]) of a shard table: hdr, rec_off, rec_len, index, tile_start, tile2rec, cap_tiles, total bytes."""
+    key = (int(nbytes), int(max_records))
+    lay = _layout_cache.get(key)
+    if lay is None:
+        arr = (ctypes.c_uint64 * 8)()
+        check(lib().b2_tfrecord_table_layout(key[0], key[1], arr))
+        lay = _layout_cache[key] = tuple(int(x) for x in arr)
+        if len(_layout_cache) > 4096:
+            _layout_cache.clear()
+    return lay
+
+
+class ShardTable:
+    """Device-resident description of one opened shard (b2_tfrecord_open).  Nothing here synchronises until
+    header() / fetch() is called, so open -> parse chains can be enqueued shard after shard."""
+
+    def __init__(self, shard, nbytes, max_records, table=None):
+        self.shard, self.nbytes, self.max_records = shard, int(nbytes), int(max_records)
+        self.layout = table_layout(self.nbytes, self.max_records)
+        need = self.layout[7]
+        if table is None or table.numel() < need:
+            table = torch.empty((need,), dtype=torch.uint8, device=shard.device)
+        self.table = table
+        self._hdr = None
+
+    def _view(self, k, nbytes, dtype):
+        o = self.layout[k]
+        return self.table[o:o + nbytes].view(dtype)
+
+    @property
+    def hdr_dev(self):
+        return self._view(0, 64, torch.int64)
+
+    @property
+    def rec_off(self):
+        return self._view(1, 8 * self.max_records, torch.int64)
+
+    @property
+    def rec_len(self):
+        return self._view(2, 8 * self.max_records, torch.int64)
+
+    @property
+    def index_dev(self):
+        return self._view(3, ctypes.sizeof(_lib.ExampleIndex) * self.max_records, torch.uint8)
+
+    def header(self):
+        """(records, scan status, tiles, longest record, records with parse status != 0) — one small D2H read."""
+        h = self.hdr_dev.cpu().numpy()
+        return int(h[0]), int(h[1]), int(h[2]), int(h[3]), int(h[4])
+
+    def check(self, what="shard"):
+        """Raise what TensorFlow raises: DataLossError for a corrupt frame / data CRC, B2Error for a full table."""
+        n, st, _, _, bad = self.header()
+        if st == 2:
+            raise B2Error("%s holds more than max_records=%d records" % (what, self.max_records))
+        if st != 0:
+            raise DataLossError("corrupted record #%d in %s (bad frame or length CRC)" % (n, what))
+        if bad:
+            raise DataLossError("%d record(s) of %s failed the data CRC or the feature template" % (bad, what))
+        return n
+
+
+def open_shard_async(data, device=None, max_records=4096, nbytes=None, table=None):
+    """Upload (if needed) and enqueue frame scan + feature index on the current stream.  No host synchronisation."""
     ctx = get_ctx(device)
     shard = to_device(data, ctx.device)
     if shard.dtype != torch.uint8 or shard.dim() != 1:
         raise B2Error("open_shard: shard must be a flat uint8 buffer")
     nbytes = int(shard.numel()) if nbytes is None else int(nbytes)
-    cap = 1 << 12
+    st = ShardTable(shard, nbytes, max_records, table)
+    check(lib().b2_tfrecord_open(ctx.handle, ptr(shard), nbytes, st.max_records, ptr(st.table), ctx.stream()))
+    return st
+
+
+def open_shard(data, device=None, with_index=True, nbytes=None, max_records=4096):
+    """Upload (if needed), walk the frames and locate the features; ONE small D2H read-back (the table)."""
+    ctx = get_ctx(device)
+    cap = int(max_records)
     while True:
-        rec_off = torch.empty((cap,), dtype=torch.int64, device=ctx.device)
-        rec_len = torch.empty((cap,), dtype=torch.int64, device=ctx.device)
-        res = torch.zeros((2,), dtype=torch.int64, device=ctx.device)
-        check(lib().b2_tfrecord_scan(ctx.handle, ptr(shard), nbytes, cap, ptr(rec_off), ptr(rec_len), ptr(res), ctx.stream()))
-        n, st = (int(v) for v in res.cpu())
-        if st == 2:
+        st = open_shard_async(data, ctx.device, cap, nbytes)
+        data = st.shard
+        lay = st.layout
+        host = st.table[:lay[4]].cpu().numpy()          # hdr + rec_off + rec_len + index in one copy
+        n, status = int(host[:8].view(np.int64)[0]), int(host[8:16].view(np.int64)[0])
+        if status == 2:
             cap *= 16
             continue
-        if st != 0:
+        if status != 0:
             raise DataLossError("corrupted record #%d (bad frame or length CRC)" % n)
         break
-    lens_host = rec_len[:n].cpu().numpy().astype(np.uint64) if n else np.zeros(0, np.uint64)
-    index_dev = index = None
-    if with_index and n:
-        index_dev = torch.empty((n * ctypes.sizeof(_lib.ExampleIndex),), dtype=torch.uint8, device=ctx.device)
-        check(lib().b2_tfrecord_index(ctx.handle, ptr(shard), ptr(rec_off), ptr(rec_len), n, ptr(index_dev), ctx.stream()))
-        index = index_dev.cpu().numpy().view(np.dtype(_lib.EXAMPLE_INDEX_DTYPE))
-    elif with_index:
-        index = np.zeros(0, np.dtype(_lib.EXAMPLE_INDEX_DTYPE))
-    return ShardIndex(shard, nbytes, n, rec_off, rec_len, index_dev, index, lens_host)
+    lens_host = host[lay[2]:lay[2] + 8 * n].view(np.uint64).copy()
+    esz = ctypes.sizeof(_lib.ExampleIndex)
+    index = host[lay[3]:lay[3] + esz * n].view(np.dtype(_lib.EXAMPLE_INDEX_DTYPE)).copy() if with_index else None
+    return ShardIndex(st.shard, st.nbytes, n, st.rec_off, st.rec_len, st.index_dev if with_index else None, index,
+                      lens_host, table=st)
 
 
 def _align16(x):
@@ -271,7 +342,7 @@ def parse_shard(si: ShardIndex, mode, verify_crc=True, mean=None, std=None, num_
     count = si.n - first if count is None else count
     if count <= 0:
         return None, None, None
-    idx = si.index[first:first + count]
+    idx = si.index[first:first + count] if si.index is not None else None
     sink = _lib.ParseSink()
     sink.verify_crc = 1 if verify_crc else 0
     img_buf = tgt_buf = None
@@ -371,52 +442,154 @@ def build_records(items, device=None):
     return out, offsets, pos
 
 
-def iter_parsed_shards(shards, mode, verify_crc=True, mean=None, std=None, num_classes=None, out=None, device=None):
-    """Parse a sequence of shards with a one-ahead software pipeline.
+def _make_sink(ctx, mode, verify_crc, mean, std, num_classes, channels, img_buf, tgt_buf):
+    sink = _lib.ParseSink()
+    sink.verify_crc = 1 if verify_crc else 0
+    if mode == "none":
+        sink.mode = _lib.SINK_NONE
+    elif mode == "raw":
+        sink.mode = _lib.SINK_RAW
+        sink.img_out, sink.img_stride = img_buf.data_ptr(), img_buf.stride(0) * img_buf.element_size()
+        sink.tgt_out, sink.tgt_stride = tgt_buf.data_ptr(), tgt_buf.stride(0) * tgt_buf.element_size()
+    elif mode == "norm_onehot":
+        sink.mode = _lib.SINK_NORM_ONEHOT
+        sink.img_out, sink.img_stride = img_buf.data_ptr(), img_buf.stride(0) * 4
+        sink.tgt_out, sink.tgt_stride = tgt_buf.data_ptr(), tgt_buf.stride(0) * 4
+        sink.mean, sink.std = mean.data_ptr(), std.data_ptr()
+        sink.channels, sink.num_classes = int(channels), int(num_classes)
+        sink._keep = (mean, std)
+    else:
+        raise ValueError(mode)
+    return sink
 
-    shards: iterable of uint8 tensors (CUDA-resident, or pinned host tensors which are uploaded here).  While the
-    fused parse kernel of shard k runs on the caller's stream, the upload + frame scan + feature index of shard k+1
-    (and the small D2H read-back of its tables) proceed on a side stream, so the host never stalls the GPU.
-    Yields (img_buf, tgt_buf, status_dev, ShardIndex) per shard.  `out` = optional (img_buf, tgt_buf) to reuse.
+
+def parse_table(st: ShardTable, mode, img_elems=0, tgt_elems=0, verify_crc=True, mean=None, std=None, num_classes=None,
+                out=None, status=None):
+    """Enqueue the fused pass over EVERY record of an opened shard; no host synchronisation.
+
+    The record count lives on the device, so outputs are sized for st.max_records rows:
+    mode 'raw': (max_records, img_elems) / (max_records, tgt_elems) uint8 rows of payload bytes as stored;
+    mode 'norm_onehot': (max_records, img_elems) float32 and (max_records, tgt_elems*K) float32;
+    mode 'none': CRC verification only.  A payload longer than its row gives status 3.
+    Returns (img_buf, tgt_buf, status_dev[max_records]); rows / entries >= the record count are untouched.
+    """
+    ctx = get_ctx(st.shard.device)
+    cap = st.max_records
+    img_buf = tgt_buf = None
+    C = 1
+    if mode == "raw":
+        img_buf, tgt_buf = out if out is not None else (
+            torch.empty((cap, _align16(max(1, img_elems))), dtype=torch.uint8, device=ctx.device),
+            torch.empty((cap, _align16(max(1, tgt_elems))), dtype=torch.uint8, device=ctx.device))
+    elif mode == "norm_onehot":
+        K = int(num_classes)
+        mean = to_device(np.asarray(mean, dtype=np.float32) if not isinstance(mean, torch.Tensor) else mean, ctx.device)
+        std = to_device(np.asarray(std, dtype=np.float32) if not isinstance(std, torch.Tensor) else std, ctx.device)
+        C = int(mean.numel())
+        if std.numel() != C:
+            raise B2Error("parse_table: mean/std must have one entry per band")
+        il, tl = int(img_elems), int(tgt_elems)
+        if (il * 4) % 16 or (tl * K * 4) % 16:
+            il, tl = _align16(il), _align16(tl)
+        img_buf, tgt_buf = out if out is not None else (
+            torch.empty((cap, il), dtype=torch.float32, device=ctx.device),
+            torch.empty((cap, tl * K), dtype=torch.float32, device=ctx.device))
+    sink = _make_sink(ctx, mode, verify_crc, mean, std, num_classes, C, img_buf, tgt_buf)
+    if status is None:
+        status = torch.empty((cap,), dtype=torch.int32, device=ctx.device)
+    check(lib().b2_tfrecord_parse_table(ctx.handle, ptr(st.shard), st.nbytes, cap, ptr(st.table), ctypes.byref(sink),
+                                        ptr(status), ctx.stream()))
+    return img_buf, tgt_buf, status
+
+
+class ShardPipeline:
+    """Streams shards through open -> fused parse on `depth` CUDA streams with NO per-shard host synchronisation.
+
+    Each slot owns its device staging buffer (for host shards), shard table, status array and output buffers, so
+    the upload + scan + index of shard k+1 overlap the fused pass of shard k.  Iterating yields
+    (img_buf, tgt_buf, status_dev, table) with the producing work already ordered before the caller's current
+    stream; the buffers of a slot are recycled `depth` shards later, after whatever the caller enqueued on them.
+    """
+
+    def __init__(self, mode, img_elems, tgt_elems, max_records, verify_crc=True, mean=None, std=None, num_classes=None,
+                 device=None, depth=3, max_shard_bytes=0):
+        self.ctx = get_ctx(device)
+        dev = self.ctx.device
+        self.mode, self.verify_crc, self.num_classes = mode, verify_crc, num_classes
+        self.img_elems, self.tgt_elems, self.cap, self.depth = int(img_elems), int(tgt_elems), int(max_records), int(depth)
+        self.mean = None if mean is None else to_device(np.asarray(mean, dtype=np.float32) if not isinstance(mean, torch.Tensor) else mean, dev)
+        self.std = None if std is None else to_device(np.asarray(std, dtype=np.float32) if not isinstance(std, torch.Tensor) else std, dev)
+        self.streams = [torch.cuda.Stream(dev) for _ in range(self.depth)]
+        self.ready = [torch.cuda.Event() for _ in range(self.depth)]
+        self.release = [None] * self.depth
+        self.slots = [dict(stage=None, table=None, status=torch.zeros((self.cap,), dtype=torch.int32, device=dev), out=None)
+                      for _ in range(self.depth)]
+        self.max_shard_bytes = int(max_shard_bytes)
+
+    def _submit(self, k, shard):
+        slot = k % self.depth
+        sl, stream = self.slots[slot], self.streams[slot]
+        main = torch.cuda.current_stream(self.ctx.device)
+        if self.release[slot] is not None:
+            stream.wait_event(self.release[slot])
+        else:
+            stream.wait_stream(main)
+        with torch.cuda.stream(stream):
+            nbytes = int(shard.numel())
+            if not shard.is_cuda:
+                if sl["stage"] is None or sl["stage"].numel() < nbytes:
+                    sl["stage"] = torch.empty((max(nbytes, self.max_shard_bytes) + 16,), dtype=torch.uint8, device=self.ctx.device)
+                sl["stage"][:nbytes].copy_(shard, non_blocking=True)
+                shard = sl["stage"]
+            need = table_layout(nbytes, self.cap)[7]
+            if sl["table"] is None or sl["table"].numel() < need:
+                sl["table"] = torch.empty((need + need // 8,), dtype=torch.uint8, device=self.ctx.device)
+            st = open_shard_async(shard, self.ctx.device, self.cap, nbytes=nbytes, table=sl["table"])
+            img, tgt, status = parse_table(st, self.mode, self.img_elems, self.tgt_elems, self.verify_crc, self.mean,
+                                           self.std, self.num_classes, out=sl["out"], status=sl["status"])
+            if sl["out"] is None and img is not None:
+                sl["out"] = (img, tgt)
+            self.ready[slot].record(stream)
+        return slot, (img, tgt, status, st)
+
+    def run(self, shards):
+        main = torch.cuda.current_stream(self.ctx.device)
+        pending = []
+        k = 0
+        for shard in shards:
+            pending.append(self._submit(k, shard))
+            k += 1
+            if len(pending) == self.depth:
+                slot, res = pending.pop(0)
+                main.wait_event(self.ready[slot])
+                yield res
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self.release[slot] = ev
+        while pending:
+            slot, res = pending.pop(0)
+            main.wait_event(self.ready[slot])
+            yield res
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.release[slot] = ev
+
+
+def iter_parsed_shards(shards, mode, verify_crc=True, mean=None, std=None, num_classes=None, out=None, device=None,
+                       img_elems=None, tgt_elems=None, max_records=None, depth=3):
+    """Parse a sequence of shards (CUDA-resident or pinned-host uint8 tensors).
+
+    With img_elems / tgt_elems / max_records given (the chip shape and records-per-shard bound a reader knows from
+    its dataset), the shards stream through ShardPipeline without any host synchronisation.  Otherwise each shard
+    is opened synchronously to learn its shapes.  Yields (img_buf, tgt_buf, status_dev, table-or-ShardIndex).
     """
     ctx = get_ctx(device)
-    main = torch.cuda.current_stream(ctx.device)
-    side = _side_stream(ctx.device)
-    if isinstance(mean, np.ndarray) or isinstance(mean, (list, tuple)):
-        mean = to_device(np.asarray(mean, dtype=np.float32), ctx.device)
-    if isinstance(std, np.ndarray) or isinstance(std, (list, tuple)):
-        std = to_device(np.asarray(std, dtype=np.float32), ctx.device)
-
-    def prefetch(s):
-        with torch.cuda.stream(side):
-            si = open_shard(s, ctx.device)
-        for t in (si.shard, si.rec_off, si.rec_len, si.index_dev):
-            if t is not None:
-                t.record_stream(main)
-        return si
-
-    it = iter(shards)
-    try:
-        nxt = prefetch(next(it))
-    except StopIteration:
+    if img_elems is not None and max_records is not None:
+        pipe = ShardPipeline(mode, img_elems, tgt_elems or 0, max_records, verify_crc, mean, std, num_classes, ctx.device, depth)
+        yield from pipe.run(shards)
         return
-    while nxt is not None:
-        si = nxt
-        main.wait_stream(side)
-        res = parse_shard(si, mode, verify_crc=verify_crc, mean=mean, std=std, num_classes=num_classes, out=out)
-        try:
-            nxt = prefetch(next(it))
-        except StopIteration:
-            nxt = None
-        yield res + (si,)
+    for s in shards:
+        si = open_shard(s, ctx.device)
+        yield parse_shard(si, mode, verify_crc=verify_crc, mean=mean, std=std, num_classes=num_classes, out=out) + (si,)
 
 
-_side = {}
-
-
-def _side_stream(device):
-    s = _side.get(device.index)
-    if s is None:
-        # high priority: the tiny scan/index kernels must slip in between the CTAs of a running parse kernel
-        s = _side[device.index] = torch.cuda.Stream(device, priority=-1)
-    return s

@@ -115,6 +115,19 @@ typedef struct {
 int b2_tfrecord_index(b2_ctx* ctx, const uint8_t* shard_dev, const uint64_t* rec_offsets_dev,
                       const uint64_t* rec_lens_dev, int n, b2_example_index* index_out_dev, b2_stream stream);
 
+/* ---- device-resident shard tables: open + parse with NO host round trip in between -------------------------------
+ * b2_tfrecord_open = b2_tfrecord_scan + b2_tfrecord_index writing ONE caller-owned table (b2_tfrecord_table_bytes
+ * bytes, 16-byte aligned) that b2_tfrecord_parse_table consumes directly, so a reader can enqueue
+ * open -> parse for shard after shard (on alternating streams) and read the tables back once per batch.
+ * Layout (b2_tfrecord_table_layout): offsets[0] hdr int64[8] = { records, scan status (as b2_tfrecord_scan),
+ * tiles, longest record, records whose parse status != 0, .. }, [1] rec_offsets uint64[max_records],
+ * [2] rec_lens uint64[max_records], [3] index b2_example_index[max_records], [4] tile_start uint32[max_records+1],
+ * [5] tile2rec uint32[offsets[6]], offsets[7] = total bytes.  The rest of the table is scratch. */
+uint64_t b2_tfrecord_table_bytes(uint64_t shard_nbytes, uint64_t max_records);
+int b2_tfrecord_table_layout(uint64_t shard_nbytes, uint64_t max_records, uint64_t offsets[8]);
+int b2_tfrecord_open(b2_ctx* ctx, const uint8_t* shard_dev, uint64_t shard_nbytes, uint64_t max_records,
+                     uint8_t* table_dev, b2_stream stream);
+
 enum { B2_SINK_NONE = 0, B2_SINK_RAW = 1, B2_SINK_NORM_ONEHOT = 2 };
 typedef struct {
     int32_t mode;        /* B2_SINK_NONE: CRC only.  RAW: payload bytes copied as stored (uint8 arrays; packed
@@ -132,10 +145,17 @@ typedef struct {
 } b2_parse_sink;
 
 /* One fused pass over the records: CRC verify + payload scatter/cast.  status_dev[i]: 0 ok, 1 data-CRC mismatch
- * (TF: DataLossError), 2 index status != 0, 3 payload larger than its output stride. */
+ * (TF: DataLossError), 2 index status != 0, 3 payload larger than its output stride.  Uses the context workspace:
+ * calls on one context must be stream-ordered (b2_tfrecord_parse_table has no such restriction). */
 int b2_tfrecord_parse(b2_ctx* ctx, const uint8_t* shard_dev, uint64_t shard_nbytes, const uint64_t* rec_offsets_dev,
                       const uint64_t* rec_lens_dev, const b2_example_index* index_dev, int n,
                       uint64_t max_record_len, const b2_parse_sink* sink, int32_t* status_dev, b2_stream stream);
+
+/* The same fused pass over every record of an opened shard; grid and record count come from the table on the
+ * device.  status_dev needs max_records entries; entries >= hdr[0] are left untouched.  hdr[4] counts the records
+ * whose status is non-zero.  A table may be parsed again (e.g. with another sink) without re-opening. */
+int b2_tfrecord_parse_table(b2_ctx* ctx, const uint8_t* shard_dev, uint64_t shard_nbytes, uint64_t max_records,
+                            uint8_t* table_dev, const b2_parse_sink* sink, int32_t* status_dev, b2_stream stream);
 
 /* Host-side: the protobuf bytes around the two payloads for convert_to_example's eight keys in sorted
  * (deterministic) order (_tfrecord_image_translation.py:199-211).  kind 1 = BytesList, 2 = FloatList.

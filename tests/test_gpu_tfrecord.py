@@ -252,3 +252,125 @@ def test_band_stats_exact(dev, dtype, B):
     m2, s2 = onorm.mean_std_from_stats(want)
     np.testing.assert_array_equal(m1, m2)
     np.testing.assert_array_equal(s1, s2)
+
+
+# ------------------------------------------------------------------------------------------------ opened-shard tables
+def _small_shard(n, size, seed, id_jitter=True, K=10):
+    rng = np.random.default_rng(seed)
+    recs, chips = [], []
+    for i in range(n):
+        img = rng.integers(0, 256, (size, size, 3), dtype=np.uint8)
+        lab = rng.integers(0, K + 2, (size, size), dtype=np.uint8)
+        key = "256:2:1.0:43:%d:%d" % (int(rng.integers(-5000, 5000)) if id_jitter else 7, i if id_jitter else 3)
+        chips.append((img, lab, key))
+        recs.append(oep.convert_to_example(img, lab, size, size, 3, size, size, key).SerializeToString())
+    return b"".join(otfr.frame(r) for r in recs), recs, chips
+
+
+@pytest.mark.parametrize("n,size", [(300, 8), (70, 40), (1, 16)])
+def test_scan_many_records_with_drifting_lengths(dev, n, size):
+    """More records than one speculative scan round, identifier lengths drifting: same table as the sequential walk."""
+    from dl_image_segmentation_b200 import ops
+    shard, recs, chips = _small_shard(n, size, seed=n)
+    si = ops.open_shard(shard, dev)
+    o, l = otfr.scan(shard)
+    assert si.n == n == len(o)
+    np.testing.assert_array_equal(si.rec_off[:n].cpu().numpy().astype(np.uint64), o)
+    np.testing.assert_array_equal(si.rec_len[:n].cpu().numpy().astype(np.uint64), l)
+    assert (si.index["status"] == 0).all()
+    assert si.identifiers(shard) == [c[2].encode() for c in chips]
+    # a corrupt length CRC deep inside (beyond the first scan round) stops the walk exactly there
+    k = min(n - 1, 200)
+    bad = bytearray(shard)
+    bad[int(o[k]) - 12 + 9] ^= 0x10
+    st = ops.open_shard_async(bytes(bad), dev, max_records=512)
+    nn, status = st.header()[:2]
+    assert (nn, status) == (k, 1)
+    # capacity smaller than the shard -> status 2 with the table full
+    if n > 4:
+        st = ops.open_shard_async(shard, dev, max_records=4)
+        assert st.header()[:2] == (4, 2)
+        with pytest.raises(ops.B2Error):
+            st.check()
+
+
+def test_scan_wildly_varying_records(dev):
+    """Record lengths that defeat the stride prediction (every hop misses its window) still give the sequential result."""
+    from dl_image_segmentation_b200 import ops
+    rng = np.random.default_rng(5)
+    recs = [rng.integers(0, 256, int(rng.integers(0, 9000)), dtype=np.uint8).tobytes() for _ in range(150)]
+    shard = b"".join(otfr.frame(r) for r in recs)
+    si = ops.open_shard(shard, dev, with_index=False)
+    o, l = otfr.scan(shard)
+    assert si.n == 150
+    np.testing.assert_array_equal(si.rec_off[:150].cpu().numpy().astype(np.uint64), o)
+    np.testing.assert_array_equal(si.rec_len[:150].cpu().numpy().astype(np.uint64), l)
+    st = ops.parse_shard(si, "none", verify_crc=True)[2]
+    assert not st.cpu().numpy().any()
+    got = ops.crc32c(shard, o, l, device=dev)
+    assert [int(x) for x in got] == [otfr.crc32c(r) for r in recs]
+
+
+@pytest.mark.parametrize("depth", [1, 3])
+def test_shard_pipeline_matches_oracle(dev, depth):
+    """open -> fused parse enqueued shard after shard without host syncs == oracle; bad records are reported."""
+    import torch
+
+    from dl_image_segmentation_b200 import ops
+    size, K = 24, 10
+    mean = np.array([101.5, 99.25, 120.0], np.float32)
+    std = np.array([47.0, 51.5, 33.3], np.float32)
+    counts = [5, 17, 1, 12, 9]
+    shards, chips = [], []
+    for s, n in enumerate(counts):
+        sh, _, ch = _small_shard(n, size, seed=100 + s)
+        shards.append(sh)
+        chips.append(ch)
+    # shard 3: flip a payload byte of record 2 (data CRC must catch it)
+    o3, _ = otfr.scan(shards[3])
+    bad = bytearray(shards[3])
+    bad[int(o3[2]) + 300] ^= 0x01
+    shards[3] = bytes(bad)
+    host = [torch.from_numpy(np.frombuffer(s, np.uint8).copy()).pin_memory() for s in shards]
+    for source in (host, [h.to(dev) for h in host]):
+        pipe = ops.ShardPipeline("norm_onehot", size * size * 3, size * size, max_records=20, mean=mean, std=std,
+                                 num_classes=K, device=dev, depth=depth)
+        seen = 0
+        for s, (ib, tb, st, table) in enumerate(pipe.run(source)):
+            n, status, tiles, max_len, n_bad = table.header()
+            assert (n, status) == (counts[s], 0)
+            stat = st[:n].cpu().numpy()
+            want_bad = [2] if s == 3 else []
+            assert list(np.nonzero(stat)[0]) == want_bad and n_bad == len(want_bad)
+            if want_bad:
+                with pytest.raises(ops.DataLossError):
+                    table.check()
+            wi = onorm.normalise(np.stack([c[0] for c in chips[s]]), mean, std)
+            wt = onorm.one_hot(np.stack([c[1] for c in chips[s]]), K)
+            gi = ib[:n].cpu().numpy().reshape(wi.shape)
+            gt = tb[:n].cpu().numpy().reshape(wt.shape)
+            for r in range(n):
+                if r in want_bad:
+                    continue
+                np.testing.assert_array_equal(gi[r], wi[r])
+                np.testing.assert_array_equal(gt[r], wt[r])
+            seen += 1
+        assert seen == len(counts)
+
+
+def test_parse_table_raw_and_reparse(dev):
+    """A table can be parsed twice (raw, then CRC only); raw rows equal the stored payload bytes."""
+    from dl_image_segmentation_b200 import ops
+    shard, recs, chips = _small_shard(11, 30, seed=9)
+    st = ops.open_shard_async(shard, dev, max_records=16)
+    ib, tb, status = ops.parse_table(st, "raw", 30 * 30 * 3, 30 * 30)
+    n = st.check()
+    assert n == 11 and not status[:n].cpu().numpy().any()
+    for r, (img, lab, _) in enumerate(chips):
+        assert bytes(ib[r, :2700].cpu().numpy()) == img.tobytes()
+        assert bytes(tb[r, :900].cpu().numpy()) == lab.tobytes()
+    _, _, status2 = ops.parse_table(st, "none")
+    assert st.check() == 11 and not status2[:n].cpu().numpy().any()
+    # rows too small for the payload -> status 3 for every record
+    _, _, status3 = ops.parse_table(st, "raw", 100, 900)
+    assert list(status3[:n].cpu().numpy()) == [3] * 11

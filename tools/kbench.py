@@ -26,6 +26,8 @@ except Exception:
 
 
 def timeit(fn, iters, warmup=3):
+    if os.environ.get("KB_QUICK"):          # under ncu: one warm-up + one measured launch per variant
+        iters, warmup = 1, 1
     for _ in range(warmup):
         fn(0)
     torch.cuda.synchronize()
@@ -149,23 +151,33 @@ def bench_parse(dev, n_shards=8):
     import bench as B
     B.N_SHARDS = n_shards
     shards = B.make_shards_on_device(dev, 7)
-    sis = [ops.open_shard(s, dev) for s in shards]
+    n = B.RECS_PER_SHARD
+    tabs = [ops.open_shard_async(s, dev, max_records=n) for s in shards]
+    assert all(t.check() == n for t in tabs)
     mean = ops.to_device(np.array([127.0, 128.0, 126.5], np.float32), dev)
     std = ops.to_device(np.array([73.0, 74.0, 72.5], np.float32), dev)
-    out = (torch.empty((B.RECS_PER_SHARD, B.H * B.W * B.C), dtype=torch.float32, device=dev),
-           torch.empty((B.RECS_PER_SHARD, B.H * B.W * B.K), dtype=torch.float32, device=dev))
-    rec = shards[0].numel() // B.RECS_PER_SHARD
-    n = B.RECS_PER_SHARD
+    out = (torch.empty((n, B.H * B.W * B.C), dtype=torch.float32, device=dev),
+           torch.empty((n, B.H * B.W * B.K), dtype=torch.float32, device=dev))
+    out_raw = (torch.empty((n, B.H * B.W * B.C), dtype=torch.uint8, device=dev),
+               torch.empty((n, B.H * B.W), dtype=torch.uint8, device=dev))
+    status = torch.empty((n,), dtype=torch.int32, device=dev)
+    rec = shards[0].numel() // n
     img_b, hot_b = B.H * B.W * B.C * 4, B.H * B.W * B.K * 4
+
+    def fn_open(i):
+        ops.open_shard_async(shards[i % n_shards], dev, max_records=n, table=tabs[i % n_shards].table)
+    report("open (scan + index) one shard of %d records" % n, timeit(fn_open, 16), n * 12)
     for name, mode, verify, algo in (
             ("parse crc-only", "none", True, n * rec),
             ("parse norm+onehot no-crc", "norm_onehot", False, n * (rec + img_b + hot_b)),
             ("parse norm+onehot +crc", "norm_onehot", True, n * (rec + img_b + hot_b)),
             ("parse raw +crc", "raw", True, n * (rec + B.H * B.W * (B.C + 1)))):
         def fn(i):
-            ops.parse_shard(sis[i % n_shards], mode, verify_crc=verify, mean=mean, std=std, num_classes=B.K,
-                            out=out if mode == "norm_onehot" else None)
+            ops.parse_table(tabs[i % n_shards], mode, B.H * B.W * B.C, B.H * B.W, verify_crc=verify, mean=mean, std=std,
+                            num_classes=B.K, out=out if mode == "norm_onehot" else (out_raw if mode == "raw" else None),
+                            status=status)
         report(name, timeit(fn, 16), algo)
+        assert not status.cpu().numpy().any()
     big = torch.empty((1 << 30,), dtype=torch.uint8, device=dev)
     big2 = torch.empty((1 << 30,), dtype=torch.uint8, device=dev)
     report("reference: torch zero_ 1 GiB (write-only)", timeit(lambda i: big.zero_(), 10), 1 << 30)
