@@ -137,39 +137,51 @@ def run_ours(args, rank, world):
         dist.all_reduce(acc)                      # exact integer counters: identical mean/std on every rank
     mean, std = ops.mean_std_from_stats(ops.stats_to_python(acc))
     mean_d, std_d = ops.to_device(mean, dev), ops.to_device(std, dev)
-    del raw_i
-    out = (torch.empty((RECS_PER_SHARD, H * W * C), dtype=torch.float32, device=dev),
-           torch.empty((RECS_PER_SHARD, H * W * K), dtype=torch.float32, device=dev))
+    del raw_i, si0
     pinned = [s.cpu().pin_memory() for s in shards]
+    max_bytes = max(int(s.numel()) for s in shards)
+    # the reader's public streaming API: upload (host shards) -> open -> fused parse, no per-shard host sync
+    pipe = ops.ShardPipeline("norm_onehot", H * W * C, H * W, max_records=RECS_PER_SHARD, verify_crc=True, mean=mean_d,
+                             std=std_d, num_classes=K, device=dev, depth=3, max_shard_bytes=max_bytes)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     kern_events = []
+    want = torch.tensor([RECS_PER_SHARD, 0, 0], dtype=torch.int64, device=dev)
 
-    def step_resident(record_kernel=False):
-        st = None
-        if record_kernel:                      # per-launch events need the un-pipelined order
-            for s in shards:
-                si = ops.open_shard(s, dev)
-                a, b = ev(), ev()
-                a.record()
-                _, _, st = ops.parse_shard(si, "norm_onehot", verify_crc=True, mean=mean_d, std=std_d, num_classes=K, out=out)
-                b.record()
-                kern_events.append((a, b))
-            return st
-        for _, _, st, _ in ops.iter_parsed_shards(shards, "norm_onehot", verify_crc=True, mean=mean_d, std=std_d,
-                                                  num_classes=K, out=out, device=dev):
-            pass
-        return st
+    def consume(source):
+        """Drain the pipeline; per shard accumulate |records - expected| + scan status + bad records on the device."""
+        bad = torch.zeros((), dtype=torch.int64, device=dev)
+        for _, _, _, table in pipe.run(source):
+            h = table.hdr_dev
+            bad += (h[[0, 1, 4]] - want).abs().sum()
+        return bad
+
+    def step_resident():
+        return consume(shards)
 
     def step_e2e():
-        bad = torch.zeros((), dtype=torch.int32, device=dev)
-        for _, _, st, _ in ops.iter_parsed_shards(pinned, "norm_onehot", verify_crc=True, mean=mean_d, std=std_d,
-                                                  num_classes=K, out=out, device=dev):
-            bad += st.abs().sum().to(torch.int32)
-        if int(bad.cpu()):                                                    # D2H: job status
+        bad = consume(pinned)                                   # H2D of every shard inside
+        if int(bad.cpu()):                                      # D2H: the job's status word
             raise RuntimeError("parse status != 0")
         return bad
 
-    def timed(fn, steps, warmup, **kw):
+    ev_out = (torch.empty((RECS_PER_SHARD, H * W * C), dtype=torch.float32, device=dev),
+              torch.empty((RECS_PER_SHARD, H * W * K), dtype=torch.float32, device=dev))
+
+    def step_kernel_events():
+        """Un-pipelined pass with CUDA events around every launch of the dominant kernel (same stream)."""
+        out, status = ev_out, None
+        for s in shards:
+            st = ops.open_shard_async(s, dev, max_records=RECS_PER_SHARD)
+            a, b = ev(), ev()
+            a.record()
+            i_, t_, status = ops.parse_table(st, "norm_onehot", H * W * C, H * W, verify_crc=True, mean=mean_d, std=std_d,
+                                             num_classes=K, out=out, status=status)
+            b.record()
+            out = (i_, t_)
+            kern_events.append((a, b))
+            assert st.check("bench shard") == RECS_PER_SHARD
+
+    def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
@@ -179,8 +191,9 @@ def run_ours(args, rank, world):
         l0 = ctx.launches
         a, b = ev(), ev()
         a.record()
+        last = None
         for _ in range(steps):
-            fn(**kw)
+            last = fn()
         b.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -190,17 +203,19 @@ def run_ours(args, rank, world):
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, ctx.launches - l0
+        return ms, ctx.launches - l0, last
 
     sampler = ClockSampler(local)
     sampler.start()
-    ms, launches = timed(step_resident, args.steps, args.warmup)
+    ms, launches, bad = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop()
-    timed(step_resident, 2, 0, record_kernel=True)          # per-launch CUDA events of the dominant kernel
-    st = step_resident()
-    assert not st.cpu().numpy().any(), "parse status != 0"
-    e2e_steps = max(1, min(args.steps, 5))
-    ms_e2e, _ = timed(step_e2e, e2e_steps, 1)
+    assert int(bad.cpu()) == 0, "parse status != 0"
+    step_kernel_events()                                    # warm-up of the un-pipelined order
+    del kern_events[:]
+    step_kernel_events()                                    # per-launch CUDA events of the dominant kernel
+    step_kernel_events()
+    e2e_steps = max(1, min(args.steps, 10))
+    ms_e2e, _, _ = timed(step_e2e, e2e_steps, 2)
 
     recs_step = N_SHARDS * RECS_PER_SHARD
     value = world * recs_step * args.steps / (ms / 1e3)
@@ -221,8 +236,8 @@ def run_ours(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8->f32", "data": "synthetic",
         "config": config_dict(world), "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "chips/s", "h2d_bytes_per_step": int(sum(p.numel() for p in pinned)),
-                "d2h_bytes_per_step": int(N_SHARDS * (RECS_PER_SHARD * (80 + 8 + 4) + 16)), "steps": e2e_steps},
-        "roofline": {"bound": "hbm", "kernel": "parse_kernel<NORM_ONEHOT> (+ per-record CRC fold)", "achieved": achieved,
+                "d2h_bytes_per_step": 8, "steps": e2e_steps},
+        "roofline": {"bound": "hbm", "kernel": "fused_parse_kernel<NORM_ONEHOT> (CRC-32C verify + normalise + one-hot)", "achieved": achieved,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                      "launch_ms": k_avg_ms, "algorithmic_bytes_per_launch": algo, "traffic": args.traffic},
     }
@@ -262,13 +277,13 @@ def cpu_baseline(host_shards, mean, std, budget_s=12.0, chunk=25):
         par(delayed(_parse_one)((p, mean, std)) for p in pieces[:cores])           # warm-up
         t0 = time.time()
         i = 0
-        while time.time() - t0 < budget_s and i < len(pieces):
-            batch = pieces[i:i + 4 * cores]
+        while time.time() - t0 < budget_s:
+            batch = [pieces[(i + k) % len(pieces)] for k in range(4 * cores)]
             done += sum(par(delayed(_parse_one)((p, mean, std)) for p in batch))
             i += len(batch)
     dt = time.time() - t0
     return {"value": done / dt, "unit": "chips/s", "cores": cores, "kind": "port",
-            "sample": "%d records of the same shards, %d worker threads (reference: dataset.map(parse_fn, 8)), %.1f s; "
+            "sample": "%d records (4 of the shards, cycled), %d worker threads (reference: dataset.map(parse_fn, 8)), %.1f s; "
                       "restatement because TensorFlow is not installable" % (done, cores, dt)}
 
 

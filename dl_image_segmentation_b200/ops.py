@@ -519,7 +519,11 @@ class ShardPipeline:
         self.img_elems, self.tgt_elems, self.cap, self.depth = int(img_elems), int(tgt_elems), int(max_records), int(depth)
         self.mean = None if mean is None else to_device(np.asarray(mean, dtype=np.float32) if not isinstance(mean, torch.Tensor) else mean, dev)
         self.std = None if std is None else to_device(np.asarray(std, dtype=np.float32) if not isinstance(std, torch.Tensor) else std, dev)
+        # upload + scan + index run on high-priority streams so that their few CTAs slip in between the CTAs of the
+        # fused pass of an earlier shard (which saturates every SM) instead of queueing behind it
+        self.open_streams = [torch.cuda.Stream(dev, priority=-1) for _ in range(self.depth)]
         self.streams = [torch.cuda.Stream(dev) for _ in range(self.depth)]
+        self.opened = [torch.cuda.Event() for _ in range(self.depth)]
         self.ready = [torch.cuda.Event() for _ in range(self.depth)]
         self.release = [None] * self.depth
         self.slots = [dict(stage=None, table=None, status=torch.zeros((self.cap,), dtype=torch.int32, device=dev), out=None)
@@ -528,14 +532,14 @@ class ShardPipeline:
 
     def _submit(self, k, shard):
         slot = k % self.depth
-        sl, stream = self.slots[slot], self.streams[slot]
+        sl, ostream, stream = self.slots[slot], self.open_streams[slot], self.streams[slot]
         main = torch.cuda.current_stream(self.ctx.device)
         if self.release[slot] is not None:
-            stream.wait_event(self.release[slot])
+            ostream.wait_event(self.release[slot])
         else:
-            stream.wait_stream(main)
-        with torch.cuda.stream(stream):
-            nbytes = int(shard.numel())
+            ostream.wait_stream(main)
+        nbytes = int(shard.numel())
+        with torch.cuda.stream(ostream):
             if not shard.is_cuda:
                 if sl["stage"] is None or sl["stage"].numel() < nbytes:
                     sl["stage"] = torch.empty((max(nbytes, self.max_shard_bytes) + 16,), dtype=torch.uint8, device=self.ctx.device)
@@ -545,6 +549,9 @@ class ShardPipeline:
             if sl["table"] is None or sl["table"].numel() < need:
                 sl["table"] = torch.empty((need + need // 8,), dtype=torch.uint8, device=self.ctx.device)
             st = open_shard_async(shard, self.ctx.device, self.cap, nbytes=nbytes, table=sl["table"])
+            self.opened[slot].record(ostream)
+        stream.wait_event(self.opened[slot])
+        with torch.cuda.stream(stream):
             img, tgt, status = parse_table(st, self.mode, self.img_elems, self.tgt_elems, self.verify_crc, self.mean,
                                            self.std, self.num_classes, out=sl["out"], status=sl["status"])
             if sl["out"] is None and img is not None:
