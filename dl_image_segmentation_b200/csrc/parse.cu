@@ -33,7 +33,7 @@ namespace b2 {
 
 constexpr int kBufBytes = kTile + 128;   // tile + 32-byte halo, rounded so the second buffer stays 128-byte aligned
 constexpr int kHotMaxK = 32;             // one-hot through shared-memory blocks + bulk stores up to this many classes
-constexpr int kHotLabels = 256;          // labels per block (one per thread): one bulk store moves 1024*K bytes
+constexpr int kHotLabels = 64;           // labels per warp block (two per lane): one bulk store moves 256*K bytes
 
 // ---------------------------------------------------------------- PTX: mbarrier + bulk async copies (TMA, 1-D)
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -82,6 +82,7 @@ struct ParseArgs {
     int32_t* status;                 // per-record status (parse) ...
     uint32_t* crc_out;               // ... or raw CRCs (b2_crc32c)
     int64_t* n_bad;                  // hdr[4] of an opened shard, or NULL
+    uint32_t* sched;                 // [0] next chunk of q tiles, [1] CTAs that have finished; both zero between launches
 };
 
 struct __align__(16) TileJob {
@@ -349,10 +350,8 @@ fused_parse_kernel(const ParseArgs a) {
     __shared__ float s_mean[64], s_std[64], s_rcp[64];
     __shared__ int s_exact_div;
     const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     const uint64_t total = a.hdr ? (uint64_t)a.hdr[2] : (uint64_t)a.n * a.tiles_x;
-    const uint64_t w0 = (uint64_t)blockIdx.x * a.q;
-    if (w0 >= total) return;
-    const uint32_t nq = (uint32_t)(total - w0 < a.q ? total - w0 : a.q);
     const bool want_crc = a.sink.verify_crc || a.crc_out;
     const int C = a.sink.channels, K = a.sink.num_classes;
     const bool use_hot = K <= kHotMaxK;
@@ -367,7 +366,7 @@ fused_parse_kernel(const ParseArgs a) {
             s_rcp[c] = __frcp_rn(a.sink.std[c]);
         }
         if (use_hot)
-            for (int i = tid; i < 2 * kHotLabels * K; i += kTileThreads) hot_all[i] = 0.0f;
+            for (int i = tid; i < (kTileThreads / 32) * (kHotLabels * K + 4); i += kTileThreads) hot_all[i] = 0.0f;
     }
     if (tid == 0) {
         mbar_init(&bar[0], 1);
@@ -384,7 +383,28 @@ fused_parse_kernel(const ParseArgs a) {
         }
         if (bad) s_exact_div = 1;
     }
-    if (tid == 0) make_job<kMode>(a, (uint32_t)w0, &job[0], dyn, &bar[0]);
+    // Tiles are handed out in chunks of q consecutive tiles from a device-side counter, so the per-CTA set-up above is
+    // paid once per resident CTA and a CTA that drew cheap (image) tiles simply draws more of them.
+    uint32_t feed_w = 0, feed_left = 0;   // thread 0 only: next tile of the current chunk, tiles left in it
+    bool feed_end = false;
+    auto next_job = [&](TileJob* jb, uint8_t* buf, uint64_t* br) {
+        if (feed_left == 0 && !feed_end) {
+            const uint64_t w = (uint64_t)atomicAdd(&a.sched[0], 1u) * a.q;
+            if (w >= total) feed_end = true;
+            else {
+                feed_w = (uint32_t)w;
+                feed_left = (uint32_t)(total - w < a.q ? total - w : a.q);
+            }
+        }
+        if (feed_end) {
+            jb->flags = 4;
+            return;
+        }
+        make_job<kMode>(a, feed_w, jb, buf, br);
+        feed_w++;
+        feed_left--;
+    };
+    if (tid == 0) next_job(&job[0], dyn, &bar[0]);
     __syncthreads();
     const bool exact_div = kMode == B2_SINK_NORM_ONEHOT && s_exact_div != 0;
     // image loop stride: the largest S <= 256 with 4 S a multiple of C, so that a thread's four bytes always fall on
@@ -398,15 +418,17 @@ fused_parse_kernel(const ParseArgs a) {
     uint32_t s = 0;                       // running CRC state of this thread
     Run run;
     run.open = false;
-    uint32_t hot_it = 0;                  // one-hot blocks issued so far (block = hot_it & 1)
-    uint32_t slot0 = 0xFFFFFFFFu, slot1 = 0xFFFFFFFFu;   // the float this thread set in block 0 / 1
+    float* hot = hot_all + warp * (kHotLabels * K + 4);   // this warp's one-hot block; float kHotLabels*K is a dummy
+    const uint32_t hot_dummy = kHotLabels * K;
+    uint32_t slot0 = hot_dummy, slot1 = hot_dummy;        // the floats this lane set in the block last time
 
-    for (uint32_t it = 0; it < nq; it++) {
+    for (uint32_t it = 0;; it++) {
         const uint32_t b = it & 1;
-        if (tid == 0 && it + 1 < nq) make_job<kMode>(a, (uint32_t)(w0 + it + 1), &job[b ^ 1], dyn + (b ^ 1) * kBufBytes, &bar[b ^ 1]);
+        if (tid == 0) next_job(&job[b ^ 1], dyn + (b ^ 1) * kBufBytes, &bar[b ^ 1]);
         const TileJob j = job[b];
         const bool valid = (j.flags & 1) != 0;
-        if (run.open && (!valid || j.r != run.r)) run_flush(a, run, s, want_crc, red);
+        if (run.open && (!valid || j.r != run.r || j.tile != run.last_tile + 1)) run_flush(a, run, s, want_crc, red);
+        if (j.flags & 4) break;
         if (valid) {
             uint8_t* buf8w = dyn + b * kBufBytes;
             if (j.cb) {
@@ -487,40 +509,39 @@ fused_parse_kernel(const ParseArgs a) {
                     const uint64_t lo = po > ts ? po : ts, hi = (po + pl < te) ? po + pl : te;
                     const uint32_t base = (uint32_t)(po - ts);
                     if (use_hot) {
-                        // The CTA fills a block of kHotLabels*K floats in shared memory — zero except ONE 1.0f per label,
-                        // so a label costs one 4-byte shared-memory write — and thread 0 pushes the block to HBM with a
-                        // single TMA bulk store; two blocks alternate so the store of one overlaps the fill of the other.
+                        // Each warp owns a block of kHotLabels*K floats in shared memory — zero except ONE 1.0f per label,
+                        // so a label costs one 4-byte shared-memory write — and pushes it to HBM with a single TMA bulk
+                        // store; out-of-range labels write a dummy float past the block, so nothing is predicated.
                         // Work unit = 4 labels (4K floats: a whole number of 16-byte groups, 16-byte aligned in the
                         // output); a unit belongs to the tile holding its first label, later labels may sit in the halo.
                         const uint32_t j_lo = (uint32_t)((lo - po + 3) >> 2), j_hi = (uint32_t)((hi - po + 3) >> 2);
                         const uint32_t L_beg = 4 * j_lo, L_end = (4 * j_hi < pl) ? 4 * j_hi : pl;
-                        for (uint32_t L0 = L_beg; L0 < L_end; L0 += kHotLabels, hot_it++) {
-                            const uint32_t hb = hot_it & 1;
-                            float* hot = hot_all + hb * kHotLabels * K;
-                            if (hot_it >= 2) {   // the bulk store that used this block two rounds ago must have read it
-                                if (tid == 0) bulk_wait_read<1>();
-                                __syncthreads();
+                        for (uint32_t L0 = L_beg + warp * kHotLabels; L0 < L_end; L0 += (kTileThreads / 32) * kHotLabels) {
+                            if (lane == 0) bulk_wait_read<0>();   // this warp's previous bulk store has read the block
+                            __syncwarp();
+                            hot[slot0] = 0.0f;
+                            hot[slot1] = 0.0f;
+                            const uint32_t l0 = L0 + 2 * lane;
+                            slot0 = slot1 = hot_dummy;
+                            if (l0 < L_end) {
+                                const uint32_t lab = buf8[base + l0];
+                                if (lab < (uint32_t)K) slot0 = (2 * lane) * K + lab;
                             }
-                            const uint32_t old = hb ? slot1 : slot0;
-                            if (old != 0xFFFFFFFFu) hot[old] = 0.0f;
-                            uint32_t mine = 0xFFFFFFFFu;
-                            if (L0 + tid < L_end) {
-                                const uint32_t lab = buf8[base + L0 + tid];
-                                if (lab < (uint32_t)K) {
-                                    mine = tid * K + lab;
-                                    hot[mine] = 1.0f;
-                                }
+                            if (l0 + 1 < L_end) {
+                                const uint32_t lab = buf8[base + l0 + 1];
+                                if (lab < (uint32_t)K) slot1 = (2 * lane + 1) * K + lab;
                             }
-                            if (hb) slot1 = mine; else slot0 = mine;
+                            hot[slot0] = 1.0f;
+                            hot[slot1] = 1.0f;
                             fence_proxy_async();
-                            __syncthreads();
+                            __syncwarp();
                             const uint32_t nl = (L_end - L0 < (uint32_t)kHotLabels) ? L_end - L0 : (uint32_t)kHotLabels;
                             const uint32_t nfl = nl * K, nb16 = (nfl * 4) & ~15u;
-                            if (tid == 0) {
+                            if (lane == 0) {
                                 if (nb16) bulk_s2g(dst + (size_t)L0 * K, hot, nb16);
                                 bulk_commit();
                             }
-                            if ((uint32_t)tid < (nfl & 3)) dst[(size_t)L0 * K + (nfl & ~3u) + tid] = hot[(nfl & ~3u) + tid];
+                            if ((uint32_t)lane < (nfl & 3)) dst[(size_t)L0 * K + (nfl & ~3u) + lane] = hot[(nfl & ~3u) + lane];
                         }
                     } else {
                         // generic path (K > 32): float4 group g holds one-hot floats [4g, 4g+4), owned by the tile of label 4g/K
@@ -554,8 +575,14 @@ fused_parse_kernel(const ParseArgs a) {
         }
         __syncthreads();   // everyone is done with buffer b and job[b]
     }
-    if (run.open) run_flush(a, run, s, want_crc, red);
-    if (kMode == B2_SINK_NORM_ONEHOT && tid == 0) bulk_wait_read<0>();   // shared memory must outlive the bulk stores
+    if (kMode == B2_SINK_NORM_ONEHOT && lane == 0) bulk_wait_read<0>();   // shared memory must outlive the bulk stores
+    if (tid == 0) {   // the last CTA out re-arms the chunk counter for the next launch
+        __threadfence();
+        if (atomicAdd(&a.sched[1], 1u) == gridDim.x - 1) {
+            a.sched[0] = 0;
+            a.sched[1] = 0;
+        }
+    }
 }
 
 }  // namespace b2
@@ -572,7 +599,7 @@ LaunchCfg g_cfg[64];
 
 size_t dyn_bytes(int mode, int K) {
     size_t d = 2 * (size_t)kBufBytes;
-    if (mode == B2_SINK_NORM_ONEHOT && K <= kHotMaxK) d += (size_t)2 * kHotLabels * K * sizeof(float);
+    if (mode == B2_SINK_NORM_ONEHOT && K <= kHotMaxK) d += (size_t)(kTileThreads / 32) * (kHotLabels * K + 4) * sizeof(float);
     return d;
 }
 
@@ -584,7 +611,10 @@ int launch_fused(b2_ctx* ctx, const ParseArgs& pa, uint64_t max_tiles, cudaStrea
         B2_CUDA(cudaFuncSetAttribute(fused_parse_kernel<B2_SINK_NORM_ONEHOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         cfg.ready = true;
     }
-    const unsigned grid = (unsigned)((max_tiles + pa.q - 1) / pa.q);
+    // persistent grid: as many CTAs as fit on the GPU at once (4 per SM), never more than there are chunks
+    const uint64_t chunks = (max_tiles + pa.q - 1) / pa.q;
+    const uint64_t resident = (uint64_t)ctx->sm_count * (pa.sink.mode == B2_SINK_NORM_ONEHOT ? 4 : 6);
+    const unsigned grid = (unsigned)(chunks < resident ? chunks : resident);
     const size_t dyn = dyn_bytes(pa.sink.mode, pa.sink.num_classes);
     switch (pa.sink.mode) {
         case B2_SINK_NONE: fused_parse_kernel<B2_SINK_NONE><<<grid, kTileThreads, dyn, s>>>(pa); break;
@@ -638,11 +668,11 @@ extern "C" int b2_tfrecord_parse(b2_ctx* ctx, const uint8_t* shard, uint64_t nby
     if (!tx) tx = 1;
     B2_REQUIRE(tx * (uint64_t)n < (1ull << 32), "b2_tfrecord_parse: too many tiles for one call");
     // per-record accumulators live in the context workspace: calls on one context must be stream-ordered
-    if (int e = ws_reserve(ctx, (size_t)n * 8, s)) return e;
-    B2_CUDA(cudaMemsetAsync(ctx->ws, 0, (size_t)n * 8, s));
+    if (int e = ws_reserve(ctx, (size_t)n * 8 + 8, s)) return e;
+    B2_CUDA(cudaMemsetAsync(ctx->ws, 0, (size_t)n * 8 + 8, s));
     uint32_t* acc = static_cast<uint32_t*>(ctx->ws);
     ParseArgs pa{shard, nbytes, rec_off, rec_len, index, *sink, ctx->crc_dev, nullptr, nullptr, nullptr,
-                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(), acc, acc + n, status, nullptr, nullptr};
+                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(), acc, acc + n, status, nullptr, nullptr, acc + 2 * (size_t)n};
     return launch_fused(ctx, pa, tx * (uint64_t)n, s);
 }
 
@@ -656,7 +686,7 @@ extern "C" int b2_tfrecord_parse_table(b2_ctx* ctx, const uint8_t* shard, uint64
     DeviceGuard g(ctx->device);
     const TableView v = table_view(table, nbytes, max_records);
     ParseArgs pa{shard, nbytes, v.rec_off, v.rec_len, v.index, *sink, ctx->crc_dev, v.tile2rec, v.tile_start, v.hdr,
-                 0, 0, tiles_per_cta(), v.crc_acc, v.done, status, nullptr, v.hdr + 4};
+                 0, 0, tiles_per_cta(), v.crc_acc, v.done, status, nullptr, v.hdr + 4, reinterpret_cast<uint32_t*>(v.hdr + 5)};
     return launch_fused(ctx, pa, v.cap_tiles, static_cast<cudaStream_t>(stream));
 }
 
@@ -671,14 +701,14 @@ extern "C" int b2_crc32c(b2_ctx* ctx, const uint8_t* data, const uint64_t* offse
     uint64_t tx = (max_len + 15 + kTile - 1) / kTile;
     if (!tx) tx = 1;
     B2_REQUIRE(tx * (uint64_t)n < (1ull << 32), "b2_crc32c: too many tiles for one call");
-    if (int e = ws_reserve(ctx, (size_t)n * 8, s)) return e;
-    B2_CUDA(cudaMemsetAsync(ctx->ws, 0, (size_t)n * 8, s));
+    if (int e = ws_reserve(ctx, (size_t)n * 8 + 8, s)) return e;
+    B2_CUDA(cudaMemsetAsync(ctx->ws, 0, (size_t)n * 8 + 8, s));
     uint32_t* acc = static_cast<uint32_t*>(ctx->ws);
     b2_parse_sink sink;
     memset(&sink, 0, sizeof(sink));
     sink.mode = B2_SINK_NONE;
     sink.verify_crc = 1;
     ParseArgs pa{data, ~0ull, offsets, lens, nullptr, sink, ctx->crc_dev, nullptr, nullptr, nullptr,
-                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(), acc, acc + n, nullptr, crc_out, nullptr};
+                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(), acc, acc + n, nullptr, crc_out, nullptr, acc + 2 * (size_t)n};
     return launch_fused(ctx, pa, tx * (uint64_t)n, s);
 }

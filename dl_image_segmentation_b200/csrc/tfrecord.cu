@@ -206,6 +206,7 @@ scan_kernel(const uint8_t* __restrict__ shard, uint64_t nbytes, uint64_t cap, Sc
         o.hdr[2] = (int64_t)run;
         o.hdr[3] = (int64_t)s_maxlen;
         o.hdr[4] = 0;
+        o.hdr[5] = 0;   // chunk scheduler words of the fused pass
     }
 }
 

@@ -1,0 +1,50 @@
+// membw.cu — development probe: what does THIS B200 sustain for write-only / read-only / copy streams?
+// (The roofline denominator stays MEASURED_PEAKS.json's copy figure; this only tells how far a write-dominated
+//  kernel such as the fused parse pass can possibly get.)   nvcc -arch=sm_100a -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+__global__ void k_write(uint4* p, size_t n, int cs) {
+    const uint4 v = make_uint4(1, 2, 3, 4);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (cs) asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p + i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        else p[i] = v;
+    }
+}
+__global__ void k_read(const uint4* p, size_t n, uint32_t* sink) {
+    uint32_t acc = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p + i));
+        acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if (acc == 0x12345678u) *sink = acc;
+}
+// write through shared memory + TMA bulk stores: each CTA streams `chunk`-byte blocks
+__global__ void k_bulk_write(uint8_t* p, size_t nbytes, uint32_t chunk) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    for (uint32_t i = threadIdx.x; i < chunk / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = i;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t s = (uint32_t)__cvta_generic_to_shared(sm);
+        for (size_t o = (size_t)blockIdx.x * chunk; o + chunk <= nbytes; o += (size_t)gridDim.x * chunk) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p + o), "r"(s), "r"(chunk) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 8;" ::: "memory");
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+extern "C" {
+void mb_write(void* p, size_t nbytes, int grid, int block, int cs, void* stream) {
+    k_write<<<grid, block, 0, (cudaStream_t)stream>>>((uint4*)p, nbytes / 16, cs);
+}
+void mb_read(const void* p, size_t nbytes, int grid, int block, void* sink, void* stream) {
+    k_read<<<grid, block, 0, (cudaStream_t)stream>>>((const uint4*)p, nbytes / 16, (uint32_t*)sink);
+}
+void mb_bulk_write(void* p, size_t nbytes, int grid, unsigned chunk, void* stream) {
+    cudaFuncSetAttribute(k_bulk_write, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    k_bulk_write<<<grid, 128, chunk, (cudaStream_t)stream>>>((uint8_t*)p, nbytes, chunk);
+}
+}
