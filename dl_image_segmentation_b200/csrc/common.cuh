@@ -28,6 +28,7 @@ struct b2_ctx {
     uint64_t launches;
     b2::CrcTables* crc_dev;  // device copy
     b2::CrcTables* crc_host;
+    unsigned long long* prof_dev;  // 8 phase counters (b2_debug_parse_phases)
     void* ws;                // grow-on-demand workspace
     size_t ws_bytes;
 };

@@ -114,6 +114,8 @@ int b2_ctx_create(int device, b2_ctx** out) {
     build_tables(c->crc_host);
     B2_CUDA(cudaMalloc(&c->crc_dev, sizeof(CrcTables)));
     B2_CUDA(cudaMemcpy(c->crc_dev, c->crc_host, sizeof(CrcTables), cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMalloc(&c->prof_dev, 128));
+    B2_CUDA(cudaMemset(c->prof_dev, 0, 128));
     *out = c;
     return 0;
 }
@@ -124,6 +126,7 @@ int b2_ctx_destroy(b2_ctx* ctx) {
     cudaDeviceSynchronize();
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->crc_dev) cudaFree(ctx->crc_dev);
+    if (ctx->prof_dev) cudaFree(ctx->prof_dev);
     delete ctx->crc_host;
     delete ctx;
     return 0;

@@ -34,6 +34,7 @@ namespace b2 {
 constexpr int kBufBytes = kTile + 128;   // tile + 32-byte halo, rounded so the second buffer stays 128-byte aligned
 constexpr int kHotMaxK = 32;             // one-hot through shared-memory blocks + bulk stores up to this many classes
 constexpr int kHotLabels = 64;           // labels per warp block (two per lane): one bulk store moves 256*K bytes
+constexpr int kHotBlocks = 2;            // blocks per warp: the bulk store of one overlaps the fill of the other
 
 // ---------------------------------------------------------------- PTX: mbarrier + bulk async copies (TMA, 1-D)
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -73,6 +74,7 @@ struct ParseArgs {
     // tile -> record map.  Opened shard: tile2rec / tile_start / hdr (device-resident counts).  Otherwise uniform:
     // tile w belongs to record w / tiles_x.
     const uint32_t* tile2rec;
+    const uint32_t* order;           // position -> tile id (NULL: identity)
     const uint32_t* tile_start;
     const int64_t* hdr;
     uint32_t tiles_x, n;
@@ -83,6 +85,7 @@ struct ParseArgs {
     uint32_t* crc_out;               // ... or raw CRCs (b2_crc32c)
     int64_t* n_bad;                  // hdr[4] of an opened shard, or NULL
     uint32_t* sched;                 // [0] next chunk of q tiles, [1] CTAs that have finished; both zero between launches
+    unsigned long long* prof;        // phase cycle counters (development aid, kProf instantiation only)
 };
 
 struct __align__(16) TileJob {
@@ -100,6 +103,7 @@ template <int kMode>
 __device__ __forceinline__ void make_job(const ParseArgs& a, uint32_t w, TileJob* j, uint8_t* buf, uint64_t* bar) {
     uint32_t r, tile;
     if (a.tile2rec) {
+        if (a.order) w = a.order[w];
         r = a.tile2rec[w];
         tile = w - a.tile_start[r];
     } else {
@@ -339,8 +343,24 @@ __device__ __forceinline__ void run_flush(const ParseArgs& a, Run& run, uint32_t
     run.open = false;
 }
 
-template <int kMode>
-__global__ void __launch_bounds__(kTileThreads, kMode == B2_SINK_NORM_ONEHOT ? 4 : 6)
+// Development aid: cycles spent by lane 0 of every warp in each phase of the tile loop (B2_PARSE_PROFILE=1).
+#define PROF_BEGIN() \
+    long long prof_t = 0; \
+    unsigned long long prof_acc[7] = {0, 0, 0, 0, 0, 0, 0}; \
+    if (kProf && lane == 0) prof_t = clock64();
+#define PROF_MARK(k) \
+    if (kProf && lane == 0) { \
+        const long long t_ = clock64(); \
+        prof_acc[k] += (unsigned long long)(t_ - prof_t); \
+        prof_t = t_; \
+    }
+#define PROF_END() \
+    if (kProf && lane == 0) { \
+        for (int k_ = 0; k_ < 7; k_++) atomicAdd(&a.prof[k_ + (warp == 0 ? 0 : 8)], prof_acc[k_]); \
+    }
+
+template <int kMode, bool kProf = false>
+__global__ void __launch_bounds__(kTileThreads, kMode == B2_SINK_NORM_ONEHOT ? 3 : 6)
 fused_parse_kernel(const ParseArgs a) {
     extern __shared__ __align__(128) uint8_t dyn[];
     __shared__ CrcSmem cs;
@@ -366,7 +386,7 @@ fused_parse_kernel(const ParseArgs a) {
             s_rcp[c] = __frcp_rn(a.sink.std[c]);
         }
         if (use_hot)
-            for (int i = tid; i < (kTileThreads / 32) * (kHotLabels * K + 4); i += kTileThreads) hot_all[i] = 0.0f;
+            for (int i = tid; i < (kTileThreads / 32) * kHotBlocks * (kHotLabels * K + 4); i += kTileThreads) hot_all[i] = 0.0f;
     }
     if (tid == 0) {
         mbar_init(&bar[0], 1);
@@ -414,26 +434,32 @@ fused_parse_kernel(const ParseArgs a) {
         const uint32_t m = (C % 4 == 0) ? C / 4 : ((C % 2 == 0) ? C / 2 : C);
         img_S = kTileThreads - (kTileThreads % m);
     }
+    PROF_BEGIN();
     uint32_t phase = 0;
     uint32_t s = 0;                       // running CRC state of this thread
     Run run;
     run.open = false;
-    float* hot = hot_all + warp * (kHotLabels * K + 4);   // this warp's one-hot block; float kHotLabels*K is a dummy
+    // this warp's one-hot blocks; float kHotLabels*K of a block is a dummy that is never stored
+    float* hot_w = hot_all + warp * kHotBlocks * (kHotLabels * K + 4);
     const uint32_t hot_dummy = kHotLabels * K;
-    uint32_t slot0 = hot_dummy, slot1 = hot_dummy;        // the floats this lane set in the block last time
+    uint32_t slotA0 = hot_dummy, slotA1 = hot_dummy, slotB0 = hot_dummy, slotB1 = hot_dummy;   // floats this lane set last time
+    uint32_t hot_it = 0;
 
     for (uint32_t it = 0;; it++) {
         const uint32_t b = it & 1;
         if (tid == 0) next_job(&job[b ^ 1], dyn + (b ^ 1) * kBufBytes, &bar[b ^ 1]);
+        PROF_MARK(6);
         const TileJob j = job[b];
         const bool valid = (j.flags & 1) != 0;
         if (run.open && (!valid || j.r != run.r || j.tile != run.last_tile + 1)) run_flush(a, run, s, want_crc, red);
+        PROF_MARK(5);
         if (j.flags & 4) break;
         if (valid) {
             uint8_t* buf8w = dyn + b * kBufBytes;
             if (j.cb) {
                 mbar_wait(&bar[b], (phase >> b) & 1);
                 phase ^= 1u << b;
+            PROF_MARK(0);
             }
             if (j.tail) {
                 if (tid < (int)j.tail) buf8w[j.cb + tid] = a.shard[j.ts + j.cb + tid];
@@ -461,6 +487,7 @@ fused_parse_kernel(const ParseArgs a) {
                     sink_raw(buf32, buf8, ts, te, j.tgt_off, j.tgt_len, static_cast<uint8_t*>(a.sink.tgt_out) + (uint64_t)j.r * a.sink.tgt_stride);
             }
             if (kMode == B2_SINK_NORM_ONEHOT && (j.flags & 2)) {
+                PROF_MARK(1);
                 // ---- uint8 image -> (x-mean)/std float32
                 if (a.sink.img_out && j.img_len && j.img_off < te && j.img_off + j.img_len > ts && (uint32_t)tid < img_S) {
                     float* dst = reinterpret_cast<float*>(static_cast<uint8_t*>(a.sink.img_out) + (uint64_t)j.r * a.sink.img_stride);
@@ -501,6 +528,7 @@ fused_parse_kernel(const ParseArgs a) {
                         }
                     }
                 }
+                PROF_MARK(2);
                 // ---- uint8 target -> one-hot float32
                 if (a.sink.tgt_out && j.tgt_len && j.tgt_off < te && j.tgt_off + j.tgt_len > ts) {
                     float* dst = reinterpret_cast<float*>(static_cast<uint8_t*>(a.sink.tgt_out) + (uint64_t)j.r * a.sink.tgt_stride);
@@ -517,12 +545,15 @@ fused_parse_kernel(const ParseArgs a) {
                         const uint32_t j_lo = (uint32_t)((lo - po + 3) >> 2), j_hi = (uint32_t)((hi - po + 3) >> 2);
                         const uint32_t L_beg = 4 * j_lo, L_end = (4 * j_hi < pl) ? 4 * j_hi : pl;
                         for (uint32_t L0 = L_beg + warp * kHotLabels; L0 < L_end; L0 += (kTileThreads / 32) * kHotLabels) {
-                            if (lane == 0) bulk_wait_read<0>();   // this warp's previous bulk store has read the block
+                            const uint32_t hb = hot_it & 1;
+                            hot_it++;
+                            float* hot = hot_w + hb * (kHotLabels * K + 4);
+                            if (lane == 0) bulk_wait_read<kHotBlocks - 1>();   // the store that last used this block has read it
                             __syncwarp();
-                            hot[slot0] = 0.0f;
-                            hot[slot1] = 0.0f;
+                            hot[hb ? slotB0 : slotA0] = 0.0f;
+                            hot[hb ? slotB1 : slotA1] = 0.0f;
                             const uint32_t l0 = L0 + 2 * lane;
-                            slot0 = slot1 = hot_dummy;
+                            uint32_t slot0 = hot_dummy, slot1 = hot_dummy;
                             if (l0 < L_end) {
                                 const uint32_t lab = buf8[base + l0];
                                 if (lab < (uint32_t)K) slot0 = (2 * lane) * K + lab;
@@ -533,6 +564,7 @@ fused_parse_kernel(const ParseArgs a) {
                             }
                             hot[slot0] = 1.0f;
                             hot[slot1] = 1.0f;
+                            if (hb) { slotB0 = slot0; slotB1 = slot1; } else { slotA0 = slot0; slotA1 = slot1; }
                             fence_proxy_async();
                             __syncwarp();
                             const uint32_t nl = (L_end - L0 < (uint32_t)kHotLabels) ? L_end - L0 : (uint32_t)kHotLabels;
@@ -573,9 +605,12 @@ fused_parse_kernel(const ParseArgs a) {
                 }
             }
         }
+        PROF_MARK(3);
         __syncthreads();   // everyone is done with buffer b and job[b]
+        PROF_MARK(4);
     }
     if (kMode == B2_SINK_NORM_ONEHOT && lane == 0) bulk_wait_read<0>();   // shared memory must outlive the bulk stores
+    PROF_END();
     if (tid == 0) {   // the last CTA out re-arms the chunk counter for the next launch
         __threadfence();
         if (atomicAdd(&a.sched[1], 1u) == gridDim.x - 1) {
@@ -599,7 +634,7 @@ LaunchCfg g_cfg[64];
 
 size_t dyn_bytes(int mode, int K) {
     size_t d = 2 * (size_t)kBufBytes;
-    if (mode == B2_SINK_NORM_ONEHOT && K <= kHotMaxK) d += (size_t)(kTileThreads / 32) * (kHotLabels * K + 4) * sizeof(float);
+    if (mode == B2_SINK_NORM_ONEHOT && K <= kHotMaxK) d += (size_t)(kTileThreads / 32) * kHotBlocks * (kHotLabels * K + 4) * sizeof(float);
     return d;
 }
 
@@ -609,17 +644,21 @@ int launch_fused(b2_ctx* ctx, const ParseArgs& pa, uint64_t max_tiles, cudaStrea
         B2_CUDA(cudaFuncSetAttribute(fused_parse_kernel<B2_SINK_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         B2_CUDA(cudaFuncSetAttribute(fused_parse_kernel<B2_SINK_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         B2_CUDA(cudaFuncSetAttribute(fused_parse_kernel<B2_SINK_NORM_ONEHOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        B2_CUDA(cudaFuncSetAttribute(fused_parse_kernel<B2_SINK_NORM_ONEHOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         cfg.ready = true;
     }
     // persistent grid: as many CTAs as fit on the GPU at once (4 per SM), never more than there are chunks
     const uint64_t chunks = (max_tiles + pa.q - 1) / pa.q;
-    const uint64_t resident = (uint64_t)ctx->sm_count * (pa.sink.mode == B2_SINK_NORM_ONEHOT ? 4 : 6);
+    const uint64_t resident = (uint64_t)ctx->sm_count * (pa.sink.mode == B2_SINK_NORM_ONEHOT ? 3 : 6);
     const unsigned grid = (unsigned)(chunks < resident ? chunks : resident);
     const size_t dyn = dyn_bytes(pa.sink.mode, pa.sink.num_classes);
     switch (pa.sink.mode) {
         case B2_SINK_NONE: fused_parse_kernel<B2_SINK_NONE><<<grid, kTileThreads, dyn, s>>>(pa); break;
         case B2_SINK_RAW: fused_parse_kernel<B2_SINK_RAW><<<grid, kTileThreads, dyn, s>>>(pa); break;
-        default: fused_parse_kernel<B2_SINK_NORM_ONEHOT><<<grid, kTileThreads, dyn, s>>>(pa); break;
+        default:
+            if (pa.prof) fused_parse_kernel<B2_SINK_NORM_ONEHOT, true><<<grid, kTileThreads, dyn, s>>>(pa);
+            else fused_parse_kernel<B2_SINK_NORM_ONEHOT><<<grid, kTileThreads, dyn, s>>>(pa);
+            break;
     }
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
@@ -671,8 +710,8 @@ extern "C" int b2_tfrecord_parse(b2_ctx* ctx, const uint8_t* shard, uint64_t nby
     if (int e = ws_reserve(ctx, (size_t)n * 8 + 8, s)) return e;
     B2_CUDA(cudaMemsetAsync(ctx->ws, 0, (size_t)n * 8 + 8, s));
     uint32_t* acc = static_cast<uint32_t*>(ctx->ws);
-    ParseArgs pa{shard, nbytes, rec_off, rec_len, index, *sink, ctx->crc_dev, nullptr, nullptr, nullptr,
-                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(), acc, acc + n, status, nullptr, nullptr, acc + 2 * (size_t)n};
+    ParseArgs pa{shard, nbytes, rec_off, rec_len, index, *sink, ctx->crc_dev, nullptr, nullptr, nullptr, nullptr,
+                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(), acc, acc + n, status, nullptr, nullptr, acc + 2 * (size_t)n, nullptr};
     return launch_fused(ctx, pa, tx * (uint64_t)n, s);
 }
 
@@ -685,8 +724,10 @@ extern "C" int b2_tfrecord_parse_table(b2_ctx* ctx, const uint8_t* shard, uint64
     if (int e = check_sink(sink, "b2_tfrecord_parse_table")) return e;
     DeviceGuard g(ctx->device);
     const TableView v = table_view(table, nbytes, max_records);
-    ParseArgs pa{shard, nbytes, v.rec_off, v.rec_len, v.index, *sink, ctx->crc_dev, v.tile2rec, v.tile_start, v.hdr,
-                 0, 0, tiles_per_cta(), v.crc_acc, v.done, status, nullptr, v.hdr + 4, reinterpret_cast<uint32_t*>(v.hdr + 5)};
+    ParseArgs pa{shard, nbytes, v.rec_off, v.rec_len, v.index, *sink, ctx->crc_dev, v.tile2rec,
+                 getenv("B2_PARSE_NATURAL_ORDER") ? nullptr : v.order, v.tile_start, v.hdr,
+                 0, 0, tiles_per_cta(), v.crc_acc, v.done, status, nullptr, v.hdr + 4, reinterpret_cast<uint32_t*>(v.hdr + 5),
+                 getenv("B2_PARSE_PROFILE") ? ctx->prof_dev : nullptr};
     return launch_fused(ctx, pa, v.cap_tiles, static_cast<cudaStream_t>(stream));
 }
 
@@ -708,7 +749,17 @@ extern "C" int b2_crc32c(b2_ctx* ctx, const uint8_t* data, const uint64_t* offse
     memset(&sink, 0, sizeof(sink));
     sink.mode = B2_SINK_NONE;
     sink.verify_crc = 1;
-    ParseArgs pa{data, ~0ull, offsets, lens, nullptr, sink, ctx->crc_dev, nullptr, nullptr, nullptr,
-                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(), acc, acc + n, nullptr, crc_out, nullptr, acc + 2 * (size_t)n};
+    ParseArgs pa{data, ~0ull, offsets, lens, nullptr, sink, ctx->crc_dev, nullptr, nullptr, nullptr, nullptr,
+                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(), acc, acc + n, nullptr, crc_out, nullptr, acc + 2 * (size_t)n, nullptr};
     return launch_fused(ctx, pa, tx * (uint64_t)n, s);
+}
+
+/* development aid: read and reset the phase counters filled when B2_PARSE_PROFILE is set */
+extern "C" int b2_debug_parse_phases(b2_ctx* ctx, uint64_t out[16]) {
+    B2_REQUIRE(ctx && out, "b2_debug_parse_phases: NULL argument");
+    DeviceGuard g(ctx->device);
+    B2_CUDA(cudaDeviceSynchronize());
+    B2_CUDA(cudaMemcpy(out, ctx->prof_dev, 128, cudaMemcpyDeviceToHost));
+    B2_CUDA(cudaMemset(ctx->prof_dev, 0, 128));
+    return 0;
 }

@@ -117,9 +117,11 @@ __host__ __device__ __forceinline__ uint32_t record_tiles(uint64_t d0, uint64_t 
 // ---------------------------------------------------------------- shard table (b2_tfrecord_open / _parse_table)
 // One caller-owned device buffer describing an opened shard; every section 16-byte aligned:
 //   hdr int64[8]        [0] records  [1] scan status  [2] tiles  [3] longest record  [4] records with status != 0
+//                       [5] chunk scheduler words of the fused pass  [6] heavy / light tile counters of the index pass
 //   rec_off uint64[cap] | rec_len uint64[cap] | index b2_example_index[cap] | tile_start uint32[cap+1]
 //   crc_acc uint32[cap] | done uint32[cap]   (scratch of the fused pass; zero between launches)
 //   tile2rec uint32[cap_tiles]               (owner record of every 8 KiB tile)
+//   order uint32[cap_tiles]                  (processing order of the tiles: label-payload tiles first, see index_kernel)
 struct TableView {
     int64_t* hdr;
     uint64_t* rec_off;
@@ -129,6 +131,7 @@ struct TableView {
     uint32_t* crc_acc;
     uint32_t* done;
     uint32_t* tile2rec;
+    uint32_t* order;
     uint64_t cap, cap_tiles, bytes;
 };
 __host__ __device__ inline TableView table_view(uint8_t* t, uint64_t nbytes, uint64_t cap) {
@@ -145,6 +148,7 @@ __host__ __device__ inline TableView table_view(uint8_t* t, uint64_t nbytes, uin
     v.crc_acc = reinterpret_cast<uint32_t*>(t + o);        o += up(4 * cap);
     v.done = reinterpret_cast<uint32_t*>(t + o);           o += up(4 * cap);
     v.tile2rec = reinterpret_cast<uint32_t*>(t + o);       o += up(4 * v.cap_tiles);
+    v.order = reinterpret_cast<uint32_t*>(t + o);          o += up(4 * v.cap_tiles);
     v.bytes = o;
     return v;
 }

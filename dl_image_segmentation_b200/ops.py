@@ -464,7 +464,7 @@ def _make_sink(ctx, mode, verify_crc, mean, std, num_classes, channels, img_buf,
 
 
 def parse_table(st: ShardTable, mode, img_elems=0, tgt_elems=0, verify_crc=True, mean=None, std=None, num_classes=None,
-                out=None, status=None):
+                out=None, status=None, want_img=True, want_tgt=True):
     """Enqueue the fused pass over EVERY record of an opened shard; no host synchronisation.
 
     The record count lives on the device, so outputs are sized for st.max_records rows:
@@ -495,6 +495,10 @@ def parse_table(st: ShardTable, mode, img_elems=0, tgt_elems=0, verify_crc=True,
             torch.empty((cap, il), dtype=torch.float32, device=ctx.device),
             torch.empty((cap, tl * K), dtype=torch.float32, device=ctx.device))
     sink = _make_sink(ctx, mode, verify_crc, mean, std, num_classes, C, img_buf, tgt_buf)
+    if not want_img:
+        sink.img_out = None          # the C ABI skips a NULL output
+    if not want_tgt:
+        sink.tgt_out = None
     if status is None:
         status = torch.empty((cap,), dtype=torch.int32, device=ctx.device)
     check(lib().b2_tfrecord_parse_table(ctx.handle, ptr(st.shard), st.nbytes, cap, ptr(st.table), ctypes.byref(sink),

@@ -150,6 +150,8 @@ def bench_parse(dev, n_shards=8):
     sys.path.insert(0, ROOT)
     import bench as B
     B.N_SHARDS = n_shards
+    if os.environ.get("KB_RECS"):           # longer shards: separates steady-state rate from launch/tail effects
+        B.RECS_PER_SHARD = int(os.environ["KB_RECS"])
     shards = B.make_shards_on_device(dev, 7)
     n = B.RECS_PER_SHARD
     tabs = [ops.open_shard_async(s, dev, max_records=n) for s in shards]
@@ -178,6 +180,26 @@ def bench_parse(dev, n_shards=8):
                             status=status)
         report(name, timeit(fn, 16), algo)
         assert not status.cpu().numpy().any()
+    if os.environ.get("B2_PARSE_PROFILE"):
+        import ctypes
+        ph = (ctypes.c_uint64 * 16)()
+        _lib.check(_lib.lib().b2_debug_parse_phases(_lib.get_ctx(dev).handle, ph))     # reset
+        for i in range(4):
+            ops.parse_table(tabs[i], "norm_onehot", B.H * B.W * B.C, B.H * B.W, verify_crc=True, mean=mean, std=std,
+                            num_classes=B.K, out=out, status=status)
+        _lib.check(_lib.lib().b2_debug_parse_phases(_lib.get_ctx(dev).handle, ph))
+        names = ["tile wait", "crc", "image sink", "one-hot sink", "end barrier", "flush", "job fetch"]
+        for label, o in (("warp 0", 0), ("warps 1-7", 8)):
+            tot = float(sum(ph[o:o + 7]))
+            print(json.dumps({"phase share of cycles, norm+onehot +crc, " + label: {k: round(ph[o + i] / tot, 4) for i, k in enumerate(names)},
+                              "cycles": tot}))
+    if os.environ.get("KB_SPLIT"):          # which sink limits the fused pass?
+        for name, wi, wt, algo in (("parse image sink only, no crc", True, False, n * (rec + img_b)),
+                                   ("parse one-hot sink only, no crc", False, True, n * (rec + hot_b))):
+            def fn2(i):
+                ops.parse_table(tabs[i % n_shards], "norm_onehot", B.H * B.W * B.C, B.H * B.W, verify_crc=False, mean=mean,
+                                std=std, num_classes=B.K, out=out, status=status, want_img=wi, want_tgt=wt)
+            report(name, timeit(fn2, 16), algo)
     big = torch.empty((1 << 30,), dtype=torch.uint8, device=dev)
     big2 = torch.empty((1 << 30,), dtype=torch.uint8, device=dev)
     report("reference: torch zero_ 1 GiB (write-only)", timeit(lambda i: big.zero_(), 10), 1 << 30)

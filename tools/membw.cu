@@ -36,7 +36,57 @@ __global__ void k_bulk_write(uint8_t* p, size_t nbytes, uint32_t chunk) {
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
+// emulate the fused pass's label tiles: CTAs draw regions of `per_region` chunks from a counter; the 8 warps of a CTA
+// push the region's chunks round-robin (warp w: chunks w, w+8, ...) with `depth` bulk stores in flight per warp
+__global__ void k_bulk_pattern(uint8_t* p, size_t nbytes, uint32_t chunk, uint32_t per_region, uint32_t misalign,
+                               unsigned int* counter, int depth) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ unsigned int s_region;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t i = threadIdx.x; i < 8 * 2 * chunk / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = i;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const size_t region_bytes = (size_t)chunk * per_region;
+    const size_t n_regions = (nbytes - 256) / region_bytes;
+    uint32_t it = 0;
+    for (;;) {
+        if (threadIdx.x == 0) s_region = atomicAdd(counter, 1u);
+        __syncthreads();
+        const unsigned int region = s_region;
+        if (region >= n_regions) break;
+        uint8_t* base = p + region * region_bytes + misalign;
+        for (uint32_t c = warp; c < per_region; c += 8, it++) {
+            if (depth >= 10) {   // as the fused pass: every lane writes the block, then a proxy fence, then the store
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                float* blk = reinterpret_cast<float*>(sm + (warp * 2 + (it & 1)) * chunk);
+                blk[(lane * 20 + it) % (chunk / 4)] = 1.0f;
+                blk[(lane * 20 + 10 + it) % (chunk / 4)] = 0.0f;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+            }
+            if (lane == 0) {
+                const uint32_t s = (uint32_t)__cvta_generic_to_shared(sm + (warp * 2 + (it & 1)) * chunk);
+                if (depth >= 10) {}
+                else if (depth == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(base + (size_t)c * chunk), "r"(s), "r"(chunk) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 extern "C" {
+void mb_bulk_pattern(void* p, size_t nbytes, int grid, unsigned chunk, unsigned per_region, unsigned misalign, void* counter,
+                     int depth, void* stream) {
+    cudaFuncSetAttribute(k_bulk_pattern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaMemsetAsync(counter, 0, 4, (cudaStream_t)stream);
+    k_bulk_pattern<<<grid, 256, 8 * 2 * chunk, (cudaStream_t)stream>>>((uint8_t*)p, nbytes, chunk, per_region, misalign,
+                                                                     (unsigned int*)counter, depth);
+}
 void mb_write(void* p, size_t nbytes, int grid, int block, int cs, void* stream) {
     k_write<<<grid, block, 0, (cudaStream_t)stream>>>((uint4*)p, nbytes / 16, cs);
 }

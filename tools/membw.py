@@ -33,3 +33,12 @@ for grid in (148 * 2, 148 * 4, 148 * 8):
     for chunk in (2560, 8192, 32768):
         ms = t(lambda: L.mb_bulk_write(p, ctypes.c_size_t(N), grid, chunk, st))
         print(json.dumps({"probe": "write TMA bulk store", "grid": grid, "chunk": chunk, "GB/s": round(N / ms / 1e6, 1)}))
+
+ctr = torch.zeros((4,), dtype=torch.int32, device=dev)
+for grid in (148 * 3, 148 * 4):
+    for chunk, per_region in ((2560, 128), (5120, 64)):
+        for depth in (1, 2, 10):
+            ms = t(lambda: L.mb_bulk_pattern(p, ctypes.c_size_t(N), grid, chunk, per_region, 32, ctypes.c_void_p(ctr.data_ptr()), depth, st))
+            print(json.dumps({"probe": "bulk-store pattern (label tiles)", "grid": grid, "chunk": chunk, "chunks_per_region": per_region,
+                              "mode": {1: "1 in flight", 2: "2 in flight", 10: "2 in flight + smem writes + proxy fence"}[depth],
+                              "GB/s": round(N / ms / 1e6, 1)}))
