@@ -147,22 +147,33 @@ def run_ours(args, rank, world):
     kern_events = []
     want = torch.tensor([RECS_PER_SHARD, 0, 0], dtype=torch.int64, device=dev)
 
-    def consume(source):
-        """Drain the pipeline; per shard accumulate |records - expected| + scan status + bad records on the device."""
+    idx014 = torch.tensor([0, 1, 4], dtype=torch.int64, device=dev)
+
+    def make_pass(source):
+        """One pass over all shards as a CUDA graph; per shard the consumer folds |records - expected| + scan status +
+        bad records into one device-side status word."""
         bad = torch.zeros((), dtype=torch.int64, device=dev)
-        for _, _, _, table in pipe.run(source):
-            h = table.hdr_dev
-            bad += (h[[0, 1, 4]] - want).abs().sum()
-        return bad
+
+        def consume(img, tgt, status, table):
+            bad.add_((table.hdr_dev.index_select(0, idx014) - want).abs().sum())
+        return ops.CapturedPass(pipe, source, consume), bad
+
+    pass_res, bad_res = make_pass(shards)
+    pass_e2e, bad_e2e = make_pass(pinned)                       # H2D of every shard inside the graph
+    host_status = torch.zeros((), dtype=torch.int64).pin_memory()
 
     def step_resident():
-        return consume(shards)
+        pass_res.replay()
+        return bad_res
 
     def step_e2e():
-        bad = consume(pinned)                                   # H2D of every shard inside
-        if int(bad.cpu()):                                      # D2H: the job's status word
+        bad_e2e.zero_()
+        pass_e2e.replay()
+        host_status.copy_(bad_e2e, non_blocking=True)           # D2H: the job's status word
+        torch.cuda.current_stream().synchronize()
+        if int(host_status):
             raise RuntimeError("parse status != 0")
-        return bad
+        return bad_e2e
 
     ev_out = (torch.empty((RECS_PER_SHARD, H * W * C), dtype=torch.float32, device=dev),
               torch.empty((RECS_PER_SHARD, H * W * K), dtype=torch.float32, device=dev))
@@ -188,7 +199,6 @@ def run_ours(args, rank, world):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        l0 = ctx.launches
         a, b = ev(), ev()
         a.record()
         last = None
@@ -203,19 +213,21 @@ def run_ours(args, rank, world):
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, ctx.launches - l0, last
+        return ms, last
 
     sampler = ClockSampler(local)
     sampler.start()
-    ms, launches, bad = timed(step_resident, args.steps, args.warmup)
+    bad_res.zero_()
+    ms, bad = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop()
     assert int(bad.cpu()) == 0, "parse status != 0"
+    launches = pass_res.launches_per_replay * args.steps        # our kernels inside the timed region (graph nodes)
     step_kernel_events()                                    # warm-up of the un-pipelined order
     del kern_events[:]
     step_kernel_events()                                    # per-launch CUDA events of the dominant kernel
     step_kernel_events()
     e2e_steps = max(1, min(args.steps, 10))
-    ms_e2e, _, _ = timed(step_e2e, e2e_steps, 2)
+    ms_e2e, _ = timed(step_e2e, e2e_steps, 2)
 
     recs_step = N_SHARDS * RECS_PER_SHARD
     value = world * recs_step * args.steps / (ms / 1e3)

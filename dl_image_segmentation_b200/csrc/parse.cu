@@ -6,35 +6,49 @@
 //                                   cast -> per-band normalise, label -> one-hot (north-star row A17)
 //
 // Work decomposition.  Record data is cut into 8 KiB tiles on a 16-byte aligned grid anchored at the record's
-// (aligned-down) data start.  A 256-thread CTA owns a run of `q` consecutive tiles.  For every tile
-//   * one elected thread issues a TMA bulk copy (cp.async.bulk, SASS UBLKCP) of the tile + 32-byte halo into one
-//     of two shared-memory buffers and arms an mbarrier; the copy of tile i+1 overlaps the work on tile i,
-//   * the CTA computes the tile's CRC-32C partial from shared memory (the bytes cross HBM exactly once),
-//   * the payload sinks read the same shared-memory tile: raw copy, or uint8 -> (x-mean)/std float32 with
-//     128-bit streaming stores, and label -> one-hot through per-warp shared-memory blocks that are pushed to
-//     HBM with TMA bulk stores (cp.async.bulk.global.shared::cta): a label costs ONE 4-byte shared-memory write,
-//     the 4*K output bytes per label never pass through registers,
-//   * thread 0 advances the tile's CRC partial to the end of the record (one GF(2)[x] multiplication by a
-//     tabulated power of x), XORs it into the record's accumulator and counts the tile; the CTA that completes
-//     a record un-advances the zero padding, compares with the stored masked CRC and writes the record's status.
-// There is no second kernel and no per-tile workspace.
+// (aligned-down) data start.  The kernel is persistent (3 CTAs per SM) and warp-specialised:
+//   * the PRODUCER warp draws chunks of q consecutive tiles from a device-side counter, describes each tile in
+//     shared memory and starts a TMA bulk copy (cp.async.bulk, SASS UBLKCP) of the tile + 32-byte halo into a ring of
+//     shared-memory buffers; an mbarrier per buffer flips when the bytes have landed;
+//   * the eight CONSUMER warps compute the tile's CRC-32C contribution from shared memory (the bytes cross HBM
+//     exactly once) and run the payload sinks on the same shared-memory tile: raw copy, or uint8 -> (x-mean)/std
+//     float32 with 128-bit streaming stores, and label -> one-hot through per-warp shared-memory blocks that are
+//     pushed to HBM with TMA bulk stores (cp.async.bulk.global.shared::cta): a label costs ONE 4-byte shared-memory
+//     write, the 4*K output bytes per label never pass through registers;
+//   * producer and consumers meet only through mbarriers (full / empty per buffer); there is no __syncthreads in
+//     the steady state and no second kernel: the CRC state of a thread runs on across the consecutive tiles of a
+//     record, the warps of a CTA fold their states through a shared-memory slot when the run of tiles ends, and
+//     the last warp there merges { CRC partial, tiles done } into the record's 64-bit accumulator with one
+//     compare-and-swap; whoever completes a record un-advances the zero padding, compares with the stored
+//     masked CRC and writes the record's status.
 //
 // CRC-32C without a CRC instruction: the pure CRC (zero init) is linear over GF(2), so
-//   * thread i CRCs its two 16-byte vectors (tile offsets 16 i and 16 i + 4096) with slice-by-4 table steps whose
-//     "advance" also skips the gap between them,
-//   * one multiplication by x^(8*(4080-16 i)) moves its partial to the end of the tile,
-//   * partials XOR together (warp shuffles, then 8 words of shared memory) into one word per tile.
-// The 0xFFFFFFFF init is XORed into the first four data bytes.
+//   * thread i consumes vectors i and i+256 (16 bytes each) of every tile with slice-by-4 table steps; the step
+//     after a vector's last word also skips the 4080 bytes to the thread's next vector, in this tile or the next;
+//   * when the run ends, one GF(2)[x] multiplication by x^(-128 i) aligns thread i's state with the tile end,
+//     the states XOR together, and one more multiplication by a tabulated power of x moves the partial to the
+//     end of the record.  The 0xFFFFFFFF init is XORed into the first four data bytes.
 #include <cstring>
 
 #include "tfrecord_common.cuh"
+
+#ifndef B2_STAGES
+#define B2_STAGES 2
+#endif
+#ifndef B2_HOT_BLOCKS
+#define B2_HOT_BLOCKS 2
+#endif
 
 namespace b2 {
 
 constexpr int kBufBytes = kTile + 128;   // tile + 32-byte halo, rounded so the second buffer stays 128-byte aligned
 constexpr int kHotMaxK = 32;             // one-hot through shared-memory blocks + bulk stores up to this many classes
 constexpr int kHotLabels = 64;           // labels per warp block (two per lane): one bulk store moves 256*K bytes
-constexpr int kHotBlocks = 2;            // blocks per warp: the bulk store of one overlaps the fill of the other
+constexpr int kHotBlocks = B2_HOT_BLOCKS;            // blocks per warp: the bulk store of one overlaps the fill of the other
+constexpr int kStages = B2_STAGES;               // tile buffers in the producer -> consumer ring
+constexpr int kConsumerWarps = kTileThreads / 32;
+constexpr int kCtaThreads = kTileThreads + 32;   // 8 consumer warps + 1 producer warp
+constexpr int kRunSlots = 4;             // shared-memory CRC accumulators for runs in flight (> kStages)
 
 // ---------------------------------------------------------------- PTX: mbarrier + bulk async copies (TMA, 1-D)
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -43,6 +57,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -74,18 +91,18 @@ struct ParseArgs {
     // tile -> record map.  Opened shard: tile2rec / tile_start / hdr (device-resident counts).  Otherwise uniform:
     // tile w belongs to record w / tiles_x.
     const uint32_t* tile2rec;
-    const uint32_t* order;           // position -> tile id (NULL: identity)
     const uint32_t* tile_start;
     const int64_t* hdr;
     uint32_t tiles_x, n;
     uint32_t q;                      // consecutive tiles per CTA
-    uint32_t* crc_acc;               // per record, zero on entry, zero again on exit
-    uint32_t* done;
+    unsigned long long* acc;         // per record { CRC partial (low word), tiles accounted for (high word) }: zero on
+                                     // entry, zero again on exit
     int32_t* status;                 // per-record status (parse) ...
     uint32_t* crc_out;               // ... or raw CRCs (b2_crc32c)
     int64_t* n_bad;                  // hdr[4] of an opened shard, or NULL
     uint32_t* sched;                 // [0] next chunk of q tiles, [1] CTAs that have finished; both zero between launches
     unsigned long long* prof;        // phase cycle counters (development aid, kProf instantiation only)
+    uint32_t row_mask;               // ~0; development probes pass 0 so that every record lands in output row 0 (L2-resident)
 };
 
 struct __align__(16) TileJob {
@@ -103,7 +120,6 @@ template <int kMode>
 __device__ __forceinline__ void make_job(const ParseArgs& a, uint32_t w, TileJob* j, uint8_t* buf, uint64_t* bar) {
     uint32_t r, tile;
     if (a.tile2rec) {
-        if (a.order) w = a.order[w];
         r = a.tile2rec[w];
         tile = w - a.tile_start[r];
     } else {
@@ -115,8 +131,9 @@ __device__ __forceinline__ void make_job(const ParseArgs& a, uint32_t w, TileJob
     j->r = r;
     j->tile = tile;
     j->nt = nt;
-    if (tile >= nt) {
+    if (tile >= nt) {   // uniform map only: this record has fewer tiles than the longest one
         j->flags = 0;
+        mbar_arrive(bar);
         return;
     }
     const uint64_t d1 = d0 + len, ts = (d0 & ~15ull) + (uint64_t)tile * kTile, te = ts + kTile;
@@ -160,9 +177,12 @@ __device__ __forceinline__ void make_job(const ParseArgs& a, uint32_t w, TileJob
     }
     j->cb = cb;
     j->tail = tail;
+    for (uint32_t i = 0; i < tail; i++) buf[cb + i] = a.shard[ts + cb + i];   // < 16 bytes, last tile of a shard only
     if (cb) {
-        mbar_expect_tx(bar, cb);
+        mbar_expect_tx(bar, cb);          // release: the job and the tail bytes are visible to whoever sees the phase flip
         bulk_g2s(buf, a.shard + ts, cb, bar);
+    } else {
+        mbar_arrive(bar);
     }
 }
 
@@ -176,7 +196,7 @@ __device__ __forceinline__ void sink_raw(const uint32_t* buf32, const uint8_t* b
         // 16-byte destination groups whose FIRST byte lies in the tile; last partial group done bytewise
         const uint64_t g_lo = (lo - po + 15) >> 4, g_hi = (hi - po + 15) >> 4;
         const uint64_t full = pl >> 4;
-        for (uint64_t g = g_lo + threadIdx.x; g < g_hi; g += blockDim.x) {
+        for (uint64_t g = g_lo + threadIdx.x; g < g_hi; g += kTileThreads) {
             const uint32_t o = (uint32_t)(po + 16 * g - ts);
             if (g < full) {
                 uint4 v;
@@ -190,7 +210,7 @@ __device__ __forceinline__ void sink_raw(const uint32_t* buf32, const uint8_t* b
             }
         }
     } else {
-        for (uint64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) dst[p - po] = buf8[p - ts];
+        for (uint64_t p = lo + threadIdx.x; p < hi; p += kTileThreads) dst[p - po] = buf8[p - ts];
     }
 }
 
@@ -204,7 +224,12 @@ __device__ __forceinline__ float norm_fast(float d, float sd, float rc) {
     return __fmaf_rn(rem, rc, q);
 }
 
-__device__ inline void finalize_record(const ParseArgs& a, const TileJob& j) {
+struct RecRef {   // what finalize_record needs to know about the record
+    uint32_t r, nt;
+    uint64_t d0, d1;
+};
+
+__device__ inline void finalize_record(const ParseArgs& a, const RecRef& j, uint32_t acc) {
     const uint32_t r = j.r;
     const uint64_t d0 = j.d0, len = j.d1 - j.d0;
     const bool want_crc = a.sink.verify_crc || a.crc_out;
@@ -214,9 +239,7 @@ __device__ inline void finalize_record(const ParseArgs& a, const TileJob& j) {
             uint32_t s = 0xFFFFFFFFu;
             for (uint64_t i = 0; i < len; i++) s = (s >> 8) ^ __ldg(&a.tab->t4[3][(s ^ a.shard[d0 + i]) & 0xff]);
             crc = ~s;
-            atomicExch(&a.crc_acc[r], 0u);
         } else {
-            uint32_t acc = atomicExch(&a.crc_acc[r], 0u);
             // acc sits at the end of the last tile; un-advance by the zero padding after the record end
             const uint64_t pad = (d0 & ~15ull) + (uint64_t)j.nt * kTile - j.d1;
             acc = multmodp(__ldg(&a.tab->xinv16[pad >> 4]), acc);
@@ -224,7 +247,6 @@ __device__ inline void finalize_record(const ParseArgs& a, const TileJob& j) {
             crc = ~acc;
         }
     }
-    a.done[r] = 0;
     if (a.crc_out) {
         a.crc_out[r] = crc;
         return;
@@ -300,50 +322,59 @@ __device__ __forceinline__ uint32_t crc_tile_step(uint32_t s, const uint4* buf4,
     return s;
 }
 
-struct Run {             // consecutive tiles of one record handled by this CTA (uniform across the CTA)
+struct Run {             // consecutive tiles of one record handled by this CTA (uniform across the consumer warps)
     uint32_t r, nt, last_tile, tiles;
     uint64_t d0, d1;
     bool open;
 };
+struct RunAcc {          // shared-memory meeting point of the eight consumer warps at the end of a run
+    uint32_t crc, warps;
+};
 
-// Close a run: fold the per-thread CRC states into the record accumulator, count the tiles, finalise the record
-// if this was its last outstanding run.  Called by all threads (contains __syncthreads).
-__device__ __forceinline__ void run_flush(const ParseArgs& a, Run& run, uint32_t& s, bool want_crc, uint32_t* red) {
-    const int tid = threadIdx.x;
+// Close a run.  No CTA-wide barrier: every consumer warp folds its lanes' CRC states, XORs the result into the run's
+// shared-memory slot and counts itself; the warp that arrives last moves the partial to the end of the record and
+// merges { CRC, tiles } into the record's 64-bit accumulator with one compare-and-swap loop (a single address, so no
+// fences are needed), finalising the record when its tile count is complete.  The other warps are already working
+// on the next tile.
+__device__ __forceinline__ void run_flush(const ParseArgs& a, Run& run, uint32_t& s, uint32_t& run_seq, bool want_crc,
+                                          RunAcc* racc) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    RunAcc* ra = racc + (run_seq & (kRunSlots - 1));
     const bool crc = want_crc && run.d1 - run.d0 >= 4;
     if (crc) {
         uint32_t t = multmodp_fast(__ldg(&a.tab->xinv16[tid]), s);
 #pragma unroll
         for (int o = 16; o; o >>= 1) t ^= __shfl_xor_sync(0xffffffffu, t, o);
-        if ((tid & 31) == 0) red[tid >> 5] = t;
-        __syncthreads();
+        if (lane == 0 && t) atomicXor(&ra->crc, t);
     }
-    if (tid == 0) {
-        if (crc) {
-            uint32_t c = 0;
-#pragma unroll
-            for (int k = 0; k < kTileThreads / 32; k++) c ^= red[k];
-            c = multmodp_fast(tile_power(a.tab, run.nt - 1 - run.last_tile), c);
-            if (c) atomicXor(&a.crc_acc[run.r], c);
-        }
-        __threadfence();
-        const uint32_t old = atomicAdd(&a.done[run.r], run.tiles);
-        if (old + run.tiles == run.nt) {
-            __threadfence();
-            TileJob j;
-            j.r = run.r;
-            j.nt = run.nt;
-            j.d0 = run.d0;
-            j.d1 = run.d1;
-            finalize_record(a, j);
+    if (lane == 0) {
+        __threadfence_block();
+        if (atomicAdd(&ra->warps, 1u) == kConsumerWarps - 1) {
+            __threadfence_block();
+            uint32_t c = atomicExch(&ra->crc, 0u);
+            ra->warps = 0;
+            if (crc) c = multmodp_fast(tile_power(a.tab, run.nt - 1 - run.last_tile), c);
+            unsigned long long* acc = a.acc + run.r;
+            unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(acc), upd;
+            for (;;) {
+                upd = (old ^ (unsigned long long)c) + ((unsigned long long)run.tiles << 32);
+                const unsigned long long seen = atomicCAS(acc, old, upd);
+                if (seen == old) break;
+                old = seen;
+            }
+            if ((uint32_t)(upd >> 32) == run.nt) {
+                *acc = 0ull;               // re-arm for the next launch; nobody else touches a finished record
+                RecRef rr{run.r, run.nt, run.d0, run.d1};
+                finalize_record(a, rr, (uint32_t)upd);
+            }
         }
     }
-    if (crc) __syncthreads();   // red[] may be rewritten by the next flush
     s = 0;
     run.open = false;
+    run_seq++;
 }
 
-// Development aid: cycles spent by lane 0 of every warp in each phase of the tile loop (B2_PARSE_PROFILE=1).
+// Development aid: cycles spent by lane 0 of every consumer warp in each phase of the tile loop (B2_PARSE_PROFILE=1).
 #define PROF_BEGIN() \
     long long prof_t = 0; \
     unsigned long long prof_acc[7] = {0, 0, 0, 0, 0, 0, 0}; \
@@ -359,14 +390,18 @@ __device__ __forceinline__ void run_flush(const ParseArgs& a, Run& run, uint32_t
         for (int k_ = 0; k_ < 7; k_++) atomicAdd(&a.prof[k_ + (warp == 0 ? 0 : 8)], prof_acc[k_]); \
     }
 
+// Warp-specialised persistent kernel: warp 8 is the PRODUCER (draws chunks of q tiles from the device-side counter,
+// describes each tile in shared memory and starts its TMA bulk copy into a ring of kStages buffers), warps 0..7 are
+// CONSUMERS (CRC, payload sinks).  They meet only through mbarriers: full[s] flips when tile s has landed, empty[s]
+// when all eight consumer warps are done with it — there is no __syncthreads in the steady state.
 template <int kMode, bool kProf = false>
-__global__ void __launch_bounds__(kTileThreads, kMode == B2_SINK_NORM_ONEHOT ? 3 : 6)
+__global__ void __launch_bounds__(kCtaThreads, kMode == B2_SINK_NORM_ONEHOT ? 3 : 5)
 fused_parse_kernel(const ParseArgs a) {
     extern __shared__ __align__(128) uint8_t dyn[];
     __shared__ CrcSmem cs;
-    __shared__ uint32_t red[kTileThreads / 32];
-    __shared__ TileJob job[2];
-    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ TileJob job[kStages];
+    __shared__ __align__(8) uint64_t full[kStages], empty[kStages];
+    __shared__ RunAcc racc[kRunSlots];
     __shared__ float s_mean[64], s_std[64], s_rcp[64];
     __shared__ int s_exact_div;
     const int tid = threadIdx.x;
@@ -375,57 +410,70 @@ fused_parse_kernel(const ParseArgs a) {
     const bool want_crc = a.sink.verify_crc || a.crc_out;
     const int C = a.sink.channels, K = a.sink.num_classes;
     const bool use_hot = K <= kHotMaxK;
-    float* hot_all = reinterpret_cast<float*>(dyn + 2 * kBufBytes);
+    float* hot_all = reinterpret_cast<float*>(dyn + kStages * kBufBytes);
 
     if (want_crc) load_crc_tables(&cs, a.tab);
     if (kMode == B2_SINK_NORM_ONEHOT) {
         if (tid == 0) s_exact_div = 0;
-        for (int c = tid; c < C; c += kTileThreads) {
+        for (int c = tid; c < C; c += kCtaThreads) {
             s_mean[c] = a.sink.mean[c];
             s_std[c] = a.sink.std[c];
             s_rcp[c] = __frcp_rn(a.sink.std[c]);
         }
         if (use_hot)
-            for (int i = tid; i < (kTileThreads / 32) * kHotBlocks * (kHotLabels * K + 4); i += kTileThreads) hot_all[i] = 0.0f;
+            for (int i = tid; i < kConsumerWarps * kHotBlocks * (kHotLabels * K + 4); i += kCtaThreads) hot_all[i] = 0.0f;
     }
     if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+        for (int k = 0; k < kStages; k++) {
+            mbar_init(&full[k], 1);
+            mbar_init(&empty[k], kConsumerWarps);
+        }
+        for (int k = 0; k < kRunSlots; k++) racc[k].crc = racc[k].warps = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (kMode == B2_SINK_NORM_ONEHOT) {
         int bad = 0;
-        for (int i = tid; i < C * 256; i += kTileThreads) {
+        for (int i = tid; i < C * 256; i += kCtaThreads) {
             const int c = i >> 8;
             const float d = __fsub_rn((float)(i & 255), s_mean[c]);
             bad |= __float_as_uint(norm_fast(d, s_std[c], s_rcp[c])) != __float_as_uint(__fdiv_rn(d, s_std[c]));
         }
         if (bad) s_exact_div = 1;
+        __syncthreads();
     }
-    // Tiles are handed out in chunks of q consecutive tiles from a device-side counter, so the per-CTA set-up above is
-    // paid once per resident CTA and a CTA that drew cheap (image) tiles simply draws more of them.
-    uint32_t feed_w = 0, feed_left = 0;   // thread 0 only: next tile of the current chunk, tiles left in it
-    bool feed_end = false;
-    auto next_job = [&](TileJob* jb, uint8_t* buf, uint64_t* br) {
-        if (feed_left == 0 && !feed_end) {
-            const uint64_t w = (uint64_t)atomicAdd(&a.sched[0], 1u) * a.q;
-            if (w >= total) feed_end = true;
-            else {
+
+    if (warp == kConsumerWarps) {
+        // ------------------------------------------------------------------------------------------ producer
+        if (lane != 0) return;
+        uint32_t feed_w = 0, feed_left = 0;
+        for (uint32_t it = 0;; it++) {
+            const uint32_t slot = it % kStages, use = it / kStages;
+            if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
+            if (feed_left == 0) {
+                const uint64_t w = (uint64_t)atomicAdd(&a.sched[0], 1u) * a.q;
+                if (w >= total) {
+                    job[slot].flags = 4;
+                    mbar_arrive(&full[slot]);
+                    break;
+                }
                 feed_w = (uint32_t)w;
                 feed_left = (uint32_t)(total - w < a.q ? total - w : a.q);
             }
+            make_job<kMode>(a, feed_w, &job[slot], dyn + slot * kBufBytes, &full[slot]);
+            feed_w++;
+            feed_left--;
         }
-        if (feed_end) {
-            jb->flags = 4;
-            return;
+        // the last CTA out re-arms the chunk counter for the next launch
+        __threadfence();
+        if (atomicAdd(&a.sched[1], 1u) == gridDim.x - 1) {
+            a.sched[0] = 0;
+            a.sched[1] = 0;
         }
-        make_job<kMode>(a, feed_w, jb, buf, br);
-        feed_w++;
-        feed_left--;
-    };
-    if (tid == 0) next_job(&job[0], dyn, &bar[0]);
-    __syncthreads();
+        return;
+    }
+
+    // ---------------------------------------------------------------------------------------------- consumers
     const bool exact_div = kMode == B2_SINK_NORM_ONEHOT && s_exact_div != 0;
     // image loop stride: the largest S <= 256 with 4 S a multiple of C, so that a thread's four bytes always fall on
     // the same four bands and their constants stay in registers
@@ -434,9 +482,8 @@ fused_parse_kernel(const ParseArgs a) {
         const uint32_t m = (C % 4 == 0) ? C / 4 : ((C % 2 == 0) ? C / 2 : C);
         img_S = kTileThreads - (kTileThreads % m);
     }
-    PROF_BEGIN();
-    uint32_t phase = 0;
     uint32_t s = 0;                       // running CRC state of this thread
+    uint32_t run_seq = 0;
     Run run;
     run.open = false;
     // this warp's one-hot blocks; float kHotLabels*K of a block is a dummy that is never stored
@@ -444,58 +491,52 @@ fused_parse_kernel(const ParseArgs a) {
     const uint32_t hot_dummy = kHotLabels * K;
     uint32_t slotA0 = hot_dummy, slotA1 = hot_dummy, slotB0 = hot_dummy, slotB1 = hot_dummy;   // floats this lane set last time
     uint32_t hot_it = 0;
+    PROF_BEGIN();
 
     for (uint32_t it = 0;; it++) {
-        const uint32_t b = it & 1;
-        if (tid == 0) next_job(&job[b ^ 1], dyn + (b ^ 1) * kBufBytes, &bar[b ^ 1]);
-        PROF_MARK(6);
-        const TileJob j = job[b];
-        const bool valid = (j.flags & 1) != 0;
-        if (run.open && (!valid || j.r != run.r || j.tile != run.last_tile + 1)) run_flush(a, run, s, want_crc, red);
+        const uint32_t slot = it % kStages, use = it / kStages;
+        mbar_wait(&full[slot], use & 1);
+        PROF_MARK(0);
+        const TileJob& j = job[slot];
+        const uint32_t flags = j.flags;
+        const bool valid = (flags & 1) != 0;
+        if (run.open && (!valid || j.r != run.r || j.tile != run.last_tile + 1)) run_flush(a, run, s, run_seq, want_crc, racc);
         PROF_MARK(5);
-        if (j.flags & 4) break;
+        if (flags & 4) break;
         if (valid) {
-            uint8_t* buf8w = dyn + b * kBufBytes;
-            if (j.cb) {
-                mbar_wait(&bar[b], (phase >> b) & 1);
-                phase ^= 1u << b;
-            PROF_MARK(0);
-            }
-            if (j.tail) {
-                if (tid < (int)j.tail) buf8w[j.cb + tid] = a.shard[j.ts + j.cb + tid];
-                __syncthreads();
-            }
-            const uint4* buf4 = reinterpret_cast<const uint4*>(buf8w);
-            const uint32_t* buf32 = reinterpret_cast<const uint32_t*>(buf8w);
-            const uint8_t* buf8 = buf8w;
+            const uint8_t* buf8 = dyn + slot * kBufBytes;
+            const uint4* buf4 = reinterpret_cast<const uint4*>(buf8);
+            const uint32_t* buf32 = reinterpret_cast<const uint32_t*>(buf8);
             const uint64_t ts = j.ts, te = ts + kTile;
+            const uint64_t d0 = j.d0, d1 = j.d1;
             if (!run.open) {
                 run.open = true;
                 run.r = j.r;
                 run.nt = j.nt;
-                run.d0 = j.d0;
-                run.d1 = j.d1;
+                run.d0 = d0;
+                run.d1 = d1;
                 run.tiles = 0;
             }
             run.tiles++;
             run.last_tile = j.tile;
-            if (want_crc && j.d1 - j.d0 >= 4) s = crc_tile_step(s, buf4, &cs, j, j.tile != 0 && te <= j.d1);
-            if (kMode == B2_SINK_RAW && (j.flags & 2)) {
+            if (want_crc && d1 - d0 >= 4) s = crc_tile_step(s, buf4, &cs, j, j.tile != 0 && te <= d1);
+            PROF_MARK(1);
+            if (kMode == B2_SINK_RAW && (flags & 2)) {
                 if (a.sink.img_out)
-                    sink_raw(buf32, buf8, ts, te, j.img_off, j.img_len, static_cast<uint8_t*>(a.sink.img_out) + (uint64_t)j.r * a.sink.img_stride);
+                    sink_raw(buf32, buf8, ts, te, j.img_off, j.img_len, static_cast<uint8_t*>(a.sink.img_out) + (uint64_t)(j.r & a.row_mask) * a.sink.img_stride);
                 if (a.sink.tgt_out)
-                    sink_raw(buf32, buf8, ts, te, j.tgt_off, j.tgt_len, static_cast<uint8_t*>(a.sink.tgt_out) + (uint64_t)j.r * a.sink.tgt_stride);
+                    sink_raw(buf32, buf8, ts, te, j.tgt_off, j.tgt_len, static_cast<uint8_t*>(a.sink.tgt_out) + (uint64_t)(j.r & a.row_mask) * a.sink.tgt_stride);
             }
-            if (kMode == B2_SINK_NORM_ONEHOT && (j.flags & 2)) {
-                PROF_MARK(1);
+            if (kMode == B2_SINK_NORM_ONEHOT && (flags & 2)) {
                 // ---- uint8 image -> (x-mean)/std float32
-                if (a.sink.img_out && j.img_len && j.img_off < te && j.img_off + j.img_len > ts && (uint32_t)tid < img_S) {
-                    float* dst = reinterpret_cast<float*>(static_cast<uint8_t*>(a.sink.img_out) + (uint64_t)j.r * a.sink.img_stride);
-                    const uint64_t po = j.img_off;
-                    const uint32_t pl = (uint32_t)j.img_len;
+                const uint64_t ipo = j.img_off, ipl64 = j.img_len;
+                if (a.sink.img_out && ipl64 && ipo < te && ipo + ipl64 > ts && (uint32_t)tid < img_S) {
+                    float* dst = reinterpret_cast<float*>(static_cast<uint8_t*>(a.sink.img_out) + (uint64_t)(j.r & a.row_mask) * a.sink.img_stride);
+                    const uint64_t po = ipo;
+                    const uint32_t pl = (uint32_t)ipl64;
                     const uint64_t lo = po > ts ? po : ts, hi = (po + pl < te) ? po + pl : te;
                     // float4 group g = image bytes [4g, 4g+4); owned by the tile that holds its first byte
-                    const uint32_t g_lo = (uint32_t)((lo - po + 3) >> 2), g_hi = (uint32_t)((hi - po + 3) >> 2), full = pl >> 2;
+                    const uint32_t g_lo = (uint32_t)((lo - po + 3) >> 2), g_hi = (uint32_t)((hi - po + 3) >> 2), full4 = pl >> 2;
                     const uint32_t base = (uint32_t)(po - ts);  // wraps when po < ts; base + 4g is back in [0, kTile)
                     uint32_t g = g_lo + tid;
                     float mu[4], sd[4], rc[4];
@@ -519,7 +560,7 @@ fused_parse_kernel(const ParseArgs a) {
                             const float d = __fsub_rn(v, mu[k]);
                             f[k] = exact_div ? __fdiv_rn(d, sd[k]) : norm_fast(d, sd[k], rc[k]);
                         }
-                        if (g < full) {
+                        if (g < full4) {
                             st_cs(reinterpret_cast<float4*>(dst) + g, make_float4(f[0], f[1], f[2], f[3]));
                         } else {   // the payload's last 1..3 bytes
                             if (4 * g + 0 < pl) dst[4 * g + 0] = f[0];
@@ -530,22 +571,23 @@ fused_parse_kernel(const ParseArgs a) {
                 }
                 PROF_MARK(2);
                 // ---- uint8 target -> one-hot float32
-                if (a.sink.tgt_out && j.tgt_len && j.tgt_off < te && j.tgt_off + j.tgt_len > ts) {
-                    float* dst = reinterpret_cast<float*>(static_cast<uint8_t*>(a.sink.tgt_out) + (uint64_t)j.r * a.sink.tgt_stride);
-                    const uint64_t po = j.tgt_off;
-                    const uint32_t pl = (uint32_t)j.tgt_len;
+                const uint64_t tpo = j.tgt_off, tpl64 = j.tgt_len;
+                if (a.sink.tgt_out && tpl64 && tpo < te && tpo + tpl64 > ts) {
+                    float* dst = reinterpret_cast<float*>(static_cast<uint8_t*>(a.sink.tgt_out) + (uint64_t)(j.r & a.row_mask) * a.sink.tgt_stride);
+                    const uint64_t po = tpo;
+                    const uint32_t pl = (uint32_t)tpl64;
                     const uint64_t lo = po > ts ? po : ts, hi = (po + pl < te) ? po + pl : te;
                     const uint32_t base = (uint32_t)(po - ts);
                     if (use_hot) {
-                        // Each warp owns a block of kHotLabels*K floats in shared memory — zero except ONE 1.0f per label,
-                        // so a label costs one 4-byte shared-memory write — and pushes it to HBM with a single TMA bulk
-                        // store; out-of-range labels write a dummy float past the block, so nothing is predicated.
+                        // Each warp owns blocks of kHotLabels*K floats in shared memory — zero except ONE 1.0f per label,
+                        // so a label costs one 4-byte shared-memory write — and pushes a block to HBM with a single TMA
+                        // bulk store; out-of-range labels write a dummy float past the block, so nothing is predicated.
                         // Work unit = 4 labels (4K floats: a whole number of 16-byte groups, 16-byte aligned in the
                         // output); a unit belongs to the tile holding its first label, later labels may sit in the halo.
                         const uint32_t j_lo = (uint32_t)((lo - po + 3) >> 2), j_hi = (uint32_t)((hi - po + 3) >> 2);
                         const uint32_t L_beg = 4 * j_lo, L_end = (4 * j_hi < pl) ? 4 * j_hi : pl;
-                        for (uint32_t L0 = L_beg + warp * kHotLabels; L0 < L_end; L0 += (kTileThreads / 32) * kHotLabels) {
-                            const uint32_t hb = hot_it & 1;
+                        for (uint32_t L0 = L_beg + warp * kHotLabels; L0 < L_end; L0 += kConsumerWarps * kHotLabels) {
+                            const uint32_t hb = kHotBlocks > 1 ? (hot_it & 1) : 0;
                             hot_it++;
                             float* hot = hot_w + hb * (kHotLabels * K + 4);
                             if (lane == 0) bulk_wait_read<kHotBlocks - 1>();   // the store that last used this block has read it
@@ -578,7 +620,7 @@ fused_parse_kernel(const ParseArgs a) {
                     } else {
                         // generic path (K > 32): float4 group g holds one-hot floats [4g, 4g+4), owned by the tile of label 4g/K
                         const uint32_t nfl = pl * (uint32_t)K;
-                        const uint32_t g_lo = (uint32_t)(((lo - po) * K + 3) >> 2), g_hi = (uint32_t)(((hi - po) * K + 3) >> 2), full = nfl >> 2;
+                        const uint32_t g_lo = (uint32_t)(((lo - po) * K + 3) >> 2), g_hi = (uint32_t)(((hi - po) * K + 3) >> 2), full4 = nfl >> 2;
                         for (uint32_t g = g_lo + tid; g < g_hi; g += kTileThreads) {
                             const uint32_t f0 = 4 * g;
                             uint32_t l = f0 / (uint32_t)K;
@@ -593,7 +635,7 @@ fused_parse_kernel(const ParseArgs a) {
                                     l++;
                                 }
                             }
-                            if (g < full) {
+                            if (g < full4) {
                                 st_cs(reinterpret_cast<float4*>(dst) + g, make_float4(f[0], f[1], f[2], f[3]));
                             } else {
                                 if (f0 + 0 < nfl) dst[f0 + 0] = f[0];
@@ -603,21 +645,15 @@ fused_parse_kernel(const ParseArgs a) {
                         }
                     }
                 }
+                PROF_MARK(3);
             }
         }
-        PROF_MARK(3);
-        __syncthreads();   // everyone is done with buffer b and job[b]
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);   // this warp is done with the buffer and its job
         PROF_MARK(4);
     }
     if (kMode == B2_SINK_NORM_ONEHOT && lane == 0) bulk_wait_read<0>();   // shared memory must outlive the bulk stores
     PROF_END();
-    if (tid == 0) {   // the last CTA out re-arms the chunk counter for the next launch
-        __threadfence();
-        if (atomicAdd(&a.sched[1], 1u) == gridDim.x - 1) {
-            a.sched[0] = 0;
-            a.sched[1] = 0;
-        }
-    }
 }
 
 }  // namespace b2
@@ -633,7 +669,7 @@ struct LaunchCfg {
 LaunchCfg g_cfg[64];
 
 size_t dyn_bytes(int mode, int K) {
-    size_t d = 2 * (size_t)kBufBytes;
+    size_t d = (size_t)kStages * kBufBytes;
     if (mode == B2_SINK_NORM_ONEHOT && K <= kHotMaxK) d += (size_t)(kTileThreads / 32) * kHotBlocks * (kHotLabels * K + 4) * sizeof(float);
     return d;
 }
@@ -649,15 +685,15 @@ int launch_fused(b2_ctx* ctx, const ParseArgs& pa, uint64_t max_tiles, cudaStrea
     }
     // persistent grid: as many CTAs as fit on the GPU at once (4 per SM), never more than there are chunks
     const uint64_t chunks = (max_tiles + pa.q - 1) / pa.q;
-    const uint64_t resident = (uint64_t)ctx->sm_count * (pa.sink.mode == B2_SINK_NORM_ONEHOT ? 3 : 6);
+    const uint64_t resident = (uint64_t)ctx->sm_count * (pa.sink.mode == B2_SINK_NORM_ONEHOT ? 3 : 5);
     const unsigned grid = (unsigned)(chunks < resident ? chunks : resident);
     const size_t dyn = dyn_bytes(pa.sink.mode, pa.sink.num_classes);
     switch (pa.sink.mode) {
-        case B2_SINK_NONE: fused_parse_kernel<B2_SINK_NONE><<<grid, kTileThreads, dyn, s>>>(pa); break;
-        case B2_SINK_RAW: fused_parse_kernel<B2_SINK_RAW><<<grid, kTileThreads, dyn, s>>>(pa); break;
+        case B2_SINK_NONE: fused_parse_kernel<B2_SINK_NONE><<<grid, kCtaThreads, dyn, s>>>(pa); break;
+        case B2_SINK_RAW: fused_parse_kernel<B2_SINK_RAW><<<grid, kCtaThreads, dyn, s>>>(pa); break;
         default:
-            if (pa.prof) fused_parse_kernel<B2_SINK_NORM_ONEHOT, true><<<grid, kTileThreads, dyn, s>>>(pa);
-            else fused_parse_kernel<B2_SINK_NORM_ONEHOT><<<grid, kTileThreads, dyn, s>>>(pa);
+            if (pa.prof) fused_parse_kernel<B2_SINK_NORM_ONEHOT, true><<<grid, kCtaThreads, dyn, s>>>(pa);
+            else fused_parse_kernel<B2_SINK_NORM_ONEHOT><<<grid, kCtaThreads, dyn, s>>>(pa);
             break;
     }
     ctx->launches++;
@@ -710,8 +746,8 @@ extern "C" int b2_tfrecord_parse(b2_ctx* ctx, const uint8_t* shard, uint64_t nby
     if (int e = ws_reserve(ctx, (size_t)n * 8 + 8, s)) return e;
     B2_CUDA(cudaMemsetAsync(ctx->ws, 0, (size_t)n * 8 + 8, s));
     uint32_t* acc = static_cast<uint32_t*>(ctx->ws);
-    ParseArgs pa{shard, nbytes, rec_off, rec_len, index, *sink, ctx->crc_dev, nullptr, nullptr, nullptr, nullptr,
-                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(), acc, acc + n, status, nullptr, nullptr, acc + 2 * (size_t)n, nullptr};
+    ParseArgs pa{shard, nbytes, rec_off, rec_len, index, *sink, ctx->crc_dev, nullptr, nullptr, nullptr,
+                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(), reinterpret_cast<unsigned long long*>(acc), status, nullptr, nullptr, acc + 2 * (size_t)n, nullptr, ~0u};
     return launch_fused(ctx, pa, tx * (uint64_t)n, s);
 }
 
@@ -724,10 +760,9 @@ extern "C" int b2_tfrecord_parse_table(b2_ctx* ctx, const uint8_t* shard, uint64
     if (int e = check_sink(sink, "b2_tfrecord_parse_table")) return e;
     DeviceGuard g(ctx->device);
     const TableView v = table_view(table, nbytes, max_records);
-    ParseArgs pa{shard, nbytes, v.rec_off, v.rec_len, v.index, *sink, ctx->crc_dev, v.tile2rec,
-                 getenv("B2_PARSE_NATURAL_ORDER") ? nullptr : v.order, v.tile_start, v.hdr,
-                 0, 0, tiles_per_cta(), v.crc_acc, v.done, status, nullptr, v.hdr + 4, reinterpret_cast<uint32_t*>(v.hdr + 5),
-                 getenv("B2_PARSE_PROFILE") ? ctx->prof_dev : nullptr};
+    ParseArgs pa{shard, nbytes, v.rec_off, v.rec_len, v.index, *sink, ctx->crc_dev, v.tile2rec, v.tile_start, v.hdr,
+                 0, 0, tiles_per_cta(), v.acc, status, nullptr, v.hdr + 4, reinterpret_cast<uint32_t*>(v.hdr + 5),
+                 getenv("B2_PARSE_PROFILE") ? ctx->prof_dev : nullptr, getenv("B2_DEBUG_ROW0") ? 0u : ~0u};
     return launch_fused(ctx, pa, v.cap_tiles, static_cast<cudaStream_t>(stream));
 }
 
@@ -749,8 +784,8 @@ extern "C" int b2_crc32c(b2_ctx* ctx, const uint8_t* data, const uint64_t* offse
     memset(&sink, 0, sizeof(sink));
     sink.mode = B2_SINK_NONE;
     sink.verify_crc = 1;
-    ParseArgs pa{data, ~0ull, offsets, lens, nullptr, sink, ctx->crc_dev, nullptr, nullptr, nullptr, nullptr,
-                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(), acc, acc + n, nullptr, crc_out, nullptr, acc + 2 * (size_t)n, nullptr};
+    ParseArgs pa{data, ~0ull, offsets, lens, nullptr, sink, ctx->crc_dev, nullptr, nullptr, nullptr,
+                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(), reinterpret_cast<unsigned long long*>(acc), nullptr, crc_out, nullptr, acc + 2 * (size_t)n, nullptr, ~0u};
     return launch_fused(ctx, pa, tx * (uint64_t)n, s);
 }
 

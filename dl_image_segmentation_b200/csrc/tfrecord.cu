@@ -64,8 +64,7 @@ struct ScanOut {
     uint64_t* lens;
     int64_t* hdr;          // [0] n, [1] status, [2] total tiles, [3] max len, [4] n_bad (zeroed here)
     uint32_t* tile_start;  // cap + 1 entries, or NULL (legacy b2_tfrecord_scan)
-    uint32_t* crc_acc;     // cap entries zeroed here, or NULL
-    uint32_t* done;
+    unsigned long long* acc;   // cap entries zeroed here, or NULL
     int hdr_words;         // how many int64 of hdr exist (2 legacy, 8 table)
 };
 
@@ -80,11 +79,8 @@ scan_kernel(const uint8_t* __restrict__ shard, uint64_t nbytes, uint64_t cap, Sc
     __shared__ unsigned long long s_first_bad, s_maxlen;
     __shared__ uint32_t s_warp[kScanThreads / 32];
     const int tid = threadIdx.x;
-    if (o.crc_acc)
-        for (uint64_t i = tid; i < cap; i += kScanThreads) {
-            o.crc_acc[i] = 0;
-            o.done[i] = 0;
-        }
+    if (o.acc)
+        for (uint64_t i = tid; i < cap; i += kScanThreads) o.acc[i] = 0ull;
     if (tid == 0) {
         s_pos = 0;
         s_n = 0;
@@ -207,7 +203,6 @@ scan_kernel(const uint8_t* __restrict__ shard, uint64_t nbytes, uint64_t cap, Sc
         o.hdr[3] = (int64_t)s_maxlen;
         o.hdr[4] = 0;
         o.hdr[5] = 0;   // chunk scheduler words of the fused pass
-        o.hdr[6] = 0;   // heavy / light tile counters of the index pass
     }
 }
 
@@ -287,8 +282,7 @@ __device__ inline bool key_is(Win& w, uint64_t s, uint64_t e, const char* lit, i
 __global__ void __launch_bounds__(kIdxWarps * 32)
 index_kernel(const uint8_t* __restrict__ shard, uint64_t nbytes, const uint64_t* __restrict__ rec_off,
              const uint64_t* __restrict__ rec_len, int n, b2_example_index* __restrict__ out,
-             const int64_t* __restrict__ n_dev, const uint32_t* __restrict__ tile_start, uint32_t* __restrict__ tile2rec,
-             uint32_t* __restrict__ order, uint32_t* __restrict__ order_cnt) {
+             const int64_t* __restrict__ n_dev, const uint32_t* __restrict__ tile_start, uint32_t* __restrict__ tile2rec) {
     __shared__ __align__(16) uint8_t s_win[kIdxWarps][kIdxWin];
     const int r = blockIdx.x * kIdxWarps + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -388,33 +382,6 @@ index_kernel(const uint8_t* __restrict__ shard, uint64_t nbytes, const uint64_t*
             if (have[k] != 1) st = 2;
     ix.status = st;
     if (lane == 0) out[r] = ix;
-    if (order) {
-        // Processing order for the fused pass: tiles holding label payload come first.  A label tile expands K*4-fold
-        // (one-hot float32) while an image tile expands 4-fold, so handing the expensive tiles out first leaves
-        // only cheap ones for the end of the kernel, where CTAs run dry one after the other.
-        const uint32_t t0 = tile_start[r], nt = tile_start[r + 1] - t0, total = (uint32_t)n_dev[2];
-        uint32_t h0 = nt, h1 = nt;   // heavy tiles = [h0, h1)
-        if (st == 0 && ix.tgt_len) {
-            const uint64_t A = d0 & ~15ull;
-            h0 = (uint32_t)((ix.tgt_off - A) / kTile);
-            h1 = (uint32_t)((ix.tgt_off + ix.tgt_len - 1 - A) / kTile) + 1;
-            if (h1 > nt) h1 = nt;
-            if (h0 > h1) h0 = h1;
-        }
-        const uint32_t nh = h1 - h0, nl = nt - nh;
-        uint32_t hpos = 0, lpos = 0;
-        if (lane == 0) {
-            hpos = atomicAdd(&order_cnt[0], nh);
-            lpos = atomicAdd(&order_cnt[1], nl);
-        }
-        hpos = __shfl_sync(0xffffffffu, hpos, 0);
-        lpos = __shfl_sync(0xffffffffu, lpos, 0);
-        const uint32_t lstart = total - lpos - nl;
-        for (uint32_t t = lane; t < nt; t += 32) {
-            if (t >= h0 && t < h1) order[hpos + (t - h0)] = t0 + t;
-            else order[lstart + (t < h0 ? t : t - nh)] = t0 + t;
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------- build
@@ -592,7 +559,7 @@ extern "C" int b2_tfrecord_scan(b2_ctx* ctx, const uint8_t* shard, uint64_t nbyt
     B2_REQUIRE(ctx && (shard || nbytes == 0) && rec_off && rec_len && result, "b2_tfrecord_scan: NULL argument");
     B2_REQUIRE((reinterpret_cast<uintptr_t>(shard) & 15) == 0, "b2_tfrecord_scan: shard must be 16-byte aligned");
     DeviceGuard g(ctx->device);
-    ScanOut o{rec_off, rec_len, result, nullptr, nullptr, nullptr, 2};
+    ScanOut o{rec_off, rec_len, result, nullptr, nullptr, 2};
     scan_kernel<<<1, kScanThreads, 0, static_cast<cudaStream_t>(stream)>>>(shard, nbytes, max_records, o, ctx->crc_dev);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
@@ -607,7 +574,7 @@ extern "C" int b2_tfrecord_index(b2_ctx* ctx, const uint8_t* shard, const uint64
     if (n == 0) return 0;
     DeviceGuard g(ctx->device);
     index_kernel<<<(n + kIdxWarps - 1) / kIdxWarps, kIdxWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        shard, ~0ull, rec_off, rec_len, n, out, nullptr, nullptr, nullptr, nullptr, nullptr);
+        shard, ~0ull, rec_off, rec_len, n, out, nullptr, nullptr, nullptr);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;
@@ -642,11 +609,10 @@ extern "C" int b2_tfrecord_open(b2_ctx* ctx, const uint8_t* shard, uint64_t nbyt
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const TableView v = table_view(table, nbytes, max_records);
-    ScanOut o{v.rec_off, v.rec_len, v.hdr, v.tile_start, v.crc_acc, v.done, 8};
+    ScanOut o{v.rec_off, v.rec_len, v.hdr, v.tile_start, v.acc, 8};
     scan_kernel<<<1, kScanThreads, 0, s>>>(shard, nbytes, max_records, o, ctx->crc_dev);
     index_kernel<<<(unsigned)((max_records + kIdxWarps - 1) / kIdxWarps), kIdxWarps * 32, 0, s>>>(
-        shard, nbytes, v.rec_off, v.rec_len, (int)max_records, v.index, v.hdr, v.tile_start, v.tile2rec, v.order,
-        reinterpret_cast<uint32_t*>(v.hdr + 6));
+        shard, nbytes, v.rec_off, v.rec_len, (int)max_records, v.index, v.hdr, v.tile_start, v.tile2rec);
     ctx->launches += 2;
     B2_CUDA(cudaGetLastError());
     return 0;

@@ -117,21 +117,18 @@ __host__ __device__ __forceinline__ uint32_t record_tiles(uint64_t d0, uint64_t 
 // ---------------------------------------------------------------- shard table (b2_tfrecord_open / _parse_table)
 // One caller-owned device buffer describing an opened shard; every section 16-byte aligned:
 //   hdr int64[8]        [0] records  [1] scan status  [2] tiles  [3] longest record  [4] records with status != 0
-//                       [5] chunk scheduler words of the fused pass  [6] heavy / light tile counters of the index pass
+//                       [5] chunk scheduler words of the fused pass
 //   rec_off uint64[cap] | rec_len uint64[cap] | index b2_example_index[cap] | tile_start uint32[cap+1]
-//   crc_acc uint32[cap] | done uint32[cap]   (scratch of the fused pass; zero between launches)
+//   acc uint64[cap]                          (scratch of the fused pass: CRC partial | tiles done; zero between launches)
 //   tile2rec uint32[cap_tiles]               (owner record of every 8 KiB tile)
-//   order uint32[cap_tiles]                  (processing order of the tiles: label-payload tiles first, see index_kernel)
 struct TableView {
     int64_t* hdr;
     uint64_t* rec_off;
     uint64_t* rec_len;
     b2_example_index* index;
     uint32_t* tile_start;
-    uint32_t* crc_acc;
-    uint32_t* done;
+    unsigned long long* acc;
     uint32_t* tile2rec;
-    uint32_t* order;
     uint64_t cap, cap_tiles, bytes;
 };
 __host__ __device__ inline TableView table_view(uint8_t* t, uint64_t nbytes, uint64_t cap) {
@@ -145,10 +142,8 @@ __host__ __device__ inline TableView table_view(uint8_t* t, uint64_t nbytes, uin
     v.rec_len = reinterpret_cast<uint64_t*>(t + o);        o += up(8 * cap);
     v.index = reinterpret_cast<b2_example_index*>(t + o);  o += up(sizeof(b2_example_index) * cap);
     v.tile_start = reinterpret_cast<uint32_t*>(t + o);     o += up(4 * (cap + 1));
-    v.crc_acc = reinterpret_cast<uint32_t*>(t + o);        o += up(4 * cap);
-    v.done = reinterpret_cast<uint32_t*>(t + o);           o += up(4 * cap);
+    v.acc = reinterpret_cast<unsigned long long*>(t + o);  o += up(8 * cap);
     v.tile2rec = reinterpret_cast<uint32_t*>(t + o);       o += up(4 * v.cap_tiles);
-    v.order = reinterpret_cast<uint32_t*>(t + o);          o += up(4 * v.cap_tiles);
     v.bytes = o;
     return v;
 }

@@ -586,6 +586,36 @@ class ShardPipeline:
             self.release[slot] = ev
 
 
+class CapturedPass:
+    """A whole pass over a fixed list of shards (device tensors or pinned host tensors) recorded as ONE CUDA graph:
+    uploads, open, fused parse and the caller's per-shard consumer.  replay() enqueues everything with a single
+    launch, so the host cost per shard disappears (the tables and kernels never needed the host in the first place)."""
+
+    def __init__(self, pipe, shards, consume=None):
+        self.pipe, self.shards = pipe, list(shards)
+        for res in pipe.run(self.shards):               # warm-up: allocates every slot's buffers outside the capture
+            if consume is not None:
+                consume(*res)
+        torch.cuda.synchronize(pipe.ctx.device)
+        pipe.release = [None] * pipe.depth              # events recorded outside the capture must not leak into it
+        self.graph = torch.cuda.CUDAGraph()
+        self.results = []
+        side = torch.cuda.Stream(pipe.ctx.device)
+        side.wait_stream(torch.cuda.current_stream(pipe.ctx.device))
+        l0 = pipe.ctx.launches
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(self.graph, stream=side):
+                for res in pipe.run(self.shards):
+                    self.results.append(consume(*res) if consume is not None else res)
+        self.launches_per_replay = pipe.ctx.launches - l0
+        torch.cuda.current_stream(pipe.ctx.device).wait_stream(side)
+        pipe.release = [None] * pipe.depth
+
+    def replay(self):
+        self.graph.replay()
+        return self.results
+
+
 def iter_parsed_shards(shards, mode, verify_crc=True, mean=None, std=None, num_classes=None, out=None, device=None,
                        img_elems=None, tgt_elems=None, max_records=None, depth=3):
     """Parse a sequence of shards (CUDA-resident or pinned-host uint8 tensors).
