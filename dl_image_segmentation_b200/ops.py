@@ -507,77 +507,99 @@ def parse_table(st: ShardTable, mode, img_elems=0, tgt_elems=0, verify_crc=True,
 
 
 class ShardPipeline:
-    """Streams shards through open -> fused parse on `depth` CUDA streams with NO per-shard host synchronisation.
+    """Streams shards through upload -> open -> fused parse with NO per-shard host synchronisation.
 
-    Each slot owns its device staging buffer (for host shards), shard table, status array and output buffers, so
-    the upload + scan + index of shard k+1 overlap the fused pass of shard k.  Iterating yields
-    (img_buf, tgt_buf, status_dev, table) with the producing work already ordered before the caller's current
-    stream; the buffers of a slot are recycled `depth` shards later, after whatever the caller enqueued on them.
+    Two rings.  OPEN slots (`open_ahead` of them) own a device staging buffer (for host shards) and a shard table:
+    upload + frame scan + feature index of later shards run ahead on high-priority streams — the fused pass is a
+    persistent kernel that fills every SM, so the small open kernels can only run in the gaps between two fused
+    passes and must be queued well before they are needed.  PARSE slots (`depth` of them) own the status array
+    and the output buffers.  Iterating yields (img_buf, tgt_buf, status_dev, table) with the producing work already
+    ordered before the caller's current stream; a parse slot is recycled `depth` shards later, after whatever
+    the caller enqueued on its buffers.
     """
 
     def __init__(self, mode, img_elems, tgt_elems, max_records, verify_crc=True, mean=None, std=None, num_classes=None,
-                 device=None, depth=3, max_shard_bytes=0):
+                 device=None, depth=3, max_shard_bytes=0, open_ahead=8):
         self.ctx = get_ctx(device)
         dev = self.ctx.device
         self.mode, self.verify_crc, self.num_classes = mode, verify_crc, num_classes
         self.img_elems, self.tgt_elems, self.cap, self.depth = int(img_elems), int(tgt_elems), int(max_records), int(depth)
+        self.open_ahead = max(int(open_ahead), self.depth)
         self.mean = None if mean is None else to_device(np.asarray(mean, dtype=np.float32) if not isinstance(mean, torch.Tensor) else mean, dev)
         self.std = None if std is None else to_device(np.asarray(std, dtype=np.float32) if not isinstance(std, torch.Tensor) else std, dev)
-        # upload + scan + index run on high-priority streams so that their few CTAs slip in between the CTAs of the
-        # fused pass of an earlier shard (which saturates every SM) instead of queueing behind it
-        self.open_streams = [torch.cuda.Stream(dev, priority=-1) for _ in range(self.depth)]
+        self.open_streams = [torch.cuda.Stream(dev, priority=-1) for _ in range(min(self.open_ahead, 4))]
         self.streams = [torch.cuda.Stream(dev) for _ in range(self.depth)]
-        self.opened = [torch.cuda.Event() for _ in range(self.depth)]
+        self.oslots = [dict(stage=None, table=None, opened=torch.cuda.Event(), parsed=None) for _ in range(self.open_ahead)]
         self.ready = [torch.cuda.Event() for _ in range(self.depth)]
         self.release = [None] * self.depth
-        self.slots = [dict(stage=None, table=None, status=torch.zeros((self.cap,), dtype=torch.int32, device=dev), out=None)
-                      for _ in range(self.depth)]
+        self.slots = [dict(status=torch.zeros((self.cap,), dtype=torch.int32, device=dev), out=None) for _ in range(self.depth)]
         self.max_shard_bytes = int(max_shard_bytes)
 
-    def _submit(self, k, shard):
-        slot = k % self.depth
-        sl, ostream, stream = self.slots[slot], self.open_streams[slot], self.streams[slot]
+    def reset_events(self):
+        """Forget events of earlier passes (needed before the pipeline is recorded into a CUDA graph)."""
+        self.release = [None] * self.depth
+        for o in self.oslots:
+            o["parsed"] = None
+
+    def _submit_open(self, k, shard):
+        o = self.oslots[k % self.open_ahead]
+        ostream = self.open_streams[k % len(self.open_streams)]
         main = torch.cuda.current_stream(self.ctx.device)
-        if self.release[slot] is not None:
-            ostream.wait_event(self.release[slot])
-        else:
-            ostream.wait_stream(main)
+        if o["parsed"] is not None:
+            ostream.wait_event(o["parsed"])         # the fused pass that last read this table / staging buffer is done
+        ostream.wait_stream(main)
         nbytes = int(shard.numel())
         with torch.cuda.stream(ostream):
             if not shard.is_cuda:
-                if sl["stage"] is None or sl["stage"].numel() < nbytes:
-                    sl["stage"] = torch.empty((max(nbytes, self.max_shard_bytes) + 16,), dtype=torch.uint8, device=self.ctx.device)
-                sl["stage"][:nbytes].copy_(shard, non_blocking=True)
-                shard = sl["stage"]
+                if o["stage"] is None or o["stage"].numel() < nbytes:
+                    o["stage"] = torch.empty((max(nbytes, self.max_shard_bytes) + 16,), dtype=torch.uint8, device=self.ctx.device)
+                o["stage"][:nbytes].copy_(shard, non_blocking=True)
+                shard = o["stage"]
             need = table_layout(nbytes, self.cap)[7]
-            if sl["table"] is None or sl["table"].numel() < need:
-                sl["table"] = torch.empty((need + need // 8,), dtype=torch.uint8, device=self.ctx.device)
-            st = open_shard_async(shard, self.ctx.device, self.cap, nbytes=nbytes, table=sl["table"])
-            self.opened[slot].record(ostream)
-        stream.wait_event(self.opened[slot])
+            if o["table"] is None or o["table"].numel() < need:
+                o["table"] = torch.empty((need + need // 8,), dtype=torch.uint8, device=self.ctx.device)
+            st = open_shard_async(shard, self.ctx.device, self.cap, nbytes=nbytes, table=o["table"])
+            o["opened"].record(ostream)
+        return o, st
+
+    def _submit_parse(self, k, opened):
+        o, st = opened
+        slot = k % self.depth
+        sl, stream = self.slots[slot], self.streams[slot]
+        if self.release[slot] is not None:
+            stream.wait_event(self.release[slot])
+        stream.wait_event(o["opened"])
         with torch.cuda.stream(stream):
             img, tgt, status = parse_table(st, self.mode, self.img_elems, self.tgt_elems, self.verify_crc, self.mean,
                                            self.std, self.num_classes, out=sl["out"], status=sl["status"])
             if sl["out"] is None and img is not None:
                 sl["out"] = (img, tgt)
             self.ready[slot].record(stream)
+            o["parsed"] = torch.cuda.Event()
+            o["parsed"].record(stream)
         return slot, (img, tgt, status, st)
 
     def run(self, shards):
         main = torch.cuda.current_stream(self.ctx.device)
-        pending = []
-        k = 0
-        for shard in shards:
-            pending.append(self._submit(k, shard))
-            k += 1
-            if len(pending) == self.depth:
-                slot, res = pending.pop(0)
-                main.wait_event(self.ready[slot])
-                yield res
-                ev = torch.cuda.Event()
-                ev.record(main)
-                self.release[slot] = ev
-        while pending:
+        it = iter(shards)
+        opened, pending = [], []
+        k_open = k_parse = 0
+        exhausted = False
+        while True:
+            while not exhausted and len(opened) + len(pending) < self.open_ahead:
+                try:
+                    shard = next(it)
+                except StopIteration:
+                    exhausted = True
+                    break
+                opened.append(self._submit_open(k_open, shard))
+                k_open += 1
+            if opened and len(pending) < self.depth:
+                pending.append(self._submit_parse(k_parse, opened.pop(0)))
+                k_parse += 1
+                continue
+            if not pending:
+                break
             slot, res = pending.pop(0)
             main.wait_event(self.ready[slot])
             yield res
@@ -597,7 +619,7 @@ class CapturedPass:
             if consume is not None:
                 consume(*res)
         torch.cuda.synchronize(pipe.ctx.device)
-        pipe.release = [None] * pipe.depth              # events recorded outside the capture must not leak into it
+        pipe.reset_events()                             # events recorded outside the capture must not leak into it
         self.graph = torch.cuda.CUDAGraph()
         self.results = []
         side = torch.cuda.Stream(pipe.ctx.device)
@@ -609,7 +631,7 @@ class CapturedPass:
                     self.results.append(consume(*res) if consume is not None else res)
         self.launches_per_replay = pipe.ctx.launches - l0
         torch.cuda.current_stream(pipe.ctx.device).wait_stream(side)
-        pipe.release = [None] * pipe.depth
+        pipe.reset_events()
 
     def replay(self):
         self.graph.replay()
