@@ -30,21 +30,24 @@ namespace b2 {
 // Frames are a linked list (each length tells where the next header is), so the walk is inherently serial and,
 // done naively, pays one cold HBM round trip (~1 us) per record.  Records of one shard have nearly the same
 // length (fixed-size chips + a short identifier), so the CTA works in rounds of kScanR records:
-//   1. all threads prefetch, with coalesced 128-bit loads, a +-kScanHW byte window around the PREDICTED position
-//      of each of the next kScanR headers (prediction = position of the current header + k * last stride),
-//   2. thread 0 walks the chain reading lengths from shared memory (falling back to a global read, and ending
-//      the round, when a header lies outside its window) — exactly the positions the sequential reader visits,
-//   3. one thread per visited header verifies its masked length CRC and publishes offset / length.
+//   1. all threads prefetch, with coalesced 128-bit loads, a window around the PREDICTED position of each of the
+//      next kScanR headers (prediction = position of the current header + k * last stride),
+//   2. thread 0 hops through shared memory: read 8 length bytes, add, next window — nothing else; the hop chain
+//      ends at the first header that lies outside its window (the next round re-anchors there; the first window
+//      of a round always contains its header, so every round advances),
+//   3. one thread per visited header does what the hop skipped: bounds, capacity, masked length CRC (table in
+//      shared memory, stored CRC from the window), and publishes offset / length; the first failure cuts the
+//      walk exactly where RecordReader would stop.
 // The result (record table, count, status) is identical to RecordReader's sequential walk for any input.
 constexpr int kScanThreads = 512;
-constexpr int kScanR = 64;
-constexpr int kScanHW = 256;
+constexpr int kScanR = 128;
+constexpr int kScanHW = 112;
 constexpr int kScanWB = 2 * kScanHW + 32;   // bytes per window (multiple of 16)
 
-__device__ __forceinline__ uint32_t crc_hdr8(uint64_t l, const CrcTables* tab) {
+__device__ __forceinline__ uint32_t crc_hdr8(uint64_t l, const uint32_t* t) {   // t = byte table (reflected CRC-32C)
     uint32_t s = 0xFFFFFFFFu;
 #pragma unroll
-    for (int i = 0; i < 8; i++) s = (s >> 8) ^ __ldg(&tab->t4[3][(s ^ (uint32_t)(l >> (8 * i))) & 0xff]);
+    for (int i = 0; i < 8; i++) s = (s >> 8) ^ t[(s ^ (uint32_t)(l >> (8 * i))) & 0xff];
     return mask_crc(~s);
 }
 __device__ __forceinline__ uint64_t rd_u64(const uint8_t* p) {
@@ -59,6 +62,13 @@ __device__ __forceinline__ uint32_t rd_u32(const uint8_t* p) {
     for (int i = 0; i < 4; i++) v |= (uint32_t)p[i] << (8 * i);
     return v;
 }
+// 8 bytes at an arbitrary byte offset of a 4-byte aligned shared-memory buffer: three word loads + two funnel shifts
+__device__ __forceinline__ uint64_t smem_u64_unaligned(const uint8_t* base, uint32_t off) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(base) + (off >> 2);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], sh = (off & 3) * 8;
+    return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+}
+
 struct ScanOut {
     uint64_t* offs;
     uint64_t* lens;
@@ -71,22 +81,24 @@ struct ScanOut {
 __global__ void __launch_bounds__(kScanThreads)
 scan_kernel(const uint8_t* __restrict__ shard, uint64_t nbytes, uint64_t cap, ScanOut o,
             const CrcTables* __restrict__ tab) {
-    __shared__ __align__(16) uint8_t win[kScanR][kScanWB];
+    __shared__ __align__(16) uint8_t win[kScanR][kScanWB + 16];
     __shared__ uint64_t w_lo[kScanR];            // absolute start of each window
-    __shared__ uint64_t r_pos[kScanR], r_len[kScanR];
+    __shared__ uint64_t r_pos[kScanR];           // header positions visited this round
+    __shared__ uint32_t s_crc[256];
     __shared__ uint64_t s_pos, s_est, s_n;
-    __shared__ int s_m, s_state;                 // records visited this round; 0 continue, 1 clean end, 2 error, 3 cap
+    __shared__ int s_m, s_state;                 // headers visited this round; 0 continue, 1 clean end, 2 error, 3 capacity
     __shared__ unsigned long long s_first_bad, s_maxlen;
+    __shared__ int s_bad_kind;
     __shared__ uint32_t s_warp[kScanThreads / 32];
     const int tid = threadIdx.x;
     if (o.acc)
         for (uint64_t i = tid; i < cap; i += kScanThreads) o.acc[i] = 0ull;
+    for (int i = tid; i < 256; i += kScanThreads) s_crc[i] = __ldg(&tab->t4[3][i]);
     if (tid == 0) {
         s_pos = 0;
         s_n = 0;
         s_est = 0;
-        s_state = nbytes == 0 ? 1 : 0;
-        s_first_bad = ~0ull;
+        s_state = nbytes == 0 ? 1 : (nbytes < 12 ? 2 : 0);   // a shard shorter than one header is truncated
         s_maxlen = 0;
     }
     __syncthreads();
@@ -105,10 +117,10 @@ scan_kernel(const uint8_t* __restrict__ shard, uint64_t nbytes, uint64_t cap, Sc
             __syncthreads();
             est = s_est;
         }
-        // 1. prefetch windows
+        // 1. prefetch windows (vector kScanWB/16 of a window is slack for the unaligned 8-byte read)
         for (int i = tid; i < kScanR * (kScanWB / 16); i += kScanThreads) {
             const int k = i / (kScanWB / 16), j = i % (kScanWB / 16);
-            const uint64_t c = base + (uint64_t)k * est;   // may overflow for garbage est: harmless, only a prefetch hint
+            const uint64_t c = base + (uint64_t)k * est;   // may overflow for a garbage est: harmless, only a prefetch hint
             const uint64_t lo = c > (uint64_t)kScanHW ? (c - kScanHW) & ~15ull : 0;
             if (j == 0) w_lo[k] = lo;
             const uint64_t a = lo + 16ull * j;
@@ -117,48 +129,60 @@ scan_kernel(const uint8_t* __restrict__ shard, uint64_t nbytes, uint64_t cap, Sc
             reinterpret_cast<uint4*>(&win[k][0])[j] = v;
         }
         __syncthreads();
-        // 2. serial walk over shared memory
+        // 2. serial hop chain over shared memory: nothing but "read length, add"
         if (tid == 0) {
-            uint64_t pos = base, n = n0, last_stride = est;
-            int m = 0, state = 0;
+            uint64_t pos = base;
+            int m = 0;
             for (int k = 0; k < kScanR; k++) {
-                if (pos >= nbytes) { state = 1; break; }
-                if (nbytes - pos < 12) { state = 2; break; }
-                const bool in_win = pos >= w_lo[k] && pos + 12 <= w_lo[k] + kScanWB;
-                const uint64_t l = in_win ? rd_u64(&win[k][pos - w_lo[k]]) : rd_u64(shard + pos);
-                const bool bounds_bad = l > nbytes - pos - 12 || nbytes - pos - 12 - l < 4;
-                if (n >= cap) {                  // RecordReader checks this header's CRC and bounds before the count
-                    state = (crc_hdr8(l, tab) != rd_u32(shard + pos + 8) || bounds_bad) ? 2 : 3;
-                    break;
-                }
-                if (bounds_bad) { state = 2; break; }   // status 1 at this record whatever its length CRC says
-                r_pos[m] = pos;
-                r_len[m] = l;
-                m++;
-                n++;
-                last_stride = 16 + l;
+                const uint64_t off = pos - w_lo[k];                     // wraps to huge when pos < w_lo[k]
+                if (off > (uint64_t)(kScanWB - 12) || pos >= nbytes || nbytes - pos < 12) break;
+                const uint64_t l = smem_u64_unaligned(&win[k][0], (uint32_t)off);
+                r_pos[m++] = pos;
+                if (l > nbytes) break;                                  // certainly out of bounds: step 3 reports it
                 pos += 16 + l;
-                if (!in_win) break;              // prediction lost: re-anchor the windows
             }
             s_m = m;
-            s_pos = pos;
-            s_n = n;
-            s_est = last_stride;
-            s_state = state;
+            s_first_bad = ~0ull;
+            s_bad_kind = 0;
         }
         __syncthreads();
-        // 3. parallel header CRC check + publish (entries past a corrupt header are cut off by the final count)
+        // 3. everything the hop skipped, one thread per visited header, in RecordReader's order of checks
         const int m = s_m;
         for (int k = tid; k < m; k += kScanThreads) {
-            const uint64_t pos = r_pos[k], l = r_len[k];
-            if (crc_hdr8(l, tab) != rd_u32(shard + pos + 8)) atomicMin(&s_first_bad, (unsigned long long)(n0 + k));
-            o.offs[n0 + k] = pos + 12;
-            o.lens[n0 + k] = l;
+            const uint64_t pos = r_pos[k];
+            const uint8_t* hp = &win[k][pos - w_lo[k]];
+            const uint64_t l = rd_u64(hp);
+            const bool crc_bad = crc_hdr8(l, s_crc) != rd_u32(hp + 8);
+            const bool bounds_bad = l > nbytes - pos - 12 || nbytes - pos - 12 - l < 4;
+            const bool cap_bad = n0 + k >= cap;
+            if (crc_bad || bounds_bad || cap_bad) {
+                atomicMin(&s_first_bad, (unsigned long long)k);
+            } else {
+                o.offs[n0 + k] = pos + 12;
+                o.lens[n0 + k] = l;
+            }
         }
         __syncthreads();
-        if (tid == 0 && s_first_bad != ~0ull) {
-            s_n = s_first_bad;
-            s_state = 2;
+        if (tid == 0) {
+            const unsigned long long fb = s_first_bad;
+            if (fb != ~0ull) {                   // the walk stops at header fb of this round
+                const uint64_t pos = r_pos[fb];
+                const uint8_t* hp = &win[fb][pos - w_lo[fb]];
+                const uint64_t l = rd_u64(hp);
+                const bool crc_bad = crc_hdr8(l, s_crc) != rd_u32(hp + 8);
+                const bool bounds_bad = l > nbytes - pos - 12 || nbytes - pos - 12 - l < 4;
+                s_n = n0 + fb;
+                s_state = (crc_bad || bounds_bad) ? 2 : 3;
+            } else {
+                s_n = n0 + m;
+                const uint64_t last = r_pos[m - 1];
+                const uint64_t l = rd_u64(&win[m - 1][last - w_lo[m - 1]]);
+                const uint64_t pos = last + 16 + l;      // in bounds: header m-1 passed the checks
+                s_pos = pos;
+                s_est = 16 + l;
+                if (pos >= nbytes) s_state = 1;          // == nbytes: clean end
+                else if (nbytes - pos < 12) s_state = 2; // truncated header
+            }
         }
         __syncthreads();
     }
@@ -186,7 +210,6 @@ scan_kernel(const uint8_t* __restrict__ shard, uint64_t nbytes, uint64_t cap, Sc
         if ((tid & 31) >= d) inc += t;
     }
     if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
-    if (tid == 0) s_maxlen = 0;
     __syncthreads();
     uint32_t wbase = 0;
     for (int w = 0; w < (tid >> 5); w++) wbase += s_warp[w];
@@ -207,21 +230,26 @@ scan_kernel(const uint8_t* __restrict__ shard, uint64_t nbytes, uint64_t cap, Sc
 }
 
 // ---------------------------------------------------------------------------------------------- index
-// One WARP per record walks the protobuf structure.  All 32 lanes execute the same walk over a
-// 512-byte window of the record held in shared memory; when the walk leaves the window the warp reloads it with
-// one coalesced 128-bit load per lane, so a record costs a handful of HBM round trips (its header bytes sit in
-// three clusters: before the image payload, between the payloads, after the target payload) instead of one per
-// byte.  Everything is bounds-checked against the record; a malformed message sets status 1 instead of faulting.
-constexpr int kIdxWarps = 8;
-constexpr int kIdxWin = 512;
+// One WARP per record walks the protobuf structure in two phases:
+//   A. all lanes together hop over the map entries of Example.features (tag + length, then skip), reading through
+//      a 512-byte window of the shard in shared memory that the warp refills with one coalesced 128-bit load per
+//      lane — a record costs a handful of HBM round trips (entry headers sit in three clusters: before the image
+//      payload, between the payloads, after the target payload), not one per byte;
+//   B. lane e then parses entry e on its own (key, Feature oneof, list, value) through a private 128-byte window,
+//      so the eight entries of a record are decoded side by side instead of one after the other;
+//   C. lane 0 applies the per-entry results in file order (last duplicate wins, like a protobuf map).
+// Everything is bounds-checked against the record; a malformed message sets status 1 instead of faulting.
+constexpr int kIdxWarps = 4;
+constexpr int kIdxWin = 512;    // phase A window, per warp
+constexpr int kLaneWin = 128;   // phase B window, per lane
 struct Win {
     const uint8_t* g;
     uint64_t nbytes;   // bytes that may be read from g
-    uint8_t* s;        // this warp's kIdxWin bytes of shared memory
-    uint64_t lo;       // window = [lo, lo + kIdxWin); ~0 = empty
+    uint8_t* s;        // shared-memory backing
+    uint64_t lo;       // window = [lo, lo + size)
 };
-__device__ __forceinline__ uint32_t win_byte(Win& w, uint64_t p) {
-    if (p - w.lo >= (uint64_t)kIdxWin) {           // warp-uniform
+__device__ __forceinline__ uint32_t win_byte(Win& w, uint64_t p) {   // warp-uniform p: cooperative refill
+    if (p - w.lo >= (uint64_t)kIdxWin) {
         __syncwarp();
         w.lo = p & ~15ull;
         const uint64_t a = w.lo + 16ull * (threadIdx.x & 31);
@@ -232,15 +260,31 @@ __device__ __forceinline__ uint32_t win_byte(Win& w, uint64_t p) {
     }
     return w.s[p - w.lo];
 }
+__device__ __forceinline__ uint32_t lane_byte(Win& w, uint64_t p) {  // per-lane p: private refill
+    if (p - w.lo >= (uint64_t)kLaneWin) {
+        w.lo = p & ~15ull;
+#pragma unroll
+        for (int j = 0; j < kLaneWin / 16; j++) {
+            const uint64_t a = w.lo + 16ull * j;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (a < w.nbytes) v = ld16_bounded(w.g, a, w.nbytes);
+            reinterpret_cast<uint4*>(w.s)[j] = v;
+        }
+    }
+    return w.s[p - w.lo];
+}
 struct Cursor {
     uint64_t p, end;
     bool ok;
 };
+template <bool kLane>
+__device__ __forceinline__ uint32_t rd_byte(Win& w, uint64_t p) { return kLane ? lane_byte(w, p) : win_byte(w, p); }
+template <bool kLane>
 __device__ inline uint64_t rd_varint(Win& w, Cursor& c) {
     uint64_t v = 0;
     for (int s = 0; s < 70; s += 7) {
         if (c.p >= c.end) { c.ok = false; return 0; }
-        const uint32_t x = win_byte(w, c.p++);
+        const uint32_t x = rd_byte<kLane>(w, c.p++);
         v |= (uint64_t)(x & 0x7F) << s;
         if (!(x & 0x80)) return v;
     }
@@ -248,20 +292,21 @@ __device__ inline uint64_t rd_varint(Win& w, Cursor& c) {
     return 0;
 }
 // reads a tag and, for LEN fields, the sub-range; skips other wire types. returns field number (0 on end/error)
+template <bool kLane>
 __device__ inline uint32_t next_field(Win& w, Cursor& c, int& wt, uint64_t& v0, uint64_t& v1) {
     if (!c.ok || c.p >= c.end) return 0;
-    const uint64_t tag = rd_varint(w, c);
+    const uint64_t tag = rd_varint<kLane>(w, c);
     if (!c.ok) return 0;
     wt = (int)(tag & 7);
     const uint32_t f = (uint32_t)(tag >> 3);
     if (wt == 0) {
-        v0 = rd_varint(w, c);
+        v0 = rd_varint<kLane>(w, c);
     } else if (wt == 1) {
         v0 = c.p; v1 = c.p + 8; c.p += 8;
     } else if (wt == 5) {
         v0 = c.p; v1 = c.p + 4; c.p += 4;
     } else if (wt == 2) {
-        const uint64_t n = rd_varint(w, c);
+        const uint64_t n = rd_varint<kLane>(w, c);
         if (!c.ok || n > c.end - c.p) { c.ok = false; return 0; }
         v0 = c.p; v1 = c.p + n; c.p += n;
     } else {
@@ -275,8 +320,84 @@ __device__ inline uint32_t next_field(Win& w, Cursor& c, int& wt, uint64_t& v0, 
 __device__ inline bool key_is(Win& w, uint64_t s, uint64_t e, const char* lit, int n) {
     if (e - s != (uint64_t)n) return false;
     for (int i = 0; i < n; i++)
-        if (win_byte(w, s + i) != (uint32_t)(uint8_t)lit[i]) return false;
+        if (lane_byte(w, s + i) != (uint32_t)(uint8_t)lit[i]) return false;
     return true;
+}
+
+struct EntryResult {     // what one map entry contributes
+    uint64_t ps, pe;     // payload / identifier byte range
+    int64_t ival;
+    int32_t which;       // 0 img, 1 h, 2 w, 3 c, 4 tgt, 5 th, 6 tw, 7 id; -1 not ours; -2 malformed
+    int32_t okk;         // payload kind (1 bytes, 2 floats) or 1 = well-formed scalar, 0 = wrong type / count
+};
+
+// phase B: parse ONE map entry [a2, b2v)
+__device__ inline EntryResult parse_entry(Win& w, uint64_t a2, uint64_t b2v) {
+    EntryResult r;
+    r.ps = r.pe = 0; r.ival = 0; r.which = -1; r.okk = 0;
+    Cursor en{a2, b2v, true};
+    int wt3; uint64_t a3, b3;
+    uint64_t ks = 0, ke = 0, vs = 0, ve = 0;
+    bool hk = false, hv = false;
+    while (uint32_t f3 = next_field<true>(w, en, wt3, a3, b3)) {
+        if (f3 == 1 && wt3 == 2) { ks = a3; ke = b3; hk = true; }
+        else if (f3 == 2 && wt3 == 2) { vs = a3; ve = b3; hv = true; }
+    }
+    if (!en.ok) { r.which = -2; return r; }
+    if (!hk) return r;
+    int which = -1;
+    if (key_is(w, ks, ke, "image/image_data", 16)) which = 0;
+    else if (key_is(w, ks, ke, "image/height", 12)) which = 1;
+    else if (key_is(w, ks, ke, "image/width", 11)) which = 2;
+    else if (key_is(w, ks, ke, "image/channels", 14)) which = 3;
+    else if (key_is(w, ks, ke, "target/target_data", 18)) which = 4;
+    else if (key_is(w, ks, ke, "target/height", 13)) which = 5;
+    else if (key_is(w, ks, ke, "target/width", 12)) which = 6;
+    else if (key_is(w, ks, ke, "identifier", 10)) which = 7;
+    if (which < 0) return r;
+    // Feature oneof: last member present wins
+    int kind = 0; uint64_t ls = 0, le = 0;
+    if (hv) {
+        Cursor fe{vs, ve, true};
+        int wt4; uint64_t a4, b4;
+        while (uint32_t f4 = next_field<true>(w, fe, wt4, a4, b4)) {
+            if (wt4 == 2 && f4 >= 1 && f4 <= 3) { kind = (int)f4; ls = a4; le = b4; }
+        }
+        if (!fe.ok) { r.which = -2; return r; }
+    }
+    // the list message: field 1 repeated
+    uint64_t ps = 0, pe = 0; int count = 0; int64_t ival = 0; bool packed_ok = true;
+    if (kind) {
+        Cursor li{ls, le, true};
+        int wt5; uint64_t a5, b5;
+        while (uint32_t f5 = next_field<true>(w, li, wt5, a5, b5)) {
+            if (f5 != 1) continue;
+            if (kind == 1) {
+                if (wt5 == 2) { ps = a5; pe = b5; count++; }
+            } else if (kind == 2) {
+                if (wt5 == 2) { ps = a5; pe = b5; count++; }      // packed floats (one chunk expected)
+                else if (wt5 == 5) { packed_ok = false; }          // unpacked fixed32: not supported on device
+            } else {
+                if (wt5 == 2) {
+                    Cursor pk{a5, b5, true};
+                    while (pk.ok && pk.p < pk.end) { ival = (int64_t)rd_varint<true>(w, pk); count++; }
+                    if (!pk.ok) li.ok = false;
+                } else if (wt5 == 0) { ival = (int64_t)a5; count++; }
+            }
+        }
+        if (!li.ok) { r.which = -2; return r; }
+    }
+    r.which = which;
+    r.ps = ps; r.pe = pe; r.ival = ival;
+    if (which == 0 || which == 4) {
+        if (kind == 1 && count == 1) r.okk = 1;
+        else if (kind == 2 && packed_ok && count <= 1 && ((pe - ps) & 3) == 0) r.okk = 2;
+    } else if (which == 7) {
+        r.okk = (kind == 1 && count == 1) ? 1 : 0;
+    } else {
+        r.okk = (kind == 3 && count == 1) ? 1 : 0;
+    }
+    return r;
 }
 
 __global__ void __launch_bounds__(kIdxWarps * 32)
@@ -284,8 +405,11 @@ index_kernel(const uint8_t* __restrict__ shard, uint64_t nbytes, const uint64_t*
              const uint64_t* __restrict__ rec_len, int n, b2_example_index* __restrict__ out,
              const int64_t* __restrict__ n_dev, const uint32_t* __restrict__ tile_start, uint32_t* __restrict__ tile2rec) {
     __shared__ __align__(16) uint8_t s_win[kIdxWarps][kIdxWin];
-    const int r = blockIdx.x * kIdxWarps + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    __shared__ __align__(16) uint8_t s_lane[kIdxWarps][32][kLaneWin];
+    __shared__ uint64_t s_ent[kIdxWarps][32][2];
+    __shared__ EntryResult s_res[kIdxWarps][32];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * kIdxWarps + wib;
     if (n_dev && (int64_t)r >= n_dev[0]) return;   // opened shard: the record count is only known on the device
     if (r >= n) return;
     const uint64_t d0 = rec_off[r], dl = rec_len[r];
@@ -293,90 +417,58 @@ index_kernel(const uint8_t* __restrict__ shard, uint64_t nbytes, const uint64_t*
         const uint32_t t0 = tile_start[r], t1 = tile_start[r + 1];
         for (uint32_t t = t0 + lane; t < t1; t += 32) tile2rec[t] = (uint32_t)r;
     }
-    Win w{shard, nbytes < d0 + dl ? nbytes : d0 + dl, &s_win[threadIdx.x >> 5][0], ~0ull - kIdxWin};
+    const uint64_t lim = nbytes < d0 + dl ? nbytes : d0 + dl;
+    Win w{shard, lim, &s_win[wib][0], ~0ull - kIdxWin};
+    Win lw{shard, lim, &s_lane[wib][lane][0], ~0ull - kLaneWin};
     b2_example_index ix;
     memset(&ix, 0, sizeof(ix));
     int have[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // img, h, w, c, tgt, th, tw, id : 1 ok, -1 wrong type/count
     int64_t dims[5] = {0, 0, 0, 0, 0};
+    bool ok = true;
     Cursor ex{d0, d0 + dl, true};
     int wt; uint64_t a, b;
-    while (uint32_t f = next_field(w, ex, wt, a, b)) {
+    while (uint32_t f = next_field<false>(w, ex, wt, a, b)) {
         if (f != 1 || wt != 2) continue;  // Example.features
         Cursor fs{a, b, true};
-        int wt2; uint64_t a2, b2v;
-        while (uint32_t f2 = next_field(w, fs, wt2, a2, b2v)) {
-            if (f2 != 1 || wt2 != 2) continue;  // Features.feature map entry
-            Cursor en{a2, b2v, true};
-            int wt3; uint64_t a3, b3;
-            uint64_t ks = 0, ke = 0, vs = 0, ve = 0;
-            bool hk = false, hv = false;
-            while (uint32_t f3 = next_field(w, en, wt3, a3, b3)) {
-                if (f3 == 1 && wt3 == 2) { ks = a3; ke = b3; hk = true; }
-                else if (f3 == 2 && wt3 == 2) { vs = a3; ve = b3; hv = true; }
+        bool more = true;
+        while (more && ok) {
+            // phase A: collect up to 32 map entries
+            int ne = 0;
+            int wt2; uint64_t a2, b2v;
+            while (ne < 32) {
+                const uint32_t f2 = next_field<false>(w, fs, wt2, a2, b2v);
+                if (!f2) { more = false; break; }
+                if (f2 != 1 || wt2 != 2) continue;  // Features.feature map entry
+                if (lane == 0) { s_ent[wib][ne][0] = a2; s_ent[wib][ne][1] = b2v; }
+                ne++;
             }
-            if (!en.ok) { ex.ok = false; break; }
-            if (!hk) continue;
-            int which = -1;
-            if (key_is(w, ks, ke, "image/image_data", 16)) which = 0;
-            else if (key_is(w, ks, ke, "image/height", 12)) which = 1;
-            else if (key_is(w, ks, ke, "image/width", 11)) which = 2;
-            else if (key_is(w, ks, ke, "image/channels", 14)) which = 3;
-            else if (key_is(w, ks, ke, "target/target_data", 18)) which = 4;
-            else if (key_is(w, ks, ke, "target/height", 13)) which = 5;
-            else if (key_is(w, ks, ke, "target/width", 12)) which = 6;
-            else if (key_is(w, ks, ke, "identifier", 10)) which = 7;
-            if (which < 0) continue;
-            // Feature oneof: last member present wins
-            int kind = 0; uint64_t ls = 0, le = 0;
-            if (hv) {
-                Cursor fe{vs, ve, true};
-                int wt4; uint64_t a4, b4;
-                while (uint32_t f4 = next_field(w, fe, wt4, a4, b4)) {
-                    if (wt4 == 2 && f4 >= 1 && f4 <= 3) { kind = (int)f4; ls = a4; le = b4; }
+            if (!fs.ok) { ok = false; break; }
+            __syncwarp();
+            // phase B: one entry per lane
+            if (lane < ne) s_res[wib][lane] = parse_entry(lw, s_ent[wib][lane][0], s_ent[wib][lane][1]);
+            __syncwarp();
+            // phase C: apply in file order (all lanes redundantly: the state stays warp-uniform)
+            for (int e = 0; e < ne; e++) {
+                const EntryResult q = s_res[wib][e];
+                if (q.which == -2) { ok = false; break; }
+                if (q.which < 0) continue;
+                if (q.which == 0) { ix.img_off = q.ps; ix.img_len = q.pe - q.ps; ix.img_kind = q.okk; have[0] = q.okk ? 1 : -1; }
+                else if (q.which == 4) { ix.tgt_off = q.ps; ix.tgt_len = q.pe - q.ps; ix.tgt_kind = q.okk; have[4] = q.okk ? 1 : -1; }
+                else if (q.which == 7) {
+                    if (q.okk) { ix.id_off = q.ps; ix.id_len = q.pe - q.ps; have[7] = 1; } else have[7] = -1;
+                } else {
+                    const int d = q.which < 4 ? q.which - 1 : q.which - 2;  // h,w,c,th,tw -> 0..4
+                    if (q.okk) { dims[d] = q.ival; have[q.which] = 1; } else have[q.which] = -1;
                 }
-                if (!fe.ok) { ex.ok = false; break; }
             }
-            // the list message: field 1 repeated
-            uint64_t ps = 0, pe = 0; int count = 0; int64_t ival = 0; bool packed_ok = true;
-            if (kind) {
-                Cursor li{ls, le, true};
-                int wt5; uint64_t a5, b5;
-                while (uint32_t f5 = next_field(w, li, wt5, a5, b5)) {
-                    if (f5 != 1) continue;
-                    if (kind == 1) {
-                        if (wt5 == 2) { ps = a5; pe = b5; count++; }
-                    } else if (kind == 2) {
-                        if (wt5 == 2) { ps = a5; pe = b5; count++; }      // packed floats (one chunk expected)
-                        else if (wt5 == 5) { packed_ok = false; }          // unpacked fixed32: not supported on device
-                    } else {
-                        if (wt5 == 2) {
-                            Cursor pk{a5, b5, true};
-                            while (pk.ok && pk.p < pk.end) { ival = (int64_t)rd_varint(w, pk); count++; }
-                            if (!pk.ok) li.ok = false;
-                        } else if (wt5 == 0) { ival = (int64_t)a5; count++; }
-                    }
-                }
-                if (!li.ok) { ex.ok = false; break; }
-            }
-            if (which == 0 || which == 4) {
-                int okk = 0;
-                if (kind == 1 && count == 1) okk = 1;
-                else if (kind == 2 && packed_ok && count <= 1 && ((pe - ps) & 3) == 0) okk = 2;
-                if (which == 0) { ix.img_off = ps; ix.img_len = pe - ps; ix.img_kind = okk; have[0] = okk ? 1 : -1; }
-                else { ix.tgt_off = ps; ix.tgt_len = pe - ps; ix.tgt_kind = okk; have[4] = okk ? 1 : -1; }
-            } else if (which == 7) {
-                if (kind == 1 && count == 1) { ix.id_off = ps; ix.id_len = pe - ps; have[7] = 1; } else have[7] = -1;
-            } else {
-                const int d = which < 4 ? which - 1 : which - 2;  // h,w,c,th,tw -> 0..4
-                if (kind == 3 && count == 1) { dims[d] = ival; have[which] = 1; } else have[which] = -1;
-            }
+            __syncwarp();
         }
-        if (!fs.ok) ex.ok = false;
-        if (!ex.ok) break;
+        if (!ok) break;
     }
+    if (!ex.ok) ok = false;
     ix.height = (int32_t)dims[0]; ix.width = (int32_t)dims[1]; ix.channels = (int32_t)dims[2];
     ix.tgt_height = (int32_t)dims[3]; ix.tgt_width = (int32_t)dims[4];
-    int st = ex.ok ? 0 : 1;
+    int st = ok ? 0 : 1;
     if (st == 0)
         for (int k = 0; k < 8; k++)
             if (have[k] != 1) st = 2;

@@ -374,3 +374,32 @@ def test_parse_table_raw_and_reparse(dev):
     # rows too small for the payload -> status 3 for every record
     _, _, status3 = ops.parse_table(st, "raw", 100, 900)
     assert list(status3[:n].cpu().numpy()) == [3] * 11
+
+
+def test_scan_tiny_and_truncated_shards(dev):
+    """Shards shorter than a header, ending inside a header, or ending inside the data are DataLoss at the right record."""
+    from dl_image_segmentation_b200 import ops
+    recs = [bytes(range(40)), b"", bytes(7), bytes(300)]
+    shard = b"".join(otfr.frame(r) for r in recs)
+    for cut in (5, 11, 12, 20, len(otfr.frame(recs[0])) + 3, len(shard) - 1, len(shard) - 4, len(shard) - 5):
+        st = ops.open_shard_async(shard[:cut], dev, max_records=16)
+        n, status = st.header()[:2]
+        try:
+            o, _ = otfr.scan(shard[:cut])
+            want = (len(o), 0)
+        except otfr.DataLossError:
+            # the oracle raises at the first bad frame: count the good ones before it
+            good, pos = 0, 0
+            while True:
+                try:
+                    otfr.scan(shard[:cut][pos:pos + 16 + len(recs[good])])
+                except Exception:
+                    break
+                if pos + 16 + len(recs[good]) > cut:
+                    break
+                pos += 16 + len(recs[good])
+                good += 1
+            want = (good, 1)
+        assert (n, status) == want, cut
+    st = ops.open_shard_async(shard, dev, max_records=16)
+    assert st.header()[:2] == (4, 0)
