@@ -77,13 +77,33 @@ def images_to_tfrecords(name, directory, out_directory, num_shards, num_proc=Non
 
 
 def parse_records_norm_onehot(records, mean, std, num_classes):
-    """records: list of Example bytes (uint8 arrays stored as BytesList) -> (N,H,W,C) f32, (N,H,W,K) f32."""
-    imgs, hots = [], []
-    for r in records:
+    """records: list of Example bytes (uint8 arrays stored as BytesList) -> (N,H,W,C) f32, (N,H,W,K) f32.
+
+    Same values as normalise.normalise / normalise.one_hot (float32 subtract + IEEE divide; label == k), written
+    straight into the batch arrays so that the CPU baseline is not handicapped by temporaries."""
+    mean = np.asarray(mean, dtype=np.float32)
+    std = np.asarray(std, dtype=np.float32)
+    imgs = hots = None
+    mean_row = std_row = None
+    for n, r in enumerate(records):
         img, tgt, _ = example_proto.parse_8bit_array_proto(r)
-        imgs.append(normalise.normalise(img, mean, std))
-        hots.append(normalise.one_hot(tgt, num_classes))
-    return np.stack(imgs), np.stack(hots)
+        if imgs is None:
+            imgs = np.empty((len(records),) + img.shape, np.float32)
+            hots = np.empty((len(records),) + tgt.shape[:2] + (num_classes,), np.float32)
+        h, w, c = img.shape
+        if mean_row is None or mean_row.size != w * c:
+            mean_row, std_row = np.tile(mean, w), np.tile(std, w)       # long inner loops: NumPy broadcasts over 3 are slow
+        o2 = imgs[n].reshape(h, w * c)
+        np.subtract(img.reshape(h, w * c), mean_row, out=o2, dtype=np.float32)
+        np.divide(o2, std_row, out=o2)
+        lab = (tgt[..., 0] if tgt.ndim == 3 else tgt).reshape(-1)
+        hn = hots[n].reshape(-1, num_classes)
+        hn[:] = 0.0
+        ok = np.nonzero(lab < num_classes)[0]
+        hn[ok, lab[ok]] = 1.0
+    if imgs is None:
+        return np.zeros((0,), np.float32), np.zeros((0,), np.float32)
+    return imgs, hots
 
 
 def parse_shard_bytes(buf, mean, std, num_classes, verify=True):
