@@ -31,11 +31,14 @@ namespace b2 {
 // SHARE the validity column: each loads P/GPP of the T bytes and the bit masks are OR-ed with warp shuffles,
 // which removes (GPP-1)/GPP of the byte loads and their registers.  GPP = 0: every thread loads all T bytes.
 // All loads of a thread are issued back to back before any is consumed (T + T/GPP independent requests).
-template <int P, int GPP, bool kNodata>
+// kFullT: T == P is known at compile time (the common case, e.g. T = 16), so no load or slot is predicated.
+// Addresses advance by one scene plane per step (two adds) instead of being recomputed from t.
+template <int P, int GPP, bool kNodata, bool kFullT>
 __global__ void __launch_bounds__(256, (P <= 16 ? (kNodata ? 4 : 6) : 2))
 median_kernel(const uint16_t* __restrict__ stack, const uint8_t* __restrict__ valid,
-              const uint8_t* __restrict__ nodata, int T, uint64_t hw, int B, uint64_t n_groups,
+              const uint8_t* __restrict__ nodata, int T_rt, uint64_t hw, int B, uint64_t n_groups,
               double* __restrict__ out, uint8_t* __restrict__ out_mask) {
+    const int T = kFullT ? P : T_rt;
     const uint64_t g_raw = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = g_raw < n_groups;
     const uint64_t g = live ? g_raw : n_groups - 1;   // keep every lane alive for the shuffles
@@ -44,45 +47,77 @@ median_kernel(const uint16_t* __restrict__ stack, const uint8_t* __restrict__ va
     const uint64_t plane = hw * (uint64_t)B;          // elements per scene
 
     uint32_t v[P];
+    {
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(stack + e0);
+        const uint64_t step = plane * 2;
 #pragma unroll
-    for (int t = 0; t < P; t++) v[t] = (t < T) ? __ldg(reinterpret_cast<const uint32_t*>(stack + (uint64_t)t * plane + e0)) : 0u;
+        for (int t = 0; t < P; t++) {
+            v[t] = (kFullT || t < T) ? __ldg(reinterpret_cast<const uint32_t*>(p)) : 0u;
+            p += step;
+        }
+    }
     uint32_t vmask = 0;                               // bit t set = scene t usable at this pixel
     if (GPP) {
         constexpr int kPer = GPP ? (P + GPP - 1) / GPP : P;
         const int sub = (int)(g % (GPP ? GPP : 1));
         uint32_t vb[kPer];
+        const uint8_t* p = valid + (uint64_t)sub * hw + pix;
+        const uint64_t step = (uint64_t)(GPP ? GPP : 1) * hw;
 #pragma unroll
         for (int j = 0; j < kPer; j++) {
             const int t = sub + j * GPP;
-            vb[j] = (t < T) ? __ldg(valid + (uint64_t)t * hw + pix) : 0u;
+            vb[j] = ((kFullT && (j + 1) * GPP <= P) || t < T) ? __ldg(p) : 0u;
+            p += step;
         }
 #pragma unroll
-        for (int j = 0; j < kPer; j++) vmask |= (vb[j] ? 1u : 0u) << (sub + j * GPP);
+        for (int j = 0; j < kPer; j++) vmask |= (vb[j] ? 1u : 0u) << (j * GPP);
+        vmask <<= sub;
 #pragma unroll
         for (int o = 1; o < GPP; o <<= 1) vmask |= __shfl_xor_sync(0xffffffffu, vmask, o);
     } else {
         uint32_t vb[P];
+        const uint8_t* p = valid + pix;
 #pragma unroll
-        for (int t = 0; t < P; t++) vb[t] = (t < T) ? __ldg(valid + (uint64_t)t * hw + pix) : 0u;
+        for (int t = 0; t < P; t++) {
+            vb[t] = (kFullT || t < T) ? __ldg(p) : 0u;
+            p += hw;
+        }
 #pragma unroll
         for (int t = 0; t < P; t++) vmask |= (vb[t] ? 1u : 0u) << t;
     }
-    uint32_t ndm[kNodata ? P : 1];                    // per half 0xFFFF where the (t,band) sample is nodata
+    uint32_t cnt;                                     // valid count per half
     if (kNodata) {
+        uint32_t ndm[P];                              // per half 0xFFFF where the (t,band) sample is nodata
+        const uint8_t* p = nodata + e0;
 #pragma unroll
         for (int t = 0; t < P; t++) {
-            const uint32_t two = (t < T) ? __ldg(reinterpret_cast<const uint16_t*>(nodata + (uint64_t)t * plane + e0)) : 0u;
+            const uint32_t two = (kFullT || t < T) ? __ldg(reinterpret_cast<const uint16_t*>(p)) : 0u;
             ndm[t] = ((two & 0xFFu) ? 0x0000FFFFu : 0u) | ((two & 0xFF00u) ? 0xFFFF0000u : 0u);
+            p += plane;
         }
-    }
-    uint32_t tg = 0xFFFFFFFFu, cnt = 0;               // next sentinel per half (0xFFFF first); valid count per half
+        uint32_t tg = 0xFFFFFFFFu;                    // next sentinel per half (0xFFFF first)
+        cnt = 0;
 #pragma unroll
-    for (int t = 0; t < P; t++) {
-        uint32_t im = ((vmask >> t) & 1u) ? 0u : 0xFFFFFFFFu;     // per half: 0xFFFF where the entry is invalid
-        if (kNodata) im |= ndm[t];
-        v[t] = (v[t] & ~im) | (tg & im);
-        tg ^= im;
-        cnt += (~im) & 0x00010001u;
+        for (int t = 0; t < P; t++) {
+            uint32_t im = ((vmask >> t) & 1u) ? 0u : 0xFFFFFFFFu;     // per half: 0xFFFF where the entry is invalid
+            im |= ndm[t];
+            v[t] = (v[t] & ~im) | (tg & im);
+            tg ^= im;
+            cnt += (~im) & 0x00010001u;
+        }
+    } else {
+        // both halves share the validity: invalid entry number k gets the sentinel 0xFFFF (k even) or 0 (k odd);
+        // slots t >= T are invalid too (their bits are 0 in vmask).  One bit test + two predicated moves per slot.
+        uint32_t tg = 0xFFFFFFFFu;
+#pragma unroll
+        for (int t = 0; t < P; t++) {
+            if (!((vmask >> t) & 1u)) {
+                v[t] = tg;
+                tg = ~tg;
+            }
+        }
+        const uint32_t n = (uint32_t)__popc(vmask & (P < 32 ? ((1u << P) - 1u) : 0xFFFFFFFFu));
+        cnt = n | (n << 16);
     }
     MedNet<P>::run(v);
     const uint32_t lo = v[P / 2 - 1], hi = v[P / 2];
@@ -154,10 +189,13 @@ static void launch_median(const uint16_t* stack, const uint8_t* valid, const uin
                           int B, double* out, uint8_t* mask, cudaStream_t s) {
     const uint64_t n_groups = hw * (uint64_t)B / 2;
     const unsigned grid = (unsigned)((n_groups + 255) / 256);
-    if (nodata)
-        median_kernel<P, GPP, true><<<grid, 256, 0, s>>>(stack, valid, nodata, T, hw, B, n_groups, out, mask);
-    else
-        median_kernel<P, GPP, false><<<grid, 256, 0, s>>>(stack, valid, nodata, T, hw, B, n_groups, out, mask);
+    if (nodata) {
+        if (T == P) median_kernel<P, GPP, true, true><<<grid, 256, 0, s>>>(stack, valid, nodata, T, hw, B, n_groups, out, mask);
+        else median_kernel<P, GPP, true, false><<<grid, 256, 0, s>>>(stack, valid, nodata, T, hw, B, n_groups, out, mask);
+    } else {
+        if (T == P) median_kernel<P, GPP, false, true><<<grid, 256, 0, s>>>(stack, valid, nodata, T, hw, B, n_groups, out, mask);
+        else median_kernel<P, GPP, false, false><<<grid, 256, 0, s>>>(stack, valid, nodata, T, hw, B, n_groups, out, mask);
+    }
 }
 
 template <int P>
