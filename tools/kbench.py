@@ -106,7 +106,8 @@ def bench_mosaic(dev, pool=256, chips=4096, iters=5):
             "GB/s_min_touched": round(touched_min / (ms / 1e3) / 1e9, 1), "mean_eligible": float(nel.float().mean().cpu())})
 
 
-def bench_decode(dev, kind, n_distinct=16, reps=16):
+def bench_decode(dev, kind, n_distinct=16, reps=None):
+    reps = reps or int(os.environ.get("KB_DECODE_REPS", "16"))
     import time
 
     import synthetic as syn
