@@ -44,22 +44,28 @@ __device__ __forceinline__ uint32_t lzw_width(uint32_t k) { return k < 254 ? 9 :
 constexpr int kLzwWarps = 4;
 constexpr int kLzwMaxCodes = 3840;  // code positions per segment (entries 258..4095 -> at most 3838 + slack)
 
+constexpr int kLzwOffs = kLzwMaxCodes + 40;   // per resident warp, in the context workspace: offs[k] = output offset of
+                                              // code position k of the current segment (kept out of shared memory so
+                                              // that 64 warps per SM stay resident: the decode is latency-bound)
 struct LzwWarpSmem {
-    uint32_t offs[kLzwMaxCodes + 40];  // offs[k] = output offset of code position k of the current segment
     uint32_t b_off[33];                // this round: output offset of each lane's string (+ end sentinel)
     int32_t b_src[32];                 // >=0: source offset in dst ; <0: literal value = -1 - b_src
 };
 
 __global__ void __launch_bounds__(kLzwWarps * 32)
 lzw_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ streams, const int* __restrict__ order,
-           int n_streams, uint8_t* scratch, int32_t* __restrict__ status) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    LzwWarpSmem* sm = reinterpret_cast<LzwWarpSmem*>(smem_raw) + (threadIdx.x >> 5);
+           int n_streams, uint8_t* scratch, int32_t* __restrict__ status, uint32_t* offs_ws, unsigned int* next_stream) {
+    __shared__ LzwWarpSmem sm_all[kLzwWarps];
+    LzwWarpSmem* sm = &sm_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    const int wi = blockIdx.x * kLzwWarps + (threadIdx.x >> 5);
+    uint32_t* offs = offs_ws + (size_t)(blockIdx.x * kLzwWarps + (threadIdx.x >> 5)) * kLzwOffs;
+  for (;;) {                                                           // persistent warps draw streams from a counter
+    int wi = 0;
+    if (lane == 0) wi = (int)atomicAdd(next_stream, 1u);
+    wi = __shfl_sync(0xffffffffu, wi, 0);
     if (wi >= n_streams) return;
     const b2_stream_desc sd = streams[order ? order[wi] : wi];
-    if (sd.codec != CODEC_LZW) return;
+    if (sd.codec != CODEC_LZW) continue;
     const uint8_t* src = blob + sd.src_off;
     uint8_t* dst = scratch + sd.dst_off;
     const uint32_t src_bits = sd.src_len * 8u, dst_len = sd.dst_len;
@@ -105,7 +111,7 @@ lzw_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ 
             } else {
                 e = code - 258;
                 if (k == 0 || e + 1 > k) bad = true;                   // first code after Clear must be a literal; entry must exist
-                else if (e < n) len = sm->offs[e + 1] - sm->offs[e] + 1;
+                else if (e < n) len = __ldcg(offs + e + 1) - __ldcg(offs + e) + 1;
                 else dep = (int32_t)(e - n);
             }
         }
@@ -132,7 +138,7 @@ lzw_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ 
         int32_t srcv;
         if (lane < m) {
             if (code < 256) srcv = -1 - (int32_t)code;
-            else if (e < n) srcv = (int32_t)sm->offs[e];
+            else if (e < n) srcv = (int32_t)__ldcg(offs + e);
             else srcv = 0;  // fixed below from the producing lane's offset
         } else srcv = -1;
         {
@@ -140,8 +146,8 @@ lzw_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ 
             const uint32_t so = __shfl_sync(0xffffffffu, my_off, dl);
             if (lane < m && code >= 256 && e >= n) srcv = (int32_t)so;
         }
-        if (lane < m) sm->offs[k] = my_off;
-        if (lane == 0) sm->offs[n + m] = out + tot;
+        if (lane < m) offs[k] = my_off;
+        if (lane == 0) offs[n + m] = out + tot;
         sm->b_off[lane] = (lane < m) ? my_off : (out + tot);
         sm->b_src[lane] = srcv;
         if (lane == 0) sm->b_off[32] = out + tot;
@@ -181,6 +187,8 @@ lzw_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ 
     }
     if (err == 0 && out < dst_len) err = 1;                            // stream ended early / table overflow
     if (err && lane == 0) set_status(status, sd.image, 10 + err);
+    __syncwarp();
+  }
 }
 
 // ================================================================================================ DEFLATE
@@ -532,9 +540,11 @@ __device__ __forceinline__ T load_sample(const uint8_t* p, bool swap) {
 
 template <typename T>
 __global__ void __launch_bounds__(128)
-hdiff_undo_kernel(uint8_t* __restrict__ scratch, const b2_image_desc* __restrict__ imgs, int img_index,
+hdiff_undo_kernel(uint8_t* __restrict__ scratch, const b2_image_desc* __restrict__ imgs, int img_base,
                   const int32_t* __restrict__ status) {
+    const int img_index = img_base + blockIdx.y;              // one launch covers a batch of images
     const b2_image_desc im = imgs[img_index];
+    if (im.format != 1 || im.predictor != 2 || im.bytes_per_sample != (int)sizeof(T)) return;
     if (status && status[img_index] != 0) return;
     const int planes = im.planar == 2 ? im.samples : 1;
     const int spb = im.planar == 2 ? 1 : im.samples;
@@ -640,13 +650,16 @@ extern "C" int b2_decode_streams(b2_ctx* ctx, const uint8_t* blob, const b2_stre
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (codec_mask & 1u) {   // LZW
-        const size_t smem = sizeof(LzwWarpSmem) * kLzwWarps;
-        static bool attr_set[64] = {false};
-        if (!attr_set[ctx->device & 63]) {
-            B2_CUDA(cudaFuncSetAttribute(lzw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set[ctx->device & 63] = true;
-        }
-        lzw_kernel<<<(n_streams + kLzwWarps - 1) / kLzwWarps, kLzwWarps * 32, smem, s>>>(blob, streams, nullptr, n_streams, scratch, status);
+        // persistent warps (up to 64 per SM), each with its own offset table in the context workspace
+        unsigned ctas = (unsigned)((n_streams + kLzwWarps - 1) / kLzwWarps);
+        const unsigned resident = (unsigned)ctx->sm_count * (64 / kLzwWarps);
+        if (ctas > resident) ctas = resident;
+        const size_t offs_bytes = (size_t)ctas * kLzwWarps * kLzwOffs * sizeof(uint32_t);
+        if (int e = ws_reserve(ctx, offs_bytes + 256, s)) return e;
+        unsigned int* counter = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(ctx->ws) + offs_bytes);
+        B2_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
+        lzw_kernel<<<ctas, kLzwWarps * 32, 0, s>>>(blob, streams, nullptr, n_streams, scratch, status,
+                                                  static_cast<uint32_t*>(ctx->ws), counter);
         ctx->launches++;
         B2_CUDA(cudaGetLastError());
     }
@@ -677,6 +690,7 @@ extern "C" int b2_assemble_images(b2_ctx* ctx, uint8_t* scratch, const b2_image_
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     bool any_png = false, any_tiff = false;
     uint64_t max_bytes = 0;
+    long long max_rows[5] = {0, 0, 0, 0, 0};       // predictor-2 rows of the largest image, per sample size
     for (int i = 0; i < n_images; i++) {
         const b2_image_desc& im = imgs_host[i];
         if (im.format == 2) any_png = true;
@@ -685,17 +699,23 @@ extern "C" int b2_assemble_images(b2_ctx* ctx, uint8_t* scratch, const b2_image_
             const uint64_t nb = (uint64_t)im.width * im.height * im.samples * im.bytes_per_sample;
             if (nb > max_bytes) max_bytes = nb;
             if (im.predictor == 2) {
+                if (im.bytes_per_sample != 1 && im.bytes_per_sample != 2 && im.bytes_per_sample != 4)
+                    return fail("b2_assemble_images: predictor 2 needs 8/16/32-bit samples");
                 const int planes = im.planar == 2 ? im.samples : 1;
                 const long long rows = (long long)im.blocks_across * im.blocks_down * planes * im.block_h;
-                const unsigned grid = (unsigned)((rows * 32 + 127) / 128);
-                switch (im.bytes_per_sample) {
-                    case 1: hdiff_undo_kernel<uint8_t><<<grid, 128, 0, s>>>(scratch, imgs_dev, i, status); break;
-                    case 2: hdiff_undo_kernel<uint16_t><<<grid, 128, 0, s>>>(scratch, imgs_dev, i, status); break;
-                    case 4: hdiff_undo_kernel<uint32_t><<<grid, 128, 0, s>>>(scratch, imgs_dev, i, status); break;
-                    default: return fail("b2_assemble_images: predictor 2 needs 8/16/32-bit samples");
-                }
-                ctx->launches++;
+                if (rows > max_rows[im.bytes_per_sample]) max_rows[im.bytes_per_sample] = rows;
             }
+        }
+    }
+    for (int bs = 1; bs <= 4; bs <<= 1) {          // one launch per sample size and 65535 images (grid.y = image)
+        if (!max_rows[bs]) continue;
+        const unsigned gx = (unsigned)((max_rows[bs] * 32 + 127) / 128);
+        for (int s0 = 0; s0 < n_images; s0 += 65535) {
+            const int m = n_images - s0 < 65535 ? n_images - s0 : 65535;
+            if (bs == 1) hdiff_undo_kernel<uint8_t><<<dim3(gx, m), 128, 0, s>>>(scratch, imgs_dev, s0, status);
+            else if (bs == 2) hdiff_undo_kernel<uint16_t><<<dim3(gx, m), 128, 0, s>>>(scratch, imgs_dev, s0, status);
+            else hdiff_undo_kernel<uint32_t><<<dim3(gx, m), 128, 0, s>>>(scratch, imgs_dev, s0, status);
+            ctx->launches++;
         }
     }
     B2_CUDA(cudaGetLastError());
