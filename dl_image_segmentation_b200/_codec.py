@@ -65,85 +65,94 @@ def _align(x, a=256):
     return (int(x) + a - 1) // a * a
 
 
+class DecodePlan(ctypes.Structure):
+    _fields_ = [("stage_bytes", ctypes.c_uint64), ("scratch_bytes", ctypes.c_uint64), ("out_bytes", ctypes.c_uint64),
+                ("compressed_bytes", ctypes.c_uint64), ("n_streams", ctypes.c_int32), ("codec_mask", ctypes.c_uint32),
+                ("max_raw_len", ctypes.c_uint32), ("filled", ctypes.c_int32)]
+
+
+_lib.register_signatures({
+    "b2_decode_plan_batch": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _u64, _i, ctypes.POINTER(DecodePlan)]),
+})
+
+
+class _HostStaging:
+    """Pinned host buffers of one device's decode path, grown on demand and reused between batches."""
+
+    def __init__(self):
+        self.stage = torch.empty((1 << 20,), dtype=torch.uint8).pin_memory()
+        self.streams = torch.empty((4096 * STREAM_DESC_DTYPE.itemsize,), dtype=torch.uint8).pin_memory()
+        self.busy = None          # event: the last H2D copies out of these buffers
+
+    def wait(self):
+        if self.busy is not None:
+            self.busy.synchronize()
+            self.busy = None
+
+
+_staging = {}
+
+
+def _ptr_of(blob):
+    """(address, size, keep-alive object) of a host blob without copying it."""
+    if isinstance(blob, bytes):
+        return ctypes.cast(ctypes.c_char_p(blob), ctypes.c_void_p).value or 0, len(blob), blob
+    a = _host_bytes(blob)
+    return a.ctypes.data, a.size, a
+
+
 def decode_blobs(blobs, device=None, timings=None):
     """Decode a batch of encoded chips on the GPU.
 
     blobs: list of bytes / uint8 arrays (host).  Returns (arrays, status): arrays[i] is an (H,W,bands) CUDA
-    tensor of the file's dtype (None when status[i] != 0).
+    tensor of the file's dtype (None when status[i] != 0).  All per-file host work (header parse, descriptor
+    tables, gathering the compressed bytes into one pinned buffer) happens in ONE native, multi-threaded call.
     """
     ctx = get_ctx(device)
     n = len(blobs)
-    hosts = [_host_bytes(b) for b in blobs]
-    infos, status = [], np.zeros(n, dtype=np.int32)
-    stage_parts, stage_pos = [], 0
-    streams = []
-    images = np.zeros(n, dtype=IMAGE_DESC_DTYPE)
-    scratch_pos = out_pos = 0
-    mask = 0
-    max_raw = 0
-    for i, a in enumerate(hosts):
-        info = ImageInfo()
-        check(lib().b2_image_probe(a.ctypes.data, a.size, ctypes.byref(info)))
-        infos.append(info)
-        if info.status != 0:
-            status[i] = info.status
-            continue
-        nb = info.n_blocks
-        offs = np.zeros(nb, np.uint64)
-        cnts = np.zeros(nb, np.uint64)
-        dlen = np.zeros(nb, np.uint64)
-        try:
-            check(lib().b2_image_blocks(a.ctypes.data, a.size, ctypes.byref(info), offs.ctypes.data, cnts.ctypes.data,
-                                        dlen.ctypes.data, nb))
-        except B2Error:
-            status[i] = 2
-            continue
-        bs = _B2_SIZE[info.dtype]
-        im = images[i]
-        im["scratch_off"], im["out_off"], im["block_bytes"] = scratch_pos, out_pos, info.block_bytes
-        im["format"], im["width"], im["height"], im["samples"] = info.format, info.width, info.height, info.samples
-        im["bytes_per_sample"], im["predictor"], im["planar"], im["big_endian"] = bs, info.predictor, info.planar, info.big_endian
-        im["block_w"], im["block_h"] = info.block_w, info.block_h
-        im["blocks_across"], im["blocks_down"] = info.blocks_across, info.blocks_down
-        if info.format == 2:                                   # PNG: concatenate the IDAT payloads into one zlib stream
-            total = 0
-            for o, c in zip(offs, cnts):
-                stage_parts.append(a[int(o):int(o + c)])
-                total += int(c)
-            streams.append((stage_pos, scratch_pos, total, int(info.block_bytes), 8, i))
-            stage_pos += total
-            scratch_pos += _align(info.block_bytes)
-            mask |= 2
-        else:                                                  # TIFF: the file as is, one stream per tile / strip
-            stage_parts.append(a)
-            codec = {1: 1, 5: 5, 8: 8, 32946: 8}[info.compression]
-            mask |= {1: 4, 5: 1, 8: 2}[codec]
-            for k in range(nb):
-                streams.append((stage_pos + int(offs[k]), scratch_pos + k * int(info.block_bytes), int(cnts[k]), int(dlen[k]), codec, i))
-                if codec == 1:
-                    max_raw = max(max_raw, int(dlen[k]))
-            stage_pos += a.size
-            scratch_pos += _align(nb * int(info.block_bytes))
-        out_pos += _align(info.width * info.height * info.samples * bs)
-        pad = (-stage_pos) % 16
-        if pad:
-            stage_parts.append(np.zeros(pad, np.uint8))
-            stage_pos += pad
     arrays = [None] * n
-    if not streams:
+    if n == 0:
+        return arrays, np.zeros(0, np.int32)
+    hs = _staging.setdefault(ctx.device.index, _HostStaging())
+    ptrs = (ctypes.c_void_p * n)()
+    sizes = np.zeros(n, np.uint64)
+    keep = []
+    for i, b in enumerate(blobs):
+        p, sz, k = _ptr_of(b)
+        ptrs[i], sizes[i] = p, sz
+        keep.append(k)
+    infos = (ImageInfo * n)()
+    status = np.zeros(n, dtype=np.int32)
+    images = np.zeros(n, dtype=IMAGE_DESC_DTYPE)
+    plan = DecodePlan()
+    hs.wait()                                                  # the previous batch's uploads have left the pinned buffers
+    ssz = STREAM_DESC_DTYPE.itemsize
+    for _ in range(2):
+        check(lib().b2_decode_plan_batch(ptrs, sizes.ctypes.data, n, infos, status.ctypes.data, images.ctypes.data,
+                                         hs.streams.data_ptr(), hs.streams.numel() // ssz, hs.stage.data_ptr(),
+                                         hs.stage.numel(), 0, ctypes.byref(plan)))
+        if plan.filled:
+            break
+        if hs.stage.numel() < plan.stage_bytes:
+            hs.stage = torch.empty((int(plan.stage_bytes * 1.25) + 4096,), dtype=torch.uint8).pin_memory()
+        if hs.streams.numel() // ssz < plan.n_streams:
+            hs.streams = torch.empty((int(plan.n_streams * 1.25 + 64) * ssz,), dtype=torch.uint8).pin_memory()
+    del keep
+    if plan.n_streams == 0:
         return arrays, status
-    sd = np.array(streams, dtype=STREAM_DESC_DTYPE)
-    blob_h = torch.from_numpy(np.concatenate(stage_parts)) if len(stage_parts) > 1 else torch.from_numpy(np.array(stage_parts[0]))
-    blob_d = blob_h.to(ctx.device, non_blocking=True)
-    sd_d = torch.from_numpy(sd.view(np.uint8).reshape(-1)).to(ctx.device, non_blocking=True)
-    im_d = torch.from_numpy(images.view(np.uint8).reshape(-1).copy()).to(ctx.device, non_blocking=True)
-    scratch = torch.empty((max(scratch_pos, 16),), dtype=torch.uint8, device=ctx.device)
-    out = torch.empty((max(out_pos, 16),), dtype=torch.uint8, device=ctx.device)
-    st_d = torch.from_numpy(status.copy()).to(ctx.device)
+    blob_d = hs.stage[:plan.stage_bytes].to(ctx.device, non_blocking=True)
+    sd_d = hs.streams[:plan.n_streams * ssz].to(ctx.device, non_blocking=True)
+    im_d = torch.from_numpy(images.view(np.uint8).reshape(-1)).to(ctx.device, non_blocking=True)
+    st_d = torch.from_numpy(status).to(ctx.device, non_blocking=True)
+    hs.busy = torch.cuda.Event()
+    hs.busy.record(torch.cuda.current_stream(ctx.device))
+    scratch = torch.empty((plan.scratch_bytes,), dtype=torch.uint8, device=ctx.device)
+    out = torch.empty((plan.out_bytes,), dtype=torch.uint8, device=ctx.device)
     if timings is not None:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         ev[0].record()
-    check(lib().b2_decode_streams(ctx.handle, ptr(blob_d), ptr(sd_d), len(sd), mask, max_raw, ptr(scratch), ptr(st_d), ctx.stream()))
+    check(lib().b2_decode_streams(ctx.handle, ptr(blob_d), ptr(sd_d), plan.n_streams, plan.codec_mask, plan.max_raw_len,
+                                  ptr(scratch), ptr(st_d), ctx.stream()))
     if timings is not None:
         ev[1].record()
     check(lib().b2_assemble_images(ctx.handle, ptr(scratch), ptr(im_d), images.ctypes.data, n, ptr(out), ptr(st_d), ctx.stream()))
@@ -151,11 +160,12 @@ def decode_blobs(blobs, device=None, timings=None):
         ev[2].record()
         torch.cuda.synchronize()
         timings.update(decode_ms=ev[0].elapsed_time(ev[1]), assemble_ms=ev[1].elapsed_time(ev[2]),
-                       compressed_bytes=int(sum(int(s[2]) for s in streams)), decoded_bytes=int(out_pos), streams=len(streams))
+                       compressed_bytes=int(plan.compressed_bytes), decoded_bytes=int(plan.out_bytes), streams=int(plan.n_streams))
     status = st_d.cpu().numpy()
-    for i, info in enumerate(infos):
+    for i in range(n):
         if status[i] != 0:
             continue
+        info = infos[i]
         bs = _B2_SIZE[info.dtype]
         nbytes = info.width * info.height * info.samples * bs
         o = int(images[i]["out_off"])

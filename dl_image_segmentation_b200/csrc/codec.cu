@@ -945,3 +945,125 @@ extern "C" int b2_image_blocks(const uint8_t* blob, uint64_t size, const b2_imag
     }
     return 0;
 }
+
+// ================================================================================================ host: batch planner
+// Plans the device work for a whole batch of encoded chips in one native call (header parse of every file, stream
+// and image descriptor tables, and the gather of the compressed bytes into ONE pinned staging buffer, copied by a
+// few host threads), so that the Python shim does no per-file work.  Replaces the per-file open/parse that
+// rasterio / tf.io.read_file do inside the reference's worker loop (_img_to_tf_mp.py:43-53, _img_to_tf_threaded.py:87-105).
+#include <thread>
+
+namespace {
+inline uint64_t up_to(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+struct ImgPlan {
+    uint64_t stage_off, scratch_off, out_off;
+    int stream0;
+};
+
+void fill_image(const uint8_t* blob, uint64_t size, int i, const b2_image_info& info, const ImgPlan& pl,
+                b2_stream_desc* streams, uint8_t* stage, int32_t* status) {
+    std::vector<uint64_t> offs(info.n_blocks), cnts(info.n_blocks), dlen(info.n_blocks);
+    if (b2_image_blocks(blob, size, &info, offs.data(), cnts.data(), dlen.data(), info.n_blocks) != 0) {
+        status[i] = 2;   // stream slots of this image stay codec 0 (ignored by the kernels)
+        return;
+    }
+    if (info.format == 2) {   // PNG: concatenate the IDAT payloads into one zlib stream
+        uint64_t total = 0;
+        for (int k = 0; k < info.n_blocks; k++) {
+            memcpy(stage + pl.stage_off + total, blob + offs[k], cnts[k]);
+            total += cnts[k];
+        }
+        b2_stream_desc& sd = streams[pl.stream0];
+        sd.src_off = pl.stage_off;
+        sd.dst_off = pl.scratch_off;
+        sd.src_len = (uint32_t)total;
+        sd.dst_len = (uint32_t)info.block_bytes;
+        sd.codec = CODEC_ZLIB;
+        sd.image = i;
+    } else {                  // TIFF: the file as is, one stream per tile / strip
+        memcpy(stage + pl.stage_off, blob, size);
+        const int codec = info.compression == 1 ? CODEC_RAW : (info.compression == 5 ? CODEC_LZW : CODEC_ZLIB);
+        for (int k = 0; k < info.n_blocks; k++) {
+            b2_stream_desc& sd = streams[pl.stream0 + k];
+            sd.src_off = pl.stage_off + offs[k];
+            sd.dst_off = pl.scratch_off + (uint64_t)k * info.block_bytes;
+            sd.src_len = (uint32_t)cnts[k];
+            sd.dst_len = (uint32_t)dlen[k];
+            sd.codec = codec;
+            sd.image = i;
+        }
+    }
+}
+}  // namespace
+
+extern "C" int b2_decode_plan_batch(const uint8_t* const* blobs, const uint64_t* sizes, int n, b2_image_info* infos,
+                                    int32_t* status, b2_image_desc* images, b2_stream_desc* streams, int streams_cap,
+                                    uint8_t* stage, uint64_t stage_cap, int n_threads, b2_decode_plan* plan) {
+    B2_REQUIRE(blobs && sizes && infos && status && images && plan, "b2_decode_plan_batch: NULL argument");
+    B2_REQUIRE(n >= 0, "b2_decode_plan_batch: n < 0");
+    memset(plan, 0, sizeof(*plan));
+    std::vector<ImgPlan> pl((size_t)n);
+    uint64_t stage_pos = 0, scratch_pos = 0, out_pos = 0, compressed = 0;
+    int n_streams = 0;
+    uint32_t mask = 0, max_raw = 0;
+    for (int i = 0; i < n; i++) {
+        b2_image_info& info = infos[i];
+        memset(&images[i], 0, sizeof(b2_image_desc));
+        status[i] = 0;
+        if (!blobs[i] || sizes[i] == 0) { memset(&info, 0, sizeof(info)); info.status = 2; status[i] = 2; continue; }
+        b2_image_probe(blobs[i], sizes[i], &info);
+        if (info.status != 0) { status[i] = info.status; continue; }
+        const int bs = info.dtype == B2_U8 || info.dtype == B2_I8 ? 1 : (info.dtype == B2_U16 || info.dtype == B2_I16 ? 2 : (info.dtype == B2_F64 ? 8 : 4));
+        pl[i] = ImgPlan{stage_pos, scratch_pos, out_pos, n_streams};
+        b2_image_desc& im = images[i];
+        im.scratch_off = scratch_pos;
+        im.out_off = out_pos;
+        im.block_bytes = info.block_bytes;
+        im.format = info.format; im.width = info.width; im.height = info.height; im.samples = info.samples;
+        im.bytes_per_sample = bs; im.predictor = info.predictor; im.planar = info.planar; im.big_endian = info.big_endian;
+        im.block_w = info.block_w; im.block_h = info.block_h;
+        im.blocks_across = info.blocks_across; im.blocks_down = info.blocks_down;
+        if (info.format == 2) {
+            n_streams += 1;
+            stage_pos += sizes[i];                       // upper bound of the IDAT payload bytes
+            scratch_pos += up_to(info.block_bytes, 256);
+            mask |= 2u;
+        } else {
+            n_streams += info.n_blocks;
+            stage_pos += sizes[i];
+            scratch_pos += up_to((uint64_t)info.n_blocks * info.block_bytes, 256);
+            mask |= info.compression == 1 ? 4u : (info.compression == 5 ? 1u : 2u);
+            if (info.compression == 1 && info.block_bytes > max_raw) max_raw = (uint32_t)info.block_bytes;
+        }
+        compressed += sizes[i];
+        stage_pos = up_to(stage_pos, 16);
+        out_pos += up_to((uint64_t)info.width * info.height * info.samples * bs, 256);
+    }
+    plan->stage_bytes = stage_pos + 16;
+    plan->scratch_bytes = scratch_pos + 16;
+    plan->out_bytes = out_pos + 16;
+    plan->compressed_bytes = compressed;
+    plan->n_streams = n_streams;
+    plan->codec_mask = mask;
+    plan->max_raw_len = max_raw;
+    plan->filled = 0;
+    if (!streams || !stage || streams_cap < n_streams || stage_cap < plan->stage_bytes) return 0;   // sizes only
+    memset(streams, 0, sizeof(b2_stream_desc) * (size_t)n_streams);
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    if (nt > 32) nt = 32;
+    if (nt > n) nt = n;
+    if (nt < 1) nt = 1;
+    auto work = [&](int t) {
+        for (int i = t; i < n; i += nt)
+            if (status[i] == 0) fill_image(blobs[i], sizes[i], i, infos[i], pl[i], streams, stage, status);
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    plan->filled = 1;
+    return 0;
+}

@@ -231,6 +231,26 @@ typedef struct {         /* one image to assemble from its decoded blocks       
     int32_t block_w, block_h, blocks_across, blocks_down;
 } b2_image_desc;
 
+typedef struct {
+    uint64_t stage_bytes;      /* host staging buffer needed for the compressed bytes                          */
+    uint64_t scratch_bytes;    /* device scratch for the decoded blocks                                        */
+    uint64_t out_bytes;        /* device buffer for the assembled (H,W,samples) arrays (256-byte aligned each) */
+    uint64_t compressed_bytes;
+    int32_t n_streams;
+    uint32_t codec_mask;       /* for b2_decode_streams                                                        */
+    uint32_t max_raw_len;
+    int32_t filled;            /* 1: streams / images / stage were written; 0: sizes only (buffers too small)  */
+} b2_decode_plan;
+
+/* Host-side, multi-threaded: plan the decode of a whole batch of encoded chips in ONE call — b2_image_probe +
+ * b2_image_blocks for every file, the stream and image descriptor tables, and the gather of all compressed bytes
+ * into one (pinned) staging buffer.  Replaces the per-file open / header read inside the reference's worker loop
+ * (_img_to_tf_mp.py:43-53, _img_to_tf_threaded.py:87-105).  Call with streams == NULL (or too small a capacity)
+ * to learn the sizes.  status[i] != 0 marks a file the reference would skip (:133-136); its streams are inert. */
+int b2_decode_plan_batch(const uint8_t* const* blobs, const uint64_t* sizes, int n, b2_image_info* infos_out,
+                         int32_t* status_out, b2_image_desc* images_out, b2_stream_desc* streams_out, int streams_cap,
+                         uint8_t* stage_host, uint64_t stage_cap, int n_threads, b2_decode_plan* plan);
+
 /* codec_mask: bit0 LZW, bit1 zlib, bit2 stored streams present.  status_dev (one int32 per image) must be
  * zeroed by the caller; non-zero afterwards = that image failed to decode (skip it, _img_to_tf_mp.py:133-136). */
 int b2_decode_streams(b2_ctx* ctx, const uint8_t* blob_dev, const b2_stream_desc* streams_dev, int n_streams,

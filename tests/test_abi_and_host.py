@@ -179,3 +179,54 @@ def test_two_rank_gloo_partition_and_stats(tmp_path):
     data = rng.integers(0, 65536, (8, 16, 16, 4)).astype(np.uint16)
     m, s = onorm.mean_std_from_stats(onorm.band_stats(data))
     assert r0["mean"] == m.tolist() and r0["std"] == s.tolist()
+
+
+def test_batch_decode_planner_matches_per_file_calls(lib):
+    """b2_decode_plan_batch (one native call per batch) == b2_image_probe + b2_image_blocks per file; the compressed bytes
+    land in the staging buffer where the stream table says; unreadable files are marked, their streams inert."""
+    from dl_image_segmentation_b200 import _codec
+    G = os.path.join(ROOT, "tests", "golden")
+    names = ["gdalstyle_tiled_lzw_u16x4.tif", "libpng_rgb.png", "libtiff_cv2_lzw_u16x4.tif", "libpng_label.png",
+             "libtiff_pil_deflate_u8.tif", "gdalstyle_tiled_lzw_label.tif"]
+    blobs = [open(os.path.join(G, f), "rb").read() for f in names] + [b"not an image at all", b""]
+    n = len(blobs)
+    ptrs = (ctypes.c_void_p * n)()
+    sizes = np.zeros(n, np.uint64)
+    for i, b in enumerate(blobs):
+        ptrs[i] = ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p).value
+        sizes[i] = len(b)
+    infos = (_codec.ImageInfo * n)()
+    status = np.zeros(n, np.int32)
+    images = np.zeros(n, _codec.IMAGE_DESC_DTYPE)
+    plan = _codec.DecodePlan()
+    assert lib.b2_decode_plan_batch(ptrs, sizes.ctypes.data, n, infos, status.ctypes.data, images.ctypes.data, None, 0, None, 0,
+                                    2, ctypes.byref(plan)) == 0
+    assert plan.filled == 0 and plan.n_streams > 0
+    streams = np.zeros(plan.n_streams, _codec.STREAM_DESC_DTYPE)
+    stage = np.zeros(plan.stage_bytes, np.uint8)
+    assert lib.b2_decode_plan_batch(ptrs, sizes.ctypes.data, n, infos, status.ctypes.data, images.ctypes.data,
+                                    streams.ctypes.data, len(streams), stage.ctypes.data, stage.size, 3, ctypes.byref(plan)) == 0
+    assert plan.filled == 1
+    assert list(status[-2:] != 0) == [True, True] and not status[:-2].any()
+    k = 0
+    for i, b in enumerate(blobs[:-2]):
+        info = _codec.probe(b)
+        assert (info.width, info.height, info.samples, info.n_blocks) == (infos[i].width, infos[i].height, infos[i].samples, infos[i].n_blocks)
+        nb = info.n_blocks
+        offs, cnts, dlen = (np.zeros(nb, np.uint64) for _ in range(3))
+        a = np.frombuffer(b, np.uint8)
+        assert lib.b2_image_blocks(a.ctypes.data, a.size, ctypes.byref(info), offs.ctypes.data, cnts.ctypes.data, dlen.ctypes.data, nb) == 0
+        if info.format == 2:
+            sd = streams[k]
+            want = b"".join(b[int(o):int(o + c)] for o, c in zip(offs, cnts))
+            assert bytes(stage[int(sd["src_off"]):int(sd["src_off"]) + int(sd["src_len"])]) == want
+            assert (int(sd["codec"]), int(sd["image"]), int(sd["dst_len"])) == (8, i, int(info.block_bytes))
+            k += 1
+        else:
+            for j in range(nb):
+                sd = streams[k + j]
+                assert bytes(stage[int(sd["src_off"]):int(sd["src_off"]) + int(sd["src_len"])]) == b[int(offs[j]):int(offs[j] + cnts[j])]
+                assert int(sd["dst_len"]) == int(dlen[j]) and int(sd["image"]) == i
+                assert int(sd["dst_off"]) == int(images[i]["scratch_off"]) + j * int(info.block_bytes)
+            k += nb
+    assert k == plan.n_streams
