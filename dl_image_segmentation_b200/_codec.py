@@ -101,7 +101,7 @@ def _ptr_of(blob):
     return a.ctypes.data, a.size, a
 
 
-def decode_blobs(blobs, device=None, timings=None):
+def decode_blobs(blobs, device=None, timings=None, want_infos=False):
     """Decode a batch of encoded chips on the GPU.
 
     blobs: list of bytes / uint8 arrays (host).  Returns (arrays, status): arrays[i] is an (H,W,bands) CUDA
@@ -112,7 +112,7 @@ def decode_blobs(blobs, device=None, timings=None):
     n = len(blobs)
     arrays = [None] * n
     if n == 0:
-        return arrays, np.zeros(0, np.int32)
+        return (arrays, np.zeros(0, np.int32), []) if want_infos else (arrays, np.zeros(0, np.int32))
     hs = _staging.setdefault(ctx.device.index, _HostStaging())
     ptrs = (ctypes.c_void_p * n)()
     sizes = np.zeros(n, np.uint64)
@@ -139,7 +139,7 @@ def decode_blobs(blobs, device=None, timings=None):
             hs.streams = torch.empty((int(plan.n_streams * 1.25 + 64) * ssz,), dtype=torch.uint8).pin_memory()
     del keep
     if plan.n_streams == 0:
-        return arrays, status
+        return (arrays, status, infos) if want_infos else (arrays, status)
     blob_d = hs.stage[:plan.stage_bytes].to(ctx.device, non_blocking=True)
     sd_d = hs.streams[:plan.n_streams * ssz].to(ctx.device, non_blocking=True)
     im_d = torch.from_numpy(images.view(np.uint8).reshape(-1)).to(ctx.device, non_blocking=True)
@@ -170,7 +170,28 @@ def decode_blobs(blobs, device=None, timings=None):
         nbytes = info.width * info.height * info.samples * bs
         o = int(images[i]["out_off"])
         arrays[i] = out[o:o + nbytes].view(_B2_TO_TORCH[info.dtype]).view(info.height, info.width, info.samples)
-    return arrays, status
+    return (arrays, status, infos) if want_infos else (arrays, status)
+
+
+def probe_blobs(blobs):
+    """Header-only pass over a batch (one native call): list of ImageInfo, status != 0 for unreadable files."""
+    n = len(blobs)
+    if n == 0:
+        return []
+    ptrs = (ctypes.c_void_p * n)()
+    sizes = np.zeros(n, np.uint64)
+    keep = []
+    for i, b in enumerate(blobs):
+        p, sz, k = _ptr_of(b)
+        ptrs[i], sizes[i] = p, sz
+        keep.append(k)
+    infos = (ImageInfo * n)()
+    status = np.zeros(n, dtype=np.int32)
+    images = np.zeros(n, dtype=IMAGE_DESC_DTYPE)
+    plan = DecodePlan()
+    check(lib().b2_decode_plan_batch(ptrs, sizes.ctypes.data, n, infos, status.ctypes.data, images.ctypes.data, None, 0, None, 0,
+                                     1, ctypes.byref(plan)))
+    return infos
 
 
 def to_float32(t):

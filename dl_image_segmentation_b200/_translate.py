@@ -39,27 +39,37 @@ class ChipError(Exception):
     pass
 
 
-def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, device=None):
+def _read_or_error(path):
+    try:
+        return _read(path)
+    except Exception as e:                                                  # unreadable file: the reference skips the chip
+        return e
+
+
+def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, device=None, blobs=None):
     """Read + (optionally) decode a batch of chip pairs.  Returns one entry per pair: a dict ready for
-    ops.build_records, or the Exception that makes the reference skip the chip."""
+    ops.build_records, or the Exception that makes the reference skip the chip.  `blobs` = the 2n file contents
+    (image, label, image, label, ...) when the caller has already read them (run_worker prefetches on threads)."""
     ctx = get_ctx(device)
     n = len(img_paths)
-    blobs, errs = [], [None] * n
-    for i in range(n):
-        try:
-            blobs += [_read(img_paths[i]), _read(lbl_paths[i])]
-        except Exception as e:                                              # unreadable file
-            errs[i] = e
-            blobs += [b"", b""]
-    infos = [_codec.probe(b) if b else None for b in blobs]
+    if blobs is None:
+        blobs = []
+        for i in range(n):
+            blobs += [_read_or_error(img_paths[i]), _read_or_error(lbl_paths[i])]
+    errs = [None] * n
+    for k, b in enumerate(blobs):
+        if isinstance(b, Exception):
+            if errs[k // 2] is None:
+                errs[k // 2] = b
+            blobs[k] = b""
     arrays = [None] * (2 * n)
-    if store_as_array:
-        live = [k for k in range(2 * n) if blobs[k] and infos[k].status == 0]
-        dec, st = _codec.decode_blobs([blobs[k] for k in live], device=ctx.device)
-        for k, a, s in zip(live, dec, st):
-            arrays[k] = a
-            if s != 0 and errs[k // 2] is None:
-                errs[k // 2] = ChipError("could not decode %s (codec status %d)" % ((img_paths, lbl_paths)[k % 2][k // 2], int(s)))
+    if store_as_array:                                                      # ONE native planning call + the decode kernels
+        arrays, st, infos = _codec.decode_blobs(blobs, device=ctx.device, want_infos=True)
+        for k in range(2 * n):
+            if blobs[k] and infos[k].status == 0 and st[k] != 0 and errs[k // 2] is None:
+                errs[k // 2] = ChipError("could not decode %s (codec status %d)" % ((img_paths, lbl_paths)[k % 2][k // 2], int(st[k])))
+    else:
+        infos = _codec.probe_blobs(blobs)
     out = []
     for i in range(n):
         if errs[i] is not None:
@@ -67,8 +77,8 @@ def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, devi
             continue
         ii, li = infos[2 * i], infos[2 * i + 1]
         try:
-            for info, p in ((ii, img_paths[i]), (li, lbl_paths[i])):
-                if info is None or info.status != 0:
+            for info, p, b in ((ii, img_paths[i], blobs[2 * i]), (li, lbl_paths[i], blobs[2 * i + 1])):
+                if not b or info.status != 0:
                     raise ChipError("'%s' not recognized as a supported file format." % p)
             if validate is not None:
                 validate(ii)
@@ -90,7 +100,11 @@ def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, devi
 
 
 def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_directory, num_shards, key_fn,
-               store_as_array, label="process", progress_every=100, validate=None, device=None, batch_pairs=64):
+               store_as_array, label="process", progress_every=100, validate=None, device=None, batch_pairs=None,
+               io_threads=8):
+    """The reference's worker loop, restructured as a three-stage pipeline: a thread pool reads the files of batch
+    k+1 while the GPU decodes and serialises batch k and a writer thread appends batch k-1 to the shard file."""
+    from concurrent.futures import ThreadPoolExecutor
     num_workers = len(ranges)
     assert not num_shards % num_workers
     per = int(num_shards / num_workers)
@@ -98,35 +112,98 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
     num_files = ranges[worker_index][1] - ranges[worker_index][0]
     ctx = get_ctx(device)
     counter = 0
+    os.makedirs(output_directory, exist_ok=True)
+    if batch_pairs is None:
+        # the entropy decoders run one warp per compressed stream and are latency-bound: a batch should carry a few
+        # thousand streams, but not more than ~1 GB of file bytes (pinned staging) — sized from the first pair
+        try:
+            pair_bytes = os.path.getsize(img_filenames[ranges[worker_index][0]]) + os.path.getsize(lbl_filenames[ranges[worker_index][0]])
+        except (OSError, IndexError):
+            pair_bytes = 1 << 20
+        batch_pairs = int(max(32, min(2048, (768 << 20) // max(1, pair_bytes))))
+    n_slots = 3
+    pinned = [None] * n_slots                                               # rotating pinned write-back buffers
+    slot_futs = [[] for _ in range(n_slots)]                                # positional writes still reading a buffer
+    # the work list: (shard, [file indices]) in shard order, batches never straddle a shard
+    batches = []
     for s in range(per):
-        shard = worker_index * per + s
-        output_file = os.path.join(output_directory, "%s-%.5d-of-%.5d" % (name, shard, num_shards))
-        os.makedirs(output_directory, exist_ok=True)
-        shard_counter = 0
         lo, hi = int(shard_ranges[s]), int(shard_ranges[s + 1])
-        with open(output_file, "wb") as f:
-            for b0 in range(lo, hi, batch_pairs):
-                idx = list(range(b0, min(b0 + batch_pairs, hi)))
-                pairs = load_pairs([img_filenames[i] for i in idx], [lbl_filenames[i] for i in idx], store_as_array,
-                                   key_fn, validate, ctx.device)
-                items = []
-                for i, p in zip(idx, pairs):
-                    if isinstance(p, Exception):
-                        print(p)
-                        print("SKIPPED: Unexpected eror while decoding %s." % img_filenames[i])
-                        continue
-                    items.append(p)
-                    shard_counter += 1
-                    counter += 1
-                    if not counter % progress_every:
-                        print("%s [%s %d]: Processed %d of %d images in %s batch." %
-                              (datetime.now(), label, worker_index, counter, num_files, label))
-                        sys.stdout.flush()
-                if items:
-                    buf, _, total = ops.build_records(items, ctx.device)
-                    f.write(buf[:total].cpu().numpy().tobytes())
-        print("%s [%s %d]: Wrote %d images to %s" % (datetime.now(), label, worker_index, shard_counter, output_file))
-        sys.stdout.flush()
+        if lo == hi:
+            batches.append((s, []))
+        for b0 in range(lo, hi, batch_pairs):
+            batches.append((s, list(range(b0, min(b0 + batch_pairs, hi)))))
+    open_files = []
+    with ThreadPoolExecutor(max_workers=max(1, io_threads)) as pool, ThreadPoolExecutor(max_workers=1) as writer, \
+            ThreadPoolExecutor(max_workers=8) as wpool:
+        def submit_reads(idx):
+            paths = []
+            for i in idx:
+                paths += [img_filenames[i], lbl_filenames[i]]
+            return [pool.submit(_read_or_error, p) for p in paths]
+        pending_reads = submit_reads(batches[0][1]) if batches else []
+        cur_file, cur_shard, shard_counter, cur_off = None, -1, 0, 0
+
+        def finish_shard():
+            nonlocal cur_file
+            if cur_file is not None:
+                print("%s [%s %d]: Wrote %d images to %s" % (datetime.now(), label, worker_index, shard_counter, cur_file.name))
+                sys.stdout.flush()
+                cur_file = None                                              # closed after its last positional write
+
+        for bi, (s, idx) in enumerate(batches):
+            blobs = [f.result() for f in pending_reads]
+            pending_reads = submit_reads(batches[bi + 1][1]) if bi + 1 < len(batches) else []
+            if s != cur_shard:
+                finish_shard()
+                shard = worker_index * per + s
+                cur_file = open(os.path.join(output_directory, "%s-%.5d-of-%.5d" % (name, shard, num_shards)), "wb")
+                open_files.append(cur_file)
+                cur_shard, shard_counter, cur_off = s, 0, 0
+            if not idx:
+                continue
+            pairs = load_pairs([img_filenames[i] for i in idx], [lbl_filenames[i] for i in idx], store_as_array,
+                               key_fn, validate, ctx.device, blobs=blobs)
+            items = []
+            for i, p in zip(idx, pairs):
+                if isinstance(p, Exception):
+                    print(p)
+                    print("SKIPPED: Unexpected eror while decoding %s." % img_filenames[i])
+                    continue
+                items.append(p)
+                shard_counter += 1
+                counter += 1
+                if not counter % progress_every:
+                    print("%s [%s %d]: Processed %d of %d images in %s batch." %
+                          (datetime.now(), label, worker_index, counter, num_files, label))
+                    sys.stdout.flush()
+            if items:
+                buf, _, total = ops.build_records(items, ctx.device)
+                slot = bi % n_slots
+                for x in slot_futs[slot]:                                    # the writes that last used this buffer
+                    for y in x.result():
+                        y.result()
+                slot_futs[slot] = []
+                if pinned[slot] is None or pinned[slot].numel() < total:
+                    pinned[slot] = torch.empty((int(total * 1.1) + 4096,), dtype=torch.uint8).pin_memory()
+                host = pinned[slot][:total]
+                host.copy_(buf[:total], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream(ctx.device))
+
+                def _write(fd=cur_file.fileno(), h=host, ev=done, off=cur_off):
+                    ev.synchronize()                                         # the records have arrived in pinned memory
+                    mv = memoryview(h.numpy())
+                    step = 16 << 20                                          # positional writes: order-free, several in flight
+                    return [wpool.submit(os.pwrite, fd, mv[o:o + step], off + o) for o in range(0, len(mv), step)]
+                cur_off += total
+                slot_futs[slot].append(writer.submit(_write))
+        finish_shard()
+        for fl in slot_futs:
+            for x in fl:
+                for y in x.result():
+                    y.result()
+    for f in open_files:
+        f.close()
     print("%s [%s %d]: Wrote %d images to %d shards." % (datetime.now(), label, worker_index, counter, per))
     sys.stdout.flush()
     return counter
