@@ -38,12 +38,15 @@
 #ifndef B2_HOT_BLOCKS
 #define B2_HOT_BLOCKS 2
 #endif
+#ifndef B2_HOT_LABELS
+#define B2_HOT_LABELS 64
+#endif
 
 namespace b2 {
 
 constexpr int kBufBytes = kTile + 128;   // tile + 32-byte halo, rounded so the second buffer stays 128-byte aligned
 constexpr int kHotMaxK = 32;             // one-hot through shared-memory blocks + bulk stores up to this many classes
-constexpr int kHotLabels = 64;           // labels per warp block (two per lane): one bulk store moves 256*K bytes
+constexpr int kHotLabels = B2_HOT_LABELS;  // labels per warp block (one or two per lane): one bulk store moves 4*K bytes per label
 constexpr int kHotBlocks = B2_HOT_BLOCKS;            // blocks per warp: the bulk store of one overlaps the fill of the other
 constexpr int kStages = B2_STAGES;               // tile buffers in the producer -> consumer ring
 constexpr int kConsumerWarps = kTileThreads / 32;
@@ -115,19 +118,59 @@ __device__ __forceinline__ uint32_t tile_power(const CrcTables* tab, uint32_t j)
     return j < 2048 ? __ldg(&tab->tpow[j]) : xpow8(tab, (uint64_t)j * kTile);
 }
 
-// thread 0: describe tile w and start its copy into buf
+// What the producer knows about the record it is currently cutting into tiles.  Consecutive tiles almost always
+// belong to the same record, so the table lookups (tile -> record -> offsets -> feature index: three dependent
+// L2 round trips) are paid once per record, not once per tile.
+struct RecCache {
+    uint32_t r, t0, nt, flags;     // record, its first tile, its tile count, 2 = sinks may run
+    uint64_t d0, len;
+    uint64_t img_off, img_len, tgt_off, tgt_len;
+};
+
 template <int kMode>
-__device__ __forceinline__ void make_job(const ParseArgs& a, uint32_t w, TileJob* j, uint8_t* buf, uint64_t* bar) {
-    uint32_t r, tile;
+__device__ __forceinline__ void rec_lookup(const ParseArgs& a, uint32_t w, RecCache& c) {
+    uint32_t r;
     if (a.tile2rec) {
+        if (c.r != 0xFFFFFFFFu && w - c.t0 < c.nt) return;               // still inside the cached record
         r = a.tile2rec[w];
-        tile = w - a.tile_start[r];
+        c.t0 = a.tile_start[r];
     } else {
         r = w / a.tiles_x;
-        tile = w - r * a.tiles_x;
+        if (r == c.r) return;
+        c.t0 = r * a.tiles_x;
     }
-    const uint64_t d0 = a.rec_off[r], len = a.rec_len[r];
-    const uint32_t nt = record_tiles(d0, len);
+    c.r = r;
+    c.d0 = a.rec_off[r];
+    c.len = a.rec_len[r];
+    c.nt = record_tiles(c.d0, c.len);
+    c.flags = 0;
+    c.img_off = c.img_len = c.tgt_off = c.tgt_len = 0;
+    if (kMode != B2_SINK_NONE && a.index != nullptr) {
+        const b2_example_index* ix = a.index + r;
+        bool ok = ix->status == 0;
+        const uint64_t il = ix->img_len, tl = ix->tgt_len;
+        if (kMode == B2_SINK_RAW) ok = ok && il <= a.sink.img_stride && tl <= a.sink.tgt_stride;
+        if (kMode == B2_SINK_NORM_ONEHOT) {
+            const uint64_t K = (uint64_t)a.sink.num_classes;
+            ok = ok && ix->img_kind == 1 && ix->tgt_kind == 1 && il * 4 <= a.sink.img_stride && tl * K * 4 <= a.sink.tgt_stride &&
+                 il < (1ull << 31) && tl * K < (1ull << 31);
+        }
+        if (ok) {
+            c.flags = 2;
+            c.img_off = ix->img_off;
+            c.img_len = il;
+            c.tgt_off = ix->tgt_off;
+            c.tgt_len = tl;
+        }
+    }
+}
+
+// producer: describe tile w and start its copy into buf
+template <int kMode>
+__device__ __forceinline__ void make_job(const ParseArgs& a, uint32_t w, RecCache& c, TileJob* j, uint8_t* buf, uint64_t* bar) {
+    rec_lookup<kMode>(a, w, c);
+    const uint32_t r = c.r, tile = w - c.t0, nt = c.nt;
+    const uint64_t d0 = c.d0, len = c.len;
     j->r = r;
     j->tile = tile;
     j->nt = nt;
@@ -140,27 +183,11 @@ __device__ __forceinline__ void make_job(const ParseArgs& a, uint32_t w, TileJob
     j->ts = ts;
     j->d0 = d0;
     j->d1 = d1;
-    uint32_t flags = 1;
-    j->img_off = j->img_len = j->tgt_off = j->tgt_len = 0;
-    if (kMode != B2_SINK_NONE && a.index != nullptr) {
-        const b2_example_index* ix = a.index + r;
-        bool ok = ix->status == 0;
-        const uint64_t il = ix->img_len, tl = ix->tgt_len;
-        if (kMode == B2_SINK_RAW) ok = ok && il <= a.sink.img_stride && tl <= a.sink.tgt_stride;
-        if (kMode == B2_SINK_NORM_ONEHOT) {
-            const uint64_t K = (uint64_t)a.sink.num_classes;
-            ok = ok && ix->img_kind == 1 && ix->tgt_kind == 1 && il * 4 <= a.sink.img_stride && tl * K * 4 <= a.sink.tgt_stride &&
-                 il < (1ull << 31) && tl * K < (1ull << 31);
-        }
-        if (ok) {
-            flags |= 2;
-            j->img_off = ix->img_off;
-            j->img_len = il;
-            j->tgt_off = ix->tgt_off;
-            j->tgt_len = tl;
-        }
-    }
-    j->flags = flags;
+    j->img_off = c.img_off;
+    j->img_len = c.img_len;
+    j->tgt_off = c.tgt_off;
+    j->tgt_len = c.tgt_len;
+    j->flags = 1 | c.flags;
     // bytes to stage: [ts, min(te + 32, d1)), never touching shard[lim...]
     const uint64_t lim = a.nbytes != ~0ull ? a.nbytes : d1;
     uint64_t want = (d1 + 15) & ~15ull;
@@ -447,6 +474,9 @@ fused_parse_kernel(const ParseArgs a) {
         // ------------------------------------------------------------------------------------------ producer
         if (lane != 0) return;
         uint32_t feed_w = 0, feed_left = 0;
+        RecCache rc;
+        rc.r = 0xFFFFFFFFu;
+        rc.t0 = rc.nt = 0;
         for (uint32_t it = 0;; it++) {
             const uint32_t slot = it % kStages, use = it / kStages;
             if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
@@ -460,7 +490,7 @@ fused_parse_kernel(const ParseArgs a) {
                 feed_w = (uint32_t)w;
                 feed_left = (uint32_t)(total - w < a.q ? total - w : a.q);
             }
-            make_job<kMode>(a, feed_w, &job[slot], dyn + slot * kBufBytes, &full[slot]);
+            make_job<kMode>(a, feed_w, rc, &job[slot], dyn + slot * kBufBytes, &full[slot]);
             feed_w++;
             feed_left--;
         }
@@ -594,15 +624,16 @@ fused_parse_kernel(const ParseArgs a) {
                             __syncwarp();
                             hot[hb ? slotB0 : slotA0] = 0.0f;
                             hot[hb ? slotB1 : slotA1] = 0.0f;
-                            const uint32_t l0 = L0 + 2 * lane;
+                            constexpr uint32_t kPerLane = kHotLabels / 32;
+                            const uint32_t l0 = L0 + kPerLane * lane;
                             uint32_t slot0 = hot_dummy, slot1 = hot_dummy;
                             if (l0 < L_end) {
                                 const uint32_t lab = buf8[base + l0];
-                                if (lab < (uint32_t)K) slot0 = (2 * lane) * K + lab;
+                                if (lab < (uint32_t)K) slot0 = (kPerLane * lane) * K + lab;
                             }
-                            if (l0 + 1 < L_end) {
+                            if (kPerLane > 1 && l0 + 1 < L_end) {
                                 const uint32_t lab = buf8[base + l0 + 1];
-                                if (lab < (uint32_t)K) slot1 = (2 * lane + 1) * K + lab;
+                                if (lab < (uint32_t)K) slot1 = (kPerLane * lane + 1) * K + lab;
                             }
                             hot[slot0] = 1.0f;
                             hot[slot1] = 1.0f;

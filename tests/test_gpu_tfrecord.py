@@ -403,3 +403,46 @@ def test_scan_tiny_and_truncated_shards(dev):
         assert (n, status) == want, cut
     st = ops.open_shard_async(shard, dev, max_records=16)
     assert st.header()[:2] == (4, 0)
+
+
+def test_captured_pass_graph_replay(dev):
+    """A whole pass recorded as one CUDA graph (uploads from pinned memory included) replays to the oracle's values,
+    and a replay after the host data changed parses the NEW bytes (the graph holds addresses, not data)."""
+    import torch
+
+    from dl_image_segmentation_b200 import ops
+    size, K, n = 20, 6, 7
+    mean = np.array([90.0, 100.0, 110.0], np.float32)
+    std = np.array([40.0, 50.0, 60.0], np.float32)
+    shards, chips = [], []
+    for s in range(5):
+        sh, _, ch = _small_shard(n, size, seed=300 + s, K=K)
+        shards.append(sh)
+        chips.append(ch)
+    host = [torch.from_numpy(np.frombuffer(s, np.uint8).copy()).pin_memory() for s in shards]
+    pipe = ops.ShardPipeline("norm_onehot", size * size * 3, size * size, max_records=8, mean=mean, std=std,
+                             num_classes=K, device=dev, depth=2, open_ahead=3)
+    seen = []
+
+    def consume(img, tgt, status, table):
+        seen.append((img[:n].clone(), tgt[:n].clone(), status[:n].clone(), table.hdr_dev.clone()))
+        return len(seen) - 1
+    cp = ops.CapturedPass(pipe, host, consume)
+    del seen[:len(seen) - len(shards)]                     # keep the tensors created during the capture
+    for rep in range(2):
+        if rep == 1:                                       # new data behind the same pinned addresses
+            order = [3, 4, 0, 1, 2]
+            new = [bytes(host[k].numpy()) for k in order]
+            for h, b in zip(host, new):
+                h.copy_(torch.from_numpy(np.frombuffer(b, np.uint8).copy()))
+            chips = [chips[k] for k in order]
+        cp.replay()
+        torch.cuda.synchronize()
+        for s, (gi, gt, st, hdr) in enumerate(seen):
+            assert int(hdr[0]) == n and int(hdr[1]) == 0 and int(hdr[4]) == 0
+            assert not st.cpu().numpy().any()
+            wi = onorm.normalise(np.stack([c[0] for c in chips[s]]), mean, std)
+            wt = onorm.one_hot(np.stack([c[1] for c in chips[s]]), K)
+            np.testing.assert_array_equal(gi.cpu().numpy().reshape(wi.shape), wi)
+            np.testing.assert_array_equal(gt.cpu().numpy().reshape(wt.shape), wt)
+    assert cp.launches_per_replay == 3 * len(shards)

@@ -42,3 +42,19 @@ for grid in (148 * 3, 148 * 4):
             print(json.dumps({"probe": "bulk-store pattern (label tiles)", "grid": grid, "chunk": chunk, "chunks_per_region": per_region,
                               "mode": {1: "1 in flight", 2: "2 in flight", 10: "2 in flight + smem writes + proxy fence"}[depth],
                               "GB/s": round(N / ms / 1e6, 1)}))
+
+if os.environ.get("MB_MIX"):
+    nrec = 250
+    tin = torch.randint(0, 10, (nrec * 32 * 8192,), dtype=torch.uint8, device=dev)
+    outs = [(torch.empty((nrec * 24 * 32768,), dtype=torch.uint8, device=dev), torch.empty((nrec * 8 * 327680,), dtype=torch.uint8, device=dev)) for _ in range(4)]
+    tins = [tin.clone() for _ in range(4)]
+    it = [0]
+    def mix(grid):
+        k = it[0] % 4; it[0] += 1
+        L.mb_mix(ctypes.c_void_p(tins[k].data_ptr()), ctypes.c_void_p(outs[k][0].data_ptr()), ctypes.c_void_p(outs[k][1].data_ptr()), nrec,
+                 ctypes.c_void_p(ctr.data_ptr()), grid, st)
+    total = nrec * (32 * 8192 + 24 * 32768 + 8 * 327680)
+    for grid in (148 * 2, 148 * 3, 148 * 4):
+        ms = t(lambda: mix(grid), it=12)
+        print(json.dumps({"probe": "fused-parse traffic without arithmetic (TMA tile loads + float4 stores + bulk stores)", "grid": grid,
+                          "ms_per_250_records": round(ms, 4), "GB/s": round(total / ms / 1e6, 1)}))
