@@ -65,7 +65,7 @@ SIGNATURES = {
     "b2_debug_parse_phases": (_i, [_vp, ctypes.POINTER(_u64)]),
     "b2_median_composite_u16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "b2_nearest_date_mosaic": (_i, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f, _i, _i, _i, _i, _i, _i,
-                                    _vp, _vp, _vp, _vp, _vp]),
+                                    _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2_normalise_onehot": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _u64, _i, _i, _vp, _vp, _vp]),
     "b2_band_stats": (_i, [_vp, _vp, _i, _vp, _u64, _i, _vp, _vp]),
     "b2_crc32c": (_i, [_vp, _vp, _vp, _vp, _i, _u64, _vp, _vp]),

@@ -231,13 +231,16 @@ static bool dispatch_median(int P, const uint16_t* stack, const uint8_t* valid, 
 // Main loop: one thread per pixel walks `order`, probing one validity byte per scene (coalesced across
 // the warp) and stops at the first valid scene; only that scene's pixel is read.  Filtered-out scenes
 // are never touched, so the kernel moves far fewer bytes than the dense T-deep definition.
-template <int PB>  // bytes per pixel (all bands), 0 = runtime
+// kStats = element size (1 or 2 bytes) when the exact integer band statistics {n, sum x, sum x^2 lo16, sum x^2 hi} of the
+// valid output pixels are accumulated in the same pass (B = PB / kStats <= 4 bands); 0 = no statistics.  Fusing them
+// saves the separate statistics pass its re-read of the whole output.
+template <int PB, int kStats = 0>  // PB = bytes per pixel (all bands), 0 = runtime
 __global__ void __launch_bounds__(256)
 mosaic_kernel(const void* const* __restrict__ stacks, const uint8_t* const* __restrict__ valids,
               const int32_t* __restrict__ scene_day, const float* __restrict__ scene_cf, int32_t ref_day,
               int32_t min_day, int32_t max_day, float max_cf, int T, uint32_t hw, int pb_runtime,
               uint8_t* __restrict__ out, uint8_t* __restrict__ out_mask, int16_t* __restrict__ src_index,
-              int32_t* __restrict__ n_eligible) {
+              int32_t* __restrict__ n_eligible, unsigned long long* __restrict__ stats) {
     extern __shared__ int32_t sm[];  // key[T], order[T], n
     int32_t* key = sm;
     int32_t* order = sm + T;
@@ -272,6 +275,10 @@ mosaic_kernel(const void* const* __restrict__ stacks, const uint8_t* const* __re
     if (n_eligible && blockIdx.x == 0 && threadIdx.x == 0) n_eligible[chip] = ne;
     const uint8_t* vchip = valids[chip];
     const uint8_t* schip = static_cast<const uint8_t*>(stacks[chip]);
+    constexpr int kSB = kStats ? PB / (kStats ? kStats : 1) : 1;   // bands with fused statistics
+    unsigned long long st_n = 0, st_s[kSB], st_q[kSB];
+#pragma unroll
+    for (int b = 0; b < kSB; b++) st_s[b] = st_q[b] = 0;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
         int sel = -1;
         for (int k = 0; k < ne; k++) {
@@ -283,23 +290,73 @@ mosaic_kernel(const void* const* __restrict__ stacks, const uint8_t* const* __re
         }
         uint8_t* o = out + ((size_t)chip * hw + p) * pb;
         const uint8_t* s = schip + ((size_t)(sel < 0 ? 0 : sel) * hw + p) * pb;
+        uint32_t w[4] = {0, 0, 0, 0};                              // the pixel's bytes (fast paths), for the statistics
         if (PB == 16) {
             uint4 v = sel < 0 ? make_uint4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uint4*>(s));
             *reinterpret_cast<uint4*>(o) = v;
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
         } else if (PB == 8) {
             uint2 v = sel < 0 ? make_uint2(0, 0) : __ldg(reinterpret_cast<const uint2*>(s));
             *reinterpret_cast<uint2*>(o) = v;
+            w[0] = v.x; w[1] = v.y;
         } else if (PB == 4) {
             uint32_t v = sel < 0 ? 0u : __ldg(reinterpret_cast<const uint32_t*>(s));
             *reinterpret_cast<uint32_t*>(o) = v;
+            w[0] = v;
         } else if (PB == 2) {
             uint16_t v = sel < 0 ? (uint16_t)0 : __ldg(reinterpret_cast<const uint16_t*>(s));
             *reinterpret_cast<uint16_t*>(o) = v;
+            w[0] = v;
         } else {
             for (int i = 0; i < pb; i++) o[i] = sel < 0 ? (uint8_t)0 : s[i];
         }
         out_mask[(size_t)chip * hw + p] = sel < 0;
         if (src_index) src_index[(size_t)chip * hw + p] = (int16_t)sel;
+        if (kStats && sel >= 0) {
+            st_n++;
+#pragma unroll
+            for (int b = 0; b < kSB; b++) {
+                const unsigned long long x = kStats == 2 ? ((w[b >> 1] >> (16 * (b & 1))) & 0xFFFFu) : ((w[b >> 2] >> (8 * (b & 3))) & 0xFFu);
+                st_s[b] += x;
+                st_q[b] += x * x;
+            }
+        }
+    }
+    if (kStats) {   // warp shuffle -> shared memory -> one 64-bit atomic per (CTA, band, counter)
+        __shared__ unsigned long long red[8][2 * kSB + 1];
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) st_n += __shfl_xor_sync(0xffffffffu, st_n, o);
+        if (lane == 0) red[wid][2 * kSB] = st_n;
+#pragma unroll
+        for (int b = 0; b < kSB; b++) {
+            unsigned long long sv = st_s[b], qv = st_q[b];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                sv += __shfl_xor_sync(0xffffffffu, sv, o);
+                qv += __shfl_xor_sync(0xffffffffu, qv, o);
+            }
+            if (lane == 0) {
+                red[wid][b] = sv;
+                red[wid][kSB + b] = qv;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < kSB) {
+            const int b = threadIdx.x;
+            unsigned long long n = 0, sv = 0, qv = 0;
+            for (int k = 0; k < 8; k++) {
+                n += red[k][2 * kSB];
+                sv += red[k][b];
+                qv += red[k][kSB + b];
+            }
+            if (n) {
+                atomicAdd(stats + 4 * b + 0, n);
+                atomicAdd(stats + 4 * b + 1, sv);
+                atomicAdd(stats + 4 * b + 2, qv & 0xFFFFull);
+                atomicAdd(stats + 4 * b + 3, qv >> 16);
+            }
+        }
     }
 }
 
@@ -334,7 +391,7 @@ extern "C" int b2_nearest_date_mosaic(b2_ctx* ctx, const void* const* stacks, co
                                       const int32_t* scene_day, const float* scene_cf, int32_t ref_day,
                                       int32_t min_day, int32_t max_day, float max_cf, int n_chips, int T, int H,
                                       int W, int B, int elem_bytes, void* out, uint8_t* out_mask,
-                                      int16_t* src_index, int32_t* n_eligible, b2_stream stream) {
+                                      int16_t* src_index, int32_t* n_eligible, uint64_t* stats_acc, b2_stream stream) {
     B2_REQUIRE(ctx && stacks && valids && scene_day && scene_cf && out && out_mask, "b2_nearest_date_mosaic: NULL argument");
     B2_REQUIRE(n_chips >= 1 && n_chips <= 65535, "b2_nearest_date_mosaic: n_chips must be in [1,65535] per call");
     B2_REQUIRE(T >= 1 && T <= 4096 && H >= 1 && W >= 1 && B >= 1, "b2_nearest_date_mosaic: bad T/H/W/B");
@@ -354,13 +411,29 @@ extern "C" int b2_nearest_date_mosaic(b2_ctx* ctx, const void* const* stacks, co
     const bool al = reinterpret_cast<uintptr_t>(out) % 16 == 0;  // per-chip stack alignment is the caller's contract
 #define B2_MOSAIC(PBV)                                                                                              \
     mosaic_kernel<PBV><<<grid, 256, smem, s>>>(stacks, valids, scene_day, scene_cf, ref_day, min_day, max_day, max_cf, \
-                                               T, hw, pb, static_cast<uint8_t*>(out), out_mask, src_index, n_eligible)
+                                               T, hw, pb, static_cast<uint8_t*>(out), out_mask, src_index, n_eligible, nullptr)
+#define B2_MOSAIC_STATS(PBV, EB)                                                                                    \
+    mosaic_kernel<PBV, EB><<<grid, 256, smem, s>>>(stacks, valids, scene_day, scene_cf, ref_day, min_day, max_day,  \
+                                                   max_cf, T, hw, pb, static_cast<uint8_t*>(out), out_mask, src_index, \
+                                                   n_eligible, reinterpret_cast<unsigned long long*>(stats_acc))
+    if (stats_acc) {
+        B2_REQUIRE(al && (elem_bytes == 1 || elem_bytes == 2) && B <= 4 && (pb == 2 || pb == 4 || pb == 8),
+                   "b2_nearest_date_mosaic: fused statistics need uint8 / uint16 chips of at most 4 bands, 2-, 4- or "
+                   "8-byte pixels and a 16-byte aligned output (use b2_band_stats otherwise)");
+        if (pb == 8 && elem_bytes == 2) B2_MOSAIC_STATS(8, 2);
+        else if (pb == 4 && elem_bytes == 2) B2_MOSAIC_STATS(4, 2);
+        else if (pb == 2 && elem_bytes == 2) B2_MOSAIC_STATS(2, 2);
+        else if (pb == 4 && elem_bytes == 1) B2_MOSAIC_STATS(4, 1);
+        else if (pb == 2 && elem_bytes == 1) B2_MOSAIC_STATS(2, 1);
+        else return fail("b2_nearest_date_mosaic: fused statistics: unsupported pixel layout");
+    } else
     if (al && pb == 16) B2_MOSAIC(16);
     else if (al && pb == 8) B2_MOSAIC(8);
     else if (al && pb == 4) B2_MOSAIC(4);
     else if (al && pb == 2) B2_MOSAIC(2);
     else B2_MOSAIC(0);
 #undef B2_MOSAIC
+#undef B2_MOSAIC_STATS
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;

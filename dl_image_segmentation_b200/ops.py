@@ -83,12 +83,13 @@ _I32_MIN, _I32_MAX = -(1 << 31), (1 << 31) - 1
 
 
 def nearest_date_mosaic(stacks, valids, scene_day, scene_cf, ref_day, min_day=None, max_day=None, max_cf=None,
-                        device=None, want_src=True, ptr_tables=None):
+                        device=None, want_src=True, ptr_tables=None, stats_acc=None):
     """Batched nearest-to-reference-date mosaic.  b2_nearest_date_mosaic.
 
     stacks: (N,T,H,W,B) tensor or list of N (T,H,W,B) tensors; valids: (N,T,H,W) / list of (T,H,W) uint8;
     scene_day (N,T) int32; scene_cf (N,T) float32.  Returns out (N,H,W,B), mask (N,H,W) bool,
-    src (N,H,W) int16 or None, n_eligible (N,) int32 — all on the device.
+    src (N,H,W) int16 or None, n_eligible (N,) int32 — all on the device.  stats_acc: optional (B,4) int64
+    CUDA tensor; the band statistics of the valid output pixels are accumulated into it in the same pass.
     """
     ctx = get_ctx(device)
     if isinstance(stacks, (list, tuple)):
@@ -124,7 +125,7 @@ def nearest_date_mosaic(stacks, valids, scene_day, scene_cf, ref_day, min_day=No
         ctx.handle, ptr(sp), ptr(vp), ptr(day), ptr(cf), int(ref_day),
         _I32_MIN if min_day is None else int(min_day), _I32_MAX if max_day is None else int(max_day),
         float("nan") if max_cf is None else float(max_cf), n, T, H, W, B, eb, ptr(out), ptr(mask), ptr(src), ptr(nel),
-        ctx.stream()))
+        ptr(stats_acc), ctx.stream()))
     return out, mask.view(torch.bool), src, nel
 
 

@@ -66,13 +66,16 @@ int b2_median_composite_u16(b2_ctx* ctx, const uint16_t* stack_dev, const uint8_
  *   (T,H,W) u8.  scene_day_dev / scene_cf_dev: (n_chips,T).  out (n_chips,H,W,B) same element type;
  *   out_mask (n_chips,H,W) u8 = 1 where no valid scene (out = 0); src_index (n_chips,H,W) int16 or NULL;
  *   n_eligible (n_chips) int32 or NULL — 0 means the reference returns None (:614-615).
+ *   stats_acc (B,4) uint64 or NULL: the exact band statistics of b2_band_stats over the VALID output pixels are
+ *   accumulated in the same pass (uint8 / uint16 chips of at most 4 bands), so configs[4]'s per-band mean / std cost
+ *   no second read of the output.
  */
 int b2_nearest_date_mosaic(b2_ctx* ctx, const void* const* stacks_dev, const uint8_t* const* valids_dev,
                            const int32_t* scene_day_dev, const float* scene_cf_dev,
                            int32_t ref_day, int32_t min_day, int32_t max_day, float max_cf,
                            int n_chips, int T, int H, int W, int B, int elem_bytes,
                            void* out_dev, uint8_t* out_mask_dev, int16_t* src_index_dev,
-                           int32_t* n_eligible_dev, b2_stream stream);
+                           int32_t* n_eligible_dev, uint64_t* stats_acc_dev, b2_stream stream);
 
 /* ------------------------------------------------------------------ K4: cast / normalise / one-hot / statistics
  * North-star row A17 (not in the reference; nearest analogue parse_tfrecords.ipynb cell 21).

@@ -152,3 +152,28 @@ def test_reference_entry_points(dev):
     np.testing.assert_array_equal(res.mask.cpu().numpy()[..., 0], r_mask)
     assert pkg.create_img_array_for_tile("tile-a", "sentinel-2:L1C", dt.date(2020, 1, 25), max_cloud_fraction=0.0,
                                          scene_source=src) is None
+
+
+@pytest.mark.parametrize("dtype,B", [(np.uint16, 4), (np.uint16, 2), (np.uint8, 4), (np.uint16, 1)])
+def test_mosaic_fused_band_statistics(dev, dtype, B):
+    """Statistics accumulated inside the mosaic kernel == oracle band_stats over the valid output pixels, and they
+    accumulate across calls (configs[4]: one allreduce of these counters gives the dataset mean / std)."""
+    import torch
+
+    from dl_image_segmentation_b200 import ops
+    from oracle import normalise as onorm
+    rng = np.random.default_rng(11)
+    n, T, H, W = 5, 9, 24, 20
+    stacks = rng.integers(0, np.iinfo(dtype).max + 1, (n, T, H, W, B)).astype(dtype)
+    valids = (rng.random((n, T, H, W)) > 0.6).astype(np.uint8)
+    valids[0] = 0                                              # a chip without any valid pixel
+    days = np.sort(rng.integers(0, 100, (n, T)), axis=1).astype(np.int32)
+    cfs = rng.random((n, T)).astype(np.float32)
+    acc = torch.zeros((B, 4), dtype=torch.int64, device=dev)
+    want = [(0, 0, 0)] * B
+    for rep in range(2):
+        out, mask, _, nel = ops.nearest_date_mosaic(stacks, valids, days, cfs, 50, 10, 90, 0.7, device=dev, stats_acc=acc)
+        o, m = out.cpu().numpy(), mask.cpu().numpy()
+        got = onorm.band_stats(o.reshape(-1, B), (~m).reshape(-1).astype(np.uint8))
+        want = [(a[0] + b[0], a[1] + b[1], a[2] + b[2]) for a, b in zip(want, got)]
+    assert ops.stats_to_python(acc) == want

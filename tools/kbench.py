@@ -93,13 +93,13 @@ def bench_mosaic(dev, pool=256, chips=4096, iters=5):
     def fn(i):
         _lib.check(_lib.lib().b2_nearest_date_mosaic(ctx.handle, _lib.ptr(sp), _lib.ptr(vp), _lib.ptr(day_d), _lib.ptr(cf_d),
                                                      f["ref_day"], f["min_day"], f["max_day"], f["max_cf"], chips, T, H, W, B, 2,
-                                                     _lib.ptr(out), _lib.ptr(mask), None, _lib.ptr(nel), ctx.stream()))
+                                                     _lib.ptr(out), _lib.ptr(mask), None, _lib.ptr(nel), None, ctx.stream()))
     ms = timeit(fn, iters)
     dense = chips * (T * H * W * B * 2 + T * H * W + H * W * B * 2 + H * W)
     # bytes actually touched: one pixel read + probes of eligible scenes until the first valid one (estimated from src)
     _lib.check(_lib.lib().b2_nearest_date_mosaic(ctx.handle, _lib.ptr(sp), _lib.ptr(vp), _lib.ptr(day_d), _lib.ptr(cf_d),
                                                  f["ref_day"], f["min_day"], f["max_day"], f["max_cf"], chips, T, H, W, B, 2,
-                                                 _lib.ptr(out), _lib.ptr(mask), _lib.ptr(src), _lib.ptr(nel), ctx.stream()))
+                                                 _lib.ptr(out), _lib.ptr(mask), _lib.ptr(src), _lib.ptr(nel), None, ctx.stream()))
     touched_min = chips * (H * W * B * 2 * 2 + H * W + H * W)
     report("mosaic_kernel<8> cfg5 T=32 256x256x4 u16, %d chips" % chips, ms, dense,
            {"chips_per_s": round(chips / ms * 1e3, 1), "note": "dense-equivalent bytes; the kernel skips filtered/occluded scenes",
