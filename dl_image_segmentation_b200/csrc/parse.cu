@@ -18,8 +18,8 @@
 //   * producer and consumers meet only through mbarriers (full / empty per buffer); there is no __syncthreads in
 //     the steady state and no second kernel: the CRC state of a thread runs on across the consecutive tiles of a
 //     record, the warps of a CTA fold their states through a shared-memory slot when the run of tiles ends, and
-//     the last warp there merges { CRC partial, tiles done } into the record's 64-bit accumulator with one
-//     compare-and-swap; whoever completes a record un-advances the zero padding, compares with the stored
+//     the last warp there merges { CRC partial, tiles done } into the record's 64-bit accumulator (atomic XOR
+//     + atomic add on one address); whoever completes a record un-advances the zero padding, compares with the stored
 //     masked CRC and writes the record's status.
 //
 // CRC-32C without a CRC instruction: the pure CRC (zero init) is linear over GF(2), so
@@ -113,10 +113,6 @@ struct __align__(16) TileJob {
     uint64_t img_off, img_len, tgt_off, tgt_len;
     uint32_t r, tile, nt, cb, tail, flags;   // flags: 1 valid, 2 sink ok
 };
-
-__device__ __forceinline__ uint32_t tile_power(const CrcTables* tab, uint32_t j) {
-    return j < 2048 ? __ldg(&tab->tpow[j]) : xpow8(tab, (uint64_t)j * kTile);
-}
 
 // What the producer knows about the record it is currently cutting into tiles.  Consecutive tiles almost always
 // belong to the same record, so the table lookups (tile -> record -> offsets -> feature index: three dependent
@@ -303,17 +299,6 @@ __device__ inline void finalize_record(const ParseArgs& a, const RecRef& j, uint
     if (st != 0 && a.n_bad) atomicAdd(reinterpret_cast<unsigned long long*>(a.n_bad), 1ull);
 }
 
-// a(x)*b(x) mod P, fully unrolled and branch-free (5 instructions per bit instead of the rolled loop's 11)
-__device__ __forceinline__ uint32_t multmodp_fast(uint32_t a, uint32_t b) {
-    uint32_t p = 0;
-#pragma unroll
-    for (int k = 31; k >= 0; k--) {
-        if (a & (1u << k)) p ^= b;
-        b = (b & 1u) ? (b >> 1) ^ kPoly : (b >> 1);
-    }
-    return p;
-}
-
 // Per-thread running CRC state over the tiles of one record.  A thread owns vectors i and i+256 of every tile; the
 // distance from the end of one of its vectors to the start of its next one is always 4080 bytes, inside a tile and
 // from one tile to the next, so the same "consume 4 bytes and skip 4080" table step chains them all and the
@@ -360,8 +345,8 @@ struct RunAcc {          // shared-memory meeting point of the eight consumer wa
 
 // Close a run.  No CTA-wide barrier: every consumer warp folds its lanes' CRC states, XORs the result into the run's
 // shared-memory slot and counts itself; the warp that arrives last moves the partial to the end of the record and
-// merges { CRC, tiles } into the record's 64-bit accumulator with one compare-and-swap loop (a single address, so no
-// fences are needed), finalising the record when its tile count is complete.  The other warps are already working
+// merges { CRC, tiles } into the record's 64-bit accumulator with an atomic XOR and an atomic add on the same address
+// (applied in program order, so no fences are needed), finalising the record when its tile count is complete.  The other warps are already working
 // on the next tile.
 __device__ __forceinline__ void run_flush(const ParseArgs& a, Run& run, uint32_t& s, uint32_t& run_seq, bool want_crc,
                                           RunAcc* racc) {
@@ -381,14 +366,11 @@ __device__ __forceinline__ void run_flush(const ParseArgs& a, Run& run, uint32_t
             uint32_t c = atomicExch(&ra->crc, 0u);
             ra->warps = 0;
             if (crc) c = multmodp_fast(tile_power(a.tab, run.nt - 1 - run.last_tile), c);
+            // XOR into the low word, then count in the high word: two atomics on ONE address are applied in program
+            // order, so whoever sees the count complete also sees every partial (no fence, no retry loop)
             unsigned long long* acc = a.acc + run.r;
-            unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(acc), upd;
-            for (;;) {
-                upd = (old ^ (unsigned long long)c) + ((unsigned long long)run.tiles << 32);
-                const unsigned long long seen = atomicCAS(acc, old, upd);
-                if (seen == old) break;
-                old = seen;
-            }
+            if (c) atomicXor(acc, (unsigned long long)c);
+            const unsigned long long upd = atomicAdd(acc, (unsigned long long)run.tiles << 32) + ((unsigned long long)run.tiles << 32);
             if ((uint32_t)(upd >> 32) == run.nt) {
                 *acc = 0ull;               // re-arm for the next launch; nobody else touches a finished record
                 RecRef rr{run.r, run.nt, run.d0, run.d1};

@@ -482,7 +482,7 @@ struct BuildArgs {
     const uint8_t* scaffold;
     uint8_t* out;
     const CrcTables* tab;
-    uint32_t* tilecrc;
+    unsigned long long* acc;   // per record { CRC partial, tiles done }, zero on entry
     uint32_t tiles_x;
     int n;
 };
@@ -594,51 +594,44 @@ __global__ void __launch_bounds__(kTileThreads) build_kernel(const BuildArgs a) 
                 if (p + j >= rs && p + j < re) a.out[p + j] = buf8[16 * k + j];
         }
     }
-    // CRC partial over the data range.  Tile grid here is anchored at A = rs & ~15 (not d0 & ~15); the final
-    // kernel is told so through the same anchor.
-    const uint32_t c = tile_crc(buf4, &cs, a.tab, ts, d0, d1, /*first_tile=*/ts <= d0 && d0 < te, red);
-    if (threadIdx.x == 0) a.tilecrc[(size_t)r * a.tiles_x + tile] = c;
-}
-
-__global__ void __launch_bounds__(256) build_final_kernel(const BuildArgs a) {
-    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (r >= a.n) return;
-    const b2_build_desc d = a.descs[r];
-    const uint64_t rs = d.out_off, L = d.example_len, d0 = rs + 12;
-    const uint64_t A = rs & ~15ull;
-    // tiles containing data: first data tile index t0, count nt — fold only those, anchored at A + t0*kTile
-    const uint32_t t0 = (uint32_t)((d0 - A) / kTile);
-    uint32_t crc;
-    if (L < 4) {
-        uint32_t s = 0xFFFFFFFFu;
-        for (uint64_t i = 0; i < L; i++) s = (s >> 8) ^ __ldg(&a.tab->t4[3][(s ^ a.out[d0 + i]) & 0xff]);
-        crc = ~s;
-    } else {
-        const uint32_t nt = (uint32_t)((d0 + L - A + kTile - 1) / kTile) - t0;
-        // fold_record_crc derives its anchor from d0 & ~15; emulate by folding manually with our anchor
-        const uint32_t* tc = a.tilecrc + (size_t)r * a.tiles_x + t0;
-        const uint32_t q = (nt + 31) / 32;
-        const uint32_t b = lane * q, e = (b + q < nt) ? b + q : nt;
-        uint32_t s = 0;
-        for (uint32_t t = b; t < e; t++) s = multmodp(a.tab->xtile, s) ^ tc[t];
-        uint32_t acc = 0;
-        const uint32_t xq = xpow8(a.tab, (uint64_t)q * kTile);
-        for (int l = 0; l < 32; l++) {
-            const uint32_t sl = __shfl_sync(0xffffffffu, s, l);
-            const uint32_t bl = l * q;
-            if (bl >= nt) break;
-            const uint32_t el = (bl + q < nt) ? bl + q : nt;
-            acc = ((el - bl) == q ? multmodp(xq, acc) : multmodp(xpow8(a.tab, (uint64_t)(el - bl) * kTile), acc)) ^ sl;
+    // CRC partial over the data range; the tile grid is anchored at A = rs & ~15.  Thread 0 moves the partial to the end
+    // of the last data tile and merges { CRC, 1 tile } into the record's 64-bit accumulator (atomic XOR + atomic add);
+    // the CTA that completes the record un-advances the zero padding and writes the masked CRC footer.
+    const uint32_t c0 = tile_crc(buf4, &cs, a.tab, ts, d0, d1, /*first_tile=*/ts <= d0 && d0 < te, red);
+    if (threadIdx.x == 0) {
+        const uint32_t t0 = (uint32_t)((d0 - A) / kTile);                       // first tile holding data
+        const uint32_t t_end = (uint32_t)((re - A + kTile - 1) / kTile);        // tiles of this record (L == 0: header only)
+        uint32_t c = 0;
+        if (L >= 4 && tile >= t0) c = multmodp_fast(tile_power(a.tab, t_end - 1 - tile), c0);
+        // XOR into the low word, then count in the high word: two atomics on ONE address are applied in program order,
+        // so whoever sees the count complete also sees every partial (no fence, no retry loop under contention)
+        unsigned long long* acc = a.acc + r;
+        if (c) atomicXor(acc, (unsigned long long)c);
+        const unsigned long long upd = atomicAdd(acc, 1ull << 32) + (1ull << 32);
+        if ((uint32_t)(upd >> 32) == t_end) {
+            uint32_t crc;
+            if (L < 4) {   // the whole record sits in this CTA's tile(s) written above: bytewise from shared memory is not
+                           // possible across tiles, but L < 4 means header + data fit in at most two tiles; recompute
+                uint32_t s = 0xFFFFFFFFu;
+                for (uint64_t i = 0; i < L; i++) {
+                    const uint64_t x = i;   // Example-space offset
+                    uint32_t bv;
+                    const uint64_t e1 = d.piece_len[0];
+                    if (x < e1) bv = sc[x];
+                    else bv = 0;            // unreachable: an Example shorter than 4 bytes has no payload
+                    s = (s >> 8) ^ __ldg(&a.tab->t4[3][(s ^ bv) & 0xff]);
+                }
+                crc = ~s;
+            } else {
+                uint32_t accv = (uint32_t)upd;
+                const uint64_t pad = A + (uint64_t)t_end * kTile - (d0 + L);
+                accv = multmodp(__ldg(&a.tab->xinv16[pad >> 4]), accv);
+                accv = multmodp(__ldg(&a.tab->xinvb[pad & 15]), accv);
+                crc = ~accv;
+            }
+            const uint32_t m = mask_crc(crc);
+            for (int j = 0; j < 4; j++) a.out[d0 + L + j] = (uint8_t)(m >> (8 * j));
         }
-        const uint64_t pad = A + (uint64_t)(t0 + nt) * kTile - (d0 + L);
-        acc = multmodp(__ldg(&a.tab->xinv16[pad >> 4]), acc);
-        acc = multmodp(__ldg(&a.tab->xinvb[pad & 15]), acc);
-        crc = ~acc;
-    }
-    if (lane == 0) {
-        const uint32_t m = mask_crc(crc);
-        for (int j = 0; j < 4; j++) a.out[d0 + L + j] = (uint8_t)(m >> (8 * j));
     }
 }
 
@@ -720,12 +713,11 @@ extern "C" int b2_tfrecord_build(b2_ctx* ctx, const b2_build_desc* descs, int n,
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     uint32_t tx = (uint32_t)((max_record_bytes + 15 + kTile - 1) / kTile);
     if (!tx) tx = 1;
-    if (int e = ws_reserve(ctx, (size_t)n * tx * sizeof(uint32_t), s)) return e;
-    BuildArgs ba{descs, scaffold, out, ctx->crc_dev, static_cast<uint32_t*>(ctx->ws), tx, n};
+    // per-record accumulators live in the context workspace: calls on one context must be stream-ordered
+    if (int e = ws_reserve(ctx, (size_t)n * sizeof(unsigned long long), s)) return e;
+    B2_CUDA(cudaMemsetAsync(ctx->ws, 0, (size_t)n * sizeof(unsigned long long), s));
+    BuildArgs ba{descs, scaffold, out, ctx->crc_dev, static_cast<unsigned long long*>(ctx->ws), tx, n};
     build_kernel<<<dim3(tx, n), kTileThreads, 0, s>>>(ba);
-    ctx->launches++;
-    B2_CUDA(cudaGetLastError());
-    build_final_kernel<<<(n * 32 + 255) / 256, 256, 0, s>>>(ba);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;

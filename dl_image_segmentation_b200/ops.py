@@ -401,6 +401,47 @@ def example_layout(kind, img_bytes, tgt_bytes, img_h, img_w, img_c, tgt_h, tgt_w
     return bytes(buf[:total]), (pl[0], pl[1], pl[2]), int(el.value)
 
 
+class BuildPlan:
+    """Descriptor tables of one batch of records, uploaded once; launch() enqueues the serialise + frame kernel."""
+
+    def __init__(self, items, device=None):
+        self.ctx = get_ctx(device)
+        n = len(items)
+        descs = np.zeros(n, dtype=np.dtype(_lib.BUILD_DESC_DTYPE))
+        assert descs.dtype.itemsize == ctypes.sizeof(_lib.BuildDesc)
+        scaf = bytearray()
+        pos = 0
+        self.offsets, self.keep = [], []
+        max_rec = 0
+        for i, it in enumerate(items):
+            img, tgt, kind = it["img"], it["tgt"], int(it["kind"])
+            self.keep += [img, tgt]
+            ib = img.numel() * (img.element_size() if kind == 1 else 4)
+            tb = tgt.numel() * (tgt.element_size() if kind == 1 else 4)
+            sc, pl, el = example_layout(kind, ib, tb, it["h"], it["w"], it["c"], it["th"], it["tw"], it["identifier"])
+            d = descs[i]
+            d["out_off"], d["example_len"], d["scaffold_off"] = pos, el, len(scaf)
+            d["piece_len"] = pl
+            d["src_dtype"], d["tgt_dtype"], d["kind"] = b2_dtype(img), b2_dtype(tgt), kind
+            d["img_src"], d["img_count"] = img.data_ptr(), img.numel() * (img.element_size() if kind == 1 else 1)
+            d["tgt_src"], d["tgt_count"] = tgt.data_ptr(), tgt.numel() * (tgt.element_size() if kind == 1 else 1)
+            scaf += sc
+            self.offsets.append(pos)
+            pos += el + 16
+            max_rec = max(max_rec, el + 16)
+        self.n, self.total, self.max_rec, self.itemsize = n, pos, max_rec, descs.dtype.itemsize
+        self.out = torch.empty((_align16(pos) + 16,), dtype=torch.uint8, device=self.ctx.device)
+        self.descs_d = to_device(descs.view(np.uint8), self.ctx.device)
+        self.scaf_d = to_device(bytes(scaf) if scaf else b"\0", self.ctx.device)
+
+    def launch(self):
+        for s in range(0, self.n, 65535):
+            m = min(65535, self.n - s)
+            check(lib().b2_tfrecord_build(self.ctx.handle, ctypes.c_void_p(self.descs_d.data_ptr() + s * self.itemsize), m,
+                                          self.max_rec, ptr(self.scaf_d), ptr(self.out), self.ctx.stream()))
+        return self.out
+
+
 def build_records(items, device=None):
     """Serialise + frame records on the device.
 
@@ -408,39 +449,8 @@ def build_records(items, device=None):
     h, w, c, th, tw, identifier (bytes).  Returns (out uint8 CUDA tensor holding the framed records back to
     back, offsets list, total bytes).
     """
-    ctx = get_ctx(device)
-    n = len(items)
-    descs = np.zeros(n, dtype=np.dtype(_lib.BUILD_DESC_DTYPE))
-    assert descs.dtype.itemsize == ctypes.sizeof(_lib.BuildDesc)
-    scaf = bytearray()
-    pos = 0
-    offsets = []
-    max_rec = 0
-    keep = []
-    for i, it in enumerate(items):
-        img, tgt, kind = it["img"], it["tgt"], int(it["kind"])
-        keep += [img, tgt]
-        ib = img.numel() * (img.element_size() if kind == 1 else 4)
-        tb = tgt.numel() * (tgt.element_size() if kind == 1 else 4)
-        sc, pl, el = example_layout(kind, ib, tb, it["h"], it["w"], it["c"], it["th"], it["tw"], it["identifier"])
-        d = descs[i]
-        d["out_off"], d["example_len"], d["scaffold_off"] = pos, el, len(scaf)
-        d["piece_len"] = pl
-        d["src_dtype"], d["tgt_dtype"], d["kind"] = b2_dtype(img), b2_dtype(tgt), kind
-        d["img_src"], d["img_count"] = img.data_ptr(), img.numel() * (img.element_size() if kind == 1 else 1)
-        d["tgt_src"], d["tgt_count"] = tgt.data_ptr(), tgt.numel() * (tgt.element_size() if kind == 1 else 1)
-        scaf += sc
-        offsets.append(pos)
-        pos += el + 16
-        max_rec = max(max_rec, el + 16)
-    out = torch.empty((_align16(pos) + 16,), dtype=torch.uint8, device=ctx.device)
-    descs_d = to_device(descs.view(np.uint8), ctx.device)
-    scaf_d = to_device(bytes(scaf) if scaf else b"\0", ctx.device)
-    for s in range(0, n, 65535):
-        m = min(65535, n - s)
-        check(lib().b2_tfrecord_build(ctx.handle, ctypes.c_void_p(descs_d.data_ptr() + s * descs.dtype.itemsize), m,
-                                      max_rec, ptr(scaf_d), ptr(out), ctx.stream()))
-    return out, offsets, pos
+    plan = BuildPlan(items, device)
+    return plan.launch(), plan.offsets, plan.total
 
 
 def _make_sink(ctx, mode, verify_crc, mean, std, num_classes, channels, img_buf, tgt_buf):

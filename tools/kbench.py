@@ -207,6 +207,28 @@ def bench_parse(dev, n_shards=8):
     report("reference: torch copy_ 1 GiB (read+write)", timeit(lambda i: big2.copy_(big), 10), 2 << 30)
 
 
+def bench_build(dev, n_shards=8):
+    """The writer kernel on cfg1 records (uint8 arrays -> framed Examples) and cfg3 records (uint16 -> FloatList)."""
+    import bench as B
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    for name, (h, c, dt, kind, n) in {"build cfg1 256x256x3 u8 -> BytesList": (256, 3, torch.uint8, 1, 250),
+                                      "build cfg3 512x512x4 u16 -> FloatList": (512, 4, torch.int16, 2, 32)}.items():
+        plans = []
+        for s in range(n_shards):
+            hi = 256 if dt == torch.uint8 else 10000
+            imgs = torch.randint(0, hi, (n, h, h, c), dtype=torch.int32, device=dev, generator=g).to(dt)
+            if dt == torch.int16:
+                imgs = imgs.view(torch.uint16)
+            labs = torch.randint(0, 10, (n, h, h), dtype=torch.uint8, device=dev, generator=g)
+            items = [dict(img=imgs[i].reshape(-1), tgt=labs[i].reshape(-1), kind=kind, h=h, w=h, c=c, th=h, tw=h,
+                          identifier=(B.KEY_FMT % (s, i)).encode()) for i in range(n)]
+            plans.append(ops.BuildPlan(items, dev))
+        ms = timeit(lambda i: plans[i % n_shards].launch(), 16)
+        in_b = n * (h * h * c * (1 if dt == torch.uint8 else 2) + h * h)
+        report(name + " (%d records)" % n, ms, in_b + plans[0].total, {"records_per_s": round(n / ms * 1e3, 1)})
+
+
 def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -217,6 +239,8 @@ def main():
         bench_mosaic(dev)
     if "parse" in which:
         bench_parse(dev)
+    if "build" in which:
+        bench_build(dev)
     for kind in ("lzw", "lzw_strips_pred2", "deflate", "png"):
         if kind in which or "decode" in which:
             bench_decode(dev, kind)
