@@ -21,7 +21,8 @@ class ImageInfo(ctypes.Structure):
                 ("tiled", ctypes.c_int32), ("block_w", ctypes.c_int32), ("block_h", ctypes.c_int32),
                 ("blocks_across", ctypes.c_int32), ("blocks_down", ctypes.c_int32), ("n_blocks", ctypes.c_int32),
                 ("status", ctypes.c_int32), ("has_nodata", ctypes.c_int32), ("pad_", ctypes.c_int32),
-                ("nodata", ctypes.c_double), ("block_bytes", ctypes.c_uint64)]
+                ("nodata", ctypes.c_double), ("block_bytes", ctypes.c_uint64),
+                ("geotransform", ctypes.c_double * 6), ("has_geo", ctypes.c_int32), ("epsg", ctypes.c_int32)]
 
 
 STREAM_DESC_DTYPE = np.dtype([("src_off", "<u8"), ("dst_off", "<u8"), ("src_len", "<u4"), ("dst_len", "<u4"),
@@ -59,6 +60,12 @@ def probe(blob) -> ImageInfo:
     info = ImageInfo()
     check(lib().b2_image_probe(a.ctypes.data, a.size, ctypes.byref(info)))
     return info
+
+
+def georef_strings(info):
+    """(str(src.get_transform()), str(src.read_crs())) as rasterio would print them (reference _img_to_tf_mp.py:49-50)."""
+    gt = [float(v) for v in info.geotransform]
+    return str(gt), ("EPSG:%d" % info.epsg) if info.epsg else "None"
 
 
 def _align(x, a=256):

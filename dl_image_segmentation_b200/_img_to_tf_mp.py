@@ -25,9 +25,8 @@ def load_image_rasterio(img_path, parse_dltile_filename=True, decode=True, devic
         raise _translate.ChipError("'%s' not recognized as a supported file format." % img_path)
     tile_key = _translate.tile_key_from_path(img_path, parse_dltile_filename)
     if not parse_dltile_filename:
-        # reference :63-67 joins filename | geotransform | crs; georeferencing tags are not parsed yet
-        # (SURVEY.md section 8f row 2), so non-georeferenced defaults are reported like GDAL does for a PNG
-        tile_key = "|".join((os.path.basename(img_path), "[0.0, 1.0, 0.0, 0.0, 0.0, 1.0]", "None"))
+        # reference :63-67: filename | str(geotransform) | str(crs), from the GeoTIFF tags (GDAL defaults for a PNG)
+        tile_key = "|".join((os.path.basename(img_path),) + _codec.georef_strings(info))
     if decode:
         (arr,), (st,) = _codec.decode_blobs([image_data], device=device)
         if st != 0:
@@ -40,10 +39,11 @@ def load_image_rasterio(img_path, parse_dltile_filename=True, decode=True, devic
 def _process_image_files_mp_worker(proc_index, ranges, name, img_filenames, lbl_filenames, output_directory,
                                    num_shards, dltile_from_filename, store_as_array, device=None):
     """One worker = one GPU: writes its shards (reference :78-157)."""
-    def key_fn(p):
+    def key_fn(p, info=None):
         if dltile_from_filename:
             return _translate.tile_key_from_path(p, True)
-        return "|".join((os.path.basename(p), "[0.0, 1.0, 0.0, 0.0, 0.0, 1.0]", "None"))
+        gt, crs = _codec.georef_strings(info) if info is not None else ("[0.0, 1.0, 0.0, 0.0, 0.0, 1.0]", "None")
+        return "|".join((os.path.basename(p), gt, crs))
     return _translate.run_worker(proc_index, ranges, name, img_filenames, lbl_filenames, output_directory, num_shards,
                                  key_fn, store_as_array, label="process", progress_every=100, device=device)
 

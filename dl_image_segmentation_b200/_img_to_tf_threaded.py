@@ -70,7 +70,7 @@ def _process_image(filename, coder, parse_dltile_filename=True, png_to_jpg=False
 def _process_image_files_worker(coder, thread_index, ranges, name, filenames, labels, out_folder, num_shards,
                                 dltile_from_filename, png_to_jpg, store_as_array=False, device=None):
     """One worker = one GPU (reference :136-219)."""
-    def key_fn(p):
+    def key_fn(p, info=None):
         return _translate.tile_key_from_path(p, dltile_from_filename)
 
     def validate(info):

@@ -83,7 +83,7 @@ def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, devi
             if validate is not None:
                 validate(ii)
                 validate(li)
-            ikey, lkey = key_fn(img_paths[i]), key_fn(lbl_paths[i])
+            ikey, lkey = key_fn(img_paths[i], ii), key_fn(lbl_paths[i], li)
             assert ikey == lkey                                             # _img_to_tf_mp.py:132
         except Exception as e:
             out.append(e)

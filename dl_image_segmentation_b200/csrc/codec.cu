@@ -761,6 +761,10 @@ struct TiffTags {
     int off_type = 0, cnt_type = 0;
     bool has_nodata = false;
     double nodata = 0;
+    // GeoTIFF: ModelPixelScale (33550), ModelTiepoint (33922), ModelTransformation (34264), GeoKeyDirectory (34735)
+    int n_scale = 0, n_tie = 0, n_xform = 0;
+    double scale[3] = {0, 0, 0}, tie[6] = {0, 0, 0, 0, 0, 0}, xform[16] = {0};
+    int epsg = 0;              // ProjectedCSTypeGeoKey (3072) or GeographicTypeGeoKey (2048) when it is an EPSG code
 };
 
 // value i of an IFD entry of SHORT/LONG type
@@ -807,6 +811,33 @@ int parse_tiff(const uint8_t* blob, uint64_t size, TiffTags& t, Rd& r) {
                 break;
             case 273: case 324: t.off_pos = pos; t.off_cnt = cnt; t.off_type = type; break;
             case 279: case 325: t.cnt_pos = pos; t.cnt_cnt = cnt; t.cnt_type = type; break;
+            case 33550: case 33922: case 34264:
+                if (type == 12) {
+                    double* dst = tag == 33550 ? t.scale : (tag == 33922 ? t.tie : t.xform);
+                    const uint32_t cap = tag == 33550 ? 3 : (tag == 33922 ? 6 : 16);
+                    const uint32_t m = cnt < cap ? cnt : cap;
+                    for (uint32_t k = 0; k < m; k++) {
+                        uint64_t bits = 0;
+                        for (int j = 0; j < 8; j++) bits |= (uint64_t)blob[pos + 8 * k + (r.be ? 7 - j : j)] << (8 * j);
+                        memcpy(&dst[k], &bits, 8);
+                    }
+                    (tag == 33550 ? t.n_scale : (tag == 33922 ? t.n_tie : t.n_xform)) = (int)m;
+                }
+                break;
+            case 34735:
+                if (type == 3 && cnt >= 4) {
+                    const uint32_t nkeys = r.u16(pos + 6);
+                    int proj = 0, geog = 0;
+                    for (uint32_t k = 0; k < nkeys && 4 * (k + 2) <= cnt; k++) {
+                        const uint64_t q = pos + 8 * (k + 1);
+                        const uint32_t key = r.u16(q), loc = r.u16(q + 2), val = r.u16(q + 6);
+                        if (loc != 0) continue;
+                        if (key == 3072) proj = (int)val;
+                        else if (key == 2048) geog = (int)val;
+                    }
+                    t.epsg = (proj && proj != 32767) ? proj : ((geog && geog != 32767) ? geog : 0);
+                }
+                break;
             case 42113: {
                 std::string s(reinterpret_cast<const char*>(blob + pos), (size_t)nb);
                 t.has_nodata = true;
@@ -867,6 +898,8 @@ extern "C" int b2_image_probe(const uint8_t* blob, uint64_t size, b2_image_info*
         info->predictor = 1;
         info->compression = 8;
         info->block_bytes = (uint64_t)info->height * ((uint64_t)info->width * info->samples + 1);
+        info->geotransform[1] = 1;
+        info->geotransform[5] = 1;
         if (n_idat == 0 && info->status == 0) info->status = 2;
         return 0;
     }
@@ -886,6 +919,22 @@ extern "C" int b2_image_probe(const uint8_t* blob, uint64_t size, b2_image_info*
     info->tiled = t.tile_w ? 1 : 0;
     info->has_nodata = t.has_nodata;
     info->nodata = t.nodata;
+    // affine geotransform in GDAL order (x0, dx, rx, y0, ry, dy); identity-like default when the file has none
+    info->geotransform[0] = 0; info->geotransform[1] = 1; info->geotransform[2] = 0;
+    info->geotransform[3] = 0; info->geotransform[4] = 0; info->geotransform[5] = 1;
+    info->has_geo = 0;
+    info->epsg = t.epsg;
+    if (t.n_xform == 16) {
+        info->geotransform[0] = t.xform[3]; info->geotransform[1] = t.xform[0]; info->geotransform[2] = t.xform[1];
+        info->geotransform[3] = t.xform[7]; info->geotransform[4] = t.xform[4]; info->geotransform[5] = t.xform[5];
+        info->has_geo = 1;
+    } else if (t.n_scale >= 2 && t.n_tie >= 6) {
+        info->geotransform[1] = t.scale[0];
+        info->geotransform[5] = -t.scale[1];
+        info->geotransform[0] = t.tie[3] - t.tie[0] * t.scale[0];
+        info->geotransform[3] = t.tie[4] + t.tie[1] * t.scale[1];
+        info->has_geo = 1;
+    }
     if (!t.has_size || t.width == 0 || t.height == 0 || t.spp == 0) { info->status = 2; return 0; }
     if (info->dtype < 0 || t.mixed || t.fill_order != 1 || (t.planar != 1 && t.planar != 2) ||
         !(t.compression == 1 || t.compression == 5 || t.compression == 8 || t.compression == 32946) ||

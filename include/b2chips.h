@@ -209,6 +209,10 @@ typedef struct {
     int32_t has_nodata, pad_;
     double nodata;       /* GDAL_NODATA tag 42113 (_descartes_img_chips.py:794-795)                           */
     uint64_t block_bytes; /* decoded bytes of one full block (PNG: h * (1 + w*samples) filtered bytes)        */
+    /* what src.get_transform() / src.read_crs() return (_img_to_tf_mp.py:49-50), for identifiers built with
+     * dltile_from_filename=False (:63-67): GDAL-order affine, default (0,1,0,0,0,1); EPSG code or 0               */
+    double geotransform[6];
+    int32_t has_geo, epsg;
 } b2_image_info;
 
 /* Host-side header parse (TIFF IFD / PNG chunks); never touches the GPU. */

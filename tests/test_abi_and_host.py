@@ -45,7 +45,7 @@ def test_struct_layouts_match_the_header(lib):
     assert ctypes.sizeof(_lib.ExampleIndex) == 80 == np.dtype(_lib.EXAMPLE_INDEX_DTYPE).itemsize
     assert ctypes.sizeof(_lib.BuildDesc) == 80 == np.dtype(_lib.BUILD_DESC_DTYPE).itemsize
     assert ctypes.sizeof(_lib.ParseSink) == 64
-    assert ctypes.sizeof(_codec.ImageInfo) == 88
+    assert ctypes.sizeof(_codec.ImageInfo) == 88 + 6 * 8 + 8
     assert _codec.STREAM_DESC_DTYPE.itemsize == 32 and _codec.IMAGE_DESC_DTYPE.itemsize == 72
 
 
@@ -230,3 +230,19 @@ def test_batch_decode_planner_matches_per_file_calls(lib):
                 assert int(sd["dst_off"]) == int(images[i]["scratch_off"]) + j * int(info.block_bytes)
             k += nb
     assert k == plan.n_streams
+
+
+def test_georeferenced_identifier_strings(lib, tmp_path):
+    """dltile_from_filename=False: identifier = basename | str(geotransform) | str(crs) (reference _img_to_tf_mp.py:49-50,
+    63-67), read from the GeoTIFF tags (ModelPixelScale / ModelTiepoint / GeoKeyDirectory); GDAL defaults for a PNG."""
+    from dl_image_segmentation_b200 import _codec
+    img = np.arange(16 * 16 * 2, dtype=np.uint16).reshape(16, 16, 2)
+    info = _codec.probe(syn.tiff_bytes(img, tile=16))
+    assert info.has_geo == 1 and info.epsg == 32643
+    assert _codec.georef_strings(info) == ("[499980.0, 10.0, 0.0, 5300040.0, 0.0, -10.0]", "EPSG:32643")
+    info = _codec.probe(syn.tiff_bytes(img, tile=16, geo=False))
+    assert info.has_geo == 0 and _codec.georef_strings(info) == ("[0.0, 1.0, 0.0, 0.0, 0.0, 1.0]", "None")
+    info = _codec.probe(syn.png_bytes(np.zeros((4, 4, 3), np.uint8)))
+    assert _codec.georef_strings(info) == ("[0.0, 1.0, 0.0, 0.0, 0.0, 1.0]", "None")
+    big = _codec.probe(syn.tiff_bytes(img, tile=16, big_endian=True))
+    assert _codec.georef_strings(big) == ("[499980.0, 10.0, 0.0, 5300040.0, 0.0, -10.0]", "EPSG:32643")
