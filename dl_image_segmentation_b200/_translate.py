@@ -124,85 +124,77 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
     n_slots = 3
     pinned = [None] * n_slots                                               # rotating pinned write-back buffers
     slot_futs = [[] for _ in range(n_slots)]                                # positional writes still reading a buffer
-    # the work list: (shard, [file indices]) in shard order, batches never straddle a shard
-    batches = []
-    for s in range(per):
-        lo, hi = int(shard_ranges[s]), int(shard_ranges[s + 1])
-        if lo == hi:
-            batches.append((s, []))
-        for b0 in range(lo, hi, batch_pairs):
-            batches.append((s, list(range(b0, min(b0 + batch_pairs, hi)))))
-    open_files = []
+    # decode batches run over the worker's whole file range (the entropy decoders want thousands of streams per launch);
+    # records are then serialised and written shard by shard, so a batch may feed several shard files
+    lo_all, hi_all = int(shard_ranges[0]), int(shard_ranges[-1])
+    batches = [(b0, min(b0 + batch_pairs, hi_all)) for b0 in range(lo_all, hi_all, batch_pairs)]
+    files = [open(os.path.join(output_directory, "%s-%.5d-of-%.5d" % (name, worker_index * per + s, num_shards)), "wb")
+             for s in range(per)]
+    shard_off = [0] * per
+    shard_count = [0] * per
+    seq = 0
     with ThreadPoolExecutor(max_workers=max(1, io_threads)) as pool, ThreadPoolExecutor(max_workers=1) as writer, \
             ThreadPoolExecutor(max_workers=8) as wpool:
-        def submit_reads(idx):
+        def submit_reads(rng):
             paths = []
-            for i in idx:
+            for i in range(*rng):
                 paths += [img_filenames[i], lbl_filenames[i]]
             return [pool.submit(_read_or_error, p) for p in paths]
-        pending_reads = submit_reads(batches[0][1]) if batches else []
-        cur_file, cur_shard, shard_counter, cur_off = None, -1, 0, 0
-
-        def finish_shard():
-            nonlocal cur_file
-            if cur_file is not None:
-                print("%s [%s %d]: Wrote %d images to %s" % (datetime.now(), label, worker_index, shard_counter, cur_file.name))
-                sys.stdout.flush()
-                cur_file = None                                              # closed after its last positional write
-
-        for bi, (s, idx) in enumerate(batches):
+        pending_reads = submit_reads(batches[0]) if batches else []
+        for bi, (b0, b1) in enumerate(batches):
             blobs = [f.result() for f in pending_reads]
-            pending_reads = submit_reads(batches[bi + 1][1]) if bi + 1 < len(batches) else []
-            if s != cur_shard:
-                finish_shard()
-                shard = worker_index * per + s
-                cur_file = open(os.path.join(output_directory, "%s-%.5d-of-%.5d" % (name, shard, num_shards)), "wb")
-                open_files.append(cur_file)
-                cur_shard, shard_counter, cur_off = s, 0, 0
-            if not idx:
-                continue
+            pending_reads = submit_reads(batches[bi + 1]) if bi + 1 < len(batches) else []
+            idx = list(range(b0, b1))
             pairs = load_pairs([img_filenames[i] for i in idx], [lbl_filenames[i] for i in idx], store_as_array,
                                key_fn, validate, ctx.device, blobs=blobs)
-            items = []
-            for i, p in zip(idx, pairs):
-                if isinstance(p, Exception):
-                    print(p)
-                    print("SKIPPED: Unexpected eror while decoding %s." % img_filenames[i])
+            for s in range(per):
+                lo, hi = max(b0, int(shard_ranges[s])), min(b1, int(shard_ranges[s + 1]))
+                if lo >= hi:
                     continue
-                items.append(p)
-                shard_counter += 1
-                counter += 1
-                if not counter % progress_every:
-                    print("%s [%s %d]: Processed %d of %d images in %s batch." %
-                          (datetime.now(), label, worker_index, counter, num_files, label))
-                    sys.stdout.flush()
-            if items:
-                buf, _, total = ops.build_records(items, ctx.device)
-                slot = bi % n_slots
-                for x in slot_futs[slot]:                                    # the writes that last used this buffer
-                    for y in x.result():
-                        y.result()
-                slot_futs[slot] = []
-                if pinned[slot] is None or pinned[slot].numel() < total:
-                    pinned[slot] = torch.empty((int(total * 1.1) + 4096,), dtype=torch.uint8).pin_memory()
-                host = pinned[slot][:total]
-                host.copy_(buf[:total], non_blocking=True)
-                done = torch.cuda.Event()
-                done.record(torch.cuda.current_stream(ctx.device))
+                items = []
+                for i in range(lo, hi):
+                    p = pairs[i - b0]
+                    if isinstance(p, Exception):
+                        print(p)
+                        print("SKIPPED: Unexpected eror while decoding %s." % img_filenames[i])
+                        continue
+                    items.append(p)
+                    shard_count[s] += 1
+                    counter += 1
+                    if not counter % progress_every:
+                        print("%s [%s %d]: Processed %d of %d images in %s batch." %
+                              (datetime.now(), label, worker_index, counter, num_files, label))
+                        sys.stdout.flush()
+                if items:
+                    buf, _, total = ops.build_records(items, ctx.device)
+                    slot = seq % n_slots
+                    seq += 1
+                    for x in slot_futs[slot]:                                # the writes that last used this buffer
+                        for y in x.result():
+                            y.result()
+                    slot_futs[slot] = []
+                    if pinned[slot] is None or pinned[slot].numel() < total:
+                        pinned[slot] = torch.empty((int(total * 1.1) + 4096,), dtype=torch.uint8).pin_memory()
+                    host = pinned[slot][:total]
+                    host.copy_(buf[:total], non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(torch.cuda.current_stream(ctx.device))
 
-                def _write(fd=cur_file.fileno(), h=host, ev=done, off=cur_off):
-                    ev.synchronize()                                         # the records have arrived in pinned memory
-                    mv = memoryview(h.numpy())
-                    step = 16 << 20                                          # positional writes: order-free, several in flight
-                    return [wpool.submit(os.pwrite, fd, mv[o:o + step], off + o) for o in range(0, len(mv), step)]
-                cur_off += total
-                slot_futs[slot].append(writer.submit(_write))
-        finish_shard()
+                    def _write(fd=files[s].fileno(), h=host, ev=done, off=shard_off[s]):
+                        ev.synchronize()                                     # the records have arrived in pinned memory
+                        mv = memoryview(h.numpy())
+                        step = 16 << 20                                      # positional writes: order-free, several in flight
+                        return [wpool.submit(os.pwrite, fd, mv[o:o + step], off + o) for o in range(0, len(mv), step)]
+                    shard_off[s] += total
+                    slot_futs[slot].append(writer.submit(_write))
+                if hi == int(shard_ranges[s + 1]):
+                    print("%s [%s %d]: Wrote %d images to %s" % (datetime.now(), label, worker_index, shard_count[s], files[s].name))
+                    sys.stdout.flush()
         for fl in slot_futs:
             for x in fl:
                 for y in x.result():
                     y.result()
-    for f in open_files:
+    for f in files:
         f.close()
     print("%s [%s %d]: Wrote %d images to %d shards." % (datetime.now(), label, worker_index, counter, per))
     sys.stdout.flush()
