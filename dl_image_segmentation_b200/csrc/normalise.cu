@@ -13,7 +13,30 @@ namespace b2 {
 template <typename T>
 __device__ __forceinline__ float to_f32(T v) { return (float)v; }
 
-// One thread per output float4 of the image: elements [4g, 4g+4) of the flattened (n_pixels*C) array.
+// four consecutive elements starting at element e0 (e0 % 4 == 0), as floats; one vector load when the base is aligned
+template <typename T>
+__device__ __forceinline__ void load4(const T* __restrict__ img, uint64_t e0, uint64_t n_elems, bool vec_ok, float (&x)[4]) {
+    if (vec_ok && e0 + 4 <= n_elems) {
+        if (sizeof(T) == 1) {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(img + e0));
+#pragma unroll
+            for (int k = 0; k < 4; k++) x[k] = to_f32((T)((w >> (8 * k)) & 0xFFu));
+        } else if (sizeof(T) == 2) {
+            const uint2 w = __ldg(reinterpret_cast<const uint2*>(img + e0));
+            x[0] = to_f32((T)(w.x & 0xFFFFu)); x[1] = to_f32((T)(w.x >> 16));
+            x[2] = to_f32((T)(w.y & 0xFFFFu)); x[3] = to_f32((T)(w.y >> 16));
+        } else {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(img + e0));
+            x[0] = __uint_as_float(w.x); x[1] = __uint_as_float(w.y); x[2] = __uint_as_float(w.z); x[3] = __uint_as_float(w.w);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) x[k] = (e0 + k < n_elems) ? to_f32(img[e0 + k]) : 0.0f;
+    }
+}
+
+// One thread per output float4 of the image: elements [4g, 4g+4) of the flattened (n_pixels*C) array.  The band of
+// the first element advances by a constant per grid stride, so there is no division in the loop.
 template <typename T>
 __global__ void __launch_bounds__(256)
 normalise_kernel(const T* __restrict__ img, const float* __restrict__ mean, const float* __restrict__ stdv,
@@ -24,15 +47,20 @@ normalise_kernel(const T* __restrict__ img, const float* __restrict__ mean, cons
         s_std[c] = stdv[c];
     }
     __syncthreads();
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(img) & (4 * sizeof(T) - 1)) == 0;
     const uint64_t groups = (n_elems + 3) >> 2;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t c0 = (uint32_t)((4 * g) % (uint64_t)C);
+    const uint32_t cstep = (uint32_t)((4 * stride) % (uint64_t)C);
+    for (; g < groups; g += stride) {
         const uint64_t e0 = 4 * g;
-        uint32_t c = (uint32_t)(e0 % (uint64_t)C);
-        float f[4];
+        float x[4], f[4];
+        load4<T>(img, e0, n_elems, vec_ok, x);
+        uint32_t c = c0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const float x = (e0 + k < n_elems) ? to_f32(img[e0 + k]) : 0.0f;
-            f[k] = __fdiv_rn(x - s_mean[c], s_std[c]);
+            f[k] = __fdiv_rn(x[k] - s_mean[c], s_std[c]);
             c = (c + 1 == (uint32_t)C) ? 0 : c + 1;
         }
         if (e0 + 4 <= n_elems) {
@@ -40,6 +68,8 @@ normalise_kernel(const T* __restrict__ img, const float* __restrict__ mean, cons
         } else {
             for (uint64_t e = e0; e < n_elems; e++) out[e] = f[e - e0];
         }
+        c0 += cstep;
+        if (c0 >= (uint32_t)C) c0 -= (uint32_t)C;
     }
 }
 
@@ -50,23 +80,32 @@ __device__ __forceinline__ bool label_is<uint8_t>(uint8_t lab, uint32_t k) { ret
 template <>
 __device__ __forceinline__ bool label_is<float>(float lab, uint32_t k) { return lab == (float)k; }
 
-// One thread per output float4 of the one-hot tensor: floats [4g, 4g+4) of the flattened (n_pixels*K) array.
+// One thread per output float4 of the one-hot tensor: floats [4g, 4g+4) of the flattened (n_pixels*K) array.  The
+// (label, class) position of the first float advances by a constant per grid stride: no division in the loop.
 template <typename L>
 __global__ void __launch_bounds__(256)
 onehot_kernel(const L* __restrict__ label, uint64_t n_pixels, int K, float* __restrict__ out) {
     const uint64_t n_fl = n_pixels * (uint64_t)K;
     const uint64_t groups = (n_fl + 3) >> 2;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t l0 = (4 * g) / (uint64_t)K;
+    uint32_t c0 = (uint32_t)(4 * g - l0 * (uint64_t)K);
+    const uint64_t lstep = (4 * stride) / (uint64_t)K;
+    const uint32_t cstep = (uint32_t)(4 * stride - lstep * (uint64_t)K);
+    for (; g < groups; g += stride) {
         const uint64_t f0 = 4 * g;
-        uint64_t l = f0 / (uint64_t)K;
-        uint32_t c = (uint32_t)(f0 - l * (uint64_t)K);
+        uint64_t l = l0;
+        uint32_t c = c0;
         float f[4];
+        L lab = (l < n_pixels) ? __ldg(label + l) : (L)0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            f[k] = (l < n_pixels && label_is<L>(__ldg(label + l), c)) ? 1.0f : 0.0f;
+            f[k] = (l < n_pixels && label_is<L>(lab, c)) ? 1.0f : 0.0f;
             if (++c == (uint32_t)K) {
                 c = 0;
                 l++;
+                if (k < 3) lab = (l < n_pixels) ? __ldg(label + l) : (L)0;
             }
         }
         if (f0 + 4 <= n_fl) {
@@ -74,66 +113,92 @@ onehot_kernel(const L* __restrict__ label, uint64_t n_pixels, int K, float* __re
         } else {
             for (uint64_t e = f0; e < n_fl; e++) out[e] = f[e - f0];
         }
+        l0 += lstep;
+        c0 += cstep;
+        if (c0 >= (uint32_t)K) {
+            c0 -= (uint32_t)K;
+            l0++;
+        }
     }
 }
 
-// Band statistics.  Thread-private 64-bit accumulators per band (B <= kMaxB), warp-shuffle + shared-memory
-// reduction, then one 64-bit atomic per (CTA, band, counter).  x*x is split at bit 16 so that the global
-// accumulators cannot overflow 2^64 for any realistic dataset.
+// Band statistics.  Thread-private 64-bit accumulators per band, warp-shuffle + shared-memory reduction, then one
+// 64-bit atomic per (CTA, band, counter).  x*x is split at bit 16 so that the global accumulators cannot overflow
+// 2^64 for any realistic dataset.  kB = compile-time band count (0 = runtime, up to kMaxB):
+// with kB known the pixel is fetched with ONE vector load and the accumulators stay in a few registers.
 constexpr int kMaxB = 16;
 
-template <typename T>
+template <typename T, int kB>
 __global__ void __launch_bounds__(256)
-stats_kernel(const T* __restrict__ img, const uint8_t* __restrict__ valid, uint64_t n_pixels, int B,
+stats_kernel(const T* __restrict__ img, const uint8_t* __restrict__ valid, uint64_t n_pixels, int B_rt,
              unsigned long long* __restrict__ acc) {
-    unsigned long long cnt = 0, sum[kMaxB], sq[kMaxB];
+    constexpr int NB = kB ? kB : kMaxB;
+    const int B = kB ? kB : B_rt;
+    unsigned long long cnt = 0, sum[NB], sq[NB];
 #pragma unroll
-    for (int b = 0; b < kMaxB; b++) sum[b] = sq[b] = 0;
+    for (int b = 0; b < NB; b++) sum[b] = sq[b] = 0;
+    constexpr int PB = kB * (int)sizeof(T);                               // bytes per pixel when known
+    const bool vec_ok = kB && (PB == 2 || PB == 4 || PB == 8 || PB == 16) && (reinterpret_cast<uintptr_t>(img) % (PB ? PB : 1)) == 0;
     for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pixels; p += (uint64_t)gridDim.x * blockDim.x) {
         if (valid && !valid[p]) continue;
         cnt++;
-        const T* px = img + p * (uint64_t)B;
+        if (vec_ok) {
+            uint32_t w[4] = {0, 0, 0, 0};
+            const uint8_t* px = reinterpret_cast<const uint8_t*>(img) + p * (uint64_t)PB;
+            if (PB == 16) { const uint4 v = __ldg(reinterpret_cast<const uint4*>(px)); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+            else if (PB == 8) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(px)); w[0] = v.x; w[1] = v.y; }
+            else if (PB == 4) w[0] = __ldg(reinterpret_cast<const uint32_t*>(px));
+            else w[0] = __ldg(reinterpret_cast<const uint16_t*>(px));
 #pragma unroll
-        for (int b = 0; b < kMaxB; b++) {
-            if (b < B) {
-                const unsigned long long x = (unsigned long long)px[b];
+            for (int b = 0; b < NB; b++) {
+                const unsigned long long x = sizeof(T) == 2 ? ((w[b >> 1] >> (16 * (b & 1))) & 0xFFFFu) : ((w[b >> 2] >> (8 * (b & 3))) & 0xFFu);
                 sum[b] += x;
                 sq[b] += x * x;
             }
+        } else {
+            const T* px = img + p * (uint64_t)B;
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                if (b < B) {
+                    const unsigned long long x = (unsigned long long)px[b];
+                    sum[b] += x;
+                    sq[b] += x * x;
+                }
+            }
         }
     }
-    __shared__ unsigned long long red[8][2 * kMaxB + 1];
+    __shared__ unsigned long long red[8][2 * NB + 1];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) red[wid][2 * kMaxB] = cnt;
+    if (lane == 0) red[wid][2 * NB] = cnt;
 #pragma unroll
-    for (int b = 0; b < kMaxB; b++) {
+    for (int b = 0; b < NB; b++) {
         if (b < B) {
-            unsigned long long s = sum[b], q = sq[b];
+            unsigned long long sv = sum[b], q = sq[b];
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, o);
+                sv += __shfl_xor_sync(0xffffffffu, sv, o);
                 q += __shfl_xor_sync(0xffffffffu, q, o);
             }
             if (lane == 0) {
-                red[wid][b] = s;
-                red[wid][kMaxB + b] = q;
+                red[wid][b] = sv;
+                red[wid][NB + b] = q;
             }
         }
     }
     __syncthreads();
     if (threadIdx.x < B) {
         const int b = threadIdx.x;
-        unsigned long long n = 0, s = 0, q = 0;
+        unsigned long long n = 0, sv = 0, q = 0;
         for (int w = 0; w < 8; w++) {
-            n += red[w][2 * kMaxB];
-            s += red[w][b];
-            q += red[w][kMaxB + b];
+            n += red[w][2 * NB];
+            sv += red[w][b];
+            q += red[w][NB + b];
         }
         // per-CTA q < 2^64 is guaranteed (<= 2^32 per pixel, a CTA sees far fewer than 2^32 pixels)
         atomicAdd(acc + 4 * b + 0, n);
-        atomicAdd(acc + 4 * b + 1, s);
+        atomicAdd(acc + 4 * b + 1, sv);
         atomicAdd(acc + 4 * b + 2, q & 0xFFFFull);
         atomicAdd(acc + 4 * b + 3, q >> 16);
     }
@@ -196,12 +261,17 @@ extern "C" int b2_band_stats(b2_ctx* ctx, const void* img, int dtype, const uint
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const unsigned grid = stream_grid(ctx, n_pixels);
     unsigned long long* a = reinterpret_cast<unsigned long long*>(acc);
-    if (dtype == B2_U8)
-        stats_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(img), valid, n_pixels, B, a);
-    else if (dtype == B2_U16)
-        stats_kernel<uint16_t><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(img), valid, n_pixels, B, a);
-    else
+#define B2_STATS(TY, KB) stats_kernel<TY, KB><<<grid, 256, 0, s>>>(static_cast<const TY*>(img), valid, n_pixels, B, a)
+    if (dtype == B2_U8) {
+        if (B == 2) B2_STATS(uint8_t, 2); else if (B == 4) B2_STATS(uint8_t, 4); else if (B == 8) B2_STATS(uint8_t, 8);
+        else B2_STATS(uint8_t, 0);
+    } else if (dtype == B2_U16) {
+        if (B == 1) B2_STATS(uint16_t, 1); else if (B == 2) B2_STATS(uint16_t, 2); else if (B == 4) B2_STATS(uint16_t, 4);
+        else if (B == 8) B2_STATS(uint16_t, 8); else B2_STATS(uint16_t, 0);
+    } else {
         return fail("b2_band_stats: dtype must be u8 or u16");
+    }
+#undef B2_STATS
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;

@@ -207,6 +207,37 @@ def bench_parse(dev, n_shards=8):
     report("reference: torch copy_ 1 GiB (read+write)", timeit(lambda i: big2.copy_(big), 10), 2 << 30)
 
 
+def bench_k4(dev):
+    """Standalone K4 kernels (cast + normalise, one-hot, exact band statistics)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(4)
+    N, H, W, C, K = 1024, 256, 256, 3, 10
+    imgs = [torch.randint(0, 256, (N, H, W, C), dtype=torch.uint8, device=dev, generator=g) for _ in range(2)]
+    labs = [torch.randint(0, K, (N, H, W), dtype=torch.uint8, device=dev, generator=g) for _ in range(2)]
+    mean = ops.to_device(np.array([127.0, 128.0, 126.5], np.float32), dev)
+    std = ops.to_device(np.array([73.0, 74.0, 72.5], np.float32), dev)
+    ctx = _lib.get_ctx(dev)
+    o_img = torch.empty((N, H, W, C), dtype=torch.float32, device=dev)
+    o_hot = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+    L = _lib.lib()
+
+    def f_norm(i):
+        _lib.check(L.b2_normalise_onehot(ctx.handle, _lib.ptr(imgs[i & 1]), _lib.B2_U8, None, 0, _lib.ptr(mean), _lib.ptr(std),
+                                         N * H * W, C, 1, _lib.ptr(o_img), None, ctx.stream()))
+    report("normalise_kernel u8 -> f32, %d chips 256x256x3" % N, timeit(f_norm, 10), N * H * W * C * 5)
+
+    def f_hot(i):
+        _lib.check(L.b2_normalise_onehot(ctx.handle, None, 0, _lib.ptr(labs[i & 1]), _lib.B2_U8, None, None, N * H * W, 1, K, None,
+                                         _lib.ptr(o_hot), ctx.stream()))
+    report("onehot_kernel u8 -> f32 x10, %d chips 256x256" % N, timeit(f_hot, 10), N * H * W * (1 + 4 * K))
+    st16 = [torch.randint(0, 10001, (256, 512, 512, 4), dtype=torch.int32, device=dev, generator=g).to(torch.int16).view(torch.uint16) for _ in range(2)]
+    acc = torch.zeros((4, 4), dtype=torch.int64, device=dev)
+
+    def f_stats(i):
+        _lib.check(L.b2_band_stats(ctx.handle, _lib.ptr(st16[i & 1]), _lib.B2_U16, None, 256 * 512 * 512, 4, _lib.ptr(acc), ctx.stream()))
+    report("stats_kernel u16 x4 bands, 256 chips 512x512", timeit(f_stats, 10), 256 * 512 * 512 * 4 * 2)
+
+
 def bench_build(dev, n_shards=8):
     """The writer kernel on cfg1 records (uint8 arrays -> framed Examples) and cfg3 records (uint16 -> FloatList)."""
     import bench as B
@@ -241,6 +272,8 @@ def main():
         bench_parse(dev)
     if "build" in which:
         bench_build(dev)
+    if "k4" in which:
+        bench_k4(dev)
     for kind in ("lzw", "lzw_strips_pred2", "deflate", "png"):
         if kind in which or "decode" in which:
             bench_decode(dev, kind)
