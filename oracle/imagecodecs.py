@@ -203,6 +203,38 @@ def decode_image(blob: bytes) -> np.ndarray:
     raise DecodeError("unknown image format")
 
 
+def georef_strings(blob: bytes):
+    """(str(src.get_transform()), str(src.read_crs())) of load_image_rasterio (_img_to_tf_mp.py:49-50), restated from
+    the GeoTIFF tags: affine from ModelTransformation (34264) or ModelPixelScale (33550) + ModelTiepoint (33922) in
+    GDAL order [x0, dx, rx, y0, ry, dy]; CRS from the GeoKeyDirectory's ProjectedCSType (3072) / GeographicType (2048)
+    EPSG code.  Files without georeferencing (PNG, plain TIFF) give GDAL's default transform and no CRS."""
+    gt, crs = [0.0, 1.0, 0.0, 0.0, 0.0, 1.0], "None"
+    if blob[:8] != _PNG_SIG:
+        tags = parse_tiff(blob)["tags"]
+        if 34264 in tags and len(tags[34264]) == 16:
+            m = tags[34264]
+            gt = [m[3], m[0], m[1], m[7], m[4], m[5]]
+        elif 33550 in tags and 33922 in tags and len(tags[33550]) >= 2 and len(tags[33922]) >= 6:
+            sx, sy = tags[33550][0], tags[33550][1]
+            i, j, _, x, y, _ = tags[33922][:6]
+            gt = [x - i * sx, sx, 0.0, y + j * sy, 0.0, -sy]
+        if 34735 in tags and len(tags[34735]) >= 4:
+            d = tags[34735]
+            proj = geog = 0
+            for k in range(d[3]):
+                if 4 * (k + 2) > len(d):
+                    break
+                key, loc, _, val = d[4 * (k + 1):4 * (k + 2)]
+                if loc == 0 and key == 3072:
+                    proj = val
+                elif loc == 0 and key == 2048:
+                    geog = val
+            code = proj if proj not in (0, 32767) else (geog if geog not in (0, 32767) else 0)
+            if code:
+                crs = "EPSG:%d" % code
+    return str([float(v) for v in gt]), crs
+
+
 def image_shape(blob: bytes):
     """(height, width, bands) from the header only — load_image_rasterio(decode=False), :51-53."""
     if blob[:8] == _PNG_SIG:

@@ -25,7 +25,10 @@ def load_image(path, parse_dltile_filename=True, decode=True):
     else:
         h, w, b = imagecodecs.image_shape(blob)
         data = blob
-    return data, h, w, b, partition.tile_key(path, parse_dltile_filename)
+    if parse_dltile_filename:
+        return data, h, w, b, partition.tile_key(path, True)
+    gt_str, crs_str = imagecodecs.georef_strings(blob)                                  # :49-50
+    return data, h, w, b, "|".join((os.path.basename(path), gt_str, crs_str))         # :63-67
 
 
 def build_record(img_path, lbl_path, dltile_from_filename=True, store_as_array=True):

@@ -1,0 +1,90 @@
+"""-m gpu: the drop-in translators (images_to_tfrecords_mp / _mt) against the oracle's restatement of the reference
+worker loop: same shard files, byte for byte, including skipped chips, empty shards and every identifier flavour."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+import synthetic as syn
+from oracle import partition as opart
+from oracle import tfrecord as otfr
+from oracle import translate as otr
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_dataset(root, kind, n, size, corrupt=(), mismatch=()):
+    os.makedirs(root / "images")
+    os.makedirs(root / "labels")
+    ext = "png" if kind == "png" else "tif"
+    for i in range(n):
+        if kind == "png":
+            img, lab, key = syn.cfg1_chip(i, size=size)
+            a, b = syn.png_bytes(img), syn.png_bytes(lab)
+        else:
+            img, lab, key = syn.cfg3_chip(i, size=size)
+            a, b = syn.tiff_bytes(img, tile=32), syn.tiff_bytes(lab, tile=32, nodata=255)
+        name = key.replace(":", "#")
+        if i in corrupt:
+            a = a[:len(a) // 2]
+        (root / "images" / (name + "." + ext)).write_bytes(a)
+        lname = name + ("x" if i in mismatch else "")
+        (root / "labels" / (lname + "." + ext)).write_bytes(b)
+    return ext
+
+
+def _same_shards(a, b):
+    fa, fb = sorted(os.listdir(a)), sorted(os.listdir(b))
+    assert fa == fb and fa
+    for f in fa:
+        assert open(os.path.join(a, f), "rb").read() == open(os.path.join(b, f), "rb").read(), f
+    return fa
+
+
+@pytest.mark.parametrize("kind,store_as_array", [("png", True), ("png", False), ("tif", True), ("tif", False)])
+def test_images_to_tfrecords_mp_matches_reference_worker_loop(dev, tmp_path, kind, store_as_array):
+    import dl_image_segmentation_b200 as pkg
+    n = 23
+    ext = _write_dataset(tmp_path, kind, n, 48 if kind == "png" else 64, corrupt=(5,), mismatch=(11,))
+    out_g, out_c = str(tmp_path / "g"), str(tmp_path / "c")
+    with contextlib.redirect_stdout(io.StringIO()) as log:
+        wrote = pkg.images_to_tfrecords_mp("t", str(tmp_path), out_g, 6, num_proc=3, file_ext=ext, store_as_array=store_as_array)
+    want = otr.images_to_tfrecords("t", str(tmp_path), out_c, 6, num_proc=3, file_ext=ext, store_as_array=store_as_array, n_jobs=1)
+    files = _same_shards(out_g, out_c)
+    assert len(files) == 6 and files[0] == "t-00000-of-00006"
+    skipped = 1 + (1 if store_as_array else 0)      # the key mismatch always skips; the truncated file only fails when decoded
+    assert sum(wrote) == want
+    assert log.getvalue().count("SKIPPED: Unexpected eror while decoding") >= skipped
+    total = sum(len(otfr.read_records(open(os.path.join(out_g, f), "rb").read(), verify=True)) for f in files)
+    assert total == want and total <= n - 1
+
+
+def test_georeferenced_identifiers_and_more_shards_than_chips(dev, tmp_path):
+    """dltile_from_filename=False (identifier = name|geotransform|crs) and shards that stay empty."""
+    import dl_image_segmentation_b200 as pkg
+    ext = _write_dataset(tmp_path, "tif", 3, 32)
+    out_g, out_c = str(tmp_path / "g"), str(tmp_path / "c")
+    with contextlib.redirect_stdout(io.StringIO()):
+        pkg.images_to_tfrecords_mp("e", str(tmp_path), out_g, 4, num_proc=2, file_ext=ext, dltile_from_filename=False)
+    otr.images_to_tfrecords("e", str(tmp_path), out_c, 4, num_proc=2, file_ext=ext, dltile_from_filename=False, n_jobs=1)
+    files = _same_shards(out_g, out_c)
+    assert len(files) == 4
+    ids = []
+    from oracle import example_proto as oep
+    for f in files:
+        for r in otfr.read_records(open(os.path.join(out_g, f), "rb").read(), verify=True):
+            ids.append(oep.parse_example(r)["identifier"][1][0].decode())
+    assert len(ids) == 3 and all(i.endswith("|[499980.0, 10.0, 0.0, 5300040.0, 0.0, -10.0]|EPSG:32643") for i in ids)
+
+
+@pytest.mark.parametrize("store_as_array", [False, True])
+def test_images_to_tfrecords_mt_png(dev, tmp_path, store_as_array):
+    import dl_image_segmentation_b200 as pkg
+    _write_dataset(tmp_path, "png", 10, 40)
+    out_g, out_c = str(tmp_path / "g"), str(tmp_path / "c")
+    with contextlib.redirect_stdout(io.StringIO()):
+        pkg.images_to_tfrecords_mt("m", str(tmp_path), out_g, 2, num_threads=2, store_as_array=store_as_array)
+    otr.images_to_tfrecords("m", str(tmp_path), out_c, 2, num_proc=2, file_ext="png", store_as_array=store_as_array, n_jobs=1)
+    _same_shards(out_g, out_c)
