@@ -447,3 +447,85 @@ def test_captured_pass_graph_replay(dev):
             np.testing.assert_array_equal(gi.cpu().numpy().reshape(wi.shape), wi)
             np.testing.assert_array_equal(gt.cpu().numpy().reshape(wt.shape), wt)
     assert cp.launches_per_replay == 3 * len(shards)
+
+
+def test_index_fuzz_against_oracle_parser(dev):
+    """Seeded fuzz: random key orders, unknown extra features, duplicate keys, dropped / mistyped required keys, empty and
+    multi-kilobyte payloads, float-list payloads, odd identifiers.  The device index must agree with the oracle's
+    protobuf walk on every record: same status class, same payload bytes, dims and identifier."""
+    from dl_image_segmentation_b200 import ops
+    rng = np.random.default_rng(77)
+    recs, expect = [], []
+    for i in range(160):
+        h, w, c = int(rng.integers(1, 40)), int(rng.integers(1, 40)), int(rng.integers(1, 5))
+        floats = bool(rng.integers(0, 2))
+        if floats:
+            img = rng.integers(0, 60000, (h, w, c)).astype(np.uint16)
+        else:
+            img = rng.integers(0, 256, (h, w, c)).astype(np.uint8)
+        lab = rng.integers(0, 256, (h, w)).astype(np.uint8)
+        key = "".join(chr(int(x)) for x in rng.integers(33, 127, int(rng.integers(0, 200))))
+        ex = oep.convert_to_example(img, lab, h, w, c, h, w, key)
+        feats = dict(ex.features)
+        order = list(feats)
+        rng.shuffle(order)
+        status = 0
+        mode = int(rng.integers(0, 8))
+        if mode == 1:                                        # drop a required key
+            order.remove(order[int(rng.integers(0, len(order)))])
+            status = 2
+        elif mode == 2:                                      # wrong type for a dimension
+            feats["image/width"] = oep.Feature("float", [float(w)])
+            status = 2
+        elif mode == 3:                                      # two values where one is expected
+            feats["target/height"] = oep.Feature("int64", [h, h])
+            status = 2
+        built = {}
+        for k in order:
+            built[k] = feats[k]
+            if rng.random() < 0.3:                           # unknown features sprinkled in between
+                j = int(rng.integers(0, 3))
+                built["zz/%d/%d" % (i, len(built))] = oep.Feature(["bytes", "float", "int64"][j],
+                                                                    [[b"junk" * int(rng.integers(0, 50))], [1.5, -2.0], [7, -9]][j])
+        rec = oep.Example(built).SerializeToString(deterministic=False)
+        if mode == 4:                                        # duplicate key: the later entry wins (protobuf map semantics)
+            dup = oep.Example({"image/height": oep.Feature("int64", [h + 100])}).SerializeToString(deterministic=False)
+            # splice the inner Features entries: outer tag 0x0a + varint length
+            def inner(b):
+                p, ln, sh = 1, 0, 0
+                while True:
+                    x = b[p]; p += 1
+                    ln |= (x & 0x7F) << sh; sh += 7
+                    if not x & 0x80:
+                        break
+                return b[p:p + ln]
+            body = inner(rec) + inner(dup)
+            ln, var = len(body), b""
+            while True:
+                var += bytes([(ln & 0x7F) | (0x80 if ln > 0x7F else 0)])
+                ln >>= 7
+                if not ln:
+                    break
+            rec = b"\x0a" + var + body
+        recs.append(rec)
+        expect.append((status, mode, h, w, c, key))
+    shard = b"".join(otfr.frame(r) for r in recs)
+    si = ops.open_shard(shard, dev)
+    assert si.n == len(recs)
+    for r, (rec, (status, mode, h, w, c, key)) in enumerate(zip(recs, expect)):
+        ix = si.index[r]
+        assert int(ix["status"]) == status, (r, mode)
+        if status:
+            continue
+        f = oep.parse_example(rec)
+        assert int(ix["height"]) == f["image/height"][1][0] == (h + 100 if mode == 4 else h)
+        assert (int(ix["width"]), int(ix["channels"]), int(ix["tgt_height"]), int(ix["tgt_width"])) == (w, c, h, w)
+        kind = {"bytes": 1, "float": 2}[f["image/image_data"][0]]
+        assert int(ix["img_kind"]) == kind == int(ix["tgt_kind"])
+        o, l = int(ix["img_off"]), int(ix["img_len"])
+        if kind == 1:
+            assert shard[o:o + l] == f["image/image_data"][1][0]
+            assert shard[int(ix["tgt_off"]):int(ix["tgt_off"]) + int(ix["tgt_len"])] == f["target/target_data"][1][0]
+        else:
+            assert np.array_equal(np.frombuffer(shard[o:o + l], "<f4"), np.asarray(f["image/image_data"][1], np.float32))
+        assert shard[int(ix["id_off"]):int(ix["id_off"]) + int(ix["id_len"])] == key.encode("utf-8")
