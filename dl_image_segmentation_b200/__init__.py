@@ -13,6 +13,8 @@ from ._tfrecord_image_translation import (convert_to_example, featuretemplate_by
                                           parse_encoded_gdal_proto_eager, parse_encoded_gdal_proto_wrapped,
                                           parse_encoded_rgb_img_proto, parse_higher_dtype_array_proto)
 
+from ._geotiff import encode_geotiffs, write_chip_pair  # noqa: F401
+
 __version__ = "0.1.0"
 from ._img_to_tf_mp import process_dataset_mp as images_to_tfrecords_mp  # noqa: F401,E402
 from ._img_to_tf_threaded import process_dataset_multithreaded as images_to_tfrecords_mt  # noqa: F401,E402

@@ -1,0 +1,173 @@
+"""GeoTIFF chip writer on the GPU — the save step of ``create_chips_for_tile`` (reference
+``_descartes_img_chips.py:781-797``: GTiff, ``COMPRESS=LZW``, ``TILED=TRUE``, bands written one by one, nodata on the
+label band ``:794-795``) with the georeferencing of ``_gdal_dataset_from_geocontext`` (``:804-849``).
+
+The pixels never leave the device uncompressed: ``b2_tile_split`` cuts the (H,W,bands) raster into zero-padded
+256x256 pixel-interleaved tiles, ``b2_lzw_encode`` compresses every tile of a whole batch of chips in one launch,
+and only the code streams come back to the host, where the IFD (baseline tags, GeoTIFF keys, GDAL_NODATA) is put
+around them.  Files are classic little-endian TIFF, PlanarConfiguration 1, Predictor 1 — what GDAL writes for these
+options — and read back bit-exactly through libtiff (tests) and through the K1 decoder.
+"""
+import ctypes
+import os
+import struct
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import B2Error, check, get_ctx, lib, ptr
+
+ENC_DESC_DTYPE = np.dtype([("src_off", "<u8"), ("dst_off", "<u8"), ("src_len", "<u4"), ("dst_cap", "<u4")])
+_vp, _i = ctypes.c_void_p, ctypes.c_int
+_lib.register_signatures({
+    "b2_lzw_encode": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "b2_tile_split": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+})
+
+_SAMPLE_FORMAT = {"u": 1, "i": 2, "f": 3}
+_NP_OF_TORCH = {torch.uint8: np.uint8, torch.int8: np.int8, torch.int16: np.int16, torch.int32: np.int32,
+                torch.float32: np.float32, torch.float64: np.float64}
+for _n, _t in (("uint16", np.uint16), ("uint32", np.uint32)):
+    if hasattr(torch, _n):
+        _NP_OF_TORCH[getattr(torch, _n)] = _t
+
+
+def lzw_encode_tiles(raw, lengths, device=None):
+    """TIFF-LZW encode consecutive byte ranges of one device buffer.  raw: uint8 CUDA tensor; lengths: list of ints
+    (ranges are back to back, each padded to 16 bytes).  Returns list of bytes (the code streams)."""
+    ctx = get_ctx(device)
+    n = len(lengths)
+    descs = np.zeros(n, ENC_DESC_DTYPE)
+    so = do = 0
+    for k, ln in enumerate(lengths):
+        cap = (int(ln) * 3) // 2 + 64
+        descs[k] = (so, do, int(ln), cap)
+        so += (int(ln) + 15) & ~15
+        do += (cap + 15) & ~15
+    out = torch.empty((max(do, 16),), dtype=torch.uint8, device=ctx.device)
+    out_len = torch.empty((n,), dtype=torch.int32, device=ctx.device)
+    d_dev = torch.from_numpy(descs.view(np.uint8).reshape(-1)).to(ctx.device)
+    check(lib().b2_lzw_encode(ctx.handle, ptr(raw), ptr(d_dev), n, ptr(out), ptr(out_len), ctx.stream()))
+    lens = out_len.cpu().numpy().view(np.uint32)
+    if (lens == 0xFFFFFFFF).any():
+        raise B2Error("b2_lzw_encode: output capacity exceeded")
+    host = out.cpu().numpy()
+    return [host[int(descs[k]["dst_off"]):int(descs[k]["dst_off"]) + int(lens[k])].tobytes() for k in range(n)]
+
+
+def _ifd(width, height, bands, np_dtype, tile, blocks, nodata, geotransform, epsg):
+    """Classic little-endian TIFF around the compressed tiles: header, one IFD (tags ascending), out-of-line values,
+    tile data."""
+    dt = np.dtype(np_dtype)
+    ent = {}
+
+    def put(tag, typ, fmt, vals):
+        ent[tag] = (typ, len(vals), struct.pack("<%d%s" % (len(vals), fmt), *vals))
+    put(256, 3, "H", [width])
+    put(257, 3, "H", [height])
+    put(258, 3, "H", [dt.itemsize * 8] * bands)
+    put(259, 3, "H", [5])                                                  # LZW
+    rgb = bands >= 3 and dt == np.uint8                                     # GDAL: RGB only for >= 3 Byte bands
+    put(262, 3, "H", [2 if rgb else 1])
+    put(277, 3, "H", [bands])
+    put(284, 3, "H", [1])                                                  # pixel-interleaved
+    extra = bands - (3 if rgb else 1)
+    if extra > 0:
+        put(338, 3, "H", [0] * extra)
+    put(339, 3, "H", [_SAMPLE_FORMAT[dt.kind]] * bands)
+    put(322, 3, "H", [tile])
+    put(323, 3, "H", [tile])
+    if geotransform is not None:
+        x0, dx, _, y0, _, dy = [float(v) for v in geotransform]
+        put(33550, 12, "d", [dx, -dy, 0.0])
+        put(33922, 12, "d", [0.0, 0.0, 0.0, x0, y0, 0.0])
+        if epsg:
+            put(34735, 3, "H", [1, 1, 0, 3, 1024, 0, 1, 1, 1025, 0, 1, 1, 3072, 0, 1, int(epsg)])
+    if nodata is not None:
+        s = str(nodata).encode() + b"\0"
+        ent[42113] = (2, len(s), s)
+    put(324, 4, "I", [0] * len(blocks))
+    put(325, 4, "I", [len(b) for b in blocks])
+    tags = sorted(ent)
+    ifd_off = 8
+    extra_off = ifd_off + 2 + 12 * len(tags) + 4
+    tail = bytearray()
+    where = {}
+    for t in tags:
+        typ, cnt, val = ent[t]
+        if len(val) > 4:
+            if len(tail) % 2:
+                tail += b"\0"
+            where[t] = len(tail)
+            tail += val
+    data_off = extra_off + len(tail)
+    offs, cur = [], data_off
+    for b in blocks:
+        offs.append(cur)
+        cur += len(b)
+    ob = struct.pack("<%dI" % len(offs), *offs)
+    if 324 in where:
+        tail[where[324]:where[324] + len(ob)] = ob
+    out = bytearray(b"II" + struct.pack("<HI", 42, ifd_off) + struct.pack("<H", len(tags)))
+    for t in tags:
+        typ, cnt, val = ent[t]
+        if t == 324 and 324 not in where:
+            val = ob
+        field = struct.pack("<I", extra_off + where[t]) if t in where else val.ljust(4, b"\0")
+        out += struct.pack("<HHI", t, typ, cnt) + field
+    out += struct.pack("<I", 0) + tail + b"".join(blocks)
+    return bytes(out)
+
+
+def encode_geotiffs(arrays, nodata=None, geotransform=(499980.0, 10.0, 0.0, 5300040.0, 0.0, -10.0), epsg=32643, tile=256,
+                    device=None):
+    """A batch of (H,W,bands) / (H,W) rasters (CUDA tensors or numpy arrays, any TIFF sample type) -> list of GeoTIFF
+    file bytes.  nodata: one value for all, or a list (None entries = no GDAL_NODATA tag).  All tiles of the batch are
+    compressed in ONE b2_lzw_encode launch."""
+    ctx = get_ctx(device)
+    n = len(arrays)
+    nod = list(nodata) if isinstance(nodata, (list, tuple)) else [nodata] * n
+    metas, lengths, parts = [], [], []
+    for a in arrays:
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+        t = t.to(ctx.device).contiguous()
+        if t.dim() == 2:
+            t = t[:, :, None]
+        if t.dtype == torch.bool:
+            t = t.to(torch.uint8)
+        if t.dtype not in _NP_OF_TORCH:
+            raise B2Error("encode_geotiffs: unsupported dtype %s" % t.dtype)
+        H, W, B = (int(x) for x in t.shape)
+        pb = B * t.element_size()
+        across, down = (W + tile - 1) // tile, (H + tile - 1) // tile
+        tb = tile * tile * pb
+        tiles = torch.empty((across * down * tb,), dtype=torch.uint8, device=ctx.device)
+        check(lib().b2_tile_split(ctx.handle, ptr(t), H, W, pb, tile, tile, ptr(tiles), ctx.stream()))
+        parts.append(tiles)
+        lengths += [tb] * (across * down)
+        metas.append((W, H, B, _NP_OF_TORCH[t.dtype], across * down))
+    raw = torch.cat(parts) if len(parts) > 1 else parts[0]                  # tile sizes are multiples of 16
+    streams = lzw_encode_tiles(raw, lengths, ctx.device)
+    files, k = [], 0
+    for (W, H, B, dt, nb), nd in zip(metas, nod):
+        files.append(_ifd(W, H, B, dt, tile, streams[k:k + nb], nd, geotransform, epsg))
+        k += nb
+    return files
+
+
+def write_chip_pair(img_arr, lbl_arr, out_base, dltile_key, label_ndv=None, geotransform=(499980.0, 10.0, 0.0, 5300040.0, 0.0, -10.0),
+                    epsg=32643, device=None):
+    """The tail of create_chips_for_tile (reference :735-800): images/<key>.tif and labels/<key>.tif under out_base,
+    ':' replaced by '#'; the label gets the nodata value.  Returns (img_file, lbl_file)."""
+    out_img_folder, out_lbl_folder = os.path.join(out_base, "images"), os.path.join(out_base, "labels")
+    os.makedirs(out_img_folder, exist_ok=True)
+    os.makedirs(out_lbl_folder, exist_ok=True)
+    fn = dltile_key.replace(":", "#")
+    img_file, lbl_file = os.path.join(out_img_folder, fn) + ".tif", os.path.join(out_lbl_folder, fn) + ".tif"
+    a, b = encode_geotiffs([img_arr, lbl_arr], nodata=[None, label_ndv], geotransform=geotransform, epsg=epsg, device=device)
+    with open(img_file, "wb") as f:
+        f.write(a)
+    with open(lbl_file, "wb") as f:
+        f.write(b)
+    return img_file, lbl_file

@@ -268,6 +268,26 @@ int b2_assemble_images(b2_ctx* ctx, uint8_t* scratch_dev, const b2_image_desc* i
                        const b2_image_desc* images_host, int n_images, uint8_t* out_dev, int32_t* status_dev,
                        b2_stream stream);
 
+/* ------------------------------------------------------------------ K1w: GeoTIFF writer (tile split + TIFF-LZW encode)
+ * Replace GDAL's GTiff driver with COMPRESS=LZW, TILED=TRUE behind _gdal_dataset_from_geocontext + WriteArray
+ * (_descartes_img_chips.py:781-797, 804-849): the chip pair a composite is saved as.  The IFD / GeoTIFF tags are
+ * assembled on the host (dl_image_segmentation_b200/_geotiff.py). */
+typedef struct {
+    uint64_t src_off;    /* raw tile bytes in raw_dev                                                          */
+    uint64_t dst_off;    /* where the code stream goes in out_dev (multiple of 4)                              */
+    uint32_t src_len;
+    uint32_t dst_cap;    /* 3/2 * src_len + 16 always suffices                                                 */
+} b2_enc_desc;
+
+/* TIFF-LZW encode n streams (MSB-first, leading Clear, early-change widths, Clear at 4094 entries, EOI).
+ * out_len_dev[i] = bytes produced, 0xFFFFFFFF if dst_cap was too small. */
+int b2_lzw_encode(b2_ctx* ctx, const uint8_t* raw_dev, const b2_enc_desc* descs_dev, int n, uint8_t* out_dev,
+                  uint32_t* out_len_dev, b2_stream stream);
+
+/* (H,W) raster of pixel_bytes-byte pixels (bands interleaved) -> zero-padded tile_w x tile_h tiles, tile-major. */
+int b2_tile_split(b2_ctx* ctx, const uint8_t* img_dev, int H, int W, int pixel_bytes, int tile_w, int tile_h,
+                  uint8_t* tiles_dev, b2_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

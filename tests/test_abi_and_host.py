@@ -23,7 +23,7 @@ LIB = os.path.join(ROOT, "dl_image_segmentation_b200", "libb2chips.so")
 def lib():
     if not os.path.exists(LIB):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "dl_image_segmentation_b200", "csrc"), "-j8"])
-    from dl_image_segmentation_b200 import _codec, _lib  # noqa: F401  (registers the codec signatures)
+    from dl_image_segmentation_b200 import _codec, _geotiff, _lib  # noqa: F401  (register the codec / writer signatures)
     return _lib.lib()
 
 

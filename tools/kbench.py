@@ -238,6 +238,32 @@ def bench_k4(dev):
     report("stats_kernel u16 x4 bands, 256 chips 512x512", timeit(f_stats, 10), 256 * 512 * 512 * 4 * 2)
 
 
+def bench_encode(dev, n_chips=256):
+    """GeoTIFF writer: tile split + TIFF-LZW encode of cfg3-style chips (512x512x4 u16 + 512x512 u8 labels)."""
+    import time
+
+    import synthetic as syn
+    from dl_image_segmentation_b200 import _geotiff
+    arrs = []
+    for i in range(16):
+        img, lab, _ = syn.cfg3_chip(i)
+        arrs += [torch.from_numpy(img.view(np.int16)).to(dev).view(torch.uint16), torch.from_numpy(lab).to(dev)]
+    batch = (arrs * ((2 * n_chips + len(arrs) - 1) // len(arrs)))[:2 * n_chips]
+    nd = [None, 255] * n_chips
+    best = None
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        files = _geotiff.encode_geotiffs(batch, nodata=nd, device=dev)
+        torch.cuda.synchronize()
+        dt = (time.time() - t0) * 1e3
+        best = dt if best is None or dt < best else best
+    raw = sum(int(a.numel()) * a.element_size() for a in batch)
+    report("encode GeoTIFF (tile split + LZW) %d chip pairs, wall incl. D2H + IFD" % n_chips, best, raw + sum(len(f) for f in files),
+           {"chip_pairs_per_s": round(n_chips / best * 1e3, 1), "raw_GB/s": round(raw / best / 1e6, 2),
+            "compressed_fraction": round(sum(len(f) for f in files) / raw, 3)})
+
+
 def bench_build(dev, n_shards=8):
     """The writer kernel on cfg1 records (uint8 arrays -> framed Examples) and cfg3 records (uint16 -> FloatList)."""
     import bench as B
@@ -274,6 +300,8 @@ def main():
         bench_build(dev)
     if "k4" in which:
         bench_k4(dev)
+    if "encode" in which:
+        bench_encode(dev)
     for kind in ("lzw", "lzw_strips_pred2", "deflate", "png"):
         if kind in which or "decode" in which:
             bench_decode(dev, kind)
