@@ -33,32 +33,41 @@ for _n, _t in (("uint16", np.uint16), ("uint32", np.uint32)):
         _NP_OF_TORCH[getattr(torch, _n)] = _t
 
 
-def lzw_encode_tiles(raw, lengths, device=None):
-    """TIFF-LZW encode consecutive byte ranges of one device buffer.  raw: uint8 CUDA tensor; lengths: list of ints
-    (ranges are back to back, each padded to 16 bytes).  Returns list of bytes (the code streams)."""
+def _encode_compact(raw, lengths, device=None):
+    """TIFF-LZW encode consecutive byte ranges of one device buffer (back to back, each padded to 16 bytes).
+    Returns (host uint8 array holding all code streams back to back, numpy array of their lengths)."""
     ctx = get_ctx(device)
     n = len(lengths)
+    ln = np.asarray(lengths, dtype=np.int64)
+    cap = (ln * 3) // 2 + 64
     descs = np.zeros(n, ENC_DESC_DTYPE)
-    so = do = 0
-    for k, ln in enumerate(lengths):
-        cap = (int(ln) * 3) // 2 + 64
-        descs[k] = (so, do, int(ln), cap)
-        so += (int(ln) + 15) & ~15
-        do += (cap + 15) & ~15
-    out = torch.empty((max(do, 16),), dtype=torch.uint8, device=ctx.device)
+    descs["src_len"], descs["dst_cap"] = ln, cap
+    descs["src_off"] = np.concatenate(([0], np.cumsum((ln + 15) & ~15)[:-1]))
+    dcap = (cap + 15) & ~15
+    descs["dst_off"] = np.concatenate(([0], np.cumsum(dcap)[:-1]))
+    out = torch.empty((max(int(dcap.sum()), 16),), dtype=torch.uint8, device=ctx.device)
     out_len = torch.empty((n,), dtype=torch.int32, device=ctx.device)
     d_dev = torch.from_numpy(descs.view(np.uint8).reshape(-1)).to(ctx.device)
     check(lib().b2_lzw_encode(ctx.handle, ptr(raw), ptr(d_dev), n, ptr(out), ptr(out_len), ctx.stream()))
-    lens = out_len.cpu().numpy().view(np.uint32)
+    lens = out_len.cpu().numpy().view(np.uint32).astype(np.int64)          # small read-back; waits for the encoder
     if (lens == 0xFFFFFFFF).any():
         raise B2Error("b2_lzw_encode: output capacity exceeded")
-    host = out.cpu().numpy()
-    return [host[int(descs[k]["dst_off"]):int(descs[k]["dst_off"]) + int(lens[k])].tobytes() for k in range(n)]
+    # compact the code streams on the device (the capacity slots are 1.5x the raw size), then ONE copy to the host
+    packed = torch.cat([out[int(o):int(o) + int(l)] for o, l in zip(descs["dst_off"], lens)]) if n else out[:0]
+    return packed.cpu().numpy(), lens
 
 
-def _ifd(width, height, bands, np_dtype, tile, blocks, nodata, geotransform, epsg):
+def lzw_encode_tiles(raw, lengths, device=None):
+    """As _encode_compact, returning one bytes object per stream."""
+    host, lens = _encode_compact(raw, lengths, device)
+    ends = np.cumsum(lens)
+    return [host[int(e - l):int(e)].tobytes() for e, l in zip(ends, lens)]
+
+
+def _ifd(width, height, bands, np_dtype, tile, block_lens, block_data, nodata, geotransform, epsg):
     """Classic little-endian TIFF around the compressed tiles: header, one IFD (tags ascending), out-of-line values,
-    tile data."""
+    tile data (block_data = the code streams of this file back to back, a buffer)."""
+    blocks = [None] * len(block_lens)
     dt = np.dtype(np_dtype)
     ent = {}
 
@@ -88,7 +97,7 @@ def _ifd(width, height, bands, np_dtype, tile, blocks, nodata, geotransform, eps
         s = str(nodata).encode() + b"\0"
         ent[42113] = (2, len(s), s)
     put(324, 4, "I", [0] * len(blocks))
-    put(325, 4, "I", [len(b) for b in blocks])
+    put(325, 4, "I", [int(l) for l in block_lens])
     tags = sorted(ent)
     ifd_off = 8
     extra_off = ifd_off + 2 + 12 * len(tags) + 4
@@ -103,9 +112,9 @@ def _ifd(width, height, bands, np_dtype, tile, blocks, nodata, geotransform, eps
             tail += val
     data_off = extra_off + len(tail)
     offs, cur = [], data_off
-    for b in blocks:
+    for l in block_lens:
         offs.append(cur)
-        cur += len(b)
+        cur += int(l)
     ob = struct.pack("<%dI" % len(offs), *offs)
     if 324 in where:
         tail[where[324]:where[324] + len(ob)] = ob
@@ -116,8 +125,8 @@ def _ifd(width, height, bands, np_dtype, tile, blocks, nodata, geotransform, eps
             val = ob
         field = struct.pack("<I", extra_off + where[t]) if t in where else val.ljust(4, b"\0")
         out += struct.pack("<HHI", t, typ, cnt) + field
-    out += struct.pack("<I", 0) + tail + b"".join(blocks)
-    return bytes(out)
+    out += struct.pack("<I", 0) + tail
+    return b"".join((bytes(out), block_data))
 
 
 def encode_geotiffs(arrays, nodata=None, geotransform=(499980.0, 10.0, 0.0, 5300040.0, 0.0, -10.0), epsg=32643, tile=256,
@@ -148,11 +157,14 @@ def encode_geotiffs(arrays, nodata=None, geotransform=(499980.0, 10.0, 0.0, 5300
         lengths += [tb] * (across * down)
         metas.append((W, H, B, _NP_OF_TORCH[t.dtype], across * down))
     raw = torch.cat(parts) if len(parts) > 1 else parts[0]                  # tile sizes are multiples of 16
-    streams = lzw_encode_tiles(raw, lengths, ctx.device)
-    files, k = [], 0
+    host, lens = _encode_compact(raw, lengths, ctx.device)
+    mv = memoryview(host)
+    files, k, pos = [], 0, 0
     for (W, H, B, dt, nb), nd in zip(metas, nod):
-        files.append(_ifd(W, H, B, dt, tile, streams[k:k + nb], nd, geotransform, epsg))
+        size = int(lens[k:k + nb].sum())
+        files.append(_ifd(W, H, B, dt, tile, lens[k:k + nb], mv[pos:pos + size], nd, geotransform, epsg))
         k += nb
+        pos += size
     return files
 
 

@@ -16,13 +16,16 @@
 
 namespace b2 {
 
-constexpr int kEncWarps = 2;            // streams per CTA
+constexpr int kEncWarps = 4;            // streams per CTA
 constexpr int kEncSlots = 8192;         // hash slots per stream (4094 entries at most: load < 0.5)
 constexpr int kEncWin = 2048;           // staged input bytes per refill
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 
+// The dictionary of a stream — kEncSlots words of (key << 12) | code, key = (prefix << 8) | byte — lives in the context
+// workspace, not in shared memory: the walk is latency-bound (a few hundred cycles per input byte whatever memory the
+// table is in), so what counts is how many streams are resident, and 32 KiB of shared memory per stream would allow
+// six per SM where the L2-resident tables allow sixty-four.
 struct EncSmem {
-    uint32_t table[kEncSlots];          // (key << 12) | code, key = (prefix << 8) | byte
     uint8_t win[kEncWin];
 };
 
@@ -63,9 +66,10 @@ struct BitWriter {
 
 __global__ void __launch_bounds__(kEncWarps * 32)
 lzw_encode_kernel(const uint8_t* __restrict__ raw, const b2_enc_desc* __restrict__ descs, int n, uint8_t* __restrict__ out,
-                  uint32_t* __restrict__ out_len, unsigned int* next_stream) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    EncSmem* sm = reinterpret_cast<EncSmem*>(smem_raw) + (threadIdx.x >> 5);
+                  uint32_t* __restrict__ out_len, unsigned int* next_stream, uint32_t* tables) {
+    __shared__ __align__(16) EncSmem sm_all[kEncWarps];
+    EncSmem* sm = &sm_all[threadIdx.x >> 5];
+    uint32_t* table = tables + (size_t)(blockIdx.x * kEncWarps + (threadIdx.x >> 5)) * kEncSlots;
     const int lane = threadIdx.x & 31;
     const bool writer = lane == 0;
     for (;;) {                                           // persistent warps draw tiles from a counter
@@ -79,7 +83,7 @@ lzw_encode_kernel(const uint8_t* __restrict__ raw, const b2_enc_desc* __restrict
         BitWriter w{out + d.dst_off, d.dst_cap, 0, 0, 0, false};
         enum { CLEAR = 256, EOI = 257, FIRST = 258, LIMIT = 4094 };
         int nbits = 9, next = FIRST;
-        for (int i = lane; i < kEncSlots; i += 32) sm->table[i] = kEmpty;
+        for (int i = lane; i < kEncSlots; i += 32) __stcg(table + i, kEmpty);
         uint32_t win_lo = 0x80000000u;                   // window = [win_lo, win_lo + kEncWin); the first access misses
         auto byte_at = [&](uint32_t p) -> uint32_t {
             if (p - win_lo >= (uint32_t)kEncWin) {       // warp-uniform: refill with coalesced 16-byte loads
@@ -110,7 +114,7 @@ lzw_encode_kernel(const uint8_t* __restrict__ raw, const b2_enc_desc* __restrict
                 uint32_t h = (key * 2654435761u) >> 19;  // 13 bits
                 uint32_t found = kEmpty;
                 for (;;) {
-                    const uint32_t e = sm->table[h];
+                    const uint32_t e = __ldcg(table + h);
                     if (e == kEmpty) break;
                     if ((e >> 12) == key) { found = e & 0xFFFu; break; }
                     h = (h + 1) & (kEncSlots - 1);
@@ -120,14 +124,14 @@ lzw_encode_kernel(const uint8_t* __restrict__ raw, const b2_enc_desc* __restrict
                     continue;
                 }
                 w.put(cur, nbits, writer);
-                if (writer) sm->table[h] = (key << 12) | (uint32_t)next;
+                if (writer) __stcg(table + h, (key << 12) | (uint32_t)next);
                 __syncwarp();
                 next++;
                 cur = c;
                 if (next == LIMIT) {
                     w.put(CLEAR, nbits, writer);
                     __syncwarp();
-                    for (int k = lane; k < kEncSlots; k += 32) sm->table[k] = kEmpty;
+                    for (int k = lane; k < kEncSlots; k += 32) __stcg(table + k, kEmpty);
                     __syncwarp();
                     nbits = 9;
                     next = FIRST;
@@ -177,19 +181,14 @@ extern "C" int b2_lzw_encode(b2_ctx* ctx, const uint8_t* raw, const b2_enc_desc*
     if (n <= 0) return 0;
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const size_t smem = sizeof(EncSmem) * kEncWarps;
-    static bool attr_set[64] = {false};
-    if (!attr_set[ctx->device & 63]) {
-        B2_CUDA(cudaFuncSetAttribute(lzw_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[ctx->device & 63] = true;
-    }
     unsigned ctas = (unsigned)((n + kEncWarps - 1) / kEncWarps);
-    const unsigned resident = (unsigned)ctx->sm_count * 3;
+    const unsigned resident = (unsigned)ctx->sm_count * (64 / kEncWarps);
     if (ctas > resident) ctas = resident;
-    if (int e = ws_reserve(ctx, 256, s)) return e;
-    unsigned int* counter = static_cast<unsigned int*>(ctx->ws);
+    const size_t table_bytes = (size_t)ctas * kEncWarps * kEncSlots * sizeof(uint32_t);
+    if (int e = ws_reserve(ctx, table_bytes + 256, s)) return e;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(ctx->ws) + table_bytes);
     B2_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
-    lzw_encode_kernel<<<ctas, kEncWarps * 32, smem, s>>>(raw, descs, n, out, out_len, counter);
+    lzw_encode_kernel<<<ctas, kEncWarps * 32, 0, s>>>(raw, descs, n, out, out_len, counter, static_cast<uint32_t*>(ctx->ws));
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;

@@ -238,7 +238,8 @@ def bench_k4(dev):
     report("stats_kernel u16 x4 bands, 256 chips 512x512", timeit(f_stats, 10), 256 * 512 * 512 * 4 * 2)
 
 
-def bench_encode(dev, n_chips=256):
+def bench_encode(dev, n_chips=None):
+    n_chips = n_chips or int(os.environ.get("KB_ENC_CHIPS", "256"))
     """GeoTIFF writer: tile split + TIFF-LZW encode of cfg3-style chips (512x512x4 u16 + 512x512 u8 labels)."""
     import time
 
