@@ -154,22 +154,30 @@ lzw_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ 
         __syncwarp();
         if (tot > dst_len - out) tot = dst_len - out;                  // libtiff truncates the last string
         // ---- bytes: each output byte chases its chain down to a literal or to already-written output
+        // owner of output byte p = last lane whose string starts at or before p.  For the 32 consecutive bytes of a chunk
+        // that is one ballot (strings starting before the chunk) plus one OR-reduction of "a string starts at chunk
+        // byte j" bits; only bytes that refer back INTO this round fall through to the binary search.
+        const uint32_t my_rel = my_off - out;                           // lanes >= m: tot (never an owner of a live byte)
         for (uint32_t base = 0; base < tot; base += 32) {
             const uint32_t idx = base + lane;
+            const uint32_t before = __popc(__ballot_sync(0xffffffffu, lane < m && my_rel < base));
+            const uint32_t starts = __reduce_or_sync(0xffffffffu, (lane < m && my_rel - base < 32u) ? (1u << (my_rel - base)) : 0u);
             if (idx < tot) {
                 uint32_t p = out + idx;
                 uint32_t val = 0;
+                int lo_l = (int)(before + __popc(starts & (0xFFFFFFFFu >> (31 - lane)))) - 1;
                 for (;;) {                                             // p strictly decreases: always terminates
-                    int lo_l = 0, hi_l = m;                            // owner = last lane with b_off <= p
-                    while (hi_l - lo_l > 1) {
-                        const int mid = (lo_l + hi_l) >> 1;
-                        if (sm->b_off[mid] <= p) lo_l = mid; else hi_l = mid;
-                    }
                     const int32_t s = sm->b_src[lo_l];
                     if (s < 0) { val = (uint32_t)(-1 - s); break; }
                     const uint32_t q = (uint32_t)s + (p - sm->b_off[lo_l]);
                     if (q < out) { val = dst[q]; break; }
                     p = q;
+                    int hi_l = m;                                       // in-round reference: owner by binary search
+                    lo_l = 0;
+                    while (hi_l - lo_l > 1) {
+                        const int mid = (lo_l + hi_l) >> 1;
+                        if (sm->b_off[mid] <= p) lo_l = mid; else hi_l = mid;
+                    }
                 }
                 dst[out + idx] = (uint8_t)val;
             }
