@@ -605,10 +605,25 @@ assemble_kernel(const uint8_t* __restrict__ scratch, const b2_image_desc* __rest
     uint8_t* dst = out + im.out_off;
     const bool fast = (im.planar == 1) && !(im.big_endian && bs > 1);
     if (fast) {
-        // row segments are contiguous in both layouts: copy bytes; one loop index = one output byte-quad
+        // row segments are contiguous in both layouts
         const uint64_t rowbytes = (uint64_t)Wd * S * bs;
         const uint64_t total = rowbytes * Hd;
         const uint64_t blk_rowbytes = (uint64_t)im.block_w * S * bs;
+        if ((rowbytes & 15) == 0 && (blk_rowbytes & 15) == 0 && total < (1ull << 35) &&
+            ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | im.block_bytes) & 15) == 0) {
+            // every 16-byte group of the output lies inside one block row: one 128-bit load + store, 32-bit index math
+            const uint32_t gpr = (uint32_t)(rowbytes >> 4), bgpr = (uint32_t)(blk_rowbytes >> 4);
+            const uint32_t groups = gpr * (uint32_t)Hd;
+            const uint32_t blk_g = (uint32_t)(im.block_bytes >> 4);
+            for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+                const uint32_t y = g / gpr, xg = g - y * gpr;
+                const uint32_t bx = xg / bgpr, by = y / (uint32_t)im.block_h;
+                const uint64_t sg = (uint64_t)(by * (uint32_t)im.blocks_across + bx) * blk_g +
+                                    (uint64_t)(y - by * (uint32_t)im.block_h) * bgpr + (xg - bx * bgpr);
+                st_cs(reinterpret_cast<uint4*>(dst) + g, ld_nc(reinterpret_cast<const uint4*>(src) + sg));
+            }
+            return;
+        }
         for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < total; i += (uint64_t)gridDim.x * blockDim.x * 4) {
             uint32_t v = 0;
 #pragma unroll
