@@ -125,6 +125,7 @@ def run_ours(args, rank, world):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        ops.bind_host_to_gpu(local)             # pinned staging memory on the NUMA node next to this rank's GPU
         dist.init_process_group("nccl", device_id=dev)
     ctx = _lib.get_ctx(dev)
     shards = make_shards_on_device(dev, 2002 + rank)

@@ -22,6 +22,26 @@ for _n in ("uint16", "uint32"):
         _T2NP[getattr(torch, _n)] = _n
 
 
+def bind_host_to_gpu(device_index):
+    """Pin this process to the CPU cores (and so, by first touch, the NUMA node) closest to a GPU.  On a multi-GPU box
+    the pinned staging buffers of the streaming paths then sit next to the PCIe root the GPU hangs off, so N ranks
+    uploading at once do not funnel through one socket's memory controllers.  Best effort: returns the CPU set or None."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 class DataLossError(B2Error):
     """A TFRecord frame or data CRC did not verify (TensorFlow raises tf.errors.DataLossError)."""
 
