@@ -299,39 +299,9 @@ __device__ inline void finalize_record(const ParseArgs& a, const RecRef& j, uint
     if (st != 0 && a.n_bad) atomicAdd(reinterpret_cast<unsigned long long*>(a.n_bad), 1ull);
 }
 
-// Per-thread running CRC state over the tiles of one record.  A thread owns vectors i and i+256 of every tile; the
-// distance from the end of one of its vectors to the start of its next one is always 4080 bytes, inside a tile and
-// from one tile to the next, so the same "consume 4 bytes and skip 4080" table step chains them all and the
-// expensive per-thread alignment (one GF(2)[x] multiplication) is paid once per run of tiles, not once per tile.
-// On return the state sits at (tile end + 16 i): run_flush() un-advances by 16 i.
 __device__ __forceinline__ uint32_t crc_tile_step(uint32_t s, const uint4* buf4, const CrcSmem* cs, const TileJob& j,
                                                   bool interior) {
-    const int i = threadIdx.x;
-    uint4 v0 = buf4[i], v1 = buf4[i + 256];
-    if (!interior) {
-        v0 = mask_vec(v0, j.ts + 16ull * i, j.d0, j.d1);
-        v1 = mask_vec(v1, j.ts + 4096 + 16ull * i, j.d0, j.d1);
-        if (j.tile == 0 && i < 2) {  // init XOR lives in the first 4 data bytes, i.e. inside vectors 0/1 of tile 0
-            uint32_t w[4] = {v0.x, v0.y, v0.z, v0.w};
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint64_t p = j.ts + 16ull * i + 4 * q + k;
-                    if (p >= j.d0 && p < j.d0 + 4) w[q] ^= 0xFFu << (8 * k);
-                }
-            v0 = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-    }
-    s = adv4(cs->t4, s ^ v0.x);
-    s = adv4(cs->t4, s ^ v0.y);
-    s = adv4(cs->t4, s ^ v0.z);
-    s = adv4(cs->s, s ^ v0.w);
-    s = adv4(cs->t4, s ^ v1.x);
-    s = adv4(cs->t4, s ^ v1.y);
-    s = adv4(cs->t4, s ^ v1.z);
-    s = adv4(cs->s, s ^ v1.w);
-    return s;
+    return crc_running_step(s, buf4, cs, j.ts, j.d0, j.d1, j.tile == 0, interior);
 }
 
 struct Run {             // consecutive tiles of one record handled by this CTA (uniform across the consumer warps)

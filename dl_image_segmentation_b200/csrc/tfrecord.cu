@@ -525,19 +525,23 @@ __device__ __forceinline__ uint32_t payload_word(const void* src, int kind, int 
     return __funnelshift_r(b0, b1, (uint32_t)(j & 3) * 8);
 }
 
+constexpr int kBuildRun = 4;   // consecutive tiles of one record per CTA: tables, header CRC and the per-thread CRC
+                               // alignment are paid once per run
+
 __global__ void __launch_bounds__(kTileThreads) build_kernel(const BuildArgs a) {
     __shared__ __align__(16) uint4 buf4[kTile / 16];
     __shared__ CrcSmem cs;
     __shared__ uint32_t red[kTileThreads / 32];
     __shared__ uint32_t hdr_crc;
     const int r = blockIdx.y;
-    const uint32_t tile = blockIdx.x;
     const b2_build_desc d = a.descs[r];
     const uint64_t rs = d.out_off, L = d.example_len;
-    const uint64_t d0 = rs + 12, d1 = d0 + L, re = d1;  // footer (4 bytes at d1) is written by the final kernel
+    const uint64_t d0 = rs + 12, d1 = d0 + L, re = d1;  // footer (4 bytes at d1) is written by whoever completes the record
     const uint64_t A = rs & ~15ull;
-    const uint64_t ts = A + (uint64_t)tile * kTile, te = ts + kTile;
-    if (ts >= re) return;
+    const uint32_t t_end = (uint32_t)((re - A + kTile - 1) / kTile);        // tiles of this record (L == 0: header only)
+    const uint32_t t_lo = blockIdx.x * kBuildRun;
+    if (t_lo >= t_end) return;
+    const uint32_t t_hi = t_lo + kBuildRun < t_end ? t_lo + kBuildRun : t_end;
     load_crc_tables(&cs, a.tab);
     if (threadIdx.x == 0) {
         uint32_t s = 0xFFFFFFFFu;
@@ -545,11 +549,60 @@ __global__ void __launch_bounds__(kTileThreads) build_kernel(const BuildArgs a) 
         hdr_crc = mask_crc(~s);
     }
     __syncthreads();
+    uint32_t crc_state = 0;                                              // this thread's running CRC over the run
+  for (uint32_t tile = t_lo; tile < t_hi; tile++) {
+    const uint64_t ts = A + (uint64_t)tile * kTile, te = ts + kTile;
     const uint64_t ib = d.kind == 1 ? d.img_count : d.img_count * 4, tb = d.kind == 1 ? d.tgt_count : d.tgt_count * 4;
     // Example-space segment boundaries
     const uint64_t e1 = d.piece_len[0], e2 = e1 + ib, e3 = e2 + d.piece_len[1], e4 = e3 + tb;
     const uint8_t* sc = a.scaffold + d.scaffold_off;
     uint32_t* buf32 = reinterpret_cast<uint32_t*>(buf4);
+    // Fast path: the whole tile lies inside ONE payload (31 of the 33 tiles of a cfg1 record).  Its bytes are then a
+    // plain copy (BytesList) or a widening to float32 (FloatList) of a contiguous source range at an arbitrary byte
+    // phase: each thread produces 16 tile bytes from two aligned source vectors and a funnel shift.
+    {
+        const int64_t e_lo = (int64_t)ts - (int64_t)d0, e_hi = (int64_t)te - (int64_t)d0;
+        const void* psrc = nullptr;
+        uint64_t pstart = 0, pcount = 0;
+        int pdtype = 0;
+        if (e_lo >= (int64_t)e1 && (uint64_t)e_hi <= e2) { psrc = d.img_src; pstart = (uint64_t)e_lo - e1; pcount = d.img_count; pdtype = d.src_dtype; }
+        else if (e_lo >= (int64_t)e3 && (uint64_t)e_hi <= e4) { psrc = d.tgt_src; pstart = (uint64_t)e_lo - e3; pcount = d.tgt_count; pdtype = d.tgt_dtype; }
+        if (psrc && d.kind == 1 && (reinterpret_cast<uintptr_t>(psrc) & 3) == 0) {
+            // payload bytes [pstart, pstart + kTile) -> tile; source words are 4-byte aligned, phase = pstart & 3
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(psrc) + (pstart & ~3ull));
+            const uint32_t sh = (uint32_t)(pstart & 3) * 8;
+            const uint64_t last_word = (pcount + 3) / 4 - 1 - (pstart >> 2);   // last source word that may be read
+            for (int g = threadIdx.x; g < kTile / 16; g += blockDim.x) {
+                uint32_t wv[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    const uint64_t wi = 4ull * g + k;
+                    wv[k] = (wi <= last_word && (k < 4 || sh)) ? __ldg(q + wi) : 0u;
+                }
+                buf4[g] = make_uint4(__funnelshift_r(wv[0], wv[1], sh), __funnelshift_r(wv[1], wv[2], sh),
+                                     __funnelshift_r(wv[2], wv[3], sh), __funnelshift_r(wv[3], wv[4], sh));
+            }
+            goto staged;
+        }
+        if (psrc && d.kind == 2 && (pdtype == B2_U16 || pdtype == B2_U8)) {
+            // payload bytes = float32(element i) little-endian; tile starts at payload byte pstart (phase pstart & 3)
+            const uint64_t i0 = pstart >> 2;
+            const uint32_t sh = (uint32_t)(pstart & 3) * 8;
+            for (int w = threadIdx.x; w < kTile / 4; w += blockDim.x) {
+                const uint64_t i = i0 + w;
+                uint32_t a, b;
+                if (pdtype == B2_U16) {
+                    a = i < pcount ? __float_as_uint((float)__ldg(static_cast<const uint16_t*>(psrc) + i)) : 0u;
+                    b = (sh && i + 1 < pcount) ? __float_as_uint((float)__ldg(static_cast<const uint16_t*>(psrc) + i + 1)) : 0u;
+                } else {
+                    a = i < pcount ? __float_as_uint((float)__ldg(static_cast<const uint8_t*>(psrc) + i)) : 0u;
+                    b = (sh && i + 1 < pcount) ? __float_as_uint((float)__ldg(static_cast<const uint8_t*>(psrc) + i + 1)) : 0u;
+                }
+                buf32[w] = __funnelshift_r(a, b, sh);
+            }
+            goto staged;
+        }
+    }
     for (int w = threadIdx.x; w < kTile / 4; w += blockDim.x) {
         const uint64_t p = ts + 4ull * w;  // absolute position of this word
         uint32_t word = 0;
@@ -582,6 +635,7 @@ __global__ void __launch_bounds__(kTileThreads) build_kernel(const BuildArgs a) 
         }
         buf32[w] = word;
     }
+staged:
     __syncthreads();
     // write out the bytes of [max(ts,rs), min(te,re))
     const uint8_t* buf8 = reinterpret_cast<const uint8_t*>(buf4);
@@ -594,33 +648,34 @@ __global__ void __launch_bounds__(kTileThreads) build_kernel(const BuildArgs a) 
                 if (p + j >= rs && p + j < re) a.out[p + j] = buf8[16 * k + j];
         }
     }
-    // CRC partial over the data range; the tile grid is anchored at A = rs & ~15.  Thread 0 moves the partial to the end
-    // of the last data tile and merges { CRC, 1 tile } into the record's 64-bit accumulator (atomic XOR + atomic add);
-    // the CTA that completes the record un-advances the zero padding and writes the masked CRC footer.
-    const uint32_t c0 = tile_crc(buf4, &cs, a.tab, ts, d0, d1, /*first_tile=*/ts <= d0 && d0 < te, red);
+    // running CRC over the data range; the tile grid is anchored at A = rs & ~15
+    if (L >= 4 && te > d0) crc_state = crc_running_step(crc_state, buf4, &cs, ts, d0, d1, ts <= d0 && d0 < te, ts >= d0 && te <= d1);
+    __syncthreads();                                                       // buf4 is restaged by the next tile
+  }
+    // End of the run: align the per-thread states with the end of the run's last tile, fold them, move the partial to
+    // the end of the record's last tile and merge { CRC, tiles } into the record's 64-bit accumulator (atomic XOR +
+    // atomic add on one address, applied in program order); the CTA that completes the record un-advances the zero
+    // padding and writes the masked CRC footer.
+    uint32_t t = multmodp_fast(__ldg(&a.tab->xinv16[threadIdx.x]), crc_state);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) t ^= __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t t0 = (uint32_t)((d0 - A) / kTile);                       // first tile holding data
-        const uint32_t t_end = (uint32_t)((re - A + kTile - 1) / kTile);        // tiles of this record (L == 0: header only)
         uint32_t c = 0;
-        if (L >= 4 && tile >= t0) c = multmodp_fast(tile_power(a.tab, t_end - 1 - tile), c0);
-        // XOR into the low word, then count in the high word: two atomics on ONE address are applied in program order,
-        // so whoever sees the count complete also sees every partial (no fence, no retry loop under contention)
+#pragma unroll
+        for (int k = 0; k < kTileThreads / 32; k++) c ^= red[k];
+        if (L >= 4 && c) c = multmodp_fast(tile_power(a.tab, t_end - t_hi), c);
         unsigned long long* acc = a.acc + r;
-        if (c) atomicXor(acc, (unsigned long long)c);
-        const unsigned long long upd = atomicAdd(acc, 1ull << 32) + (1ull << 32);
+        if (L >= 4 && c) atomicXor(acc, (unsigned long long)c);
+        const unsigned long long add = (unsigned long long)(t_hi - t_lo) << 32;
+        const unsigned long long upd = atomicAdd(acc, add) + add;
         if ((uint32_t)(upd >> 32) == t_end) {
             uint32_t crc;
-            if (L < 4) {   // the whole record sits in this CTA's tile(s) written above: bytewise from shared memory is not
-                           // possible across tiles, but L < 4 means header + data fit in at most two tiles; recompute
+            if (L < 4) {   // an Example shorter than 4 bytes has no payload: its bytes are scaffold bytes
+                const uint8_t* sc = a.scaffold + d.scaffold_off;
                 uint32_t s = 0xFFFFFFFFu;
-                for (uint64_t i = 0; i < L; i++) {
-                    const uint64_t x = i;   // Example-space offset
-                    uint32_t bv;
-                    const uint64_t e1 = d.piece_len[0];
-                    if (x < e1) bv = sc[x];
-                    else bv = 0;            // unreachable: an Example shorter than 4 bytes has no payload
-                    s = (s >> 8) ^ __ldg(&a.tab->t4[3][(s ^ bv) & 0xff]);
-                }
+                for (uint64_t i = 0; i < L; i++) s = (s >> 8) ^ __ldg(&a.tab->t4[3][(s ^ sc[i]) & 0xff]);
                 crc = ~s;
             } else {
                 uint32_t accv = (uint32_t)upd;
@@ -717,7 +772,7 @@ extern "C" int b2_tfrecord_build(b2_ctx* ctx, const b2_build_desc* descs, int n,
     if (int e = ws_reserve(ctx, (size_t)n * sizeof(unsigned long long), s)) return e;
     B2_CUDA(cudaMemsetAsync(ctx->ws, 0, (size_t)n * sizeof(unsigned long long), s));
     BuildArgs ba{descs, scaffold, out, ctx->crc_dev, static_cast<unsigned long long*>(ctx->ws), tx, n};
-    build_kernel<<<dim3(tx, n), kTileThreads, 0, s>>>(ba);
+    build_kernel<<<dim3((tx + kBuildRun - 1) / kBuildRun, n), kTileThreads, 0, s>>>(ba);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;

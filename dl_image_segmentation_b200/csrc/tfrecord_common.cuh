@@ -113,6 +113,43 @@ __device__ inline uint32_t xpow8(const CrcTables* tab, uint64_t n) {
 // Fold the per-tile partials of one record into its CRC-32C (one warp per record, all lanes return it).
 __device__ __forceinline__ uint32_t mask_crc(uint32_t c) { return ((c >> 15) | (c << 17)) + 0xa282ead8u; }
 
+// Per-thread running CRC state over consecutive tiles of one record.  A thread owns vectors i and i+256 of every tile; the
+// distance from the end of one of its vectors to the start of its next one is always 4080 bytes, inside a tile and
+// from one tile to the next, so the same "consume 4 bytes and skip 4080" table step chains them all and the
+// expensive per-thread alignment (one GF(2)[x] multiplication) is paid once per run of tiles, not once per tile.
+// On return the state sits at (tile end + 16 i): the caller un-advances by 16 i (xinv16[i]) when the run ends.
+// ts = absolute start of the tile; [d0, d1) = the record's data; first = the tile holding d0 (the 0xFFFFFFFF init is
+// XORed into the first four data bytes); interior = no byte of the tile lies outside [d0, d1).
+__device__ __forceinline__ uint32_t crc_running_step(uint32_t s, const uint4* buf4, const CrcSmem* cs, uint64_t ts, uint64_t d0,
+                                                     uint64_t d1, bool first, bool interior) {
+    const int i = threadIdx.x;
+    uint4 v0 = buf4[i], v1 = buf4[i + 256];
+    if (!interior) {
+        v0 = mask_vec(v0, ts + 16ull * i, d0, d1);
+        v1 = mask_vec(v1, ts + 4096 + 16ull * i, d0, d1);
+        if (first && ts + 16ull * i + 16 > d0 && ts + 16ull * i < d0 + 4) {   // vectors touching the first four data bytes
+            uint32_t w[4] = {v0.x, v0.y, v0.z, v0.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint64_t p = ts + 16ull * i + 4 * q + k;
+                    if (p >= d0 && p < d0 + 4) w[q] ^= 0xFFu << (8 * k);
+                }
+            v0 = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    s = adv4(cs->t4, s ^ v0.x);
+    s = adv4(cs->t4, s ^ v0.y);
+    s = adv4(cs->t4, s ^ v0.z);
+    s = adv4(cs->s, s ^ v0.w);
+    s = adv4(cs->t4, s ^ v1.x);
+    s = adv4(cs->t4, s ^ v1.y);
+    s = adv4(cs->t4, s ^ v1.z);
+    s = adv4(cs->s, s ^ v1.w);
+    return s;
+}
+
 // x^(8*8192*j): advance a tile partial by j tiles
 __device__ __forceinline__ uint32_t tile_power(const CrcTables* tab, uint32_t j) {
     return j < 2048 ? __ldg(&tab->tpow[j]) : xpow8(tab, (uint64_t)j * kTile);
