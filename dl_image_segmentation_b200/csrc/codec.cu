@@ -200,91 +200,259 @@ lzw_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ 
 }
 
 // ================================================================================================ DEFLATE
-struct InfWarpSmem {
-    uint16_t lit_lut[1024];   // (symbol << 4) | length, 0 = not a short code
-    uint16_t dist_lut[256];
-    uint16_t lit_count[16], dist_count[16];
-    uint16_t lit_sym[288], dist_sym[32];
-    uint8_t lens[320];
-    uint16_t cl_lut[128];
-};
-constexpr int kInfWarps = 4;
+// The decode loop is one dependent chain per symbol (peek -> table -> drop), so everything on that chain is kept
+// short: the compressed bytes sit in a 512-byte shared-memory window that the warp refills with coalesced loads
+// one half ahead of the reader (the bit buffer is topped up with one aligned 32-bit word whose fetch was issued a
+// refill earlier), and literal/length and distance codes resolve through two-level tables whose entries carry the
+// base value and the number of extra bits, so no second lookup follows a hit.
+constexpr int kInfWarps = 1;        // one warp per CTA: every shared-memory address in the symbol loop is an immediate
+constexpr int kLitRoot = 10, kDistRoot = 8;
+constexpr int kLitSub = 320, kDistSub = 256;     // second-level entries; a code set needing more decodes bit by bit
+constexpr int kWinWords = 128;
+constexpr int kInfStage = 256;
 
-struct BitReader {
-    const uint8_t* src;
-    uint32_t len, pos;
+// table entry: [15:0] value | [23:16] code bits to drop | [27:24] extra bits (BASE) or index bits (SUB) | [31:28] kind.
+// One flag bit per kind makes each test in the symbol loop a single predicate-setting instruction; a literal sits in
+// the low byte, where a byte store takes it without a shift; no flag = no such code.  E_SUB with value 0xFFFF marks
+// a prefix whose second-level table did not fit (decode bit by bit).
+enum : uint32_t { E_LIT = 1u << 28, E_BASE = 1u << 29, E_EOB = 1u << 30, E_SUB = 1u << 31 };
+constexpr uint32_t kNoSub = 0xFFFFu;
+__device__ __forceinline__ uint32_t ent_drop(uint32_t e) { return __byte_perm(e, 0u, 0x4442); }
+__device__ __forceinline__ uint32_t ent_extra(uint32_t e) { return (e >> 24) & 15u; }
+__device__ __forceinline__ uint32_t ent_value(uint32_t e) { return e & 0xFFFFu; }
+
+struct alignas(16) InfWarpSmem {
+    uint32_t win[kWinWords];
+    uint32_t lit_tab[(1 << kLitRoot) + kLitSub];
+    uint32_t dist_tab[(1 << kDistRoot) + kDistSub];
+    uint16_t code[288];       // build scratch: rank, then bit-reversed canonical code of each symbol
+    uint16_t first[16], offs[16];
+    uint16_t lit_count[16], dist_count[16], cl_count[16];
+    uint16_t lit_sym[288], dist_sym[32], cl_sym[19];
+    uint16_t cl_lut[128];     // (symbol << 4) | length
+    uint8_t lens[320];
+    uint8_t cl_lens[19];
+    alignas(16) uint8_t stage[kInfStage];   // literals waiting for one coalesced store
+};
+
+// Shared-memory load through a 32-bit shared-space address held in a register.  The symbol loop uses this instead of
+// pointers: with pointers the compiler re-derives the shared window base (an S2R) inside the loop, on the critical path.
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// the shared-space address of p as a value the compiler cannot re-derive (so it stays in its register)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+
+struct InfReader {
+    const uint8_t* base;      // 16-byte aligned address at or below the first byte of the stream
+    uint32_t end;             // offset from base of the first byte past the stream
+    uint32_t* win;            // words [W, W+128) of the stream, W = wpos & ~63
+    uint32_t win_s;           // the same, as a shared-space address (kept in a register: see lds32)
+    uint32_t wpos;            // next word (from base) to append to buf
+    uint32_t nextw;           // that word, fetched ahead
+    uint2 nxt;                // this lane's two words of [W+128, W+192), in flight from global memory
     uint64_t buf;
     int cnt;
-    __device__ __forceinline__ void refill() {
-        while (cnt <= 32) {
-            uint32_t w = 0;
-            if (pos + 4 <= len) {
-                w = (uint32_t)src[pos] | ((uint32_t)src[pos + 1] << 8) | ((uint32_t)src[pos + 2] << 16) | ((uint32_t)src[pos + 3] << 24);
-            } else {
-                for (uint32_t j = 0; j < 4; j++)
-                    if (pos + j < len) w |= (uint32_t)src[pos + j] << (8 * j);
+    int lane;
+
+    // this lane's 8 bytes of the 256-byte half window starting at word `w`; bytes past the stream read as zero
+    __device__ __forceinline__ uint2 fetch(uint32_t w) const {
+        const uint64_t b = (uint64_t)w * 4 + (uint32_t)lane * 8;
+        uint2 v = make_uint2(0u, 0u);
+        if (b < end) {
+            v = *reinterpret_cast<const uint2*>(base + b);
+            if (b + 8 > end) {
+                uint64_t x = ((uint64_t)v.y << 32) | v.x;
+                x &= (1ull << (8 * (uint32_t)(end - b))) - 1;
+                v = make_uint2((uint32_t)x, (uint32_t)(x >> 32));
             }
-            buf |= (uint64_t)w << cnt;
-            pos += 4;
+        }
+        return v;
+    }
+    __device__ __forceinline__ void advance() {
+        __syncwarp();
+        *reinterpret_cast<uint2*>(win + (((wpos + 64) & 127) + lane * 2)) = nxt;
+        nxt = fetch(wpos + 128);
+        __syncwarp();
+    }
+    __device__ __forceinline__ void refill() {
+        if (cnt <= 32) {
+            buf |= (uint64_t)nextw << cnt;
             cnt += 32;
+            wpos++;
+            if (__builtin_expect((wpos & 63) == 0, 0)) advance();
+            nextw = lds32(win_s + ((wpos & 127u) << 2));
         }
     }
-    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1)); }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)buf & ((1u << n) - 1u); }
     __device__ __forceinline__ void drop(int n) { buf >>= n; cnt -= n; }
-    __device__ __forceinline__ uint32_t take(int n) { uint32_t v = peek(n); drop(n); return v; }
+    __device__ __forceinline__ uint32_t take(int n) { const uint32_t v = peek(n); drop(n); return v; }
+    // offset from base of the next unconsumed byte (call on a byte boundary)
+    __device__ __forceinline__ uint32_t byte_pos() const { return (uint32_t)(((uint64_t)wpos * 32 - (uint64_t)cnt) >> 3); }
     // true once more bits were consumed than the stream holds
-    __device__ __forceinline__ bool overrun() const { return (int64_t)pos * 8 - cnt > (int64_t)len * 8; }
+    __device__ __forceinline__ bool overrun() const { return (int64_t)wpos * 32 - cnt > (int64_t)end * 8; }
+    __device__ __forceinline__ void seek(uint32_t bytepos) {
+        const uint32_t w = bytepos >> 2, W = w & ~63u;
+        __syncwarp();
+        const uint2 a = fetch(W), b = fetch(W + 64);
+        nxt = fetch(W + 128);
+        *reinterpret_cast<uint2*>(win + ((W & 127) + lane * 2)) = a;
+        *reinterpret_cast<uint2*>(win + (((W + 64) & 127) + lane * 2)) = b;
+        __syncwarp();
+        wpos = w;
+        buf = 0;
+        cnt = 0;
+        nextw = lds32(win_s + ((wpos & 127u) << 2));
+        refill();
+        drop((int)(bytepos & 3u) * 8);
+        refill();
+    }
 };
 
-// Build LUT (root_bits) + canonical count/symbol arrays from code lengths lens[0..n).  Warp-cooperative.
-// Returns false for an over-subscribed code.
-__device__ bool build_huffman(const uint8_t* lens, int n, uint16_t* lut, int root_bits, uint16_t* count, uint16_t* syms, int lane) {
-    for (int i = lane; i < (1 << root_bits); i += 32) lut[i] = 0;
+__constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+template <bool kDist>
+__device__ __forceinline__ uint32_t sym_entry(int s, int drop) {
+    const uint32_t d = (uint32_t)drop << 16;
+    if (kDist) return s < 30 ? (uint32_t)c_dist_base[s] | E_BASE | ((uint32_t)c_dist_extra[s] << 24) | d : d;
+    if (s < 256) return (uint32_t)s | E_LIT | d;
+    if (s == 256) return E_EOB | d;
+    if (s < 286) return (uint32_t)c_len_base[s - 257] | E_BASE | ((uint32_t)c_len_extra[s - 257] << 24) | d;
+    return d;
+}
+
+// Canonical Huffman code from lens[0..n): counts, per-length first code, symbols sorted by (length, value) and each
+// symbol's bit-reversed code.  Warp-cooperative; false for an over-subscribed set.
+__device__ bool canonical_codes(InfWarpSmem* sm, const uint8_t* lens, int n, uint16_t* count, uint16_t* syms, int lane) {
     if (lane < 16) count[lane] = 0;
     __syncwarp();
-    // counts and canonical first codes (serial: tiny)
-    uint32_t first[16], offs[16];
-    if (lane == 0) {
-        for (int i = 0; i < n; i++) count[lens[i]]++;
-        count[0] = 0;
+    // rank of each symbol among the earlier symbols of its length: 32 symbols per step
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        const int s = c0 + lane;
+        const int l = s < n ? lens[s] : 0;
+        const uint32_t m = __match_any_sync(0xffffffffu, l);
+        const uint32_t before = count[l];
+        __syncwarp();
+        if (s < n) sm->code[s] = (uint16_t)(before + __popc(m & ((1u << lane) - 1u)));
+        if (l && lane == __ffs(m) - 1) count[l] = (uint16_t)(before + __popc(m));
+        __syncwarp();
     }
-    __syncwarp();
     int left = 1;
     uint32_t code = 0, off = 0;
     bool ok = true;
     for (int l = 1; l < 16; l++) {
-        left = (left << 1) - (int)count[l];
+        const int c = count[l];
+        left = (left << 1) - c;
         if (left < 0) ok = false;
-        first[l] = code;
-        offs[l] = off;
-        code = (code + count[l]) << 1;
-        off += count[l];
+        if (lane == 0) { sm->first[l] = (uint16_t)code; sm->offs[l] = (uint16_t)off; }
+        code = (code + c) << 1;
+        off += c;
     }
+    __syncwarp();
     if (!ok) return false;
-    // symbols sorted by (length, value); rank inside a length = number of earlier symbols of the same length
     for (int s = lane; s < n; s += 32) {
         const int l = lens[s];
         if (!l) continue;
-        int rank = 0;
-        for (int t = 0; t < s; t++) rank += (lens[t] == l);
-        syms[offs[l] + rank] = (uint16_t)s;
-        if (l <= root_bits) {
-            uint32_t c = first[l] + rank;                     // canonical code, MSB first
-            uint32_t r = __brev(c) >> (32 - l);               // as it appears in the LSB-first bit stream
-            for (uint32_t i = r; i < (1u << root_bits); i += (1u << l)) lut[i] = (uint16_t)((s << 4) | l);
-        }
+        const uint32_t rank = sm->code[s];
+        syms[sm->offs[l] + rank] = (uint16_t)s;
+        sm->code[s] = (uint16_t)(__brev((uint32_t)sm->first[l] + rank) >> (32 - l));   // as read LSB-first from the stream
     }
     __syncwarp();
     return true;
 }
 
-// canonical bit-by-bit decode for codes longer than the LUT root (puff-style)
-__device__ __forceinline__ int decode_slow(BitReader& br, const uint16_t* count, const uint16_t* syms) {
+// One-level LUT for the code-length code: (symbol << 4) | length.
+__device__ bool build_cl_lut(InfWarpSmem* sm, int lane) {
+    for (int i = lane; i < 128; i += 32) sm->cl_lut[i] = 0;
+    if (!canonical_codes(sm, sm->cl_lens, 19, sm->cl_count, sm->cl_sym, lane)) return false;
+    if (lane < 19) {
+        const int l = sm->cl_lens[lane];
+        if (l) for (uint32_t i = sm->code[lane]; i < 128u; i += (1u << l)) sm->cl_lut[i] = (uint16_t)((lane << 4) | l);
+    }
+    __syncwarp();
+    return true;
+}
+
+// Two-level table: `root` index bits, then per-prefix second-level tables sized for the longest code under the prefix.
+template <bool kDist>
+__device__ bool build_table(InfWarpSmem* sm, const uint8_t* lens, int n, uint32_t* tab, int root, int sub_cap,
+                            uint16_t* count, uint16_t* syms, int lane) {
+    const int nroot = 1 << root;
+    for (int i = lane; i < nroot + sub_cap; i += 32) tab[i] = 0;
+    if (!canonical_codes(sm, lens, n, count, syms, lane)) return false;
+    bool any_long = false;
+    for (int s = lane; s < n; s += 32) {
+        const int l = lens[s];
+        if (!l) continue;
+        const uint32_t r = sm->code[s];
+        if (l <= root) {
+            const uint32_t e = sym_entry<kDist>(s, l);
+            for (uint32_t i = r; i < (uint32_t)nroot; i += (1u << l)) tab[i] = e;
+        } else {
+            atomicMax(tab + (r & (nroot - 1)), (uint32_t)l);       // mark: longest code under this prefix
+            any_long = true;
+        }
+    }
+    __syncwarp();
+    if (!__any_sync(0xffffffffu, any_long)) return true;
+    // allocate the second-level tables in prefix order
+    const int per = nroot / 32;
+    uint32_t mine = 0;
+    for (int i = 0; i < per; i++) {
+        const uint32_t e = tab[lane * per + i];
+        if (e && e < 16u) mine += 1u << (e - root);
+    }
+    uint32_t incl = mine;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    uint32_t off = incl - mine;
+    for (int i = 0; i < per; i++) {
+        const uint32_t e = tab[lane * per + i];
+        if (e && e < 16u) {
+            const uint32_t sb = e - root, size = 1u << sb;
+            tab[lane * per + i] = off + size <= (uint32_t)sub_cap ? (uint32_t)(nroot + off) | E_SUB | (sb << 24) | ((uint32_t)root << 16)
+                                                                  : (E_SUB | kNoSub);
+            off += size;
+        }
+    }
+    __syncwarp();
+    for (int s = lane; s < n; s += 32) {
+        const int l = lens[s];
+        if (l <= root) continue;
+        const uint32_t r = sm->code[s];
+        const uint32_t pe = tab[r & (nroot - 1)];
+        if (!(pe & E_SUB) || ent_value(pe) == kNoSub) continue;
+        const uint32_t sb = ent_extra(pe), base = ent_value(pe);
+        const uint32_t e = sym_entry<kDist>(s, l - root);
+        for (uint32_t i = r >> root; i < (1u << sb); i += (1u << (l - root))) tab[base + i] = e;
+    }
+    __syncwarp();
+    return true;
+}
+
+// canonical bit-by-bit decode (puff-style) of the code at the bottom of `bits`: the fallback for prefixes whose
+// second-level table did not fit.  Returns (symbol << 4) | code length, or -1.  Works on a copy of the bit buffer so
+// that the reader's state never has its address taken (it must stay in registers).
+__device__ __noinline__ int decode_slow(uint32_t bits, const uint16_t* count, const uint16_t* syms) {
     int code = 0, first = 0, index = 0;
     for (int l = 1; l < 16; l++) {
-        code |= (int)br.take(1);
+        code |= (int)(bits & 1u);
+        bits >>= 1;
         const int c = count[l];
-        if (code - c < first) return syms[index + (code - first)];
+        if (code - c < first) return ((int)syms[index + (code - first)] << 4) | l;
         index += c;
         first += c;
         first <<= 1;
@@ -293,21 +461,20 @@ __device__ __forceinline__ int decode_slow(BitReader& br, const uint16_t* count,
     return -1;
 }
 
-__device__ __forceinline__ int decode_sym(BitReader& br, const uint16_t* lut, int root_bits, const uint16_t* count, const uint16_t* syms) {
-    br.refill();
-    const uint16_t e = lut[br.peek(root_bits)];
-    if (e) {
-        br.drop(e & 15);
-        return e >> 4;
+// Second step for an E_SUB first-level entry (its drop field already applied): the symbol's own entry, its
+// remaining code bits dropped.
+template <bool kDist>
+__device__ __forceinline__ uint32_t resolve_entry(InfReader& br, uint32_t e, uint32_t tab_s, const uint16_t* count, const uint16_t* syms) {
+    if (ent_value(e) != kNoSub) {
+        e = lds32(tab_s + ((ent_value(e) + br.peek(ent_extra(e))) << 2));
+        br.drop(ent_drop(e));
+        return e;
     }
-    return decode_slow(br, count, syms);
+    const int s = decode_slow((uint32_t)br.buf, count, syms);
+    if (s < 0) return 0u;
+    br.drop(s & 15);
+    return sym_entry<kDist>(s >> 4, 0);
 }
-
-__constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-__constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-__constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-__constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
-__constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 __global__ void __launch_bounds__(kInfWarps * 32)
 inflate_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ streams, const int* __restrict__ order,
@@ -321,16 +488,37 @@ inflate_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restric
     if (sd.codec != CODEC_ZLIB) return;
     uint8_t* dst = scratch + sd.dst_off;
     const uint32_t dst_len = sd.dst_len;
-    BitReader br{blob + sd.src_off, sd.src_len, 0, 0, 0};
+    InfReader br;
+    {
+        const uint8_t* src = blob + sd.src_off;
+        const uint32_t skip = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+        br.base = src - skip;
+        br.end = skip + sd.src_len;
+        br.win = sm->win;
+        br.win_s = smem_addr(sm->win);
+        br.lane = lane;
+        br.seek(skip);
+    }
+    const uint32_t lit_s = smem_addr(sm->lit_tab), dist_s = smem_addr(sm->dist_tab);
     int err = 0;
     uint32_t out = 0;
     // zlib header (RFC 1950)
-    br.refill();
     {
         const uint32_t cmf = br.take(8), flg = br.take(8);
         if ((cmf & 15) != 8 || ((cmf << 8) | flg) % 31 != 0 || (flg & 0x20)) err = 1;
     }
-    uint32_t npend = 0, mylit = 0;        // literals gathered for one coalesced store
+    // Literals go to a shared-memory stage with one uniform byte store each (all lanes store the same value, so a
+    // lane always reads back what it wrote itself) and leave for global memory in one coalesced burst.
+    const uint32_t stage_s = smem_addr(sm->stage);
+    uint32_t sp = stage_s;                // next free stage byte
+#define B2_FLUSH_LITERALS()                                                         \
+    {                                                                               \
+        const uint32_t n_ = sp - stage_s;                                           \
+        if (n_ > dst_len - out) { err = 3; break; }                                 \
+        for (uint32_t i_ = lane; i_ < n_; i_ += 32) dst[out + i_] = sm->stage[i_];  \
+        out += n_;                                                                  \
+        sp = stage_s;                                                               \
+    }
     bool last = false;
     while (!err && !last) {
         br.refill();
@@ -341,18 +529,13 @@ inflate_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restric
             br.refill();
             const uint32_t ln = br.take(16), nln = br.take(16);
             if ((ln ^ 0xFFFFu) != nln) { err = 2; break; }
-            // flush pending literals first
-            if (npend) { if (lane < npend) dst[out + lane] = (uint8_t)mylit; out += npend; npend = 0; }
+            B2_FLUSH_LITERALS();
             if (ln > dst_len - out) { err = 3; break; }
-            // bytes still in the bit buffer belong to the stored data
-            const uint32_t start = br.pos - (uint32_t)(br.cnt >> 3);
-            if (start + ln > br.len) { err = 4; break; }
-            for (uint32_t i = lane; i < ln; i += 32) dst[out + i] = br.src[start + i];
+            const uint32_t start = br.byte_pos();
+            if ((uint64_t)start + ln > br.end) { err = 4; break; }
+            for (uint32_t i = lane; i < ln; i += 32) dst[out + i] = br.base[start + i];
             out += ln;
-            br.pos = start + ln;
-            br.buf = 0;
-            br.cnt = 0;
-            __syncwarp();
+            br.seek(start + ln);
             continue;
         }
         if (type == 3) { err = 5; break; }
@@ -369,18 +552,15 @@ inflate_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restric
             ndist = (int)br.take(5) + 1;
             const int ncl = (int)br.take(4) + 4;
             if (nlit > 286 || ndist > 30) { err = 6; break; }
-            __shared__ uint8_t cl_lens_all[kInfWarps][19];
-            uint8_t* cl_lens = cl_lens_all[threadIdx.x >> 5];
-            if (lane < 19) cl_lens[lane] = 0;
+            if (lane < 19) sm->cl_lens[lane] = 0;
             __syncwarp();
             for (int i = 0; i < ncl; i++) {
                 br.refill();
                 const uint32_t v = br.take(3);
-                if (lane == 0) cl_lens[c_cl_order[i]] = (uint8_t)v;
+                if (lane == 0) sm->cl_lens[c_cl_order[i]] = (uint8_t)v;
             }
             __syncwarp();
-            __shared__ uint16_t cl_cnt_all[kInfWarps][16], cl_sym_all[kInfWarps][19];
-            if (!build_huffman(cl_lens, 19, sm->cl_lut, 7, cl_cnt_all[threadIdx.x >> 5], cl_sym_all[threadIdx.x >> 5], lane)) { err = 7; break; }
+            if (!build_cl_lut(sm, lane)) { err = 7; break; }
             int idx = 0;
             int prev = 0;
             while (idx < nlit + ndist) {
@@ -406,52 +586,139 @@ inflate_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restric
             __syncwarp();
             if (sm->lens[256] == 0) { err = 11; break; }
         }
-        if (!build_huffman(sm->lens, nlit, sm->lit_lut, 10, sm->lit_count, sm->lit_sym, lane)) { err = 12; break; }
-        if (!build_huffman(sm->lens + 288, ndist, sm->dist_lut, 8, sm->dist_count, sm->dist_sym, lane)) { err = 13; break; }
-        // ---- symbols
+        if (!build_table<false>(sm, sm->lens, nlit, sm->lit_tab, kLitRoot, kLitSub, sm->lit_count, sm->lit_sym, lane)) { err = 12; break; }
+        if (!build_table<true>(sm, sm->lens + 288, ndist, sm->dist_tab, kDistRoot, kDistSub, sm->dist_count, sm->dist_sym, lane)) { err = 13; break; }
+        // ---- symbols.  After a refill the buffer holds >= 33 bits: enough for two codes (<= 15 bits each), or for
+        // one length code + extra (<= 20), or one distance code + extra (<= 28).  Two first-level lookups are made
+        // back to back (the second is simply discarded unless the first was a literal) and the common case, two
+        // literals, costs one branch.
         while (true) {
-            const int sym = decode_sym(br, sm->lit_lut, 10, sm->lit_count, sm->lit_sym);
-            if (sym < 0) { err = 14; break; }
-            if (sym < 256) {
-                if (lane == npend) mylit = (uint32_t)sym;
-                if (++npend == 32) {
-                    if (out + 32 > dst_len) { err = 3; break; }
-                    dst[out + lane] = (uint8_t)mylit;
-                    out += 32;
-                    npend = 0;
-                    __syncwarp();
-                }
+            // Pairs of first-level literals, the bulk of an image stream, run in a PTX loop whose only taken branch
+            // is its back edge (a taken branch costs a lone warp ~25 cycles, and the compiler's block layout put
+            // three or four of them on this path): predicated bit-buffer top-up, two table lookups back to back
+            // (the second is discarded unless both are literals), two byte stores into the stage.  It leaves with
+            // why = 0: `e` is a first-level entry (its code bits dropped) that is not half of a literal pair;
+            // 1: the stage is full; 2: the input window must advance before the next word can be fetched.
+            uint32_t e, why;
+            asm volatile(
+                "{\n\t"
+                ".reg .pred pneed, padv, pfull, ppair;\n\t"
+                ".reg .b64 add64, b1, nw64;\n\t"
+                ".reg .b32 t, idx, e1, e2, d1, d2, c1, a;\n"
+                "B2_INF_LOOP:\n\t"
+                "setp.gt.u32 pfull, %4, %9;\n\t"
+                "@pfull bra B2_INF_FULL;\n\t"
+                "setp.le.s32 pneed, %1, 32;\n\t"
+                "cvt.u64.u32 nw64, %3;\n\t"
+                "and.b32 t, %1, 63;\n\t"
+                "shl.b64 add64, nw64, t;\n\t"
+                "@pneed or.b64 %0, %0, add64;\n\t"
+                "@pneed add.s32 %1, %1, 32;\n\t"
+                "@pneed add.u32 %2, %2, 1;\n\t"
+                "and.b32 t, %2, 63;\n\t"
+                "setp.eq.and.u32 padv, t, 0, pneed;\n\t"
+                "@padv bra B2_INF_ADV;\n\t"
+                "and.b32 t, %2, 127;\n\t"
+                "shl.b32 t, t, 2;\n\t"
+                "add.u32 a, %8, t;\n\t"
+                "@pneed ld.shared.u32 %3, [a];\n\t"
+                "cvt.u32.u64 idx, %0;\n\t"
+                "and.b32 idx, idx, 1023;\n\t"
+                "shl.b32 idx, idx, 2;\n\t"
+                "add.u32 a, %7, idx;\n\t"
+                "ld.shared.u32 e1, [a];\n\t"
+                "prmt.b32 d1, e1, 0, 0x4442;\n\t"
+                "shr.u64 b1, %0, d1;\n\t"
+                "sub.s32 c1, %1, d1;\n\t"
+                "cvt.u32.u64 idx, b1;\n\t"
+                "and.b32 idx, idx, 1023;\n\t"
+                "shl.b32 idx, idx, 2;\n\t"
+                "add.u32 a, %7, idx;\n\t"
+                "ld.shared.u32 e2, [a];\n\t"
+                "and.b32 t, e1, e2;\n\t"
+                "and.b32 t, t, 0x10000000;\n\t"
+                "setp.ne.u32 ppair, t, 0;\n\t"
+                "@!ppair bra B2_INF_NOPAIR;\n\t"
+                "st.shared.u8 [%4], e1;\n\t"
+                "st.shared.u8 [%4+1], e2;\n\t"
+                "add.u32 %4, %4, 2;\n\t"
+                "prmt.b32 d2, e2, 0, 0x4442;\n\t"
+                "shr.u64 %0, b1, d2;\n\t"
+                "sub.s32 %1, c1, d2;\n\t"
+                "bra B2_INF_LOOP;\n"
+                "B2_INF_NOPAIR:\n\t"
+                "mov.b64 %0, b1;\n\t"
+                "mov.b32 %1, c1;\n\t"
+                "mov.b32 %5, e1;\n\t"
+                "mov.u32 %6, 0;\n\t"
+                "bra B2_INF_DONE;\n"
+                "B2_INF_FULL:\n\t"
+                "mov.u32 %5, 0;\n\t"
+                "mov.u32 %6, 1;\n\t"
+                "bra B2_INF_DONE;\n"
+                "B2_INF_ADV:\n\t"
+                "mov.u32 %5, 0;\n\t"
+                "mov.u32 %6, 2;\n"
+                "B2_INF_DONE:\n\t"
+                "}"
+                : "+l"(br.buf), "+r"(br.cnt), "+r"(br.wpos), "+r"(br.nextw), "+r"(sp), "=r"(e), "=r"(why)
+                : "r"(lit_s), "r"(br.win_s), "r"(stage_s + (uint32_t)(kInfStage - 2))
+                : "memory");
+            if (why == 1) {
+                B2_FLUSH_LITERALS();
                 continue;
             }
-            if (npend) {
-                if (out + npend > dst_len) { err = 3; break; }
-                if (lane < npend) dst[out + lane] = (uint8_t)mylit;
-                out += npend;
-                npend = 0;
-                __syncwarp();
+            if (why == 2) {
+                br.advance();
+                br.nextw = lds32(br.win_s + ((br.wpos & 127u) << 2));
+                continue;
             }
-            if (sym == 256) { if (br.overrun()) err = 18; break; }
-            const int li = sym - 257;
-            if (li >= 29) { err = 15; break; }
+            if (e & E_SUB) e = resolve_entry<false>(br, e, lit_s, sm->lit_count, sm->lit_sym);
+            if (e & E_LIT) {
+                asm volatile("st.shared.u8 [%0], %1;" ::"r"(sp), "r"(e) : "memory");
+                sp += 1;
+                continue;
+            }
+            B2_FLUSH_LITERALS();
+            if (e & E_EOB) { if (br.overrun()) err = 18; break; }
+            if (!(e & E_BASE)) { err = 14; break; }
             br.refill();
-            const uint32_t mlen = c_len_base[li] + br.take(c_len_extra[li]);
-            const int ds = decode_sym(br, sm->dist_lut, 8, sm->dist_count, sm->dist_sym);
-            if (ds < 0 || ds >= 30) { err = 16; break; }
+            const uint32_t mlen = ent_value(e) + br.take(ent_extra(e));
             br.refill();
-            const uint32_t dist = c_dist_base[ds] + br.take(c_dist_extra[ds]);
+            uint32_t d = lds32(dist_s + (br.peek(kDistRoot) << 2));
+            br.drop(ent_drop(d));
+            if (d & E_SUB) d = resolve_entry<true>(br, d, dist_s, sm->dist_count, sm->dist_sym);
+            if (!(d & E_BASE)) { err = 16; break; }
+            const uint32_t dist = ent_value(d) + br.take(ent_extra(d));
             if (dist > out) { err = 17; break; }
             if (mlen > dst_len - out) { err = 3; break; }
-            // overlapped copies repeat the last `dist` bytes periodically: every source byte is already written
-            for (uint32_t i = lane; i < mlen; i += 32) dst[out + i] = dst[out - dist + (dist >= mlen ? i : i % dist)];
+            // Overlapped copies repeat the last `dist` bytes periodically, so every source byte is already written:
+            // issue up to four loads per lane before the first store.
+            __syncwarp();
+            {
+                const uint8_t* from = dst + (out - dist);
+                uint8_t* to = dst + out;
+                for (uint32_t i0 = 0; i0 < mlen; i0 += 128) {
+                    uint8_t v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t i = i0 + k * 32 + lane;
+                        if (i < mlen) v[k] = from[dist >= mlen ? i : i % dist];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t i = i0 + k * 32 + lane;
+                        if (i < mlen) to[i] = v[k];
+                    }
+                }
+            }
             out += mlen;
             __syncwarp();
             if (br.overrun()) { err = 18; break; }
         }
     }
-    if (!err && npend) {
-        if (out + npend > dst_len) err = 3;
-        else { if (lane < npend) dst[out + lane] = (uint8_t)mylit; out += npend; }
-    }
+    while (!err && sp != stage_s) B2_FLUSH_LITERALS();
+#undef B2_FLUSH_LITERALS
     if (!err && out < dst_len) err = 19;          // fewer bytes than the image needs
     if (err && lane == 0) set_status(status, sd.image, 20 + err);
 }

@@ -697,6 +697,16 @@ int check_sink(const b2_parse_sink* sink, const char* who) {
     return 0;
 }
 
+// Development builds (-DB2_DEV_KNOBS) can alias every output row onto row 0 to time the kernel without its
+// output footprint (the roofline experiment in DESIGN.md).  The shipped library has no such switch.
+uint32_t dev_row_mask() {
+#ifdef B2_DEV_KNOBS
+    return getenv("B2_DEBUG_ROW0") ? 0u : ~0u;
+#else
+    return ~0u;
+#endif
+}
+
 uint32_t tiles_per_cta() {
     static int q = -1;
     if (q < 0) {
@@ -745,7 +755,7 @@ extern "C" int b2_tfrecord_parse_table(b2_ctx* ctx, const uint8_t* shard, uint64
     const TableView v = table_view(table, nbytes, max_records);
     ParseArgs pa{shard, nbytes, v.rec_off, v.rec_len, v.index, *sink, ctx->crc_dev, v.tile2rec, v.tile_start, v.hdr,
                  0, 0, tiles_per_cta(), v.acc, status, nullptr, v.hdr + 4, reinterpret_cast<uint32_t*>(v.hdr + 5),
-                 getenv("B2_PARSE_PROFILE") ? ctx->prof_dev : nullptr, getenv("B2_DEBUG_ROW0") ? 0u : ~0u};
+                 getenv("B2_PARSE_PROFILE") ? ctx->prof_dev : nullptr, dev_row_mask()};
     return launch_fused(ctx, pa, v.cap_tiles, static_cast<cudaStream_t>(stream));
 }
 
