@@ -8,25 +8,26 @@
 // widths, Clear when the table reaches 4094 entries, EOI.  Greedy longest-match parsing with an exact dictionary is
 // deterministic, so the output is byte-identical with any conforming greedy encoder (tests compare it with the CPU
 // fixture encoder and decode it back with libtiff).  Encoding is serial inside a stream (every step depends on the
-// dictionary built so far): one warp owns one tile, its dictionary is an open-addressing hash table in shared
-// memory (8192 slots of { prefix code, byte } -> code), all lanes run the same scalar walk (no divergence) and
-// cooperate on what is parallel: clearing the table and staging the input window.  Parallelism comes from the
-// thousands of tiles of a batch.
+// dictionary built so far): one warp owns one tile, all lanes run the same scalar walk (no divergence) and cooperate
+// on what is parallel: clearing the table and staging the input window.  Parallelism comes from the tiles of a batch.
+//
+// The walk is one dependent chain per input byte (key -> hash -> probe -> compare), so what it costs is the latency
+// of the probe: the dictionary — an open-addressing hash table of 6144 words, (key << 12) | code with
+// key = (prefix << 8) | byte, at most 4094 entries so the load stays under 0.67 — sits in SHARED memory (one warp per
+// CTA, so every address is "register + immediate").  With the table in global memory (L2) a byte cost ~1000 cycles
+// and a 512 KiB tile 275 ms; nine resident warps per SM instead of sixty-four is a good trade for a 5x shorter chain
+// (59 ms per tile, ~210 cycles per byte on chips whose noisy low bytes make nearly every step a dictionary miss).
 #include "common.cuh"
 
 namespace b2 {
 
-constexpr int kEncWarps = 4;            // streams per CTA
-constexpr int kEncSlots = 8192;         // hash slots per stream (4094 entries at most: load < 0.5)
-constexpr int kEncWin = 2048;           // staged input bytes per refill
+constexpr int kEncSlots = 6144;         // hash slots per stream: load <= 0.67 (4094 entries), ~1.6 probes on average
+constexpr int kEncWin = 1024;           // staged input bytes per refill
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 
-// The dictionary of a stream — kEncSlots words of (key << 12) | code, key = (prefix << 8) | byte — lives in the context
-// workspace, not in shared memory: the walk is latency-bound (a few hundred cycles per input byte whatever memory the
-// table is in), so what counts is how many streams are resident, and 32 KiB of shared memory per stream would allow
-// six per SM where the L2-resident tables allow sixty-four.
 struct EncSmem {
-    uint8_t win[kEncWin];
+    uint32_t table[kEncSlots];
+    uint32_t win[kEncWin / 4];
 };
 
 struct BitWriter {
@@ -64,13 +65,11 @@ struct BitWriter {
     }
 };
 
-__global__ void __launch_bounds__(kEncWarps * 32)
+__global__ void __launch_bounds__(32)
 lzw_encode_kernel(const uint8_t* __restrict__ raw, const b2_enc_desc* __restrict__ descs, int n, uint8_t* __restrict__ out,
-                  uint32_t* __restrict__ out_len, unsigned int* next_stream, uint32_t* tables) {
-    __shared__ __align__(16) EncSmem sm_all[kEncWarps];
-    EncSmem* sm = &sm_all[threadIdx.x >> 5];
-    uint32_t* table = tables + (size_t)(blockIdx.x * kEncWarps + (threadIdx.x >> 5)) * kEncSlots;
-    const int lane = threadIdx.x & 31;
+                  uint32_t* __restrict__ out_len, unsigned int* next_stream) {
+    __shared__ __align__(16) EncSmem sm;
+    const int lane = threadIdx.x;
     const bool writer = lane == 0;
     for (;;) {                                           // persistent warps draw tiles from a counter
         int si = 0;
@@ -83,60 +82,82 @@ lzw_encode_kernel(const uint8_t* __restrict__ raw, const b2_enc_desc* __restrict
         BitWriter w{out + d.dst_off, d.dst_cap, 0, 0, 0, false};
         enum { CLEAR = 256, EOI = 257, FIRST = 258, LIMIT = 4094 };
         int nbits = 9, next = FIRST;
-        for (int i = lane; i < kEncSlots; i += 32) __stcg(table + i, kEmpty);
-        uint32_t win_lo = 0x80000000u;                   // window = [win_lo, win_lo + kEncWin); the first access misses
-        auto byte_at = [&](uint32_t p) -> uint32_t {
-            if (p - win_lo >= (uint32_t)kEncWin) {       // warp-uniform: refill with coalesced 16-byte loads
-                __syncwarp();
-                win_lo = p & ~15u;
-                for (int k = lane; k < kEncWin / 16; k += 32) {
-                    const uint32_t a = win_lo + 16u * k;
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (a + 16 <= len && ((reinterpret_cast<uintptr_t>(src) + a) & 15) == 0) v = ld_nc(reinterpret_cast<const uint4*>(src + a));
-                    else if (a < len) {
-                        uint32_t t[4] = {0, 0, 0, 0};
-                        for (uint32_t q = a; q < len && q < a + 16; q++) t[(q - a) >> 2] |= (uint32_t)src[q] << (8 * ((q - a) & 3));
-                        v = make_uint4(t[0], t[1], t[2], t[3]);
-                    }
-                    reinterpret_cast<uint4*>(sm->win)[k] = v;
-                }
-                __syncwarp();
-            }
-            return sm->win[p - win_lo];
+        uint32_t cur = 0;
+        auto clear_table = [&]() {
+            __syncwarp();
+            for (int k = lane; k < kEncSlots / 4; k += 32) reinterpret_cast<uint4*>(sm.table)[k] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+            __syncwarp();
         };
-        __syncwarp();
+        // stage input bytes [lo, lo + kEncWin) (lo a multiple of 16) with coalesced 16-byte loads, zero past the end
+        auto stage = [&](uint32_t lo) {
+            __syncwarp();
+            for (int k = lane; k < kEncWin / 16; k += 32) {
+                const uint32_t a = lo + 16u * k;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (a + 16 <= len && ((reinterpret_cast<uintptr_t>(src) + a) & 15) == 0) v = ld_nc(reinterpret_cast<const uint4*>(src + a));
+                else if (a < len) {
+                    uint32_t t[4] = {0, 0, 0, 0};
+                    for (uint32_t q = a; q < len && q < a + 16; q++) t[(q - a) >> 2] |= (uint32_t)src[q] << (8 * ((q - a) & 3));
+                    v = make_uint4(t[0], t[1], t[2], t[3]);
+                }
+                reinterpret_cast<uint4*>(sm.win)[k] = v;
+            }
+            __syncwarp();
+        };
+        // one input byte: extend the current string if (cur, c) is in the dictionary, else emit cur and add the pair
+        auto step = [&](uint32_t c) {
+            const uint32_t key = (cur << 8) | c;
+            uint32_t h = __umulhi(key * 2654435761u, (uint32_t)kEncSlots);      // multiply-shift range reduction
+            uint32_t e = sm.table[h];
+            if ((e >> 12) == key) {                      // (an empty slot never matches: no prefix code is 4095)
+                cur = e & 0xFFFu;
+                return;
+            }
+            while (e != kEmpty) {                        // linear probing; no deletions, so a present key precedes the first hole
+                h = h + 1 == (uint32_t)kEncSlots ? 0u : h + 1;
+                e = sm.table[h];
+                if ((e >> 12) == key) {
+                    cur = e & 0xFFFu;
+                    return;
+                }
+            }
+            w.put(cur, nbits, writer);
+            sm.table[h] = (key << 12) | (uint32_t)next;  // every lane stores the same word
+            next++;
+            cur = c;
+            if (next == LIMIT) {
+                w.put(CLEAR, nbits, writer);
+                clear_table();
+                nbits = 9;
+                next = FIRST;
+            } else if (next > (1 << nbits) - 1) {
+                nbits++;
+            }
+        };
+        clear_table();
         w.put(CLEAR, nbits, writer);
         if (len) {
-            uint32_t cur = byte_at(0);
-            for (uint32_t i = 1; i < len; i++) {
-                const uint32_t c = byte_at(i);
-                const uint32_t key = (cur << 8) | c;
-                uint32_t h = (key * 2654435761u) >> 19;  // 13 bits
-                uint32_t found = kEmpty;
-                for (;;) {
-                    const uint32_t e = __ldcg(table + h);
-                    if (e == kEmpty) break;
-                    if ((e >> 12) == key) { found = e & 0xFFFu; break; }
-                    h = (h + 1) & (kEncSlots - 1);
-                }
-                if (found != kEmpty) {
-                    cur = found;
-                    continue;
-                }
-                w.put(cur, nbits, writer);
-                if (writer) __stcg(table + h, (key << 12) | (uint32_t)next);
-                __syncwarp();
-                next++;
-                cur = c;
-                if (next == LIMIT) {
-                    w.put(CLEAR, nbits, writer);
-                    __syncwarp();
-                    for (int k = lane; k < kEncSlots; k += 32) __stcg(table + k, kEmpty);
-                    __syncwarp();
-                    nbits = 9;
-                    next = FIRST;
-                } else if (next > (1 << nbits) - 1) {
-                    nbits++;
+            // bytes are taken a staged 32-bit word at a time: word j holds bytes 4j .. 4j+3
+            for (uint32_t lo = 0; lo < len; lo += kEncWin) {
+                stage(lo);
+                const uint32_t words = min((uint32_t)kEncWin, len - lo + 3u) / 4u;
+                for (uint32_t j = 0; j < words; j++) {
+                    uint32_t word = sm.win[j];
+                    const uint32_t b0 = lo + 4u * j;
+                    if (b0 >= 1 && b0 + 4 <= len) {      // the common case: four bytes, no edge
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            step(word & 0xFFu);
+                            word >>= 8;
+                        }
+                    } else {
+                        for (int k = 0; k < 4; k++) {
+                            const uint32_t b = b0 + k;
+                            if (b == 0) cur = word & 0xFFu;
+                            else if (b < len) step(word & 0xFFu);
+                            word >>= 8;
+                        }
+                    }
                 }
             }
             w.put(cur, nbits, writer);
@@ -181,14 +202,13 @@ extern "C" int b2_lzw_encode(b2_ctx* ctx, const uint8_t* raw, const b2_enc_desc*
     if (n <= 0) return 0;
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    unsigned ctas = (unsigned)((n + kEncWarps - 1) / kEncWarps);
-    const unsigned resident = (unsigned)ctx->sm_count * (64 / kEncWarps);
+    unsigned ctas = (unsigned)n;
+    const unsigned resident = (unsigned)ctx->sm_count * 9;     // 25 KiB of shared memory per CTA
     if (ctas > resident) ctas = resident;
-    const size_t table_bytes = (size_t)ctas * kEncWarps * kEncSlots * sizeof(uint32_t);
-    if (int e = ws_reserve(ctx, table_bytes + 256, s)) return e;
-    unsigned int* counter = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(ctx->ws) + table_bytes);
+    if (int e = ws_reserve(ctx, 256, s)) return e;
+    unsigned int* counter = static_cast<unsigned int*>(ctx->ws);
     B2_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
-    lzw_encode_kernel<<<ctas, kEncWarps * 32, 0, s>>>(raw, descs, n, out, out_len, counter, static_cast<uint32_t*>(ctx->ws));
+    lzw_encode_kernel<<<ctas, 32, 0, s>>>(raw, descs, n, out, out_len, counter);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;

@@ -265,6 +265,42 @@ def bench_encode(dev, n_chips=None):
             "compressed_fraction": round(sum(len(f) for f in files) / raw, 3)})
 
 
+def bench_encode_kernel(dev):
+    """lzw_encode_kernel alone (CUDA events): 256x256x4 u16 tiles of cfg3 chips, a few batch sizes."""
+    import ctypes
+
+    import synthetic as syn
+    from dl_image_segmentation_b200 import _geotiff
+    from dl_image_segmentation_b200._lib import check, get_ctx, lib, ptr
+    ctx = get_ctx(dev)
+    tiles = []
+    for i in range(4):
+        img, _, _ = syn.cfg3_chip(i)
+        for ty in range(2):
+            for tx in range(2):
+                tiles.append(np.ascontiguousarray(img[ty * 256:(ty + 1) * 256, tx * 256:(tx + 1) * 256]).view(np.uint8).reshape(-1))
+    tb = tiles[0].size
+    for n in (8, 64, 1024, 4096):
+        raw = torch.from_numpy(np.concatenate([tiles[i % len(tiles)] for i in range(n)])).to(dev)
+        cap = tb * 3 // 2 + 64
+        descs = np.zeros(n, _geotiff.ENC_DESC_DTYPE)
+        descs["src_len"], descs["dst_cap"] = tb, cap
+        descs["src_off"] = np.arange(n, dtype=np.uint64) * tb
+        descs["dst_off"] = np.arange(n, dtype=np.uint64) * ((cap + 15) & ~15)
+        out = torch.empty((n * ((cap + 15) & ~15),), dtype=torch.uint8, device=dev)
+        out_len = torch.empty((n,), dtype=torch.int32, device=dev)
+        d_dev = torch.from_numpy(descs.view(np.uint8).reshape(-1)).to(dev)
+
+        def fn(i):
+            check(lib().b2_lzw_encode(ctx.handle, ptr(raw), ptr(d_dev), n, ptr(out), ptr(out_len), ctx.stream()))
+        ms = timeit(fn, 2, warmup=1)
+        comp = int(out_len.cpu().numpy().view(np.uint32).astype(np.int64).sum())
+        report("lzw_encode_kernel %d tiles of 512 KiB" % n, ms, n * tb + comp,
+               {"raw_GB/s": round(n * tb / ms / 1e6, 2), "tiles_per_s": round(n / ms * 1e3, 1),
+                "cycles_per_byte_per_stream_at_1.9GHz": round(ms * 1e-3 * 1.9e9 / tb / max(1.0, n / (148 * 9)), 1),
+                "compressed_fraction": round(comp / (n * tb), 3)})
+
+
 def bench_build(dev, n_shards=8):
     """The writer kernel on cfg1 records (uint8 arrays -> framed Examples) and cfg3 records (uint16 -> FloatList)."""
     import bench as B
@@ -303,6 +339,8 @@ def main():
         bench_k4(dev)
     if "encode" in which:
         bench_encode(dev)
+    if "encode_kernel" in which:
+        bench_encode_kernel(dev)
     for kind in ("lzw", "lzw_strips_pred2", "deflate", "png"):
         if kind in which or "decode" in which:
             bench_decode(dev, kind)
