@@ -333,8 +333,8 @@ __device__ __forceinline__ uint32_t sym_entry(int s, int drop) {
 }
 
 // Canonical Huffman code from lens[0..n): counts, per-length first code, symbols sorted by (length, value) and each
-// symbol's bit-reversed code.  Warp-cooperative; false for an over-subscribed set.
-__device__ bool canonical_codes(InfWarpSmem* sm, const uint8_t* lens, int n, uint16_t* count, uint16_t* syms, int lane) {
+// symbol's bit-reversed code.  Warp-cooperative; false for a set zlib would reject (over-subscribed or incomplete).
+__device__ bool canonical_codes(InfWarpSmem* sm, const uint8_t* lens, int n, uint16_t* count, uint16_t* syms, int lane, bool strict) {
     if (lane < 16) count[lane] = 0;
     __syncwarp();
     // rank of each symbol among the earlier symbols of its length: 32 symbols per step
@@ -348,19 +348,22 @@ __device__ bool canonical_codes(InfWarpSmem* sm, const uint8_t* lens, int n, uin
         if (l && lane == __ffs(m) - 1) count[l] = (uint16_t)(before + __popc(m));
         __syncwarp();
     }
-    int left = 1;
+    int left = 1, longest = 0;
     uint32_t code = 0, off = 0;
     bool ok = true;
     for (int l = 1; l < 16; l++) {
         const int c = count[l];
         left = (left << 1) - c;
         if (left < 0) ok = false;
+        if (c) longest = l;
         if (lane == 0) { sm->first[l] = (uint16_t)code; sm->offs[l] = (uint16_t)off; }
         code = (code + c) << 1;
         off += c;
     }
     __syncwarp();
-    if (!ok) return false;
+    // zlib's inflate_table: over-subscribed sets are invalid, and so are incomplete ones unless the set is empty or
+    // a single one-bit code (and never for the code-length code)
+    if (!ok || (left > 0 && longest != 0 && (strict || longest != 1))) return false;
     for (int s = lane; s < n; s += 32) {
         const int l = lens[s];
         if (!l) continue;
@@ -375,7 +378,7 @@ __device__ bool canonical_codes(InfWarpSmem* sm, const uint8_t* lens, int n, uin
 // One-level LUT for the code-length code: (symbol << 4) | length.
 __device__ bool build_cl_lut(InfWarpSmem* sm, int lane) {
     for (int i = lane; i < 128; i += 32) sm->cl_lut[i] = 0;
-    if (!canonical_codes(sm, sm->cl_lens, 19, sm->cl_count, sm->cl_sym, lane)) return false;
+    if (!canonical_codes(sm, sm->cl_lens, 19, sm->cl_count, sm->cl_sym, lane, true)) return false;
     if (lane < 19) {
         const int l = sm->cl_lens[lane];
         if (l) for (uint32_t i = sm->code[lane]; i < 128u; i += (1u << l)) sm->cl_lut[i] = (uint16_t)((lane << 4) | l);
@@ -390,7 +393,7 @@ __device__ bool build_table(InfWarpSmem* sm, const uint8_t* lens, int n, uint32_
                             uint16_t* count, uint16_t* syms, int lane) {
     const int nroot = 1 << root;
     for (int i = lane; i < nroot + sub_cap; i += 32) tab[i] = 0;
-    if (!canonical_codes(sm, lens, n, count, syms, lane)) return false;
+    if (!canonical_codes(sm, lens, n, count, syms, lane, false)) return false;
     bool any_long = false;
     for (int s = lane; s < n; s += 32) {
         const int l = lens[s];
@@ -542,9 +545,9 @@ inflate_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restric
         int nlit, ndist;
         if (type == 1) {                  // fixed Huffman
             for (int i = lane; i < 288; i += 32) sm->lens[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
-            for (int i = lane; i < 30; i += 32) sm->lens[288 + i] = 5;
+            if (lane < 32) sm->lens[288 + lane] = 5;     // 32 five-bit codes make the set complete; 30 and 31 never decode
             nlit = 288;
-            ndist = 30;
+            ndist = 32;
             __syncwarp();
         } else {                          // dynamic Huffman
             br.refill();
@@ -720,6 +723,35 @@ inflate_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restric
     while (!err && sp != stage_s) B2_FLUSH_LITERALS();
 #undef B2_FLUSH_LITERALS
     if (!err && out < dst_len) err = 19;          // fewer bytes than the image needs
+    if (!err) {
+        // Adler-32 trailer (RFC 1950).  zlib verifies it in the inflate() call that delivers the last byte, so both
+        // libpng ("IDAT: incorrect data check") and libtiff/GDAL (ZIPDecode error -> failed block read) reject a
+        // stream whose check does not match: so does this decoder.
+        br.drop(br.cnt & 7);
+        br.refill();
+        uint32_t stored = br.take(8) << 24;
+        stored |= br.take(8) << 16;
+        stored |= br.take(8) << 8;
+        stored |= br.take(8);
+        if (br.overrun()) err = 18;
+        __syncwarp();
+        unsigned long long a = 0, b = 0;              // sum d_i ; sum ((n - i) mod 65521) d_i  (< 2^56 for n < 2^32)
+        uint32_t wgt = (out - (uint32_t)lane) % 65521u;
+        for (uint32_t i = lane; i < out; i += 32) {
+            const uint32_t d = dst[i];
+            a += d;
+            b += (unsigned long long)(wgt * d);
+            wgt = wgt >= 32u ? wgt - 32u : wgt + (65521u - 32u);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        const uint32_t s1 = (uint32_t)((a + 1ull) % 65521ull);
+        const uint32_t s2 = (uint32_t)((b + (unsigned long long)(out % 65521u)) % 65521ull);
+        if (!err && ((s2 << 16) | s1) != stored) err = 20;
+    }
     if (err && lane == 0) set_status(status, sd.image, 20 + err);
 }
 
@@ -1148,6 +1180,43 @@ int tiff_dtype(uint32_t bps, uint32_t fmt) {
     return -1;
 }
 const uint8_t kPngSig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+
+// CRC-32 (IEEE 802.3, the PNG chunk CRC), slice-by-8.  libpng treats a CRC mismatch in a critical chunk (IHDR, IDAT)
+// as a fatal error, so tf.image.decode_png / GDAL fail on such a file and the reference skips it: so do we.
+struct PngCrc {
+    uint32_t t[8][256];
+    PngCrc() {
+        for (uint32_t i = 0; i < 256; i++) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
+            t[0][i] = c;
+        }
+        for (uint32_t i = 0; i < 256; i++)
+            for (int s = 1; s < 8; s++) t[s][i] = (t[s - 1][i] >> 8) ^ t[0][t[s - 1][i] & 0xFF];
+    }
+    uint32_t run(const uint8_t* p, uint64_t n) const {
+        uint32_t c = 0xFFFFFFFFu;
+        while (n >= 8) {
+            uint32_t a, b;
+            memcpy(&a, p, 4);
+            memcpy(&b, p + 4, 4);
+            a ^= c;
+            c = t[7][a & 0xFF] ^ t[6][(a >> 8) & 0xFF] ^ t[5][(a >> 16) & 0xFF] ^ t[4][a >> 24] ^
+                t[3][b & 0xFF] ^ t[2][(b >> 8) & 0xFF] ^ t[1][(b >> 16) & 0xFF] ^ t[0][b >> 24];
+            p += 8;
+            n -= 8;
+        }
+        while (n--) c = (c >> 8) ^ t[0][(c ^ *p++) & 0xFF];
+        return ~c;
+    }
+};
+const PngCrc kPngCrc;
+// the chunk at blob + p (length n, already bounds-checked): type + data CRC against the stored one
+bool png_chunk_crc_ok(const uint8_t* blob, uint64_t p, uint64_t n) {
+    const uint8_t* e = blob + p + 8 + n;
+    const uint32_t stored = ((uint32_t)e[0] << 24) | ((uint32_t)e[1] << 16) | ((uint32_t)e[2] << 8) | e[3];
+    return kPngCrc.run(blob + p + 4, n + 4) == stored;
+}
 }  // namespace
 
 // Header-only probe: what load_image_rasterio(decode=False) reads (_img_to_tf_mp.py:51-53) plus what the
@@ -1171,6 +1240,7 @@ extern "C" int b2_image_probe(const uint8_t* blob, uint64_t size, b2_image_info*
                 info->samples = ct == 0 ? 1 : (ct == 2 ? 3 : (ct == 4 ? 2 : (ct == 6 ? 4 : 0)));
                 info->dtype = B2_U8;
                 if (depth != 8 || info->samples == 0 || inter != 0) info->status = 3;
+                if (!png_chunk_crc_ok(blob, p, n)) { info->status = 2; return 0; }
                 ihdr = true;
             } else if (memcmp(blob + p + 4, "IDAT", 4) == 0) {
                 n_idat++;
@@ -1258,8 +1328,10 @@ extern "C" int b2_image_blocks(const uint8_t* blob, uint64_t size, const b2_imag
         int k = 0;
         while (p + 8 <= size) {
             const uint64_t n = ((uint64_t)blob[p] << 24) | (blob[p + 1] << 16) | (blob[p + 2] << 8) | blob[p + 3];
-            if (memcmp(blob + p + 4, "IDAT", 4) == 0 && k < cap) { offsets[k] = p + 8; counts[k] = n; decoded_len[k] = 0; k++; }
-            else if (memcmp(blob + p + 4, "IEND", 4) == 0) break;
+            if (memcmp(blob + p + 4, "IDAT", 4) == 0 && k < cap) {
+                if (p + 12 + n > size || !png_chunk_crc_ok(blob, p, n)) return fail("b2_image_blocks: IDAT chunk CRC mismatch");
+                offsets[k] = p + 8; counts[k] = n; decoded_len[k] = 0; k++;
+            } else if (memcmp(blob + p + 4, "IEND", 4) == 0) break;
             p += 12 + n;
         }
         if (k) decoded_len[0] = info->block_bytes;

@@ -162,6 +162,10 @@ def parse_png(blob: bytes) -> dict:
         body = blob[p + 8:p + 8 + n]
         if len(body) != n:
             raise DecodeError("truncated chunk")
+        if typ in (b"IHDR", b"IDAT"):
+            # libpng (behind tf.image.decode_png and GDAL's PNG driver) treats a CRC mismatch in a critical chunk as fatal
+            if blob[p + 8 + n:p + 12 + n] != struct.pack(">I", zlib.crc32(typ + body) & 0xFFFFFFFF):
+                raise DecodeError("CRC mismatch in %s chunk" % typ.decode())
         if typ == b"IHDR":
             ihdr = struct.unpack(">IIBBBBB", body)
         elif typ == b"IDAT":

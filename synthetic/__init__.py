@@ -239,6 +239,80 @@ def png_bytes_manual(arr, filter_types=(0, 1, 2, 3, 4), zlevel=6, idat_chunk=Non
     return body + _png_chunk(b"IEND", b"")
 
 
+def png_bytes_raw_zlib(width, height, channels, zstream):
+    """A PNG around a caller-supplied zlib stream (tests of malformed / hand-made DEFLATE data)."""
+    ctype = {1: 0, 2: 4, 3: 2, 4: 6}[channels]
+    return (b"\x89PNG\r\n\x1a\n" + _png_chunk(b"IHDR", struct.pack(">IIBBBBB", width, height, 8, ctype, 0, 0, 0)) +
+            _png_chunk(b"IDAT", zstream) + _png_chunk(b"IEND", b""))
+
+
+def handmade_dynamic_deflate(symbols, lit_lens, data):
+    """zlib stream with ONE dynamic-Huffman block whose literal/length code has the given lengths
+    ({symbol: bits}; every other symbol unused) and one 1-bit distance code; `data` = symbols to emit (end with 256).
+    Nothing checks that the set is complete: that is the point (zlib rejects an incomplete one in the block header)."""
+    bits = []
+
+    def put(v, n):                      # n bits, LSB first (header fields, extra bits)
+        bits.extend((v >> i) & 1 for i in range(n))
+
+    def put_code(c, n):                 # Huffman code, MSB first
+        bits.extend((c >> (n - 1 - i)) & 1 for i in range(n))
+
+    def canonical(lens):
+        out, code = {}, 0
+        for ln in range(1, 16):
+            for s in sorted(k for k, v in lens.items() if v == ln):
+                out[s] = (code, ln)
+                code += 1
+            code <<= 1
+        return out
+    lens = [0] * 257
+    for s_, l_ in lit_lens.items():
+        lens[s_] = l_
+    seq = lens + [1]                    # + one distance code of one bit
+    # run-length code the sequence with symbols 0..15 and 18 only
+    rl, i = [], 0
+    while i < len(seq):
+        if seq[i] == 0:
+            j = i
+            while j < len(seq) and seq[j] == 0 and j - i < 138:
+                j += 1
+            if j - i >= 11:
+                rl.append((18, j - i - 11))
+                i = j
+                continue
+        rl.append((seq[i], None))
+        i += 1
+    used = sorted({s_ for s_, _ in rl})
+    cl_lens = {s_: 3 for s_ in used}    # a complete code-length code: pad to 8 three-bit codes
+    for s_ in range(19):
+        if len(cl_lens) == 8:
+            break
+        cl_lens.setdefault(s_, 3)
+    assert len(cl_lens) == 8
+    cl = canonical(cl_lens)
+    order = [16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15]
+    put(1, 1)
+    put(2, 2)                           # final block, dynamic
+    put(0, 5)                           # HLIT  = 257
+    put(0, 5)                           # HDIST = 1
+    put(15, 4)                          # HCLEN = 19
+    for s_ in order:
+        put(cl_lens.get(s_, 0), 3)
+    for s_, extra in rl:
+        put_code(*cl[s_])
+        if s_ == 18:
+            put(extra, 7)
+    lit = canonical(lit_lens)
+    for s_ in data:
+        put_code(*lit[s_])
+    while len(bits) % 8:
+        bits.append(0)
+    raw = bytes(sum(b << k for k, b in enumerate(bits[i:i + 8])) for i in range(0, len(bits), 8))
+    payload = bytes(s_ for s_ in data if s_ < 256)
+    return b"\x78\x01" + raw + struct.pack(">I", zlib.adler32(payload))
+
+
 # ----------------------------------------------------------------------------- smooth fields / workloads
 def smooth_field(rng, h, w, coarse=34):
     """Uniform noise on a coarse grid, bicubic-upsampled to (h, w), rescaled to [0,1]."""

@@ -113,6 +113,44 @@ def test_png_deflate_block_types(dev):
     _check(dev, blobs)
 
 
+def test_error_behaviour_of_zlib_and_libpng_is_mirrored(dev):
+    """What the reference's decoders reject, the device path rejects: zlib's inflate_table refuses an incomplete
+    literal/length set in the block header (even if the data never uses a missing code), and libpng treats a CRC
+    mismatch in a critical chunk (IHDR, IDAT) as fatal.  The hand-made stream with a complete set is the control."""
+    ok = syn.handmade_dynamic_deflate(None, {0: 2, 65: 2, 66: 2, 256: 2}, [0, 65, 256])
+    incomplete = syn.handmade_dynamic_deflate(None, {0: 2, 65: 2, 256: 2}, [0, 65, 256])
+    one_bit_only = syn.handmade_dynamic_deflate(None, {0: 1, 256: 2, 65: 2}, [0, 65, 256])         # complete, control
+    good = syn.png_bytes_raw_zlib(1, 1, 1, ok)
+    bad_idat = bytearray(good)
+    bad_idat[-16] ^= 1                                              # last CRC byte of the IDAT chunk
+    bad_ihdr = bytearray(good)
+    bad_ihdr[8 + 8 + 13] ^= 0x80                                    # first CRC byte of the IHDR chunk
+    # Adler-32 trailer wrong / missing (chunk CRC consistent): "incorrect data check" in libpng and libtiff alike
+    img = syn.cfg1_chip(0, size=32)[0]
+    z = bytearray(zlib.compress(syn.png_filter_rows(img, (0, 1, 2, 3, 4)), 6))
+    z[-1] ^= 0x55
+    tif = bytearray(syn.tiff_bytes(img, tile=None, compression="deflate"))
+    t = oic.parse_tiff(bytes(tif))
+    tif[t["offsets"][-1] + t["counts"][-1] - 1] ^= 0x55
+    blobs = [good, syn.png_bytes_raw_zlib(1, 1, 1, incomplete), syn.png_bytes_raw_zlib(1, 1, 1, one_bit_only),
+             bytes(bad_idat), bytes(bad_ihdr), syn.png_bytes_raw_zlib(32, 32, 3, bytes(z)),
+             syn.png_bytes_raw_zlib(32, 32, 3, bytes(z[:-4])), bytes(tif)]
+    want = []
+    for b in blobs:
+        try:
+            want.append(oic.decode_image(b))
+        except oic.DecodeError:
+            want.append(None)
+    assert [w is None for w in want] == [False, True, False, True, True, True, True, True]
+    got, status = _decode(dev, blobs)
+    for g, w, st in zip(got, want, status):
+        if w is None:
+            assert st != 0 and g is None
+        else:
+            assert st == 0
+            np.testing.assert_array_equal(g, w)
+
+
 def test_corrupt_chips_are_skipped_not_fatal(dev):
     img, lab, _ = syn.cfg3_chip(1, size=128)
     good = syn.tiff_bytes(img, tile=64)
@@ -136,6 +174,8 @@ def test_corrupt_chips_are_skipped_not_fatal(dev):
             want = None
         if status[i] == 0 and want is not None:
             np.testing.assert_array_equal(got[i], want)
+        if i == 5:                                               # PNG: chunk CRC + Adler-32 make damage detectable
+            assert want is None and status[i] != 0
 
 
 def test_probe_header_only(dev):

@@ -130,6 +130,21 @@ def test_decoders_against_live_libtiff_and_libpng():
         oic.decode_image(syn.tiff_bytes(lab, tile=64)[:600])
 
 
+def test_png_error_behaviour_follows_libpng_and_zlib():
+    """Critical-chunk CRC mismatch is fatal (libpng); an incomplete Huffman set is rejected in the block header (zlib)."""
+    import cv2
+    good = syn.png_bytes_raw_zlib(1, 1, 1, syn.handmade_dynamic_deflate(None, {0: 2, 65: 2, 66: 2, 256: 2}, [0, 65, 256]))
+    assert oic.decode_image(good).tolist() == [[[65]]]
+    assert cv2.imdecode(np.frombuffer(good, np.uint8), cv2.IMREAD_UNCHANGED).tolist() == [[65]]
+    bad_set = syn.png_bytes_raw_zlib(1, 1, 1, syn.handmade_dynamic_deflate(None, {0: 2, 65: 2, 256: 2}, [0, 65, 256]))
+    bad_crc = bytearray(good)
+    bad_crc[-16] ^= 1
+    for blob in (bad_set, bytes(bad_crc)):
+        with pytest.raises(oic.DecodeError):
+            oic.decode_image(blob)
+        assert cv2.imdecode(np.frombuffer(blob, np.uint8), cv2.IMREAD_UNCHANGED) is None      # libpng agrees
+
+
 def test_median_against_numpy_ma_golden():
     stack, valid = _g("median_stack.npy"), _g("median_valid.npy")
     ref = ocomp.median_composite(stack, valid)
