@@ -40,13 +40,18 @@ def timeit(fn, iters, warmup=3):
     return a.elapsed_time(b) / iters
 
 
+QUIET = False          # bench.py imports these benchmarks for its "other_configs" block and prints its own single line
+
+
 def report(name, ms, algo_bytes, extra=None):
     gbs = algo_bytes / (ms / 1e3) / 1e9
     d = {"kernel": name, "ms": round(ms, 4), "algorithmic_bytes": int(algo_bytes), "GB/s": round(gbs, 1),
          "frac_of_measured_hbm": round(gbs / PEAK, 4)}
     if extra:
         d.update(extra)
-    print(json.dumps(d), flush=True)
+    if not QUIET:
+        print(json.dumps(d), flush=True)
+    return d
 
 
 def bench_median(dev, n_tiles=8, iters=16):
@@ -66,10 +71,10 @@ def bench_median(dev, n_tiles=8, iters=16):
                                                       _lib.ptr(out), _lib.ptr(mask), ctx.stream()))
     ms = timeit(fn, iters)
     algo = T * H * W * B * 2 + T * H * W + H * W * B * 8 + H * W * B
-    report("median_kernel<16,NV=2> cfg4 (16,1024,1024,8)", ms, algo, {"tiles_per_s": round(1e3 / ms, 1), "Gpix_per_s": round(H * W / ms / 1e6, 3)})
+    return report("median_kernel<16,NV=2> cfg4 (16,1024,1024,8)", ms, algo, {"tiles_per_s": round(1e3 / ms, 1), "Gpix_per_s": round(H * W / ms / 1e6, 3)})
 
 
-def bench_mosaic(dev, pool=256, chips=4096, iters=5):
+def bench_mosaic(dev, pool=256, chips=4096, iters=5, stats=False):
     import synthetic as syn
     T, H, W, B = 32, 256, 256, 4
     g = torch.Generator(device=dev)
@@ -89,11 +94,12 @@ def bench_mosaic(dev, pool=256, chips=4096, iters=5):
     src = torch.empty((chips, H, W), dtype=torch.int16, device=dev)
     nel = torch.empty((chips,), dtype=torch.int32, device=dev)
     f = syn.CFG5_FILTER
+    acc = torch.zeros((B, 4), dtype=torch.int64, device=dev) if stats else None      # fused per-band statistics
 
     def fn(i):
         _lib.check(_lib.lib().b2_nearest_date_mosaic(ctx.handle, _lib.ptr(sp), _lib.ptr(vp), _lib.ptr(day_d), _lib.ptr(cf_d),
                                                      f["ref_day"], f["min_day"], f["max_day"], f["max_cf"], chips, T, H, W, B, 2,
-                                                     _lib.ptr(out), _lib.ptr(mask), None, _lib.ptr(nel), None, ctx.stream()))
+                                                     _lib.ptr(out), _lib.ptr(mask), None, _lib.ptr(nel), _lib.ptr(acc), ctx.stream()))
     ms = timeit(fn, iters)
     dense = chips * (T * H * W * B * 2 + T * H * W + H * W * B * 2 + H * W)
     # bytes actually touched: one pixel read + probes of eligible scenes until the first valid one (estimated from src)
@@ -101,7 +107,7 @@ def bench_mosaic(dev, pool=256, chips=4096, iters=5):
                                                  f["ref_day"], f["min_day"], f["max_day"], f["max_cf"], chips, T, H, W, B, 2,
                                                  _lib.ptr(out), _lib.ptr(mask), _lib.ptr(src), _lib.ptr(nel), None, ctx.stream()))
     touched_min = chips * (H * W * B * 2 * 2 + H * W + H * W)
-    report("mosaic_kernel<8> cfg5 T=32 256x256x4 u16, %d chips" % chips, ms, dense,
+    return report("mosaic_kernel<8%s> cfg5 T=32 256x256x4 u16, %d chips" % (", fused band stats" if stats else "", chips), ms, dense,
            {"chips_per_s": round(chips / ms * 1e3, 1), "note": "dense-equivalent bytes; the kernel skips filtered/occluded scenes",
             "GB/s_min_touched": round(touched_min / (ms / 1e3) / 1e9, 1), "mean_eligible": float(nel.float().mean().cpu())})
 
@@ -140,7 +146,7 @@ def bench_decode(dev, kind, n_distinct=16, reps=None):
     pairs = len(batch) // 2
     ms = best["decode_ms"] + best["assemble_ms"]
     algo = best["compressed_bytes"] + best["decoded_bytes"]
-    report("decode %s: %d chip pairs (%d streams)" % (kind, pairs, best["streams"]), ms, algo,
+    return report("decode %s: %d chip pairs (%d streams)" % (kind, pairs, best["streams"]), ms, algo,
            {"chip_pairs_per_s": round(pairs / ms * 1e3, 1), "decode_ms": round(best["decode_ms"], 3),
             "assemble_ms": round(best["assemble_ms"], 3), "decoded_GB/s": round(best["decoded_bytes"] / ms / 1e6, 1),
             "wall_ms_incl_host_parse_and_h2d": round(best["wall_ms"], 1)})
@@ -306,6 +312,7 @@ def bench_build(dev, n_shards=8):
     import bench as B
     g = torch.Generator(device=dev)
     g.manual_seed(3)
+    res = []
     for name, (h, c, dt, kind, n) in {"build cfg1 256x256x3 u8 -> BytesList": (256, 3, torch.uint8, 1, 250),
                                       "build cfg3 512x512x4 u16 -> FloatList": (512, 4, torch.int16, 2, 32)}.items():
         plans = []
@@ -320,7 +327,9 @@ def bench_build(dev, n_shards=8):
             plans.append(ops.BuildPlan(items, dev))
         ms = timeit(lambda i: plans[i % n_shards].launch(), 16)
         in_b = n * (h * h * c * (1 if dt == torch.uint8 else 2) + h * h)
-        report(name + " (%d records)" % n, ms, in_b + plans[0].total, {"records_per_s": round(n / ms * 1e3, 1)})
+        res.append(report(name + " (%d records)" % n, ms, in_b + plans[0].total, {"records_per_s": round(n / ms * 1e3, 1)}))
+        del plans
+    return res
 
 
 def main():
