@@ -22,7 +22,8 @@ class ImageInfo(ctypes.Structure):
                 ("blocks_across", ctypes.c_int32), ("blocks_down", ctypes.c_int32), ("n_blocks", ctypes.c_int32),
                 ("status", ctypes.c_int32), ("has_nodata", ctypes.c_int32), ("pad_", ctypes.c_int32),
                 ("nodata", ctypes.c_double), ("block_bytes", ctypes.c_uint64),
-                ("geotransform", ctypes.c_double * 6), ("has_geo", ctypes.c_int32), ("epsg", ctypes.c_int32)]
+                ("geotransform", ctypes.c_double * 6), ("has_geo", ctypes.c_int32), ("epsg", ctypes.c_int32),
+                ("png_bit_depth", ctypes.c_int32), ("png_color_type", ctypes.c_int32)]
 
 
 STREAM_DESC_DTYPE = np.dtype([("src_off", "<u8"), ("dst_off", "<u8"), ("src_len", "<u4"), ("dst_len", "<u4"),
@@ -30,11 +31,13 @@ STREAM_DESC_DTYPE = np.dtype([("src_off", "<u8"), ("dst_off", "<u8"), ("src_len"
 IMAGE_DESC_DTYPE = np.dtype([("scratch_off", "<u8"), ("out_off", "<u8"), ("block_bytes", "<u8"), ("format", "<i4"),
                              ("width", "<i4"), ("height", "<i4"), ("samples", "<i4"), ("bytes_per_sample", "<i4"),
                              ("predictor", "<i4"), ("planar", "<i4"), ("big_endian", "<i4"), ("block_w", "<i4"),
-                             ("block_h", "<i4"), ("blocks_across", "<i4"), ("blocks_down", "<i4")])
+                             ("block_h", "<i4"), ("blocks_across", "<i4"), ("blocks_down", "<i4"),
+                             ("png_bit_depth", "<i4"), ("png_color_type", "<i4"), ("png_flags", "<i4"), ("png_converted", "<i4")])
+PNG_AS_TF = 1      # b2chips.h B2_PNG_AS_TF: present palette / sub-byte / 16-bit PNGs as tf.image.decode_png does (else: as GDAL does)
 
 _vp, _i, _u64, _u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32
 _lib.register_signatures({
-    "b2_image_probe": (_i, [_vp, _u64, ctypes.POINTER(ImageInfo)]),
+    "b2_image_probe": (_i, [_vp, _u64, _u32, ctypes.POINTER(ImageInfo)]),
     "b2_image_blocks": (_i, [_vp, _u64, ctypes.POINTER(ImageInfo), _vp, _vp, _vp, _i]),
     "b2_decode_streams": (_i, [_vp, _vp, _vp, _i, _u32, _u32, _vp, _vp, _vp]),
     "b2_assemble_images": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
@@ -54,11 +57,11 @@ def _host_bytes(blob):
     return np.frombuffer(blob, dtype=np.uint8)
 
 
-def probe(blob) -> ImageInfo:
+def probe(blob, png_as_tf=False) -> ImageInfo:
     """Header-only read: height / width / bands / dtype (load_image_rasterio(decode=False), reference :51-53)."""
     a = _host_bytes(blob)
     info = ImageInfo()
-    check(lib().b2_image_probe(a.ctypes.data, a.size, ctypes.byref(info)))
+    check(lib().b2_image_probe(a.ctypes.data, a.size, PNG_AS_TF if png_as_tf else 0, ctypes.byref(info)))
     return info
 
 
@@ -79,7 +82,7 @@ class DecodePlan(ctypes.Structure):
 
 
 _lib.register_signatures({
-    "b2_decode_plan_batch": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _u64, _i, ctypes.POINTER(DecodePlan)]),
+    "b2_decode_plan_batch": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _u64, _i, _u32, ctypes.POINTER(DecodePlan)]),
 })
 
 
@@ -108,8 +111,11 @@ def _ptr_of(blob):
     return a.ctypes.data, a.size, a
 
 
-def decode_blobs(blobs, device=None, timings=None, want_infos=False):
+def decode_blobs(blobs, device=None, timings=None, want_infos=False, png_as_tf=False):
     """Decode a batch of encoded chips on the GPU.
+
+    png_as_tf: present palette / 1-2-4-bit / 16-bit PNGs the way tf.image.decode_png(dtype=uint8) does (the threaded
+    translator and the rgb parser) instead of the way rasterio / GDAL does (the multiprocessing translator).
 
     blobs: list of bytes / uint8 arrays (host).  Returns (arrays, status): arrays[i] is an (H,W,bands) CUDA
     tensor of the file's dtype (None when status[i] != 0).  All per-file host work (header parse, descriptor
@@ -137,7 +143,7 @@ def decode_blobs(blobs, device=None, timings=None, want_infos=False):
     for _ in range(2):
         check(lib().b2_decode_plan_batch(ptrs, sizes.ctypes.data, n, infos, status.ctypes.data, images.ctypes.data,
                                          hs.streams.data_ptr(), hs.streams.numel() // ssz, hs.stage.data_ptr(),
-                                         hs.stage.numel(), 0, ctypes.byref(plan)))
+                                         hs.stage.numel(), 0, PNG_AS_TF if png_as_tf else 0, ctypes.byref(plan)))
         if plan.filled:
             break
         if hs.stage.numel() < plan.stage_bytes:
@@ -180,7 +186,7 @@ def decode_blobs(blobs, device=None, timings=None, want_infos=False):
     return (arrays, status, infos) if want_infos else (arrays, status)
 
 
-def probe_blobs(blobs):
+def probe_blobs(blobs, png_as_tf=False):
     """Header-only pass over a batch (one native call): list of ImageInfo, status != 0 for unreadable files."""
     n = len(blobs)
     if n == 0:
@@ -197,7 +203,7 @@ def probe_blobs(blobs):
     images = np.zeros(n, dtype=IMAGE_DESC_DTYPE)
     plan = DecodePlan()
     check(lib().b2_decode_plan_batch(ptrs, sizes.ctypes.data, n, infos, status.ctypes.data, images.ctypes.data, None, 0, None, 0,
-                                     1, ctypes.byref(plan)))
+                                     1, PNG_AS_TF if png_as_tf else 0, ctypes.byref(plan)))
     return infos
 
 

@@ -28,7 +28,7 @@ class ImageCoder(object):
         raise NotImplementedError("JPEG decode is out of scope of the B200 hot path (SURVEY.md section 8f row 4)")
 
     def decode_png(self, image_data):
-        (image,), (st,) = _codec.decode_blobs([image_data], device=self.device)
+        (image,), (st,) = _codec.decode_blobs([image_data], device=self.device, png_as_tf=True)   # tf.image.decode_png
         if st != 0:
             raise _translate.ChipError("could not decode PNG (codec status %d)" % int(st))
         assert len(image.shape) == 3
@@ -80,7 +80,8 @@ def _process_image_files_worker(coder, thread_index, ranges, name, filenames, la
             raise NotImplementedError("only PNG chips are handled by the threaded translator on the GPU")
         _validate(info)
     return _translate.run_worker(thread_index, ranges, name, filenames, labels, out_folder, num_shards, key_fn,
-                                 store_as_array, label="thread", progress_every=1000, validate=validate, device=device)
+                                 store_as_array, label="thread", progress_every=1000, validate=validate, device=device,
+                                 png_as_tf=True)                     # this translator decodes with tf.image.decode_png
 
 
 def _process_image_files(name, img_files, lbl_files, out_folder, num_shards, num_threads, dltile_from_filename,

@@ -200,9 +200,9 @@ def parse_higher_dtype_array_proto(example_proto, device=None):
     return img, tgt, _identifier(si, 0)
 
 
-def _decode_pair(img_blob, tgt_blob, device=None):
+def _decode_pair(img_blob, tgt_blob, device=None, png_as_tf=False):
     from . import _codec
-    (img, tgt), status = _codec.decode_blobs([img_blob, tgt_blob], device=device)
+    (img, tgt), status = _codec.decode_blobs([img_blob, tgt_blob], device=device, png_as_tf=png_as_tf)
     for s, name in zip(status, ("image", "target")):
         if s != 0:
             raise InvalidArgumentError("could not decode %s data (codec status %d)" % (name, s))
@@ -212,7 +212,7 @@ def _decode_pair(img_blob, tgt_blob, device=None):
 def parse_encoded_rgb_img_proto(example_proto, device=None):
     """PNG-encoded payloads -> (uint8 (H,W,3), uint8 (H,W,1), identifier)  (reference :269-293, tf.io.decode_image)."""
     ib, _, tb, _, ident = _parse_byteslist_proto(example_proto, device)
-    img, tgt = _decode_pair(ib, tb, device)
+    img, tgt = _decode_pair(ib, tb, device, png_as_tf=True)             # tf.io.decode_image
     return img, tgt, ident
 
 

@@ -46,7 +46,7 @@ def _read_or_error(path):
         return e
 
 
-def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, device=None, blobs=None):
+def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, device=None, blobs=None, png_as_tf=False):
     """Read + (optionally) decode a batch of chip pairs.  Returns one entry per pair: a dict ready for
     ops.build_records, or the Exception that makes the reference skip the chip.  `blobs` = the 2n file contents
     (image, label, image, label, ...) when the caller has already read them (run_worker prefetches on threads)."""
@@ -64,12 +64,12 @@ def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, devi
             blobs[k] = b""
     arrays = [None] * (2 * n)
     if store_as_array:                                                      # ONE native planning call + the decode kernels
-        arrays, st, infos = _codec.decode_blobs(blobs, device=ctx.device, want_infos=True)
+        arrays, st, infos = _codec.decode_blobs(blobs, device=ctx.device, want_infos=True, png_as_tf=png_as_tf)
         for k in range(2 * n):
             if blobs[k] and infos[k].status == 0 and st[k] != 0 and errs[k // 2] is None:
                 errs[k // 2] = ChipError("could not decode %s (codec status %d)" % ((img_paths, lbl_paths)[k % 2][k // 2], int(st[k])))
     else:
-        infos = _codec.probe_blobs(blobs)
+        infos = _codec.probe_blobs(blobs, png_as_tf=png_as_tf)
     out = []
     for i in range(n):
         if errs[i] is not None:
@@ -101,7 +101,7 @@ def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, devi
 
 def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_directory, num_shards, key_fn,
                store_as_array, label="process", progress_every=100, validate=None, device=None, batch_pairs=None,
-               io_threads=8):
+               io_threads=8, png_as_tf=False):
     """The reference's worker loop, restructured as a three-stage pipeline: a thread pool reads the files of batch
     k+1 while the GPU decodes and serialises batch k and a writer thread appends batch k-1 to the shard file."""
     from concurrent.futures import ThreadPoolExecutor
@@ -146,7 +146,7 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
             pending_reads = submit_reads(batches[bi + 1]) if bi + 1 < len(batches) else []
             idx = list(range(b0, b1))
             pairs = load_pairs([img_filenames[i] for i in idx], [lbl_filenames[i] for i in idx], store_as_array,
-                               key_fn, validate, ctx.device, blobs=blobs)
+                               key_fn, validate, ctx.device, blobs=blobs, png_as_tf=png_as_tf)
             for s in range(per):
                 lo, hi = max(b0, int(shard_ranges[s])), min(b1, int(shard_ranges[s + 1]))
                 if lo >= hi:

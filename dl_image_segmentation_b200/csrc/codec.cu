@@ -774,9 +774,12 @@ rawcopy_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restric
 // ================================================================================================ PNG un-filter
 // One warp per image.  Rows are processed in bands of 32; lane L owns row band*32+L and runs x = step - L, so
 // the row above is always exactly one pixel ahead: `up` arrives by shuffle from lane L-1, `up-left` is the `up`
-// of the previous step, `left` is the lane's own previous result.
+// of the previous step, `left` is the lane's own previous result.  A "pixel" is the PNG filter unit: the bytes of
+// one complete pixel, at least one (1..8).  8-bit grey / grey+alpha / RGB / RGBA land in the output directly;
+// the other flavours (palette, 1/2/4-bit, 16-bit) are un-filtered into scratch and expanded by the same warp the way
+// the replaced decoder presents them (b2chips.h: B2_PNG_AS_TF or GDAL).
 __global__ void __launch_bounds__(128)
-png_unfilter_kernel(const uint8_t* __restrict__ scratch, const b2_image_desc* __restrict__ imgs, int n_images,
+png_unfilter_kernel(uint8_t* __restrict__ scratch, const b2_image_desc* __restrict__ imgs, int n_images,
                     uint8_t* __restrict__ out, int32_t* __restrict__ status) {
     const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -784,10 +787,14 @@ png_unfilter_kernel(const uint8_t* __restrict__ scratch, const b2_image_desc* __
     const b2_image_desc im = imgs[wi];
     if (im.format != 2) return;
     if (status && status[wi] != 0) return;
-    const int bpp = im.samples, w = im.width, h = im.height;
-    const size_t rb = (size_t)w * bpp;
+    const int depth = im.png_bit_depth ? im.png_bit_depth : 8, ct = im.png_color_type;
+    const int src_ch = im.png_converted ? (ct == 0 || ct == 3 ? 1 : (ct == 2 ? 3 : (ct == 4 ? 2 : 4))) : im.samples;
+    const int bpp = max(1, src_ch * depth / 8), h = im.height;
+    const size_t rb = ((size_t)im.width * src_ch * depth + 7) / 8;
+    const int w = (int)(rb / bpp);                                       // filter units per row
     const uint8_t* src = scratch + im.scratch_off;
-    uint8_t* dst = out + im.out_off;
+    uint8_t* unf = scratch + im.scratch_off + ((im.block_bytes + 15) & ~(uint64_t)15);
+    uint8_t* dst = im.png_converted ? unf : out + im.out_off;
     bool bad = false;
     for (int band = 0; band < h; band += 32) {
         const int row = band + lane;
@@ -795,13 +802,13 @@ png_unfilter_kernel(const uint8_t* __restrict__ scratch, const b2_image_desc* __
         const uint8_t* srow = src + (size_t)(live ? row : 0) * (rb + 1);
         const int ft = live ? srow[0] : 0;
         if (live && ft > 4) bad = true;
-        uint32_t left[4] = {0, 0, 0, 0}, upl[4] = {0, 0, 0, 0}, cur[4] = {0, 0, 0, 0};
+        uint32_t left[8] = {0, 0, 0, 0, 0, 0, 0, 0}, upl[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cur[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const uint8_t* prow = (band > 0) ? dst + (size_t)(band - 1) * rb : nullptr;  // row above the band (lane 0)
         for (int step = 0; step < w + 31; step++) {
             const int x = step - lane;
             const bool act = live && x >= 0 && x < w;
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
+            for (int c = 0; c < 8; c++) {
                 if (c >= bpp) break;
                 uint32_t up = __shfl_up_sync(0xffffffffu, cur[c], 1);     // lane L-1's pixel x (computed last step)
                 if (lane == 0) up = (prow && x >= 0 && x < w) ? prow[(size_t)x * bpp + c] : 0;
@@ -828,7 +835,40 @@ png_unfilter_kernel(const uint8_t* __restrict__ scratch, const b2_image_desc* __
         }
         __syncwarp();
     }
-    if (__ballot_sync(0xffffffffu, bad) && lane == 0) set_status(status, wi, 41);
+    if (__ballot_sync(0xffffffffu, bad)) {
+        if (lane == 0) set_status(status, wi, 41);
+        return;
+    }
+    if (!im.png_converted) return;
+    // ---- expand pass
+    const bool tf = (im.png_flags & B2_PNG_AS_TF) != 0;
+    const uint8_t* pal = unf + ((rb * (size_t)h + 15) & ~(size_t)15);    // 256 x RGBA (palette images)
+    uint8_t* o = out + im.out_off;
+    const int W = im.width, S = im.samples;
+    const size_t npix = (size_t)W * h;
+    if (depth == 16) {                     // big-endian samples: TF keeps the high byte, GDAL the uint16 (little-endian here)
+        const size_t ns = npix * src_ch;
+        for (size_t i = lane; i < ns; i += 32) {
+            const size_t y = i / ((size_t)W * src_ch), k = i - y * (size_t)W * src_ch;
+            const uint8_t hi = unf[y * rb + 2 * k], lo = unf[y * rb + 2 * k + 1];
+            if (tf) o[i] = hi;
+            else { o[2 * i] = lo; o[2 * i + 1] = hi; }
+        }
+        return;
+    }
+    const uint32_t vmask = (1u << depth) - 1u;
+    const uint32_t scale = depth == 1 ? 255u : (depth == 2 ? 85u : (depth == 4 ? 17u : 1u));
+    for (size_t i = lane; i < npix; i += 32) {
+        const size_t y = i / W;
+        const uint32_t x = (uint32_t)(i - y * W);
+        const uint32_t bit = x * depth;
+        const uint32_t v = (unf[y * rb + (bit >> 3)] >> (8 - depth - (bit & 7))) & vmask;     // packed MSB first
+        if (ct == 3 && tf) {
+            for (int c = 0; c < S; c++) o[i * S + c] = pal[4 * v + c];
+        } else {
+            o[i] = (uint8_t)(ct == 0 && tf ? v * scale : v);
+        }
+    }
 }
 
 // ================================================================================================ TIFF assembly
@@ -1053,7 +1093,7 @@ extern "C" int b2_assemble_images(b2_ctx* ctx, uint8_t* scratch, const b2_image_
         B2_CUDA(cudaGetLastError());
     }
     if (any_png) {
-        png_unfilter_kernel<<<(n_images * 32 + 127) / 128, 128, 0, s>>>(scratch, imgs_dev, n_images, out, status);
+        png_unfilter_kernel<<<(n_images * 32 + 127) / 128, 128, 0, s>>>(scratch, imgs_dev, n_images, out, status);   // (+ expand pass)
         ctx->launches++;
         B2_CUDA(cudaGetLastError());
     }
@@ -1221,14 +1261,14 @@ bool png_chunk_crc_ok(const uint8_t* blob, uint64_t p, uint64_t n) {
 
 // Header-only probe: what load_image_rasterio(decode=False) reads (_img_to_tf_mp.py:51-53) plus what the
 // decoder needs.  info->status: 0 ok, 2 corrupt header, 3 unsupported flavour.
-extern "C" int b2_image_probe(const uint8_t* blob, uint64_t size, b2_image_info* info) {
+extern "C" int b2_image_probe(const uint8_t* blob, uint64_t size, uint32_t flags, b2_image_info* info) {
     B2_REQUIRE(blob && info, "b2_image_probe: NULL argument");
     memset(info, 0, sizeof(*info));
     if (size >= 8 && memcmp(blob, kPngSig, 8) == 0) {
         info->format = 2;
         uint64_t p = 8;
-        bool ihdr = false;
-        int n_idat = 0;
+        bool ihdr = false, plte = false, trns = false;
+        int n_idat = 0, src_ch = 0, depth = 0, ct = 0;
         while (p + 8 <= size) {
             const uint64_t n = ((uint64_t)blob[p] << 24) | (blob[p + 1] << 16) | (blob[p + 2] << 8) | blob[p + 3];
             if (p + 12 + n > size) { info->status = 2; return 0; }
@@ -1236,12 +1276,19 @@ extern "C" int b2_image_probe(const uint8_t* blob, uint64_t size, b2_image_info*
                 const uint8_t* d = blob + p + 8;
                 info->width = (int32_t)(((uint32_t)d[0] << 24) | (d[1] << 16) | (d[2] << 8) | d[3]);
                 info->height = (int32_t)(((uint32_t)d[4] << 24) | (d[5] << 16) | (d[6] << 8) | d[7]);
-                const int depth = d[8], ct = d[9], inter = d[12];
-                info->samples = ct == 0 ? 1 : (ct == 2 ? 3 : (ct == 4 ? 2 : (ct == 6 ? 4 : 0)));
-                info->dtype = B2_U8;
-                if (depth != 8 || info->samples == 0 || inter != 0) info->status = 3;
+                depth = d[8];
+                ct = d[9];
+                const int inter = d[12];
+                src_ch = ct == 0 ? 1 : (ct == 2 ? 3 : (ct == 3 ? 1 : (ct == 4 ? 2 : (ct == 6 ? 4 : 0))));
+                bool ok = src_ch != 0 && (depth == 8 || (depth == 16 && ct != 3) || ((depth == 1 || depth == 2 || depth == 4) && (ct == 0 || ct == 3)));
+                if (!ok || inter != 0) info->status = 3;
                 if (!png_chunk_crc_ok(blob, p, n)) { info->status = 2; return 0; }
                 ihdr = true;
+            } else if (memcmp(blob + p + 4, "PLTE", 4) == 0 && n_idat == 0) {
+                if (n % 3 != 0 || n > 768 || !png_chunk_crc_ok(blob, p, n)) { info->status = 2; return 0; }
+                plte = true;
+            } else if (memcmp(blob + p + 4, "tRNS", 4) == 0 && n_idat == 0) {
+                trns = true;
             } else if (memcmp(blob + p + 4, "IDAT", 4) == 0) {
                 n_idat++;
             } else if (memcmp(blob + p + 4, "IEND", 4) == 0) {
@@ -1250,6 +1297,16 @@ extern "C" int b2_image_probe(const uint8_t* blob, uint64_t size, b2_image_info*
             p += 12 + n;
         }
         if (!ihdr || info->width <= 0 || info->height <= 0) { info->status = 2; return 0; }
+        if (info->status == 0 && ct == 3 && !plte) { info->status = 2; return 0; }
+        info->png_bit_depth = depth;
+        info->png_color_type = ct;
+        if (flags & B2_PNG_AS_TF) {            // libpng transforms as tf.image.decode_png(dtype=uint8) sets them up
+            info->samples = ct == 3 ? (trns ? 4 : 3) : src_ch;
+            info->dtype = B2_U8;
+        } else {                               // GDAL's PNG driver
+            info->samples = src_ch;
+            info->dtype = depth == 16 ? B2_U16 : B2_U8;
+        }
         info->n_blocks = n_idat;          // IDAT chunks to concatenate
         info->block_w = info->width;
         info->block_h = info->height;
@@ -1257,7 +1314,8 @@ extern "C" int b2_image_probe(const uint8_t* blob, uint64_t size, b2_image_info*
         info->planar = 1;
         info->predictor = 1;
         info->compression = 8;
-        info->block_bytes = (uint64_t)info->height * ((uint64_t)info->width * info->samples + 1);
+        const uint64_t rb = ((uint64_t)info->width * src_ch * (depth ? depth : 8) + 7) / 8;
+        info->block_bytes = (uint64_t)info->height * (rb + 1);
         info->geotransform[1] = 1;
         info->geotransform[5] = 1;
         if (n_idat == 0 && info->status == 0) info->status = 2;
@@ -1392,6 +1450,29 @@ void fill_image(const uint8_t* blob, uint64_t size, int i, const b2_image_info& 
         sd.dst_len = (uint32_t)info.block_bytes;
         sd.codec = CODEC_ZLIB;
         sd.image = i;
+        if (info.png_color_type == 3) {   // 256-entry RGBA table from PLTE (+ tRNS): missing colours black, missing alpha opaque
+            uint8_t* pal = stage + up_to(pl.stage_off + total, 16);
+            for (int k = 0; k < 256; k++) { pal[4 * k] = pal[4 * k + 1] = pal[4 * k + 2] = 0; pal[4 * k + 3] = 255; }
+            uint64_t p = 8;
+            while (p + 8 <= size) {
+                const uint64_t n = ((uint64_t)blob[p] << 24) | (blob[p + 1] << 16) | (blob[p + 2] << 8) | blob[p + 3];
+                if (p + 12 + n > size) break;
+                if (memcmp(blob + p + 4, "PLTE", 4) == 0) {
+                    for (uint64_t k = 0; k < n / 3 && k < 256; k++) memcpy(pal + 4 * k, blob + p + 8 + 3 * k, 3);
+                } else if (memcmp(blob + p + 4, "tRNS", 4) == 0) {
+                    for (uint64_t k = 0; k < n && k < 256; k++) pal[4 * k + 3] = blob[p + 8 + k];
+                } else if (memcmp(blob + p + 4, "IDAT", 4) == 0) {
+                    break;
+                }
+                p += 12 + n;
+            }
+            b2_stream_desc& ps = streams[pl.stream0 + 1];
+            ps.src_off = (uint64_t)(pal - stage);
+            ps.dst_off = pl.scratch_off + up_to(info.block_bytes, 16) + up_to(info.block_bytes - (uint64_t)info.height, 16);
+            ps.src_len = ps.dst_len = 1024;
+            ps.codec = CODEC_RAW;
+            ps.image = i;
+        }
     } else {                  // TIFF: the file as is, one stream per tile / strip
         memcpy(stage + pl.stage_off, blob, size);
         const int codec = info.compression == 1 ? CODEC_RAW : (info.compression == 5 ? CODEC_LZW : CODEC_ZLIB);
@@ -1410,7 +1491,7 @@ void fill_image(const uint8_t* blob, uint64_t size, int i, const b2_image_info& 
 
 extern "C" int b2_decode_plan_batch(const uint8_t* const* blobs, const uint64_t* sizes, int n, b2_image_info* infos,
                                     int32_t* status, b2_image_desc* images, b2_stream_desc* streams, int streams_cap,
-                                    uint8_t* stage, uint64_t stage_cap, int n_threads, b2_decode_plan* plan) {
+                                    uint8_t* stage, uint64_t stage_cap, int n_threads, uint32_t flags, b2_decode_plan* plan) {
     B2_REQUIRE(blobs && sizes && infos && status && images && plan, "b2_decode_plan_batch: NULL argument");
     B2_REQUIRE(n >= 0, "b2_decode_plan_batch: n < 0");
     memset(plan, 0, sizeof(*plan));
@@ -1423,7 +1504,7 @@ extern "C" int b2_decode_plan_batch(const uint8_t* const* blobs, const uint64_t*
         memset(&images[i], 0, sizeof(b2_image_desc));
         status[i] = 0;
         if (!blobs[i] || sizes[i] == 0) { memset(&info, 0, sizeof(info)); info.status = 2; status[i] = 2; continue; }
-        b2_image_probe(blobs[i], sizes[i], &info);
+        b2_image_probe(blobs[i], sizes[i], flags, &info);
         if (info.status != 0) { status[i] = info.status; continue; }
         const int bs = info.dtype == B2_U8 || info.dtype == B2_I8 ? 1 : (info.dtype == B2_U16 || info.dtype == B2_I16 ? 2 : (info.dtype == B2_F64 ? 8 : 4));
         pl[i] = ImgPlan{stage_pos, scratch_pos, out_pos, n_streams};
@@ -1436,9 +1517,24 @@ extern "C" int b2_decode_plan_batch(const uint8_t* const* blobs, const uint64_t*
         im.block_w = info.block_w; im.block_h = info.block_h;
         im.blocks_across = info.blocks_across; im.blocks_down = info.blocks_down;
         if (info.format == 2) {
+            im.png_bit_depth = info.png_bit_depth;
+            im.png_color_type = info.png_color_type;
+            im.png_flags = (int32_t)flags;
+            im.png_converted = info.png_bit_depth != 8 || info.png_color_type == 3;
             n_streams += 1;
             stage_pos += sizes[i];                       // upper bound of the IDAT payload bytes
-            scratch_pos += up_to(info.block_bytes, 256);
+            if (im.png_converted) {                      // + un-filtered bytes + palette (see b2_image_desc)
+                const uint64_t unf = info.block_bytes - (uint64_t)info.height;
+                scratch_pos += up_to(up_to(info.block_bytes, 16) + up_to(unf, 16) + 1024, 256);
+                if (info.png_color_type == 3) {
+                    n_streams += 1;                      // the palette travels as a stored stream
+                    stage_pos = up_to(stage_pos, 16) + 1024;
+                    mask |= 4u;
+                    if (max_raw < 1024) max_raw = 1024;
+                }
+            } else {
+                scratch_pos += up_to(info.block_bytes, 256);
+            }
             mask |= 2u;
         } else {
             n_streams += info.n_blocks;

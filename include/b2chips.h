@@ -208,15 +208,26 @@ typedef struct {
     int32_t status;      /* 0 ok, 2 corrupt header, 3 flavour out of scope                                    */
     int32_t has_nodata, pad_;
     double nodata;       /* GDAL_NODATA tag 42113 (_descartes_img_chips.py:794-795)                           */
-    uint64_t block_bytes; /* decoded bytes of one full block (PNG: h * (1 + w*samples) filtered bytes)        */
+    uint64_t block_bytes; /* decoded bytes of one full block (PNG: h * (1 + row bytes) filtered bytes)          */
     /* what src.get_transform() / src.read_crs() return (_img_to_tf_mp.py:49-50), for identifiers built with
      * dltile_from_filename=False (:63-67): GDAL-order affine, default (0,1,0,0,0,1); EPSG code or 0               */
     double geotransform[6];
     int32_t has_geo, epsg;
+    int32_t png_bit_depth, png_color_type; /* IHDR fields (0 for TIFF)                                          */
 } b2_image_info;
 
+/* How PNG flavours beyond 8-bit grey / RGB(A) are presented (flags of b2_image_probe / b2_decode_plan_batch).
+ * The two reference paths disagree on them, so the caller says which one it replaces:
+ *   B2_PNG_AS_TF   tf.image.decode_png(dtype=uint8) (_img_to_tf_threaded.py:59, _tfrecord_image_translation.py:283,289;
+ *                  libpng transforms): palette -> RGB (RGBA with tRNS), 1/2/4-bit grey scaled to 0..255,
+ *                  16-bit samples -> their high byte;
+ *   0              rasterio / GDAL's PNG driver (_img_to_tf_mp.py:45-48): palette -> one band of indices,
+ *                  1/2/4-bit grey unscaled, 16-bit samples -> uint16.
+ * 8-bit grey, grey+alpha, RGB and RGBA are the same in both.  Interlaced PNGs are out of scope (status 3). */
+#define B2_PNG_AS_TF 1u
+
 /* Host-side header parse (TIFF IFD / PNG chunks); never touches the GPU. */
-int b2_image_probe(const uint8_t* blob, uint64_t size, b2_image_info* info);
+int b2_image_probe(const uint8_t* blob, uint64_t size, uint32_t flags, b2_image_info* info);
 /* Host-side: offset / byte count / decoded length of each compressed block (TIFF) or IDAT payload (PNG). */
 int b2_image_blocks(const uint8_t* blob, uint64_t size, const b2_image_info* info, uint64_t* offsets,
                     uint64_t* counts, uint64_t* decoded_len, int cap);
@@ -236,6 +247,8 @@ typedef struct {         /* one image to assemble from its decoded blocks       
     uint64_t block_bytes;
     int32_t format, width, height, samples, bytes_per_sample, predictor, planar, big_endian;
     int32_t block_w, block_h, blocks_across, blocks_down;
+    int32_t png_bit_depth, png_color_type, png_flags, png_converted; /* PNG flavours that need the expand pass:   *
+                           * scratch = filtered bytes | un-filtered bytes | 256-entry RGBA palette (16-byte aligned each) */
 } b2_image_desc;
 
 typedef struct {
@@ -256,7 +269,7 @@ typedef struct {
  * to learn the sizes.  status[i] != 0 marks a file the reference would skip (:133-136); its streams are inert. */
 int b2_decode_plan_batch(const uint8_t* const* blobs, const uint64_t* sizes, int n, b2_image_info* infos_out,
                          int32_t* status_out, b2_image_desc* images_out, b2_stream_desc* streams_out, int streams_cap,
-                         uint8_t* stage_host, uint64_t stage_cap, int n_threads, b2_decode_plan* plan);
+                         uint8_t* stage_host, uint64_t stage_cap, int n_threads, uint32_t flags, b2_decode_plan* plan);
 
 /* codec_mask: bit0 LZW, bit1 zlib, bit2 stored streams present.  status_dev (one int32 per image) must be
  * zeroed by the caller; non-zero afterwards = that image failed to decode (skip it, _img_to_tf_mp.py:133-136). */

@@ -155,19 +155,25 @@ _PNG_SIG = b"\x89PNG\r\n\x1a\n"
 def parse_png(blob: bytes) -> dict:
     if blob[:8] != _PNG_SIG:
         raise DecodeError("not a PNG")
-    p, idat, ihdr = 8, [], None
+    p, idat, ihdr, plte, trns = 8, [], None, None, None
     while p + 8 <= len(blob):
         (n,) = struct.unpack(">I", blob[p:p + 4])
         typ = blob[p + 4:p + 8]
         body = blob[p + 8:p + 8 + n]
         if len(body) != n:
             raise DecodeError("truncated chunk")
-        if typ in (b"IHDR", b"IDAT"):
+        if typ in (b"IHDR", b"IDAT", b"PLTE"):
             # libpng (behind tf.image.decode_png and GDAL's PNG driver) treats a CRC mismatch in a critical chunk as fatal
             if blob[p + 8 + n:p + 12 + n] != struct.pack(">I", zlib.crc32(typ + body) & 0xFFFFFFFF):
                 raise DecodeError("CRC mismatch in %s chunk" % typ.decode())
         if typ == b"IHDR":
             ihdr = struct.unpack(">IIBBBBB", body)
+        elif typ == b"PLTE" and not idat:
+            if n % 3 or n > 768:
+                raise DecodeError("bad PLTE")
+            plte = body
+        elif typ == b"tRNS" and not idat:
+            trns = body
         elif typ == b"IDAT":
             idat.append(body)
         elif typ == b"IEND":
@@ -176,16 +182,27 @@ def parse_png(blob: bytes) -> dict:
     if ihdr is None:
         raise DecodeError("no IHDR")
     w, h, depth, ctype, comp, flt, inter = ihdr
-    return dict(width=w, height=h, depth=depth, color_type=ctype, interlace=inter, idat=b"".join(idat))
+    return dict(width=w, height=h, depth=depth, color_type=ctype, interlace=inter, idat=b"".join(idat), plte=plte, trns=trns)
 
 
-def decode_png(blob: bytes) -> np.ndarray:
-    """8-bit grey / RGB / grey+alpha / RGBA, non-interlaced -> (H,W,C) uint8 (decode_png with channels=0)."""
+def decode_png(blob: bytes, as_tf: bool = True) -> np.ndarray:
+    """Non-interlaced PNG -> (H,W,C).  8-bit grey / grey+alpha / RGB / RGBA are the samples as stored.  The other
+    flavours depend on who decodes (the two reference paths disagree):
+      as_tf=True   tf.image.decode_png(dtype=uint8) (_img_to_tf_threaded.py:59; libpng png_set_palette_to_rgb,
+                   png_set_expand_gray_1_2_4_to_8, png_set_strip_16): palette -> RGB (RGBA when a tRNS chunk is present),
+                   1/2/4-bit grey scaled by 255/(2^bits-1), 16-bit -> the high byte of every sample;
+      as_tf=False  rasterio / GDAL PNG driver (_img_to_tf_mp.py:45-48): palette -> the indices as one band, sub-byte
+                   grey unscaled, 16-bit -> uint16."""
     t = parse_png(blob)
-    ch = {0: 1, 2: 3, 4: 2, 6: 4}.get(t["color_type"])
-    if t["depth"] != 8 or ch is None or t["interlace"]:
-        raise DecodeError("PNG flavour out of scope (depth %d, colour type %d)" % (t["depth"], t["color_type"]))
-    h, rb = t["height"], t["width"] * ch
+    depth, ct = t["depth"], t["color_type"]
+    ch = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}.get(ct)
+    ok = ch is not None and (depth == 8 or (depth == 16 and ct != 3) or (depth in (1, 2, 4) and ct in (0, 3)))
+    if not ok or t["interlace"]:
+        raise DecodeError("PNG flavour out of scope (depth %d, colour type %d, interlace %d)" % (depth, ct, t["interlace"]))
+    if ct == 3 and t["plte"] is None:
+        raise DecodeError("palette image without PLTE")
+    h, w = t["height"], t["width"]
+    rb = (w * ch * depth + 7) // 8
     try:
         raw = zlib.decompress(t["idat"])
     except zlib.error as e:
@@ -194,14 +211,39 @@ def decode_png(blob: bytes) -> np.ndarray:
         raise DecodeError("short PNG stream")
     src = np.frombuffer(raw, dtype=np.uint8, count=h * (rb + 1))
     dst = np.zeros(h * rb, dtype=np.uint8)
-    if clib().orc_png_unfilter(src.ctypes.data, dst.ctypes.data, h, rb, ch) != 0:
+    if clib().orc_png_unfilter(src.ctypes.data, dst.ctypes.data, h, rb, max(1, ch * depth // 8)) != 0:
         raise DecodeError("bad PNG filter type")
-    return dst.reshape(h, t["width"], ch)
+    rows = dst.reshape(h, rb)
+    if depth == 8 and ct != 3:
+        return rows.reshape(h, w, ch)
+    if depth == 16:
+        be = rows.reshape(h, w, ch, 2)
+        if as_tf:
+            return be[..., 0].copy()
+        return (be[..., 0].astype(np.uint16) << 8) | be[..., 1]
+    # packed samples, most significant bits first
+    bits = np.unpackbits(rows, axis=1)[:, :w * depth].reshape(h, w, depth)
+    v = np.zeros((h, w), np.uint8)
+    for k in range(depth):
+        v = (v << 1) | bits[..., k]
+    if ct == 0:
+        scale = {1: 255, 2: 85, 4: 17}[depth] if as_tf else 1
+        return (v * np.uint8(scale))[..., None]
+    if not as_tf:
+        return v[..., None]
+    pal = np.zeros((256, 4), np.uint8)
+    pal[:, 3] = 255
+    pl = np.frombuffer(t["plte"], np.uint8).reshape(-1, 3)
+    pal[:len(pl), :3] = pl
+    if t["trns"] is not None:
+        tr = np.frombuffer(t["trns"], np.uint8)[:256]
+        pal[:len(tr), 3] = tr
+    return pal[v][..., :4 if t["trns"] is not None else 3].copy()
 
 
-def decode_image(blob: bytes) -> np.ndarray:
+def decode_image(blob: bytes, png_as_tf: bool = True) -> np.ndarray:
     if blob[:8] == _PNG_SIG:
-        return decode_png(blob)
+        return decode_png(blob, png_as_tf)
     if blob[:2] in (b"II", b"MM"):
         return decode_tiff(blob)
     raise DecodeError("unknown image format")
@@ -243,6 +285,6 @@ def image_shape(blob: bytes):
     """(height, width, bands) from the header only — load_image_rasterio(decode=False), :51-53."""
     if blob[:8] == _PNG_SIG:
         t = parse_png(blob)
-        return t["height"], t["width"], {0: 1, 2: 3, 4: 2, 6: 4}[t["color_type"]]
+        return t["height"], t["width"], {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[t["color_type"]]     # GDAL: a palette image is one band
     t = parse_tiff(blob)
     return t["height"], t["width"], t["spp"]

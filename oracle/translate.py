@@ -19,7 +19,7 @@ def load_image(path, parse_dltile_filename=True, decode=True):
     with open(path, "rb") as f:
         blob = f.read()
     if decode:
-        arr = imagecodecs.decode_image(blob)
+        arr = imagecodecs.decode_image(blob, png_as_tf=False)        # rasterio -> GDAL's PNG driver
         h, w, b = arr.shape
         data = arr
     else:

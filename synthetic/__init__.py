@@ -239,6 +239,30 @@ def png_bytes_manual(arr, filter_types=(0, 1, 2, 3, 4), zlevel=6, idat_chunk=Non
     return body + _png_chunk(b"IEND", b"")
 
 
+def png_bytes_flavour(samples, depth, ctype, palette=None, trns=None, filter_types=(0, 1, 2, 3, 4), zlevel=6):
+    """PNG of any non-interlaced flavour.  samples: (H,W) or (H,W,C) integers < 2**depth (palette indices for
+    colour type 3); depth 1/2/4 packs them most-significant-bits first, depth 16 stores them big-endian."""
+    a = np.asarray(samples)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    H, W, C = a.shape
+    assert C == {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[ctype]
+    if depth == 16:
+        rows = a.astype(">u2").view(np.uint8).reshape(H, W, 2 * C)
+    elif depth == 8:
+        rows = a.astype(np.uint8)
+    else:
+        bits = ((a[:, :, 0].astype(np.uint8)[:, :, None] >> np.arange(depth - 1, -1, -1)) & 1).reshape(H, W * depth)
+        rows = np.packbits(bits, axis=1)[:, :, None]                      # (H, ceil(W*depth/8), 1): filter unit = 1 byte
+    z = zlib.compress(png_filter_rows(rows, filter_types), zlevel)
+    body = b"\x89PNG\r\n\x1a\n" + _png_chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, depth, ctype, 0, 0, 0))
+    if palette is not None:
+        body += _png_chunk(b"PLTE", np.asarray(palette, np.uint8).reshape(-1, 3).tobytes())
+    if trns is not None:
+        body += _png_chunk(b"tRNS", bytes(trns))
+    return body + _png_chunk(b"IDAT", z) + _png_chunk(b"IEND", b"")
+
+
 def png_bytes_raw_zlib(width, height, channels, zstream):
     """A PNG around a caller-supplied zlib stream (tests of malformed / hand-made DEFLATE data)."""
     ctype = {1: 0, 2: 4, 3: 2, 4: 6}[channels]

@@ -45,8 +45,8 @@ def test_struct_layouts_match_the_header(lib):
     assert ctypes.sizeof(_lib.ExampleIndex) == 80 == np.dtype(_lib.EXAMPLE_INDEX_DTYPE).itemsize
     assert ctypes.sizeof(_lib.BuildDesc) == 80 == np.dtype(_lib.BUILD_DESC_DTYPE).itemsize
     assert ctypes.sizeof(_lib.ParseSink) == 64
-    assert ctypes.sizeof(_codec.ImageInfo) == 88 + 6 * 8 + 8
-    assert _codec.STREAM_DESC_DTYPE.itemsize == 32 and _codec.IMAGE_DESC_DTYPE.itemsize == 72
+    assert ctypes.sizeof(_codec.ImageInfo) == 88 + 6 * 8 + 8 + 8
+    assert _codec.STREAM_DESC_DTYPE.itemsize == 32 and _codec.IMAGE_DESC_DTYPE.itemsize == 72 + 16
 
 
 def test_example_layout_matches_oracle_bytes(lib):
@@ -200,12 +200,12 @@ def test_batch_decode_planner_matches_per_file_calls(lib):
     images = np.zeros(n, _codec.IMAGE_DESC_DTYPE)
     plan = _codec.DecodePlan()
     assert lib.b2_decode_plan_batch(ptrs, sizes.ctypes.data, n, infos, status.ctypes.data, images.ctypes.data, None, 0, None, 0,
-                                    2, ctypes.byref(plan)) == 0
+                                    2, 0, ctypes.byref(plan)) == 0
     assert plan.filled == 0 and plan.n_streams > 0
     streams = np.zeros(plan.n_streams, _codec.STREAM_DESC_DTYPE)
     stage = np.zeros(plan.stage_bytes, np.uint8)
     assert lib.b2_decode_plan_batch(ptrs, sizes.ctypes.data, n, infos, status.ctypes.data, images.ctypes.data,
-                                    streams.ctypes.data, len(streams), stage.ctypes.data, stage.size, 3, ctypes.byref(plan)) == 0
+                                    streams.ctypes.data, len(streams), stage.ctypes.data, stage.size, 3, 0, ctypes.byref(plan)) == 0
     assert plan.filled == 1
     assert list(status[-2:] != 0) == [True, True] and not status[:-2].any()
     k = 0

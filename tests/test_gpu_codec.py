@@ -113,6 +113,33 @@ def test_png_deflate_block_types(dev):
     _check(dev, blobs)
 
 
+@pytest.mark.parametrize("as_tf", [True, False])
+def test_png_palette_subbyte_and_16bit_flavours(dev, as_tf):
+    """Palette, 1/2/4-bit and 16-bit PNGs under both presentations (tf.image.decode_png vs rasterio/GDAL) == oracle
+    (which tests/test_oracle_golden.py pins against Pillow and OpenCV's libpng), mixed with ordinary chips in one batch."""
+    import torch
+    from dl_image_segmentation_b200 import _codec
+    from test_oracle_golden import _png_flavour_cases
+    cases = _png_flavour_cases()
+    img, lab, _ = syn.cfg1_chip(5, size=64)
+    blobs = [syn.png_bytes(img)] + [b for _, b in cases] + [syn.png_bytes(lab)]
+    wants = [oic.decode_png(b, as_tf) for b in blobs]
+    arrays, status, infos = _codec.decode_blobs(blobs, device=dev, want_infos=True, png_as_tf=as_tf)
+    assert not np.asarray(status).any(), list(status)
+    for (name, _), a, w, info in zip([("rgb", 0)] + cases + [("label", 0)], arrays, wants, infos):
+        g = a.cpu().numpy() if a.dtype != torch.uint16 else a.view(torch.int16).cpu().numpy().view(np.uint16)
+        assert g.dtype == w.dtype and g.shape == w.shape, (name, g.dtype, g.shape, w.dtype, w.shape)
+        np.testing.assert_array_equal(g, w, err_msg=name)
+        assert (info.height, info.width, info.samples) == w.shape
+        p = _codec.probe(blobs[0], png_as_tf=as_tf)
+        assert (p.height, p.width, p.samples, p.png_bit_depth, p.png_color_type) == (64, 64, 3, 8, 2)
+    # interlaced PNGs stay out of scope: flagged, not mis-decoded
+    inter = bytearray(blobs[0])
+    inter[8 + 8 + 12] = 1
+    inter[8 + 8 + 13:8 + 8 + 17] = zlib.crc32(bytes(inter[12:8 + 8 + 13])).to_bytes(4, "big")
+    assert _codec.probe(bytes(inter), png_as_tf=as_tf).status == 3
+
+
 def test_error_behaviour_of_zlib_and_libpng_is_mirrored(dev):
     """What the reference's decoders reject, the device path rejects: zlib's inflate_table refuses an incomplete
     literal/length set in the block header (even if the data never uses a missing code), and libpng treats a CRC

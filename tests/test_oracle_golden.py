@@ -130,6 +130,58 @@ def test_decoders_against_live_libtiff_and_libpng():
         oic.decode_image(syn.tiff_bytes(lab, tile=64)[:600])
 
 
+def _png_flavour_cases():
+    rng = np.random.default_rng(77)
+    H, W = 37, 53                                             # W * depth not a multiple of 8: rows end mid-byte
+    pal = rng.integers(0, 256, (256, 3), dtype=np.uint8)
+    cases = []
+    for depth in (1, 2, 4, 8):
+        idx = rng.integers(0, 1 << depth, (H, W), dtype=np.uint8)
+        cases.append(("palette%d" % depth, syn.png_bytes_flavour(idx, depth, 3, palette=pal[:1 << depth])))
+        cases.append(("palette%d+tRNS" % depth, syn.png_bytes_flavour(idx, depth, 3, palette=pal[:1 << depth],
+                                                                      trns=rng.integers(0, 256, max(1, (1 << depth) // 2), dtype=np.uint8))))
+        if depth < 8:
+            cases.append(("grey%d" % depth, syn.png_bytes_flavour(idx, depth, 0)))
+    cases.append(("short palette", syn.png_bytes_flavour(rng.integers(0, 8, (H, W), dtype=np.uint8), 4, 3, palette=pal[:5])))
+    for ct, C in ((0, 1), (2, 3), (4, 2), (6, 4)):
+        cases.append(("16-bit ct%d" % ct, syn.png_bytes_flavour(rng.integers(0, 65536, (H, W, C)), 16, ct)))
+    return cases
+
+
+def test_png_flavours_against_pillow_and_libpng():
+    """Palette, 1/2/4-bit and 16-bit PNGs under both presentations: tf.image.decode_png's libpng transforms (checked
+    against Pillow's, which applies the same expansions, and OpenCV's libpng for palettes) and GDAL's raw view
+    (indices / unscaled / uint16; checked against Pillow's raw modes and OpenCV's 16-bit read)."""
+    import cv2
+    from PIL import Image
+    for name, blob in _png_flavour_cases():
+        tf_view, gdal_view = oic.decode_png(blob, True), oic.decode_png(blob, False)
+        im = Image.open(io.BytesIO(blob))
+        im.load()
+        if name.startswith("palette") or name == "short palette":
+            want = np.asarray(im.convert("RGBA" if "tRNS" in name else "RGB"))
+            assert np.array_equal(tf_view, want), name
+            assert np.array_equal(gdal_view[..., 0], np.asarray(im)), name            # mode P: the indices
+            if "tRNS" not in name:
+                assert np.array_equal(cv2.imdecode(np.frombuffer(blob, np.uint8), cv2.IMREAD_COLOR)[..., ::-1], tf_view), name
+        elif name.startswith("grey"):
+            depth = int(name[4:])
+            want = np.asarray(im.convert("L"))                                       # '1' -> 0/255, L;2 -> x85, L;4 -> x17
+            assert np.array_equal(tf_view[..., 0], want), name
+            assert np.array_equal(gdal_view[..., 0], want // {1: 255, 2: 85, 4: 17}[depth]), name
+        else:
+            full = cv2.imdecode(np.frombuffer(blob, np.uint8), cv2.IMREAD_UNCHANGED)  # libpng, 16 bits kept
+            if full.ndim == 2:
+                full = full[..., None]
+            if full.shape[-1] >= 3:                                                  # OpenCV hands back B,G,R[,A]
+                full = full[..., [2, 1, 0] + ([3] if full.shape[-1] == 4 else [])]
+            if gdal_view.shape[-1] == 2:                                             # grey+alpha: OpenCV expands to BGRA
+                assert np.array_equal(gdal_view[..., 0], full[..., 0]) and np.array_equal(gdal_view[..., 1], full[..., 3]), name
+            else:
+                assert np.array_equal(gdal_view, full), name
+            assert gdal_view.dtype == np.uint16 and np.array_equal(tf_view, (gdal_view >> 8).astype(np.uint8)), name
+
+
 def test_png_error_behaviour_follows_libpng_and_zlib():
     """Critical-chunk CRC mismatch is fatal (libpng); an incomplete Huffman set is rejected in the block header (zlib)."""
     import cv2
