@@ -48,10 +48,15 @@ constexpr int kBufBytes = kTile + 128;   // tile + 32-byte halo, rounded so the 
 constexpr int kHotMaxK = 32;             // one-hot through shared-memory blocks + bulk stores up to this many classes
 constexpr int kHotLabels = B2_HOT_LABELS;  // labels per warp block (one or two per lane): one bulk store moves 4*K bytes per label
 constexpr int kHotBlocks = B2_HOT_BLOCKS;            // blocks per warp: the bulk store of one overlaps the fill of the other
-constexpr int kStages = B2_STAGES;               // tile buffers in the producer -> consumer ring
+// Tile buffers in the producer -> consumer ring.  The normalise + one-hot pass is bound by its output traffic and
+// short of shared memory (the one-hot blocks), so two do; the CRC-only and raw-copy passes are bound by the CRC chain
+// and by how well the bulk loads hide behind it: four buffers (ncu: a third of their stall samples were consumers
+// waiting for a tile with two).
+__host__ __device__ constexpr int stages_for(int mode) { return mode == B2_SINK_NORM_ONEHOT ? B2_STAGES : 4; }
+constexpr int kMaxStages = 4;
 constexpr int kConsumerWarps = kTileThreads / 32;
 constexpr int kCtaThreads = kTileThreads + 32;   // 8 consumer warps + 1 producer warp
-constexpr int kRunSlots = 4;             // shared-memory CRC accumulators for runs in flight (> kStages)
+constexpr int kRunSlots = 8;             // shared-memory CRC accumulators for runs in flight (> stages)
 
 // ---------------------------------------------------------------- PTX: mbarrier + bulk async copies (TMA, 1-D)
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -376,6 +381,8 @@ __device__ __forceinline__ void run_flush(const ParseArgs& a, Run& run, uint32_t
 template <int kMode, bool kProf = false>
 __global__ void __launch_bounds__(kCtaThreads, kMode == B2_SINK_NORM_ONEHOT ? 3 : 5)
 fused_parse_kernel(const ParseArgs a) {
+    constexpr int kStages = stages_for(kMode);
+    static_assert(kStages <= kMaxStages && kRunSlots > kStages, "ring sizes");
     extern __shared__ __align__(128) uint8_t dyn[];
     __shared__ CrcSmem cs;
     __shared__ TileJob job[kStages];
@@ -652,7 +659,7 @@ struct LaunchCfg {
 LaunchCfg g_cfg[64];
 
 size_t dyn_bytes(int mode, int K) {
-    size_t d = (size_t)kStages * kBufBytes;
+    size_t d = (size_t)stages_for(mode) * kBufBytes;
     if (mode == B2_SINK_NORM_ONEHOT && K <= kHotMaxK) d += (size_t)(kTileThreads / 32) * kHotBlocks * (kHotLabels * K + 4) * sizeof(float);
     return d;
 }
@@ -707,15 +714,17 @@ uint32_t dev_row_mask() {
 #endif
 }
 
-uint32_t tiles_per_cta() {
+// Tiles per scheduler chunk (= the longest run whose per-thread CRC state is carried): 2 keeps the output streams of the
+// normalise + one-hot pass balanced; the CRC-only and raw passes amortise the per-run alignment multiply over 8.
+uint32_t tiles_per_cta(int mode) {
     static int q = -1;
     if (q < 0) {
         const char* e = getenv("B2_PARSE_TILES_PER_CTA");
-        q = e ? atoi(e) : 2;
-        if (q < 1) q = 1;
+        q = e ? atoi(e) : 0;
+        if (q < 0) q = 0;
         if (q > 64) q = 64;
     }
-    return (uint32_t)q;
+    return q ? (uint32_t)q : (mode == B2_SINK_NORM_ONEHOT ? 2u : 8u);
 }
 
 }  // namespace
@@ -740,7 +749,7 @@ extern "C" int b2_tfrecord_parse(b2_ctx* ctx, const uint8_t* shard, uint64_t nby
     B2_CUDA(cudaMemsetAsync(ctx->ws, 0, (size_t)n * 8 + 8, s));
     uint32_t* acc = static_cast<uint32_t*>(ctx->ws);
     ParseArgs pa{shard, nbytes, rec_off, rec_len, index, *sink, ctx->crc_dev, nullptr, nullptr, nullptr,
-                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(), reinterpret_cast<unsigned long long*>(acc), status, nullptr, nullptr, acc + 2 * (size_t)n, nullptr, ~0u};
+                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(sink->mode), reinterpret_cast<unsigned long long*>(acc), status, nullptr, nullptr, acc + 2 * (size_t)n, nullptr, ~0u};
     return launch_fused(ctx, pa, tx * (uint64_t)n, s);
 }
 
@@ -754,7 +763,7 @@ extern "C" int b2_tfrecord_parse_table(b2_ctx* ctx, const uint8_t* shard, uint64
     DeviceGuard g(ctx->device);
     const TableView v = table_view(table, nbytes, max_records);
     ParseArgs pa{shard, nbytes, v.rec_off, v.rec_len, v.index, *sink, ctx->crc_dev, v.tile2rec, v.tile_start, v.hdr,
-                 0, 0, tiles_per_cta(), v.acc, status, nullptr, v.hdr + 4, reinterpret_cast<uint32_t*>(v.hdr + 5),
+                 0, 0, tiles_per_cta(sink->mode), v.acc, status, nullptr, v.hdr + 4, reinterpret_cast<uint32_t*>(v.hdr + 5),
                  getenv("B2_PARSE_PROFILE") ? ctx->prof_dev : nullptr, dev_row_mask()};
     return launch_fused(ctx, pa, v.cap_tiles, static_cast<cudaStream_t>(stream));
 }
@@ -778,7 +787,7 @@ extern "C" int b2_crc32c(b2_ctx* ctx, const uint8_t* data, const uint64_t* offse
     sink.mode = B2_SINK_NONE;
     sink.verify_crc = 1;
     ParseArgs pa{data, ~0ull, offsets, lens, nullptr, sink, ctx->crc_dev, nullptr, nullptr, nullptr,
-                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(), reinterpret_cast<unsigned long long*>(acc), nullptr, crc_out, nullptr, acc + 2 * (size_t)n, nullptr, ~0u};
+                 (uint32_t)tx, (uint32_t)n, tiles_per_cta(B2_SINK_NONE), reinterpret_cast<unsigned long long*>(acc), nullptr, crc_out, nullptr, acc + 2 * (size_t)n, nullptr, ~0u};
     return launch_fused(ctx, pa, tx * (uint64_t)n, s);
 }
 
