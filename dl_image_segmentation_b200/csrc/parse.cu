@@ -32,6 +32,9 @@
 
 #include "tfrecord_common.cuh"
 
+#ifndef B2_WAIT_HINT_NS
+#define B2_WAIT_HINT_NS 4000u
+#endif
 #ifndef B2_STAGES
 #define B2_STAGES 2
 #endif
@@ -72,8 +75,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"     // %2: suspend-time hint (ns): sleep, do not spin
+        "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(smem_addr(bar)), "r"(parity), "r"(B2_WAIT_HINT_NS) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
