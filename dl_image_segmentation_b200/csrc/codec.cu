@@ -791,49 +791,68 @@ png_unfilter_kernel(uint8_t* __restrict__ scratch, const b2_image_desc* __restri
     const int src_ch = im.png_converted ? (ct == 0 || ct == 3 ? 1 : (ct == 2 ? 3 : (ct == 4 ? 2 : 4))) : im.samples;
     const int bpp = max(1, src_ch * depth / 8), h = im.height;
     const size_t rb = ((size_t)im.width * src_ch * depth + 7) / 8;
-    const int w = (int)(rb / bpp);                                       // filter units per row
     const uint8_t* src = scratch + im.scratch_off;
     uint8_t* unf = scratch + im.scratch_off + ((im.block_bytes + 15) & ~(uint64_t)15);
     uint8_t* dst = im.png_converted ? unf : out + im.out_off;
     bool bad = false;
-    for (int band = 0; band < h; band += 32) {
-        const int row = band + lane;
-        const bool live = row < h;
-        const uint8_t* srow = src + (size_t)(live ? row : 0) * (rb + 1);
-        const int ft = live ? srow[0] : 0;
-        if (live && ft > 4) bad = true;
-        uint32_t left[8] = {0, 0, 0, 0, 0, 0, 0, 0}, upl[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cur[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const uint8_t* prow = (band > 0) ? dst + (size_t)(band - 1) * rb : nullptr;  // row above the band (lane 0)
-        for (int step = 0; step < w + 31; step++) {
-            const int x = step - lane;
-            const bool act = live && x >= 0 && x < w;
+    // One pass for a progressive image; the seven Adam7 passes otherwise (each a reduced image, un-filtered against
+    // its own previous row and written straight to its pixels' places: row stride dy rows, pixel stride dx pixels).
+    const bool adam7 = (im.png_flags & 0x100) != 0;
+    const int full_w = (int)(rb / bpp);
+    for (int pass = 0; pass < (adam7 ? 7 : 1); pass++) {
+        int x0 = 0, y0 = 0, dx = 1, dy = 1;
+        if (adam7) {
+            x0 = (0x0402010 >> (4 * (6 - pass))) & 15;                    // 0 4 0 2 0 1 0
+            y0 = (0x0040201 >> (4 * (6 - pass))) & 15;                    // 0 0 4 0 2 0 1
+            dx = (0x8844221 >> (4 * (6 - pass))) & 15;                    // 8 8 4 4 2 2 1
+            dy = (0x8884422 >> (4 * (6 - pass))) & 15;                    // 8 8 8 4 4 2 2
+        }
+        const int w = full_w > x0 ? (full_w - x0 + dx - 1) / dx : 0;      // filter units per row of this pass
+        const int ph = h > y0 ? (h - y0 + dy - 1) / dy : 0;
+        if (w == 0 || ph == 0) continue;
+        const size_t prb = (size_t)w * bpp;                               // bytes per row of this pass
+        uint8_t* pdst = dst + (size_t)y0 * rb + (size_t)x0 * bpp;
+        const size_t row_stride = (size_t)dy * rb, px_stride = (size_t)dx * bpp;
+        for (int band = 0; band < ph; band += 32) {
+            const int row = band + lane;
+            const bool live = row < ph;
+            const uint8_t* srow = src + (size_t)(live ? row : 0) * (prb + 1);
+            const int ft = live ? srow[0] : 0;
+            if (live && ft > 4) bad = true;
+            uint32_t left[8] = {0, 0, 0, 0, 0, 0, 0, 0}, upl[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cur[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const uint8_t* prow = (band > 0) ? pdst + (size_t)(band - 1) * row_stride : nullptr;  // row above the band (lane 0)
+            for (int step = 0; step < w + 31; step++) {
+                const int x = step - lane;
+                const bool act = live && x >= 0 && x < w;
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                if (c >= bpp) break;
-                uint32_t up = __shfl_up_sync(0xffffffffu, cur[c], 1);     // lane L-1's pixel x (computed last step)
-                if (lane == 0) up = (prow && x >= 0 && x < w) ? prow[(size_t)x * bpp + c] : 0;
-                if (act) {
-                    const uint32_t raw = srow[1 + (size_t)x * bpp + c];
-                    const uint32_t a = left[c], b = up, cc = upl[c];
-                    uint32_t pred;
-                    if (ft == 0) pred = 0;
-                    else if (ft == 1) pred = a;
-                    else if (ft == 2) pred = b;
-                    else if (ft == 3) pred = (a + b) >> 1;
-                    else {
-                        const int p = (int)a + (int)b - (int)cc;
-                        const int pa = abs(p - (int)a), pb = abs(p - (int)b), pc = abs(p - (int)cc);
-                        pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : cc);
+                for (int c = 0; c < 8; c++) {
+                    if (c >= bpp) break;
+                    uint32_t up = __shfl_up_sync(0xffffffffu, cur[c], 1);     // lane L-1's pixel x (computed last step)
+                    if (lane == 0) up = (prow && x >= 0 && x < w) ? prow[(size_t)x * px_stride + c] : 0;
+                    if (act) {
+                        const uint32_t raw = srow[1 + (size_t)x * bpp + c];
+                        const uint32_t a = left[c], b = up, cc = upl[c];
+                        uint32_t pred;
+                        if (ft == 0) pred = 0;
+                        else if (ft == 1) pred = a;
+                        else if (ft == 2) pred = b;
+                        else if (ft == 3) pred = (a + b) >> 1;
+                        else {
+                            const int p = (int)a + (int)b - (int)cc;
+                            const int pa = abs(p - (int)a), pb = abs(p - (int)b), pc = abs(p - (int)cc);
+                            pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : cc);
+                        }
+                        const uint32_t v = (raw + pred) & 0xFFu;
+                        pdst[(size_t)row * row_stride + (size_t)x * px_stride + c] = (uint8_t)v;
+                        left[c] = v;
+                        upl[c] = b;
+                        cur[c] = v;
                     }
-                    const uint32_t v = (raw + pred) & 0xFFu;
-                    dst[(size_t)row * rb + (size_t)x * bpp + c] = (uint8_t)v;
-                    left[c] = v;
-                    upl[c] = b;
-                    cur[c] = v;
                 }
             }
+            __syncwarp();
         }
-        __syncwarp();
+        src += (size_t)ph * (prb + 1);
     }
     if (__ballot_sync(0xffffffffu, bad)) {
         if (lane == 0) set_status(status, wi, 41);
@@ -1220,6 +1239,7 @@ int tiff_dtype(uint32_t bps, uint32_t fmt) {
     return -1;
 }
 const uint8_t kPngSig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+const int kAdam7[7][4] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};   // x0, y0, dx, dy
 
 // CRC-32 (IEEE 802.3, the PNG chunk CRC), slice-by-8.  libpng treats a CRC mismatch in a critical chunk (IHDR, IDAT)
 // as a fatal error, so tf.image.decode_png / GDAL fail on such a file and the reference skips it: so do we.
@@ -1267,7 +1287,7 @@ extern "C" int b2_image_probe(const uint8_t* blob, uint64_t size, uint32_t flags
     if (size >= 8 && memcmp(blob, kPngSig, 8) == 0) {
         info->format = 2;
         uint64_t p = 8;
-        bool ihdr = false, plte = false, trns = false;
+        bool ihdr = false, plte = false, trns = false, interlaced = false;
         int n_idat = 0, src_ch = 0, depth = 0, ct = 0;
         while (p + 8 <= size) {
             const uint64_t n = ((uint64_t)blob[p] << 24) | (blob[p + 1] << 16) | (blob[p + 2] << 8) | blob[p + 3];
@@ -1281,7 +1301,8 @@ extern "C" int b2_image_probe(const uint8_t* blob, uint64_t size, uint32_t flags
                 const int inter = d[12];
                 src_ch = ct == 0 ? 1 : (ct == 2 ? 3 : (ct == 3 ? 1 : (ct == 4 ? 2 : (ct == 6 ? 4 : 0))));
                 bool ok = src_ch != 0 && (depth == 8 || (depth == 16 && ct != 3) || ((depth == 1 || depth == 2 || depth == 4) && (ct == 0 || ct == 3)));
-                if (!ok || inter != 0) info->status = 3;
+                if (!ok || inter > 1 || (inter == 1 && depth < 8)) info->status = 3;
+                interlaced = inter == 1;
                 if (!png_chunk_crc_ok(blob, p, n)) { info->status = 2; return 0; }
                 ihdr = true;
             } else if (memcmp(blob + p + 4, "PLTE", 4) == 0 && n_idat == 0) {
@@ -1316,6 +1337,18 @@ extern "C" int b2_image_probe(const uint8_t* blob, uint64_t size, uint32_t flags
         info->compression = 8;
         const uint64_t rb = ((uint64_t)info->width * src_ch * (depth ? depth : 8) + 7) / 8;
         info->block_bytes = (uint64_t)info->height * (rb + 1);
+        if (interlaced) {                      // Adam7: seven reduced images, each row with its own filter byte
+            const uint64_t bpp = (uint64_t)src_ch * depth / 8;
+            uint64_t total = 0;
+            for (int p7 = 0; p7 < 7; p7++) {
+                const int x0 = kAdam7[p7][0], y0 = kAdam7[p7][1], dx = kAdam7[p7][2], dy = kAdam7[p7][3];
+                const uint64_t wp = info->width > x0 ? (uint64_t)(info->width - x0 + dx - 1) / dx : 0;
+                const uint64_t hp = info->height > y0 ? (uint64_t)(info->height - y0 + dy - 1) / dy : 0;
+                if (wp && hp) total += hp * (wp * bpp + 1);
+            }
+            info->block_bytes = total;
+            info->tiled = 1;                   // PNG: marks Adam7 for the planner (the field is otherwise TIFF-only)
+        }
         info->geotransform[1] = 1;
         info->geotransform[5] = 1;
         if (n_idat == 0 && info->status == 0) info->status = 2;
@@ -1468,7 +1501,8 @@ void fill_image(const uint8_t* blob, uint64_t size, int i, const b2_image_info& 
             }
             b2_stream_desc& ps = streams[pl.stream0 + 1];
             ps.src_off = (uint64_t)(pal - stage);
-            ps.dst_off = pl.scratch_off + up_to(info.block_bytes, 16) + up_to(info.block_bytes - (uint64_t)info.height, 16);
+            ps.dst_off = pl.scratch_off + up_to(info.block_bytes, 16) +
+                         up_to((uint64_t)info.height * (((uint64_t)info.width * info.png_bit_depth + 7) / 8), 16);   // palette: 1 sample
             ps.src_len = ps.dst_len = 1024;
             ps.codec = CODEC_RAW;
             ps.image = i;
@@ -1519,12 +1553,13 @@ extern "C" int b2_decode_plan_batch(const uint8_t* const* blobs, const uint64_t*
         if (info.format == 2) {
             im.png_bit_depth = info.png_bit_depth;
             im.png_color_type = info.png_color_type;
-            im.png_flags = (int32_t)flags;
+            im.png_flags = (int32_t)flags | (info.tiled ? 0x100 : 0);           // bit 8: Adam7
             im.png_converted = info.png_bit_depth != 8 || info.png_color_type == 3;
             n_streams += 1;
             stage_pos += sizes[i];                       // upper bound of the IDAT payload bytes
             if (im.png_converted) {                      // + un-filtered bytes + palette (see b2_image_desc)
-                const uint64_t unf = info.block_bytes - (uint64_t)info.height;
+                const int sc = info.png_color_type == 2 ? 3 : (info.png_color_type == 4 ? 2 : (info.png_color_type == 6 ? 4 : 1));
+                const uint64_t unf = (uint64_t)info.height * (((uint64_t)info.width * sc * info.png_bit_depth + 7) / 8);
                 scratch_pos += up_to(up_to(info.block_bytes, 16) + up_to(unf, 16) + 1024, 256);
                 if (info.png_color_type == 3) {
                     n_streams += 1;                      // the palette travels as a stored stream

@@ -223,7 +223,8 @@ typedef struct {
  *                  16-bit samples -> their high byte;
  *   0              rasterio / GDAL's PNG driver (_img_to_tf_mp.py:45-48): palette -> one band of indices,
  *                  1/2/4-bit grey unscaled, 16-bit samples -> uint16.
- * 8-bit grey, grey+alpha, RGB and RGBA are the same in both.  Interlaced PNGs are out of scope (status 3). */
+ * 8-bit grey, grey+alpha, RGB and RGBA are the same in both.  Adam7-interlaced files are decoded for bit depths 8 and
+ * 16; interlaced 1/2/4-bit files are out of scope (status 3). */
 #define B2_PNG_AS_TF 1u
 
 /* Host-side header parse (TIFF IFD / PNG chunks); never touches the GPU. */

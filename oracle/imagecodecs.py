@@ -197,23 +197,39 @@ def decode_png(blob: bytes, as_tf: bool = True) -> np.ndarray:
     depth, ct = t["depth"], t["color_type"]
     ch = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}.get(ct)
     ok = ch is not None and (depth == 8 or (depth == 16 and ct != 3) or (depth in (1, 2, 4) and ct in (0, 3)))
-    if not ok or t["interlace"]:
+    if not ok or t["interlace"] > 1 or (t["interlace"] == 1 and depth < 8):
         raise DecodeError("PNG flavour out of scope (depth %d, colour type %d, interlace %d)" % (depth, ct, t["interlace"]))
     if ct == 3 and t["plte"] is None:
         raise DecodeError("palette image without PLTE")
     h, w = t["height"], t["width"]
     rb = (w * ch * depth + 7) // 8
+    bpp = max(1, ch * depth // 8)
     try:
         raw = zlib.decompress(t["idat"])
     except zlib.error as e:
         raise DecodeError(str(e))
-    if len(raw) < h * (rb + 1):
-        raise DecodeError("short PNG stream")
-    src = np.frombuffer(raw, dtype=np.uint8, count=h * (rb + 1))
-    dst = np.zeros(h * rb, dtype=np.uint8)
-    if clib().orc_png_unfilter(src.ctypes.data, dst.ctypes.data, h, rb, max(1, ch * depth // 8)) != 0:
-        raise DecodeError("bad PNG filter type")
-    rows = dst.reshape(h, rb)
+
+    def unfilter(buf, off, hh, rbb):
+        if len(buf) < off + hh * (rbb + 1):
+            raise DecodeError("short PNG stream")
+        src = np.frombuffer(buf, dtype=np.uint8, count=hh * (rbb + 1), offset=off)
+        dst = np.zeros(hh * rbb, dtype=np.uint8)
+        if clib().orc_png_unfilter(src.ctypes.data, dst.ctypes.data, hh, rbb, bpp) != 0:
+            raise DecodeError("bad PNG filter type")
+        return dst.reshape(hh, rbb)
+    if t["interlace"]:
+        # Adam7 (PNG spec section 8.2): seven reduced images, each with its own filtered scanlines, depth >= 8 here
+        rows = np.zeros((h, w, bpp), np.uint8)
+        off = 0
+        for x0, y0, dx, dy in ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)):
+            wp, hp = (w - x0 + dx - 1) // dx if w > x0 else 0, (h - y0 + dy - 1) // dy if h > y0 else 0
+            if wp == 0 or hp == 0:
+                continue
+            rows[y0::dy, x0::dx] = unfilter(raw, off, hp, wp * bpp).reshape(hp, wp, bpp)
+            off += hp * (wp * bpp + 1)
+        rows = rows.reshape(h, rb)
+    else:
+        rows = unfilter(raw, 0, h, rb)
     if depth == 8 and ct != 3:
         return rows.reshape(h, w, ch)
     if depth == 16:

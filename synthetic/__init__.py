@@ -239,23 +239,36 @@ def png_bytes_manual(arr, filter_types=(0, 1, 2, 3, 4), zlevel=6, idat_chunk=Non
     return body + _png_chunk(b"IEND", b"")
 
 
-def png_bytes_flavour(samples, depth, ctype, palette=None, trns=None, filter_types=(0, 1, 2, 3, 4), zlevel=6):
-    """PNG of any non-interlaced flavour.  samples: (H,W) or (H,W,C) integers < 2**depth (palette indices for
-    colour type 3); depth 1/2/4 packs them most-significant-bits first, depth 16 stores them big-endian."""
+ADAM7 = ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2))   # x0, y0, dx, dy
+
+
+def png_bytes_flavour(samples, depth, ctype, palette=None, trns=None, filter_types=(0, 1, 2, 3, 4), zlevel=6, interlace=False):
+    """PNG of any flavour.  samples: (H,W) or (H,W,C) integers < 2**depth (palette indices for colour type 3);
+    depth 1/2/4 packs them most-significant-bits first, depth 16 stores them big-endian; interlace=True writes the
+    seven Adam7 passes (each a reduced image with its own filtered scanlines)."""
     a = np.asarray(samples)
     if a.ndim == 2:
         a = a[:, :, None]
     H, W, C = a.shape
     assert C == {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[ctype]
-    if depth == 16:
-        rows = a.astype(">u2").view(np.uint8).reshape(H, W, 2 * C)
-    elif depth == 8:
-        rows = a.astype(np.uint8)
+
+    def scanlines(sub):
+        if sub.shape[0] == 0 or sub.shape[1] == 0:
+            return b""
+        if depth == 16:
+            rows = sub.astype(">u2").view(np.uint8).reshape(sub.shape[0], sub.shape[1], 2 * C)
+        elif depth == 8:
+            rows = sub.astype(np.uint8)
+        else:
+            bits = ((sub[:, :, 0].astype(np.uint8)[:, :, None] >> np.arange(depth - 1, -1, -1)) & 1).reshape(sub.shape[0], -1)
+            rows = np.packbits(bits, axis=1)[:, :, None]                  # (h, ceil(w*depth/8), 1): filter unit = 1 byte
+        return bytes(png_filter_rows(rows, filter_types))
+    if interlace:
+        raw = b"".join(scanlines(a[y0::dy, x0::dx]) for x0, y0, dx, dy in ADAM7)
     else:
-        bits = ((a[:, :, 0].astype(np.uint8)[:, :, None] >> np.arange(depth - 1, -1, -1)) & 1).reshape(H, W * depth)
-        rows = np.packbits(bits, axis=1)[:, :, None]                      # (H, ceil(W*depth/8), 1): filter unit = 1 byte
-    z = zlib.compress(png_filter_rows(rows, filter_types), zlevel)
-    body = b"\x89PNG\r\n\x1a\n" + _png_chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, depth, ctype, 0, 0, 0))
+        raw = scanlines(a)
+    z = zlib.compress(raw, zlevel)
+    body = b"\x89PNG\r\n\x1a\n" + _png_chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, depth, ctype, 0, 0, 1 if interlace else 0))
     if palette is not None:
         body += _png_chunk(b"PLTE", np.asarray(palette, np.uint8).reshape(-1, 3).tobytes())
     if trns is not None:

@@ -133,11 +133,18 @@ def test_png_palette_subbyte_and_16bit_flavours(dev, as_tf):
         assert (info.height, info.width, info.samples) == w.shape
         p = _codec.probe(blobs[0], png_as_tf=as_tf)
         assert (p.height, p.width, p.samples, p.png_bit_depth, p.png_color_type) == (64, 64, 3, 8, 2)
-    # interlaced PNGs stay out of scope: flagged, not mis-decoded
-    inter = bytearray(blobs[0])
-    inter[8 + 8 + 12] = 1
-    inter[8 + 8 + 13:8 + 8 + 17] = zlib.crc32(bytes(inter[12:8 + 8 + 13])).to_bytes(4, "big")
-    assert _codec.probe(bytes(inter), png_as_tf=as_tf).status == 3
+    # Adam7 files of awkward geometries (empty passes) in one batch; sub-byte interlaced stays out of scope (flagged)
+    from test_oracle_golden import _png_interlaced_cases
+    inter = _png_interlaced_cases()
+    blobs = [b for _, b, _, _, _ in inter]
+    arrays, status = _codec.decode_blobs(blobs, device=dev, png_as_tf=as_tf)
+    assert not np.asarray(status).any(), list(status)
+    for (name, b, _, _, _), a in zip(inter, arrays):
+        w = oic.decode_png(b, as_tf)
+        g = a.cpu().numpy() if a.dtype != torch.uint16 else a.view(torch.int16).cpu().numpy().view(np.uint16)
+        assert g.dtype == w.dtype and g.shape == w.shape, name
+        np.testing.assert_array_equal(g, w, err_msg=name)
+    assert _codec.probe(syn.png_bytes_flavour(np.zeros((5, 5), np.uint8), 4, 0, interlace=True), png_as_tf=as_tf).status == 3
 
 
 def test_error_behaviour_of_zlib_and_libpng_is_mirrored(dev):

@@ -148,6 +148,41 @@ def _png_flavour_cases():
     return cases
 
 
+def _png_interlaced_cases():
+    """Adam7 files (name, blob, samples as written) of several geometries, including ones where passes are empty."""
+    rng = np.random.default_rng(78)
+    cases = []
+    pal = rng.integers(0, 256, (256, 3), dtype=np.uint8)
+    for (H, W) in ((37, 53), (1, 1), (3, 2), (8, 8), (9, 5), (64, 64)):
+        for ct, C, depth in ((2, 3, 8), (0, 1, 8), (6, 4, 8), (4, 2, 8), (3, 1, 8), (2, 3, 16), (0, 1, 16)):
+            a = rng.integers(0, 1 << depth, (H, W, C))
+            cases.append(("adam7 %dx%d ct%d/%d" % (H, W, ct, depth),
+                          syn.png_bytes_flavour(a, depth, ct, palette=pal if ct == 3 else None, interlace=True), a, ct, depth))
+    return cases
+
+
+def test_png_adam7_against_pillow():
+    from PIL import Image
+    for name, blob, a, ct, depth in _png_interlaced_cases():
+        got = oic.decode_png(blob, True)
+        im = Image.open(io.BytesIO(blob))
+        im.load()
+        if ct == 3:
+            want = np.asarray(im.convert("RGB"))
+        elif depth == 16 and ct == 0:
+            want = (np.asarray(im).astype(np.uint16) >> 8).astype(np.uint8)[..., None]
+        else:
+            want = np.asarray(im)
+            want = want[..., None] if want.ndim == 2 else want
+        assert got.shape == want.shape and np.array_equal(got, want), name
+        if depth == 16:
+            assert np.array_equal(oic.decode_png(blob, False), a.astype(np.uint16)), name
+        elif ct != 3:
+            assert np.array_equal(oic.decode_png(blob, False), a.astype(np.uint8)), name
+    with pytest.raises(oic.DecodeError):                                  # sub-byte interlaced stays out of scope
+        oic.decode_png(syn.png_bytes_flavour(np.zeros((5, 5), np.uint8), 4, 0, interlace=True))
+
+
 def test_png_flavours_against_pillow_and_libpng():
     """Palette, 1/2/4-bit and 16-bit PNGs under both presentations: tf.image.decode_png's libpng transforms (checked
     against Pillow's, which applies the same expansions, and OpenCV's libpng for palettes) and GDAL's raw view
