@@ -52,11 +52,9 @@ def _process_image_files_mp(name, img_files, lbl_files, out_folder, num_shards, 
                             store_as_array):
     assert len(img_files) == len(lbl_files)
     ranges = _translate.worker_ranges(len(img_files), num_proc)
-    res = []
-    for proc_idx, dev in _translate.my_workers(len(ranges)):
-        res.append(_process_image_files_mp_worker(proc_idx, ranges, name, img_files, lbl_files, out_folder, num_shards,
-                                                  dltile_from_filename, store_as_array, device=dev))
-    return res
+    # joblib.Parallel(n_jobs=num_proc) over processes in the reference (:180); here one GPU per worker, concurrently
+    return _translate.run_workers(len(ranges), lambda proc_idx, dev: _process_image_files_mp_worker(
+        proc_idx, ranges, name, img_files, lbl_files, out_folder, num_shards, dltile_from_filename, store_as_array, device=dev))
 
 
 def _find_image_files(data_dir, file_ext):

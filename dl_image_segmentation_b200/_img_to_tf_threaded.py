@@ -91,9 +91,9 @@ def _process_image_files(name, img_files, lbl_files, out_folder, num_shards, num
     print("Launching %d threads for spacings: %s" % (num_threads, ranges))
     sys.stdout.flush()
     coder = ImageCoder()
-    for thread_index, dev in _translate.my_workers(len(ranges)):
-        _process_image_files_worker(coder, thread_index, ranges, name, img_files, lbl_files, out_folder, num_shards,
-                                    dltile_from_filename, png_to_jpg, store_as_array, device=dev)
+    _translate.run_workers(len(ranges), lambda thread_index, dev: _process_image_files_worker(
+        coder, thread_index, ranges, name, img_files, lbl_files, out_folder, num_shards, dltile_from_filename, png_to_jpg,
+        store_as_array, device=dev))
     print("%s: Finished writing all %d images in data set." % (datetime.now(), len(img_files)))
     sys.stdout.flush()
 

@@ -7,6 +7,7 @@ Kept from the reference: shard sub-ranges ``np.linspace(lo, hi, S/P + 1).astype(
 ``'%s-%.5d-of-%.5d'`` (``:115``), records in list order, skip-and-continue on any per-chip failure with the same
 messages (``:133-136``), key equality check (``:132``), progress / summary prints (``:145-157``).
 """
+import ctypes
 import os
 import sys
 from datetime import datetime
@@ -15,7 +16,8 @@ import numpy as np
 import torch
 
 from . import _codec, ops
-from ._lib import get_ctx
+from . import _lib as _lib_mod
+from ._lib import check, get_ctx, lib
 
 
 def tile_key_from_path(path, parse_dltile_filename=True):
@@ -37,6 +39,50 @@ def _read(path):
 
 class ChipError(Exception):
     pass
+
+
+_vp, _i, _u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
+_lib_mod.register_signatures({
+    "b2_read_files": (_i, [_vp, _i, _vp, _u64, _vp, _vp, _vp, _i, _vp]),
+})
+
+
+class FileBatchReader:
+    """Reads whole batches of files with ONE native, multi-threaded call (b2_read_files) into a reusable host buffer:
+    the per-file open().read() of the reference's worker loop costs the interpreter ~30 us a file, which is what bounds
+    the translators once decode and serialisation run on the GPU.  read() returns one uint8 array view per file (or the
+    OSError the reference's except branch would have caught); a view stays valid until `depth` more batches were read."""
+
+    def __init__(self, depth=3, threads=0):
+        self.bufs = [np.empty(0, np.uint8) for _ in range(depth)]
+        self.k = 0
+        self.threads = int(threads)
+
+    def read(self, paths):
+        n = len(paths)
+        if n == 0:
+            return []
+        enc = [os.fsencode(p) for p in paths]
+        arr = (ctypes.c_char_p * n)(*enc)
+        offs, sizes = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        status = np.zeros(n, np.int32)
+        need = ctypes.c_uint64(0)
+        slot = self.k % len(self.bufs)
+        self.k += 1
+        buf = self.bufs[slot]
+        for _ in range(2):
+            check(lib().b2_read_files(arr, n, buf.ctypes.data if buf.size else None, buf.size, offs.ctypes.data, sizes.ctypes.data,
+                                      status.ctypes.data, self.threads, ctypes.byref(need)))
+            if buf.size >= need.value and buf.size:
+                break
+            buf = self.bufs[slot] = np.empty(int(need.value * 1.25) + 4096, np.uint8)
+        out = []
+        for i in range(n):
+            if status[i]:
+                out.append(OSError(int(status[i]), os.strerror(int(status[i])), paths[i]))
+            else:
+                out.append(buf[int(offs[i]):int(offs[i]) + int(sizes[i])])
+        return out
 
 
 def _read_or_error(path):
@@ -66,7 +112,7 @@ def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, devi
     if store_as_array:                                                      # ONE native planning call + the decode kernels
         arrays, st, infos = _codec.decode_blobs(blobs, device=ctx.device, want_infos=True, png_as_tf=png_as_tf)
         for k in range(2 * n):
-            if blobs[k] and infos[k].status == 0 and st[k] != 0 and errs[k // 2] is None:
+            if len(blobs[k]) and infos[k].status == 0 and st[k] != 0 and errs[k // 2] is None:
                 errs[k // 2] = ChipError("could not decode %s (codec status %d)" % ((img_paths, lbl_paths)[k % 2][k // 2], int(st[k])))
     else:
         infos = _codec.probe_blobs(blobs, png_as_tf=png_as_tf)
@@ -78,7 +124,7 @@ def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, devi
         ii, li = infos[2 * i], infos[2 * i + 1]
         try:
             for info, p, b in ((ii, img_paths[i], blobs[2 * i]), (li, lbl_paths[i], blobs[2 * i + 1])):
-                if not b or info.status != 0:
+                if not len(b) or info.status != 0:
                     raise ChipError("'%s' not recognized as a supported file format." % p)
             if validate is not None:
                 validate(ii)
@@ -135,15 +181,17 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
     seq = 0
     with ThreadPoolExecutor(max_workers=max(1, io_threads)) as pool, ThreadPoolExecutor(max_workers=1) as writer, \
             ThreadPoolExecutor(max_workers=8) as wpool:
+        reader = FileBatchReader(depth=3, threads=io_threads)
+
         def submit_reads(rng):
             paths = []
             for i in range(*rng):
                 paths += [img_filenames[i], lbl_filenames[i]]
-            return [pool.submit(_read_or_error, p) for p in paths]
-        pending_reads = submit_reads(batches[0]) if batches else []
+            return pool.submit(reader.read, paths)                          # one native call; the GIL is free meanwhile
+        pending_reads = submit_reads(batches[0]) if batches else None
         for bi, (b0, b1) in enumerate(batches):
-            blobs = [f.result() for f in pending_reads]
-            pending_reads = submit_reads(batches[bi + 1]) if bi + 1 < len(batches) else []
+            blobs = pending_reads.result()
+            pending_reads = submit_reads(batches[bi + 1]) if bi + 1 < len(batches) else None
             idx = list(range(b0, b1))
             pairs = load_pairs([img_filenames[i] for i in idx], [lbl_filenames[i] for i in idx], store_as_array,
                                key_fn, validate, ctx.device, blobs=blobs, png_as_tf=png_as_tf)
@@ -199,6 +247,34 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
     print("%s [%s %d]: Wrote %d images to %d shards." % (datetime.now(), label, worker_index, counter, per))
     sys.stdout.flush()
     return counter
+
+
+def run_workers(num_workers, fn):
+    """Run fn(worker_index, device) for every worker this OS process owns.  Workers on different GPUs run
+    concurrently, one host thread per GPU (the C ABI's rule is one context = one device = one thread at a time;
+    the decode / serialise work is native or on the device, so the threads do not fight over the GIL); workers
+    that share a GPU run one after the other on that GPU's thread.  Results come back in worker order."""
+    mine = my_workers(num_workers)
+    by_dev = {}
+    for p, dev in mine:
+        by_dev.setdefault(dev, []).append(p)
+    results = {}
+
+    def on_device(dev):
+        torch.cuda.set_device(dev)
+        for p in by_dev[dev]:
+            results[p] = fn(p, dev)
+    if len(by_dev) <= 1:
+        for dev in by_dev:
+            on_device(dev)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        for dev in by_dev:
+            get_ctx(dev)                                                   # contexts are created on the calling thread
+        with ThreadPoolExecutor(max_workers=len(by_dev)) as pool:
+            for f in [pool.submit(on_device, dev) for dev in by_dev]:
+                f.result()
+    return [results[p] for p, _ in mine]
 
 
 def my_workers(num_workers):

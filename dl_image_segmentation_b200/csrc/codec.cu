@@ -1609,3 +1609,58 @@ extern "C" int b2_decode_plan_batch(const uint8_t* const* blobs, const uint64_t*
     plan->filled = 1;
     return 0;
 }
+
+// ================================================================================================ host file reader
+#include <cerrno>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+extern "C" int b2_read_files(const char* const* paths, int n, uint8_t* dst, uint64_t dst_cap, uint64_t* offsets, uint64_t* sizes,
+                             int32_t* status, int n_threads, uint64_t* needed) {
+    B2_REQUIRE(paths && offsets && sizes && status && needed, "b2_read_files: NULL argument");
+    B2_REQUIRE(n >= 0, "b2_read_files: n < 0");
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    if (nt > 32) nt = 32;
+    if (nt > n) nt = n;
+    if (nt < 1) nt = 1;
+    auto fan = [&](auto&& body) {
+        if (nt == 1) { body(0); return; }
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back(body, t);
+        for (auto& x : th) x.join();
+    };
+    fan([&](int t) {                                     // sizes
+        for (int i = t; i < n; i += nt) {
+            struct stat sb;
+            status[i] = 0;
+            sizes[i] = 0;
+            if (!paths[i] || stat(paths[i], &sb) != 0) status[i] = paths[i] ? errno : EINVAL;
+            else if (!S_ISREG(sb.st_mode)) status[i] = S_ISDIR(sb.st_mode) ? EISDIR : EINVAL;
+            else sizes[i] = (uint64_t)sb.st_size;
+        }
+    });
+    uint64_t pos = 0;
+    for (int i = 0; i < n; i++) {
+        offsets[i] = pos;
+        pos += (sizes[i] + 15) & ~15ull;
+    }
+    *needed = pos;
+    if (!dst || dst_cap < pos) return 0;
+    fan([&](int t) {                                     // contents
+        for (int i = t; i < n; i += nt) {
+            if (status[i] != 0 || sizes[i] == 0) continue;
+            const int fd = open(paths[i], O_RDONLY | O_CLOEXEC);
+            if (fd < 0) { status[i] = errno; continue; }
+            uint64_t got = 0;
+            while (got < sizes[i]) {
+                const ssize_t r = pread(fd, dst + offsets[i] + got, sizes[i] - got, (off_t)got);
+                if (r < 0 && errno == EINTR) continue;
+                if (r <= 0) { status[i] = r < 0 ? errno : EIO; break; }     // short file: it changed under us
+                got += (uint64_t)r;
+            }
+            close(fd);
+        }
+    });
+    return 0;
+}

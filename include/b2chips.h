@@ -272,6 +272,15 @@ int b2_decode_plan_batch(const uint8_t* const* blobs, const uint64_t* sizes, int
                          int32_t* status_out, b2_image_desc* images_out, b2_stream_desc* streams_out, int streams_cap,
                          uint8_t* stage_host, uint64_t stage_cap, int n_threads, uint32_t flags, b2_decode_plan* plan);
 
+/* Host-side, multi-threaded: read n files back to back into dst (every file starts 16-byte aligned).  Replaces the
+ * per-file open(filename,'rb').read() of the reference's worker loops (_img_to_tf_mp.py:43-44,
+ * _img_to_tf_threaded.py:87-88), which costs the Python shim ~30 us of interpreter time per file.
+ * offsets / sizes: [n], filled in both modes.  status[i] = 0, or the errno of the failing call (that chip is then
+ * skipped the way the reference's except branch does, :133-136).  *needed = bytes dst must hold.  With dst == NULL or
+ * dst_cap < *needed only the sizes are gathered (call again with a buffer).  n_threads <= 0: one per host core (<= 32). */
+int b2_read_files(const char* const* paths, int n, uint8_t* dst, uint64_t dst_cap, uint64_t* offsets, uint64_t* sizes,
+                  int32_t* status, int n_threads, uint64_t* needed);
+
 /* codec_mask: bit0 LZW, bit1 zlib, bit2 stored streams present.  status_dev (one int32 per image) must be
  * zeroed by the caller; non-zero afterwards = that image failed to decode (skip it, _img_to_tf_mp.py:133-136). */
 int b2_decode_streams(b2_ctx* ctx, const uint8_t* blob_dev, const b2_stream_desc* streams_dev, int n_streams,

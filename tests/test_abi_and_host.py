@@ -246,3 +246,27 @@ def test_georeferenced_identifier_strings(lib, tmp_path):
     assert _codec.georef_strings(info) == ("[0.0, 1.0, 0.0, 0.0, 0.0, 1.0]", "None")
     big = _codec.probe(syn.tiff_bytes(img, tile=16, big_endian=True))
     assert _codec.georef_strings(big) == ("[499980.0, 10.0, 0.0, 5300040.0, 0.0, -10.0]", "EPSG:32643")
+
+
+def test_native_batch_file_reader(tmp_path):
+    """b2_read_files (one native multi-threaded call per batch) == open(p,'rb').read() per file; unreadable files come
+    back as the OSError the reference's except branch would have caught; buffers are reused between batches."""
+    from dl_image_segmentation_b200 import _translate
+    rng = np.random.default_rng(3)
+    paths, want = [], []
+    for i, n in enumerate([0, 1, 15, 16, 17, 4096, 100003, 7]):
+        p = tmp_path / ("f%d.bin" % i)
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        p.write_bytes(data)
+        paths.append(str(p))
+        want.append(data)
+    (tmp_path / "adir").mkdir()
+    paths += [str(tmp_path / "missing.bin"), str(tmp_path / "adir")]
+    rd = _translate.FileBatchReader(depth=2, threads=3)
+    for rep in range(3):                                        # the third batch reuses the first buffer
+        got = rd.read(paths)
+        for g, w in zip(got[:len(want)], want):
+            assert isinstance(g, np.ndarray) and g.tobytes() == w
+        assert isinstance(got[-2], FileNotFoundError) and isinstance(got[-1], IsADirectoryError)
+        assert got[-2].filename == paths[-2]
+    assert rd.read([]) == []

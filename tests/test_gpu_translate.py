@@ -61,6 +61,30 @@ def test_images_to_tfrecords_mp_matches_reference_worker_loop(dev, tmp_path, kin
     assert total == want and total <= n - 1
 
 
+def test_two_gpus_in_one_process_write_the_same_shards(dev, tmp_path):
+    """the shard files do not depend on how many GPUs wrote them.  num_proc=4 workers on 2 GPUs (two
+    concurrent host threads, two workers each) vs the same call confined to one GPU vs the CPU restatement."""
+    import torch
+
+    import dl_image_segmentation_b200 as pkg
+    from dl_image_segmentation_b200 import _translate
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ext = _write_dataset(tmp_path, "png", 41, 48)
+    out2, out1, out_c = str(tmp_path / "g2"), str(tmp_path / "g1"), str(tmp_path / "c")
+    with contextlib.redirect_stdout(io.StringIO()):
+        pkg.images_to_tfrecords_mp("t", str(tmp_path), out2, 8, num_proc=4, file_ext=ext)
+        assert sorted({d for _, d in _translate.my_workers(4)}) == [0, 1]
+        real = torch.cuda.device_count
+        torch.cuda.device_count = lambda: 1                                  # same call, one GPU
+        try:
+            pkg.images_to_tfrecords_mp("t", str(tmp_path), out1, 8, num_proc=4, file_ext=ext)
+        finally:
+            torch.cuda.device_count = real
+    otr.images_to_tfrecords("t", str(tmp_path), out_c, 8, num_proc=4, file_ext=ext, n_jobs=1)
+    assert len(_same_shards(out2, out_c)) == 8 and len(_same_shards(out1, out_c)) == 8
+
+
 def test_georeferenced_identifiers_and_more_shards_than_chips(dev, tmp_path):
     """dltile_from_filename=False (identifier = name|geotransform|crs) and shards that stay empty."""
     import dl_image_segmentation_b200 as pkg

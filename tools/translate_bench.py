@@ -3,7 +3,7 @@
 TFRecord files, through the drop-in images_to_tfrecords_mp, next to the oracle restatement of the reference's
 multiprocessing CPU path (joblib over all host cores) on the same files.  Prints one JSON line per arm.
 
-    python tools/translate_bench.py [png|lzw] [n_pairs]
+    python tools/translate_bench.py [png|lzw] [n_pairs] [gpu_workers]
 """
 import json
 import os
@@ -56,6 +56,7 @@ def main():
     kind = sys.argv[1] if len(sys.argv) > 1 else "png"
     n = int(sys.argv[2]) if len(sys.argv) > 2 else (1536 if kind == "png" else 512)
     shards = 8
+    workers = int(sys.argv[3]) if len(sys.argv) > 3 else 1      # GPU workers (num_proc): one host thread per GPU in this process
     base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
     root = tempfile.mkdtemp(prefix="b2tr_", dir=base)
     try:
@@ -70,14 +71,14 @@ def main():
         import dl_image_segmentation_b200 as pkg
         out_g = os.path.join(root, "out_gpu")
         with contextlib.redirect_stdout(io.StringIO()):
-            pkg.images_to_tfrecords_mp("warm", root, os.path.join(root, "out_warm"), shards, num_proc=1, file_ext=ext)
+            pkg.images_to_tfrecords_mp("warm", root, os.path.join(root, "out_warm"), shards, num_proc=workers, file_ext=ext)
             torch.cuda.synchronize()
             t0 = time.time()
-            pkg.images_to_tfrecords_mp("bench", root, out_g, shards, num_proc=1, file_ext=ext)
+            pkg.images_to_tfrecords_mp("bench", root, out_g, shards, num_proc=workers, file_ext=ext)
             torch.cuda.synchronize()
             gpu_s = time.time() - t0
         out_bytes = sum(os.path.getsize(os.path.join(out_g, f)) for f in os.listdir(out_g))
-        print(json.dumps({"arm": "b200 (1 GPU, drop-in images_to_tfrecords_mp, files on %s)" % base, "kind": kind, "pairs": n,
+        print(json.dumps({"arm": "b200 (%d GPU worker(s) in one process, drop-in images_to_tfrecords_mp, files on %s)" % (workers, base), "kind": kind, "pairs": n,
                           "seconds": round(gpu_s, 3), "pairs_per_s": round(n / gpu_s, 1), "input_MB": round(in_bytes / 1e6, 1),
                           "output_MB": round(out_bytes / 1e6, 1), "dataset_generation_s": round(gen_s, 1)}), flush=True)
         from oracle import translate as otr
