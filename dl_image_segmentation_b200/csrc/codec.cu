@@ -905,6 +905,17 @@ __device__ __forceinline__ T load_sample(const uint8_t* p, bool swap) {
 }
 
 template <typename T>
+__device__ __forceinline__ T swap_sample(T v) {
+    if (sizeof(T) == 2) return (T)__byte_perm((uint32_t)v, 0, 0x0001);
+    if (sizeof(T) == 4) return (T)__byte_perm((uint32_t)v, 0, 0x0123);
+    return v;
+}
+
+// One warp per block row.  kSpb > 0: the row is walked in coalesced 512-byte chunks (16 bytes per lane); each lane sums
+// its samples per channel, one warp scan per channel turns the sums into running totals, and the lane rewrites its 16
+// bytes in place.  kSpb == 0 (more than 4 interleaved samples, or rows that are not 16-byte multiples): the generic walk,
+// one channel at a time with each lane owning a run of consecutive pixels.
+template <typename T, int kSpb>
 __global__ void __launch_bounds__(128)
 hdiff_undo_kernel(uint8_t* __restrict__ scratch, const b2_image_desc* __restrict__ imgs, int img_base,
                   const int32_t* __restrict__ status) {
@@ -914,6 +925,9 @@ hdiff_undo_kernel(uint8_t* __restrict__ scratch, const b2_image_desc* __restrict
     if (status && status[img_index] != 0) return;
     const int planes = im.planar == 2 ? im.samples : 1;
     const int spb = im.planar == 2 ? 1 : im.samples;
+    const bool fast_ok = spb >= 1 && spb <= 4 && (((size_t)im.block_w * spb * sizeof(T)) & 15) == 0 && (im.block_bytes & 15) == 0 &&
+                         (im.scratch_off & 15) == 0 && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0;
+    if (kSpb == 0 ? fast_ok : (!fast_ok || spb != kSpb)) return;        // exactly one instantiation handles an image
     const long long rows_total = (long long)im.blocks_across * im.blocks_down * planes * im.block_h;
     const long long wrow = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -923,6 +937,67 @@ hdiff_undo_kernel(uint8_t* __restrict__ scratch, const b2_image_desc* __restrict
     uint8_t* base = scratch + im.scratch_off + (uint64_t)blk * im.block_bytes + (uint64_t)ry * im.block_w * spb * sizeof(T);
     const bool swap = im.big_endian && sizeof(T) > 1;
     const int bw = im.block_w;
+    if (kSpb > 0) {
+        constexpr int V = 16 / (int)sizeof(T);                            // samples per lane per chunk
+        constexpr int S = kSpb > 0 ? kSpb : 1;
+        const uint32_t n_samples = (uint32_t)bw * S;
+        T carry[S];
+#pragma unroll
+        for (int c = 0; c < S; c++) carry[c] = 0;
+        for (uint32_t s0 = 0; s0 < n_samples; s0 += 32 * V) {
+            const uint32_t mine = s0 + lane * V;                           // first sample of this lane
+            const bool live = mine < n_samples;                            // rows are multiples of 16 bytes: all or nothing
+            T v[V];
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (live) q = *reinterpret_cast<const uint4*>(base + (size_t)mine * sizeof(T));
+            memcpy(v, &q, 16);
+            if (swap) {
+#pragma unroll
+                for (int j = 0; j < V; j++) v[j] = swap_sample<T>(v[j]);
+            }
+            const int ph = (int)(mine % S);                                // channel of v[0]
+            T loc[S], incl[S];
+#pragma unroll
+            for (int c = 0; c < S; c++) loc[c] = 0;
+#pragma unroll
+            for (int j = 0; j < V; j++) {
+                const int ch = (ph + j) % S;
+#pragma unroll
+                for (int c = 0; c < S; c++) if (ch == c) loc[c] += v[j];
+            }
+#pragma unroll
+            for (int c = 0; c < S; c++) {
+                T x = loc[c];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const T t = (T)__shfl_up_sync(0xffffffffu, (uint32_t)x, o);
+                    if (lane >= o) x += t;
+                }
+                incl[c] = x;
+            }
+            T run[S];
+#pragma unroll
+            for (int c = 0; c < S; c++) run[c] = (T)(carry[c] + incl[c] - loc[c]);
+#pragma unroll
+            for (int j = 0; j < V; j++) {
+                const int ch = (ph + j) % S;
+#pragma unroll
+                for (int c = 0; c < S; c++)
+                    if (ch == c) { run[c] += v[j]; v[j] = run[c]; }
+            }
+#pragma unroll
+            for (int c = 0; c < S; c++) carry[c] = (T)(carry[c] + (T)__shfl_sync(0xffffffffu, (uint32_t)incl[c], 31));
+            if (live) {
+                if (swap) {                                                // store back in FILE byte order; assemble swaps once
+#pragma unroll
+                    for (int j = 0; j < V; j++) v[j] = swap_sample<T>(v[j]);
+                }
+                memcpy(&q, v, 16);
+                *reinterpret_cast<uint4*>(base + (size_t)mine * sizeof(T)) = q;
+            }
+        }
+        return;
+    }
     const int per = (bw + 31) / 32;
     const int x0 = lane * per, x1 = min(bw, x0 + per);
     for (int c = 0; c < spb; c++) {
@@ -939,10 +1014,7 @@ hdiff_undo_kernel(uint8_t* __restrict__ scratch, const b2_image_desc* __restrict
             uint8_t* p = base + ((size_t)x * spb + c) * sizeof(T);
             run += load_sample<T>(p, swap);
             T v = run;                                             // store back in FILE byte order; assemble swaps once
-            if (swap) {
-                if (sizeof(T) == 2) v = (T)__byte_perm((uint32_t)v, 0, 0x0001);
-                else if (sizeof(T) == 4) v = (T)__byte_perm((uint32_t)v, 0, 0x0123);
-            }
+            if (swap) v = swap_sample<T>(v);
             memcpy(p, &v, sizeof(T));
         }
     }
@@ -1072,6 +1144,7 @@ extern "C" int b2_assemble_images(b2_ctx* ctx, uint8_t* scratch, const b2_image_
     bool any_png = false, any_tiff = false;
     uint64_t max_bytes = 0;
     long long max_rows[5] = {0, 0, 0, 0, 0};       // predictor-2 rows of the largest image, per sample size
+    unsigned spb_mask[5] = {0, 0, 0, 0, 0};        // interleave factors present (bit 0: images that need the generic walk)
     for (int i = 0; i < n_images; i++) {
         const b2_image_desc& im = imgs_host[i];
         if (im.format == 2) any_png = true;
@@ -1085,6 +1158,10 @@ extern "C" int b2_assemble_images(b2_ctx* ctx, uint8_t* scratch, const b2_image_
                 const int planes = im.planar == 2 ? im.samples : 1;
                 const long long rows = (long long)im.blocks_across * im.blocks_down * planes * im.block_h;
                 if (rows > max_rows[im.bytes_per_sample]) max_rows[im.bytes_per_sample] = rows;
+                const int spb = im.planar == 2 ? 1 : im.samples;
+                const bool fast = spb >= 1 && spb <= 4 && (((size_t)im.block_w * spb * im.bytes_per_sample) & 15) == 0 &&
+                                  (im.block_bytes & 15) == 0 && (im.scratch_off & 15) == 0 && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0;
+                spb_mask[im.bytes_per_sample] |= 1u << (fast ? spb : 0);
             }
         }
     }
@@ -1093,10 +1170,17 @@ extern "C" int b2_assemble_images(b2_ctx* ctx, uint8_t* scratch, const b2_image_
         const unsigned gx = (unsigned)((max_rows[bs] * 32 + 127) / 128);
         for (int s0 = 0; s0 < n_images; s0 += 65535) {
             const int m = n_images - s0 < 65535 ? n_images - s0 : 65535;
-            if (bs == 1) hdiff_undo_kernel<uint8_t><<<dim3(gx, m), 128, 0, s>>>(scratch, imgs_dev, s0, status);
-            else if (bs == 2) hdiff_undo_kernel<uint16_t><<<dim3(gx, m), 128, 0, s>>>(scratch, imgs_dev, s0, status);
-            else hdiff_undo_kernel<uint32_t><<<dim3(gx, m), 128, 0, s>>>(scratch, imgs_dev, s0, status);
-            ctx->launches++;
+            for (int sp = 0; sp <= 4; sp++) {       // one instantiation per interleave factor present (0 = generic walk)
+                if (!(spb_mask[bs] & (1u << sp))) continue;
+#define B2_HDIFF(TT, SP) hdiff_undo_kernel<TT, SP><<<dim3(gx, m), 128, 0, s>>>(scratch, imgs_dev, s0, status)
+#define B2_HDIFF_T(TT) (sp == 0 ? B2_HDIFF(TT, 0) : sp == 1 ? B2_HDIFF(TT, 1) : sp == 2 ? B2_HDIFF(TT, 2) : sp == 3 ? B2_HDIFF(TT, 3) : B2_HDIFF(TT, 4))
+                if (bs == 1) B2_HDIFF_T(uint8_t);
+                else if (bs == 2) B2_HDIFF_T(uint16_t);
+                else B2_HDIFF_T(uint32_t);
+#undef B2_HDIFF_T
+#undef B2_HDIFF
+                ctx->launches++;
+            }
         }
     }
     B2_CUDA(cudaGetLastError());
