@@ -813,6 +813,10 @@ png_unfilter_kernel(uint8_t* __restrict__ scratch, const b2_image_desc* __restri
         const size_t prb = (size_t)w * bpp;                               // bytes per row of this pass
         uint8_t* pdst = dst + (size_t)y0 * rb + (size_t)x0 * bpp;
         const size_t row_stride = (size_t)dy * rb, px_stride = (size_t)dx * bpp;
+        // Every lane walks its own row, so a byte-wide access is 32 separate sectors per instruction: the filtered bytes are
+        // fetched an aligned 32-bit word at a time and, for a progressive image, the results leave as 32-bit words too
+        // (4x fewer L1 / L2 transactions, which is what bounds this kernel).
+        const bool word_out = !adam7 && (rb & 3) == 0 && (reinterpret_cast<uintptr_t>(pdst) & 3) == 0;
         for (int band = 0; band < ph; band += 32) {
             const int row = band + lane;
             const bool live = row < ph;
@@ -821,6 +825,9 @@ png_unfilter_kernel(uint8_t* __restrict__ scratch, const b2_image_desc* __restri
             if (live && ft > 4) bad = true;
             uint32_t left[8] = {0, 0, 0, 0, 0, 0, 0, 0}, upl[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cur[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             const uint8_t* prow = (band > 0) ? pdst + (size_t)(band - 1) * row_stride : nullptr;  // row above the band (lane 0)
+            const uintptr_t in0 = reinterpret_cast<uintptr_t>(srow) + 1;                           // first filtered byte
+            uint32_t rword = 0, wword = 0;
+            uint8_t* const orow = pdst + (size_t)row * row_stride;
             for (int step = 0; step < w + 31; step++) {
                 const int x = step - lane;
                 const bool act = live && x >= 0 && x < w;
@@ -830,7 +837,10 @@ png_unfilter_kernel(uint8_t* __restrict__ scratch, const b2_image_desc* __restri
                     uint32_t up = __shfl_up_sync(0xffffffffu, cur[c], 1);     // lane L-1's pixel x (computed last step)
                     if (lane == 0) up = (prow && x >= 0 && x < w) ? prow[(size_t)x * px_stride + c] : 0;
                     if (act) {
-                        const uint32_t raw = srow[1 + (size_t)x * bpp + c];
+                        const uint32_t k = (uint32_t)x * bpp + c;             // byte index in the row
+                        const uintptr_t ia = in0 + k;
+                        if ((ia & 3) == 0 || k == 0) rword = *reinterpret_cast<const uint32_t*>(ia & ~(uintptr_t)3);
+                        const uint32_t raw = (rword >> (8 * (ia & 3))) & 0xFFu;
                         const uint32_t a = left[c], b = up, cc = upl[c];
                         uint32_t pred;
                         if (ft == 0) pred = 0;
@@ -843,7 +853,15 @@ png_unfilter_kernel(uint8_t* __restrict__ scratch, const b2_image_desc* __restri
                             pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : cc);
                         }
                         const uint32_t v = (raw + pred) & 0xFFu;
-                        pdst[(size_t)row * row_stride + (size_t)x * px_stride + c] = (uint8_t)v;
+                        if (word_out) {
+                            wword |= v << (8 * (k & 3));
+                            if ((k & 3) == 3) {
+                                *reinterpret_cast<uint32_t*>(orow + (k & ~3u)) = wword;
+                                wword = 0;
+                            }
+                        } else {
+                            orow[(size_t)x * px_stride + c] = (uint8_t)v;
+                        }
                         left[c] = v;
                         upl[c] = b;
                         cur[c] = v;
