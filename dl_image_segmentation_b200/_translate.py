@@ -239,11 +239,15 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                             # on tmpfs, the speed of one); page faults on a shared mapping do not, so the chunks are
                             # copied into a mapping of the (grown) file by several threads at once
                             end = off + len(src)
-                            os.ftruncate(fd, end)                            # this thread is the only one that grows files
-                            a0 = off & ~(mmap.ALLOCATIONGRANULARITY - 1)
-                            mm = mmap.mmap(fd, end - a0, offset=a0)
-                            dst = np.frombuffer(mm, dtype=np.uint8)[off - a0:]
-                            return [wpool.submit(np.copyto, dst[o:o + step], src[o:o + step]) for o in range(0, len(src), step)]
+                            try:
+                                os.ftruncate(fd, end)                        # this thread is the only one that grows files
+                                a0 = off & ~(mmap.ALLOCATIONGRANULARITY - 1)
+                                mm = mmap.mmap(fd, end - a0, offset=a0)
+                            except (OSError, ValueError):                    # a file system without shared mappings: write(2)
+                                mm = None
+                            if mm is not None:
+                                dst = np.frombuffer(mm, dtype=np.uint8)[off - a0:]
+                                return [wpool.submit(np.copyto, dst[o:o + step], src[o:o + step]) for o in range(0, len(src), step)]
                         mv = memoryview(src)                                 # positional writes: order-free, several in flight
                         return [wpool.submit(os.pwrite, fd, mv[o:o + step], off + o) for o in range(0, len(mv), step)]
                     shard_off[s] += total
