@@ -33,13 +33,12 @@ __device__ __forceinline__ void set_status(int32_t* status, int image, int code)
 
 // ================================================================================================ LZW
 // bits consumed by the first k codes of a segment (k = number of codes after the Clear)
+// (branch-free: every code costs 9 bits, plus one more for each width step it lies beyond)
 __device__ __forceinline__ uint32_t lzw_cum_bits(uint32_t k) {
-    if (k <= 254) return 9 * k;
-    if (k <= 766) return 2286 + 10 * (k - 254);
-    if (k <= 1790) return 7406 + 11 * (k - 766);
-    return 18670 + 12 * (k - 1790);
+    const int s = (int)k;
+    return 9u * k + (uint32_t)(max(s - 254, 0) + max(s - 766, 0) + max(s - 1790, 0));
 }
-__device__ __forceinline__ uint32_t lzw_width(uint32_t k) { return k < 254 ? 9 : (k < 766 ? 10 : (k < 1790 ? 11 : 12)); }
+__device__ __forceinline__ uint32_t lzw_width(uint32_t k) { return 9u + (k >= 254) + (k >= 766) + (k >= 1790); }
 
 constexpr int kLzwWarps = 4;
 constexpr int kLzwMaxCodes = 3840;  // code positions per segment (entries 258..4095 -> at most 3838 + slack)
@@ -104,14 +103,14 @@ lzw_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ 
         uint32_t len = 0;
         int32_t dep = -1;                                              // lane this string's length depends on
         bool bad = false;
-        uint32_t e = 0;
+        uint32_t e = 0, off_e = 0;
         if (lane < m) {
             if (code < 256) {
                 len = 1;
             } else {
                 e = code - 258;
                 if (k == 0 || e + 1 > k) bad = true;                   // first code after Clear must be a literal; entry must exist
-                else if (e < n) len = __ldcg(offs + e + 1) - __ldcg(offs + e) + 1;
+                else if (e < n) { off_e = __ldcg(offs + e); len = __ldcg(offs + e + 1) - off_e + 1; }
                 else dep = (int32_t)(e - n);
             }
         }
@@ -138,7 +137,7 @@ lzw_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ 
         int32_t srcv;
         if (lane < m) {
             if (code < 256) srcv = -1 - (int32_t)code;
-            else if (e < n) srcv = (int32_t)__ldcg(offs + e);
+            else if (e < n) srcv = (int32_t)off_e;
             else srcv = 0;  // fixed below from the producing lane's offset
         } else srcv = -1;
         {
