@@ -528,7 +528,7 @@ __device__ __forceinline__ uint32_t payload_word(const void* src, int kind, int 
 constexpr int kBuildRun = 4;   // consecutive tiles of one record per CTA: tables, header CRC and the per-thread CRC
                                // alignment are paid once per run
 
-__global__ void __launch_bounds__(kTileThreads) build_kernel(const BuildArgs a) {
+__global__ void __launch_bounds__(kTileThreads, 8) build_kernel(const BuildArgs a) {
     __shared__ __align__(16) uint4 buf4[kTile / 16];
     __shared__ CrcSmem cs;
     __shared__ uint32_t red[kTileThreads / 32];
