@@ -236,6 +236,24 @@ def test_normalise_onehot_standalone(dev, dtype):
     np.testing.assert_array_equal(gh2.cpu().numpy(), onorm.one_hot(lab, 10))
 
 
+@pytest.mark.parametrize("K,C,n", [(1, 1, 1000), (3, 3, 257), (10, 3, 700001), (24, 16, 5000), (25, 17, 5000), (40, 2, 3333)])
+def test_standalone_k4_kernel_variants(dev, K, C, n):
+    """The shared-memory / bulk-store one-hot (K <= 24) and the tabulated u8 normalise (C <= 16) against their per-element
+    fallbacks' definition (the oracle), over ragged sizes and more blocks than resident CTAs (double-buffer reuse)."""
+    from dl_image_segmentation_b200 import ops
+    rng = np.random.default_rng(K * 100 + C)
+    img = rng.integers(0, 256, (n, C), dtype=np.uint8)
+    lab = rng.integers(0, K + 3, n).astype(np.uint8)
+    lab[::97] = 255
+    mean = rng.normal(100, 50, C).astype(np.float32)
+    std = (rng.random(C) * 80 + 0.5).astype(np.float32)
+    gi, gh = ops.normalise_onehot(img, lab, mean, std, K, device=dev)
+    np.testing.assert_array_equal(gi.cpu().numpy(), onorm.normalise(img, mean, std))
+    np.testing.assert_array_equal(gh.cpu().numpy(), onorm.one_hot(lab, K))
+    _, gh2 = ops.normalise_onehot(None, lab.astype(np.float32), None, None, K, device=dev)   # float labels (array records)
+    np.testing.assert_array_equal(gh2.cpu().numpy(), onorm.one_hot(lab, K))
+
+
 @pytest.mark.parametrize("dtype,B", [(np.uint8, 3), (np.uint16, 4), (np.uint16, 8), (np.uint16, 13)])
 def test_band_stats_exact(dev, dtype, B):
     from dl_image_segmentation_b200 import ops
