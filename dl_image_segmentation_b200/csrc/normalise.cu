@@ -241,6 +241,48 @@ stats_kernel(const T* __restrict__ img, const uint8_t* __restrict__ valid, uint6
     for (int b = 0; b < NB; b++) sum[b] = sq[b] = 0;
     constexpr int PB = kB * (int)sizeof(T);                               // bytes per pixel when known
     const bool vec_ok = kB && (PB == 2 || PB == 4 || PB == 8 || PB == 16) && (reinterpret_cast<uintptr_t>(img) % (PB ? PB : 1)) == 0;
+    // Fast path: every pixel counts and a pixel is 2..16 bytes: 16 bytes (1..8 pixels) per load, sums of x in 32 bits (folded
+    // into the 64-bit totals every 4096 loads: 4096 * 8 * 65535 < 2^32), x*x through one 32x32->64 multiply-add each.
+    if (vec_ok && !valid && (reinterpret_cast<uintptr_t>(img) & 15) == 0) {
+        constexpr int PPL = PB ? 16 / PB : 1;                               // pixels per 16-byte load
+        const uint64_t n_vec = n_pixels / PPL;
+        uint32_t s32[NB];
+#pragma unroll
+        for (int b = 0; b < NB; b++) s32[b] = 0;
+        uint32_t since = 0;
+        for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += (uint64_t)gridDim.x * blockDim.x) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(img) + v);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < PPL; i++) {
+#pragma unroll
+                for (int b = 0; b < NB; b++) {
+                    const int e = i * NB + b;                               // sample index inside the 16 bytes
+                    const uint32_t x = sizeof(T) == 2 ? ((w[e >> 1] >> (16 * (e & 1))) & 0xFFFFu) : ((w[e >> 2] >> (8 * (e & 3))) & 0xFFu);
+                    s32[b] += x;
+                    sq[b] += (unsigned long long)x * x;
+                }
+            }
+            cnt += PPL;
+            if (++since == 4096) {
+#pragma unroll
+                for (int b = 0; b < NB; b++) { sum[b] += s32[b]; s32[b] = 0; }
+                since = 0;
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; b++) sum[b] += s32[b];
+        // the pixels that do not fill a vector
+        for (uint64_t p = n_vec * PPL + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pixels; p += (uint64_t)gridDim.x * blockDim.x) {
+            cnt++;
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const unsigned long long x = (unsigned long long)img[p * (uint64_t)NB + b];
+                sum[b] += x;
+                sq[b] += x * x;
+            }
+        }
+    } else
     for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pixels; p += (uint64_t)gridDim.x * blockDim.x) {
         if (valid && !valid[p]) continue;
         cnt++;
