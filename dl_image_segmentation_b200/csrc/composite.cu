@@ -279,46 +279,69 @@ mosaic_kernel(const void* const* __restrict__ stacks, const uint8_t* const* __re
     unsigned long long st_n = 0, st_s[kSB], st_q[kSB];
 #pragma unroll
     for (int b = 0; b < kSB; b++) st_s[b] = st_q[b] = 0;
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
-        int sel = -1;
+    // A pixel is a chain of dependent loads (validity of the best scene, of the next one ..., then the pixel itself), so a
+    // thread keeps kMU pixels in flight: their validity probes of one scene are issued together, then their pixel loads.
+    constexpr int kMU = 4;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < hw; p0 += kMU * stride) {
+        int sel[kMU];
+        bool live[kMU];
+#pragma unroll
+        for (int u = 0; u < kMU; u++) {
+            sel[u] = -1;
+            live[u] = p0 + u * stride < hw;
+        }
         for (int k = 0; k < ne; k++) {
             const int t = order[k];
-            if (__ldg(vchip + (size_t)t * hw + p)) {
-                sel = t;
-                break;
-            }
-        }
-        uint8_t* o = out + ((size_t)chip * hw + p) * pb;
-        const uint8_t* s = schip + ((size_t)(sel < 0 ? 0 : sel) * hw + p) * pb;
-        uint32_t w[4] = {0, 0, 0, 0};                              // the pixel's bytes (fast paths), for the statistics
-        if (PB == 16) {
-            uint4 v = sel < 0 ? make_uint4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uint4*>(s));
-            *reinterpret_cast<uint4*>(o) = v;
-            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-        } else if (PB == 8) {
-            uint2 v = sel < 0 ? make_uint2(0, 0) : __ldg(reinterpret_cast<const uint2*>(s));
-            *reinterpret_cast<uint2*>(o) = v;
-            w[0] = v.x; w[1] = v.y;
-        } else if (PB == 4) {
-            uint32_t v = sel < 0 ? 0u : __ldg(reinterpret_cast<const uint32_t*>(s));
-            *reinterpret_cast<uint32_t*>(o) = v;
-            w[0] = v;
-        } else if (PB == 2) {
-            uint16_t v = sel < 0 ? (uint16_t)0 : __ldg(reinterpret_cast<const uint16_t*>(s));
-            *reinterpret_cast<uint16_t*>(o) = v;
-            w[0] = v;
-        } else {
-            for (int i = 0; i < pb; i++) o[i] = sel < 0 ? (uint8_t)0 : s[i];
-        }
-        out_mask[(size_t)chip * hw + p] = sel < 0;
-        if (src_index) src_index[(size_t)chip * hw + p] = (int16_t)sel;
-        if (kStats && sel >= 0) {
-            st_n++;
+            uint8_t v[kMU];
+            bool open = false;
 #pragma unroll
-            for (int b = 0; b < kSB; b++) {
-                const unsigned long long x = kStats == 2 ? ((w[b >> 1] >> (16 * (b & 1))) & 0xFFFFu) : ((w[b >> 2] >> (8 * (b & 3))) & 0xFFu);
-                st_s[b] += x;
-                st_q[b] += x * x;
+            for (int u = 0; u < kMU; u++) {
+                v[u] = 0;
+                if (live[u] && sel[u] < 0) {
+                    v[u] = __ldg(vchip + (size_t)t * hw + (p0 + u * stride));
+                    open = true;
+                }
+            }
+            if (!open) break;
+#pragma unroll
+            for (int u = 0; u < kMU; u++)
+                if (v[u]) sel[u] = t;
+        }
+        uint32_t w[kMU][4];                                        // the pixels' bytes (fast paths), for the statistics
+#pragma unroll
+        for (int u = 0; u < kMU; u++) {
+            w[u][0] = w[u][1] = w[u][2] = w[u][3] = 0;
+            if (!live[u] || sel[u] < 0) continue;
+            const uint8_t* s = schip + ((size_t)sel[u] * hw + (p0 + u * stride)) * pb;
+            if (PB == 16) { const uint4 q = __ldg(reinterpret_cast<const uint4*>(s)); w[u][0] = q.x; w[u][1] = q.y; w[u][2] = q.z; w[u][3] = q.w; }
+            else if (PB == 8) { const uint2 q = __ldg(reinterpret_cast<const uint2*>(s)); w[u][0] = q.x; w[u][1] = q.y; }
+            else if (PB == 4) w[u][0] = __ldg(reinterpret_cast<const uint32_t*>(s));
+            else if (PB == 2) w[u][0] = __ldg(reinterpret_cast<const uint16_t*>(s));
+        }
+#pragma unroll
+        for (int u = 0; u < kMU; u++) {
+            if (!live[u]) continue;
+            const uint32_t p = p0 + u * stride;
+            uint8_t* o = out + ((size_t)chip * hw + p) * pb;
+            if (PB == 16) *reinterpret_cast<uint4*>(o) = make_uint4(w[u][0], w[u][1], w[u][2], w[u][3]);
+            else if (PB == 8) *reinterpret_cast<uint2*>(o) = make_uint2(w[u][0], w[u][1]);
+            else if (PB == 4) *reinterpret_cast<uint32_t*>(o) = w[u][0];
+            else if (PB == 2) *reinterpret_cast<uint16_t*>(o) = (uint16_t)w[u][0];
+            else {
+                const uint8_t* s = schip + ((size_t)(sel[u] < 0 ? 0 : sel[u]) * hw + p) * pb;
+                for (int i = 0; i < pb; i++) o[i] = sel[u] < 0 ? (uint8_t)0 : s[i];
+            }
+            out_mask[(size_t)chip * hw + p] = sel[u] < 0;
+            if (src_index) src_index[(size_t)chip * hw + p] = (int16_t)sel[u];
+            if (kStats && sel[u] >= 0) {
+                st_n++;
+#pragma unroll
+                for (int b = 0; b < kSB; b++) {
+                    const unsigned long long x = kStats == 2 ? ((w[u][b >> 1] >> (16 * (b & 1))) & 0xFFFFu) : ((w[u][b >> 2] >> (8 * (b & 3))) & 0xFFu);
+                    st_s[b] += x;
+                    st_q[b] += x * x;
+                }
             }
         }
     }
