@@ -6,6 +6,7 @@ cannot be decoded is reported through a per-image status (the reference prints a
 ``_img_to_tf_mp.py:133-136``); nothing here decodes on the CPU.
 """
 import ctypes
+import threading
 
 import numpy as np
 import torch
@@ -93,6 +94,7 @@ class _HostStaging:
         self.stage = torch.empty((1 << 20,), dtype=torch.uint8).pin_memory()
         self.streams = torch.empty((4096 * STREAM_DESC_DTYPE.itemsize,), dtype=torch.uint8).pin_memory()
         self.busy = None          # event: the last H2D copies out of these buffers
+        self.pending = False      # planned into, not yet uploaded
 
     def wait(self):
         if self.busy is not None:
@@ -101,6 +103,7 @@ class _HostStaging:
 
 
 _staging = {}
+_pool_lock = threading.Lock()
 
 
 def _ptr_of(blob):
@@ -111,22 +114,51 @@ def _ptr_of(blob):
     return a.ctypes.data, a.size, a
 
 
-def decode_blobs(blobs, device=None, timings=None, want_infos=False, png_as_tf=False):
-    """Decode a batch of encoded chips on the GPU.
+class _StagingPool:
+    """A few pinned staging sets per device, handed out in rotation: a batch can be planned (host work, any thread) while
+    the previous one is still being uploaded and decoded."""
 
-    png_as_tf: present palette / 1-2-4-bit / 16-bit PNGs the way tf.image.decode_png(dtype=uint8) does (the threaded
-    translator and the rgb parser) instead of the way rasterio / GDAL does (the multiprocessing translator).
+    def __init__(self, n=3):
+        self.sets = [_HostStaging() for _ in range(n)]
+        self.k = 0
+        self.lock = threading.Lock()
 
-    blobs: list of bytes / uint8 arrays (host).  Returns (arrays, status): arrays[i] is an (H,W,bands) CUDA
-    tensor of the file's dtype (None when status[i] != 0).  All per-file host work (header parse, descriptor
-    tables, gathering the compressed bytes into one pinned buffer) happens in ONE native, multi-threaded call.
-    """
+    def take(self):
+        with self.lock:
+            hs = self.sets[self.k % len(self.sets)]
+            self.k += 1
+            if hs.pending:
+                raise B2Error("decode staging: more batches planned ahead than there are staging sets")
+            hs.pending = True
+        hs.wait()                                              # its last uploads have left the pinned buffers
+        return hs
+
+
+class PlannedBatch:
+    """Result of plan_blobs: everything decode_planned needs, all of it host-side."""
+    __slots__ = ("n", "hs", "plan", "infos", "status", "images", "png_as_tf")
+
+
+def plan_blobs(blobs, device=None, png_as_tf=False):
+    """Host half of decode_blobs: header parse, descriptor tables and the gather of all compressed bytes into one pinned
+    buffer, in ONE native multi-threaded call.  Touches no GPU state besides pinned host memory, so the translators run
+    it on their read-ahead thread while the GPU works on the previous batch."""
     ctx = get_ctx(device)
     n = len(blobs)
-    arrays = [None] * n
+    pb = PlannedBatch()
+    pb.n, pb.png_as_tf = n, png_as_tf
+    pb.infos = (ImageInfo * max(n, 1))()
+    pb.status = np.zeros(n, dtype=np.int32)
+    pb.images = np.zeros(n, dtype=IMAGE_DESC_DTYPE)
+    pb.plan = DecodePlan()
+    pb.hs = None
     if n == 0:
-        return (arrays, np.zeros(0, np.int32), []) if want_infos else (arrays, np.zeros(0, np.int32))
-    hs = _staging.setdefault(ctx.device.index, _HostStaging())
+        return pb
+    with _pool_lock:
+        pool = _staging.get(ctx.device.index)
+        if pool is None:
+            pool = _staging[ctx.device.index] = _StagingPool()
+    hs = pb.hs = pool.take()
     ptrs = (ctypes.c_void_p * n)()
     sizes = np.zeros(n, np.uint64)
     keep = []
@@ -134,31 +166,40 @@ def decode_blobs(blobs, device=None, timings=None, want_infos=False, png_as_tf=F
         p, sz, k = _ptr_of(b)
         ptrs[i], sizes[i] = p, sz
         keep.append(k)
-    infos = (ImageInfo * n)()
-    status = np.zeros(n, dtype=np.int32)
-    images = np.zeros(n, dtype=IMAGE_DESC_DTYPE)
-    plan = DecodePlan()
-    hs.wait()                                                  # the previous batch's uploads have left the pinned buffers
     ssz = STREAM_DESC_DTYPE.itemsize
     for _ in range(2):
-        check(lib().b2_decode_plan_batch(ptrs, sizes.ctypes.data, n, infos, status.ctypes.data, images.ctypes.data,
+        check(lib().b2_decode_plan_batch(ptrs, sizes.ctypes.data, n, pb.infos, pb.status.ctypes.data, pb.images.ctypes.data,
                                          hs.streams.data_ptr(), hs.streams.numel() // ssz, hs.stage.data_ptr(),
-                                         hs.stage.numel(), 0, PNG_AS_TF if png_as_tf else 0, ctypes.byref(plan)))
-        if plan.filled:
+                                         hs.stage.numel(), 0, PNG_AS_TF if png_as_tf else 0, ctypes.byref(pb.plan)))
+        if pb.plan.filled:
             break
-        if hs.stage.numel() < plan.stage_bytes:
-            hs.stage = torch.empty((int(plan.stage_bytes * 1.25) + 4096,), dtype=torch.uint8).pin_memory()
-        if hs.streams.numel() // ssz < plan.n_streams:
-            hs.streams = torch.empty((int(plan.n_streams * 1.25 + 64) * ssz,), dtype=torch.uint8).pin_memory()
+        if hs.stage.numel() < pb.plan.stage_bytes:
+            hs.stage = torch.empty((int(pb.plan.stage_bytes * 1.25) + 4096,), dtype=torch.uint8).pin_memory()
+        if hs.streams.numel() // ssz < pb.plan.n_streams:
+            hs.streams = torch.empty((int(pb.plan.n_streams * 1.25 + 64) * ssz,), dtype=torch.uint8).pin_memory()
     del keep
+    return pb
+
+
+def decode_planned(pb, device=None, timings=None, want_infos=False):
+    """Device half of decode_blobs: upload, decode kernels, assembly.  Returns what decode_blobs returns."""
+    ctx = get_ctx(device)
+    n, plan, infos, images = pb.n, pb.plan, pb.infos, pb.images
+    arrays = [None] * n
+    if n == 0:
+        return (arrays, np.zeros(0, np.int32), []) if want_infos else (arrays, np.zeros(0, np.int32))
+    hs = pb.hs
     if plan.n_streams == 0:
-        return (arrays, status, infos) if want_infos else (arrays, status)
+        hs.pending = False
+        return (arrays, pb.status, infos) if want_infos else (arrays, pb.status)
+    ssz = STREAM_DESC_DTYPE.itemsize
     blob_d = hs.stage[:plan.stage_bytes].to(ctx.device, non_blocking=True)
     sd_d = hs.streams[:plan.n_streams * ssz].to(ctx.device, non_blocking=True)
     im_d = torch.from_numpy(images.view(np.uint8).reshape(-1)).to(ctx.device, non_blocking=True)
-    st_d = torch.from_numpy(status).to(ctx.device, non_blocking=True)
+    st_d = torch.from_numpy(pb.status).to(ctx.device, non_blocking=True)
     hs.busy = torch.cuda.Event()
     hs.busy.record(torch.cuda.current_stream(ctx.device))
+    hs.pending = False
     scratch = torch.empty((plan.scratch_bytes,), dtype=torch.uint8, device=ctx.device)
     out = torch.empty((plan.out_bytes,), dtype=torch.uint8, device=ctx.device)
     if timings is not None:
@@ -184,6 +225,20 @@ def decode_blobs(blobs, device=None, timings=None, want_infos=False, png_as_tf=F
         o = int(images[i]["out_off"])
         arrays[i] = out[o:o + nbytes].view(_B2_TO_TORCH[info.dtype]).view(info.height, info.width, info.samples)
     return (arrays, status, infos) if want_infos else (arrays, status)
+
+
+def decode_blobs(blobs, device=None, timings=None, want_infos=False, png_as_tf=False):
+    """Decode a batch of encoded chips on the GPU.
+
+    png_as_tf: present palette / 1-2-4-bit / 16-bit PNGs the way tf.image.decode_png(dtype=uint8) does (the threaded
+    translator and the rgb parser) instead of the way rasterio / GDAL does (the multiprocessing translator).
+
+    blobs: list of bytes / uint8 arrays (host).  Returns (arrays, status): arrays[i] is an (H,W,bands) CUDA
+    tensor of the file's dtype (None when status[i] != 0).  All per-file host work (header parse, descriptor
+    tables, gathering the compressed bytes into one pinned buffer) happens in ONE native, multi-threaded call
+    (plan_blobs); decode_planned then runs the kernels.
+    """
+    return decode_planned(plan_blobs(blobs, device, png_as_tf), device, timings, want_infos)
 
 
 def probe_blobs(blobs, png_as_tf=False):

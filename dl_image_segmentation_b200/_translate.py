@@ -93,10 +93,12 @@ def _read_or_error(path):
         return e
 
 
-def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, device=None, blobs=None, png_as_tf=False):
+def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, device=None, blobs=None, png_as_tf=False,
+               planned=None):
     """Read + (optionally) decode a batch of chip pairs.  Returns one entry per pair: a dict ready for
     ops.build_records, or the Exception that makes the reference skip the chip.  `blobs` = the 2n file contents
-    (image, label, image, label, ...) when the caller has already read them (run_worker prefetches on threads)."""
+    (image, label, image, label, ...) when the caller has already read them (run_worker prefetches on threads);
+    `planned` = their _codec.plan_blobs result when the caller has also done the host half of the decode there."""
     ctx = get_ctx(device)
     n = len(img_paths)
     if blobs is None:
@@ -111,7 +113,9 @@ def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, devi
             blobs[k] = b""
     arrays = [None] * (2 * n)
     if store_as_array:                                                      # ONE native planning call + the decode kernels
-        arrays, st, infos = _codec.decode_blobs(blobs, device=ctx.device, want_infos=True, png_as_tf=png_as_tf)
+        if planned is None:
+            planned = _codec.plan_blobs(blobs, ctx.device, png_as_tf)
+        arrays, st, infos = _codec.decode_planned(planned, ctx.device, want_infos=True)
         for k in range(2 * n):
             if len(blobs[k]) and infos[k].status == 0 and st[k] != 0 and errs[k // 2] is None:
                 errs[k // 2] = ChipError("could not decode %s (codec status %d)" % ((img_paths, lbl_paths)[k % 2][k // 2], int(st[k])))
@@ -185,18 +189,25 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
             ThreadPoolExecutor(max_workers=8) as wpool:
         reader = FileBatchReader(depth=3, threads=io_threads)
 
+        def read_and_plan(paths):
+            blobs = reader.read(paths)                                      # one native call; the GIL is free meanwhile
+            planned = None
+            if store_as_array:                                              # host half of the decode, off the main thread
+                planned = _codec.plan_blobs([b"" if isinstance(b, Exception) else b for b in blobs], ctx.device, png_as_tf)
+            return blobs, planned
+
         def submit_reads(rng):
             paths = []
             for i in range(*rng):
                 paths += [img_filenames[i], lbl_filenames[i]]
-            return pool.submit(reader.read, paths)                          # one native call; the GIL is free meanwhile
+            return pool.submit(read_and_plan, paths)
         pending_reads = submit_reads(batches[0]) if batches else None
         for bi, (b0, b1) in enumerate(batches):
-            blobs = pending_reads.result()
+            blobs, planned = pending_reads.result()
             pending_reads = submit_reads(batches[bi + 1]) if bi + 1 < len(batches) else None
             idx = list(range(b0, b1))
             pairs = load_pairs([img_filenames[i] for i in idx], [lbl_filenames[i] for i in idx], store_as_array,
-                               key_fn, validate, ctx.device, blobs=blobs, png_as_tf=png_as_tf)
+                               key_fn, validate, ctx.device, blobs=blobs, png_as_tf=png_as_tf, planned=planned)
             for s in range(per):
                 lo, hi = max(b0, int(shard_ranges[s])), min(b1, int(shard_ranges[s + 1]))
                 if lo >= hi:
