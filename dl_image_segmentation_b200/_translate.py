@@ -48,6 +48,9 @@ _lib_mod.register_signatures({
 })
 
 
+_worker_buffers = {}     # device index -> host buffers of run_worker (one worker at a time per device)
+
+
 class FileBatchReader:
     """Reads whole batches of files with ONE native, multi-threaded call (b2_read_files) into a reusable host buffer:
     the per-file open().read() of the reference's worker loop costs the interpreter ~30 us a file, which is what bounds
@@ -173,12 +176,21 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
             pair_bytes = 1 << 20
         batch_pairs = int(max(32, min(2048, (768 << 20) // max(1, pair_bytes))))
     n_slots = 4                                                             # rotating pinned write-back buffers
-    pinned = [None] * n_slots                                               # rotating pinned write-back buffers
+    # rotating pinned write-back buffers and read-ahead buffers: kept per device between calls (pinning and first-touching
+    # a few hundred MB costs ~0.1 s, which is what a worker with a few thousand chips takes altogether)
+    cache = _worker_buffers.setdefault(ctx.device.index, {"pinned": [None] * n_slots, "reader": None})
+    pinned = cache["pinned"]
     slot_futs = [[] for _ in range(n_slots)]                                # positional writes still reading a buffer
     # decode batches run over the worker's whole file range (the entropy decoders want thousands of streams per launch);
     # records are then serialised and written shard by shard, so a batch may feed several shard files
     lo_all, hi_all = int(shard_ranges[0]), int(shard_ranges[-1])
-    batches = [(b0, min(b0 + batch_pairs, hi_all)) for b0 in range(lo_all, hi_all, batch_pairs)]
+    # the first batches are small (1/8, 1/4, 1/2 of the full size): the pipeline's start-up latency is the time the first
+    # batch takes to go through read -> plan -> decode -> build -> write, and a worker with a few thousand chips is mostly that
+    batches, b0, size = [], lo_all, max(32, batch_pairs // 8)
+    while b0 < hi_all:
+        b1 = min(b0 + size, hi_all)
+        batches.append((b0, b1))
+        b0, size = b1, min(batch_pairs, size * 2)
     use_mmap = os.environ.get("B2_SHARD_WRITE", "mmap") == "mmap"
     files = [open(os.path.join(output_directory, "%s-%.5d-of-%.5d" % (name, worker_index * per + s, num_shards)), "w+b")
              for s in range(per)]
@@ -187,7 +199,9 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
     seq = 0
     with ThreadPoolExecutor(max_workers=max(1, io_threads)) as pool, ThreadPoolExecutor(max_workers=1) as writer, \
             ThreadPoolExecutor(max_workers=8) as wpool:
-        reader = FileBatchReader(depth=3, threads=io_threads)
+        reader = cache["reader"]
+        if reader is None:
+            reader = cache["reader"] = FileBatchReader(depth=3, threads=io_threads)
 
         def read_and_plan(paths):
             blobs = reader.read(paths)                                      # one native call; the GIL is free meanwhile
@@ -292,7 +306,7 @@ def run_workers(num_workers, fn):
         torch.cuda.set_device(dev)
         for p in by_dev[dev]:
             results[p] = fn(p, dev)
-    if len(by_dev) <= 1:
+    if len(by_dev) <= 1 or os.environ.get("B2_WORKER_THREADS", "1") == "0":
         for dev in by_dev:
             on_device(dev)
     else:
