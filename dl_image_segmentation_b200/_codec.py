@@ -61,6 +61,9 @@ def _host_bytes(blob):
 def probe(blob, png_as_tf=False) -> ImageInfo:
     """Header-only read: height / width / bands / dtype (load_image_rasterio(decode=False), reference :51-53)."""
     a = _host_bytes(blob)
+    if is_jpeg(a):
+        st, ji = probe_jpeg(a)
+        return jpeg_as_image_info(ji, st)
     info = ImageInfo()
     check(lib().b2_image_probe(a.ctypes.data, a.size, PNG_AS_TF if png_as_tf else 0, ctypes.byref(info)))
     return info
@@ -238,7 +241,9 @@ def decode_blobs(blobs, device=None, timings=None, want_infos=False, png_as_tf=F
     tables, gathering the compressed bytes into one pinned buffer) happens in ONE native, multi-threaded call
     (plan_blobs); decode_planned then runs the kernels.
     """
-    return decode_planned(plan_blobs(blobs, device, png_as_tf), device, timings, want_infos)
+    arrays, status, infos = decode_planned(plan_blobs(blobs, device, png_as_tf), device, timings, True)
+    arrays, status, infos = merge_jpeg(blobs, arrays, status, infos, device)
+    return (arrays, status, infos) if want_infos else (arrays, status)
 
 
 def probe_blobs(blobs, png_as_tf=False):
@@ -260,6 +265,119 @@ def probe_blobs(blobs, png_as_tf=False):
     check(lib().b2_decode_plan_batch(ptrs, sizes.ctypes.data, n, infos, status.ctypes.data, images.ctypes.data, None, 0, None, 0,
                                      1, PNG_AS_TF if png_as_tf else 0, ctypes.byref(plan)))
     return infos
+
+
+# ---------------------------------------------------------------------------------------------- JPEG (.jpg chips)
+class JpegInfo(ctypes.Structure):
+    """b2chips.h b2_jpeg_info: what the host marker walk learns about one baseline JPEG."""
+    _fields_ = [("width", ctypes.c_int32), ("height", ctypes.c_int32), ("components", ctypes.c_int32),
+                ("ycc", ctypes.c_int32), ("h", ctypes.c_int32 * 3), ("v", ctypes.c_int32 * 3),
+                ("tq", ctypes.c_int32 * 3), ("td", ctypes.c_int32 * 3), ("ta", ctypes.c_int32 * 3),
+                ("restart_interval", ctypes.c_int32), ("mcus_across", ctypes.c_int32), ("mcus_down", ctypes.c_int32),
+                ("scan_off", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+                ("qt", (ctypes.c_uint16 * 64) * 4), ("huff_counts", ((ctypes.c_uint8 * 16) * 4) * 2),
+                ("huff_syms", ((ctypes.c_uint8 * 256) * 4) * 2)]
+
+
+JPEG_JOB_DTYPE = np.dtype([("src_off", "<u8"), ("coef_off", "<u8"), ("plane_off", "<u8"), ("out_off", "<u8"),
+                           ("src_len", "<u4"), ("image", "<i4")])
+FORMAT_JPEG = 3    # ImageInfo.format of a chip that went through the JPEG path (1 TIFF, 2 PNG come from b2_image_probe)
+
+_lib.register_signatures({
+    "b2_jpeg_probe": (_i, [_vp, _u64, ctypes.POINTER(JpegInfo)]),
+    "b2_jpeg_sizes": (_i, [ctypes.POINTER(JpegInfo), ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
+    "b2_jpeg_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _u64, _vp, _vp, _vp, _vp]),
+})
+
+
+def is_jpeg(blob) -> bool:
+    """SOI marker at the start of the file (how libjpeg / GDAL / tf.image.decode_image recognise the format)."""
+    return len(blob) >= 3 and blob[0] == 0xFF and blob[1] == 0xD8 and blob[2] == 0xFF
+
+
+def probe_jpeg(blob):
+    """Header-only read of a JPEG: (status, JpegInfo); status 0 ok, 1 corrupt, 3 out-of-scope flavour."""
+    b = _host_bytes(blob)
+    info = JpegInfo()
+    st = lib().b2_jpeg_probe(b.ctypes.data if b.size else None, b.size, ctypes.byref(info))
+    return int(st), info
+
+
+def decode_jpeg_blobs(blobs, device=None):
+    """Decode a batch of baseline JPEG files on the GPU -> (arrays, status, infos): arrays[i] is an (H,W,1) or (H,W,3)
+    uint8 CUDA tensor (RGB), None where status[i] != 0.  Replaces tf.image.decode_jpeg behind ImageCoder.decode_jpeg
+    (reference _img_to_tf_threaded.py:36-38,51-56); the header walk is the only host work."""
+    ctx = get_ctx(device)
+    n = len(blobs)
+    status = np.zeros(n, np.int32)
+    arrays = [None] * n
+    infos = [None] * n
+    host = [_host_bytes(b) for b in blobs]
+    ok = []
+    for i, b in enumerate(host):
+        status[i], infos[i] = probe_jpeg(b)
+        if status[i] == 0:
+            ok.append(i)
+    if not ok:
+        return arrays, status, infos
+    m = len(ok)
+    jinfos = (JpegInfo * m)()
+    jobs = np.zeros(m, JPEG_JOB_DTYPE)
+    src = coef = plane = out = 0
+    cc, pb, ob = _u64(), _u64(), _u64()
+    for j, i in enumerate(ok):
+        jinfos[j] = infos[i]
+        check(lib().b2_jpeg_sizes(ctypes.byref(jinfos[j]), ctypes.byref(cc), ctypes.byref(pb), ctypes.byref(ob)))
+        jobs[j] = (src, coef, plane, out, host[i].size, j)
+        src = _align(src + host[i].size, 16)
+        coef += cc.value
+        plane = _align(plane + pb.value, 16)
+        out = _align(out + ob.value, 256)
+    stage = torch.empty((src,), dtype=torch.uint8).pin_memory()
+    sv = stage.numpy()
+    for j, i in enumerate(ok):
+        o = int(jobs[j]["src_off"])
+        sv[o:o + host[i].size] = host[i]
+    blob_d = stage.to(ctx.device, non_blocking=True)
+    info_h = np.frombuffer(jinfos, dtype=np.uint8)
+    info_d = torch.from_numpy(info_h.copy()).to(ctx.device)
+    jobs_d = torch.from_numpy(jobs.view(np.uint8).reshape(-1).copy()).to(ctx.device)
+    coef_d = torch.empty((max(coef, 1),), dtype=torch.int16, device=ctx.device)
+    planes_d = torch.empty((max(plane, 1),), dtype=torch.uint8, device=ctx.device)
+    out_d = torch.empty((max(out, 1),), dtype=torch.uint8, device=ctx.device)
+    st_d = torch.zeros((m,), dtype=torch.int32, device=ctx.device)
+    check(lib().b2_jpeg_decode(ctx.handle, ptr(blob_d), ptr(info_d), ctypes.addressof(jinfos), ptr(jobs_d), jobs.ctypes.data, m,
+                               ptr(coef_d), coef, ptr(planes_d), ptr(out_d), ptr(st_d), ctx.stream()))
+    st = st_d.cpu().numpy()                                   # also orders the pinned staging buffer's release
+    for j, i in enumerate(ok):
+        status[i] = st[j]
+        if st[j] == 0:
+            fi = infos[i]
+            o = int(jobs[j]["out_off"])
+            arrays[i] = out_d[o:o + fi.width * fi.height * fi.components].view(fi.height, fi.width, fi.components)
+    return arrays, status, infos
+
+
+def merge_jpeg(blobs, arrays, status, infos, device=None):
+    """The TIFF / PNG planner reports a .jpg chip as an unknown format; decode those through the JPEG path and put their
+    results in place (arrays / status / infos as decode_planned returns them)."""
+    idx = [k for k, b in enumerate(blobs) if is_jpeg(_host_bytes(b))]
+    if not idx:
+        return arrays, status, infos
+    ja, js, ji = decode_jpeg_blobs([blobs[k] for k in idx], device)
+    for j, k in enumerate(idx):
+        arrays[k], status[k] = ja[j], js[j]
+        infos[k] = jpeg_as_image_info(ji[j], js[j] if js[j] in (1, 3) else 0)   # 2 = header fine, entropy data corrupt
+    return arrays, status, infos
+
+
+def jpeg_as_image_info(jinfo, status) -> ImageInfo:
+    """The fields of ImageInfo the translators read, for a chip that went through the JPEG path."""
+    info = ImageInfo()
+    info.format, info.status, info.dtype = FORMAT_JPEG, int(status), _lib.B2_U8
+    info.width, info.height, info.samples = jinfo.width, jinfo.height, jinfo.components
+    info.geotransform[:] = (0.0, 1.0, 0.0, 0.0, 0.0, 1.0)     # GDAL's default for a file without georeferencing
+    return info
 
 
 def to_float32(t):

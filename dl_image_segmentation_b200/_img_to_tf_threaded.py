@@ -22,10 +22,14 @@ class ImageCoder(object):
         self.device = device
 
     def png_to_jpeg(self, image_data):
-        raise NotImplementedError("JPEG transcoding is out of scope of the B200 hot path (SURVEY.md section 8f row 4)")
+        raise NotImplementedError("JPEG encoding (convert_png_to_jpg) is out of scope: its bytes depend on the libjpeg "
+                                  "build behind tf.image.encode_jpeg and cannot be pinned (SURVEY.md section 8f row 4)")
 
     def decode_jpeg(self, image_data):
-        raise NotImplementedError("JPEG decode is out of scope of the B200 hot path (SURVEY.md section 8f row 4)")
+        (image,), (st,), _ = _codec.decode_jpeg_blobs([image_data], device=self.device)           # tf.image.decode_jpeg
+        if st != 0:
+            raise _translate.ChipError("could not decode JPEG (codec status %d)" % int(st))
+        return image
 
     def decode_png(self, image_data):
         (image,), (st,) = _codec.decode_blobs([image_data], device=self.device, png_as_tf=True)   # tf.image.decode_png
@@ -76,8 +80,8 @@ def _process_image_files_worker(coder, thread_index, ranges, name, filenames, la
     def validate(info):
         if png_to_jpg:
             raise NotImplementedError("convert_png_to_jpg: JPEG is out of scope of the B200 hot path")
-        if info.format != 2:
-            raise NotImplementedError("only PNG chips are handled by the threaded translator on the GPU")
+        if info.format not in (2, _codec.FORMAT_JPEG):
+            raise NotImplementedError("only PNG and JPEG chips are handled by the threaded translator on the GPU")
         _validate(info)
     return _translate.run_worker(thread_index, ranges, name, filenames, labels, out_folder, num_shards, key_fn,
                                  store_as_array, label="thread", progress_every=1000, validate=validate, device=device,

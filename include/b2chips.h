@@ -311,6 +311,49 @@ int b2_lzw_encode(b2_ctx* ctx, const uint8_t* raw_dev, const b2_enc_desc* descs_
 int b2_tile_split(b2_ctx* ctx, const uint8_t* img_dev, int H, int W, int pixel_bytes, int tile_w, int tile_h,
                   uint8_t* tiles_dev, b2_stream stream);
 
+/* ------------------------------------------------------------------ K1j: baseline JPEG decode
+ * Replace tf.image.decode_jpeg(image_data, channels=0) behind ImageCoder.decode_jpeg
+ * (_img_to_tf_threaded.py:36-38, 51-56), which _process_image runs on every .jpg chip (:97-103): libjpeg with its
+ * default settings — accurate integer ("islow") inverse DCT, triangle-filter ("fancy") chroma upsampling, 16-bit
+ * fixed-point YCbCr -> RGB.  In scope: 8-bit sequential Huffman files (SOF0 / SOF1) with one interleaved scan,
+ * 1 component -> (H,W,1) or 3 components -> (H,W,3) RGB, any 1..4 sampling factors that divide the maximum, restart
+ * intervals.  Progressive / arithmetic / lossless / 12-bit / 4-component / multi-scan files are reported as
+ * unsupported (chip status 3) and skipped the way the reference skips a chip it cannot decode (:196-199). */
+typedef struct {
+    int32_t width, height, components;
+    int32_t ycc;                    /* 1: components are Y,Cb,Cr -> RGB on output (libjpeg's JFIF / Adobe / id guess)  */
+    int32_t h[3], v[3];             /* sampling factors (1,1 for a single component: never interleaved)               */
+    int32_t tq[3], td[3], ta[3];    /* quantisation / DC / AC table selectors                                          */
+    int32_t restart_interval;       /* MCUs between RSTn markers, 0 = none                                             */
+    int32_t mcus_across, mcus_down;
+    uint32_t scan_off;              /* first entropy-coded byte of the file                                            */
+    uint32_t reserved;
+    uint16_t qt[4][64];             /* natural (row-major) order                                                       */
+    uint8_t huff_counts[2][4][16];  /* [0 DC | 1 AC][table][code length - 1]                                           */
+    uint8_t huff_syms[2][4][256];
+} b2_jpeg_info;
+
+typedef struct {
+    uint64_t src_off;    /* the file's bytes in blob_dev                                                             */
+    uint64_t coef_off;   /* int16 index into coef_dev: 64 per block, component after component, blocks row-major     */
+    uint64_t plane_off;  /* byte offset into planes_dev (multiple of 16): padded component planes one after another  */
+    uint64_t out_off;    /* byte offset into out_dev: (H,W,components) uint8                                         */
+    uint32_t src_len;
+    int32_t image;       /* slot in status_dev                                                                       */
+} b2_jpeg_job;
+
+/* Host-side marker walk up to the first SOS.  Returns the chip status: 0 ok, 1 not a JPEG / corrupt header,
+ * 3 a JPEG flavour out of scope (b2_last_error() says which). */
+int b2_jpeg_probe(const uint8_t* blob, uint64_t size, b2_jpeg_info* info);
+/* Host-side: int16 coefficients, bytes of padded component planes and bytes of the (H,W,components) result. */
+int b2_jpeg_sizes(const b2_jpeg_info* info, uint64_t* coef_count, uint64_t* plane_bytes, uint64_t* out_bytes);
+/* Entropy decode (one warp per file) -> inverse DCT (one thread per 8x8 block) -> upsample + colour conversion (one
+ * thread per pixel).  coef_dev must hold coef_count int16 (zeroed here), infos / jobs are given both as device and as
+ * host arrays (the host copy sizes the launches).  status_dev as for b2_decode_streams: 2 = corrupt entropy data. */
+int b2_jpeg_decode(b2_ctx* ctx, const uint8_t* blob_dev, const b2_jpeg_info* infos_dev, const b2_jpeg_info* infos_host,
+                   const b2_jpeg_job* jobs_dev, const b2_jpeg_job* jobs_host, int n, int16_t* coef_dev,
+                   uint64_t coef_count, uint8_t* planes_dev, uint8_t* out_dev, int32_t* status_dev, b2_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,181 @@
+"""JPEG chips (.jpg): oracle pinned against libjpeg-turbo (golden files + live cv2 / Pillow), the host marker walk of
+the C ABI against the oracle's, and — on the GPU — the decode kernels against both.  Replaces tf.image.decode_jpeg
+behind ImageCoder.decode_jpeg (reference _img_to_tf_threaded.py:36-38,51-56,97-103).  Bar: bit-exact."""
+import glob
+import io
+import os
+
+import numpy as np
+import pytest
+
+from oracle import jpegcodec as ojpg
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(G, "jpeg_*.npy")))
+
+
+def _case(name):
+    return open(os.path.join(G, "jpeg_%s.jpg" % name), "rb").read(), np.load(os.path.join(G, "jpeg_%s.npy" % name))
+
+
+def _smooth(h, w, c, rng):
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.stack([127 + 100 * np.sin(xx / (7.0 + 3 * i)) * np.cos(yy / (5.0 + 2 * i)) for i in range(c)], -1)
+    return np.clip(img + rng.normal(0, 12, img.shape), 0, 255).astype(np.uint8)
+
+
+def _live_files(seed, sizes, qualities=(100, 75, 30), restarts=(0, 3)):
+    """(name, file bytes, pixels as libjpeg-turbo decodes them) for every sampling mode cv2 can write."""
+    import cv2
+    S = {"444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+         "420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, "440": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440,
+         "411": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411}
+    rng = np.random.default_rng(seed)
+    out = []
+    for (h, w) in sizes:
+        for name, sf in S.items():
+            for q in qualities:
+                for rst in restarts:
+                    img = _smooth(h, w, 3, rng) if (h + w + q) % 2 else rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+                    ok, buf = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf,
+                                                         cv2.IMWRITE_JPEG_RST_INTERVAL, rst])
+                    assert ok
+                    out.append(("%dx%d %s q%d rst%d" % (h, w, name, q, rst), buf.tobytes(),
+                                np.ascontiguousarray(cv2.imdecode(buf, cv2.IMREAD_UNCHANGED)[..., ::-1])))
+        img = _smooth(h, w, 1, rng)[..., 0]
+        ok, buf = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 90])
+        out.append(("%dx%d grey" % (h, w), buf.tobytes(), cv2.imdecode(buf, cv2.IMREAD_UNCHANGED)[..., None]))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU: the oracle
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_against_golden_libjpeg_files(name):
+    data, want = _case(name)
+    assert np.array_equal(ojpg.decode_jpeg(data), want)
+    assert ojpg.jpeg_shape(data) == want.shape
+
+
+def test_oracle_against_live_libjpeg_turbo():
+    from PIL import Image
+    files = _live_files(1, [(64, 64), (45, 67), (16, 16), (17, 33), (8, 5), (3, 3), (9, 2), (1, 9), (1, 1)], qualities=(100, 50))
+    for name, data, want in files:
+        assert np.array_equal(ojpg.decode_jpeg(data), want), name
+        pil = np.array(Image.open(io.BytesIO(data)))
+        assert np.array_equal(pil.reshape(want.shape), want), name      # Pillow's libjpeg agrees with cv2's
+
+
+def test_oracle_reports_out_of_scope_flavours():
+    with pytest.raises(ojpg.Unsupported):
+        ojpg.decode_jpeg(open(os.path.join(G, "jpeg_progressive.jpg"), "rb").read())
+    with pytest.raises(ojpg.DecodeError):
+        ojpg.decode_jpeg(b"\x89PNG\r\n\x1a\n")
+
+
+# ------------------------------------------------------------------------------------ CPU: host half of the C ABI
+def test_host_probe_matches_oracle_parse():
+    from dl_image_segmentation_b200 import _codec
+    files = [(n,) + _case(n) for n in CASES] + _live_files(2, [(45, 67), (9, 2)], qualities=(75,))
+    for name, data, want in files:
+        st, info = _codec.probe_jpeg(data)
+        fr = ojpg.parse_jpeg(data)
+        assert st == 0, name
+        assert (info.height, info.width, info.components) == want.shape, name
+        assert info.scan_off == fr["scan"] and info.restart_interval == fr["restart"] and bool(info.ycc) == fr["ycc"], name
+        for c, comp in enumerate(fr["comps"]):
+            assert (info.h[c], info.v[c], info.tq[c], info.td[c], info.ta[c]) == (comp["h"], comp["v"], comp["tq"], comp["td"], comp["ta"])
+            assert list(info.qt[comp["tq"]]) == list(fr["qt"][comp["tq"]]), name
+            for cls, sel in ((0, comp["td"]), (1, comp["ta"])):
+                counts, syms = fr["ht"][(cls, sel)]
+                assert list(info.huff_counts[cls][sel]) == counts and list(info.huff_syms[cls][sel])[:len(syms)] == syms
+        gen = _codec.probe(data)                                          # the format-agnostic header read
+        assert (gen.format, gen.status, gen.height, gen.width, gen.samples) == (_codec.FORMAT_JPEG, 0) + want.shape
+    assert _codec.probe_jpeg(open(os.path.join(G, "jpeg_progressive.jpg"), "rb").read())[0] == 3
+    assert _codec.probe_jpeg(b"\xff\xd8\xff\xe0\x00")[0] == 1
+    assert _codec.probe_jpeg(_case(CASES[0])[0][:200])[0] == 1           # cut inside the tables
+    assert _codec.probe_jpeg(b"")[0] == 1
+
+
+# ---------------------------------------------------------------------------------------------- GPU: the kernels
+@pytest.mark.gpu
+def test_gpu_decode_matches_golden_and_oracle(dev):
+    from dl_image_segmentation_b200 import _codec
+    blobs, wants = zip(*[_case(n) for n in CASES])
+    arrays, status, infos = _codec.decode_jpeg_blobs(list(blobs), dev)
+    assert list(status) == [0] * len(CASES)
+    for name, a, want, data in zip(CASES, arrays, wants, blobs):
+        got = a.cpu().numpy()
+        assert got.dtype == np.uint8 and got.shape == want.shape, name
+        assert np.array_equal(got, want), name                            # libjpeg-turbo's pixels
+        assert np.array_equal(got, ojpg.decode_jpeg(data)), name          # the oracle's
+
+
+@pytest.mark.gpu
+def test_gpu_decode_sweep_against_live_libjpeg_turbo(dev):
+    from dl_image_segmentation_b200 import _codec
+    files = _live_files(3, [(64, 64), (45, 67), (17, 33), (8, 5), (3, 3), (9, 2), (1, 9), (1, 1), (256, 256)], qualities=(100, 40))
+    arrays, status, _ = _codec.decode_jpeg_blobs([f[1] for f in files], dev)
+    assert not status.any()
+    for (name, _, want), a in zip(files, arrays):
+        assert np.array_equal(a.cpu().numpy(), want), name
+
+
+@pytest.mark.gpu
+def test_gpu_decode_error_behaviour(dev):
+    """Out-of-scope and damaged files are data, not exceptions: a status per chip, the neighbours unaffected."""
+    from dl_image_segmentation_b200 import _codec
+    good, want = _case("420_q90")
+    prog = open(os.path.join(G, "jpeg_progressive.jpg"), "rb").read()
+    cut = good[:len(good) - 300]                                          # entropy data truncated
+    arrays, status, _ = _codec.decode_jpeg_blobs([good, prog, cut, b"not a jpeg", good], dev)
+    assert list(status) == [0, 3, 2, 1, 0]
+    assert arrays[1] is None and arrays[2] is None and arrays[3] is None
+    assert np.array_equal(arrays[0].cpu().numpy(), want) and np.array_equal(arrays[4].cpu().numpy(), want)
+    # the format-agnostic entry point routes .jpg blobs here and everything else to the TIFF / PNG decoders
+    import cv2
+    ok, png = cv2.imencode(".png", want[..., ::-1])
+    (a, b), st = _codec.decode_blobs([png.tobytes(), good], dev, png_as_tf=True)
+    assert list(st) == [0, 0] and np.array_equal(a.cpu().numpy(), want) and np.array_equal(b.cpu().numpy(), want)
+
+
+@pytest.mark.gpu
+def test_threaded_translator_on_jpg_chips(dev, tmp_path):
+    """images_to_tfrecords_mt over a folder of .jpg chips: raw file bytes + header dims in the records (store_as_array
+    False, reference :113-121) or the decoded arrays (True), next to the oracle's worker loop pieces."""
+    import cv2
+    import dl_image_segmentation_b200 as pkg
+    from dl_image_segmentation_b200 import _tfrecord_image_translation as tr
+    from oracle import tfrecord as otfr
+    rng = np.random.default_rng(5)
+    d = tmp_path / "chips"
+    (d / "images").mkdir(parents=True)
+    (d / "labels").mkdir()
+    want = {}
+    for i in range(6):
+        key = "64:0:10.0:30:%d:%d" % (i, 7 * i)
+        img = _smooth(32, 40, 3, rng)
+        lab = (rng.integers(0, 3, (32, 40)) * 100).astype(np.uint8)
+        for sub, arr in (("images", img), ("labels", lab)):
+            ok, buf = cv2.imencode(".jpg", arr, [cv2.IMWRITE_JPEG_QUALITY, 95])
+            (d / sub / (key.replace(":", "#") + ".jpg")).write_bytes(buf.tobytes())
+        want[key.encode()] = tuple((d / s / (key.replace(":", "#") + ".jpg")).read_bytes() for s in ("images", "labels"))
+    (d / "images" / "64#0#10.0#30#9#9.jpg").write_bytes(b"\xff\xd8\xff garbage")        # skipped, as the reference would
+    (d / "labels" / "64#0#10.0#30#9#9.jpg").write_bytes(want[b"64:0:10.0:30:0:0"][1])
+    for as_array in (False, True):
+        out = tmp_path / ("out%d" % as_array)
+        out.mkdir()
+        pkg.images_to_tfrecords_mt("jpgs", str(d), str(out), 1, num_threads=1, store_as_array=as_array)
+        (shard,) = sorted(os.listdir(out))
+        recs = otfr.read_records(open(os.path.join(out, shard), "rb").read())
+        assert len(recs) == 6
+        for rec in recs:
+            if as_array:
+                img, tgt, ident = tr.parse_8bit_array_proto(rec, device=dev)
+                fi, fl = want[ident]
+                assert np.array_equal(img.cpu().numpy(), ojpg.decode_jpeg(fi))
+                assert np.array_equal(tgt.cpu().numpy(), ojpg.decode_jpeg(fl)[..., 0])
+            else:
+                img, tgt, ident = tr.parse_encoded_rgb_img_proto(rec, device=dev)     # tf.io.decode_image on both blobs
+                fi, fl = want[ident]
+                assert np.array_equal(img.cpu().numpy(), ojpg.decode_jpeg(fi))
+                assert np.array_equal(tgt.cpu().numpy(), ojpg.decode_jpeg(fl))
