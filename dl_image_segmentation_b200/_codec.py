@@ -303,7 +303,7 @@ def probe_jpeg(blob):
     return int(st), info
 
 
-def decode_jpeg_blobs(blobs, device=None):
+def decode_jpeg_blobs(blobs, device=None, timings=None):
     """Decode a batch of baseline JPEG files on the GPU -> (arrays, status, infos): arrays[i] is an (H,W,1) or (H,W,3)
     uint8 CUDA tensor (RGB), None where status[i] != 0.  Replaces tf.image.decode_jpeg behind ImageCoder.decode_jpeg
     (reference _img_to_tf_threaded.py:36-38,51-56); the header walk is the only host work."""
@@ -346,8 +346,16 @@ def decode_jpeg_blobs(blobs, device=None):
     planes_d = torch.empty((max(plane, 1),), dtype=torch.uint8, device=ctx.device)
     out_d = torch.empty((max(out, 1),), dtype=torch.uint8, device=ctx.device)
     st_d = torch.zeros((m,), dtype=torch.int32, device=ctx.device)
+    if timings is not None:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
     check(lib().b2_jpeg_decode(ctx.handle, ptr(blob_d), ptr(info_d), ctypes.addressof(jinfos), ptr(jobs_d), jobs.ctypes.data, m,
                                ptr(coef_d), coef, ptr(planes_d), ptr(out_d), ptr(st_d), ctx.stream()))
+    if timings is not None:
+        ev[1].record()
+        torch.cuda.synchronize()
+        timings.update(decode_ms=ev[0].elapsed_time(ev[1]), compressed_bytes=int(sum(host[i].size for i in ok)),
+                       decoded_bytes=int(sum(infos[i].width * infos[i].height * infos[i].components for i in ok)), files=m)
     st = st_d.cpu().numpy()                                   # also orders the pinned staging buffer's release
     for j, i in enumerate(ok):
         status[i] = st[j]

@@ -152,6 +152,40 @@ def bench_decode(dev, kind, n_distinct=16, reps=None):
             "wall_ms_incl_host_parse_and_h2d": round(best["wall_ms"], 1)})
 
 
+def bench_jpeg(dev, n_distinct=16, reps=None):
+    """cfg1 chips saved as .jpg (quality 100, 4:2:0 — what tf.image.encode_jpeg behind png_to_jpeg writes) + grey labels."""
+    reps = reps or int(os.environ.get("KB_DECODE_REPS", "16")) * 4
+    import time
+
+    import cv2
+    import synthetic as syn
+    from dl_image_segmentation_b200 import _codec
+    blobs = []
+    for i in range(n_distinct):
+        img, lab, _ = syn.cfg1_chip(i)
+        for arr in (img[..., ::-1], lab.reshape(lab.shape[0], lab.shape[1])):
+            ok, buf = cv2.imencode(".jpg", np.ascontiguousarray(arr), [cv2.IMWRITE_JPEG_QUALITY, 100])
+            blobs.append(buf.tobytes())
+    batch = blobs * reps
+    best = None
+    for it in range(4):
+        tm = {}
+        t0 = time.time()
+        arrays, status, _ = _codec.decode_jpeg_blobs(batch, device=dev, timings=tm)
+        torch.cuda.synchronize()
+        tm["wall_ms"] = (time.time() - t0) * 1e3
+        assert not status.any()
+        if best is None or tm["decode_ms"] < best["decode_ms"]:
+            best = tm
+    pairs = len(batch) // 2
+    ms = best["decode_ms"]
+    return report("decode jpeg: %d chip pairs (%d files)" % (pairs, best["files"]), ms,
+                  best["compressed_bytes"] + best["decoded_bytes"],
+                  {"chip_pairs_per_s": round(pairs / ms * 1e3, 1), "decoded_GB/s": round(best["decoded_bytes"] / ms / 1e6, 1),
+                   "compressed_MB": round(best["compressed_bytes"] / 1e6, 1),
+                   "wall_ms_incl_host_parse_and_h2d": round(best["wall_ms"], 1)})
+
+
 def bench_parse(dev, n_shards=8):
     """Variants of the fused parse kernel on cfg2 shards + write-only / copy bandwidth references."""
     sys.path.insert(0, ROOT)
@@ -350,6 +384,8 @@ def main():
         bench_encode(dev)
     if "encode_kernel" in which:
         bench_encode_kernel(dev)
+    if "jpeg" in which:
+        bench_jpeg(dev)
     for kind in ("lzw", "lzw_strips_pred2", "deflate", "png"):
         if kind in which or "decode" in which:
             bench_decode(dev, kind)
