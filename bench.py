@@ -306,6 +306,8 @@ def other_configs(dev):
     out["cfg1_png_decode"] = keep(d, "chip_pairs_per_s", "decoded_GB/s")
     d = kbench.bench_decode(dev, "lzw")
     out["cfg3_lzw_geotiff_decode"] = keep(d, "chip_pairs_per_s", "decoded_GB/s")
+    d = kbench.bench_jpeg(dev)
+    out["cfg1_jpeg_decode"] = keep(d, "chip_pairs_per_s", "decoded_GB/s")
     torch.cuda.empty_cache()
     return out
 

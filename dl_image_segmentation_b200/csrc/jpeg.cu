@@ -22,11 +22,13 @@ const uint8_t h_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18
                               41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                               30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
-constexpr int kLook = 9;  // look-ahead bits
+constexpr int kLook = 10;  // look-ahead bits
 
-struct HuffTable {        // one (class, id) table in shared memory
+struct HuffTable {              // the DC or AC table of one component, in shared memory
     uint16_t look[1 << kLook];  // (length << 8) | symbol for codes of <= kLook bits, 0 = longer code
-    int32_t mincode[17], maxcode[17], valptr[17];
+    uint32_t lj[17];            // lj[l] = first 16-bit left-justified value beyond the codes of length <= l
+    int32_t base[17];           // symbol index of a length-l code = base[l] + code
+    uint8_t syms[256];
 };
 
 struct BitReader {
@@ -61,35 +63,37 @@ struct BitReader {
             n += 8;
         }
     }
-    __device__ __forceinline__ uint32_t peek(int k) {  // k <= 16
-        if (n < k) fill();
-        return (uint32_t)(acc >> (n - k)) & ((1u << k) - 1u);
+    // make at least 32 bits available: four stream bytes at once when none of them is 0xFF (no stuffing, no marker)
+    __device__ __forceinline__ void refill32() {
+        if (marker == 0 && p + 8 <= end) {
+            const uint32_t* a = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~uintptr_t(3));
+            const uint32_t lo = __ldg(a), hi = __ldg(a + 1);
+            const uint32_t x = __funnelshift_r(lo, hi, 8 * (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3));  // bytes p..p+3, LE
+            if ((((~x) - 0x01010101u) & x & 0x80808080u) == 0) {
+                acc = (acc << 32) | __byte_perm(x, 0, 0x0123);
+                n += 32;
+                p += 4;
+                return;
+            }
+        }
+        fill();
     }
-    __device__ __forceinline__ void skip(int k) { n -= k; }
-    __device__ __forceinline__ uint32_t get(int k) {
-        if (k == 0) return 0;
-        const uint32_t v = peek(k);
-        n -= k;
-        return v;
-    }
+    // the next 32 bits of the stream, left-aligned (call with n >= 32)
+    __device__ __forceinline__ uint32_t top32() const { return (uint32_t)(acc >> (n - 32)); }
 };
 
-__device__ __forceinline__ int huff_decode(BitReader& br, const HuffTable& t) {
-    if (br.n < 16) br.fill();
-    const uint32_t top16 = (uint32_t)(br.acc >> (br.n - 16)) & 0xFFFFu;
-    const uint32_t e = t.look[top16 >> (16 - kLook)];
-    if (e) {
-        br.n -= (int)(e >> 8);
-        return (int)(e & 0xFFu);
-    }
-    for (int l = kLook + 1; l <= 16; l++) {
-        const int code = (int)(top16 >> (16 - l));
-        if (t.maxcode[l] >= 0 && code <= t.maxcode[l] && code >= t.mincode[l]) {
-            br.n -= l;
-            return -1 - (t.valptr[l] + code - t.mincode[l]);  // index into the symbol list, resolved by the caller
-        }
-    }
-    return 1 << 20;  // no such code
+// code at the top of the left-aligned window w -> (length << 8) | symbol, or 0 for "no such code"
+__device__ __forceinline__ uint32_t huff_lookup(uint32_t w, const HuffTable& t) {
+    const uint32_t e = t.look[w >> (32 - kLook)];
+    if (e) return e;
+    // longer codes: canonical codes grow with their length, so the length is a count of comparisons (no branches,
+    // the loads are independent of one another)
+    const uint32_t t16 = w >> 16;
+    int l = kLook + 1;
+#pragma unroll
+    for (int i = kLook + 1; i < 16; i++) l += t16 >= t.lj[i];
+    if (t16 >= t.lj[16]) return 0;
+    return ((uint32_t)l << 8) | t.syms[(t.base[l] + (int)(t16 >> (16 - l))) & 255];
 }
 
 __device__ __forceinline__ int extend(uint32_t v, int s) { return (s && v < (1u << (s - 1))) ? (int)v - (1 << s) + 1 : (int)v; }
@@ -98,39 +102,46 @@ __device__ __forceinline__ int extend(uint32_t v, int s) { return (s && v < (1u 
 __global__ void __launch_bounds__(32) jpeg_entropy_kernel(const uint8_t* __restrict__ blob, const b2_jpeg_info* __restrict__ infos,
                                                           const b2_jpeg_job* __restrict__ jobs, int n_jobs,
                                                           int16_t* __restrict__ coef, int32_t* __restrict__ status) {
-    __shared__ HuffTable tabs[8];  // [class * 4 + id]
+    __shared__ HuffTable tabs[6];
+    __shared__ uint8_t zz[64];
     const int lane = threadIdx.x;
+    zz[lane] = c_zigzag[lane];
+    zz[lane + 32] = c_zigzag[lane + 32];
     for (int j = blockIdx.x; j < n_jobs; j += gridDim.x) {
         const b2_jpeg_info& fi = infos[j];
         const b2_jpeg_job job = jobs[j];
         __syncwarp();
-        // ---- tables: which (class, id) pairs the scan uses
-        uint32_t used = 0;
-        for (int c = 0; c < fi.components; c++) used |= (1u << fi.td[c]) | (1u << (4 + fi.ta[c]));
-        for (int slot = 0; slot < 8; slot++) {
-            if (!((used >> slot) & 1u)) continue;
+        // ---- tables: slot c = DC table of component c, slot 3 + c = its AC table
+        for (int slot = 0; slot < 6; slot++) {
+            const int c = slot % 3, cls = slot / 3;
+            if (c >= fi.components) continue;
+            const int id = cls ? fi.ta[c] : fi.td[c];
             HuffTable& t = tabs[slot];
-            const uint8_t* counts = fi.huff_counts[slot >> 2][slot & 3];
+            const uint8_t* counts = fi.huff_counts[cls][id];
+            const uint8_t* syms = fi.huff_syms[cls][id];
             for (int i = lane; i < (1 << kLook); i += 32) t.look[i] = 0;
+            for (int i = lane; i < 256; i += 32) t.syms[i] = syms[i];
+            __shared__ int32_t valptr[17], mincode[17];
             if (lane == 0) {
                 int code = 0, k = 0;
                 for (int l = 1; l <= 16; l++) {
-                    t.valptr[l] = k;
-                    t.mincode[l] = code;
+                    valptr[l] = k;
+                    mincode[l] = code;
+                    t.base[l] = k - code;
                     code += counts[l - 1];
                     k += counts[l - 1];
-                    t.maxcode[l] = counts[l - 1] ? code - 1 : -1;
+                    t.lj[l] = (uint32_t)code << (16 - l);
                     code <<= 1;
                 }
+                valptr[0] = k;  // total number of symbols
             }
             __syncwarp();
-            const uint8_t* syms = fi.huff_syms[slot >> 2][slot & 3];
-            const int total = t.valptr[16] + counts[15];
+            const int total = valptr[0];
             for (int k = lane; k < total; k += 32) {
                 int l = 1;
-                while (l < 16 && t.valptr[l + 1] <= k) l++;
+                while (l < 16 && valptr[l + 1] <= k) l++;
                 if (l <= kLook) {
-                    const int code = t.mincode[l] + (k - t.valptr[l]);
+                    const int code = mincode[l] + (k - valptr[l]);
                     const int first = code << (kLook - l), cnt = 1 << (kLook - l);
                     const uint16_t e = (uint16_t)((l << 8) | syms[k]);
                     for (int i = 0; i < cnt; i++) t.look[first + i] = e;
@@ -186,32 +197,38 @@ __global__ void __launch_bounds__(32) jpeg_entropy_kernel(const uint8_t* __restr
                 }
                 const int my = m / fi.mcus_across, mx = m - my * fi.mcus_across;
                 for (int c = 0; c < fi.components && !err; c++) {
-                    const HuffTable& dc = tabs[fi.td[c]];
-                    const HuffTable& ac = tabs[4 + fi.ta[c]];
-                    const uint8_t* dcs = fi.huff_syms[0][fi.td[c]];
-                    const uint8_t* acs = fi.huff_syms[1][fi.ta[c]];
+                    const HuffTable& dc = tabs[c];
+                    const HuffTable& ac = tabs[3 + c];
                     const int bw = fi.mcus_across * fi.h[c];
                     for (int by = 0; by < fi.v[c] && !err; by++)
                         for (int bx = 0; bx < fi.h[c]; bx++) {
                             int16_t* blk = coef + comp_base[c] + ((uint64_t)(my * fi.v[c] + by) * bw + mx * fi.h[c] + bx) * 64;
-                            int s = huff_decode(br, dc);
-                            if (s < 0) s = dcs[-1 - s];
-                            if (s > 11) {
+                            // one refill check, one table load and one shift pair per symbol: code and value bits
+                            // (<= 16 + 11) are both taken from the same left-aligned 32-bit window
+                            if (br.n < 32) br.refill32();
+                            uint32_t w = br.top32();
+                            uint32_t e = huff_lookup(w, dc);
+                            int l = (int)(e >> 8), s = (int)(e & 0xFFu);
+                            if (e == 0 || s > 11) {
                                 err = 2;
                                 break;
                             }
-                            pred[c] += extend(br.get(s), s);
+                            pred[c] += s ? extend((w << l) >> (32 - s), s) : 0;
+                            br.n -= l + s;
                             blk[0] = (int16_t)pred[c];
                             int k = 1;
                             while (k < 64) {
-                                int rs = huff_decode(br, ac);
-                                if (rs < 0) rs = acs[-1 - rs];
-                                if (rs > 255) {
+                                if (br.n < 32) br.refill32();
+                                w = br.top32();
+                                e = huff_lookup(w, ac);
+                                if (e == 0) {
                                     err = 2;
                                     break;
                                 }
-                                const int r = rs >> 4;
-                                s = rs & 15;
+                                l = (int)(e >> 8);
+                                const int r = (int)(e >> 4) & 15;
+                                s = (int)(e & 15u);
+                                br.n -= l + s;
                                 if (s == 0) {
                                     if (r != 15) break;
                                     k += 16;
@@ -222,7 +239,7 @@ __global__ void __launch_bounds__(32) jpeg_entropy_kernel(const uint8_t* __restr
                                     err = 2;
                                     break;
                                 }
-                                blk[c_zigzag[k]] = (int16_t)extend(br.get(s), s);
+                                blk[zz[k]] = (int16_t)extend((w << l) >> (32 - s), s);
                                 k++;
                             }
                             if (err) break;
