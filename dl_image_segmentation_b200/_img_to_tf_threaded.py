@@ -124,6 +124,9 @@ def _find_image_files(data_dir):
 def process_dataset_multithreaded(name, directory, out_directory, num_shards, num_threads=None,
                                   dltile_from_filename=True, convert_png_to_jpg=False, store_as_array=False):
     """Process a folder of PNG chips + label chips and save it as TFRecords (reference :321-350)."""
+    if convert_png_to_jpg:          # fail before any shard is touched rather than skip every chip one by one
+        raise NotImplementedError("convert_png_to_jpg: JPEG encoding is out of scope (its bytes depend on the libjpeg build "
+                                  "behind tf.image.encode_jpeg and cannot be pinned); .jpg chips themselves are handled")
     if not num_threads:
         num_threads = num_shards
     assert not num_shards % num_threads, ("Num shards must be a multiple of num threads (incl 1*)")

@@ -512,6 +512,8 @@ extern "C" int b2_jpeg_probe(const uint8_t* blob, uint64_t size, b2_jpeg_info* i
             if (nc != 1 && nc != 3) return probe_fail(3, "only 1- and 3-component JPEGs are in scope");
             if (sl < (uint64_t)6 + 3 * nc) return probe_fail(1, "short SOF");
             if (info->height == 0 || info->width == 0) return probe_fail(3, "DNL / empty frame");
+            // tf.image.decode_jpeg refuses frames of 2^29 bytes or more ("Image too large", jpeg_mem.cc)
+            if ((uint64_t)info->height * info->width * nc >= (1ull << 29)) return probe_fail(3, "image too large");
             info->components = nc;
             for (int c = 0; c < nc; c++) {
                 ids[c] = seg[6 + 3 * c];

@@ -119,6 +119,8 @@ def parse_jpeg(blob: bytes) -> dict:
         raise Unsupported("%d-component JPEG" % nc)
     if frame["height"] == 0 or frame["width"] == 0:
         raise Unsupported("DNL / empty frame")
+    if frame["height"] * frame["width"] * nc >= 1 << 29:
+        raise Unsupported("image too large")           # tf.image.decode_jpeg's own limit (jpeg_mem.cc)
     if ns != nc or [s[0] for s in sel] != [c["id"] for c in frame["comps"]]:
         raise Unsupported("multi-scan sequential JPEG")
     if (ss, se, ahal) != (0, 63, 0):

@@ -94,6 +94,12 @@ def test_host_probe_matches_oracle_parse():
     assert _codec.probe_jpeg(b"\xff\xd8\xff\xe0\x00")[0] == 1
     assert _codec.probe_jpeg(_case(CASES[0])[0][:200])[0] == 1           # cut inside the tables
     assert _codec.probe_jpeg(b"")[0] == 1
+    data = bytearray(_case("420_q90")[0])                                 # same file, frame header claiming 40000 x 40000
+    sof = data.index(b"\xff\xc0")
+    data[sof + 5:sof + 9] = (40000).to_bytes(2, "big") * 2
+    assert _codec.probe_jpeg(bytes(data))[0] == 3                        # refused like tf.image.decode_jpeg ("too large")
+    with pytest.raises(ojpg.Unsupported):
+        ojpg.parse_jpeg(bytes(data))
 
 
 # ---------------------------------------------------------------------------------------------- GPU: the kernels
@@ -136,6 +142,50 @@ def test_gpu_decode_error_behaviour(dev):
     ok, png = cv2.imencode(".png", want[..., ::-1])
     (a, b), st = _codec.decode_blobs([png.tobytes(), good], dev, png_as_tf=True)
     assert list(st) == [0, 0] and np.array_equal(a.cpu().numpy(), want) and np.array_equal(b.cpu().numpy(), want)
+
+
+@pytest.mark.gpu
+def test_mp_translator_and_loaders_on_jpg_chips(dev, tmp_path):
+    """images_to_tfrecords_mp(file_ext='jpg') (rasterio -> GDAL's JPEG driver = the same libjpeg) and the single-chip
+    loaders of both modules."""
+    import cv2
+    import dl_image_segmentation_b200 as pkg
+    from dl_image_segmentation_b200 import _img_to_tf_mp, _img_to_tf_threaded
+    from dl_image_segmentation_b200 import _tfrecord_image_translation as tr
+    from oracle import tfrecord as otfr
+    rng = np.random.default_rng(6)
+    d = tmp_path / "chips"
+    (d / "images").mkdir(parents=True)
+    (d / "labels").mkdir()
+    files = {}
+    for i in range(5):
+        name = "64#0#10.0#30#%d#%d.jpg" % (i, i + 3)
+        img, lab = _smooth(48, 40, 3, rng), (rng.integers(0, 2, (48, 40)) * 255).astype(np.uint8)
+        for sub, arr in (("images", img), ("labels", lab)):
+            ok, buf = cv2.imencode(".jpg", arr, [cv2.IMWRITE_JPEG_QUALITY, 90])
+            (d / sub / name).write_bytes(buf.tobytes())
+        files[name[:-4].replace("#", ":").encode()] = ((d / "images" / name).read_bytes(), (d / "labels" / name).read_bytes())
+    out = tmp_path / "out"
+    out.mkdir()
+    pkg.images_to_tfrecords_mp("jpgs", str(d), str(out), 1, num_proc=1, file_ext="jpg", store_as_array=True)
+    (shard,) = sorted(os.listdir(out))
+    recs = otfr.read_records(open(os.path.join(out, shard), "rb").read())
+    assert len(recs) == 5
+    for rec in recs:
+        img, tgt, ident = tr.parse_8bit_array_proto(rec, device=dev)
+        fi, fl = files[ident]
+        assert np.array_equal(img.cpu().numpy(), ojpg.decode_jpeg(fi)) and np.array_equal(tgt.cpu().numpy(), ojpg.decode_jpeg(fl)[..., 0])
+    path = str(d / "images" / "64#0#10.0#30#2#5.jpg")
+    want = ojpg.decode_jpeg(open(path, "rb").read())
+    arr, h, w, b, key = _img_to_tf_mp.load_image_rasterio(path, device=dev)
+    assert (h, w, b, key) == (48, 40, 3, "64:0:10.0:30:2:5") and np.array_equal(arr.cpu().numpy(), want)
+    raw, h, w, b, key = _img_to_tf_mp.load_image_rasterio(path, decode=False, device=dev)
+    assert raw == open(path, "rb").read() and (h, w, b) == (48, 40, 3)
+    coder = _img_to_tf_threaded.ImageCoder(device=dev)
+    arr, h, w, b, key = _img_to_tf_threaded._process_image(path, coder, decode=True)
+    assert (h, w, b, key) == (48, 40, 3, "64:0:10.0:30:2:5") and np.array_equal(arr.cpu().numpy(), want)
+    with pytest.raises(NotImplementedError):
+        pkg.images_to_tfrecords_mt("jpgs", str(d), str(out), 1, num_threads=1, convert_png_to_jpg=True)
 
 
 @pytest.mark.gpu
