@@ -145,6 +145,37 @@ def test_gpu_decode_error_behaviour(dev):
 
 
 @pytest.mark.gpu
+def test_gpu_decode_of_damaged_files_is_contained(dev):
+    """Bit flips and cuts in the entropy-coded segment: every file gets a status, no file disturbs its neighbours, a file
+    reported as fine has exactly the oracle's pixels, and whatever the oracle rejects (bad code, bad run, missing
+    restart marker) the GPU rejects too."""
+    from dl_image_segmentation_b200 import _codec
+    rng = np.random.default_rng(11)
+    blobs = []
+    for name in ("420_q90", "422_q75_rst", "411_q60_rst", "grey_q90"):
+        data, _ = _case(name)
+        scan = ojpg.parse_jpeg(data)["scan"]
+        for _ in range(30):
+            b = bytearray(data)
+            if rng.random() < 0.25:
+                b = b[:int(rng.integers(scan + 1, len(b)))]
+            for _ in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(scan, len(b)))] = int(rng.integers(0, 256))
+            blobs.append(bytes(b))
+        blobs.append(data)                                                  # an intact neighbour in every group
+    arrays, status, _ = _codec.decode_jpeg_blobs(blobs, dev)
+    assert set(status.tolist()) <= {0, 2} and (status == 0).sum() >= 4 and (status == 2).sum() >= 10
+    for b, a, st in zip(blobs, arrays, status):
+        try:
+            want = ojpg.decode_jpeg(b)
+        except ojpg.DecodeError:
+            assert st == 2
+            continue
+        if st == 0:
+            assert np.array_equal(a.cpu().numpy(), want)
+
+
+@pytest.mark.gpu
 def test_mp_translator_and_loaders_on_jpg_chips(dev, tmp_path):
     """images_to_tfrecords_mp(file_ext='jpg') (rasterio -> GDAL's JPEG driver = the same libjpeg) and the single-chip
     loaders of both modules."""
