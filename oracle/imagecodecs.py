@@ -10,6 +10,7 @@ PNG sections 5, 9; RFC 1950/1951 via the real ``zlib``).  Chip format written by
 ``_descartes_img_chips.py:781-797`` (GTiff, COMPRESS=LZW, TILED=TRUE -> 256x256 tiles, pixel
 interleaved, predictor 1).  Tests cross-check against libtiff (cv2, Pillow) and libpng (Pillow).
 """
+import os
 import struct
 import zlib
 
@@ -262,6 +263,18 @@ def decode_image(blob: bytes, png_as_tf: bool = True) -> np.ndarray:
         return decode_png(blob, png_as_tf)
     if blob[:2] in (b"II", b"MM"):
         return decode_tiff(blob)
+    if blob[:3] == b"\xff\xd8\xff":
+        if os.environ.get("B2_ORACLE_JPEG") == "libjpeg":     # CPU-baseline timing only: libjpeg-turbo itself (through cv2),
+            import cv2                                        # the library behind tf.image.decode_jpeg / GDAL's JPEG driver
+            a = cv2.imdecode(np.frombuffer(blob, np.uint8), cv2.IMREAD_UNCHANGED)
+            if a is None:
+                raise DecodeError("libjpeg could not decode the file")
+            return np.ascontiguousarray(a[..., ::-1]) if a.ndim == 3 else a[..., None]
+        from . import jpegcodec
+        try:
+            return jpegcodec.decode_jpeg(blob)
+        except jpegcodec.DecodeError as e:
+            raise DecodeError(str(e))
     raise DecodeError("unknown image format")
 
 
@@ -302,5 +315,8 @@ def image_shape(blob: bytes):
     if blob[:8] == _PNG_SIG:
         t = parse_png(blob)
         return t["height"], t["width"], {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[t["color_type"]]     # GDAL: a palette image is one band
+    if blob[:3] == b"\xff\xd8\xff":
+        from . import jpegcodec
+        return jpegcodec.jpeg_shape(blob)
     t = parse_tiff(blob)
     return t["height"], t["width"], t["spp"]

@@ -3,7 +3,7 @@
 TFRecord files, through the drop-in images_to_tfrecords_mp, next to the oracle restatement of the reference's
 multiprocessing CPU path (joblib over all host cores) on the same files.  Prints one JSON line per arm.
 
-    python tools/translate_bench.py [png|lzw] [n_pairs] [gpu_workers]
+    python tools/translate_bench.py [png|lzw|jpg] [n_pairs] [gpu_workers]
 """
 import json
 import os
@@ -24,12 +24,17 @@ def make_dataset(kind, n, root):
     from joblib import Parallel, delayed
     os.makedirs(os.path.join(root, "images"))
     os.makedirs(os.path.join(root, "labels"))
-    ext = "png" if kind == "png" else "tif"
+    ext = {"png": "png", "jpg": "jpg"}.get(kind, "tif")
 
     def one(i):
         if kind == "png":
             img, lab, key = syn.cfg1_chip(i)
             a, b = syn.png_bytes(img), syn.png_bytes(lab)
+        elif kind == "jpg":                    # quality 100, 4:2:0: what tf.image.encode_jpeg behind png_to_jpeg writes
+            import cv2
+            img, lab, key = syn.cfg1_chip(i)
+            a = cv2.imencode(".jpg", np.ascontiguousarray(img[..., ::-1]), [cv2.IMWRITE_JPEG_QUALITY, 100])[1].tobytes()
+            b = cv2.imencode(".jpg", lab, [cv2.IMWRITE_JPEG_QUALITY, 100])[1].tobytes()
         else:
             img, lab, key = syn.cfg3_chip(i)
             a, b = syn.tiff_bytes(img, tile=256), syn.tiff_bytes(lab, tile=256, nodata=255)
@@ -54,7 +59,9 @@ def make_dataset(kind, n, root):
 
 def main():
     kind = sys.argv[1] if len(sys.argv) > 1 else "png"
-    n = int(sys.argv[2]) if len(sys.argv) > 2 else (1536 if kind == "png" else 512)
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else (512 if kind == "lzw" else 1536)
+    if kind == "jpg":
+        os.environ["B2_ORACLE_JPEG"] = "libjpeg"                # CPU arm decodes with libjpeg-turbo itself, as TF would
     shards = 8
     workers = int(sys.argv[3]) if len(sys.argv) > 3 else 1      # GPU workers (num_proc): one host thread per GPU in this process
     base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
