@@ -303,64 +303,80 @@ def probe_jpeg(blob):
     return int(st), info
 
 
+class JpegPlan(ctypes.Structure):
+    _fields_ = [("stage_bytes", _u64), ("coef_count", _u64), ("plane_bytes", _u64), ("out_bytes", _u64),
+                ("n_jobs", ctypes.c_int32), ("filled", ctypes.c_int32)]
+
+
+_lib.register_signatures({
+    "b2_jpeg_plan_batch": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _u64, _i, ctypes.POINTER(JpegPlan)]),
+})
+
+_jpeg_tls = threading.local()      # per host thread: pinned staging for the files' bytes (a worker thread owns one GPU)
+
+
+def _jpeg_stage(nbytes):
+    buf = getattr(_jpeg_tls, "stage", None)
+    if buf is None or buf.numel() < nbytes:
+        buf = _jpeg_tls.stage = torch.empty((int(nbytes * 1.25) + 4096,), dtype=torch.uint8).pin_memory()
+    return buf
+
+
 def decode_jpeg_blobs(blobs, device=None, timings=None):
     """Decode a batch of baseline JPEG files on the GPU -> (arrays, status, infos): arrays[i] is an (H,W,1) or (H,W,3)
-    uint8 CUDA tensor (RGB), None where status[i] != 0.  Replaces tf.image.decode_jpeg behind ImageCoder.decode_jpeg
-    (reference _img_to_tf_threaded.py:36-38,51-56); the header walk is the only host work."""
+    uint8 CUDA tensor (RGB), None where status[i] != 0; infos[i] the file's JpegInfo (None if the header was refused).
+    Replaces tf.image.decode_jpeg behind ImageCoder.decode_jpeg (reference _img_to_tf_threaded.py:36-38,51-56).  All
+    per-file host work — the marker walk, the job table, the gather into pinned staging — is ONE native call."""
     ctx = get_ctx(device)
     n = len(blobs)
     status = np.zeros(n, np.int32)
     arrays = [None] * n
     infos = [None] * n
-    host = [_host_bytes(b) for b in blobs]
-    ok = []
-    for i, b in enumerate(host):
-        status[i], infos[i] = probe_jpeg(b)
-        if status[i] == 0:
-            ok.append(i)
-    if not ok:
+    if n == 0:
         return arrays, status, infos
-    m = len(ok)
-    jinfos = (JpegInfo * m)()
-    jobs = np.zeros(m, JPEG_JOB_DTYPE)
-    src = coef = plane = out = 0
-    cc, pb, ob = _u64(), _u64(), _u64()
-    for j, i in enumerate(ok):
-        jinfos[j] = infos[i]
-        check(lib().b2_jpeg_sizes(ctypes.byref(jinfos[j]), ctypes.byref(cc), ctypes.byref(pb), ctypes.byref(ob)))
-        jobs[j] = (src, coef, plane, out, host[i].size, j)
-        src = _align(src + host[i].size, 16)
-        coef += cc.value
-        plane = _align(plane + pb.value, 16)
-        out = _align(out + ob.value, 256)
-    stage = torch.empty((src,), dtype=torch.uint8).pin_memory()
-    sv = stage.numpy()
-    for j, i in enumerate(ok):
-        o = int(jobs[j]["src_off"])
-        sv[o:o + host[i].size] = host[i]
-    blob_d = stage.to(ctx.device, non_blocking=True)
-    info_h = np.frombuffer(jinfos, dtype=np.uint8)
-    info_d = torch.from_numpy(info_h.copy()).to(ctx.device)
-    jobs_d = torch.from_numpy(jobs.view(np.uint8).reshape(-1).copy()).to(ctx.device)
-    coef_d = torch.empty((max(coef, 1),), dtype=torch.int16, device=ctx.device)
-    planes_d = torch.empty((max(plane, 1),), dtype=torch.uint8, device=ctx.device)
-    out_d = torch.empty((max(out, 1),), dtype=torch.uint8, device=ctx.device)
-    st_d = torch.zeros((m,), dtype=torch.int32, device=ctx.device)
+    ptrs = (ctypes.c_void_p * n)()
+    sizes = np.zeros(n, np.uint64)
+    keep = []
+    for i, b in enumerate(blobs):
+        p, sz, k = _ptr_of(b)
+        ptrs[i], sizes[i] = p, sz
+        keep.append(k)
+    jinfos = (JpegInfo * n)()
+    jobs = np.zeros(n, JPEG_JOB_DTYPE)
+    plan = JpegPlan()
+    stage = _jpeg_stage(int(sizes.sum()) + 16 * n)               # an upper bound of stage_bytes: one call suffices
+    check(lib().b2_jpeg_plan_batch(ptrs, sizes.ctypes.data, n, jinfos, status.ctypes.data, jobs.ctypes.data,
+                                   stage.data_ptr(), stage.numel(), 0, ctypes.byref(plan)))
+    del keep
+    m = int(plan.n_jobs)
+    if m == 0:
+        return arrays, status, infos
+    if not plan.filled:
+        raise B2Error("b2_jpeg_plan_batch: staging buffer smaller than its own bound")
+    blob_d = stage[:plan.stage_bytes].to(ctx.device, non_blocking=True)
+    isz = ctypes.sizeof(JpegInfo)
+    info_d = torch.from_numpy(np.frombuffer(jinfos, dtype=np.uint8, count=m * isz)).to(ctx.device, non_blocking=True)
+    jobs_d = torch.from_numpy(jobs[:m].view(np.uint8).reshape(-1)).to(ctx.device, non_blocking=True)
+    coef_d = torch.empty((max(int(plan.coef_count), 1),), dtype=torch.int16, device=ctx.device)
+    planes_d = torch.empty((max(int(plan.plane_bytes), 1),), dtype=torch.uint8, device=ctx.device)
+    out_d = torch.empty((max(int(plan.out_bytes), 1),), dtype=torch.uint8, device=ctx.device)
+    st_d = torch.zeros((n,), dtype=torch.int32, device=ctx.device)
     if timings is not None:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         ev[0].record()
     check(lib().b2_jpeg_decode(ctx.handle, ptr(blob_d), ptr(info_d), ctypes.addressof(jinfos), ptr(jobs_d), jobs.ctypes.data, m,
-                               ptr(coef_d), coef, ptr(planes_d), ptr(out_d), ptr(st_d), ctx.stream()))
+                               ptr(coef_d), int(plan.coef_count), ptr(planes_d), ptr(out_d), ptr(st_d), ctx.stream()))
     if timings is not None:
         ev[1].record()
         torch.cuda.synchronize()
-        timings.update(decode_ms=ev[0].elapsed_time(ev[1]), compressed_bytes=int(sum(host[i].size for i in ok)),
-                       decoded_bytes=int(sum(infos[i].width * infos[i].height * infos[i].components for i in ok)), files=m)
-    st = st_d.cpu().numpy()                                   # also orders the pinned staging buffer's release
-    for j, i in enumerate(ok):
-        status[i] = st[j]
-        if st[j] == 0:
-            fi = infos[i]
+        timings.update(decode_ms=ev[0].elapsed_time(ev[1]), compressed_bytes=int(jobs["src_len"][:m].sum()),
+                       decoded_bytes=int(sum(jinfos[j].width * jinfos[j].height * jinfos[j].components for j in range(m))), files=m)
+    st = st_d.cpu().numpy()                                   # also: the uploads out of the pinned buffers have finished
+    for j in range(m):
+        i = int(jobs[j]["image"])
+        fi = infos[i] = jinfos[j]
+        status[i] = st[i]
+        if st[i] == 0:
             o = int(jobs[j]["out_off"])
             arrays[i] = out_d[o:o + fi.width * fi.height * fi.components].view(fi.height, fi.width, fi.components)
     return arrays, status, infos
@@ -383,7 +399,8 @@ def jpeg_as_image_info(jinfo, status) -> ImageInfo:
     """The fields of ImageInfo the translators read, for a chip that went through the JPEG path."""
     info = ImageInfo()
     info.format, info.status, info.dtype = FORMAT_JPEG, int(status), _lib.B2_U8
-    info.width, info.height, info.samples = jinfo.width, jinfo.height, jinfo.components
+    if jinfo is not None:
+        info.width, info.height, info.samples = jinfo.width, jinfo.height, jinfo.components
     info.geotransform[:] = (0.0, 1.0, 0.0, 0.0, 0.0, 1.0)     # GDAL's default for a file without georeferencing
     return info
 

@@ -2,12 +2,13 @@
 // Replaces tf.image.decode_jpeg behind ImageCoder.decode_jpeg (_img_to_tf_threaded.py:36-38,51-56,97-103): libjpeg's
 // default pipeline — Huffman decode (ITU-T T.81 Annex F), accurate integer inverse DCT, triangle-filter chroma
 // upsampling, fixed-point YCbCr -> RGB — restated for the GPU in three kernels:
-//   jpeg_entropy_kernel   one warp per file; the warp builds 9-bit look-ahead tables in shared memory, lane 0 walks the
+//   jpeg_entropy_kernel   one warp per file; the warp builds 10-bit look-ahead tables in shared memory, lane 0 walks the
 //                         bit stream (the only serial part) and scatters the non-zero coefficients of each block
 //   jpeg_idct_kernel      one thread per 8x8 block: dequantise + column pass + row pass in registers, 8-byte row stores
 //   jpeg_colour_kernel    one thread per output pixel: upsample every component at that pixel, convert, write HWC
 #include <string.h>
 
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -581,6 +582,70 @@ extern "C" int b2_jpeg_sizes(const b2_jpeg_info* info, uint64_t* coef_count, uin
     if (coef_count) *coef_count = blocks * 64;
     if (plane_bytes) *plane_bytes = blocks * 64;
     if (out_bytes) *out_bytes = (uint64_t)info->width * info->height * info->components;
+    return 0;
+}
+
+extern "C" int b2_jpeg_plan_batch(const uint8_t* const* blobs, const uint64_t* sizes, int n, b2_jpeg_info* infos_out,
+                                  int32_t* status_out, b2_jpeg_job* jobs_out, uint8_t* stage_host, uint64_t stage_cap,
+                                  int n_threads, b2_jpeg_plan* plan) {
+    B2_REQUIRE(n >= 0 && plan && (n == 0 || (blobs && sizes && infos_out && status_out && jobs_out)),
+               "b2_jpeg_plan_batch: NULL argument");
+    memset(plan, 0, sizeof(*plan));
+    if (n == 0) {
+        plan->filled = 1;
+        return 0;
+    }
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = nt < 1 ? 1 : (nt > 32 ? 32 : nt);
+    if (nt > n) nt = n;
+    std::vector<b2_jpeg_info> all((size_t)n);
+    auto run = [&](auto&& fn) {  // fn(first, last) over [0, n) on nt threads
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(fn, (int)((int64_t)n * t / nt), (int)((int64_t)n * (t + 1) / nt));
+        fn(0, (int)((int64_t)n / nt));
+        for (auto& x : th) x.join();
+    };
+    run([&](int a, int b) {
+        for (int i = a; i < b; i++) status_out[i] = b2_jpeg_probe(blobs[i], sizes[i], &all[i]);
+    });
+    uint64_t src = 0, coef = 0, plane = 0, out = 0;
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        if (status_out[i] != 0) continue;
+        uint64_t cc = 0, pb = 0, ob = 0;
+        b2_jpeg_sizes(&all[i], &cc, &pb, &ob);
+        B2_REQUIRE(sizes[i] <= 0xFFFFFFFFull, "b2_jpeg_plan_batch: file larger than 4 GiB");
+        infos_out[m] = all[i];
+        b2_jpeg_job& j = jobs_out[m];
+        j.src_off = src;
+        j.coef_off = coef;
+        j.plane_off = plane;
+        j.out_off = out;
+        j.src_len = (uint32_t)sizes[i];
+        j.image = i;
+        src = (src + sizes[i] + 15) & ~15ull;
+        coef += cc;
+        plane = (plane + pb + 15) & ~15ull;
+        out = (out + ob + 255) & ~255ull;
+        m++;
+    }
+    plan->stage_bytes = src;
+    plan->coef_count = coef;
+    plan->plane_bytes = plane;
+    plan->out_bytes = out;
+    plan->n_jobs = m;
+    if (stage_host && stage_cap >= src) {
+        const int jobs_n = m;
+        n = jobs_n;  // run() partitions [0, n)
+        if (n > 0) {
+            if (nt > n) nt = n;
+            run([&](int a, int b) {
+                for (int j = a; j < b; j++) memcpy(stage_host + jobs_out[j].src_off, blobs[jobs_out[j].image], jobs_out[j].src_len);
+            });
+        }
+        plan->filled = 1;
+    }
+    set_error("");  // per-file probe failures are data (status_out), not an error of this call
     return 0;
 }
 

@@ -347,6 +347,24 @@ typedef struct {
 int b2_jpeg_probe(const uint8_t* blob, uint64_t size, b2_jpeg_info* info);
 /* Host-side: int16 coefficients, bytes of padded component planes and bytes of the (H,W,components) result. */
 int b2_jpeg_sizes(const b2_jpeg_info* info, uint64_t* coef_count, uint64_t* plane_bytes, uint64_t* out_bytes);
+typedef struct {
+    uint64_t stage_bytes;  /* host staging buffer needed for the files' bytes (each file 16-byte aligned)           */
+    uint64_t coef_count;   /* int16 coefficients of all jobs                                                       */
+    uint64_t plane_bytes;  /* padded component planes of all jobs                                                  */
+    uint64_t out_bytes;    /* (H,W,components) results, each 256-byte aligned                                      */
+    int32_t n_jobs;        /* files that passed b2_jpeg_probe                                                      */
+    int32_t filled;        /* 1: stage_host was large enough and holds the bytes                                   */
+} b2_jpeg_plan;
+
+/* Host-side, multi-threaded: b2_jpeg_probe + b2_jpeg_sizes for a whole batch of files in ONE call, the job table and the
+ * gather of the files' bytes into one (pinned) staging buffer — the per-file header read of the reference's worker
+ * loop (_img_to_tf_threaded.py:87-105) without ~20 us of interpreter time per file.  status_out[i] (one per file) is
+ * the probe's; infos_out / jobs_out are compact (n_jobs entries, input order), jobs_out[j].image = the file's index i.
+ * With stage_host == NULL or stage_cap too small only sizes, infos and jobs are produced (filled = 0). */
+int b2_jpeg_plan_batch(const uint8_t* const* blobs, const uint64_t* sizes, int n, b2_jpeg_info* infos_out,
+                       int32_t* status_out, b2_jpeg_job* jobs_out, uint8_t* stage_host, uint64_t stage_cap,
+                       int n_threads, b2_jpeg_plan* plan);
+
 /* Entropy decode (one warp per file) -> inverse DCT (one thread per 8x8 block) -> upsample + colour conversion (one
  * thread per pixel).  coef_dev must hold coef_count int16 (zeroed here), infos / jobs are given both as device and as
  * host arrays (the host copy sizes the launches).  status_dev as for b2_decode_streams: 2 = corrupt entropy data. */

@@ -102,6 +102,41 @@ def test_host_probe_matches_oracle_parse():
         ojpg.parse_jpeg(bytes(data))
 
 
+def test_host_batch_planner_matches_per_file_calls():
+    """b2_jpeg_plan_batch = b2_jpeg_probe + b2_jpeg_sizes per file, compacted, with the bytes gathered (no GPU involved)."""
+    import ctypes
+    from dl_image_segmentation_b200 import _codec
+    from dl_image_segmentation_b200._lib import lib
+    prog = open(os.path.join(G, "jpeg_progressive.jpg"), "rb").read()
+    blobs = [_case(CASES[0])[0], prog, b"", _case(CASES[1])[0], b"junk", _case(CASES[2])[0]] * 9
+    n = len(blobs)
+    ptrs = (ctypes.c_void_p * n)()
+    sizes = np.zeros(n, np.uint64)
+    keep = []
+    for i, b in enumerate(blobs):
+        ptrs[i], sizes[i], k = _codec._ptr_of(b)
+        keep.append(k)
+    infos, jobs, status = (_codec.JpegInfo * n)(), np.zeros(n, _codec.JPEG_JOB_DTYPE), np.zeros(n, np.int32)
+    plan = _codec.JpegPlan()
+    for stage in (None, np.zeros(int(sizes.sum()) + 16 * n, np.uint8)):
+        assert lib().b2_jpeg_plan_batch(ptrs, sizes.ctypes.data, n, infos, status.ctypes.data, jobs.ctypes.data,
+                                        stage.ctypes.data if stage is not None else None, stage.size if stage is not None else 0,
+                                        3, ctypes.byref(plan)) == 0
+        assert list(status) == [0, 3, 1, 0, 1, 0] * 9 and plan.n_jobs == 27 and plan.filled == (stage is not None)
+    ok = [i for i in range(n) if status[i] == 0]
+    src = coef = plane = out = 0
+    cc, pb, ob = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+    for j, i in enumerate(ok):
+        st, want = _codec.probe_jpeg(blobs[i])
+        assert bytes(infos[j]) == bytes(want)
+        assert tuple(jobs[j]) == (src, coef, plane, out, len(blobs[i]), i)
+        assert stage[src:src + len(blobs[i])].tobytes() == blobs[i]
+        lib().b2_jpeg_sizes(ctypes.byref(want), ctypes.byref(cc), ctypes.byref(pb), ctypes.byref(ob))
+        src, coef = (src + len(blobs[i]) + 15) & ~15, coef + cc.value
+        plane, out = (plane + pb.value + 15) & ~15, (out + ob.value + 255) & ~255
+    assert (plan.stage_bytes, plan.coef_count, plan.plane_bytes, plan.out_bytes) == (src, coef, plane, out)
+
+
 # ---------------------------------------------------------------------------------------------- GPU: the kernels
 @pytest.mark.gpu
 def test_gpu_decode_matches_golden_and_oracle(dev):
