@@ -405,6 +405,70 @@ def jpeg_as_image_info(jinfo, status) -> ImageInfo:
     return info
 
 
+JPEG_ENC_JOB_DTYPE = np.dtype([("src_off", "<u8"), ("coef_off", "<u8"), ("out_off", "<u8"), ("out_cap", "<u4"),
+                               ("width", "<i4"), ("height", "<i4"), ("components", "<i4")])
+TF_JPEG_DENSITY = (1, 300, 300)    # tf.image.encode_jpeg's defaults: density_unit 'in', x_density = y_density = 300
+
+_lib.register_signatures({
+    "b2_jpeg_header": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _u64, ctypes.POINTER(_u64)]),
+    "b2_jpeg_encode_sizes": (_i, [_i, _i, _i, ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
+    "b2_jpeg_encode_scan": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _u64, _vp, _vp, _vp]),
+})
+
+
+def jpeg_header(height, width, components, quality=100, density=TF_JPEG_DENSITY) -> bytes:
+    """SOI .. SOS of the file libjpeg writes for these settings (host only)."""
+    buf = (ctypes.c_uint8 * 1024)()
+    ln = _u64()
+    check(lib().b2_jpeg_header(height, width, components, quality, density[0], density[1], density[2], buf, 1024, ctypes.byref(ln)))
+    return bytes(buf[:ln.value])
+
+
+def encode_jpeg_arrays(arrays, quality=100, density=TF_JPEG_DENSITY, device=None):
+    """Encode a batch of (H,W,1) / (H,W,3) uint8 images (CUDA tensors or host arrays) as baseline JPEG files on the GPU
+    -> list of bytes.  Replaces tf.image.encode_jpeg(image, format='', quality=100) behind ImageCoder.png_to_jpeg
+    (reference _img_to_tf_threaded.py:36-38): grey -> one component, RGB -> YCbCr 4:2:0, standard Huffman tables."""
+    ctx = get_ctx(device)
+    n = len(arrays)
+    if n == 0:
+        return []
+    jobs = np.zeros(n, JPEG_ENC_JOB_DTYPE)
+    flat = []
+    src = coef = out = 0
+    cc, cap = _u64(), _u64()
+    for j, a in enumerate(arrays):
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+        if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] not in (1, 3):
+            raise B2Error("encode_jpeg_arrays: (H,W,1) or (H,W,3) uint8 images only (tf.image.encode_jpeg, format='')")
+        h, w, c = (int(x) for x in t.shape)
+        check(lib().b2_jpeg_encode_sizes(h, w, c, ctypes.byref(cc), ctypes.byref(cap)))
+        jobs[j] = (src, coef, out, cap.value, w, h, c)
+        flat.append(t.to(ctx.device, non_blocking=True).contiguous().reshape(-1))
+        pad = (-t.numel()) % 16
+        if pad:
+            flat.append(torch.zeros((pad,), dtype=torch.uint8, device=ctx.device))
+        src += t.numel() + pad
+        coef += cc.value
+        out = _align(out + cap.value, 16)
+    pixels = torch.cat(flat)
+    jobs_d = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(ctx.device)
+    coef_d = torch.empty((coef,), dtype=torch.int16, device=ctx.device)
+    out_d = torch.empty((out,), dtype=torch.uint8, device=ctx.device)
+    len_d = torch.zeros((n,), dtype=torch.int32, device=ctx.device)
+    check(lib().b2_jpeg_encode_scan(ctx.handle, ptr(pixels), ptr(jobs_d), jobs.ctypes.data, n, int(quality), ptr(coef_d), coef,
+                                    ptr(out_d), ptr(len_d), ctx.stream()))
+    lens = len_d.cpu().numpy().view(np.uint32)
+    files = []
+    for j in range(n):
+        if lens[j] == 0xFFFFFFFF:
+            raise B2Error("b2_jpeg_encode_scan: scan buffer too small (its own bound)")
+        o = int(jobs[j]["out_off"])
+        scan = out_d[o:o + int(lens[j])].cpu().numpy().tobytes()
+        files.append(jpeg_header(int(jobs[j]["height"]), int(jobs[j]["width"]), int(jobs[j]["components"]), quality, density)
+                     + scan + b"\xff\xd9")
+    return files
+
+
 def to_float32(t):
     """.astype(np.float32) of a decoded chip (reference :328-329) via the cast kernel (mean 0, std 1)."""
     from . import ops

@@ -3,8 +3,9 @@
 Same names and arguments as the reference; ``num_threads`` counts GPU workers.  Kept: ``*.png`` then ``*.jpg``
 discovery and the seeded shuffle (``:297-314``), the always-validate rule (3-D, at most 3 bands, ``:105-112``) even
 when the raw bytes are stored, the substring ``_is_png`` test (``:72``), skip-and-continue (``:190-199``), progress
-every 1000 chips (``:207-210``).  JPEG (``convert_png_to_jpg`` and ``.jpg`` chips) is a lossy DCT codec outside the
-north-star path: such chips raise inside the worker and are therefore skipped with the reference's message.
+every 1000 chips (``:207-210``).  ``.jpg`` chips are decoded and ``convert_png_to_jpg`` transcodes on the GPU with
+libjpeg's arithmetic (``csrc/jpeg.cu``, ``csrc/jpeg_enc.cu``); progressive / CMYK / 12-bit JPEGs are skipped with the
+reference's message.
 """
 import glob
 import os
@@ -22,8 +23,11 @@ class ImageCoder(object):
         self.device = device
 
     def png_to_jpeg(self, image_data):
-        raise NotImplementedError("JPEG encoding (convert_png_to_jpg) is out of scope: its bytes depend on the libjpeg "
-                                  "build behind tf.image.encode_jpeg and cannot be pinned (SURVEY.md section 8f row 4)")
+        # tf.image.encode_jpeg(tf.image.decode_png(image_data), format='', quality=100)  (reference :36-38)
+        image = self.decode_png(image_data)
+        if image.shape[2] not in (1, 3):
+            raise _translate.ChipError("encode_jpeg: image must have 1 or 3 channels, has %d" % int(image.shape[2]))
+        return _codec.encode_jpeg_arrays([image], quality=100, device=self.device)[0]
 
     def decode_jpeg(self, image_data):
         (image,), (st,), _ = _codec.decode_jpeg_blobs([image_data], device=self.device)           # tf.image.decode_jpeg
@@ -78,14 +82,13 @@ def _process_image_files_worker(coder, thread_index, ranges, name, filenames, la
         return _translate.tile_key_from_path(p, dltile_from_filename)
 
     def validate(info):
-        if png_to_jpg:
-            raise NotImplementedError("convert_png_to_jpg: JPEG is out of scope of the B200 hot path")
         if info.format not in (2, _codec.FORMAT_JPEG):
             raise NotImplementedError("only PNG and JPEG chips are handled by the threaded translator on the GPU")
         _validate(info)
     return _translate.run_worker(thread_index, ranges, name, filenames, labels, out_folder, num_shards, key_fn,
                                  store_as_array, label="thread", progress_every=1000, validate=validate, device=device,
-                                 png_as_tf=True)                     # this translator decodes with tf.image.decode_png
+                                 png_as_tf=True,                     # this translator decodes with tf.image.decode_png
+                                 png_to_jpg=png_to_jpg)
 
 
 def _process_image_files(name, img_files, lbl_files, out_folder, num_shards, num_threads, dltile_from_filename,
@@ -124,9 +127,6 @@ def _find_image_files(data_dir):
 def process_dataset_multithreaded(name, directory, out_directory, num_shards, num_threads=None,
                                   dltile_from_filename=True, convert_png_to_jpg=False, store_as_array=False):
     """Process a folder of PNG chips + label chips and save it as TFRecords (reference :321-350)."""
-    if convert_png_to_jpg:          # fail before any shard is touched rather than skip every chip one by one
-        raise NotImplementedError("convert_png_to_jpg: JPEG encoding is out of scope (its bytes depend on the libjpeg build "
-                                  "behind tf.image.encode_jpeg and cannot be pinned); .jpg chips themselves are handled")
     if not num_threads:
         num_threads = num_shards
     assert not num_shards % num_threads, ("Num shards must be a multiple of num threads (incl 1*)")

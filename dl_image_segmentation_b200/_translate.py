@@ -97,7 +97,7 @@ def _read_or_error(path):
 
 
 def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, device=None, blobs=None, png_as_tf=False,
-               planned=None):
+               planned=None, png_to_jpg=False):
     """Read + (optionally) decode a batch of chip pairs.  Returns one entry per pair: a dict ready for
     ops.build_records, or the Exception that makes the reference skip the chip.  `blobs` = the 2n file contents
     (image, label, image, label, ...) when the caller has already read them (run_worker prefetches on threads);
@@ -115,6 +115,24 @@ def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, devi
                 errs[k // 2] = b
             blobs[k] = b""
     arrays = [None] * (2 * n)
+    if png_to_jpg:
+        # convert_png_to_jpg (_img_to_tf_threaded.py:92-95): every PNG chip becomes the JPEG that
+        # tf.image.encode_jpeg(decode_png(data), format='', quality=100) writes; the record then carries that file (or
+        # its decoded pixels), exactly as if the chip had been a .jpg
+        blobs = list(blobs)
+        pa, pst, pinfos = _codec.decode_blobs(blobs, ctx.device, want_infos=True, png_as_tf=png_as_tf)
+        todo = [k for k in range(2 * n) if pinfos[k].format == 2 and pinfos[k].status == 0 and pst[k] == 0
+                and pa[k].shape[2] in (1, 3)]
+        for k in range(2 * n):                                              # 2 / 4 channels: encode_jpeg refuses them
+            if pinfos[k].format == 2 and pinfos[k].status == 0 and pst[k] == 0 and k not in todo and errs[k // 2] is None:
+                errs[k // 2] = ChipError("encode_jpeg: image must have 1 or 3 channels (%s)" % (img_paths, lbl_paths)[k % 2][k // 2])
+        for k, f in zip(todo, _codec.encode_jpeg_arrays([pa[k] for k in todo], quality=100, device=ctx.device)):
+            print("Converting PNG to JPEG for %s" % (img_paths, lbl_paths)[k % 2][k // 2])
+            blobs[k] = f
+        if planned is not None and planned.hs is not None:
+            planned.hs.pending = False                                      # planned from the PNG bytes: give its staging set back
+        planned = None
+        del pa
     if store_as_array:                                                      # ONE native planning call + the decode kernels
         if planned is None:
             planned = _codec.plan_blobs(blobs, ctx.device, png_as_tf)
@@ -161,7 +179,7 @@ def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, devi
 
 def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_directory, num_shards, key_fn,
                store_as_array, label="process", progress_every=100, validate=None, device=None, batch_pairs=None,
-               io_threads=8, png_as_tf=False):
+               io_threads=8, png_as_tf=False, png_to_jpg=False):
     """The reference's worker loop, restructured as a three-stage pipeline: a thread pool reads the files of batch
     k+1 while the GPU decodes and serialises batch k and a writer thread appends batch k-1 to the shard file."""
     from concurrent.futures import ThreadPoolExecutor
@@ -212,7 +230,7 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
         def read_and_plan(paths):
             blobs = reader.read(paths)                                      # one native call; the GIL is free meanwhile
             planned = None
-            if store_as_array:                                              # host half of the decode, off the main thread
+            if store_as_array and not png_to_jpg:                           # host half of the decode, off the main thread
                 planned = _codec.plan_blobs([b"" if isinstance(b, Exception) else b for b in blobs], ctx.device, png_as_tf)
             return blobs, planned
 
@@ -227,7 +245,8 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
             pending_reads = submit_reads(batches[bi + 1]) if bi + 1 < len(batches) else None
             idx = list(range(b0, b1))
             pairs = load_pairs([img_filenames[i] for i in idx], [lbl_filenames[i] for i in idx], store_as_array,
-                               key_fn, validate, ctx.device, blobs=blobs, png_as_tf=png_as_tf, planned=planned)
+                               key_fn, validate, ctx.device, blobs=blobs, png_as_tf=png_as_tf, planned=planned,
+                               png_to_jpg=png_to_jpg)
             for s in range(per):
                 lo, hi = max(b0, int(shard_ranges[s])), min(b1, int(shard_ranges[s + 1]))
                 if lo >= hi:

@@ -372,6 +372,31 @@ int b2_jpeg_decode(b2_ctx* ctx, const uint8_t* blob_dev, const b2_jpeg_info* inf
                    const b2_jpeg_job* jobs_dev, const b2_jpeg_job* jobs_host, int n, int16_t* coef_dev,
                    uint64_t coef_count, uint8_t* planes_dev, uint8_t* out_dev, int32_t* status_dev, b2_stream stream);
 
+/* ------------------------------------------------------------------ K1je: baseline JPEG encode
+ * Replace tf.image.encode_jpeg(image, format='', quality=100) behind ImageCoder.png_to_jpeg
+ * (_img_to_tf_threaded.py:36-38), the convert_png_to_jpg option of images_to_tfrecords_mt (:92-95): libjpeg's
+ * compressor with default settings (4:2:0 for RGB, standard Huffman tables, JFIF header).  Scan bytes are identical to
+ * libjpeg-turbo's; TensorFlow's header differs from a plain libjpeg one only in the JFIF density fields (unit 1,
+ * 300 x 300), which b2_jpeg_header takes as arguments. */
+typedef struct {
+    uint64_t src_off;   /* (H,W,components) uint8 pixels in pixels_dev                                              */
+    uint64_t coef_off;  /* int16 index into coef_dev: 64 per block, blocks in coding order                           */
+    uint64_t out_off;   /* where the scan bytes go in out_dev                                                       */
+    uint32_t out_cap;   /* b2_jpeg_encode_sizes' scan_cap always suffices                                           */
+    int32_t width, height, components; /* 1 (grey) or 3 (RGB)                                                       */
+} b2_jpeg_enc_job;
+
+/* Host-side: SOI, JFIF APP0, DQT, SOF0, DHT, SOS — everything before the scan bytes (the file ends with FF D9). */
+int b2_jpeg_header(int height, int width, int components, int quality, int density_unit, int x_density, int y_density,
+                   uint8_t* out, uint64_t cap, uint64_t* len);
+/* Host-side: int16 coefficients and an upper bound of the scan bytes of one image. */
+int b2_jpeg_encode_sizes(int height, int width, int components, uint64_t* coef_count, uint64_t* scan_cap);
+/* Colour conversion + down-sampling + forward DCT + quantisation (one thread per block), then Huffman coding with byte
+ * stuffing (one warp per image).  out_len_dev[j] = scan bytes of image j, 0xFFFFFFFF if out_cap was too small. */
+int b2_jpeg_encode_scan(b2_ctx* ctx, const uint8_t* pixels_dev, const b2_jpeg_enc_job* jobs_dev,
+                        const b2_jpeg_enc_job* jobs_host, int n, int quality, int16_t* coef_dev, uint64_t coef_count,
+                        uint8_t* out_dev, uint32_t* out_len_dev, b2_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import jpegcodec as ojpg
+from oracle import jpegenc as ojenc
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(G, "jpeg_*.npy")))
@@ -137,7 +138,98 @@ def test_host_batch_planner_matches_per_file_calls():
     assert (plan.stage_bytes, plan.coef_count, plan.plane_bytes, plan.out_bytes) == (src, coef, plane, out)
 
 
+def _enc_cases(seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for (h, w) in [(16, 16), (24, 40), (17, 33), (64, 64), (5, 7), (1, 1), (100, 130)]:
+        out += [rng.integers(0, 256, (h, w, 3), dtype=np.uint8), _smooth(h, w, 3, rng), _smooth(h, w, 1, rng)]
+    return out
+
+
+def test_encoder_oracle_is_byte_identical_to_libjpeg_turbo():
+    """The whole file, header included, against cv2.imencode (libjpeg-turbo) at several qualities; cv2 writes JFIF
+    density 1 x 1 without a unit, TensorFlow 300 x 300 dpi — the only bytes that differ."""
+    import cv2
+    for img in _enc_cases(7):
+        for q in (100, 90, 50, 20):
+            ok, buf = cv2.imencode(".jpg", img[..., ::-1] if img.shape[2] == 3 else img[..., 0], [cv2.IMWRITE_JPEG_QUALITY, q])
+            got = ojenc.encode_jpeg(img, q, density=(0, 1, 1))
+            assert got == buf.tobytes(), (img.shape, q)
+            tf_like = ojenc.encode_jpeg(img, q)
+            assert tf_like[:13] == got[:13] and tf_like[13:18] == b"\x01\x01\x2c\x01\x2c" and tf_like[18:] == got[18:]
+            assert np.array_equal(ojpg.decode_jpeg(tf_like), ojpg.decode_jpeg(got))
+
+
+def test_host_header_matches_oracle_header():
+    from dl_image_segmentation_b200 import _codec
+    for (h, w, c, q) in [(256, 256, 3, 100), (17, 33, 1, 75), (65535, 1, 3, 1), (40, 48, 3, 50)]:
+        for dens in ((1, 300, 300), (0, 1, 1)):
+            assert _codec.jpeg_header(h, w, c, q, dens) == ojenc.header(h, w, c, ojenc.quant_tables(q), dens)
+
+
 # ---------------------------------------------------------------------------------------------- GPU: the kernels
+@pytest.mark.gpu
+def test_gpu_encode_is_byte_identical_to_libjpeg_turbo_and_oracle(dev):
+    import cv2
+    import torch
+    from dl_image_segmentation_b200 import _codec
+    imgs = _enc_cases(8) + [np.random.default_rng(1).integers(0, 256, (256, 256, 3), dtype=np.uint8)]
+    for q in (100, 60):
+        files = _codec.encode_jpeg_arrays([torch.from_numpy(i).to(dev) for i in imgs], quality=q, density=(0, 1, 1), device=dev)
+        for img, f in zip(imgs, files):
+            ok, buf = cv2.imencode(".jpg", img[..., ::-1] if img.shape[2] == 3 else img[..., 0], [cv2.IMWRITE_JPEG_QUALITY, q])
+            assert f == buf.tobytes(), (img.shape, q)
+    files = _codec.encode_jpeg_arrays(imgs[:6], device=dev)                         # host arrays in, TensorFlow's header
+    for img, f in zip(imgs, files):
+        assert f == ojenc.encode_jpeg(img)
+    arrays, status, _ = _codec.decode_jpeg_blobs(files, dev)                        # and back through the decoder
+    assert not status.any()
+    for a, f in zip(arrays, files):
+        assert np.array_equal(a.cpu().numpy(), ojpg.decode_jpeg(f))
+
+
+@pytest.mark.gpu
+def test_convert_png_to_jpg_translator(dev, tmp_path):
+    """images_to_tfrecords_mt(convert_png_to_jpg=True): records carry encode_jpeg(decode_png(file), quality=100) — bytes
+    or decoded pixels — for image and label alike (reference :92-95 applies to both)."""
+    import cv2
+    import dl_image_segmentation_b200 as pkg
+    from dl_image_segmentation_b200 import _img_to_tf_threaded
+    from dl_image_segmentation_b200 import _tfrecord_image_translation as tr
+    from oracle import example_proto as oep
+    from oracle import tfrecord as otfr
+    rng = np.random.default_rng(9)
+    d = tmp_path / "chips"
+    (d / "images").mkdir(parents=True)
+    (d / "labels").mkdir()
+    want = {}
+    for i in range(5):
+        key = "64:0:10.0:30:%d:%d" % (i, 2 * i)
+        img, lab = _smooth(40, 56, 3, rng), (rng.integers(0, 4, (40, 56)) * 60).astype(np.uint8)
+        for sub, arr in (("images", img[..., ::-1]), ("labels", lab)):
+            ok, buf = cv2.imencode(".png", np.ascontiguousarray(arr))
+            (d / sub / (key.replace(":", "#") + ".png")).write_bytes(buf.tobytes())
+        want[key.encode()] = (ojenc.encode_jpeg(img), ojenc.encode_jpeg(lab))
+    coder = _img_to_tf_threaded.ImageCoder(device=dev)
+    png = (d / "images" / "64#0#10.0#30#1#2.png").read_bytes()
+    assert coder.png_to_jpeg(png) == want[b"64:0:10.0:30:1:2"][0]
+    for as_array in (False, True):
+        out = tmp_path / ("out%d" % as_array)
+        out.mkdir()
+        pkg.images_to_tfrecords_mt("j", str(d), str(out), 1, num_threads=1, convert_png_to_jpg=True, store_as_array=as_array)
+        (shard,) = sorted(os.listdir(out))
+        recs = otfr.read_records(open(os.path.join(out, shard), "rb").read())
+        assert len(recs) == 5
+        for rec in recs:
+            if as_array:
+                img, tgt, ident = tr.parse_8bit_array_proto(rec, device=dev)
+                fi, fl = want[ident]
+                assert np.array_equal(img.cpu().numpy(), ojpg.decode_jpeg(fi)) and np.array_equal(tgt.cpu().numpy(), ojpg.decode_jpeg(fl)[..., 0])
+            else:
+                img_bytes, dims, tgt_bytes, tdims, ident = oep._parse_byteslist_proto(rec)
+                assert (bytes(img_bytes), bytes(tgt_bytes)) == want[bytes(ident)] and tuple(int(x) for x in dims) == (40, 56, 3)
+
+
 @pytest.mark.gpu
 def test_gpu_decode_matches_golden_and_oracle(dev):
     from dl_image_segmentation_b200 import _codec
@@ -250,8 +342,6 @@ def test_mp_translator_and_loaders_on_jpg_chips(dev, tmp_path):
     coder = _img_to_tf_threaded.ImageCoder(device=dev)
     arr, h, w, b, key = _img_to_tf_threaded._process_image(path, coder, decode=True)
     assert (h, w, b, key) == (48, 40, 3, "64:0:10.0:30:2:5") and np.array_equal(arr.cpu().numpy(), want)
-    with pytest.raises(NotImplementedError):
-        pkg.images_to_tfrecords_mt("jpgs", str(d), str(out), 1, num_threads=1, convert_png_to_jpg=True)
 
 
 @pytest.mark.gpu
