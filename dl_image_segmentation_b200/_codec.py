@@ -458,14 +458,17 @@ def encode_jpeg_arrays(arrays, quality=100, density=TF_JPEG_DENSITY, device=None
     check(lib().b2_jpeg_encode_scan(ctx.handle, ptr(pixels), ptr(jobs_d), jobs.ctypes.data, n, int(quality), ptr(coef_d), coef,
                                     ptr(out_d), ptr(len_d), ctx.stream()))
     lens = len_d.cpu().numpy().view(np.uint32)
-    files = []
+    if (lens == 0xFFFFFFFF).any():
+        raise B2Error("b2_jpeg_encode_scan: scan buffer too small (its own bound)")
+    # the scans are far shorter than their bound: pack them on the device, one copy to the host
+    packed = torch.cat([out_d[int(jobs[j]["out_off"]):int(jobs[j]["out_off"]) + int(lens[j])] for j in range(n)]).cpu().numpy()
+    files, o, headers = [], 0, {}
     for j in range(n):
-        if lens[j] == 0xFFFFFFFF:
-            raise B2Error("b2_jpeg_encode_scan: scan buffer too small (its own bound)")
-        o = int(jobs[j]["out_off"])
-        scan = out_d[o:o + int(lens[j])].cpu().numpy().tobytes()
-        files.append(jpeg_header(int(jobs[j]["height"]), int(jobs[j]["width"]), int(jobs[j]["components"]), quality, density)
-                     + scan + b"\xff\xd9")
+        key = (int(jobs[j]["height"]), int(jobs[j]["width"]), int(jobs[j]["components"]))
+        if key not in headers:
+            headers[key] = jpeg_header(key[0], key[1], key[2], quality, density)
+        files.append(headers[key] + packed[o:o + int(lens[j])].tobytes() + b"\xff\xd9")
+        o += int(lens[j])
     return files
 
 
