@@ -424,7 +424,7 @@ def jpeg_header(height, width, components, quality=100, density=TF_JPEG_DENSITY)
     return bytes(buf[:ln.value])
 
 
-def encode_jpeg_arrays(arrays, quality=100, density=TF_JPEG_DENSITY, device=None):
+def encode_jpeg_arrays(arrays, quality=100, density=TF_JPEG_DENSITY, device=None, timings=None):
     """Encode a batch of (H,W,1) / (H,W,3) uint8 images (CUDA tensors or host arrays) as baseline JPEG files on the GPU
     -> list of bytes.  Replaces tf.image.encode_jpeg(image, format='', quality=100) behind ImageCoder.png_to_jpeg
     (reference _img_to_tf_threaded.py:36-38): grey -> one component, RGB -> YCbCr 4:2:0, standard Huffman tables."""
@@ -455,8 +455,15 @@ def encode_jpeg_arrays(arrays, quality=100, density=TF_JPEG_DENSITY, device=None
     coef_d = torch.empty((coef,), dtype=torch.int16, device=ctx.device)
     out_d = torch.empty((out,), dtype=torch.uint8, device=ctx.device)
     len_d = torch.zeros((n,), dtype=torch.int32, device=ctx.device)
+    if timings is not None:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
     check(lib().b2_jpeg_encode_scan(ctx.handle, ptr(pixels), ptr(jobs_d), jobs.ctypes.data, n, int(quality), ptr(coef_d), coef,
                                     ptr(out_d), ptr(len_d), ctx.stream()))
+    if timings is not None:
+        ev[1].record()
+        torch.cuda.synchronize()
+        timings.update(encode_ms=ev[0].elapsed_time(ev[1]), pixel_bytes=int(src))
     lens = len_d.cpu().numpy().view(np.uint32)
     if (lens == 0xFFFFFFFF).any():
         raise B2Error("b2_jpeg_encode_scan: scan buffer too small (its own bound)")

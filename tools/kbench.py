@@ -186,6 +186,27 @@ def bench_jpeg(dev, n_distinct=16, reps=None):
                    "wall_ms_incl_host_parse_and_h2d": round(best["wall_ms"], 1)})
 
 
+def bench_jpeg_encode(dev, n_distinct=16, reps=64):
+    """convert_png_to_jpg: cfg1 chips + labels -> quality-100 JPEG files (4:2:0 / grey), 1024 pairs per call."""
+    import synthetic as syn
+    from dl_image_segmentation_b200 import _codec
+    arrays = []
+    for i in range(n_distinct):
+        img, lab, _ = syn.cfg1_chip(i)
+        arrays += [torch.from_numpy(img).to(dev), torch.from_numpy(lab.reshape(lab.shape[0], lab.shape[1], 1)).to(dev)]
+    batch = arrays * reps
+    best = None
+    for it in range(3):
+        tm = {}
+        files = _codec.encode_jpeg_arrays(batch, quality=100, device=dev, timings=tm)
+        if best is None or tm["encode_ms"] < best["encode_ms"]:
+            best = tm
+    pairs = len(batch) // 2
+    out_bytes = sum(len(f) for f in files)
+    return report("encode jpeg: %d chip pairs (%d images)" % (pairs, len(batch)), best["encode_ms"], best["pixel_bytes"] + out_bytes,
+                  {"chip_pairs_per_s": round(pairs / best["encode_ms"] * 1e3, 1), "file_MB": round(out_bytes / 1e6, 1)})
+
+
 def bench_parse(dev, n_shards=8):
     """Variants of the fused parse kernel on cfg2 shards + write-only / copy bandwidth references."""
     sys.path.insert(0, ROOT)
@@ -386,6 +407,8 @@ def main():
         bench_encode_kernel(dev)
     if "jpeg" in which:
         bench_jpeg(dev)
+    if "jpeg_encode" in which:
+        bench_jpeg_encode(dev)
     for kind in ("lzw", "lzw_strips_pred2", "deflate", "png"):
         if kind in which or "decode" in which:
             bench_decode(dev, kind)
