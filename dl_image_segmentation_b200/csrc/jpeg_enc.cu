@@ -5,8 +5,11 @@
 // rounding half away from zero, dummy blocks beyond a component's own block grid, the standard Huffman tables.
 //   jpeg_fdct_kernel          one thread per 8x8 block in coding order: samples (colour conversion / down-sampling with
 //                             libjpeg's edge replication rules) -> forward DCT -> quantise -> zig-zag int16
-//   jpeg_huff_encode_kernel   one warp per image; lane 0 codes the blocks in order (DC prediction, run lengths, byte
-//                             stuffing) into the scan bytes
+//   jpeg_block_bits_kernel    one thread per block: length of its Huffman code (DC difference against the previous real
+//                             block of its component, run lengths)
+//   jpeg_scan_bits_kernel     one CTA per image: exclusive scan -> bit offset of every block
+//   jpeg_block_write_kernel   one thread per block: its bits into the unstuffed stream (32-bit atomicOr at the seams)
+//   jpeg_stuff_kernel         one CTA per image: 0xFF -> 0xFF 0x00 with a second scan
 // The header (SOI .. SOS) is assembled on the host by b2_jpeg_header.
 #include <string.h>
 
@@ -221,93 +224,212 @@ __global__ void __launch_bounds__(128) jpeg_fdct_kernel(const uint8_t* __restric
     for (int k = 0; k < 64; k++) dst[k] = (int16_t)res[c_zz[k]];
 }
 
-struct BitWriter {
-    uint8_t* p;
-    uint8_t* end;
-    uint64_t acc;
-    int n;
-    bool overflow;
-    __device__ __forceinline__ void put(uint32_t code, int len) {
-        acc = (acc << len) | (code & ((1u << len) - 1u));
-        n += len;
-        while (n >= 8) {
-            const uint8_t b = (uint8_t)(acc >> (n - 8));
-            n -= 8;
-            if (p + 2 > end) {
-                overflow = true;
-                continue;
-            }
-            *p++ = b;
-            if (b == 0xFF) *p++ = 0;
-        }
-    }
+// ---- Huffman coding, block-parallel: bits per block -> exclusive scan per image -> every block writes its own bits
+// (32-bit atomicOr at the seams) -> byte stuffing with a second scan.  Bit-identical to the serial coder by construction.
+struct CodeTables {
+    uint32_t codes[4][256];  // (code << 5) | length, per symbol: DC lum, AC lum, DC chroma, AC chroma
 };
 
-// one warp per image
-__global__ void __launch_bounds__(32) jpeg_huff_encode_kernel(const b2_jpeg_enc_job* __restrict__ jobs, int n_jobs,
-                                                              const int16_t* __restrict__ coef, uint8_t* __restrict__ out,
-                                                              uint32_t* __restrict__ out_len) {
-    __shared__ uint32_t codes[4][256];  // (code << 5) | length, per symbol
-    const int lane = threadIdx.x;
-    if (lane < 4) {
+__device__ __forceinline__ void build_codes(CodeTables& t) {
+    if (threadIdx.x < 4) {
+        const int k4 = threadIdx.x;
         int code = 0, k = 0;
         for (int l = 1; l <= 16; l++) {
-            for (int i = 0; i < c_std_bits[lane][l - 1]; i++) codes[lane][c_std_vals[lane][k++]] = ((uint32_t)code++ << 5) | (uint32_t)l;
+            for (int i = 0; i < c_std_bits[k4][l - 1]; i++) t.codes[k4][c_std_vals[k4][k++]] = ((uint32_t)code++ << 5) | (uint32_t)l;
             code <<= 1;
         }
     }
-    __syncwarp();
-    if (lane != 0) return;
-    for (int j = blockIdx.x; j < n_jobs; j += gridDim.x) {
-        const b2_jpeg_enc_job job = jobs[j];
-        const int nc = job.components;
-        const uint32_t n_blocks = nc == 1 ? (uint32_t)((job.width + 7) >> 3) * ((job.height + 7) >> 3)
-                                          : (uint32_t)((job.width + 15) >> 4) * ((job.height + 15) >> 4) * 6;
-        BitWriter bw;
-        bw.p = out + job.out_off;
-        bw.end = bw.p + job.out_cap;
-        bw.acc = 0;
-        bw.n = 0;
-        bw.overflow = false;
-        int pred[3] = {0, 0, 0};
-        const int16_t* blk = coef + job.coef_off;
-        for (uint32_t b = 0; b < n_blocks; b++, blk += 64) {
-            const int j6 = nc == 1 ? 0 : (int)(b % 6);
-            const int comp = j6 < 4 ? 0 : j6 - 3;
-            const uint32_t* dc = codes[comp ? 2 : 0];
-            const uint32_t* ac = codes[comp ? 3 : 1];
-            if (blk[0] == kDummy) {  // DC of the block before it, no AC
-                bw.put(dc[0] >> 5, dc[0] & 31);
-                bw.put(ac[0] >> 5, ac[0] & 31);
-                continue;
-            }
-            int v = blk[0];
-            int diff = v - (comp == 0 ? pred[0] : comp == 1 ? pred[1] : pred[2]);
-            if (comp == 0) pred[0] = v; else if (comp == 1) pred[1] = v; else pred[2] = v;
-            int nb = 32 - __clz(abs(diff));
-            bw.put(dc[nb] >> 5, dc[nb] & 31);
-            if (nb) bw.put((uint32_t)(diff < 0 ? diff - 1 : diff), nb);
-            int r = 0;
-            for (int k = 1; k < 64; k++) {
-                v = blk[k];
-                if (v == 0) {
-                    r++;
-                    continue;
-                }
-                while (r > 15) {
-                    bw.put(ac[0xF0] >> 5, ac[0xF0] & 31);
-                    r -= 16;
-                }
-                nb = 32 - __clz(abs(v));
-                const uint32_t e = ac[(r << 4) | nb];
-                bw.put(e >> 5, e & 31);
-                bw.put((uint32_t)(v < 0 ? v - 1 : v), nb);
-                r = 0;
-            }
-            if (r) bw.put(ac[0] >> 5, ac[0] & 31);
+    __syncthreads();
+}
+
+__device__ __forceinline__ uint32_t blocks_of(const b2_jpeg_enc_job& job) {
+    return job.components == 1 ? (uint32_t)((job.width + 7) >> 3) * ((job.height + 7) >> 3)
+                               : (uint32_t)((job.width + 15) >> 4) * ((job.height + 15) >> 4) * 6;
+}
+
+// DC of the previous real block of the same component in coding order (0 at the start of the scan)
+__device__ __forceinline__ int prev_dc(const int16_t* __restrict__ c0, uint32_t b, int nc) {
+    if (nc == 1) return b ? c0[(uint64_t)(b - 1) * 64] : 0;
+    const uint32_t j = b % 6;
+    if (j >= 4) return b >= 6 ? c0[(uint64_t)(b - 6) * 64] : 0;
+    for (int64_t q = (int64_t)b - 1; q >= 0; q--) {  // dummies sit at the right / bottom edge: a handful of steps at most
+        if (q % 6 >= 4) continue;
+        const int v = c0[(uint64_t)q * 64];
+        if (v != kDummy) return v;
+    }
+    return 0;
+}
+
+template <class Sink>
+__device__ __forceinline__ void code_block(const int16_t* __restrict__ blk, int pred, const uint32_t* dc, const uint32_t* ac, Sink& sink) {
+    if (blk[0] == kDummy) {  // the DC of the block before it, no AC
+        sink.put(dc[0] >> 5, dc[0] & 31);
+        sink.put(ac[0] >> 5, ac[0] & 31);
+        return;
+    }
+    const int diff = (int)blk[0] - pred;
+    int nb = 32 - __clz(abs(diff));
+    sink.put(dc[nb] >> 5, dc[nb] & 31);
+    if (nb) sink.put((uint32_t)(diff < 0 ? diff - 1 : diff) & ((1u << nb) - 1u), nb);
+    int r = 0;
+#pragma unroll 1
+    for (int k = 1; k < 64; k++) {
+        const int v = blk[k];
+        if (v == 0) {
+            r++;
+            continue;
         }
-        if (bw.n) bw.put((1u << (8 - bw.n)) - 1u, 8 - bw.n);  // pad the last byte with 1-bits
-        out_len[j] = bw.overflow ? 0xFFFFFFFFu : (uint32_t)(bw.p - (out + job.out_off));
+        while (r > 15) {
+            sink.put(ac[0xF0] >> 5, ac[0xF0] & 31);
+            r -= 16;
+        }
+        nb = 32 - __clz(abs(v));
+        const uint32_t e = ac[(r << 4) | nb];
+        sink.put(e >> 5, e & 31);
+        sink.put((uint32_t)(v < 0 ? v - 1 : v) & ((1u << nb) - 1u), nb);
+        r = 0;
+    }
+    if (r) sink.put(ac[0] >> 5, ac[0] & 31);
+}
+
+struct CountSink {
+    uint32_t bits;
+    __device__ __forceinline__ void put(uint32_t, int len) { bits += (uint32_t)len; }
+};
+
+struct WordSink {  // big-endian bit stream, written as 32-bit words; the words at both ends are shared with neighbours
+    uint32_t* w;   // next word
+    uint64_t acc;
+    int n;         // bits in acc, including the leading zeros that stand for the neighbour's bits
+    __device__ __forceinline__ void put(uint32_t code, int len) {
+        acc = (acc << len) | code;
+        n += len;
+        if (n >= 32) {
+            n -= 32;
+            atomicOr(w++, __byte_perm((uint32_t)(acc >> n), 0, 0x0123));
+        }
+    }
+    __device__ __forceinline__ void flush() {
+        if (n) atomicOr(w, __byte_perm((uint32_t)(acc << (32 - n)), 0, 0x0123));
+    }
+};
+
+// grid = (ceil(max blocks / 128), n images); bits[] is indexed by the global block number coef_off / 64 + b
+__global__ void __launch_bounds__(128) jpeg_block_bits_kernel(const b2_jpeg_enc_job* __restrict__ jobs, const int16_t* __restrict__ coef,
+                                                              uint64_t* __restrict__ bits) {
+    __shared__ CodeTables t;
+    build_codes(t);
+    const b2_jpeg_enc_job job = jobs[blockIdx.y];
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= blocks_of(job)) return;
+    const int16_t* c0 = coef + job.coef_off;
+    const int comp = job.components == 1 ? 0 : (b % 6 < 4 ? 0 : (int)(b % 6) - 3);
+    CountSink sink{0};
+    code_block(c0 + (uint64_t)b * 64, prev_dc(c0, b, job.components), t.codes[comp ? 2 : 0], t.codes[comp ? 3 : 1], sink);
+    bits[job.coef_off / 64 + b] = sink.bits;
+}
+
+// one CTA per image: bits[] -> exclusive prefix (bit offset of every block); total[j] = bits of the whole scan
+__global__ void __launch_bounds__(256) jpeg_scan_bits_kernel(const b2_jpeg_enc_job* __restrict__ jobs, uint64_t* __restrict__ bits,
+                                                             uint64_t* __restrict__ total) {
+    __shared__ uint64_t warp_sum[8];
+    __shared__ uint64_t carry;
+    const b2_jpeg_enc_job job = jobs[blockIdx.x];
+    const uint32_t nb = blocks_of(job);
+    uint64_t* v = bits + job.coef_off / 64;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += 256) {
+        const uint32_t i = base + threadIdx.x;
+        const uint64_t x = i < nb ? v[i] : 0;
+        uint64_t inc = x;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if ((threadIdx.x & 31) >= d) inc += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        uint64_t before = carry;
+        for (int wi = 0; wi < (int)(threadIdx.x >> 5); wi++) before += warp_sum[wi];
+        if (i < nb) v[i] = before + inc - x;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = before + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total[blockIdx.x] = carry;
+}
+
+// grid = (ceil(max blocks / 128), n images): every block writes its bits at its offset into the (zeroed) unstuffed stream
+__global__ void __launch_bounds__(128) jpeg_block_write_kernel(const b2_jpeg_enc_job* __restrict__ jobs, const int16_t* __restrict__ coef,
+                                                               const uint64_t* __restrict__ bits, const uint64_t* __restrict__ total,
+                                                               uint8_t* __restrict__ raw) {
+    __shared__ CodeTables t;
+    build_codes(t);
+    const b2_jpeg_enc_job job = jobs[blockIdx.y];
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x, nb = blocks_of(job);
+    if (b >= nb) return;
+    const int16_t* c0 = coef + job.coef_off;
+    const int comp = job.components == 1 ? 0 : (b % 6 < 4 ? 0 : (int)(b % 6) - 3);
+    const uint64_t off = bits[job.coef_off / 64 + b];
+    WordSink sink;
+    sink.w = reinterpret_cast<uint32_t*>(raw + ((job.out_off >> 1) & ~7ull)) + (off >> 5);
+    sink.acc = 0;
+    sink.n = (int)(off & 31);
+    code_block(c0 + (uint64_t)b * 64, prev_dc(c0, b, job.components), t.codes[comp ? 2 : 0], t.codes[comp ? 3 : 1], sink);
+    if (b == nb - 1) {  // pad the last byte of the scan with 1-bits
+        const int pad = (int)((8 - (total[blockIdx.y] & 7)) & 7);
+        if (pad) sink.put((1u << pad) - 1u, pad);
+    }
+    sink.flush();
+}
+
+// one CTA per image: insert a zero byte after every 0xFF
+__global__ void __launch_bounds__(256) jpeg_stuff_kernel(const b2_jpeg_enc_job* __restrict__ jobs, const uint64_t* __restrict__ total,
+                                                         const uint8_t* __restrict__ raw, uint8_t* __restrict__ out,
+                                                         uint32_t* __restrict__ out_len) {
+    __shared__ uint32_t warp_sum[8];
+    __shared__ uint64_t carry;
+    const b2_jpeg_enc_job job = jobs[blockIdx.x];
+    const uint64_t nbytes = (total[blockIdx.x] + 7) >> 3;
+    const uint8_t* src = raw + ((job.out_off >> 1) & ~7ull);
+    uint8_t* dst = out + job.out_off;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < nbytes; base += 256 * 16) {
+        const uint64_t i0 = base + (uint64_t)threadIdx.x * 16;
+        uint8_t v[16];
+        uint32_t ff = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            v[k] = i0 + k < nbytes ? src[i0 + k] : 0;
+            ff += v[k] == 0xFF;
+        }
+        uint32_t inc = ff;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if ((threadIdx.x & 31) >= d) inc += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        uint64_t before = carry;
+        for (int wi = 0; wi < (int)(threadIdx.x >> 5); wi++) before += warp_sum[wi];
+        uint64_t o = i0 + before + inc - ff;
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            if (i0 + k < nbytes) {
+                if (o + 2 <= job.out_cap) {
+                    dst[o] = v[k];
+                    if (v[k] == 0xFF) dst[o + 1] = 0;
+                }
+                o += v[k] == 0xFF ? 2 : 1;
+            }
+        __syncthreads();
+        if (threadIdx.x == 255) carry = before + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const uint64_t len = nbytes + carry;
+        out_len[blockIdx.x] = len <= job.out_cap ? (uint32_t)len : 0xFFFFFFFFu;
     }
 }
 
@@ -386,11 +508,32 @@ extern "C" int b2_jpeg_encode_scan(b2_ctx* ctx, const uint8_t* pixels_dev, const
     }
     QuantTables qt;
     quant_tables(quality, &qt);
-    jpeg_fdct_kernel<<<dim3((unsigned)((max_blocks + 127) / 128), n), 128, 0, s>>>(pixels_dev, jobs_dev, qt, coef_dev);
+    const dim3 per_block((unsigned)((max_blocks + 127) / 128), n);
+    jpeg_fdct_kernel<<<per_block, 128, 0, s>>>(pixels_dev, jobs_dev, qt, coef_dev);
     B2_CUDA(cudaGetLastError());
-    const int warps = n < ctx->sm_count * 32 ? n : ctx->sm_count * 32;
-    jpeg_huff_encode_kernel<<<warps, 32, 0, s>>>(jobs_dev, n, coef_dev, out_dev, out_len_dev);
+    // workspace: bit count / offset per block, total per image, the unstuffed stream (half the scan bound per image)
+    uint64_t out_end = 0;
+    for (int j = 0; j < n; j++) {
+        const uint64_t e = jobs_host[j].out_off + jobs_host[j].out_cap;
+        B2_REQUIRE(jobs_host[j].out_off % 16 == 0, "b2_jpeg_encode_scan: out_off must be a multiple of 16");
+        out_end = e > out_end ? e : out_end;
+    }
+    const uint64_t n_blocks_all = coef_count / 64;
+    const uint64_t bits_bytes = (n_blocks_all + (uint64_t)n) * sizeof(uint64_t);
+    const uint64_t raw_bytes = ((out_end / 2 + 64) + 15) & ~15ull;
+    if (ws_reserve(ctx, bits_bytes + raw_bytes, s)) return 1;
+    uint64_t* bits = static_cast<uint64_t*>(ctx->ws);
+    uint64_t* total = bits + n_blocks_all;
+    uint8_t* raw = static_cast<uint8_t*>(ctx->ws) + bits_bytes;
+    B2_CUDA(cudaMemsetAsync(raw, 0, raw_bytes, s));
+    jpeg_block_bits_kernel<<<per_block, 128, 0, s>>>(jobs_dev, coef_dev, bits);
     B2_CUDA(cudaGetLastError());
-    ctx->launches += 2;
+    jpeg_scan_bits_kernel<<<n, 256, 0, s>>>(jobs_dev, bits, total);
+    B2_CUDA(cudaGetLastError());
+    jpeg_block_write_kernel<<<per_block, 128, 0, s>>>(jobs_dev, coef_dev, bits, total, raw);
+    B2_CUDA(cudaGetLastError());
+    jpeg_stuff_kernel<<<n, 256, 0, s>>>(jobs_dev, total, raw, out_dev, out_len_dev);
+    B2_CUDA(cudaGetLastError());
+    ctx->launches += 5;
     return 0;
 }

@@ -391,8 +391,8 @@ int b2_jpeg_header(int height, int width, int components, int quality, int densi
                    uint8_t* out, uint64_t cap, uint64_t* len);
 /* Host-side: int16 coefficients and an upper bound of the scan bytes of one image. */
 int b2_jpeg_encode_sizes(int height, int width, int components, uint64_t* coef_count, uint64_t* scan_cap);
-/* Colour conversion + down-sampling + forward DCT + quantisation (one thread per block), then Huffman coding with byte
- * stuffing (one warp per image).  out_len_dev[j] = scan bytes of image j, 0xFFFFFFFF if out_cap was too small. */
+/* Colour conversion + down-sampling + forward DCT + quantisation (one thread per block), then block-parallel Huffman
+ * coding (bit count per block, scan per image, every block writes its bits) and byte stuffing; out_off multiples of 16.  out_len_dev[j] = scan bytes of image j, 0xFFFFFFFF if out_cap was too small. */
 int b2_jpeg_encode_scan(b2_ctx* ctx, const uint8_t* pixels_dev, const b2_jpeg_enc_job* jobs_dev,
                         const b2_jpeg_enc_job* jobs_host, int n, int quality, int16_t* coef_dev, uint64_t coef_count,
                         uint8_t* out_dev, uint32_t* out_len_dev, b2_stream stream);
