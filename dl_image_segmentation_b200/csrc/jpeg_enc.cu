@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(128) jpeg_fdct_kernel(const uint8_t* __restric
     const int W = job.width, H = job.height, nc = job.components;
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     int comp, bx, by;  // component and block position inside it
-    uint32_t n_blocks;
+    uint32_t n_blocks, out_b = b;
     if (nc == 1) {
         const int bw = (W + 7) >> 3, bh = (H + 7) >> 3;
         n_blocks = (uint32_t)bw * bh;
@@ -149,22 +149,27 @@ __global__ void __launch_bounds__(128) jpeg_fdct_kernel(const uint8_t* __restric
         by = b / bw;
         bx = b - by * bw;
     } else {
+        // threads are numbered plane by plane (all luminance blocks row-major, then Cb, then Cr) so that a warp works on
+        // one kind of block and on neighbouring pixels; the block is stored at its place in coding order
         const int mw = (W + 15) >> 4, mh = (H + 15) >> 4;
-        n_blocks = (uint32_t)mw * mh * 6;
-        const uint32_t mcu = b / 6, j = b - mcu * 6;
-        const int my = mcu / mw, mx = mcu - my * mw;
-        if (j < 4) {
+        const uint32_t n_mcu = (uint32_t)mw * mh;
+        n_blocks = n_mcu * 6;
+        if (b >= n_blocks) return;
+        if (b < 4 * n_mcu) {
             comp = 0;
-            by = 2 * my + (int)(j >> 1);
-            bx = 2 * mx + (int)(j & 1);
+            by = b / (2 * mw);
+            bx = b - by * (2 * mw);
+            out_b = ((uint32_t)(by >> 1) * mw + (bx >> 1)) * 6 + (by & 1) * 2 + (bx & 1);
         } else {
-            comp = (int)j - 3;
-            by = my;
-            bx = mx;
+            comp = b < 5 * n_mcu ? 1 : 2;
+            const uint32_t m = b - (3 + comp) * n_mcu;
+            by = m / mw;
+            bx = m - by * mw;
+            out_b = m * 6 + 3 + comp;
         }
     }
     if (b >= n_blocks) return;
-    int16_t* dst = coef + job.coef_off + (uint64_t)b * 64;
+    int16_t* dst = coef + job.coef_off + (uint64_t)out_b * 64;
     if (nc == 3 && comp == 0 && (by >= ((H + 7) >> 3) || bx >= ((W + 7) >> 3))) {  // beyond the luminance block grid
         dst[0] = kDummy;
         return;
