@@ -3,7 +3,10 @@
 TFRecord files, through the drop-in images_to_tfrecords_mp, next to the oracle restatement of the reference's
 multiprocessing CPU path (joblib over all host cores) on the same files.  Prints one JSON line per arm.
 
-    python tools/translate_bench.py [png|lzw|jpg] [n_pairs] [gpu_workers]
+    python tools/translate_bench.py [png|lzw|jpg|png2jpg] [n_pairs] [gpu_workers]
+
+png2jpg = PNG chips through images_to_tfrecords_mt(convert_png_to_jpg=True): decode, JPEG-encode, store the JPEG files
+(GPU arm only: the oracle's JPEG encoder is a pure-Python restatement, not a timing baseline).
 """
 import json
 import os
@@ -24,10 +27,10 @@ def make_dataset(kind, n, root):
     from joblib import Parallel, delayed
     os.makedirs(os.path.join(root, "images"))
     os.makedirs(os.path.join(root, "labels"))
-    ext = {"png": "png", "jpg": "jpg"}.get(kind, "tif")
+    ext = {"png": "png", "jpg": "jpg", "png2jpg": "png"}.get(kind, "tif")
 
     def one(i):
-        if kind == "png":
+        if kind in ("png", "png2jpg"):
             img, lab, key = syn.cfg1_chip(i)
             a, b = syn.png_bytes(img), syn.png_bytes(lab)
         elif kind == "jpg":                    # quality 100, 4:2:0: what tf.image.encode_jpeg behind png_to_jpeg writes
@@ -77,6 +80,19 @@ def main():
 
         import dl_image_segmentation_b200 as pkg
         out_g = os.path.join(root, "out_gpu")
+        if kind == "png2jpg":
+            with contextlib.redirect_stdout(io.StringIO()):
+                pkg.images_to_tfrecords_mt("warm", root, os.path.join(root, "out_warm"), shards, num_threads=workers, convert_png_to_jpg=True)
+                torch.cuda.synchronize()
+                t0 = time.time()
+                pkg.images_to_tfrecords_mt("bench", root, out_g, shards, num_threads=workers, convert_png_to_jpg=True)
+                torch.cuda.synchronize()
+                gpu_s = time.time() - t0
+            out_bytes = sum(os.path.getsize(os.path.join(out_g, f)) for f in os.listdir(out_g))
+            print(json.dumps({"arm": "b200 (%d GPU worker(s), drop-in images_to_tfrecords_mt(convert_png_to_jpg=True), files on %s)" % (workers, base),
+                              "kind": kind, "pairs": n, "seconds": round(gpu_s, 3), "pairs_per_s": round(n / gpu_s, 1),
+                              "input_MB": round(in_bytes / 1e6, 1), "output_MB": round(out_bytes / 1e6, 1)}), flush=True)
+            return
         with contextlib.redirect_stdout(io.StringIO()):
             pkg.images_to_tfrecords_mp("warm", root, os.path.join(root, "out_warm"), shards, num_proc=workers, file_ext=ext)
             torch.cuda.synchronize()
