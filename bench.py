@@ -308,6 +308,8 @@ def other_configs(dev):
     out["cfg3_lzw_geotiff_decode"] = keep(d, "chip_pairs_per_s", "decoded_GB/s")
     d = kbench.bench_jpeg(dev)
     out["cfg1_jpeg_decode"] = keep(d, "chip_pairs_per_s", "decoded_GB/s")
+    d = kbench.bench_jpeg_encode(dev)
+    out["cfg1_jpeg_encode_png_to_jpg"] = keep(d, "chip_pairs_per_s", "file_MB")
     torch.cuda.empty_cache()
     return out
 
