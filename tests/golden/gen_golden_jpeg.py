@@ -44,6 +44,15 @@ def main():
         open(os.path.join(HERE, "jpeg_%s.jpg" % name), "wb").write(data)
         np.save(os.path.join(HERE, "jpeg_%s.npy" % name), np.ascontiguousarray(ref))
         print(name, len(data), ref.shape)
+    # encoder fixtures (convert_png_to_jpg): pixels in, the file libjpeg-turbo writes for them out (cv2.imencode: JFIF
+    # density 1 x 1 without a unit; TensorFlow's 300 x 300 dpi differs in those five header bytes only)
+    for name, (h, w, c, q) in {"rgb_q100": (24, 40, 3, 100), "rgb_q75": (37, 29, 3, 75), "grey_q100": (20, 33, 1, 100)}.items():
+        img = chip(h, w, c, rng)
+        ok, buf = cv2.imencode(".jpg", np.ascontiguousarray(img[..., ::-1]) if c == 3 else img[..., 0], [cv2.IMWRITE_JPEG_QUALITY, q])
+        assert ok
+        np.save(os.path.join(HERE, "jpegenc_%s_in.npy" % name), img)
+        open(os.path.join(HERE, "jpegenc_%s_out.jpg" % name), "wb").write(buf.tobytes())
+        print("encoder", name, len(buf))
     # a progressive file: out of scope, must be reported (status 3), never mis-decoded
     f = io.BytesIO()
     Image.fromarray(chip(16, 16, 3, rng)).save(f, "JPEG", quality=80, progressive=True)

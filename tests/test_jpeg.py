@@ -160,6 +160,19 @@ def test_encoder_oracle_is_byte_identical_to_libjpeg_turbo():
             assert np.array_equal(ojpg.decode_jpeg(tf_like), ojpg.decode_jpeg(got))
 
 
+ENC_CASES = {"rgb_q100": 100, "rgb_q75": 75, "grey_q100": 100}
+
+
+def _enc_case(name):
+    return np.load(os.path.join(G, "jpegenc_%s_in.npy" % name)), open(os.path.join(G, "jpegenc_%s_out.jpg" % name), "rb").read()
+
+
+@pytest.mark.parametrize("name", sorted(ENC_CASES))
+def test_encoder_oracle_against_golden_libjpeg_files(name):
+    img, want = _enc_case(name)
+    assert ojenc.encode_jpeg(img, ENC_CASES[name], density=(0, 1, 1)) == want
+
+
 def test_host_header_matches_oracle_header():
     from dl_image_segmentation_b200 import _codec
     for (h, w, c, q) in [(256, 256, 3, 100), (17, 33, 1, 75), (65535, 1, 3, 1), (40, 48, 3, 50)]:
@@ -186,6 +199,14 @@ def test_gpu_encode_is_byte_identical_to_libjpeg_turbo_and_oracle(dev):
     assert not status.any()
     for a, f in zip(arrays, files):
         assert np.array_equal(a.cpu().numpy(), ojpg.decode_jpeg(f))
+
+
+@pytest.mark.gpu
+def test_gpu_encode_matches_golden_libjpeg_files(dev):
+    from dl_image_segmentation_b200 import _codec
+    imgs, wants = zip(*[_enc_case(n) for n in sorted(ENC_CASES)])
+    for img, want, name in zip(imgs, wants, sorted(ENC_CASES)):
+        assert _codec.encode_jpeg_arrays([img], quality=ENC_CASES[name], density=(0, 1, 1), device=dev)[0] == want, name
 
 
 @pytest.mark.gpu
