@@ -16,6 +16,10 @@ What it restates (reference = harry-gibson/dl_image_segmentation, paths under
                        (``_img_to_tf_mp.py:119,141,150``; ``parse_tfrecords.ipynb`` cell 4)
 ``imagecodecs``        ``load_image_rasterio`` (``_img_to_tf_mp.py:22-75``) and ``_process_image``
                        (``_img_to_tf_threaded.py:75-121``): TIFF (LZW / DEFLATE / none) and PNG decode
+``jpegcodec``          ``ImageCoder.decode_jpeg`` / ``.jpg`` chips (``_img_to_tf_threaded.py:36-38,51-56,97-103``):
+                       baseline JPEG decode with libjpeg's integer arithmetic
+``jpegenc``            ``ImageCoder.png_to_jpeg`` (``_img_to_tf_threaded.py:36-38,92-95``): baseline JPEG encode,
+                       byte-identical to libjpeg-turbo's files
 ``composite``          ``_descartes_img_chips.py:562-567`` (np.ma median) and ``:461-469,603-626``
                        (date/cloud filter, stable descending sort, painter's mosaic), ``:516`` dstack
 ``normalise``          north-star row A17 (cast, per-band normalise, one-hot, integer band statistics)
@@ -29,7 +33,7 @@ fixtures either.  The arithmetic it delegates lives in un-pinned third-party lib
 (conda_env_cpu.yml:5-12).  The oracle is therefore pinned from the outside instead:
 RFC 3720 B.4 CRC-32C vectors; ``google.protobuf`` (dynamic ``tensorflow.Example`` descriptor,
 deterministic serialisation); ``zlib``; libtiff 4.7.1 through ``cv2`` and ``Pillow``; libpng through
-``Pillow``; and ``numpy.ma.median`` itself (NumPy is the real implementation the reference calls).
+``Pillow``; libjpeg-turbo through ``cv2`` and ``Pillow`` (decoded pixels bit for bit, encoded files byte for byte); and ``numpy.ma.median`` itself (NumPy is the real implementation the reference calls).
 Those checks live in ``tests/test_oracle_*.py`` and the committed vectors in ``tests/golden/``.
 """
 import ctypes
