@@ -242,7 +242,7 @@ def decode_blobs(blobs, device=None, timings=None, want_infos=False, png_as_tf=F
     (plan_blobs); decode_planned then runs the kernels.
     """
     arrays, status, infos = decode_planned(plan_blobs(blobs, device, png_as_tf), device, timings, True)
-    arrays, status, infos = merge_jpeg(blobs, arrays, status, infos, device)
+    arrays, status, infos = merge_jpeg(blobs, arrays, status, infos, device, candidates=np.nonzero(status)[0])
     return (arrays, status, infos) if want_infos else (arrays, status)
 
 
@@ -382,10 +382,12 @@ def decode_jpeg_blobs(blobs, device=None, timings=None):
     return arrays, status, infos
 
 
-def merge_jpeg(blobs, arrays, status, infos, device=None):
+def merge_jpeg(blobs, arrays, status, infos, device=None, candidates=None):
     """The TIFF / PNG planner reports a .jpg chip as an unknown format; decode those through the JPEG path and put their
-    results in place (arrays / status / infos as decode_planned returns them)."""
-    idx = [k for k, b in enumerate(blobs) if is_jpeg(_host_bytes(b))]
+    results in place (arrays / status / infos as decode_planned returns them).  candidates: the indices worth a look
+    (the ones the planner refused), so that a folder of PNG / TIFF chips pays nothing per file here."""
+    cand = range(len(blobs)) if candidates is None else candidates
+    idx = [int(k) for k in cand if is_jpeg(_host_bytes(blobs[k]))]
     if not idx:
         return arrays, status, infos
     ja, js, ji = decode_jpeg_blobs([blobs[k] for k in idx], device)

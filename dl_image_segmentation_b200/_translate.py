@@ -137,14 +137,15 @@ def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, devi
         if planned is None:
             planned = _codec.plan_blobs(blobs, ctx.device, png_as_tf)
         arrays, st, infos = _codec.decode_planned(planned, ctx.device, want_infos=True)
-        arrays, st, infos = _codec.merge_jpeg(blobs, arrays, st, infos, ctx.device)          # .jpg chips
+        arrays, st, infos = _codec.merge_jpeg(blobs, arrays, st, infos, ctx.device, candidates=np.nonzero(st)[0])   # .jpg chips
         for k in range(2 * n):
             if len(blobs[k]) and infos[k].status == 0 and st[k] != 0 and errs[k // 2] is None:
                 errs[k // 2] = ChipError("could not decode %s (codec status %d)" % ((img_paths, lbl_paths)[k % 2][k // 2], int(st[k])))
     else:
         infos = _codec.probe_blobs(blobs, png_as_tf=png_as_tf)
         # .jpg chips: the reference decodes them even when it stores the file bytes (_img_to_tf_threaded.py:97-112)
-        _, st, infos = _codec.merge_jpeg(blobs, [None] * (2 * n), np.zeros(2 * n, np.int32), infos, ctx.device)
+        _, st, infos = _codec.merge_jpeg(blobs, [None] * (2 * n), np.zeros(2 * n, np.int32), infos, ctx.device,
+                                         candidates=[k for k in range(2 * n) if infos[k].status != 0])
         for k in np.nonzero(st == 2)[0]:
             if errs[k // 2] is None:
                 errs[k // 2] = ChipError("could not decode %s (codec status 2)" % (img_paths, lbl_paths)[k % 2][k // 2])
