@@ -128,9 +128,12 @@ class _StagingPool:
 
     def take(self):
         with self.lock:
-            hs = self.sets[self.k % len(self.sets)]
-            self.k += 1
-            if hs.pending:
+            for _ in range(len(self.sets)):                    # the next set in rotation that no plan is holding
+                hs = self.sets[self.k % len(self.sets)]
+                self.k += 1
+                if not hs.pending:
+                    break
+            else:
                 raise B2Error("decode staging: more batches planned ahead than there are staging sets")
             hs.pending = True
         hs.wait()                                              # its last uploads have left the pinned buffers
@@ -138,8 +141,22 @@ class _StagingPool:
 
 
 class PlannedBatch:
-    """Result of plan_blobs: everything decode_planned needs, all of it host-side."""
-    __slots__ = ("n", "hs", "plan", "infos", "status", "images", "png_as_tf")
+    """Result of plan_blobs: everything decode_planned needs, all of it host-side.  Holds one pinned staging set until
+    decode_planned has queued the uploads; a plan that is dropped instead (an exception between planning and decoding,
+    a KeyboardInterrupt in a notebook) gives the set back through release() / the destructor."""
+    __slots__ = ("n", "hs", "plan", "infos", "status", "images", "png_as_tf", "consumed")
+
+    def release(self):
+        hs = getattr(self, "hs", None)
+        if hs is not None and not getattr(self, "consumed", True):
+            hs.pending = False
+        self.consumed = True
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 def plan_blobs(blobs, device=None, png_as_tf=False):
@@ -155,6 +172,7 @@ def plan_blobs(blobs, device=None, png_as_tf=False):
     pb.images = np.zeros(n, dtype=IMAGE_DESC_DTYPE)
     pb.plan = DecodePlan()
     pb.hs = None
+    pb.consumed = True
     if n == 0:
         return pb
     with _pool_lock:
@@ -162,6 +180,7 @@ def plan_blobs(blobs, device=None, png_as_tf=False):
         if pool is None:
             pool = _staging[ctx.device.index] = _StagingPool()
     hs = pb.hs = pool.take()
+    pb.consumed = False
     ptrs = (ctypes.c_void_p * n)()
     sizes = np.zeros(n, np.uint64)
     keep = []
@@ -193,7 +212,7 @@ def decode_planned(pb, device=None, timings=None, want_infos=False):
         return (arrays, np.zeros(0, np.int32), []) if want_infos else (arrays, np.zeros(0, np.int32))
     hs = pb.hs
     if plan.n_streams == 0:
-        hs.pending = False
+        pb.release()
         return (arrays, pb.status, infos) if want_infos else (arrays, pb.status)
     ssz = STREAM_DESC_DTYPE.itemsize
     blob_d = hs.stage[:plan.stage_bytes].to(ctx.device, non_blocking=True)
@@ -202,7 +221,7 @@ def decode_planned(pb, device=None, timings=None, want_infos=False):
     st_d = torch.from_numpy(pb.status).to(ctx.device, non_blocking=True)
     hs.busy = torch.cuda.Event()
     hs.busy.record(torch.cuda.current_stream(ctx.device))
-    hs.pending = False
+    pb.release()
     scratch = torch.empty((plan.scratch_bytes,), dtype=torch.uint8, device=ctx.device)
     out = torch.empty((plan.out_bytes,), dtype=torch.uint8, device=ctx.device)
     if timings is not None:

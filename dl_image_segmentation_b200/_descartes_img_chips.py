@@ -24,6 +24,34 @@ from . import ops
 from ._lib import B2Error
 
 
+_SIGNED_VIEW = {torch.uint16: torch.int16, torch.uint32: torch.int32, torch.uint64: torch.int64}
+_NP_NAME = {torch.uint8: "uint8", torch.int8: "int8", torch.uint16: "uint16", torch.int16: "int16", torch.uint32: "uint32",
+            torch.int32: "int32", torch.uint64: "uint64", torch.int64: "int64", torch.float16: "float16",
+            torch.float32: "float32", torch.float64: "float64", torch.bool: "bool"}
+_TORCH_OF = {v: k for k, v in _NP_NAME.items()}
+
+
+def _moved(t, fn):
+    """Apply a pure data-movement op (where / index_select / cat) to a tensor whose dtype torch may not implement it for
+    (uint16 / uint32): run it on the same-width signed view and view the result back."""
+    sv = _SIGNED_VIEW.get(t.dtype)
+    return fn(t) if sv is None else fn(t.view(sv)).view(t.dtype)
+
+
+def _cast(t, dtype):
+    """.astype(dtype) with NumPy's value semantics for the integer widenings np.dstack can ask for."""
+    if t.dtype == dtype:
+        return t
+    if t.dtype in _SIGNED_VIEW:                                   # unsigned source: widen through int64 (zero-extended)
+        bits = t.element_size() * 8
+        wide = t.view(_SIGNED_VIEW[t.dtype]).to(torch.int64)
+        wide = torch.where(wide < 0, wide + (1 << bits), wide) if bits < 64 else wide
+        t = wide
+    if dtype in _SIGNED_VIEW:                                     # unsigned target: values fit, store through the signed twin
+        return t.to(torch.int64).to(_SIGNED_VIEW[dtype]).view(dtype)
+    return t.to(dtype)
+
+
 class MaskedResult:
     """np.ma-compatible pair living on the device: ``data`` (H,W,B) and boolean ``mask`` (True = masked)."""
 
@@ -35,7 +63,11 @@ class MaskedResult:
         return np.ma.MaskedArray(self.data.cpu().numpy(), mask=self.mask.cpu().numpy())
 
     def filled(self, fill_value=0):
-        return torch.where(self.mask, torch.as_tensor(fill_value, dtype=self.data.dtype, device=self.data.device), self.data)
+        fill = torch.from_numpy(np.asarray(fill_value).astype(_NP_NAME[self.data.dtype]).reshape(1)).to(self.data.device)
+        sv = _SIGNED_VIEW.get(self.data.dtype)
+        if sv is not None:
+            fill = fill.view(sv)
+        return _moved(self.data, lambda d: torch.where(self.mask, fill.reshape(()), d))
 
 
 class SceneStack:
@@ -90,7 +122,7 @@ def _select_scenes(stack, valid, keep):
     if keep == list(range(keep[0], keep[-1] + 1)):
         return stack[keep[0]:keep[-1] + 1], valid[keep[0]:keep[-1] + 1]
     ix = torch.as_tensor(keep, dtype=torch.int64, device=stack.device)
-    return stack.index_select(0, ix), valid.index_select(0, ix)
+    return _moved(stack, lambda t: t.index_select(0, ix)), _moved(valid, lambda t: t.index_select(0, ix))
 
 
 def median_composite(stack, valid, nodata_mask=None, device=None):
@@ -167,13 +199,21 @@ def stack_products_for_tile(ctx, products, bands_per_product, resampler="near", 
     arrays = []
     for product in products:
         sc = scene_source.search(ctx, product)
+        if sc is None or len(sc.dates) == 0:
+            # the reference does not test for this (:512-513): SceneCollection.mosaic of an empty collection raises
+            raise ValueError("This SceneCollection is empty (product %r)" % (product,))
         # plain mosaic(): scenes painted in search order == every scene at the same "distance", later index wins
         same_day = [0] * len(sc.dates)
         res = nearest_date_mosaic(sc.stack, sc.valid, same_day, None, 0)
         arrays.append(res.data)                     # kernel already wrote 0 where no scene is valid
-    if len({a.dtype for a in arrays}) > 1:          # np.dstack promotes mixed dtypes
-        dt = arrays[0].dtype
-        for a in arrays[1:]:
-            dt = torch.promote_types(dt, a.dtype)
-        arrays = [a.to(dt) for a in arrays]
-    return torch.cat(arrays, dim=-1)
+    if len({a.dtype for a in arrays}) > 1:          # np.dstack promotes mixed dtypes by NumPy's rules (u16 + i16 -> int32)
+        dt = np.result_type(*[np.dtype(_NP_NAME[a.dtype]) for a in arrays])
+        arrays = [_cast(a, _TORCH_OF[dt.name]) for a in arrays]
+    return _cat_last(arrays)
+
+
+def _cat_last(arrays):
+    sv = _SIGNED_VIEW.get(arrays[0].dtype)
+    if sv is None:
+        return torch.cat(arrays, dim=-1)
+    return torch.cat([a.view(sv) for a in arrays], dim=-1).view(arrays[0].dtype)

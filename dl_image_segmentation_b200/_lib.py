@@ -62,7 +62,6 @@ SIGNATURES = {
     "b2_ctx_destroy": (_i, [_vp]),
     "b2_ctx_launch_count": (_u64, [_vp]),
     "b2_ctx_sm_count": (_i, [_vp]),
-    "b2_debug_parse_phases": (_i, [_vp, ctypes.POINTER(_u64)]),
     "b2_median_composite_u16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "b2_nearest_date_mosaic": (_i, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f, _i, _i, _i, _i, _i, _i,
                                     _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -226,7 +226,8 @@ def parse_encoded_gdal_proto_eager(example_proto, device=None):
 
 
 def parse_encoded_gdal_proto_wrapped(example_proto, device=None):
-    """As _eager but always float32 (reference :319-346)."""
+    """As _eager but always float32, and without _eager's comparison with the recorded shape (reference :319-346)."""
     from . import _codec
-    img, tgt, ident = parse_encoded_gdal_proto_eager(example_proto, device)
+    ib, _, tb, _, ident = _parse_byteslist_proto(example_proto, device)
+    img, tgt = _decode_pair(ib, tb, device)
     return _codec.to_float32(img), _codec.to_float32(tgt), ident

@@ -129,8 +129,8 @@ def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, devi
         for k, f in zip(todo, _codec.encode_jpeg_arrays([pa[k] for k in todo], quality=100, device=ctx.device)):
             print("Converting PNG to JPEG for %s" % (img_paths, lbl_paths)[k % 2][k // 2])
             blobs[k] = f
-        if planned is not None and planned.hs is not None:
-            planned.hs.pending = False                                      # planned from the PNG bytes: give its staging set back
+        if planned is not None:
+            planned.release()                                               # planned from the PNG bytes: give its staging set back
         planned = None
         del pa
     if store_as_array:                                                      # ONE native planning call + the decode kernels
@@ -138,6 +138,16 @@ def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, devi
             planned = _codec.plan_blobs(blobs, ctx.device, png_as_tf)
         arrays, st, infos = _codec.decode_planned(planned, ctx.device, want_infos=True)
         arrays, st, infos = _codec.merge_jpeg(blobs, arrays, st, infos, ctx.device, candidates=np.nonzero(st)[0])   # .jpg chips
+        for k in range(2 * n):
+            if len(blobs[k]) and infos[k].status == 0 and st[k] != 0 and errs[k // 2] is None:
+                errs[k // 2] = ChipError("could not decode %s (codec status %d)" % ((img_paths, lbl_paths)[k % 2][k // 2], int(st[k])))
+    elif validate is not None:
+        # threaded translator: the reference decodes every chip even when it stores the file bytes
+        # (_img_to_tf_threaded.py:94-105), so a PNG whose IDAT data does not inflate is skipped, not stored
+        if planned is None:
+            planned = _codec.plan_blobs(blobs, ctx.device, png_as_tf)
+        _, st, infos = _codec.decode_planned(planned, ctx.device, want_infos=True)
+        _, st, infos = _codec.merge_jpeg(blobs, [None] * (2 * n), st, infos, ctx.device, candidates=np.nonzero(st)[0])
         for k in range(2 * n):
             if len(blobs[k]) and infos[k].status == 0 and st[k] != 0 and errs[k // 2] is None:
                 errs[k // 2] = ChipError("could not decode %s (codec status %d)" % ((img_paths, lbl_paths)[k % 2][k // 2], int(st[k])))
@@ -231,7 +241,7 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
         def read_and_plan(paths):
             blobs = reader.read(paths)                                      # one native call; the GIL is free meanwhile
             planned = None
-            if store_as_array and not png_to_jpg:                           # host half of the decode, off the main thread
+            if (store_as_array or validate is not None) and not png_to_jpg: # host half of the decode, off the main thread
                 planned = _codec.plan_blobs([b"" if isinstance(b, Exception) else b for b in blobs], ctx.device, png_as_tf)
             return blobs, planned
 
@@ -241,71 +251,80 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                 paths += [img_filenames[i], lbl_filenames[i]]
             return pool.submit(read_and_plan, paths)
         pending_reads = submit_reads(batches[0]) if batches else None
-        for bi, (b0, b1) in enumerate(batches):
-            blobs, planned = pending_reads.result()
-            pending_reads = submit_reads(batches[bi + 1]) if bi + 1 < len(batches) else None
-            idx = list(range(b0, b1))
-            pairs = load_pairs([img_filenames[i] for i in idx], [lbl_filenames[i] for i in idx], store_as_array,
-                               key_fn, validate, ctx.device, blobs=blobs, png_as_tf=png_as_tf, planned=planned,
-                               png_to_jpg=png_to_jpg)
-            for s in range(per):
-                lo, hi = max(b0, int(shard_ranges[s])), min(b1, int(shard_ranges[s + 1]))
-                if lo >= hi:
-                    continue
-                items = []
-                for i in range(lo, hi):
-                    p = pairs[i - b0]
-                    if isinstance(p, Exception):
-                        print(p)
-                        print("SKIPPED: Unexpected eror while decoding %s." % img_filenames[i])
+        try:
+            for bi, (b0, b1) in enumerate(batches):
+                blobs, planned = pending_reads.result()
+                pending_reads = submit_reads(batches[bi + 1]) if bi + 1 < len(batches) else None
+                idx = list(range(b0, b1))
+                pairs = load_pairs([img_filenames[i] for i in idx], [lbl_filenames[i] for i in idx], store_as_array,
+                                   key_fn, validate, ctx.device, blobs=blobs, png_as_tf=png_as_tf, planned=planned,
+                                   png_to_jpg=png_to_jpg)
+                for s in range(per):
+                    lo, hi = max(b0, int(shard_ranges[s])), min(b1, int(shard_ranges[s + 1]))
+                    if lo >= hi:
                         continue
-                    items.append(p)
-                    shard_count[s] += 1
-                    counter += 1
-                    if not counter % progress_every:
-                        print("%s [%s %d]: Processed %d of %d images in %s batch." %
-                              (datetime.now(), label, worker_index, counter, num_files, label))
-                        sys.stdout.flush()
-                if items:
-                    buf, _, total = ops.build_records(items, ctx.device)
-                    slot = seq % n_slots
-                    seq += 1
-                    for x in slot_futs[slot]:                                # the writes that last used this buffer
-                        for y in x.result():
-                            y.result()
-                    slot_futs[slot] = []
-                    if pinned[slot] is None or pinned[slot].numel() < total:
-                        pinned[slot] = torch.empty((int(total * 1.1) + 4096,), dtype=torch.uint8).pin_memory()
-                    host = pinned[slot][:total]
-                    host.copy_(buf[:total], non_blocking=True)
-                    done = torch.cuda.Event()
-                    done.record(torch.cuda.current_stream(ctx.device))
+                    items = []
+                    for i in range(lo, hi):
+                        p = pairs[i - b0]
+                        if isinstance(p, Exception):
+                            print(p)
+                            print("SKIPPED: Unexpected eror while decoding %s." % img_filenames[i])
+                            continue
+                        items.append(p)
+                        shard_count[s] += 1
+                        counter += 1
+                        if not counter % progress_every:
+                            print("%s [%s %d]: Processed %d of %d images in %s batch." %
+                                  (datetime.now(), label, worker_index, counter, num_files, label))
+                            sys.stdout.flush()
+                    if items:
+                        buf, _, total = ops.build_records(items, ctx.device)
+                        slot = seq % n_slots
+                        seq += 1
+                        for x in slot_futs[slot]:                                # the writes that last used this buffer
+                            for y in x.result():
+                                y.result()
+                        slot_futs[slot] = []
+                        if pinned[slot] is None or pinned[slot].numel() < total:
+                            pinned[slot] = torch.empty((int(total * 1.1) + 4096,), dtype=torch.uint8).pin_memory()
+                        host = pinned[slot][:total]
+                        host.copy_(buf[:total], non_blocking=True)
+                        done = torch.cuda.Event()
+                        done.record(torch.cuda.current_stream(ctx.device))
 
-                    def _write(fd=files[s].fileno(), h=host, ev=done, off=shard_off[s]):
-                        ev.synchronize()                                     # the records have arrived in pinned memory
-                        src = h.numpy()
-                        step = 16 << 20
-                        if use_mmap:
-                            # write(2) on one file serialises on its inode lock (measured: 8 threads of pwrite = 3.5 GB/s
-                            # on tmpfs, the speed of one); page faults on a shared mapping do not, so the chunks are
-                            # copied into a mapping of the (grown) file by several threads at once
-                            end = off + len(src)
-                            try:
-                                os.ftruncate(fd, end)                        # this thread is the only one that grows files
-                                a0 = off & ~(mmap.ALLOCATIONGRANULARITY - 1)
-                                mm = mmap.mmap(fd, end - a0, offset=a0)
-                            except (OSError, ValueError):                    # a file system without shared mappings: write(2)
-                                mm = None
-                            if mm is not None:
-                                dst = np.frombuffer(mm, dtype=np.uint8)[off - a0:]
-                                return [wpool.submit(np.copyto, dst[o:o + step], src[o:o + step]) for o in range(0, len(src), step)]
-                        mv = memoryview(src)                                 # positional writes: order-free, several in flight
-                        return [wpool.submit(os.pwrite, fd, mv[o:o + step], off + o) for o in range(0, len(mv), step)]
-                    shard_off[s] += total
-                    slot_futs[slot].append(writer.submit(_write))
-                if hi == int(shard_ranges[s + 1]):
-                    print("%s [%s %d]: Wrote %d images to %s" % (datetime.now(), label, worker_index, shard_count[s], files[s].name))
-                    sys.stdout.flush()
+                        def _write(fd=files[s].fileno(), h=host, ev=done, off=shard_off[s]):
+                            ev.synchronize()                                     # the records have arrived in pinned memory
+                            src = h.numpy()
+                            step = 16 << 20
+                            if use_mmap:
+                                # write(2) on one file serialises on its inode lock (measured: 8 threads of pwrite = 3.5 GB/s
+                                # on tmpfs, the speed of one); page faults on a shared mapping do not, so the chunks are
+                                # copied into a mapping of the (grown) file by several threads at once
+                                end = off + len(src)
+                                try:
+                                    os.ftruncate(fd, end)                        # this thread is the only one that grows files
+                                    a0 = off & ~(mmap.ALLOCATIONGRANULARITY - 1)
+                                    mm = mmap.mmap(fd, end - a0, offset=a0)
+                                except (OSError, ValueError):                    # a file system without shared mappings: write(2)
+                                    mm = None
+                                if mm is not None:
+                                    dst = np.frombuffer(mm, dtype=np.uint8)[off - a0:]
+                                    return [wpool.submit(np.copyto, dst[o:o + step], src[o:o + step]) for o in range(0, len(src), step)]
+                            mv = memoryview(src)                                 # positional writes: order-free, several in flight
+                            return [wpool.submit(os.pwrite, fd, mv[o:o + step], off + o) for o in range(0, len(mv), step)]
+                        shard_off[s] += total
+                        slot_futs[slot].append(writer.submit(_write))
+                    if hi == int(shard_ranges[s + 1]):
+                        print("%s [%s %d]: Wrote %d images to %s" % (datetime.now(), label, worker_index, shard_count[s], files[s].name))
+                        sys.stdout.flush()
+        finally:
+            if pending_reads is not None:                                   # aborted with a read-ahead in flight: hand its
+                try:                                                        # pinned staging set back
+                    _, dropped = pending_reads.result()
+                    if dropped is not None:
+                        dropped.release()
+                except Exception:
+                    pass
         for fl in slot_futs:
             for x in fl:
                 for y in x.result():

@@ -720,6 +720,7 @@ uint32_t dev_row_mask() {
 // Tiles per scheduler chunk (= the longest run whose per-thread CRC state is carried): 2 keeps the output streams of the
 // normalise + one-hot pass balanced; the CRC-only and raw passes amortise the per-run alignment multiply over 8.
 uint32_t tiles_per_cta(int mode) {
+#ifdef B2_DEV_KNOBS
     static int q = -1;
     if (q < 0) {
         const char* e = getenv("B2_PARSE_TILES_PER_CTA");
@@ -727,7 +728,19 @@ uint32_t tiles_per_cta(int mode) {
         if (q < 0) q = 0;
         if (q > 64) q = 64;
     }
-    return q ? (uint32_t)q : (mode == B2_SINK_NORM_ONEHOT ? 2u : 8u);
+    if (q) return (uint32_t)q;
+#endif
+    return mode == B2_SINK_NORM_ONEHOT ? 2u : 8u;
+}
+
+// Per-phase cycle counters are a development-build feature; the shipped library never reads the environment per call.
+unsigned long long* dev_profile(b2_ctx* ctx) {
+#ifdef B2_DEV_KNOBS
+    return getenv("B2_PARSE_PROFILE") ? ctx->prof_dev : nullptr;
+#else
+    (void)ctx;
+    return nullptr;
+#endif
 }
 
 }  // namespace
@@ -767,7 +780,7 @@ extern "C" int b2_tfrecord_parse_table(b2_ctx* ctx, const uint8_t* shard, uint64
     const TableView v = table_view(table, nbytes, max_records);
     ParseArgs pa{shard, nbytes, v.rec_off, v.rec_len, v.index, *sink, ctx->crc_dev, v.tile2rec, v.tile_start, v.hdr,
                  0, 0, tiles_per_cta(sink->mode), v.acc, status, nullptr, v.hdr + 4, reinterpret_cast<uint32_t*>(v.hdr + 5),
-                 getenv("B2_PARSE_PROFILE") ? ctx->prof_dev : nullptr, dev_row_mask()};
+                 dev_profile(ctx), dev_row_mask()};
     return launch_fused(ctx, pa, v.cap_tiles, static_cast<cudaStream_t>(stream));
 }
 
@@ -794,7 +807,10 @@ extern "C" int b2_crc32c(b2_ctx* ctx, const uint8_t* data, const uint64_t* offse
     return launch_fused(ctx, pa, tx * (uint64_t)n, s);
 }
 
-/* development aid: read and reset the phase counters filled when B2_PARSE_PROFILE is set */
+#ifdef B2_DEV_KNOBS
+/* development builds only (make DEV=1): with B2_PARSE_PROFILE set, b2_tfrecord_parse_table accumulates the cycles lane 0
+ * of every warp spends in { tile wait, CRC, image sink, one-hot sink, end barrier, flush, job fetch, - } (out[0..7]: warp
+ * 0, which also fetches the jobs; out[8..15]: the other warps); read and reset them here.  Not part of include/b2chips.h. */
 extern "C" int b2_debug_parse_phases(b2_ctx* ctx, uint64_t out[16]) {
     B2_REQUIRE(ctx && out, "b2_debug_parse_phases: NULL argument");
     DeviceGuard g(ctx->device);
@@ -803,3 +819,4 @@ extern "C" int b2_debug_parse_phases(b2_ctx* ctx, uint64_t out[16]) {
     B2_CUDA(cudaMemset(ctx->prof_dev, 0, 128));
     return 0;
 }
+#endif

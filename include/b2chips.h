@@ -41,10 +41,6 @@ int b2_ctx_destroy(b2_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t b2_ctx_launch_count(const b2_ctx* ctx);
 int b2_ctx_sm_count(const b2_ctx* ctx);
-/* development aid: with B2_PARSE_PROFILE set, b2_tfrecord_parse_table accumulates the cycles lane 0 of every warp
- * spends in { tile wait, CRC, image sink, one-hot sink, end barrier, flush, job fetch, - } (out[0..7]: warp 0, which
- * also fetches the jobs; out[8..15]: the other warps); read and reset them here */
-int b2_debug_parse_phases(b2_ctx* ctx, uint64_t out[16]);
 
 /* ------------------------------------------------------------------ K3: compositors
  * b2_median_composite_u16 replaces np.repeat + np.ma.masked_where + np.ma.median(axis=0)

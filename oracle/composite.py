@@ -65,3 +65,27 @@ def nearest_date_mosaic(stack, valid, scene_day, scene_cf, ref_day, min_day=None
 
 def stack_products(arrays):
     return np.dstack(arrays)                                    # :516
+
+
+def search_filter(scene_dates, min_date=None, max_date=None):
+    """Indices kept by ``dl.scenes.search(start_datetime=min_date, end_datetime=max_date)`` (``:549-552``): acquired in
+    ``[min_date, max_date)``.  Dates are ``datetime.date`` / ``datetime`` objects or plain day numbers."""
+    import datetime as _dt
+
+    def day(d):
+        if isinstance(d, _dt.datetime):
+            return d.date().toordinal()
+        return d.toordinal() if isinstance(d, _dt.date) else int(d)
+    lo = None if min_date is None else day(min_date)
+    hi = None if max_date is None else day(max_date)
+    return [i for i, d in enumerate(scene_dates) if (lo is None or day(d) >= lo) and (hi is None or day(d) < hi)]
+
+
+def create_cloudmasked_s2_array(scene_dates, stack, valid_cloudfree, nodata_mask=None, min_date=None, max_date=None):
+    """``create_cloudmasked_s2_array`` ``:521-568`` on an in-memory catalogue: date search, ``None`` when nothing is left
+    (``:554-555``), then the masked median of the surviving scenes."""
+    keep = search_filter(scene_dates, min_date, max_date)
+    if not keep:
+        return None
+    nd = None if nodata_mask is None else np.asarray(nodata_mask)[keep]
+    return median_composite(np.asarray(stack)[keep], np.asarray(valid_cloudfree)[keep], nd)

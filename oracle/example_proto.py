@@ -291,14 +291,15 @@ def parse_encoded_gdal_proto_eager(example_proto):
     # :349-386 — native dtype, shape asserts
     from .imagecodecs import decode_image
     ib, ishp, tb, tshp, ident = _parse_byteslist_proto(example_proto)
-    img = decode_image(ib)
+    img = decode_image(ib, png_as_tf=False)                     # rasterio -> GDAL's view of the file
     assert img.shape == tuple(int(x) for x in ishp)
-    tgt = decode_image(tb)
+    tgt = decode_image(tb, png_as_tf=False)
     assert tgt.shape[0] == int(tshp[0]) and tgt.shape[1] == int(tshp[1])
     return img, tgt, ident
 
 
 def parse_encoded_gdal_proto_wrapped(example_proto):
-    # :319-346 — always float32
-    img, tgt, ident = parse_encoded_gdal_proto_eager(example_proto)
-    return img.astype(np.float32), tgt.astype(np.float32), ident
+    # :319-346 — always float32; unlike _eager it never compares with the recorded shape
+    from .imagecodecs import decode_image
+    ib, _, tb, _, ident = _parse_byteslist_proto(example_proto)
+    return (decode_image(ib, png_as_tf=False).astype(np.float32), decode_image(tb, png_as_tf=False).astype(np.float32), ident)

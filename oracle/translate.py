@@ -79,6 +79,61 @@ def images_to_tfrecords(name, directory, out_directory, num_shards, num_proc=Non
     return sum(res)
 
 
+# ------------------------------------------------------------------ threaded flavour (_img_to_tf_threaded.py)
+def process_image_mt(path, parse_dltile_filename=True, png_to_jpg=False, decode=False):
+    """_process_image (_img_to_tf_threaded.py:75-121): read; PNG (substring test :72) -> decode_png, or transcode to
+    JPEG q=100 then decode_jpeg (:92-100); anything else -> decode_jpeg (:103); assert 3-D and <= 3 bands (:107-112);
+    key = file name only (:113-116); return the decoded array or the (possibly transcoded) file bytes (:118-121)."""
+    from . import jpegcodec, jpegenc
+    with open(path, "rb") as f:
+        data = f.read()
+    if ".png" in path:
+        image = imagecodecs.decode_png(data, as_tf=True)                    # tf.image.decode_png
+        if png_to_jpg:
+            if image.shape[2] not in (1, 3):
+                raise ValueError("encode_jpeg: image must have 1 or 3 channels")
+            data = jpegenc.encode_jpeg(image, quality=100, density=(1, 300, 300))   # tf.image.encode_jpeg defaults
+            image = jpegcodec.decode_jpeg(data)
+    else:
+        image = jpegcodec.decode_jpeg(data)
+    assert image.ndim == 3
+    h, w, b = image.shape
+    assert b <= 3
+    return (image if decode else data), h, w, b, partition.tile_key(path, parse_dltile_filename)
+
+
+def build_record_mt(img_path, lbl_path, dltile_from_filename=True, png_to_jpg=False, store_as_array=False):
+    ib, ih, iw, ibands, ikey = process_image_mt(img_path, dltile_from_filename, png_to_jpg, store_as_array)
+    lb, lh, lw, _, lkey = process_image_mt(lbl_path, dltile_from_filename, png_to_jpg, store_as_array)
+    assert ikey == lkey
+    return example_proto.convert_to_example(ib, lb, ih, iw, ibands, lh, lw, ikey).SerializeToString(deterministic=True)
+
+
+def images_to_tfrecords_mt(name, directory, out_directory, num_shards, num_threads=None, dltile_from_filename=True,
+                           convert_png_to_jpg=False, store_as_array=False):
+    """process_dataset_multithreaded (_img_to_tf_threaded.py:321-350) with the worker loop :136-219, run serially."""
+    if not num_threads:
+        num_threads = num_shards
+    assert not num_shards % num_threads
+    imgs, lbls = partition.find_image_files(directory, "png", also_jpg=True)
+    ranges = partition.worker_ranges(len(imgs), num_threads)
+    per = num_shards // num_threads
+    written = 0
+    os.makedirs(out_directory, exist_ok=True)
+    for t in range(len(ranges)):
+        sr = np.linspace(ranges[t][0], ranges[t][1], per + 1).astype(int)
+        for s in range(per):
+            with tfrecord.TFRecordWriter(os.path.join(out_directory, partition.shard_name(name, t * per + s, num_shards))) as w:
+                for i in range(int(sr[s]), int(sr[s + 1])):
+                    try:
+                        rec = build_record_mt(imgs[i], lbls[i], dltile_from_filename, convert_png_to_jpg, store_as_array)
+                    except Exception:                           # :196-199
+                        continue
+                    w.write(rec)
+                    written += 1
+    return written
+
+
 def parse_records_norm_onehot(records, mean, std, num_classes):
     """records: list of Example bytes (uint8 arrays stored as BytesList) -> (N,H,W,C) f32, (N,H,W,K) f32.
 

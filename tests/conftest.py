@@ -3,6 +3,7 @@ import sys
 
 import pytest
 
+os.environ.setdefault("OPENCV_LOG_LEVEL", "SILENT")       # libtiff's "unknown GeoTIFF tag" chatter through OpenCV
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

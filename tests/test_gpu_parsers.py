@@ -1,0 +1,154 @@
+"""-m gpu: the encoded-blob parsers and band stacking (A16) at the BASELINE chip shapes, through
+the drop-in API, against the oracle's restatement of `_tfrecord_image_translation.py:269-386` and `np.dstack`
+(`_descartes_img_chips.py:516`).  The small reference-run fixtures for the same entry points live in
+tests/test_reference_parity.py."""
+import numpy as np
+import pytest
+import torch
+
+import synthetic as syn
+from oracle import example_proto as oep
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda", 0)
+
+
+def _np(t):
+    if t.dtype == torch.uint16:
+        return t.view(torch.int16).cpu().numpy().view(np.uint16)
+    return t.cpu().numpy()
+
+
+def _same(got, want):
+    g = _np(got)
+    assert g.dtype == want.dtype and g.shape == want.shape and np.array_equal(g, want)
+
+
+def test_gdal_parsers_on_cfg3_lzw_geotiff_records(dev):
+    """configs[2] raw-bytes records: 512x512x4 uint16 tiled-LZW GeoTIFF + 512x512 uint8 label blob."""
+    import dl_image_segmentation_b200 as pkg
+    for i, kw in enumerate((dict(tile=256), dict(tile=None, predictor=2), dict(tile=256, compression="deflate"))):
+        img, lab, key = syn.cfg3_chip(40 + i)
+        ib, lb = syn.tiff_bytes(img, **kw), syn.tiff_bytes(lab, nodata=255, **kw)
+        rec = oep.convert_to_example(ib, lb, 512, 512, 4, 512, 512, key).SerializeToString()
+        gi, gt, gid = pkg.parse_encoded_gdal_proto_eager(rec)
+        wi, wt, wid = oep.parse_encoded_gdal_proto_eager(rec)
+        assert gi.dtype == torch.uint16 and tuple(gt.shape) == (512, 512, 1) and gid == wid == key.encode()
+        _same(gi, wi)
+        _same(gt, wt)
+        assert np.array_equal(wi, img) and np.array_equal(wt[..., 0], lab)
+        fi, ft, fid = pkg.parse_encoded_gdal_proto_wrapped(rec)
+        wfi, wft, _ = oep.parse_encoded_gdal_proto_wrapped(rec)
+        assert fi.dtype == torch.float32 and ft.dtype == torch.float32 and fid == wid
+        _same(fi, wfi)
+        _same(ft, wft)
+
+
+def test_eager_parser_checks_the_recorded_shape_and_wrapped_does_not(dev):
+    """`_eager` asserts decoded shape == recorded shape (`:377,383-384`); `_wrapped` has no such check (`:332-346`)."""
+    import dl_image_segmentation_b200 as pkg
+    img, lab, key = syn.cfg3_chip(3, size=64)
+    ib, lb = syn.tiff_bytes(img, tile=32), syn.tiff_bytes(lab, tile=32)
+    rec = oep.convert_to_example(ib, lb, 64, 60, 4, 64, 64, key).SerializeToString()       # width recorded wrongly
+    with pytest.raises(AssertionError):
+        pkg.parse_encoded_gdal_proto_eager(rec)
+    with pytest.raises(AssertionError):
+        oep.parse_encoded_gdal_proto_eager(rec)
+    fi, ft, _ = pkg.parse_encoded_gdal_proto_wrapped(rec)
+    _same(fi, img.astype(np.float32))
+    _same(ft, lab[..., None].astype(np.float32))
+
+
+def test_rgb_and_gdal_parsers_on_cfg1_png_records(dev):
+    """configs[0] raw-bytes records (threaded translator, store_as_array=False): PNG blobs, label comes back (H,W,1)."""
+    import dl_image_segmentation_b200 as pkg
+    for i in range(3):
+        img, lab, key = syn.cfg1_chip(70 + i)
+        rec = oep.convert_to_example(syn.png_bytes(img), syn.png_bytes(lab), 256, 256, 3, 256, 256, key).SerializeToString()
+        for parser in ("parse_encoded_rgb_img_proto", "parse_encoded_gdal_proto_eager", "parse_encoded_gdal_proto_wrapped"):
+            gi, gt, gid = getattr(pkg, parser)(rec)
+            wi, wt, wid = getattr(oep, parser)(rec)
+            assert tuple(gi.shape) == (256, 256, 3) and tuple(gt.shape) == (256, 256, 1) and gid == wid
+            _same(gi, wi)
+            _same(gt, wt)
+        assert np.array_equal(wi, img.astype(np.float32)) and np.array_equal(wt[..., 0], lab.astype(np.float32))
+
+
+def test_rgb_parser_and_gdal_parser_disagree_on_palette_pngs_as_the_libraries_do(dev):
+    """tf.io.decode_image expands a palette to RGB; GDAL presents one band of indices: each parser keeps the semantics of
+    the call it replaces."""
+    import dl_image_segmentation_b200 as pkg
+    rng = np.random.default_rng(5)
+    idx = rng.integers(0, 7, (24, 20)).astype(np.uint8)
+    pal = rng.integers(0, 256, (7, 3)).astype(np.uint8)
+    blob = syn.png_bytes_flavour(idx, 8, 3, palette=pal)
+    lab = syn.png_bytes(idx)
+    rec = oep.convert_to_example(blob, lab, 24, 20, 3, 24, 20, "p").SerializeToString()
+    gi, _, _ = pkg.parse_encoded_rgb_img_proto(rec)
+    _same(gi, pal[idx])
+    rec1 = oep.convert_to_example(blob, lab, 24, 20, 1, 24, 20, "p").SerializeToString()
+    gi, _, _ = pkg.parse_encoded_gdal_proto_eager(rec1)
+    _same(gi, idx[..., None])
+
+
+def test_stack_products_matches_numpy_dstack_for_mixed_dtypes(dev):
+    """A16: per-product overlay mosaic, then np.dstack with NumPy's promotion (u16+u8 -> u16, u16+i16 -> i32, +f32 -> f64 / f32)."""
+    import dl_image_segmentation_b200 as pkg
+    from dl_image_segmentation_b200 import _descartes_img_chips as dc
+    from oracle import composite as ocomp
+    rng = np.random.default_rng(77)
+    H, W = 256, 256
+    specs = {"a": (np.uint16, 3), "b": (np.uint8, 1), "c": (np.int16, 2), "d": (np.float32, 2)}
+    src = dc.SyntheticSceneSource()
+    want = {}
+    for name, (dt_, nb) in specs.items():
+        T = 3
+        if np.issubdtype(dt_, np.integer):
+            st = rng.integers(np.iinfo(dt_).min, np.iinfo(dt_).max, (T, H, W, nb), endpoint=True).astype(dt_)
+        else:
+            st = rng.normal(size=(T, H, W, nb)).astype(dt_)
+        va = (rng.random((T, H, W)) > 0.4).astype(np.uint8)
+        src.add("ctx", name, dc.SceneStack(st, va, [0] * T))
+        want[name] = ocomp.nearest_date_mosaic(st, va, [0] * T, [0.0] * T, 0)[0]
+    for combo in (("a", "b"), ("a", "c"), ("b", "c"), ("a", "b", "c"), ("a", "d"), ("c", "d"), ("a",)):
+        got = pkg.stack_products_for_tile("ctx", list(combo), ["x"] * len(combo), scene_source=src)
+        ref = np.dstack([want[n] for n in combo])
+        g = got.view(torch.int32).cpu().numpy().view(np.uint32) if got.dtype == torch.uint32 else _np(got)
+        assert g.dtype == ref.dtype, (combo, g.dtype, ref.dtype)
+        assert np.array_equal(g, ref), combo
+
+
+def test_uint16_mosaic_filled_and_noncontiguous_date_filter(dev):
+    """`filled()` on a uint16 mosaic and a search filter that keeps a non-contiguous set of scenes."""
+    import datetime as dt
+
+    import dl_image_segmentation_b200 as pkg
+    from dl_image_segmentation_b200 import _descartes_img_chips as dc
+    from oracle import composite as ocomp
+    rng = np.random.default_rng(78)
+    T, H, W, B = 6, 40, 36, 3
+    st = rng.integers(0, 65536, (T, H, W, B)).astype(np.uint16)
+    va = (rng.random((T, H, W)) > 0.5).astype(np.uint8)
+    va[:, :3, :3] = 0
+    days = [dt.date(2020, 1, 1) + dt.timedelta(days=10 * t) for t in range(T)]
+    res = pkg.nearest_date_mosaic(st, va, days, None, dt.date(2020, 1, 25))
+    out, mask, _ = ocomp.nearest_date_mosaic(st, va, [d.toordinal() for d in days], [0.0] * T, dt.date(2020, 1, 25).toordinal())
+    filled = res.filled(65535)
+    assert filled.dtype == torch.uint16
+    want = out.copy()
+    want[mask] = 65535
+    _same(filled, want)
+    # median over scenes {0, 2, 3, 5}: dates out of order in the catalogue so that the window keeps a non-contiguous set
+    shuffled = [days[0], days[5], days[1], days[2], days[4], days[3]]
+    src = dc.SyntheticSceneSource()
+    src.add("c", "sentinel-2:L1C", dc.SceneStack(st, va, shuffled))
+    lo, hi = dt.date(2020, 1, 1), dt.date(2020, 2, 5)                     # keeps days[0..3] -> catalogue indices 0, 2, 3, 5
+    got = pkg.create_cloudmasked_s2_array("c", min_date=lo, max_date=hi, scene_source=src).to_masked_array()
+    ref = ocomp.create_cloudmasked_s2_array(shuffled, st, va, None, lo, hi)
+    assert np.array_equal(np.ma.getmaskarray(got), np.ma.getmaskarray(ref)) and np.array_equal(got.filled(0), ref.filled(0))

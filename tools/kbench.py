@@ -242,8 +242,10 @@ def bench_parse(dev, n_shards=8):
                             status=status)
         report(name, timeit(fn, 16), algo)
         assert not status.cpu().numpy().any()
-    if os.environ.get("B2_PARSE_PROFILE"):
+    if os.environ.get("B2_PARSE_PROFILE"):                 # development build only: make -C csrc clean all DEV=1
         import ctypes
+        assert hasattr(_lib.lib(), "b2_debug_parse_phases"), "B2_PARSE_PROFILE needs a DEV=1 build of libb2chips.so"
+        _lib.lib().b2_debug_parse_phases.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
         ph = (ctypes.c_uint64 * 16)()
         _lib.check(_lib.lib().b2_debug_parse_phases(_lib.get_ctx(dev).handle, ph))     # reset
         for i in range(4):
