@@ -40,161 +40,286 @@ __device__ __forceinline__ uint32_t lzw_cum_bits(uint32_t k) {
 }
 __device__ __forceinline__ uint32_t lzw_width(uint32_t k) { return 9u + (k >= 254) + (k >= 766) + (k >= 1790); }
 
-constexpr int kLzwWarps = 4;
-constexpr int kLzwMaxCodes = 3840;  // code positions per segment (entries 258..4095 -> at most 3838 + slack)
+// One CTA per compressed stream (tile or strip), a whole Clear-delimited SEGMENT per pass (<= 3838 codes):
+//   A  the segment's input words are staged in shared memory with coalesced loads; thread t then extracts codes
+//      15 t .. 15 t + 14 from a sliding 64-bit window (a code's bit position depends only on its index); the first control
+//      code (Clear / EOI / end of input) bounds the segment;
+//   B  code k >= 258 names table entry e = code - 258 = "string of code e plus the first byte of string e + 1", so the
+//      strings form a forest over the code positions (parent(k) = e < k).  Pointer jumping over that forest gives every
+//      string's depth (= length - 1) and root (= its first byte) in O(log depth) rounds, each thread keeping its 15 nodes
+//      in registers;
+//   C  a block scan of the lengths gives the output offsets (registers again: a thread emits its own strings);
+//   D  one thread per string walks its chain and writes the bytes back to front — the last byte of string k is the
+//      first byte of string e + 1, then the same for e's own entry, ... down to the root literal: the classic table walk,
+//      except that no table is ever built and every string of the segment is produced at the same time.  The bytes go to
+//      a shared-memory window laid out with the alignment of their destination and leave in 16-byte stores.
+// About 1.5 warp instructions per output byte on noisy 16-bit chips (the 32-codes-per-warp-round kernel this replaces
+// needed about eight).
+constexpr int kLzwThreads = 256;
+constexpr int kLzwPer = 15;                          // codes per thread and segment
+constexpr int kLzwMaxCodes = kLzwThreads * kLzwPer;  // 3840 >= 3838 = entries 258..4095 plus the code that sees the table full
+constexpr int kLzwInWords = 1408;                    // 43 270 bits of a full segment + alignment, rounded to 5.5 words per thread
+constexpr int kLzwWindow = 12288;                    // output bytes per flush
 
-constexpr int kLzwOffs = kLzwMaxCodes + 40;   // per resident warp, in the context workspace: offs[k] = output offset of
-                                              // code position k of the current segment (kept out of shared memory so
-                                              // that 64 warps per SM stay resident: the decode is latency-bound)
-struct LzwWarpSmem {
-    uint32_t b_off[33];                // this round: output offset of each lane's string (+ end sentinel)
-    int32_t b_src[32];                 // >=0: source offset in dst ; <0: literal value = -1 - b_src
+struct LzwSmem {
+    uint32_t tcode[kLzwMaxCodes + 8];  // [15:0] code at position k, [23:16] first byte of its string (after phase B)
+    union {
+        uint32_t tnode[kLzwMaxCodes + 8];  // [15:0] pointer-jumping ancestor, [31:16] hops to it (phases B, C)
+        uint4 out16[kLzwWindow / 16 + 2];  // output window (phase D)
+    } u;
+    uint32_t in[2][kLzwInWords];       // the segment's input words as they lie in memory; the next segment's arrive meanwhile
+    uint32_t warp_sum[kLzwThreads / 32];
+    int m;                             // position of the first control code
+    int stream;                        // next stream drawn from the counter
 };
+static_assert(sizeof(LzwSmem) <= 48 * 1024, "lzw_kernel uses static shared memory");
 
-__global__ void __launch_bounds__(kLzwWarps * 32)
+// stage words [w0, w0 + kLzwInWords) of the stream (zeros beyond its last word) with asynchronous 4-byte copies
+__device__ __forceinline__ void lzw_stage(uint32_t* sdst, const uint32_t* __restrict__ wsrc, uint32_t w0, uint32_t n_words, int tid) {
+    for (int j = tid; j < kLzwInWords; j += kLzwThreads) {
+        const uint32_t w = w0 + (uint32_t)j;
+        const uint32_t ok = w < n_words ? 4u : 0u;
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sdst + j);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(wsrc + (ok ? w : 0u)), "r"(ok) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// codes 15 t .. 15 t + 14 of the segment from a sliding two-word window; kCheck: the input may end inside this span
+template <bool kCheck>
+__device__ __forceinline__ uint32_t lzw_extract(const uint32_t* __restrict__ in, uint32_t bit0, uint32_t wd0, int step_at,
+                                                uint32_t lim, uint32_t (&code)[kLzwPer], uint32_t* tcode) {
+    uint32_t widx = bit0 >> 5, sh = bit0 & 31u;
+    uint32_t hi = __byte_perm(in[widx], 0u, 0x0123), lo = __byte_perm(in[widx + 1], 0u, 0x0123);
+    widx += 2;
+    uint32_t ctl = 0, used = 0;
+#pragma unroll
+    for (int i = 0; i < kLzwPer; i++) {
+        const uint32_t wd = wd0 + (i >= step_at ? 1u : 0u);
+        uint32_t c = __funnelshift_l(lo, hi, sh) >> (32u - wd);
+        sh += wd;
+        if (sh >= 32u) { sh -= 32u; hi = lo; lo = __byte_perm(in[widx++], 0u, 0x0123); }
+        if (kCheck) {
+            used += wd;
+            if (used > lim) c = 257u;                                  // running out of input behaves like EOI
+        }
+        code[i] = c;
+        tcode[i] = c;
+        if ((c >> 1) == 128u) ctl |= 1u << i;                          // Clear (256) or EOI (257)
+    }
+    return ctl;
+}
+
+__global__ void __launch_bounds__(kLzwThreads, 4)
 lzw_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ streams, const int* __restrict__ order,
-           int n_streams, uint8_t* scratch, int32_t* __restrict__ status, uint32_t* offs_ws, unsigned int* next_stream) {
-    __shared__ LzwWarpSmem sm_all[kLzwWarps];
-    LzwWarpSmem* sm = &sm_all[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
-    uint32_t* offs = offs_ws + (size_t)(blockIdx.x * kLzwWarps + (threadIdx.x >> 5)) * kLzwOffs;
-  for (;;) {                                                           // persistent warps draw streams from a counter
-    int wi = 0;
-    if (lane == 0) wi = (int)atomicAdd(next_stream, 1u);
-    wi = __shfl_sync(0xffffffffu, wi, 0);
-    if (wi >= n_streams) return;
+           int n_streams, uint8_t* scratch, int32_t* __restrict__ status, unsigned int* next_stream) {
+    __shared__ LzwSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k0 = tid * kLzwPer;
+    uint8_t* const sout = reinterpret_cast<uint8_t*>(sm.u.out16);
+    // code width of this thread's positions: 9 bits, one more from positions 254, 766 and 1790 on; a thread's 15 positions
+    // cross at most one of the three steps
+    const uint32_t wd0 = lzw_width((uint32_t)k0);
+    const int next_step = k0 < 254 ? 254 : (k0 < 766 ? 766 : (k0 < 1790 ? 1790 : (1 << 30)));
+    const int step_at = next_step - k0;
+    const uint32_t rel0 = lzw_cum_bits((uint32_t)k0);                  // bits from the segment start to this thread's first code
+  for (;;) {                                                           // persistent CTAs draw streams from a counter
+    __syncthreads();
+    if (tid == 0) sm.stream = (int)atomicAdd(next_stream, 1u);
+    __syncthreads();
+    // two sweeps over the stream list: the large streams (image tiles) first, the small ones (label tiles, strips) fill
+    // the tail, so that the last CTAs do not finish a 512 KiB tile alone
+    const int draw = sm.stream;
+    if (draw >= 2 * n_streams) return;
+    const int wi = draw < n_streams ? draw : draw - n_streams;
     const b2_stream_desc sd = streams[order ? order[wi] : wi];
-    if (sd.codec != CODEC_LZW) continue;
+    if (sd.codec != CODEC_LZW || (sd.dst_len >= (1u << 17)) != (draw < n_streams)) continue;
     const uint8_t* src = blob + sd.src_off;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+    const uint32_t* __restrict__ wsrc = reinterpret_cast<const uint32_t*>(src - mis);   // aligned words; stream bit 0 = bit 8*mis
+    const uint32_t n_words = (mis + sd.src_len + 3u) >> 2;
     uint8_t* dst = scratch + sd.dst_off;
     const uint32_t src_bits = sd.src_len * 8u, dst_len = sd.dst_len;
-    uint32_t bitpos = 0, n = 0, out = 0;
-    int err = 0;
-    bool done = false;
-    while (!done && out < dst_len) {
-        // ---- fetch: one big-endian word per lane covering [bitpos .. bitpos + 32*12) bits
-        const uint32_t w0 = bitpos >> 5;
-        uint32_t wbe = 0;
+    uint32_t bitpos = 0, out = 0;
+    int err = 0, buf = 0;
+    lzw_stage(sm.in[0], wsrc, (8u * mis) >> 5, n_words, tid);
+    while (out < dst_len) {
+        // ---- A: all codes of the segment (its input was staged while the previous segment was being written out)
+        const uint32_t r0 = (8u * mis + bitpos) & 31u;
+        if (tid == 0) sm.m = kLzwMaxCodes;
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+        uint32_t code[kLzwPer];
         {
-            const uint32_t bo = (w0 + lane) * 4;
-            if (bo + 4 <= sd.src_len) {
-                const uint8_t* p = src + bo;
-                wbe = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
-            } else {
-                for (uint32_t j = 0; j < 4; j++)
-                    if (bo + j < sd.src_len) wbe |= (uint32_t)src[bo + j] << (24 - 8 * j);
-            }
+            const uint32_t remaining = src_bits - bitpos;              // bits of the stream from the segment start on
+            const uint32_t lim = remaining > rel0 ? remaining - rel0 : 0u;
+            const uint32_t ctl = (lim >= 12u * kLzwPer)
+                ? lzw_extract<false>(sm.in[buf], r0 + rel0, wd0, step_at, lim, code, sm.tcode + k0)
+                : lzw_extract<true>(sm.in[buf], r0 + rel0, wd0, step_at, lim, code, sm.tcode + k0);
+            if (ctl) atomicMin(&sm.m, k0 + __ffs(ctl) - 1);
         }
-        const uint32_t k = n + lane;                                   // code index inside the segment
-        const uint32_t my_bit = bitpos + lzw_cum_bits(k) - lzw_cum_bits(n);
-        const uint32_t wd = lzw_width(k);
-        const uint32_t rel = my_bit - (w0 << 5);
-        const uint32_t hi = __shfl_sync(0xffffffffu, wbe, (rel >> 5) & 31);
-        const uint32_t lo = __shfl_sync(0xffffffffu, wbe, ((rel >> 5) + 1) & 31);
-        const uint64_t win = ((uint64_t)hi << 32) | lo;
-        uint32_t code = (uint32_t)((win << (rel & 31)) >> (64 - wd));
-        const bool in_input = (my_bit + wd <= src_bits) && ((rel >> 5) + 1 < 32);
-        const bool avail = in_input && (k < kLzwMaxCodes);
-        if (!avail) code = 257;                                        // running out of input behaves like EOI
-        const bool is_ctl = (code == 256) || (code == 257);
-        const uint32_t ctl_mask = __ballot_sync(0xffffffffu, is_ctl);
-        const int m = ctl_mask ? (__ffs(ctl_mask) - 1) : 32;           // ordinary codes this round
-        // ---- lengths
-        uint32_t len = 0;
-        int32_t dep = -1;                                              // lane this string's length depends on
+        __syncthreads();
+        const int m = sm.m;
+        {   // the next segment starts right after this one's Clear: fetch its input now
+            const uint32_t nb = bitpos + lzw_cum_bits((uint32_t)m) + lzw_width((uint32_t)m);
+            if (m < kLzwMaxCodes && nb < src_bits) lzw_stage(sm.in[buf ^ 1], wsrc, (8u * mis + nb) >> 5, n_words, tid);
+        }
+        // ---- B: forest over the code positions -> depth and root by pointer jumping (own nodes in registers)
+        uint32_t node[kLzwPer];
         bool bad = false;
-        uint32_t e = 0, off_e = 0;
-        if (lane < m) {
-            if (code < 256) {
-                len = 1;
-            } else {
-                e = code - 258;
-                if (k == 0 || e + 1 > k) bad = true;                   // first code after Clear must be a literal; entry must exist
-                else if (e < n) { off_e = __ldcg(offs + e); len = __ldcg(offs + e + 1) - off_e + 1; }
-                else dep = (int32_t)(e - n);
+#pragma unroll
+        for (int i = 0; i < kLzwPer; i++) {
+            const uint32_t k = (uint32_t)(k0 + i), c = code[i];
+            uint32_t nd = k;                                           // literal / beyond the segment: a root
+            if ((int)k < m && c >= 256u) {
+                const uint32_t e = c - 258u;
+                if (e >= k) bad = true;                                // entry not defined yet (k == 0: the first code must be a literal)
+                else nd = e | (1u << 16);
+            }
+            node[i] = nd;
+            sm.u.tnode[k] = nd;
+        }
+        if (__syncthreads_or(bad)) { err = 2; break; }
+        for (;;) {
+            bool changed = false;
+#pragma unroll
+            for (int i = 0; i < kLzwPer; i++) {
+                const uint32_t j = node[i] & 0xFFFFu, par = sm.u.tnode[j];
+                if (par != j) {                                        // the ancestor is not a root yet: hop over it
+                    node[i] = ((node[i] & 0xFFFF0000u) + (par & 0xFFFF0000u)) | (par & 0xFFFFu);
+                    changed = true;
+                }
+            }
+            if (!__syncthreads_or(changed)) break;                     // every ancestor is a root: depths are final
+#pragma unroll
+            for (int i = 0; i < kLzwPer; i++) sm.u.tnode[k0 + i] = node[i];
+            __syncthreads();
+        }
+        // ---- C: first bytes, lengths, offsets
+        uint32_t run = 0;
+#pragma unroll
+        for (int i = 0; i < kLzwPer; i++) {
+            if (k0 + i < m) {
+                if (code[i] >= 256u) {
+                    const uint32_t fb = sm.tcode[node[i] & 0xFFFFu] & 0xFFu;   // the root is a literal; its low byte never changes
+                    sm.tcode[k0 + i] = code[i] | (fb << 16);
+                } else {
+                    sm.tcode[k0 + i] = code[i] * 0x10001u;
+                }
+                run += (node[i] >> 16) + 1u;
             }
         }
-        if (__ballot_sync(0xffffffffu, bad)) { err = 2; break; }
-        for (int it = 0; it < 32; it++) {
-            const uint32_t pend = __ballot_sync(0xffffffffu, dep >= 0);
-            if (!pend) break;
-            const uint32_t ld = __shfl_sync(0xffffffffu, len, dep >= 0 ? dep : 0);
-            const bool dep_ready = dep >= 0 && !((pend >> dep) & 1u);
-            if (dep_ready) {
-                len = ld + 1;
-                dep = -1 - dep;                                        // remember the lane (as -1-lane) for the source offset
-            }
-        }
-        // ---- offsets (inclusive warp scan)
-        uint32_t incl = len;
+        uint32_t incl = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        const uint32_t my_off = out + incl - len;
-        uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-        int32_t srcv;
-        if (lane < m) {
-            if (code < 256) srcv = -1 - (int32_t)code;
-            else if (e < n) srcv = (int32_t)off_e;
-            else srcv = 0;  // fixed below from the producing lane's offset
-        } else srcv = -1;
-        {
-            const int dl = dep < 0 ? (-1 - dep) : 0;                   // producing lane of an in-batch reference
-            const uint32_t so = __shfl_sync(0xffffffffu, my_off, dl);
-            if (lane < m && code >= 256 && e >= n) srcv = (int32_t)so;
+        if (lane == 31) sm.warp_sum[warp] = incl;
+        __syncthreads();                                               // also: tnode is dead, its space becomes the output window
+        uint32_t my_off = incl - run, total = 0;
+#pragma unroll
+        for (int w = 0; w < kLzwThreads / 32; w++) {
+            const uint32_t v = sm.warp_sum[w];
+            if (w < warp) my_off += v;
+            total += v;
         }
-        if (lane < m) offs[k] = my_off;
-        if (lane == 0) offs[n + m] = out + tot;
-        sm->b_off[lane] = (lane < m) ? my_off : (out + tot);
-        sm->b_src[lane] = srcv;
-        if (lane == 0) sm->b_off[32] = out + tot;
-        __syncwarp();
-        if (tot > dst_len - out) tot = dst_len - out;                  // libtiff truncates the last string
-        // ---- bytes: each output byte chases its chain down to a literal or to already-written output
-        // owner of output byte p = last lane whose string starts at or before p.  For the 32 consecutive bytes of a chunk
-        // that is one ballot (strings starting before the chunk) plus one OR-reduction of "a string starts at chunk
-        // byte j" bits; only bytes that refer back INTO this round fall through to the binary search.
-        const uint32_t my_rel = my_off - out;                           // lanes >= m: tot (never an owner of a live byte)
-        for (uint32_t base = 0; base < tot; base += 32) {
-            const uint32_t idx = base + lane;
-            const uint32_t before = __popc(__ballot_sync(0xffffffffu, lane < m && my_rel < base));
-            const uint32_t starts = __reduce_or_sync(0xffffffffu, (lane < m && my_rel - base < 32u) ? (1u << (my_rel - base)) : 0u);
-            if (idx < tot) {
-                uint32_t p = out + idx;
-                uint32_t val = 0;
-                int lo_l = (int)(before + __popc(starts & (0xFFFFFFFFu >> (31 - lane)))) - 1;
-                for (;;) {                                             // p strictly decreases: always terminates
-                    const int32_t s = sm->b_src[lo_l];
-                    if (s < 0) { val = (uint32_t)(-1 - s); break; }
-                    const uint32_t q = (uint32_t)s + (p - sm->b_off[lo_l]);
-                    if (q < out) { val = dst[q]; break; }
-                    p = q;
-                    int hi_l = m;                                       // in-round reference: owner by binary search
-                    lo_l = 0;
-                    while (hi_l - lo_l > 1) {
-                        const int mid = (lo_l + hi_l) >> 1;
-                        if (sm->b_off[mid] <= p) lo_l = mid; else hi_l = mid;
+        // ---- D: every string, back to front, through an output window that shares the destination's 16-byte alignment.
+        // libtiff truncates the last string of a tile: bytes past dst_len are dropped
+        const uint32_t room = dst_len - out;
+        const uint32_t emit = total < room ? total : room;
+        uint8_t* const gseg = dst + out;
+        if (emit == total && total <= (uint32_t)kLzwWindow) {
+            // the whole segment fits one window and the tile (the common case): no range checks on the way
+            const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(gseg) & 15u);
+            uint8_t* ptr = sout + shift + my_off;
+#pragma unroll
+            for (int i = 0; i < kLzwPer; i++) {
+                if (k0 + i < m) {
+                    uint32_t c = code[i];
+                    if (c < 256u) {
+                        *ptr++ = (uint8_t)c;
+                    } else {
+                        ptr += (node[i] >> 16) + 1u;
+                        uint8_t* q = ptr;
+                        do {
+                            *--q = (uint8_t)(sm.tcode[c - 257u] >> 16);
+                            c = sm.tcode[c - 258u] & 0xFFFFu;
+                        } while (c >= 256u);
+                        *--q = (uint8_t)c;
                     }
                 }
-                dst[out + idx] = (uint8_t)val;
             }
+            __syncthreads();
+            uint8_t* const g16 = gseg - shift;                         // 16-byte aligned
+            const uint32_t lo = shift, hi = shift + total;             // valid bytes of the window buffer
+            for (uint32_t c16 = (uint32_t)tid; c16 * 16u < hi; c16 += kLzwThreads) {
+                const uint32_t b0 = c16 * 16u;
+                if (b0 >= lo && b0 + 16u <= hi) {
+                    *reinterpret_cast<uint4*>(g16 + b0) = sm.u.out16[c16];
+                } else {
+                    for (uint32_t q = (b0 > lo ? b0 : lo); q < b0 + 16u && q < hi; q++) g16[q] = sout[q];
+                }
+            }
+            __syncthreads();
+        } else
+        for (uint32_t wv = 0; wv < emit; wv += kLzwWindow) {
+            const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(gseg + wv) & 15u);
+            const uint32_t wend = (wv + kLzwWindow < emit) ? wv + kLzwWindow : emit;
+            uint8_t* const sbase = sout + shift - wv;                  // window byte of segment byte p: sbase[p]
+            uint32_t o = my_off;
+#pragma unroll
+            for (int i = 0; i < kLzwPer; i++) {
+                if (k0 + i < m) {
+                    const uint32_t c0 = code[i];
+                    if (c0 < 256u) {                                   // a literal: one byte
+                        if (o >= wv && o < wend) sbase[o] = (uint8_t)c0;
+                        o += 1u;
+                    } else {
+                        const uint32_t len = (node[i] >> 16) + 1u;
+                        if (o < wend && o + len > wv) {
+                            uint32_t p = o + len - 1u, c = c0;
+                            for (;;) {
+                                uint32_t byte = c;
+                                if (c >= 256u) {
+                                    byte = (sm.tcode[c - 257u] >> 16) & 0xFFu;
+                                    c = sm.tcode[c - 258u] & 0xFFFFu;
+                                } else {
+                                    c = 0xFFFFFFFFu;
+                                }
+                                if (p < wend) sbase[p] = (uint8_t)byte;
+                                if (c == 0xFFFFFFFFu || p <= wv) break;
+                                p--;
+                            }
+                        }
+                        o += len;
+                    }
+                }
+            }
+            __syncthreads();
+            {
+                uint8_t* const g16 = gseg + wv - shift;                // 16-byte aligned
+                const uint32_t lo = shift, hi = shift + (wend - wv);   // valid bytes of the window buffer
+                for (uint32_t c16 = (uint32_t)tid; c16 * 16u < hi; c16 += kLzwThreads) {
+                    const uint32_t b0 = c16 * 16u;
+                    if (b0 >= lo && b0 + 16u <= hi) {
+                        *reinterpret_cast<uint4*>(g16 + b0) = sm.u.out16[c16];
+                    } else {
+                        for (uint32_t q = (b0 > lo ? b0 : lo); q < b0 + 16u && q < hi; q++) g16[q] = sout[q];
+                    }
+                }
+            }
+            __syncthreads();
         }
-        __syncwarp();
-        out += tot;
-        bitpos += lzw_cum_bits(n + m) - lzw_cum_bits(n);
-        n += m;
-        if (m < 32) {                                                  // a control code stopped the round
-            const uint32_t cc = __shfl_sync(0xffffffffu, code, m);
-            const uint32_t cw = __shfl_sync(0xffffffffu, wd, m);
-            if (cc == 256) { bitpos += cw; n = 0; }
-            else done = true;
-        }
+        out += emit;
+        const uint32_t ctl = (m < kLzwMaxCodes) ? (sm.tcode[m] & 0xFFFFu) : 257u;   // no control code within a full table: overflow, stop
+        if (ctl != 256u) break;
+        bitpos += lzw_cum_bits((uint32_t)m) + lzw_width((uint32_t)m);
+        buf ^= 1;
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");                   // nothing may still be landing when the next stream starts
     if (err == 0 && out < dst_len) err = 1;                            // stream ended early / table overflow
-    if (err && lane == 0) set_status(status, sd.image, 10 + err);
-    __syncwarp();
+    if (err && tid == 0) set_status(status, sd.image, 10 + err);
   }
 }
 
@@ -1119,17 +1244,19 @@ extern "C" int b2_decode_streams(b2_ctx* ctx, const uint8_t* blob, const b2_stre
     if (n_streams <= 0) return 0;
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (codec_mask & 1u) {   // LZW
-        // persistent warps (up to 64 per SM), each with its own offset table in the context workspace
-        unsigned ctas = (unsigned)((n_streams + kLzwWarps - 1) / kLzwWarps);
-        const unsigned resident = (unsigned)ctx->sm_count * (64 / kLzwWarps);
+    if (codec_mask & 1u) {   // LZW: persistent CTAs, one stream at a time each
+        static int per_sm = 0;
+        if (!per_sm) {
+            B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lzw_kernel, kLzwThreads, 0));
+            if (per_sm < 1) per_sm = 1;
+        }
+        unsigned ctas = (unsigned)n_streams;
+        const unsigned resident = (unsigned)(ctx->sm_count * per_sm);
         if (ctas > resident) ctas = resident;
-        const size_t offs_bytes = (size_t)ctas * kLzwWarps * kLzwOffs * sizeof(uint32_t);
-        if (int e = ws_reserve(ctx, offs_bytes + 256, s)) return e;
-        unsigned int* counter = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(ctx->ws) + offs_bytes);
+        if (int e = ws_reserve(ctx, 256, s)) return e;
+        unsigned int* counter = reinterpret_cast<unsigned int*>(ctx->ws);
         B2_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));
-        lzw_kernel<<<ctas, kLzwWarps * 32, 0, s>>>(blob, streams, nullptr, n_streams, scratch, status,
-                                                  static_cast<uint32_t*>(ctx->ws), counter);
+        lzw_kernel<<<ctas, kLzwThreads, 0, s>>>(blob, streams, nullptr, n_streams, scratch, status, counter);
         ctx->launches++;
         B2_CUDA(cudaGetLastError());
     }
