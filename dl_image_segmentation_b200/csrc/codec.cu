@@ -334,6 +334,11 @@ constexpr int kLitRoot = 10, kDistRoot = 8;
 constexpr int kLitSub = 320, kDistSub = 256;     // second-level entries; a code set needing more decodes bit by bit
 constexpr int kWinWords = 128;
 constexpr int kInfStage = 256;
+// chunk-parallel decode: 32 lanes x kParSub bits per chunk.  160 bits = 5 words: lanes in lock-step hit 32 different banks
+constexpr int kParSub = 160;
+constexpr int kParWords = 32 * kParSub / 32 + 8;     // chunk + alignment + the longest symbol (48 bits) + one fetch
+constexpr int kParMatches = 128;
+constexpr int kParStage = 2048;
 
 // table entry: [15:0] value | [23:16] code bits to drop | [27:24] extra bits (BASE) or index bits (SUB) | [31:28] kind.
 // One flag bit per kind makes each test in the symbol loop a single predicate-setting instruction; a literal sits in
@@ -357,6 +362,10 @@ struct alignas(16) InfWarpSmem {
     uint8_t lens[320];
     uint8_t cl_lens[19];
     alignas(16) uint8_t stage[kInfStage];   // literals waiting for one coalesced store
+    // chunk-parallel symbol decode (inflate_par_chunk)
+    uint32_t pwin[kParWords];               // the chunk's input words
+    uint2 mlist[kParMatches];               // matches of the chunk in stream order: {output offset in the chunk, len | dist << 16}
+    alignas(16) uint8_t pstage[kParStage];  // the chunk's literals on their way to one coalesced store
 };
 
 // Shared-memory load through a 32-bit shared-space address held in a register.  The symbol loop uses this instead of
@@ -422,6 +431,13 @@ struct InfReader {
     __device__ __forceinline__ uint32_t byte_pos() const { return (uint32_t)(((uint64_t)wpos * 32 - (uint64_t)cnt) >> 3); }
     // true once more bits were consumed than the stream holds
     __device__ __forceinline__ bool overrun() const { return (int64_t)wpos * 32 - cnt > (int64_t)end * 8; }
+    // bits consumed so far, counted from base
+    __device__ __forceinline__ uint32_t bit_pos() const { return wpos * 32u - (uint32_t)cnt; }
+    __device__ __forceinline__ void seek_bit(uint32_t bitpos) {
+        seek(bitpos >> 3);
+        drop((int)(bitpos & 7u));
+        refill();
+    }
     __device__ __forceinline__ void seek(uint32_t bytepos) {
         const uint32_t w = bytepos >> 2, W = w & ~63u;
         __syncwarp();
@@ -603,6 +619,194 @@ __device__ __forceinline__ uint32_t resolve_entry(InfReader& br, uint32_t e, uin
     return sym_entry<kDist>(s >> 4, 0);
 }
 
+// ---- chunk-parallel symbol decode ---------------------------------------------------------------------------------
+// A Huffman stream is serial only because a symbol's position is known once its predecessor is decoded — but Huffman codes
+// re-synchronise: a decoder started at a wrong bit falls into step with the true symbol sequence after a few symbols.  So
+// the 32 lanes each start at their own 160-bit sub-chunk of the block (lane 0 at the true position), decode to the end of
+// their sub-chunk and report where the next symbol would start; every lane then restarts from where its predecessor ended
+// until nothing changes any more — a fixed point that is the true decode, reached after one or two rounds when the guesses
+// re-synchronise, after at most 32 when they never do (the serial order).  A last pass over the now exactly known
+// symbols writes the literals (through shared memory, one coalesced store) and lists the matches, which are then copied
+// lane-parallel in dependency order.  Per symbol this costs a few warp instructions instead of a warp-wide dependent
+// chain; it pays for literal-dominated blocks (image data), so a block with many matches per chunk is handed to the
+// serial loop.
+struct ParTables {
+    uint32_t lit_s, dist_s, win_s;
+    const uint16_t *lit_count, *lit_sym, *dist_count, *dist_sym;
+};
+
+// 32 stream bits from bit p of the staged window
+__device__ __forceinline__ uint32_t par_fetch(uint32_t win_s, uint32_t p) {
+    const uint32_t a = win_s + ((p >> 5) << 2);
+    return __funnelshift_r(lds32(a), lds32(a + 4), p & 31u);
+}
+
+// the code at the bottom of w: its final table entry and its length in bits (0 entry: no such code)
+template <bool kDist>
+__device__ __forceinline__ uint32_t par_lookup(uint32_t w, uint32_t tab_s, const uint16_t* count, const uint16_t* syms, uint32_t& nbits) {
+    constexpr uint32_t root = kDist ? kDistRoot : kLitRoot;
+    uint32_t e = lds32(tab_s + ((w & ((1u << root) - 1u)) << 2));
+    uint32_t n = ent_drop(e);
+    if (e & E_SUB) {
+        if (ent_value(e) != kNoSub) {
+            e = lds32(tab_s + ((ent_value(e) + ((w >> n) & ((1u << ent_extra(e)) - 1u))) << 2));
+            n += ent_drop(e);
+        } else {
+            const int sl = decode_slow(w, count, syms);
+            e = sl < 0 ? 0u : sym_entry<kDist>(sl >> 4, 0);
+            n = sl < 0 ? 0u : (uint32_t)(sl & 15);
+        }
+    }
+    nbits = n;
+    return e;
+}
+
+enum : uint32_t { PAR_EOB = 1u, PAR_BAD_LIT = 2u, PAR_BAD_DIST = 4u };
+
+// Decode the symbols that start in [start, limit) (window bit positions).  kEmit: also write the literals to `lit` (+ offset
+// in the chunk's output) and append the matches to `ml`.  Returns where the next symbol starts.
+template <bool kEmit>
+__device__ __forceinline__ uint32_t par_scan(const ParTables& t, uint32_t start, uint32_t limit, uint32_t& nout, uint32_t& nmatch,
+                                             uint32_t& flags, uint8_t* lit, uint2* ml) {
+    uint32_t p = start, no = nout, nm = nmatch, fl = 0;
+    while (p < limit) {
+        const uint32_t w = par_fetch(t.win_s, p);
+        uint32_t nb;
+        const uint32_t e = par_lookup<false>(w, t.lit_s, t.lit_count, t.lit_sym, nb);
+        if (e & E_LIT) {
+            if (kEmit) lit[no] = (uint8_t)e;
+            no++;
+            p += nb;
+            continue;
+        }
+        if (e & E_EOB) { p += nb; fl = PAR_EOB; break; }
+        if (!(e & E_BASE)) { fl = PAR_BAD_LIT; break; }
+        const uint32_t mlen = ent_value(e) + ((w >> nb) & ((1u << ent_extra(e)) - 1u));
+        nb += ent_extra(e);
+        const uint32_t w2 = par_fetch(t.win_s, p + nb);
+        uint32_t nb2;
+        const uint32_t d = par_lookup<true>(w2, t.dist_s, t.dist_count, t.dist_sym, nb2);
+        if (!(d & E_BASE)) { fl = PAR_BAD_DIST; break; }
+        const uint32_t dist = ent_value(d) + ((w2 >> nb2) & ((1u << ent_extra(d)) - 1u));
+        if (kEmit) ml[nm] = make_uint2(no, mlen | (dist << 16));
+        nm++;
+        no += mlen;
+        p += nb + nb2 + ent_extra(d);
+    }
+    nout = no;
+    nmatch = nm;
+    flags = fl;
+    return p;
+}
+
+// One chunk of the current block starting at stream bit `bp` (from br.base).  Advances bp and out; sets eob when the block's
+// end-of-block code was reached, dense when the chunk held so many matches that the serial loop should take over, and
+// returns an inflate_kernel error code (0 = fine).
+__device__ __forceinline__ int inflate_par_chunk(InfWarpSmem* sm, const ParTables& t, const uint8_t* base, uint32_t end_bytes,
+                                                 uint32_t& bp, uint8_t* dst, uint32_t dst_len, uint32_t& out, bool& eob, bool& dense,
+                                                 int lane) {
+    constexpr uint32_t kFull = 0xffffffffu;
+    // ---- stage the chunk's input: words [w0, w0 + kParWords), zeros past the stream
+    const uint32_t w0 = bp >> 5, r0 = bp & 31u;
+    const uint32_t n_words = (end_bytes + 3u) >> 2;
+    __syncwarp();
+    for (int j = lane; j < kParWords; j += 32) {
+        const uint32_t w = w0 + (uint32_t)j;
+        sm->pwin[j] = w < n_words ? __ldg(reinterpret_cast<const uint32_t*>(base) + w) : 0u;
+    }
+    __syncwarp();
+    // ---- speculative decode, then restart from the predecessor's end until the chain is consistent
+    const uint32_t limit = r0 + (uint32_t)kParSub * (uint32_t)(lane + 1);
+    uint32_t start = r0 + (uint32_t)kParSub * (uint32_t)lane;
+    uint32_t nout = 0, nmatch = 0, flags = 0;
+    uint32_t endp = par_scan<false>(t, start, limit, nout, nmatch, flags, nullptr, nullptr);
+    int first_stop = 32;
+    for (int round = 0; round < 34; round++) {
+        const uint32_t pend = __shfl_up_sync(kFull, endp, 1);
+        const uint32_t stopmask = __ballot_sync(kFull, flags != 0u);
+        first_stop = stopmask ? __ffs(stopmask) - 1 : 32;
+        const bool need = lane > 0 && lane <= first_stop && pend != start;
+        if (!__any_sync(kFull, need)) break;
+        if (need) {
+            start = pend;
+            nout = 0;
+            nmatch = 0;
+            endp = par_scan<false>(t, start, limit, nout, nmatch, flags, nullptr, nullptr);
+        }
+    }
+    int valid = first_stop < 32 ? first_stop + 1 : 32;                // lanes on the true path
+    // ---- offsets; the match list holds kParMatches entries: keep as many leading lanes as fit
+    uint32_t mo = lane < valid ? nmatch : 0u, oo = lane < valid ? nout : 0u;
+    uint32_t mincl = mo, oincl = oo;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t a = __shfl_up_sync(kFull, mincl, d), b = __shfl_up_sync(kFull, oincl, d);
+        if (lane >= d) { mincl += a; oincl += b; }
+    }
+    const uint32_t fits = __ballot_sync(kFull, lane < valid && mincl <= (uint32_t)kParMatches);
+    const int keep = fits == kFull ? 32 : __ffs(~fits) - 1;            // a sub-chunk holds at most 80 matches: keep >= 1
+    bool stopped = first_stop < 32;
+    if (keep < valid) { valid = keep; stopped = false; }
+    const uint32_t total_out = __shfl_sync(kFull, oincl, valid - 1), total_m = __shfl_sync(kFull, mincl, valid - 1);
+    const uint32_t stop_flags = __shfl_sync(kFull, flags, valid - 1);
+    const uint32_t chunk_end = __shfl_sync(kFull, endp, valid - 1);
+    if (stopped && (stop_flags & PAR_BAD_LIT)) return 14;
+    if (stopped && (stop_flags & PAR_BAD_DIST)) return 16;
+    if ((uint64_t)w0 * 32u + chunk_end > (uint64_t)end_bytes * 8u) return 18;       // consumed more bits than the stream holds
+    if (total_out > dst_len - out) return 3;
+    // ---- emit: literals to the stage (or straight to their place when the chunk's output is larger), matches to the list
+    const bool staged = total_out <= (uint32_t)kParStage;
+    if (lane < valid) {
+        uint32_t no = oincl - oo, nm = mincl - mo, fl;
+        par_scan<true>(t, start, limit, no, nm, fl, staged ? sm->pstage : dst + out, sm->mlist);
+    }
+    __syncwarp();
+    if (staged)
+        for (uint32_t i = lane; i < total_out; i += 32) dst[out + i] = sm->pstage[i];
+    __syncwarp();
+    // ---- matches, lane-parallel in dependency order: a match may run once its source lies wholly before the first
+    // match that has not run yet (the first one itself always may: it only reads what it or earlier bytes wrote)
+    for (uint32_t mb = 0; mb < total_m; mb += 32) {
+        const bool have = mb + lane < total_m;
+        const uint2 me = have ? sm->mlist[mb + lane] : make_uint2(0u, 0u);
+        const uint32_t mlen = me.y & 0xFFFFu, dist = me.y >> 16;
+        const uint32_t o = out + me.x;
+        if (__any_sync(kFull, have && dist > o)) return 17;           // reaches back before the start of the output
+        const uint32_t sfrom = o - dist;
+        uint32_t pending = __ballot_sync(kFull, have);
+        while (pending) {
+            const int first = __ffs(pending) - 1;
+            const uint32_t o_first = __shfl_sync(kFull, o, first);
+            const bool ready = ((pending >> lane) & 1u) && (lane == first || sfrom + mlen <= o_first);
+            if (ready) {
+                const uint8_t* from = dst + sfrom;
+                uint8_t* to = dst + o;
+                if (dist >= mlen) {                                    // disjoint: four loads in flight before the stores
+                    for (uint32_t k = 0; k < mlen; k += 4) {
+                        uint8_t v[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) if (k + q < mlen) v[q] = from[k + q];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) if (k + q < mlen) to[k + q] = v[q];
+                    }
+                } else {                                               // overlapped: the last `dist` bytes repeat
+                    for (uint32_t k = 0, r = 0; k < mlen; k++) {
+                        to[k] = from[r];
+                        if (++r == dist) r = 0;
+                    }
+                }
+            }
+            pending &= ~__ballot_sync(kFull, ready);
+            __syncwarp();
+        }
+    }
+    out += total_out;
+    bp = w0 * 32u + chunk_end;
+    eob = stopped && (stop_flags & PAR_EOB);
+    dense = total_m > 3u * (uint32_t)valid;
+    return 0;
+}
+
 __global__ void __launch_bounds__(kInfWarps * 32)
 inflate_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ streams, const int* __restrict__ order,
                int n_streams, uint8_t* scratch, int32_t* __restrict__ status) {
@@ -715,6 +919,19 @@ inflate_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restric
         }
         if (!build_table<false>(sm, sm->lens, nlit, sm->lit_tab, kLitRoot, kLitSub, sm->lit_count, sm->lit_sym, lane)) { err = 12; break; }
         if (!build_table<true>(sm, sm->lens + 288, ndist, sm->dist_tab, kDistRoot, kDistSub, sm->dist_count, sm->dist_sym, lane)) { err = 13; break; }
+        // ---- literal-dominated blocks: chunk-parallel decode (inflate_par_chunk); a chunk dense with matches hands
+        // the rest of the block to the serial symbol loop below
+        {
+            B2_FLUSH_LITERALS();
+            const ParTables pt{lit_s, dist_s, smem_addr(sm->pwin), sm->lit_count, sm->lit_sym, sm->dist_count, sm->dist_sym};
+            uint32_t bp = br.bit_pos();
+            bool eob = false, dense = false;
+            while (!err && !eob && !dense)
+                err = inflate_par_chunk(sm, pt, br.base, br.end, bp, dst, dst_len, out, eob, dense, lane);
+            if (err) break;
+            br.seek_bit(bp);
+            if (eob) continue;
+        }
         // ---- symbols.  After a refill the buffer holds >= 33 bits: enough for two codes (<= 15 bits each), or for
         // one length code + extra (<= 20), or one distance code + extra (<= 28).  Two first-level lookups are made
         // back to back (the second is simply discarded unless the first was a literal) and the common case, two
