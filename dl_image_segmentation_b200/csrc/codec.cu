@@ -336,7 +336,8 @@ constexpr int kWinWords = 128;
 constexpr int kInfStage = 256;
 // chunk-parallel decode: 32 lanes x kParSub bits per chunk.  160 bits = 5 words: lanes in lock-step hit 32 different banks
 constexpr int kParSub = 160;
-constexpr int kParWords = 32 * kParSub / 32 + 8;     // chunk + alignment + the longest symbol (48 bits) + one fetch
+constexpr int kParWords = 32 * kParSub / 32 + 8;     // chunk + alignment + the longest symbol (48 bits) + the words fetched ahead
+constexpr int kParPre = 6;                           // words per lane requested ahead for the next chunk
 constexpr int kParMatches = 128;
 constexpr int kParStage = 2048;
 
@@ -664,35 +665,63 @@ __device__ __forceinline__ uint32_t par_lookup(uint32_t w, uint32_t tab_s, const
 enum : uint32_t { PAR_EOB = 1u, PAR_BAD_LIT = 2u, PAR_BAD_DIST = 4u };
 
 // Decode the symbols that start in [start, limit) (window bit positions).  kEmit: also write the literals to `lit` (+ offset
-// in the chunk's output) and append the matches to `ml`.  Returns where the next symbol starts.
+// in the chunk's output) and append the matches to `ml`.  Returns where the next symbol starts.  The lane keeps its own
+// 64-bit bit buffer over the staged window, topped up from a word fetched one refill ahead, so that the dependent chain
+// of a literal is one table lookup plus a handful of ALU operations.
 template <bool kEmit>
 __device__ __forceinline__ uint32_t par_scan(const ParTables& t, uint32_t start, uint32_t limit, uint32_t& nout, uint32_t& nmatch,
                                              uint32_t& flags, uint8_t* lit, uint2* ml) {
     uint32_t p = start, no = nout, nm = nmatch, fl = 0;
-    while (p < limit) {
-        const uint32_t w = par_fetch(t.win_s, p);
-        uint32_t nb;
-        const uint32_t e = par_lookup<false>(w, t.lit_s, t.lit_count, t.lit_sym, nb);
-        if (e & E_LIT) {
+    uint32_t wa = t.win_s + ((start >> 5) << 2);                      // shared address of the next word to append
+    uint64_t buf = (((uint64_t)lds32(wa + 4) << 32) | lds32(wa)) >> (start & 31u);
+    int cnt = 64 - (int)(start & 31u);
+    uint32_t nextw = lds32(wa + 8);
+    wa += 12;
+#define B2_PAR_REFILL()                                   \
+    if (cnt <= 32) {                                      \
+        buf |= (uint64_t)nextw << cnt;                    \
+        cnt += 32;                                        \
+        nextw = lds32(wa);                                \
+        wa += 4;                                          \
+    }
+    for (;;) {
+        // literals, the bulk of an image stream, in a loop of their own: the lanes leave it one by one at their first
+        // length code and the longer path below runs once for all of them, not once per symbol that any lane has there
+        uint32_t w = 0, nb = 0, e = 0;
+        bool more = false;
+        while (p < limit) {
+            B2_PAR_REFILL();
+            w = (uint32_t)buf;
+            e = par_lookup<false>(w, t.lit_s, t.lit_count, t.lit_sym, nb);
+            if (!(e & E_LIT)) { more = true; break; }
             if (kEmit) lit[no] = (uint8_t)e;
             no++;
             p += nb;
-            continue;
+            buf >>= nb;
+            cnt -= (int)nb;
         }
+        if (!more) break;
         if (e & E_EOB) { p += nb; fl = PAR_EOB; break; }
         if (!(e & E_BASE)) { fl = PAR_BAD_LIT; break; }
         const uint32_t mlen = ent_value(e) + ((w >> nb) & ((1u << ent_extra(e)) - 1u));
         nb += ent_extra(e);
-        const uint32_t w2 = par_fetch(t.win_s, p + nb);
+        buf >>= nb;
+        cnt -= (int)nb;
+        B2_PAR_REFILL();
+        w = (uint32_t)buf;
         uint32_t nb2;
-        const uint32_t d = par_lookup<true>(w2, t.dist_s, t.dist_count, t.dist_sym, nb2);
+        const uint32_t d = par_lookup<true>(w, t.dist_s, t.dist_count, t.dist_sym, nb2);
         if (!(d & E_BASE)) { fl = PAR_BAD_DIST; break; }
-        const uint32_t dist = ent_value(d) + ((w2 >> nb2) & ((1u << ent_extra(d)) - 1u));
+        const uint32_t dist = ent_value(d) + ((w >> nb2) & ((1u << ent_extra(d)) - 1u));
+        nb2 += ent_extra(d);
+        buf >>= nb2;
+        cnt -= (int)nb2;
         if (kEmit) ml[nm] = make_uint2(no, mlen | (dist << 16));
         nm++;
         no += mlen;
-        p += nb + nb2 + ent_extra(d);
+        p += nb + nb2;
     }
+#undef B2_PAR_REFILL
     nout = no;
     nmatch = nm;
     flags = fl;
@@ -704,15 +733,32 @@ __device__ __forceinline__ uint32_t par_scan(const ParTables& t, uint32_t start,
 // returns an inflate_kernel error code (0 = fine).
 __device__ __forceinline__ int inflate_par_chunk(InfWarpSmem* sm, const ParTables& t, const uint8_t* base, uint32_t end_bytes,
                                                  uint32_t& bp, uint8_t* dst, uint32_t dst_len, uint32_t& out, bool& eob, bool& dense,
-                                                 int lane) {
+                                                 uint32_t (&pre)[kParPre], uint32_t& pre_w0, int lane) {
     constexpr uint32_t kFull = 0xffffffffu;
     // ---- stage the chunk's input: words [w0, w0 + kParWords), zeros past the stream
+    // (the words of a chunk that follows a full one were requested while that one was being decoded: `pre`)
     const uint32_t w0 = bp >> 5, r0 = bp & 31u;
     const uint32_t n_words = (end_bytes + 3u) >> 2;
+    const uint32_t* __restrict__ wsrc = reinterpret_cast<const uint32_t*>(base);
     __syncwarp();
-    for (int j = lane; j < kParWords; j += 32) {
-        const uint32_t w = w0 + (uint32_t)j;
-        sm->pwin[j] = w < n_words ? __ldg(reinterpret_cast<const uint32_t*>(base) + w) : 0u;
+    if (w0 >= pre_w0 && w0 + (uint32_t)kParWords <= pre_w0 + 32u * kParPre) {
+        const uint32_t delta = w0 - pre_w0;
+#pragma unroll
+        for (int q = 0; q < kParPre; q++) {
+            const uint32_t idx = (uint32_t)(lane + 32 * q) - delta;
+            if (idx < (uint32_t)kParWords) sm->pwin[idx] = pre[q];
+        }
+    } else {
+        for (int j = lane; j < kParWords; j += 32) {
+            const uint32_t w = w0 + (uint32_t)j;
+            sm->pwin[j] = w < n_words ? __ldg(wsrc + w) : 0u;
+        }
+    }
+    pre_w0 = w0 + (uint32_t)(32 * kParSub / 32 - 4);                  // the next chunk starts 0 .. 48 bits past this one's last sub-chunk
+#pragma unroll
+    for (int q = 0; q < kParPre; q++) {
+        const uint32_t w = pre_w0 + (uint32_t)(lane + 32 * q);
+        pre[q] = w < n_words ? __ldg(wsrc + w) : 0u;
     }
     __syncwarp();
     // ---- speculative decode, then restart from the predecessor's end until the chain is consistent
@@ -926,8 +972,9 @@ inflate_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restric
             const ParTables pt{lit_s, dist_s, smem_addr(sm->pwin), sm->lit_count, sm->lit_sym, sm->dist_count, sm->dist_sym};
             uint32_t bp = br.bit_pos();
             bool eob = false, dense = false;
+            uint32_t pre[kParPre], pre_w0 = 0xFFFFFFF0u;
             while (!err && !eob && !dense)
-                err = inflate_par_chunk(sm, pt, br.base, br.end, bp, dst, dst_len, out, eob, dense, lane);
+                err = inflate_par_chunk(sm, pt, br.base, br.end, bp, dst, dst_len, out, eob, dense, pre, pre_w0, lane);
             if (err) break;
             br.seek_bit(bp);
             if (eob) continue;
@@ -1076,19 +1123,37 @@ inflate_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restric
         stored |= br.take(8);
         if (br.overrun()) err = 18;
         __syncwarp();
-        unsigned long long a = 0, b = 0;              // sum d_i ; sum ((n - i) mod 65521) d_i  (< 2^56 for n < 2^32)
-        uint32_t wgt = (out - (uint32_t)lane) % 65521u;
-        for (uint32_t i = lane; i < out; i += 32) {
-            const uint32_t d = dst[i];
-            a += d;
-            b += (unsigned long long)(wgt * d);
-            wgt = wgt >= 32u ? wgt - 32u : wgt + (65521u - 32u);
+        // a = sum d_i ; b = sum ((n - i) mod 65521) d_i, in 64 bits (n < 2^32: b < 2^57).
+        // 16 bytes per lane and load: a group at offset i0 adds (n - i0) S - T with S = sum d_k, T = sum k d_k
+        unsigned long long a = 0, b = 0, bneg = 0;
+        {
+            const uint32_t head = min(out, (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u));
+            for (uint32_t i = lane; i < head; i += 32) { const uint32_t d = dst[i]; a += d; b += (unsigned long long)((out - i) % 65521u) * d; }
+            const uint32_t groups = (out - head) >> 4;
+            const uint4* g = reinterpret_cast<const uint4*>(dst + head);
+            for (uint32_t q = lane; q < groups; q += 32) {
+                const uint4 v = g[q];
+                const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+                uint32_t S = 0, T = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t b0 = wds[k] & 0xFFu, b1 = (wds[k] >> 8) & 0xFFu, b2 = (wds[k] >> 16) & 0xFFu, b3 = wds[k] >> 24;
+                    S += b0 + b1 + b2 + b3;
+                    T += (4 * k) * b0 + (4 * k + 1) * b1 + (4 * k + 2) * b2 + (4 * k + 3) * b3;
+                }
+                a += S;
+                b += (unsigned long long)((out - head - (q << 4)) % 65521u) * S;
+                bneg += T;
+            }
+            for (uint32_t i = head + (groups << 4) + lane; i < out; i += 32) { const uint32_t d = dst[i]; a += d; b += (unsigned long long)((out - i) % 65521u) * d; }
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             a += __shfl_xor_sync(0xffffffffu, a, o);
             b += __shfl_xor_sync(0xffffffffu, b, o);
+            bneg += __shfl_xor_sync(0xffffffffu, bneg, o);
         }
+        b = b % 65521ull + 65521ull - bneg % 65521ull;
         const uint32_t s1 = (uint32_t)((a + 1ull) % 65521ull);
         const uint32_t s2 = (uint32_t)((b + (unsigned long long)(out % 65521u)) % 65521ull);
         if (!err && ((s2 << 16) | s1) != stored) err = 20;

@@ -129,6 +129,10 @@ def bench_decode(dev, kind, n_distinct=16, reps=None):
         elif kind == "deflate":
             img, lab, _ = syn.cfg3_chip(i)
             blobs += [syn.tiff_bytes(img, tile=256, compression="deflate"), syn.tiff_bytes(lab, tile=256, compression="deflate")]
+        elif kind == "png_images":                   # the two halves of a PNG pair on their own: which one bounds the batch?
+            blobs += [syn.png_bytes(syn.cfg1_chip(i)[0]), syn.png_bytes(syn.cfg1_chip(i + 100)[0])]
+        elif kind == "png_labels":
+            blobs += [syn.png_bytes(syn.cfg1_chip(i)[1]), syn.png_bytes(syn.cfg1_chip(i + 100)[1])]
         else:
             img, lab, _ = syn.cfg1_chip(i)
             blobs += [syn.png_bytes(img), syn.png_bytes(lab)]
@@ -411,7 +415,7 @@ def main():
         bench_jpeg(dev)
     if "jpeg_encode" in which:
         bench_jpeg_encode(dev)
-    for kind in ("lzw", "lzw_strips_pred2", "deflate", "png"):
+    for kind in ("lzw", "lzw_strips_pred2", "deflate", "png", "png_images", "png_labels"):
         if kind in which or "decode" in which:
             bench_decode(dev, kind)
 
