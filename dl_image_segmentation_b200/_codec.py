@@ -34,6 +34,7 @@ IMAGE_DESC_DTYPE = np.dtype([("scratch_off", "<u8"), ("out_off", "<u8"), ("block
                              ("predictor", "<i4"), ("planar", "<i4"), ("big_endian", "<i4"), ("block_w", "<i4"),
                              ("block_h", "<i4"), ("blocks_across", "<i4"), ("blocks_down", "<i4"),
                              ("png_bit_depth", "<i4"), ("png_color_type", "<i4"), ("png_flags", "<i4"), ("png_converted", "<i4")])
+PLAN_INPLACE = 0x1000   # b2chips.h B2_PLAN_INPLACE: the blobs already lie in the staging buffer (read there), nothing is gathered
 PNG_AS_TF = 1      # b2chips.h B2_PNG_AS_TF: present palette / sub-byte / 16-bit PNGs as tf.image.decode_png does (else: as GDAL does)
 
 _vp, _i, _u64, _u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32
@@ -43,6 +44,8 @@ _lib.register_signatures({
     "b2_decode_streams": (_i, [_vp, _vp, _vp, _i, _u32, _u32, _vp, _vp, _vp]),
     "b2_assemble_images": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
 })
+
+IMAGE_INFO_DTYPE = np.dtype(ImageInfo)
 
 _B2_TO_TORCH = {_lib.B2_U8: torch.uint8, _lib.B2_I8: torch.int8, _lib.B2_U16: torch.uint16, _lib.B2_I16: torch.int16,
                 _lib.B2_U32: torch.uint32, _lib.B2_I32: torch.int32, _lib.B2_F32: torch.float32, _lib.B2_F64: torch.float64}
@@ -98,11 +101,21 @@ class _HostStaging:
         self.streams = torch.empty((4096 * STREAM_DESC_DTYPE.itemsize,), dtype=torch.uint8).pin_memory()
         self.busy = None          # event: the last H2D copies out of these buffers
         self.pending = False      # planned into, not yet uploaded
+        self.pool = None
 
     def wait(self):
         if self.busy is not None:
             self.busy.synchronize()
             self.busy = None
+
+    def ensure_stage(self, nbytes):
+        """The pinned byte buffer, at least nbytes long (contents are NOT kept when it grows)."""
+        if self.stage.numel() < nbytes:
+            self.stage = torch.empty((int(nbytes * 1.25) + 4096,), dtype=torch.uint8).pin_memory()
+            pool = getattr(self, "pool", None)
+            if pool is not None:
+                pool.stage_hwm = max(pool.stage_hwm, self.stage.numel())
+        return self.stage
 
 
 _staging = {}
@@ -121,10 +134,13 @@ class _StagingPool:
     """A few pinned staging sets per device, handed out in rotation: a batch can be planned (host work, any thread) while
     the previous one is still being uploaded and decoded."""
 
-    def __init__(self, n=3):
+    def __init__(self, n=4):
         self.sets = [_HostStaging() for _ in range(n)]
         self.k = 0
         self.lock = threading.Lock()
+        self.stage_hwm = 0         # largest buffer any set needed so far: the others grow to it when they are next taken, so
+                                   # that a steady stream of equal batches never re-pins memory (cudaHostAlloc stalls every
+                                   # CUDA call of the process while it runs)
 
     def take(self):
         with self.lock:
@@ -137,6 +153,9 @@ class _StagingPool:
                 raise B2Error("decode staging: more batches planned ahead than there are staging sets")
             hs.pending = True
         hs.wait()                                              # its last uploads have left the pinned buffers
+        hs.pool = self
+        if hs.stage.numel() < self.stage_hwm:
+            hs.stage = torch.empty((self.stage_hwm,), dtype=torch.uint8).pin_memory()
         return hs
 
 
@@ -159,10 +178,39 @@ class PlannedBatch:
             pass
 
 
-def plan_blobs(blobs, device=None, png_as_tf=False):
+def take_staging(device=None):
+    """A free pinned staging set of this device (held until a plan made with it is decoded or released)."""
+    ctx = get_ctx(device)
+    with _pool_lock:
+        pool = _staging.get(ctx.device.index)
+        if pool is None:
+            pool = _staging[ctx.device.index] = _StagingPool()
+    return pool.take()
+
+
+def reserve_staging(device, nbytes):
+    """Grow every free staging set of the device to nbytes now (a worker calls this once, before its pipeline starts:
+    pinning memory later would stall every CUDA call of the process for the duration of the cudaHostAlloc)."""
+    ctx = get_ctx(device)
+    with _pool_lock:
+        pool = _staging.get(ctx.device.index)
+        if pool is None:
+            pool = _staging[ctx.device.index] = _StagingPool()
+    with pool.lock:
+        for hs in pool.sets:
+            if not hs.pending and hs.stage.numel() < nbytes:
+                hs.wait()
+                hs.stage = torch.empty((int(nbytes),), dtype=torch.uint8).pin_memory()
+        pool.stage_hwm = max(pool.stage_hwm, int(nbytes))
+
+
+def plan_blobs(blobs, device=None, png_as_tf=False, inplace=None):
     """Host half of decode_blobs: header parse, descriptor tables and the gather of all compressed bytes into one pinned
     buffer, in ONE native multi-threaded call.  Touches no GPU state besides pinned host memory, so the translators run
-    it on their read-ahead thread while the GPU works on the previous batch."""
+    it on their read-ahead thread while the GPU works on the previous batch.
+
+    inplace: a staging set (take_staging) whose pinned buffer already holds every blob, 16-byte aligned — the translators'
+    FileBatchReader reads the files straight into it — so that nothing is gathered and the buffer is uploaded as it is."""
     ctx = get_ctx(device)
     n = len(blobs)
     pb = PlannedBatch()
@@ -175,11 +223,7 @@ def plan_blobs(blobs, device=None, png_as_tf=False):
     pb.consumed = True
     if n == 0:
         return pb
-    with _pool_lock:
-        pool = _staging.get(ctx.device.index)
-        if pool is None:
-            pool = _staging[ctx.device.index] = _StagingPool()
-    hs = pb.hs = pool.take()
+    hs = pb.hs = inplace if inplace is not None else take_staging(ctx.device)
     pb.consumed = False
     ptrs = (ctypes.c_void_p * n)()
     sizes = np.zeros(n, np.uint64)
@@ -189,31 +233,73 @@ def plan_blobs(blobs, device=None, png_as_tf=False):
         ptrs[i], sizes[i] = p, sz
         keep.append(k)
     ssz = STREAM_DESC_DTYPE.itemsize
+    flags = (PNG_AS_TF if png_as_tf else 0) | (PLAN_INPLACE if inplace is not None else 0)
     for _ in range(2):
         check(lib().b2_decode_plan_batch(ptrs, sizes.ctypes.data, n, pb.infos, pb.status.ctypes.data, pb.images.ctypes.data,
                                          hs.streams.data_ptr(), hs.streams.numel() // ssz, hs.stage.data_ptr(),
-                                         hs.stage.numel(), 0, PNG_AS_TF if png_as_tf else 0, ctypes.byref(pb.plan)))
+                                         hs.stage.numel(), 0, flags, ctypes.byref(pb.plan)))
         if pb.plan.filled:
             break
         if hs.stage.numel() < pb.plan.stage_bytes:
-            hs.stage = torch.empty((int(pb.plan.stage_bytes * 1.25) + 4096,), dtype=torch.uint8).pin_memory()
+            if inplace is not None:
+                raise B2Error("plan_blobs(inplace): the staging buffer that holds the files is smaller than the plan")
+            hs.ensure_stage(int(pb.plan.stage_bytes))
         if hs.streams.numel() // ssz < pb.plan.n_streams:
             hs.streams = torch.empty((int(pb.plan.n_streams * 1.25 + 64) * ssz,), dtype=torch.uint8).pin_memory()
     del keep
     return pb
 
 
-def decode_planned(pb, device=None, timings=None, want_infos=False):
-    """Device half of decode_blobs: upload, decode kernels, assembly.  Returns what decode_blobs returns."""
+_side_streams = {}
+_status_ring = {}      # device -> [rotating pinned int32 buffers]: pinning per batch would stall the CUDA calls of other threads
+
+
+def _pinned_status(dev_index, n):
+    ring = _status_ring.setdefault(dev_index, {"k": 0, "bufs": [None] * 8})
+    ring["k"] = (ring["k"] + 1) % len(ring["bufs"])
+    b = ring["bufs"][ring["k"]]
+    if b is None or b.numel() < n:
+        b = ring["bufs"][ring["k"]] = torch.empty((max(n, 8192),), dtype=torch.int32).pin_memory()
+    return b[:n]
+
+
+def _side_stream(device):
+    st = _side_streams.get(device.index)
+    if st is None:
+        st = _side_streams[device.index] = torch.cuda.Stream(device)
+    return st
+
+
+class DecodeJob:
+    """A batch whose uploads and decode kernels are queued on the stream: device buffers + what the host knows."""
+    __slots__ = ("n", "out", "scratch", "status_dev", "images", "infos", "plan", "host_status", "blob_dev", "status_pinned",
+                 "status_ready")
+
+    def status(self):
+        """Per-image status: 0 = decoded.  Waits for THIS batch's decode only (the status words come back on a side
+        stream, so work queued behind the batch on the main stream does not delay them)."""
+        if self.status_dev is None:
+            return self.host_status
+        self.status_ready.synchronize()
+        return self.status_pinned.numpy()
+
+    def infos_array(self):
+        """The ImageInfo records as a NumPy structured array (no copy)."""
+        return np.frombuffer(self.infos, dtype=IMAGE_INFO_DTYPE, count=self.n)
+
+
+def decode_enqueue(pb, device=None, timings=None):
+    """Device half of decode_blobs without the wait: upload, decode kernels, assembly — all queued, nothing synchronised."""
     ctx = get_ctx(device)
-    n, plan, infos, images = pb.n, pb.plan, pb.infos, pb.images
-    arrays = [None] * n
-    if n == 0:
-        return (arrays, np.zeros(0, np.int32), []) if want_infos else (arrays, np.zeros(0, np.int32))
-    hs = pb.hs
-    if plan.n_streams == 0:
+    job = DecodeJob()
+    job.n, job.plan, job.infos, job.images = pb.n, pb.plan, pb.infos, pb.images
+    job.out = job.scratch = job.status_dev = job.blob_dev = None
+    job.host_status = pb.status
+    n, plan, images = pb.n, pb.plan, pb.images
+    if n == 0 or plan.n_streams == 0:
         pb.release()
-        return (arrays, pb.status, infos) if want_infos else (arrays, pb.status)
+        return job
+    hs = pb.hs
     ssz = STREAM_DESC_DTYPE.itemsize
     blob_d = hs.stage[:plan.stage_bytes].to(ctx.device, non_blocking=True)
     sd_d = hs.streams[:plan.n_streams * ssz].to(ctx.device, non_blocking=True)
@@ -237,9 +323,31 @@ def decode_planned(pb, device=None, timings=None, want_infos=False):
         torch.cuda.synchronize()
         timings.update(decode_ms=ev[0].elapsed_time(ev[1]), assemble_ms=ev[1].elapsed_time(ev[2]),
                        compressed_bytes=int(plan.compressed_bytes), decoded_bytes=int(plan.out_bytes), streams=int(plan.n_streams))
-    status = st_d.cpu().numpy()
+    job.out, job.scratch, job.status_dev, job.blob_dev = out, scratch, st_d, blob_d
+    side = _side_stream(ctx.device)
+    decoded = torch.cuda.Event()
+    decoded.record(torch.cuda.current_stream(ctx.device))
+    job.status_pinned = _pinned_status(ctx.device.index, n)
+    with torch.cuda.stream(side):
+        side.wait_event(decoded)
+        job.status_pinned.copy_(st_d, non_blocking=True)
+        job.status_ready = torch.cuda.Event()
+        job.status_ready.record(side)
+    st_d.record_stream(side)
+    return job
+
+
+def decode_planned(pb, device=None, timings=None, want_infos=False):
+    """Device half of decode_blobs: upload, decode kernels, assembly.  Returns what decode_blobs returns."""
+    n, infos, images = pb.n, pb.infos, pb.images
+    arrays = [None] * n
+    if n == 0:
+        return (arrays, np.zeros(0, np.int32), []) if want_infos else (arrays, np.zeros(0, np.int32))
+    job = decode_enqueue(pb, device, timings)
+    status = job.status()
+    out = job.out
     for i in range(n):
-        if status[i] != 0:
+        if status[i] != 0 or out is None:
             continue
         info = infos[i]
         bs = _B2_SIZE[info.dtype]

@@ -44,8 +44,9 @@ def _process_image_files_mp_worker(proc_index, ranges, name, img_filenames, lbl_
             return _translate.tile_key_from_path(p, True)
         gt, crs = _codec.georef_strings(info) if info is not None else ("[0.0, 1.0, 0.0, 0.0, 0.0, 1.0]", "None")
         return "|".join((os.path.basename(p), gt, crs))
+    path_key = (lambda p: _translate.tile_key_from_path(p, True)) if dltile_from_filename else None
     return _translate.run_worker(proc_index, ranges, name, img_filenames, lbl_filenames, output_directory, num_shards,
-                                 key_fn, store_as_array, label="process", progress_every=100, device=device)
+                                 key_fn, store_as_array, label="process", progress_every=100, device=device, path_key=path_key)
 
 
 def _process_image_files_mp(name, img_files, lbl_files, out_folder, num_shards, num_proc, dltile_from_filename,

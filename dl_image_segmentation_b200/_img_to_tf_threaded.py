@@ -88,7 +88,8 @@ def _process_image_files_worker(coder, thread_index, ranges, name, filenames, la
     return _translate.run_worker(thread_index, ranges, name, filenames, labels, out_folder, num_shards, key_fn,
                                  store_as_array, label="thread", progress_every=1000, validate=validate, device=device,
                                  png_as_tf=True,                     # this translator decodes with tf.image.decode_png
-                                 png_to_jpg=png_to_jpg)
+                                 png_to_jpg=png_to_jpg, path_key=key_fn,
+                                 fast_validate=lambda infos: (infos["format"] == 2) & (infos["samples"] <= 3))
 
 
 def _process_image_files(name, img_files, lbl_files, out_folder, num_shards, num_threads, dltile_from_filename,

@@ -78,6 +78,7 @@ SIGNATURES = {
     "b2_example_layout": (_i, [_i, _u64, _u64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                ctypes.c_int64, _vp, _u64, _vp, _u64, ctypes.POINTER(ctypes.c_uint32),
                                ctypes.POINTER(_u64)]),
+    "b2_example_layout_batch": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
     "b2_tfrecord_build": (_i, [_vp, _vp, _i, _u64, _vp, _vp, _vp]),
 }
 

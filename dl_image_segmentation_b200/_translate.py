@@ -58,9 +58,11 @@ class FileBatchReader:
     OSError the reference's except branch would have caught); a view stays valid until `depth` more batches were read."""
 
     def __init__(self, depth=3, threads=0):
+        import threading
         self.bufs = [np.empty(0, np.uint8) for _ in range(depth)]
         self.k = 0
         self.threads = int(threads)
+        self.lock = threading.Lock()       # two read-ahead threads share one reader: each call gets a buffer of its own
 
     def read(self, paths):
         n = len(paths)
@@ -71,8 +73,9 @@ class FileBatchReader:
         offs, sizes = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
         status = np.zeros(n, np.int32)
         need = ctypes.c_uint64(0)
-        slot = self.k % len(self.bufs)
-        self.k += 1
+        with self.lock:
+            slot = self.k % len(self.bufs)
+            self.k += 1
         buf = self.bufs[slot]
         for _ in range(2):
             check(lib().b2_read_files(arr, n, buf.ctypes.data if buf.size else None, buf.size, offs.ctypes.data, sizes.ctypes.data,
@@ -87,6 +90,32 @@ class FileBatchReader:
             else:
                 out.append(buf[int(offs[i]):int(offs[i]) + int(sizes[i])])
         return out
+
+
+def _read_into(self, paths, hs):
+    """Read the files straight into the pinned buffer of staging set hs (16-byte aligned each, room for the decoders'
+    look-ahead after the last one).  Returns (views, offsets, sizes, clean): one uint8 view per file, where it lies in the
+    buffer, and whether every file was read."""
+    n = len(paths)
+    enc = [os.fsencode(p) for p in paths]
+    arr = (ctypes.c_char_p * n)(*enc)
+    offs, sizes = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    status = np.zeros(n, np.int32)
+    need = ctypes.c_uint64(0)
+    for _ in range(2):
+        stage = hs.stage
+        check(lib().b2_read_files(arr, n, stage.data_ptr(), max(0, stage.numel() - 64), offs.ctypes.data, sizes.ctypes.data,
+                                  status.ctypes.data, self.threads, ctypes.byref(need)))
+        if stage.numel() - 64 >= need.value:
+            break
+        hs.wait()
+        hs.ensure_stage(int(need.value) + 64)
+    buf = hs.stage.numpy()
+    views = [buf[int(offs[i]):int(offs[i]) + int(sizes[i])] for i in range(n)]
+    return views, offs, sizes, not status.any() and bool(sizes.all())
+
+
+FileBatchReader.read_into = _read_into
 
 
 def _read_or_error(path):
@@ -188,11 +217,95 @@ def load_pairs(img_paths, lbl_paths, store_as_array, key_fn, validate=None, devi
     return out
 
 
+_ELEM_SIZE = np.zeros(8, np.int64)
+for _code, _sz in ((_lib_mod.B2_U8, 1), (_lib_mod.B2_I8, 1), (_lib_mod.B2_U16, 2), (_lib_mod.B2_I16, 2), (_lib_mod.B2_U32, 4),
+                   (_lib_mod.B2_I32, 4), (_lib_mod.B2_F32, 4), (_lib_mod.B2_F64, 8)):
+    _ELEM_SIZE[_code] = _sz
+
+
+class BatchRecords:
+    """Every record of one clean decode batch serialised by ONE kernel launch into ONE device buffer (records back to
+    back in list order), planned by one native call (b2_example_layout_batch) and a few NumPy expressions: no per-record
+    Python.  Shard files then take contiguous byte ranges of that buffer."""
+
+    def __init__(self, ctx, keys, kind, ib, tb, dims, sdt, tdt, img_src, tgt_src, icount, tcount, keep):
+        n = len(keys)
+        ids = b"".join(keys)
+        id_off = np.zeros(n + 1, np.uint64)
+        np.cumsum([len(k) for k in keys], out=id_off[1:])
+        kind = np.ascontiguousarray(kind, dtype=np.int32)
+        ib, tb = np.ascontiguousarray(ib, dtype=np.uint64), np.ascontiguousarray(tb, dtype=np.uint64)
+        dims = np.ascontiguousarray(dims, dtype=np.int32)
+        descs = np.zeros(n, dtype=np.dtype(_lib_mod.BUILD_DESC_DTYPE))
+        cap = 320 * n + len(ids) + 64
+        scaf = np.empty(cap, np.uint8)
+        sl, tot, mx = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        idb = np.frombuffer(ids, np.uint8) if ids else np.zeros(1, np.uint8)
+        check(lib().b2_example_layout_batch(n, kind.ctypes.data, ib.ctypes.data, tb.ctypes.data, dims.ctypes.data, idb.ctypes.data,
+                                            id_off.ctypes.data, descs.ctypes.data, scaf.ctypes.data, cap, ctypes.byref(sl),
+                                            ctypes.byref(tot), ctypes.byref(mx)))
+        descs["src_dtype"], descs["tgt_dtype"] = sdt, tdt
+        descs["img_src"], descs["tgt_src"] = img_src, tgt_src
+        descs["img_count"], descs["tgt_count"] = icount, tcount
+        self.total, self.rec_off = int(tot.value), descs["out_off"].astype(np.int64)
+        self.out = torch.empty(((self.total + 15) // 16 * 16 + 16,), dtype=torch.uint8, device=ctx.device)
+        descs_d = ops.to_device(descs.view(np.uint8), ctx.device)
+        scaf_d = ops.to_device(scaf[:max(1, int(sl.value))], ctx.device)
+        isz = descs.dtype.itemsize
+        for s0 in range(0, n, 65535):
+            m = min(65535, n - s0)
+            check(lib().b2_tfrecord_build(ctx.handle, ctypes.c_void_p(descs_d.data_ptr() + s0 * isz), m, int(mx.value), _lib_mod.ptr(scaf_d),
+                                          _lib_mod.ptr(self.out), ctx.stream()))
+        self.keep = (descs_d, scaf_d, keep)
+
+    @classmethod
+    def from_decode(cls, job, keys, ctx):
+        """Decoded arrays (store_as_array=True): BytesList iff image and label are both uint8, else FloatList for both
+        (convert_to_example, _tfrecord_image_translation.py:160-197)."""
+        infos, images = job.infos_array(), job.images
+        ii, li = infos[0::2], infos[1::2]
+        kind = np.where((ii["dtype"] == _lib_mod.B2_U8) & (li["dtype"] == _lib_mod.B2_U8), 1, 2)
+        inum = ii["width"].astype(np.int64) * ii["height"] * ii["samples"]
+        lnum = li["width"].astype(np.int64) * li["height"] * li["samples"]
+        ib = np.where(kind == 1, inum * _ELEM_SIZE[ii["dtype"]], inum * 4)
+        tb = np.where(kind == 1, lnum * _ELEM_SIZE[li["dtype"]], lnum * 4)
+        dims = np.stack([ii["height"], ii["width"], ii["samples"], li["height"], li["width"]], axis=1)
+        base = job.out.data_ptr()
+        return cls(ctx, keys, kind, ib, tb, dims, ii["dtype"], li["dtype"], base + images["out_off"][0::2], base + images["out_off"][1::2],
+                   np.where(kind == 1, inum * _ELEM_SIZE[ii["dtype"]], inum), np.where(kind == 1, lnum * _ELEM_SIZE[li["dtype"]], lnum), job)
+
+    @classmethod
+    def from_files(cls, dev_buf, offs, sizes, infos, keys, ctx):
+        """The files' own bytes (store_as_array=False, _img_to_tf_mp.py:73-75): BytesList of the raw file content."""
+        ii, li = infos[0::2], infos[1::2]
+        n = len(keys)
+        dims = np.stack([ii["height"], ii["width"], ii["samples"], li["height"], li["width"]], axis=1)
+        base = dev_buf.data_ptr()
+        u8 = np.full(n, _lib_mod.B2_U8, np.int32)
+        return cls(ctx, keys, np.ones(n, np.int32), sizes[0::2], sizes[1::2], dims, u8, u8, base + offs[0::2], base + offs[1::2],
+                   sizes[0::2], sizes[1::2], dev_buf)
+
+    def byte_range(self, lo, hi):
+        """Bytes of records [lo, hi) of the batch."""
+        return int(self.rec_off[lo]), (int(self.rec_off[hi]) if hi < len(self.rec_off) else self.total)
+
+
 def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_directory, num_shards, key_fn,
                store_as_array, label="process", progress_every=100, validate=None, device=None, batch_pairs=None,
-               io_threads=8, png_as_tf=False, png_to_jpg=False):
-    """The reference's worker loop, restructured as a three-stage pipeline: a thread pool reads the files of batch
-    k+1 while the GPU decodes and serialises batch k and a writer thread appends batch k-1 to the shard file."""
+               io_threads=8, png_as_tf=False, png_to_jpg=False, path_key=None, fast_validate=None):
+    """The reference's worker loop as a pipeline over decode batches:
+
+        read-ahead thread : files of batch k+2 -> pinned staging (one native call), header parse + stream tables in place
+        main thread       : upload + decode kernels of batch k+1 queued; then batch k: status, records built by one launch,
+                            device -> pinned host copy queued
+        writer threads    : batch k-1: one pwrite per shard file and batch, different files in parallel
+
+    A batch in which every chip reads, decodes and pairs up cleanly never touches per-chip Python; a batch with any
+    irregularity (unreadable / undecodable chip, key mismatch, .jpg chips, convert_png_to_jpg, raw-bytes records, identifiers
+    from the georeferencing) goes through load_pairs, which reproduces the reference's skip-and-continue chip by chip.
+
+    path_key(path) -> identifier (when it depends on the file name only); fast_validate(infos) -> boolean array, False where
+    the reference's shape asserts would fail."""
     from concurrent.futures import ThreadPoolExecutor
     num_workers = len(ranges)
     assert not num_shards % num_workers
@@ -200,140 +313,229 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
     shard_ranges = np.linspace(ranges[worker_index][0], ranges[worker_index][1], per + 1).astype(int)
     num_files = ranges[worker_index][1] - ranges[worker_index][0]
     ctx = get_ctx(device)
-    counter = 0
     os.makedirs(output_directory, exist_ok=True)
+    try:
+        pair_bytes = os.path.getsize(img_filenames[ranges[worker_index][0]]) + os.path.getsize(lbl_filenames[ranges[worker_index][0]])
+    except (OSError, IndexError):
+        pair_bytes = 1 << 20
     if batch_pairs is None:
-        # the entropy decoders run one warp per compressed stream and are latency-bound: a batch should carry a few
-        # thousand streams, but not more than ~1 GB of file bytes (pinned staging) — sized from the first pair
-        try:
-            pair_bytes = os.path.getsize(img_filenames[ranges[worker_index][0]]) + os.path.getsize(lbl_filenames[ranges[worker_index][0]])
-        except (OSError, IndexError):
-            pair_bytes = 1 << 20
-        batch_pairs = int(max(32, min(2048, (768 << 20) // max(1, pair_bytes))))
-    n_slots = 4                                                             # rotating pinned write-back buffers
-    # rotating pinned write-back buffers and read-ahead buffers: kept per device between calls (pinning and first-touching
-    # a few hundred MB costs ~0.1 s, which is what a worker with a few thousand chips takes altogether)
+        # a batch should carry thousands of compressed streams for the decoders, but not more than ~1 GB of file bytes
+        # (pinned staging) — sized from the first pair
+        batch_pairs = int(max(32, min(1024, (512 << 20) // max(1, pair_bytes))))
+    # clean batches of decoded-array records, or of raw-file records that need no decode to be validated, skip per-chip Python
+    fast = bool(not png_to_jpg and path_key is not None and (store_as_array or validate is None))
+    if fast:
+        _codec.reserve_staging(ctx.device, int(pair_bytes * batch_pairs * 1.25) + (1 << 20))
+    n_slots = 4                                                             # rotating pinned write-back buffers, kept per device
     cache = _worker_buffers.setdefault(ctx.device.index, {"pinned": [None] * n_slots, "reader": None})
     pinned = cache["pinned"]
-    slot_futs = [[] for _ in range(n_slots)]                                # positional writes still reading a buffer
-    # decode batches run over the worker's whole file range (the entropy decoders want thousands of streams per launch);
-    # records are then serialised and written shard by shard, so a batch may feed several shard files
+    slot_futs = [[] for _ in range(n_slots)]                                # writes still reading a buffer
     lo_all, hi_all = int(shard_ranges[0]), int(shard_ranges[-1])
     # the first batches are small (1/8, 1/4, 1/2 of the full size): the pipeline's start-up latency is the time the first
-    # batch takes to go through read -> plan -> decode -> build -> write, and a worker with a few thousand chips is mostly that
+    # batch takes to go through read -> plan -> decode -> build -> write
     batches, b0, size = [], lo_all, max(32, batch_pairs // 8)
     while b0 < hi_all:
         b1 = min(b0 + size, hi_all)
         batches.append((b0, b1))
         b0, size = b1, min(batch_pairs, size * 2)
-    use_mmap = os.environ.get("B2_SHARD_WRITE", "mmap") == "mmap"
     files = [open(os.path.join(output_directory, "%s-%.5d-of-%.5d" % (name, worker_index * per + s, num_shards)), "w+b")
              for s in range(per)]
     shard_off = [0] * per
     shard_count = [0] * per
-    seq = 0
-    with ThreadPoolExecutor(max_workers=max(1, io_threads)) as pool, ThreadPoolExecutor(max_workers=1) as writer, \
-            ThreadPoolExecutor(max_workers=8) as wpool:
+    state = {"counter": 0, "seq": 0}
+    copy_stream = torch.cuda.Stream(ctx.device)
+
+    def count_records(s, k):
+        """k more records in shard s: the reference's progress line at every multiple of progress_every."""
+        before = state["counter"]
+        state["counter"] += k
+        shard_count[s] += k
+        for mult in range(before // progress_every + 1, state["counter"] // progress_every + 1):
+            print("%s [%s %d]: Processed %d of %d images in %s batch." %
+                  (datetime.now(), label, worker_index, mult * progress_every, num_files, label))
+            sys.stdout.flush()
+
+    def shard_done(s):
+        print("%s [%s %d]: Wrote %d images to %s" % (datetime.now(), label, worker_index, shard_count[s], files[s].name))
+        sys.stdout.flush()
+
+    with ThreadPoolExecutor(max_workers=2) as pool, ThreadPoolExecutor(max_workers=1) as writer, \
+            ThreadPoolExecutor(max_workers=max(8, io_threads)) as wpool:
         reader = cache["reader"]
         if reader is None:
-            reader = cache["reader"] = FileBatchReader(depth=3, threads=io_threads)
+            reader = cache["reader"] = FileBatchReader(depth=5, threads=io_threads)
 
-        def read_and_plan(paths):
-            blobs = reader.read(paths)                                      # one native call; the GIL is free meanwhile
-            planned = None
-            if (store_as_array or validate is not None) and not png_to_jpg: # host half of the decode, off the main thread
-                planned = _codec.plan_blobs([b"" if isinstance(b, Exception) else b for b in blobs], ctx.device, png_as_tf)
-            return blobs, planned
+        def write_back(buf, total, pieces):
+            """Device buffer -> pinned slot -> files.  pieces: [(shard, byte lo, byte hi)] of buf."""
+            slot = state["seq"] % n_slots
+            state["seq"] += 1
+            for x in slot_futs[slot]:                                       # the writes that last used this pinned buffer
+                for y in x.result():
+                    y.result()
+            slot_futs[slot] = []
+            if pinned[slot] is None or pinned[slot].numel() < total:
+                pinned[slot] = torch.empty((int(total * 1.1) + 4096,), dtype=torch.uint8).pin_memory()
+            host = pinned[slot][:total]
+            cur = torch.cuda.current_stream(ctx.device)
+            copy_stream.wait_stream(cur)                                    # the copy runs beside the next batch's decode
+            with torch.cuda.stream(copy_stream):
+                host.copy_(buf[:total], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(copy_stream)
+            buf.record_stream(copy_stream)
+            jobs = []
+            for s, lo, hi in pieces:
+                jobs.append((files[s].fileno(), lo, hi, shard_off[s]))
+                shard_off[s] += hi - lo
 
-        def submit_reads(rng):
+            def _write(h=host, ev=done, jobs=jobs):
+                ev.synchronize()                                             # the records have arrived in pinned memory
+                mv = memoryview(h.numpy())
+                # write(2) on ONE file serialises on its inode lock (3.3 GB/s on tmpfs whatever the thread count), writes to
+                # different files do not (28 GB/s over 8 files, 46 GB/s over 16: tools/shm_write_probe.py): one pwrite per
+                # shard file and batch
+                return [wpool.submit(os.pwrite, fd, mv[lo:hi], off) for fd, lo, hi, off in jobs]
+            slot_futs[slot].append(writer.submit(_write))
+
+        def read_and_plan(rng):
             paths = []
             for i in range(*rng):
                 paths += [img_filenames[i], lbl_filenames[i]]
-            return pool.submit(read_and_plan, paths)
-        pending_reads = submit_reads(batches[0]) if batches else None
-        try:
-            for bi, (b0, b1) in enumerate(batches):
-                blobs, planned = pending_reads.result()
-                pending_reads = submit_reads(batches[bi + 1]) if bi + 1 < len(batches) else None
-                idx = list(range(b0, b1))
-                pairs = load_pairs([img_filenames[i] for i in idx], [lbl_filenames[i] for i in idx], store_as_array,
-                                   key_fn, validate, ctx.device, blobs=blobs, png_as_tf=png_as_tf, planned=planned,
-                                   png_to_jpg=png_to_jpg)
-                for s in range(per):
-                    lo, hi = max(b0, int(shard_ranges[s])), min(b1, int(shard_ranges[s + 1]))
-                    if lo >= hi:
-                        continue
-                    items = []
-                    for i in range(lo, hi):
-                        p = pairs[i - b0]
-                        if isinstance(p, Exception):
-                            print(p)
-                            print("SKIPPED: Unexpected eror while decoding %s." % img_filenames[i])
-                            continue
-                        items.append(p)
-                        shard_count[s] += 1
-                        counter += 1
-                        if not counter % progress_every:
-                            print("%s [%s %d]: Processed %d of %d images in %s batch." %
-                                  (datetime.now(), label, worker_index, counter, num_files, label))
-                            sys.stdout.flush()
-                    if items:
-                        buf, _, total = ops.build_records(items, ctx.device)
-                        slot = seq % n_slots
-                        seq += 1
-                        for x in slot_futs[slot]:                                # the writes that last used this buffer
-                            for y in x.result():
-                                y.result()
-                        slot_futs[slot] = []
-                        if pinned[slot] is None or pinned[slot].numel() < total:
-                            pinned[slot] = torch.empty((int(total * 1.1) + 4096,), dtype=torch.uint8).pin_memory()
-                        host = pinned[slot][:total]
-                        host.copy_(buf[:total], non_blocking=True)
-                        done = torch.cuda.Event()
-                        done.record(torch.cuda.current_stream(ctx.device))
+            if not fast:
+                blobs = reader.read(paths)                                  # one native call; the GIL is free meanwhile
+                planned = None
+                if (store_as_array or validate is not None) and not png_to_jpg:   # host half of the decode, off the main thread
+                    planned = _codec.plan_blobs([b"" if isinstance(b, Exception) else b for b in blobs], ctx.device, png_as_tf)
+                return dict(fast=False, blobs=blobs, planned=planned)
+            hs = _codec.take_staging(ctx.device)
+            planned = infos = offs = sizes = None
+            try:
+                blobs, offs, sizes, clean = reader.read_into(paths, hs)     # straight into the pinned staging buffer
+                if clean and store_as_array:
+                    planned = _codec.plan_blobs(blobs, ctx.device, png_as_tf, inplace=hs)
+                elif clean:                                                 # raw-bytes records: the header fields only
+                    infos = np.frombuffer(_codec.probe_blobs(blobs, png_as_tf=png_as_tf), dtype=_codec.IMAGE_INFO_DTYPE, count=len(paths))
+                    clean = not infos["status"].any()
+            except Exception:
+                planned, clean = None, False
+            if not clean or (store_as_array and planned is None):
+                if planned is not None:
+                    planned.release()
+                hs.pending = False
+                return dict(fast=False, blobs=None, planned=None)           # the chip-by-chip path re-reads the files
+            keys = [path_key(p) for p in paths]
+            return dict(fast=True, planned=planned, keys=keys, hs=hs, infos=infos, offs=offs, sizes=sizes)
 
-                        def _write(fd=files[s].fileno(), h=host, ev=done, off=shard_off[s]):
-                            ev.synchronize()                                     # the records have arrived in pinned memory
-                            src = h.numpy()
-                            step = 16 << 20
-                            if use_mmap:
-                                # write(2) on one file serialises on its inode lock (measured: 8 threads of pwrite = 3.5 GB/s
-                                # on tmpfs, the speed of one); page faults on a shared mapping do not, so the chunks are
-                                # copied into a mapping of the (grown) file by several threads at once
-                                end = off + len(src)
-                                try:
-                                    os.ftruncate(fd, end)                        # this thread is the only one that grows files
-                                    a0 = off & ~(mmap.ALLOCATIONGRANULARITY - 1)
-                                    mm = mmap.mmap(fd, end - a0, offset=a0)
-                                except (OSError, ValueError):                    # a file system without shared mappings: write(2)
-                                    mm = None
-                                if mm is not None:
-                                    dst = np.frombuffer(mm, dtype=np.uint8)[off - a0:]
-                                    return [wpool.submit(np.copyto, dst[o:o + step], src[o:o + step]) for o in range(0, len(src), step)]
-                            mv = memoryview(src)                                 # positional writes: order-free, several in flight
-                            return [wpool.submit(os.pwrite, fd, mv[o:o + step], off + o) for o in range(0, len(mv), step)]
-                        shard_off[s] += total
-                        slot_futs[slot].append(writer.submit(_write))
-                    if hi == int(shard_ranges[s + 1]):
-                        print("%s [%s %d]: Wrote %d images to %s" % (datetime.now(), label, worker_index, shard_count[s], files[s].name))
-                        sys.stdout.flush()
+        def stage1(bi):
+            """Batch bi: wait for its files + plan, queue its upload and decode (nothing synchronised)."""
+            b = pending.pop(0).result()
+            if bi + 2 < len(batches):
+                pending.append(pool.submit(read_and_plan, batches[bi + 2]))  # two batches ahead, on two threads
+            b["range"] = batches[bi]
+            if b["fast"] and store_as_array:
+                b["job"] = _codec.decode_enqueue(b["planned"], ctx.device)
+            elif b["fast"]:                                                 # the files as they are: one upload of the staging buffer
+                hs = b["hs"]
+                used = int(b["offs"][-1] + b["sizes"][-1]) + 16
+                b["dev"] = hs.stage[:used].to(ctx.device, non_blocking=True)
+                hs.busy = torch.cuda.Event()
+                hs.busy.record(torch.cuda.current_stream(ctx.device))
+                hs.pending = False
+            return b
+
+        def slow_batch(b0, b1, blobs, planned):
+            idx = list(range(b0, b1))
+            pairs = load_pairs([img_filenames[i] for i in idx], [lbl_filenames[i] for i in idx], store_as_array,
+                               key_fn, validate, ctx.device, blobs=blobs, png_as_tf=png_as_tf, planned=planned,
+                               png_to_jpg=png_to_jpg)
+            for s in range(per):
+                lo, hi = max(b0, int(shard_ranges[s])), min(b1, int(shard_ranges[s + 1]))
+                if lo >= hi:
+                    continue
+                items = []
+                for i in range(lo, hi):
+                    p = pairs[i - b0]
+                    if isinstance(p, Exception):
+                        print(p)
+                        print("SKIPPED: Unexpected eror while decoding %s." % img_filenames[i])
+                        continue
+                    items.append(p)
+                    count_records(s, 1)
+                if items:
+                    buf, _, total = ops.build_records(items, ctx.device)
+                    write_back(buf, total, [(s, 0, total)])
+                if hi == int(shard_ranges[s + 1]):
+                    shard_done(s)
+
+        def finish(b):
+            b0, b1 = b["range"]
+            if b["fast"]:
+                keys = b["keys"]
+                if store_as_array:
+                    job = b["job"]
+                    st = job.status()                                       # waits for this batch's decode only
+                    infos = job.infos_array()
+                    ok = not st.any() and not infos["status"].any()
+                else:
+                    infos, ok = b["infos"], True
+                ok = ok and keys[0::2] == keys[1::2]
+                if ok and fast_validate is not None:
+                    ok = bool(np.all(fast_validate(infos)))
+                if ok:
+                    ids = [k.encode("utf-8") for k in keys[0::2]]
+                    rec = BatchRecords.from_decode(job, ids, ctx) if store_as_array else \
+                        BatchRecords.from_files(b["dev"], b["offs"], b["sizes"], infos, ids, ctx)
+                    pieces = []
+                    done = []
+                    for s in range(per):
+                        lo, hi = max(b0, int(shard_ranges[s])), min(b1, int(shard_ranges[s + 1]))
+                        if lo >= hi:
+                            continue
+                        pieces.append((s,) + rec.byte_range(lo - b0, hi - b0))
+                        count_records(s, hi - lo)
+                        if hi == int(shard_ranges[s + 1]):
+                            done.append(s)
+                    write_back(rec.out, rec.total, pieces)
+                    for s in done:
+                        shard_done(s)
+                    return
+                b = dict(blobs=None, planned=None)                          # an irregular batch: chip by chip, from the files
+            slow_batch(b0, b1, b.get("blobs"), b.get("planned"))
+
+        pending = [pool.submit(read_and_plan, batches[k]) for k in range(min(2, len(batches)))]
+        prev = None
+        try:
+            for bi in range(len(batches)):
+                cur = stage1(bi)
+                if prev is not None:
+                    finish(prev)
+                prev = cur
+            if prev is not None:
+                finish(prev)
+                prev = None
         finally:
-            if pending_reads is not None:                                   # aborted with a read-ahead in flight: hand its
-                try:                                                        # pinned staging set back
-                    _, dropped = pending_reads.result()
-                    if dropped is not None:
-                        dropped.release()
-                except Exception:
-                    pass
+            for leftover in pending:
+                if leftover is not None:                                    # aborted with a read-ahead in flight: hand its
+                    try:                                                    # pinned staging set back (ADVICE r1)
+                        dropped = leftover.result().get("planned")
+                        if dropped is not None:
+                            dropped.release()
+                    except Exception:
+                        pass
+            if prev is not None and prev.get("planned") is not None:
+                prev["planned"].release()
+        for s in range(per):                                                # shards that received no file at all
+            if int(shard_ranges[s]) == int(shard_ranges[s + 1]):
+                shard_done(s)
         for fl in slot_futs:
             for x in fl:
                 for y in x.result():
                     y.result()
     for f in files:
         f.close()
-    print("%s [%s %d]: Wrote %d images to %d shards." % (datetime.now(), label, worker_index, counter, per))
+    print("%s [%s %d]: Wrote %d images to %d shards." % (datetime.now(), label, worker_index, state["counter"], per))
     sys.stdout.flush()
-    return counter
+    return state["counter"]
 
 
 def run_workers(num_workers, fn):

@@ -1974,7 +1974,7 @@ struct ImgPlan {
 };
 
 void fill_image(const uint8_t* blob, uint64_t size, int i, const b2_image_info& info, const ImgPlan& pl,
-                b2_stream_desc* streams, uint8_t* stage, int32_t* status) {
+                b2_stream_desc* streams, uint8_t* stage, int32_t* status, bool inplace) {
     std::vector<uint64_t> offs(info.n_blocks), cnts(info.n_blocks), dlen(info.n_blocks);
     if (b2_image_blocks(blob, size, &info, offs.data(), cnts.data(), dlen.data(), info.n_blocks) != 0) {
         status[i] = 2;   // stream slots of this image stay codec 0 (ignored by the kernels)
@@ -1982,8 +1982,8 @@ void fill_image(const uint8_t* blob, uint64_t size, int i, const b2_image_info& 
     }
     if (info.format == 2) {   // PNG: concatenate the IDAT payloads into one zlib stream
         uint64_t total = 0;
-        for (int k = 0; k < info.n_blocks; k++) {
-            memcpy(stage + pl.stage_off + total, blob + offs[k], cnts[k]);
+        for (int k = 0; k < info.n_blocks; k++) {             // in place: the payloads only ever move towards the file's start
+            memmove(stage + pl.stage_off + total, blob + offs[k], cnts[k]);
             total += cnts[k];
         }
         b2_stream_desc& sd = streams[pl.stream0];
@@ -2018,7 +2018,7 @@ void fill_image(const uint8_t* blob, uint64_t size, int i, const b2_image_info& 
             ps.image = i;
         }
     } else {                  // TIFF: the file as is, one stream per tile / strip
-        memcpy(stage + pl.stage_off, blob, size);
+        if (!inplace) memcpy(stage + pl.stage_off, blob, size);
         const int codec = info.compression == 1 ? CODEC_RAW : (info.compression == 5 ? CODEC_LZW : CODEC_ZLIB);
         for (int k = 0; k < info.n_blocks; k++) {
             b2_stream_desc& sd = streams[pl.stream0 + k];
@@ -2038,9 +2038,14 @@ extern "C" int b2_decode_plan_batch(const uint8_t* const* blobs, const uint64_t*
                                     uint8_t* stage, uint64_t stage_cap, int n_threads, uint32_t flags, b2_decode_plan* plan) {
     B2_REQUIRE(blobs && sizes && infos && status && images && plan, "b2_decode_plan_batch: NULL argument");
     B2_REQUIRE(n >= 0, "b2_decode_plan_batch: n < 0");
+    // B2_PLAN_INPLACE: every blob already lies inside stage[0, stage_cap) (read there by b2_read_files): no gather, the
+    // streams point at the files where they are (PNG IDAT payloads are compacted towards the start of their file)
+    const bool inplace = (flags & B2_PLAN_INPLACE) != 0;
+    flags &= ~B2_PLAN_INPLACE;
+    B2_REQUIRE(!inplace || stage, "b2_decode_plan_batch: B2_PLAN_INPLACE needs the buffer that holds the files");
     memset(plan, 0, sizeof(*plan));
     std::vector<ImgPlan> pl((size_t)n);
-    uint64_t stage_pos = 0, scratch_pos = 0, out_pos = 0, compressed = 0;
+    uint64_t stage_pos = 0, stage_hi = 0, scratch_pos = 0, out_pos = 0, compressed = 0;
     int n_streams = 0;
     uint32_t mask = 0, max_raw = 0;
     for (int i = 0; i < n; i++) {
@@ -2050,6 +2055,12 @@ extern "C" int b2_decode_plan_batch(const uint8_t* const* blobs, const uint64_t*
         if (!blobs[i] || sizes[i] == 0) { memset(&info, 0, sizeof(info)); info.status = 2; status[i] = 2; continue; }
         b2_image_probe(blobs[i], sizes[i], flags, &info);
         if (info.status != 0) { status[i] = info.status; continue; }
+        if (inplace) {
+            B2_REQUIRE(blobs[i] >= stage && blobs[i] + sizes[i] <= stage + stage_cap && ((blobs[i] - stage) & 15) == 0,
+                       "b2_decode_plan_batch: B2_PLAN_INPLACE blob outside the buffer or not 16-byte aligned in it");
+            B2_REQUIRE(!(info.format == 2 && info.png_color_type == 3), "b2_decode_plan_batch: palette PNGs need the gathering mode");
+            stage_pos = (uint64_t)(blobs[i] - stage);
+        }
         const int bs = info.dtype == B2_U8 || info.dtype == B2_I8 ? 1 : (info.dtype == B2_U16 || info.dtype == B2_I16 ? 2 : (info.dtype == B2_F64 ? 8 : 4));
         pl[i] = ImgPlan{stage_pos, scratch_pos, out_pos, n_streams};
         b2_image_desc& im = images[i];
@@ -2090,9 +2101,11 @@ extern "C" int b2_decode_plan_batch(const uint8_t* const* blobs, const uint64_t*
         }
         compressed += sizes[i];
         stage_pos = up_to(stage_pos, 16);
+        if (stage_pos > stage_hi) stage_hi = stage_pos;
         out_pos += up_to((uint64_t)info.width * info.height * info.samples * bs, 256);
     }
-    plan->stage_bytes = stage_pos + 16;
+    B2_REQUIRE(!inplace || stage_hi + 16 <= stage_cap, "b2_decode_plan_batch: B2_PLAN_INPLACE needs 16 spare bytes after the last file");
+    plan->stage_bytes = stage_hi + 16;
     plan->scratch_bytes = scratch_pos + 16;
     plan->out_bytes = out_pos + 16;
     plan->compressed_bytes = compressed;
@@ -2108,7 +2121,7 @@ extern "C" int b2_decode_plan_batch(const uint8_t* const* blobs, const uint64_t*
     if (nt < 1) nt = 1;
     auto work = [&](int t) {
         for (int i = t; i < n; i += nt)
-            if (status[i] == 0) fill_image(blobs[i], sizes[i], i, infos[i], pl[i], streams, stage, status);
+            if (status[i] == 0) fill_image(blobs[i], sizes[i], i, infos[i], pl[i], streams, stage, status, inplace);
     };
     if (nt == 1) work(0);
     else {

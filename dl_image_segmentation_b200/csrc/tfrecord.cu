@@ -861,3 +861,38 @@ extern "C" int b2_example_layout(int kind, uint64_t img_bytes, uint64_t tgt_byte
     (void)payload_entry_total;
     return 0;
 }
+
+/* The scaffolds and descriptor geometry of n records in one call (the per-record form costs the translators one ctypes
+ * round trip and a dozen Python objects per chip, which is what bounded them once decode and serialisation ran on the GPU). */
+extern "C" int b2_example_layout_batch(int n, const int32_t* kind, const uint64_t* img_bytes, const uint64_t* tgt_bytes,
+                                       const int32_t* dims, const uint8_t* ids, const uint64_t* id_off, b2_build_desc* descs,
+                                       uint8_t* scaffold, uint64_t scaffold_cap, uint64_t* scaffold_len, uint64_t* total_bytes,
+                                       uint64_t* max_record) {
+    B2_REQUIRE(n >= 0 && (n == 0 || (kind && img_bytes && tgt_bytes && dims && id_off && descs && scaffold)) && scaffold_len &&
+               total_bytes && max_record, "b2_example_layout_batch: NULL argument");
+    uint64_t pos = 0, sc = 0, mx = 0;
+    for (int i = 0; i < n; i++) {
+        const int32_t* d = dims + 5 * (size_t)i;
+        uint32_t pl[3];
+        uint64_t el = 0;
+        B2_REQUIRE(sc + 320 + (id_off[i + 1] - id_off[i]) <= scaffold_cap, "b2_example_layout_batch: scaffold buffer too small");
+        if (int e = b2_example_layout(kind[i], img_bytes[i], tgt_bytes[i], d[0], d[1], d[2], d[3], d[4],
+                                      ids ? ids + id_off[i] : nullptr, id_off[i + 1] - id_off[i], scaffold + sc,
+                                      scaffold_cap - sc, pl, &el)) return e;
+        b2_build_desc& o = descs[i];
+        o.out_off = pos;
+        o.example_len = el;
+        o.scaffold_off = sc;
+        o.piece_len[0] = pl[0];
+        o.piece_len[1] = pl[1];
+        o.piece_len[2] = pl[2];
+        o.kind = kind[i];
+        sc += (uint64_t)pl[0] + pl[1] + pl[2];
+        pos += el + 16;
+        if (el + 16 > mx) mx = el + 16;
+    }
+    *scaffold_len = sc;
+    *total_bytes = pos;
+    *max_record = mx;
+    return 0;
+}

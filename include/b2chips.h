@@ -169,6 +169,7 @@ int b2_example_layout(int kind, uint64_t img_payload_bytes, uint64_t tgt_payload
                       const uint8_t* identifier, uint64_t identifier_len,
                       uint8_t* scaffold, uint64_t cap, uint32_t piece_len[3], uint64_t* example_len);
 
+
 typedef struct {
     uint64_t out_off;       /* where the framed record starts in out_dev                                      */
     uint64_t example_len;   /* length of the Example (frame adds 16)                                          */
@@ -186,6 +187,15 @@ typedef struct {
 /* Serialise + frame n records: header (length + masked CRC), Example bytes, footer (masked data CRC). */
 int b2_tfrecord_build(b2_ctx* ctx, const b2_build_desc* descs_dev, int n, uint64_t max_record_bytes,
                       const uint8_t* scaffold_dev, uint8_t* out_dev, b2_stream stream);
+
+/* The same for n records in one call (the translators' worker loop, _img_to_tf_mp.py:123-141, per batch instead of per
+ * chip): dims is n x {img_h, img_w, img_c, tgt_h, tgt_w}; identifiers are ids[id_off[i] .. id_off[i+1]).  Fills out_off
+ * (records back to back from 0, 16 framing bytes each), example_len, scaffold_off, piece_len and kind of descs[i]; the
+ * caller fills the payload sources.  scaffold needs 320 bytes + the identifier per record. */
+int b2_example_layout_batch(int n, const int32_t* kind, const uint64_t* img_payload_bytes, const uint64_t* tgt_payload_bytes,
+                            const int32_t* dims, const uint8_t* ids, const uint64_t* id_off, b2_build_desc* descs,
+                            uint8_t* scaffold, uint64_t scaffold_cap, uint64_t* scaffold_len, uint64_t* total_bytes,
+                            uint64_t* max_record);
 
 /* ------------------------------------------------------------------ K1: chip decode (TIFF LZW / DEFLATE / none, PNG)
  * Replace rasterio MemoryFile(...).open().read() -> GDAL -> libtiff/libpng (_img_to_tf_mp.py:45-48,
@@ -222,6 +232,9 @@ typedef struct {
  * 8-bit grey, grey+alpha, RGB and RGBA are the same in both.  Adam7-interlaced files are decoded for bit depths 8 and
  * 16; interlaced 1/2/4-bit files are out of scope (status 3). */
 #define B2_PNG_AS_TF 1u
+/* b2_decode_plan_batch only: the blobs already lie (16-byte aligned) inside the staging buffer — b2_read_files put them
+ * there — so nothing is gathered: the stream table points at the files in place and the whole buffer is uploaded. */
+#define B2_PLAN_INPLACE 0x1000u
 
 /* Host-side header parse (TIFF IFD / PNG chunks); never touches the GPU. */
 int b2_image_probe(const uint8_t* blob, uint64_t size, uint32_t flags, b2_image_info* info);

@@ -30,6 +30,9 @@ try:
     wrap(_translate,'load_pairs','load_pairs(main)')
     wrap(ops,'build_records','build_records(main)')
     wrap(_translate.FileBatchReader,'read','read(thread)')
+    wrap(_translate.FileBatchReader,'read_into','read_into(thread)')
+    wrap(_codec,'decode_enqueue','decode_enqueue(main)'); wrap(_codec.DecodeJob,'status','job.status(main)')
+    wrap(_translate.BatchRecords,'__init__','BatchRecords(main)')
     wrap(_codec,'decode_planned','decode_planned(main)'); wrap(_codec,'plan_blobs','plan_blobs(thread)')
     wrap(os,'pwrite','pwrite(threads,sum)'); import numpy as _np; wrap(_np,'copyto','copyto(threads,sum)')
     wrap(torch.cuda.Event,'synchronize','event.sync(any)')
