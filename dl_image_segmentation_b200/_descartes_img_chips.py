@@ -217,3 +217,55 @@ def _cat_last(arrays):
     if sv is None:
         return torch.cat(arrays, dim=-1)
     return torch.cat([a.view(sv) for a in arrays], dim=-1).view(arrays[0].dtype)
+
+
+# ------------------------------------------------------------------------------------------------ label rasterisation
+def read_geojson_layer(path_or_dict):
+    """A label layer from GeoJSON (the format of the reference's label data, .MISSING_LARGE_BLOBS): list of
+    (rings, properties) per Polygon / MultiPolygon feature, in file order — what iterating the OGR layer yields.
+    Coordinates are taken as they are: they must already be in the tile's CRS (OGR's on-the-fly reprojection is PROJ's)."""
+    import json
+    gj = path_or_dict
+    if not isinstance(gj, dict):
+        with open(gj, "r") as f:
+            gj = json.load(f)
+    feats = gj["features"] if gj.get("type") == "FeatureCollection" else [gj]
+    layer = []
+    for ft in feats:
+        geom = ft.get("geometry") or {}
+        if geom.get("type") == "Polygon":
+            rings = [np.asarray(r, dtype=np.float64)[:, :2] for r in geom["coordinates"]]
+        elif geom.get("type") == "MultiPolygon":
+            rings = [np.asarray(r, dtype=np.float64)[:, :2] for poly in geom["coordinates"] for r in poly]
+        else:
+            continue                                            # RasterizeLayer burns nothing for an empty geometry
+        layer.append((rings, ft.get("properties") or {}))
+    return layer
+
+
+def create_label_array_for_tile(ctx, label_data, attrib_to_burn=None, layer_idx=0, background_value=255, device=None):
+    """Rasterises the label polygons within the geocontext -> (S, S) uint8 CUDA tensor, S = tilesize + 2 * pad
+    (reference :633-689: GDAL MEM raster filled with background_value, RasterizeLayer ALL_TOUCHED with the attribute or 1).
+
+    ctx needs ``tilesize``, ``pad`` and ``geotrans`` (GDAL order) like a DLTile.  label_data: a GeoJSON path / dict
+    (read_geojson_layer), or a list of layers / one layer = list of (rings in the tile's map coordinates, properties)."""
+    size = int(ctx.tilesize) + int(ctx.pad) * 2                 # reference :660
+    layer = label_data
+    if isinstance(label_data, (str, bytes, dict)) or hasattr(label_data, "__fspath__"):
+        layer = read_geojson_layer(label_data)
+    elif len(label_data) and isinstance(label_data[0], list):   # several layers: GetLayerByIndex(layer_idx), :668
+        layer = label_data[layer_idx]
+    gt = [float(v) for v in ctx.geotrans]
+    if gt[2] != 0.0 or gt[4] != 0.0:
+        raise B2Error("create_label_array_for_tile: rotated geotransforms are out of scope (DLTiles are north-up)")
+    inv1, inv5 = 1.0 / gt[1], 1.0 / gt[5]                       # GDALInvGeoTransform for a north-up raster
+    inv0, inv3 = -gt[0] * inv1, -gt[3] * inv5
+    feats = []
+    for rings, props in layer:
+        value = int(props[attrib_to_burn]) if attrib_to_burn else 1          # reference :684-687
+        px = []
+        for r in rings:
+            r = np.asarray(r, dtype=np.float64).reshape(-1, 2)
+            px.append(np.stack([inv0 + r[:, 0] * inv1, inv3 + r[:, 1] * inv5], axis=1))
+        feats.append((px, value))
+    return ops.rasterize_polygons(feats, size, background_value, all_touched=True, device=device)

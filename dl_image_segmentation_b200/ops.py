@@ -687,3 +687,61 @@ def iter_parsed_shards(shards, mode, verify_crc=True, mean=None, std=None, num_c
         yield parse_shard(si, mode, verify_crc=verify_crc, mean=mean, std=std, num_classes=num_classes, out=out) + (si,)
 
 
+# ------------------------------------------------------------------------------------------------ label rasterisation
+def rasterize_polygons(features, size, background_value=255, all_touched=True, device=None):
+    """Burn polygons into a (H, W) uint8 CUDA tensor with GDAL's RasterizeLayer semantics (ALL_TOUCHED by default).
+
+    features: list of (rings, value) in burn order; rings = list of (N, 2) arrays in PIXEL space (x = column, y = line),
+    first ring the shell, the others holes or further polygons (even-odd rule over all of them); value 0..255.
+    The host only lays the edges out (NumPy); the scanline fill, the edge walk and the last-feature-wins resolution run in
+    b2_rasterize_polygons.  Replaces gdal.RasterizeLayer in create_label_array_for_tile (_descartes_img_chips.py:667-688)."""
+    ctx = get_ctx(device)
+    H, W = (int(size), int(size)) if np.isscalar(size) else (int(size[0]), int(size[1]))
+    fill, fill_off, miny, rows, lines, line_feat, values, max_edges = [], [0], [], [], [], [], [], 1
+    for f, (rings, value) in enumerate(features):
+        if not 0 <= int(value) <= 255:
+            raise B2Error("rasterize_polygons: burn values must be 0..255 (GDT_Byte raster)")
+        values.append(int(value))
+        n_edges, ys = 0, []
+        for r in rings:
+            r = np.asarray(r, dtype=np.float64).reshape(-1, 2)
+            if len(r) < 2:
+                continue
+            ys.append(r[:, 1])
+            closed = r[0, 0] == r[-1, 0] and r[0, 1] == r[-1, 1]
+            o = r[:-1] if closed else r                          # fill: every vertex with its predecessor, wrapping around
+            if len(o):
+                fill.append(np.concatenate([np.roll(o, 1, axis=0), o], axis=1))
+                n_edges += len(o)
+            if all_touched:                                      # edge walk: the ring as given (GDAL does not close it)
+                lines.append(np.concatenate([r[:-1], r[1:]], axis=1))
+                line_feat.append(np.full(len(r) - 1, f, np.uint32))
+        fill_off.append(fill_off[-1] + n_edges)
+        max_edges = max(max_edges, n_edges)
+        if n_edges:
+            yy = np.concatenate(ys)
+            lo, hi = max(int(yy.min()), 0), min(int(yy.max()), H - 1)      # (int) truncation, as GDAL's miny / maxy
+            miny.append(lo)
+            rows.append(max(0, hi - lo + 1))
+        else:
+            miny.append(0)
+            rows.append(0)
+    nF = len(values)
+    job_off = np.zeros(nF + 1, np.uint32)
+    np.cumsum(rows, out=job_off[1:])
+    n_jobs = int(job_off[-1])
+    fill_a = np.ascontiguousarray(np.concatenate(fill)) if fill else np.zeros((0, 4))
+    line_a = np.ascontiguousarray(np.concatenate(lines)) if lines else np.zeros((0, 4))
+    lf = np.concatenate(line_feat) if line_feat else np.zeros(0, np.uint32)
+    if n_jobs * max_edges * 4 > (4 << 30):
+        raise B2Error("rasterize_polygons: layer too complex for one call (%d scanline jobs x %d edges)" % (n_jobs, max_edges))
+    d = lambda a, dt: to_device(np.ascontiguousarray(a, dtype=dt).view(np.uint8).reshape(-1), ctx.device) if np.asarray(a).size else None
+    fill_d, off_d, miny_d, job_d = d(fill_a, np.float64), d(fill_off, np.uint32), d(miny, np.int32), d(job_off, np.uint32)
+    line_d, lf_d, val_d = d(line_a, np.float64), d(lf, np.uint32), d(values, np.uint8)
+    owner = torch.empty((H * W,), dtype=torch.int32, device=ctx.device)
+    ints = torch.empty((max(1, n_jobs * max_edges),), dtype=torch.int32, device=ctx.device)
+    out = torch.empty((H, W), dtype=torch.uint8, device=ctx.device)
+    check(lib().b2_rasterize_polygons(ctx.handle, ptr(fill_d), ptr(off_d), ptr(miny_d), ptr(job_d), n_jobs, ptr(line_d), ptr(lf_d),
+                                      len(lf), ptr(val_d), nF, W, H, int(background_value), max_edges, ptr(owner), ptr(ints), ptr(out),
+                                      ctx.stream()))
+    return out

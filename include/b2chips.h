@@ -406,6 +406,23 @@ int b2_jpeg_encode_scan(b2_ctx* ctx, const uint8_t* pixels_dev, const b2_jpeg_en
                         const b2_jpeg_enc_job* jobs_host, int n, int quality, int16_t* coef_dev, uint64_t coef_count,
                         uint8_t* out_dev, uint32_t* out_len_dev, b2_stream stream);
 
+/* ------------------------------------------------------------------ label rasterisation
+ * Replaces gdal.RasterizeLayer(mem_ds, [1], layer, options=['ALL_TOUCHED=TRUE'[, 'ATTRIBUTE=...']]) over a raster filled with
+ * background_value, create_label_array_for_tile (_descartes_img_chips.py:633-689): polygons (any number of rings each:
+ * holes, multi-polygons) burnt in feature order — the last feature touching a pixel wins — with GDAL's two passes per
+ * feature: the pixel-centre scanline fill and, for ALL_TOUCHED, every pixel an edge passes through.
+ * Everything is in PIXEL space (the host applies the inverse geotransform) and on the device:
+ *   fill_segs      double[4] per edge of the fill pass (x1, y1, x2, y2; rings implicitly closed), grouped by feature
+ *   fill_seg_off   uint32[n_features + 1]   feat_miny int32[n_features] (first scanline of the feature, clipped to the raster)
+ *   job_off        uint32[n_features + 1]   prefix sum of the features' scanline counts; n_jobs = job_off[n_features]
+ *   line_segs      double[4] per edge of the ALL_TOUCHED pass (n_line_segs = 0: centre-only burn), line_seg_feat its feature
+ *   values         uint8[n_features] burn values; max_ints = most edges of any one feature
+ *   owner_ws       int32[width * height] scratch; ints_ws int32[n_jobs * max_ints] scratch; out uint8[height * width] */
+int b2_rasterize_polygons(b2_ctx* ctx, const double* fill_segs, const uint32_t* fill_seg_off, const int32_t* feat_miny,
+                          const uint32_t* job_off, uint32_t n_jobs, const double* line_segs, const uint32_t* line_seg_feat,
+                          uint32_t n_line_segs, const uint8_t* values, int n_features, int width, int height, int background,
+                          uint32_t max_ints, int32_t* owner_ws, int32_t* ints_ws, uint8_t* out, b2_stream stream);
+
 #ifdef __cplusplus
 }
 #endif
