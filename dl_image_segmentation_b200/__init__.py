@@ -5,8 +5,8 @@ arithmetic runs in hand-written sm_100a CUDA behind the C ABI of ``libb2chips.so
 (``include/b2chips.h``).  Importing this package does not need a GPU; calling anything does, and raises
 if the library or the device is missing — there is no CPU fallback.
 """
-from ._descartes_img_chips import (MaskedResult, SceneStack, SyntheticSceneSource, create_cloudmasked_s2_array,  # noqa: F401
-                                   create_img_array_for_tile, create_label_array_for_tile, median_composite,
+from ._descartes_img_chips import (DLTileJobConfig, MaskedResult, SceneStack, SyntheticSceneSource, create_cloudmasked_s2_array,  # noqa: F401
+                                   create_chips_for_tile, create_img_array_for_tile, create_label_array_for_tile, median_composite,
                                    nearest_date_mosaic, read_geojson_layer, stack_products_for_tile)
 from ._tfrecord_image_translation import (convert_to_example, featuretemplate_bytestring_imagechip,  # noqa: F401
                                           featuretemplate_ndarray_imagechip, parse_8bit_array_proto,

@@ -269,3 +269,63 @@ def create_label_array_for_tile(ctx, label_data, attrib_to_burn=None, layer_idx=
             px.append(np.stack([inv0 + r[:, 0] * inv1, inv3 + r[:, 1] * inv5], axis=1))
         feats.append((px, value))
     return ops.rasterize_polygons(feats, size, background_value, all_touched=True, device=device)
+
+
+# ------------------------------------------------------------------------------------------------ one training sample
+class DLTileJobConfig:
+    """What one sample needs (reference :12-102, same attribute names): the tile, the output folder, product(s), dates,
+    cloud limit, label data and burn attribute, bands, label nodata value."""
+
+    def __init__(self, dltile, out_folder_base, dl_product, ref_date, labels_data, min_date=None, max_date=None,
+                 max_cloud_fraction=None, label_attr=None, label_lyr_num=0, bands="red green blue", label_nodata_value=255):
+        self.DLTILE = dltile
+        self.OUTFOLDER = out_folder_base
+        self.PRODUCT = dl_product
+        self.TARGETDATE = ref_date
+        self.MIN_DATE = min_date
+        self.MAX_DATE = max_date
+        self.MAX_CLOUD_FRACTION = max_cloud_fraction
+        self.LABEL_DS = labels_data
+        self.LABEL_BURN_ATTR = label_attr
+        self.LABEL_LYR_NUM = label_lyr_num
+        self.BANDS = bands
+        self.LABEL_NODATA_VALUE = label_nodata_value
+
+
+def _tile_epsg(dltile):
+    e = getattr(dltile, "epsg", None)
+    if e is None:
+        crs = str(getattr(dltile, "crs", "") or "")
+        e = int(crs.split(":")[1]) if crs.upper().startswith("EPSG:") else 0
+    return int(e)
+
+
+def create_chips_for_tile(job_details, scene_source=None, device=None):
+    """Image chip + label chip for one tile job (reference :693-800): pick the compositor as the reference does (:756-770 —
+    a list of products -> stack_products_for_tile; max_cloud_fraction == 0 on "sentinel-2:L1C" -> the cloud-masked median;
+    anything else -> the nearest-date mosaic), rasterise the labels, write both as tiled LZW GeoTIFFs named after the tile
+    key with ':' -> '#' (:749, :778-797), the label with its nodata value.  Returns (job_details, image path, label path),
+    or (job_details, None, None) when no image could be made (:772-773)."""
+    from . import _geotiff
+    dltile = job_details.DLTILE
+    product, bands = job_details.PRODUCT, job_details.BANDS
+    if isinstance(product, list):
+        assert isinstance(bands, list)                                                    # reference :757
+        img = stack_products_for_tile(ctx=dltile, products=product, bands_per_product=bands, scene_source=scene_source)
+    elif job_details.MAX_CLOUD_FRACTION == 0 and product == "sentinel-2:L1C":
+        img = create_cloudmasked_s2_array(ctx=dltile, min_date=job_details.MIN_DATE, max_date=job_details.MAX_DATE, bands=bands,
+                                          scene_source=scene_source)
+    else:
+        img = create_img_array_for_tile(ctx=dltile, product=product, reference_date=job_details.TARGETDATE,
+                                        min_date=job_details.MIN_DATE, max_date=job_details.MAX_DATE,
+                                        max_cloud_fraction=job_details.MAX_CLOUD_FRACTION, bands=bands, scene_source=scene_source)
+    if img is None:
+        return (job_details, None, None)
+    img_arr = img.data if isinstance(img, MaskedResult) else img      # GDAL writes the masked array's data as it is
+    lbl_arr = create_label_array_for_tile(ctx=dltile, label_data=job_details.LABEL_DS, attrib_to_burn=job_details.LABEL_BURN_ATTR,
+                                          layer_idx=job_details.LABEL_LYR_NUM, background_value=job_details.LABEL_NODATA_VALUE,
+                                          device=device)
+    img_file, lbl_file = _geotiff.write_chip_pair(img_arr, lbl_arr, job_details.OUTFOLDER, dltile.key,
+                                                  label_ndv=job_details.LABEL_NODATA_VALUE, geotransform=tuple(dltile.geotrans),
+                                                  epsg=_tile_epsg(dltile), device=device)
+    return (job_details, img_file, lbl_file)

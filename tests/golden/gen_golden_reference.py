@@ -191,6 +191,69 @@ def ref_stack_products(products):
     return np.asarray(np.ma.filled(res, 0))
 
 
+# ------------------------------------------------------------------------------------------------ create_chips_for_tile
+class Tile:
+    """What create_chips_for_tile reads of a DLTile."""
+
+    def __init__(self, key="12:2:10.0:43:7:11", tilesize=12, pad=2, geotrans=(499680.0, 10.0, 0.0, 5300360.0, 0.0, -10.0)):
+        self.key, self.tilesize, self.pad, self.geotrans = key, tilesize, pad, geotrans
+        self.wkt, self.crs, self.epsg = 'PROJCS["WGS 84 / UTM zone 43N"]', "EPSG:32643", 32643
+
+
+def label_layer(rng, tile, n=5):
+    """Random polygons (some with holes) in the tile's map coordinates with a `cls` attribute."""
+    S = tile.tilesize + 2 * tile.pad
+    gt = tile.geotrans
+    layer = []
+    for f in range(n):
+        k = int(rng.integers(3, 8))
+        ang = np.sort(rng.random(k)) * 2 * np.pi
+        rad = rng.uniform(0.1 * S, 0.4 * S, k)
+        c = rng.uniform(0, S, 2)
+        ring = np.stack([c[0] + rad * np.cos(ang), c[1] + rad * np.sin(ang)], 1)
+        ring = np.vstack([ring, ring[:1]])
+        rings = [ring] + ([(c + (ring - c) * 0.4)[::-1].copy()] if f % 2 == 0 else [])
+        layer.append(([np.stack([gt[0] + r[:, 0] * gt[1], gt[3] + r[:, 1] * gt[5]], 1) for r in rings], {"cls": int(rng.integers(0, 9))}))
+    return layer
+
+
+def ref_create_chips(job_kind, tile, out_dir, layer, scenes, label_attr="cls", label_ndv=255):
+    """Run the reference's create_chips_for_tile (:693-800) with the recording GDAL stub.  scenes: what load_catalog takes
+    per product.  -> (returned paths, {path: recorded dataset}).  gdal.RasterizeLayer is served by oracle/rasterize.py (GDAL
+    itself cannot be had here: that arithmetic stays unpinned), everything else is the reference's own code."""
+    from oracle import rasterize as orr
+    ref = refrun.load()
+    chips = refrun.submodule("_descartes_img_chips")
+    dl, gdal, ogr = refrun.stub("descarteslabs"), sys.modules["osgeo.gdal"], sys.modules["osgeo.ogr"]
+    dl.catalog.clear()
+    for product, (bands, dates, cf, stack, nodata, cloud_product, cloudfree) in scenes.items():
+        load_catalog(product, dates, cf, stack, nodata, bands.split(" "), cloud_product, cloudfree)
+    ogr.datasets["labels.geojson"] = [layer]
+    gdal.created.clear()
+
+    def hook(ds, bands, lyr, burn_values, options):
+        assert bands == [1] and "ALL_TOUCHED=TRUE" in options
+        attr = [o.split("=")[1] for o in options if o.startswith("ATTRIBUTE=")]
+        feats = [([orr.to_pixel_space(r, ds.geotransform) for r in rings], int(a[attr[0]]) if attr else int(burn_values[0])) for rings, a in lyr]
+        burnt = orr.rasterize(feats, (ds.ysize, ds.xsize), 0)
+        touched = orr.rasterize([(f[0], 1) for f in feats], (ds.ysize, ds.xsize), 0) == 1
+        ds.data[0][touched] = burnt[touched]
+    gdal.rasterize_hook = hook
+    products = list(scenes)
+    if job_kind == "stack":
+        job = chips.DLTileJobConfig(tile, out_dir, products, dt.date(2020, 3, 1), "labels.geojson", label_attr=label_attr,
+                                    bands=[scenes[p][0] for p in products], label_nodata_value=label_ndv)
+    elif job_kind == "median":
+        job = chips.DLTileJobConfig(tile, out_dir, "sentinel-2:L1C", dt.date(2020, 3, 1), "labels.geojson", max_cloud_fraction=0,
+                                    label_attr=label_attr, bands=scenes["sentinel-2:L1C"][0], label_nodata_value=label_ndv)
+    else:
+        job = chips.DLTileJobConfig(tile, out_dir, products[0], dt.date(2020, 3, 1), "labels.geojson", max_cloud_fraction=0.6,
+                                    min_date=dt.date(2020, 1, 10), label_attr=None, bands=scenes[products[0]][0],
+                                    label_nodata_value=label_ndv)
+    _, img_file, lbl_file = ref.create_chips_for_tile(job)
+    return (img_file, lbl_file), dict(gdal.created)
+
+
 # ------------------------------------------------------------------------------------------------ main
 def _copy_shards(src, dst):
     os.makedirs(dst, exist_ok=True)
@@ -302,6 +365,36 @@ def main():
     comp["dstack_u16_i16"] = ref_stack_products([prods[0], prods[2]])
     meta["dstack_dtypes"] = {k: str(comp[k].dtype) for k in ("dstack_all", "dstack_u16_u8", "dstack_u16_i16")}
     np.savez_compressed(os.path.join(HERE, "ref_composites.npz"), **comp)
+    # ---- F: create_chips_for_tile (dispatch, file names, band-by-band writes, dtypes, nodata) with the recording GDAL stub
+    rng = np.random.default_rng(7300)
+    tile = Tile()
+    chipfix = {}
+    layer = label_layer(rng, tile)
+    for k, (rings, attrs) in enumerate(layer):
+        for j, r in enumerate(rings):
+            chipfix["layer_%d_%d" % (k, j)] = r
+    meta["chips_layer_cls"] = [a["cls"] for _, a in layer]
+    meta["chips_layer_rings"] = [len(r) for r, _ in layer]
+    S = tile.tilesize + 2 * tile.pad
+    d1, cf1, st1, nd1, cfree1 = make_catalog(rng, T=5, H=S, W=S)
+    d2, cf2, st2, nd2, _ = make_catalog(rng, T=3, H=S, W=S, bands=["class"], dtype=np.uint8, tie_days=False)
+    chipfix.update(s2_stack=st1, s2_nodata=nd1, s2_cloudfree=cfree1, s2_cf=cf1, cls_stack=st2, cls_nodata=nd2, cls_cf=cf2)
+    meta["chips_s2_dates"], meta["chips_cls_dates"] = [d.isoformat() for d in d1], [d.isoformat() for d in d2]
+    jobs = {"median": {"sentinel-2:L1C": ("red green blue", d1, cf1, st1, nd1, "sentinel-2:L1C:dlcloud:v1", cfree1)},
+            "mosaic": {"airbus:oneatlas:spot:v2": ("red green blue", d1, cf1, st1, nd1, None, None)},
+            "stack": {"airbus:oneatlas:spot:v2": ("red green blue", d1, cf1, st1, nd1, None, None),
+                      "modelout:classes": ("class", d2, cf2, st2, nd2, None, None)}}
+    meta["chips_jobs"] = {}
+    for kind, scenes in jobs.items():
+        (img_file, lbl_file), created = ref_create_chips(kind, tile, os.path.join(tmp, "chips_" + kind), layer, scenes)
+        rec = {}
+        for role, path in (("img", img_file), ("lbl", lbl_file)):
+            ds = created[path]
+            chipfix["%s_%s" % (kind, role)] = np.transpose(ds.data, (1, 2, 0))
+            rec[role] = dict(file=os.path.relpath(path, os.path.join(tmp, "chips_" + kind)), gdal_type=ds.gdt, options=ds.options,
+                             nodata=ds.nodata, geotransform=list(ds.geotransform), driver=ds.driver)
+        meta["chips_jobs"][kind] = rec
+    np.savez_compressed(os.path.join(HERE, "ref_chips_for_tile.npz"), **chipfix)
     json.dump(meta, open(os.path.join(HERE, "ref_meta.json"), "w"), indent=1, sort_keys=True)
     shutil.rmtree(tmp, ignore_errors=True)
     print("wrote reference-run fixtures:", ", ".join(sorted(k for k in meta if k.startswith("ref_"))))

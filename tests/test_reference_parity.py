@@ -372,3 +372,96 @@ def test_gpu_compositors_reproduce_reference_outputs(dev):
         assert str(got.dtype) == META["dstack_dtypes"][tag] and np.array_equal(got, COMP[tag]), tag
     with pytest.raises(ValueError):                                   # a product without scenes: mosaic() of an empty collection
         pkg.stack_products_for_tile(ctx, ["prod0", "nothing:here"], ["red green blue", "x"], scene_source=src)
+
+
+# ================================================================================================ create_chips_for_tile
+CHIPS = np.load(os.path.join(GOLD, "ref_chips_for_tile.npz"))
+GDAL_NP = {1: np.uint8, 2: np.uint16, 3: np.int16, 4: np.uint32, 5: np.int32, 6: np.float32, 7: np.float64}
+
+
+def _chips_layer():
+    return [([CHIPS["layer_%d_%d" % (k, j)] for j in range(nr)], {"cls": c})
+            for k, (nr, c) in enumerate(zip(META["chips_layer_rings"], META["chips_layer_cls"]))]
+
+
+def _chips_dates(which):
+    return [dt.date.fromisoformat(s) for s in META["chips_%s_dates" % which]]
+
+
+def test_oracle_pieces_reproduce_the_reference_create_chips_for_tile():
+    """The arrays the unmodified reference handed to GDAL band by band (recording stub) for its three dispatch modes."""
+    from oracle import rasterize as orr
+    gt = META["chips_jobs"]["median"]["img"]["geotransform"]
+    layer = _chips_layer()
+    st, nd, cfree, cf = CHIPS["s2_stack"], CHIPS["s2_nodata"], CHIPS["s2_cloudfree"], CHIPS["s2_cf"]
+    dates = _chips_dates("s2")
+    med = ocomp.create_cloudmasked_s2_array(dates, st, cfree, np.repeat(nd[..., None], 3, -1))
+    assert CHIPS["median_img"].dtype == np.float64 and np.array_equal(np.asarray(med.data), CHIPS["median_img"])
+    days = [d.toordinal() for d in dates]
+    mos = ocomp.nearest_date_mosaic(st, (~nd).astype(np.uint8), days, cf, dt.date(2020, 3, 1).toordinal(),
+                                    dt.date(2020, 1, 10).toordinal(), None, 0.6)[0]
+    assert np.array_equal(mos, CHIPS["mosaic_img"]) and CHIPS["mosaic_img"].dtype == np.uint16
+    a = ocomp.nearest_date_mosaic(st, (~nd).astype(np.uint8), [0] * len(days), [0.0] * len(days), 0)[0]
+    cst, cnd = CHIPS["cls_stack"], CHIPS["cls_nodata"]
+    b = ocomp.nearest_date_mosaic(cst, (~cnd).astype(np.uint8), [0] * len(cst), [0.0] * len(cst), 0)[0]
+    assert np.array_equal(ocomp.stack_products([a, b]), CHIPS["stack_img"])
+    for kind, attr in (("median", "cls"), ("stack", "cls"), ("mosaic", None)):
+        lab = orr.create_label_array_for_tile(12, 2, gt, layer, attr, 255)
+        assert np.array_equal(lab, CHIPS[kind + "_lbl"][..., 0]), kind
+        rec = META["chips_jobs"][kind]
+        assert rec["lbl"]["nodata"] == [255] and rec["lbl"]["gdal_type"] == 1 and rec["img"]["file"] == "images/12#2#10.0#43#7#11.tif"
+        assert rec["img"]["options"] == ["COMPRESS=LZW", "TILED=TRUE", "NUM_THREADS=4"]
+
+
+@needs_reference
+def test_committed_chip_fixtures_are_what_the_reference_writes(tmp_path):
+    g = _gen()
+    tile = g.Tile()
+    scenes = {"median": {"sentinel-2:L1C": ("red green blue", _chips_dates("s2"), CHIPS["s2_cf"], CHIPS["s2_stack"], CHIPS["s2_nodata"],
+                                            "sentinel-2:L1C:dlcloud:v1", CHIPS["s2_cloudfree"])}}
+    (img_file, lbl_file), created = g.ref_create_chips("median", tile, str(tmp_path), _chips_layer(), scenes["median"])
+    assert np.array_equal(np.transpose(created[img_file].data, (1, 2, 0)), CHIPS["median_img"])
+    assert np.array_equal(created[lbl_file].data[0], CHIPS["median_lbl"][..., 0])
+
+
+@pytest.mark.gpu
+def test_gpu_create_chips_for_tile_reproduces_the_reference(dev, tmp_path):
+    """Drop-in create_chips_for_tile in the reference's three dispatch modes: the GeoTIFFs it writes hold exactly the arrays
+    the reference handed to GDAL (dtype per `_numpy_dtype_to_gdal`, tiled LZW, label nodata tag, geotransform, file names)."""
+    import dl_image_segmentation_b200 as pkg
+    from dl_image_segmentation_b200 import _descartes_img_chips as dc
+    from oracle import imagecodecs as oic
+
+    class Tile:
+        key, tilesize, pad, epsg = "12:2:10.0:43:7:11", 12, 2, 32643
+        geotrans = tuple(META["chips_jobs"]["median"]["img"]["geotransform"])
+    src = dc.SyntheticSceneSource()
+    st, nd, cfree, cf = CHIPS["s2_stack"], CHIPS["s2_nodata"], CHIPS["s2_cloudfree"], CHIPS["s2_cf"]
+    dates = _chips_dates("s2")
+    src.add(Tile, "sentinel-2:L1C", dc.SceneStack(st, cfree, dates, cf, nodata_mask=np.repeat(nd[..., None], 3, -1).astype(np.uint8)))
+    src.add(Tile, "airbus:oneatlas:spot:v2", dc.SceneStack(st, (~nd).astype(np.uint8), dates, cf))
+    src.add(Tile, "modelout:classes", dc.SceneStack(CHIPS["cls_stack"], (~CHIPS["cls_nodata"]).astype(np.uint8), _chips_dates("cls"), CHIPS["cls_cf"]))
+    layer = _chips_layer()
+    jobs = {"median": pkg.DLTileJobConfig(Tile, str(tmp_path / "median"), "sentinel-2:L1C", dt.date(2020, 3, 1), layer, max_cloud_fraction=0,
+                                          label_attr="cls"),
+            "mosaic": pkg.DLTileJobConfig(Tile, str(tmp_path / "mosaic"), "airbus:oneatlas:spot:v2", dt.date(2020, 3, 1), layer,
+                                          max_cloud_fraction=0.6, min_date=dt.date(2020, 1, 10), label_attr=None),
+            "stack": pkg.DLTileJobConfig(Tile, str(tmp_path / "stack"), ["airbus:oneatlas:spot:v2", "modelout:classes"], dt.date(2020, 3, 1),
+                                         layer, label_attr="cls", bands=["red green blue", "class"])}
+    for kind, job in jobs.items():
+        ret, img_file, lbl_file = pkg.create_chips_for_tile(job, scene_source=src)
+        rec = META["chips_jobs"][kind]
+        assert ret is job and os.path.relpath(img_file, job.OUTFOLDER) == rec["img"]["file"]
+        assert os.path.relpath(lbl_file, job.OUTFOLDER) == rec["lbl"]["file"]
+        for role, path in (("img", img_file), ("lbl", lbl_file)):
+            blob = open(path, "rb").read()
+            got = oic.decode_image(blob, png_as_tf=False)
+            want = CHIPS["%s_%s" % (kind, role)]
+            assert got.dtype == GDAL_NP[rec[role]["gdal_type"]] == want.dtype and np.array_equal(got, want), (kind, role)
+            t = oic.parse_tiff(blob)
+            assert t["compression"] == 5 and t["tiled"]
+            assert oic.georef_strings(blob) == (str([float(v) for v in rec[role]["geotransform"]]), "EPSG:32643")
+            assert t.get("nodata") == (None if rec[role]["nodata"][0] is None else str(rec[role]["nodata"][0]))
+    none_job = pkg.DLTileJobConfig(Tile, str(tmp_path / "none"), "airbus:oneatlas:spot:v2", dt.date(2020, 3, 1), layer,
+                                   max_cloud_fraction=0.0000001)
+    assert pkg.create_chips_for_tile(none_job, scene_source=src) == (none_job, None, None)      # reference :772-773
