@@ -23,7 +23,10 @@ _vp, _i = ctypes.c_void_p, ctypes.c_int
 _lib.register_signatures({
     "b2_lzw_encode": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "b2_tile_split": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "b2_gather_ranges": (_i, [_vp, _vp, _vp, _vp, _vp, _i, ctypes.c_uint32, _vp, _vp]),
 })
+
+_pinned = {}      # device index -> pinned host buffer the packed code streams land in (grown on demand)
 
 _SAMPLE_FORMAT = {"u": 1, "i": 2, "f": 3}
 _NP_OF_TORCH = {torch.uint8: np.uint8, torch.int8: np.int8, torch.int16: np.int16, torch.int32: np.int32,
@@ -52,9 +55,21 @@ def _encode_compact(raw, lengths, device=None):
     lens = out_len.cpu().numpy().view(np.uint32).astype(np.int64)          # small read-back; waits for the encoder
     if (lens == 0xFFFFFFFF).any():
         raise B2Error("b2_lzw_encode: output capacity exceeded")
-    # compact the code streams on the device (the capacity slots are 1.5x the raw size), then ONE copy to the host
-    packed = torch.cat([out[int(o):int(o) + int(l)] for o, l in zip(descs["dst_off"], lens)]) if n else out[:0]
-    return packed.cpu().numpy(), lens
+    # compact the code streams on the device (the capacity slots are 1.5x the raw size) with one gather launch, then ONE
+    # copy into pinned host memory
+    total = int(lens.sum())
+    dst_off = np.concatenate(([0], np.cumsum(lens)[:-1])).astype(np.uint64)
+    packed = torch.empty((max(total, 16),), dtype=torch.uint8, device=ctx.device)
+    so_d = torch.from_numpy(np.ascontiguousarray(descs["dst_off"])).to(ctx.device)
+    do_d = torch.from_numpy(dst_off).to(ctx.device)
+    check(lib().b2_gather_ranges(ctx.handle, ptr(out), ptr(so_d), ptr(do_d), ptr(out_len), n, int(lens.max()) if n else 0, ptr(packed),
+                                 ctx.stream()))
+    host = _pinned.get(ctx.device.index)
+    if host is None or host.numel() < total:
+        host = _pinned[ctx.device.index] = torch.empty((int(total * 1.25) + 4096,), dtype=torch.uint8).pin_memory()
+    host[:total].copy_(packed[:total], non_blocking=True)
+    torch.cuda.current_stream(ctx.device).synchronize()
+    return host[:total].numpy(), lens
 
 
 def lzw_encode_tiles(raw, lengths, device=None):
@@ -126,14 +141,17 @@ def _ifd(width, height, bands, np_dtype, tile, block_lens, block_data, nodata, g
         field = struct.pack("<I", extra_off + where[t]) if t in where else val.ljust(4, b"\0")
         out += struct.pack("<HHI", t, typ, cnt) + field
     out += struct.pack("<I", 0) + tail
+    if block_data is None:
+        return bytes(out)                                                   # the caller writes the tile data after it
     return b"".join((bytes(out), block_data))
 
 
 def encode_geotiffs(arrays, nodata=None, geotransform=(499980.0, 10.0, 0.0, 5300040.0, 0.0, -10.0), epsg=32643, tile=256,
-                    device=None):
+                    device=None, as_parts=False):
     """A batch of (H,W,bands) / (H,W) rasters (CUDA tensors or numpy arrays, any TIFF sample type) -> list of GeoTIFF
     file bytes.  nodata: one value for all, or a list (None entries = no GDAL_NODATA tag).  All tiles of the batch are
-    compressed in ONE b2_lzw_encode launch."""
+    compressed in ONE b2_lzw_encode launch.  as_parts: return (header bytes, tile data view) per file instead of joined
+    bytes (the views point into a pinned buffer that the next call reuses): write_geotiffs writes them without a copy."""
     ctx = get_ctx(device)
     n = len(arrays)
     nod = list(nodata) if isinstance(nodata, (list, tuple)) else [nodata] * n
@@ -162,10 +180,34 @@ def encode_geotiffs(arrays, nodata=None, geotransform=(499980.0, 10.0, 0.0, 5300
     files, k, pos = [], 0, 0
     for (W, H, B, dt, nb), nd in zip(metas, nod):
         size = int(lens[k:k + nb].sum())
-        files.append(_ifd(W, H, B, dt, tile, lens[k:k + nb], mv[pos:pos + size], nd, geotransform, epsg))
+        if as_parts:
+            files.append((_ifd(W, H, B, dt, tile, lens[k:k + nb], None, nd, geotransform, epsg), mv[pos:pos + size]))
+        else:
+            files.append(_ifd(W, H, B, dt, tile, lens[k:k + nb], mv[pos:pos + size], nd, geotransform, epsg))
         k += nb
         pos += size
     return files
+
+
+def write_geotiffs(arrays, paths, nodata=None, geotransform=(499980.0, 10.0, 0.0, 5300040.0, 0.0, -10.0), epsg=32643, tile=256,
+                   device=None, io_threads=16):
+    """Encode a batch of rasters and write each to its path (the save step of create_chips_for_tile for many tiles at
+    once): one encode launch, one packed device -> pinned host copy, then header + tile data of every file written by a
+    pool of threads straight from the pinned buffer.  Returns the paths."""
+    from concurrent.futures import ThreadPoolExecutor
+    parts = encode_geotiffs(arrays, nodata=nodata, geotransform=geotransform, epsg=epsg, tile=tile, device=device, as_parts=True)
+
+    def write(job):
+        path, (head, data) = job
+        fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+        try:
+            os.write(fd, head)
+            os.write(fd, data)
+        finally:
+            os.close(fd)
+    with ThreadPoolExecutor(max_workers=max(1, io_threads)) as pool:
+        list(pool.map(write, zip(paths, parts)))
+    return list(paths)
 
 
 def write_chip_pair(img_arr, lbl_arr, out_base, dltile_key, label_ndv=None, geotransform=(499980.0, 10.0, 0.0, 5300040.0, 0.0, -10.0),

@@ -191,9 +191,51 @@ tile_split_kernel(const uint8_t* __restrict__ img, int H, int W, int pb, int tw,
     }
 }
 
+// n byte ranges of one device buffer -> back to back (dst_off[i]) in another: the code streams of a batch leave their
+// capacity-sized slots for one dense buffer, which then crosses to the host in a single copy.
+__global__ void __launch_bounds__(256)
+gather_ranges_kernel(const uint8_t* __restrict__ src, const uint64_t* __restrict__ src_off, const uint64_t* __restrict__ dst_off,
+                     const uint32_t* __restrict__ len, int n, uint8_t* __restrict__ dst) {
+    for (int r = blockIdx.y; r < n; r += gridDim.y) {
+        const uint8_t* s = src + src_off[r];
+        uint8_t* d = dst + dst_off[r];
+        const uint32_t ln = len[r];
+        // 16-byte loads (the slots are 16-byte aligned), byte stores only at the ragged edges of the destination
+        const uint32_t head = min(ln, (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(d) & 15u)) & 15u));
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < head; i += gridDim.x * blockDim.x) d[i] = s[i];
+        const uint32_t vecs = (ln - head) >> 4;
+        for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < vecs; v += gridDim.x * blockDim.x) {
+            const uint8_t* p = s + head + 16u * v;                  // source side unaligned in general: four 32-bit pieces
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint8_t* q = p + 4 * k;
+                w[k] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+            }
+            *reinterpret_cast<uint4*>(d + head + 16u * v) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        for (uint32_t i = head + (vecs << 4) + blockIdx.x * blockDim.x + threadIdx.x; i < ln; i += gridDim.x * blockDim.x) d[i] = s[i];
+    }
+}
+
 }  // namespace b2
 
 using namespace b2;
+
+extern "C" int b2_gather_ranges(b2_ctx* ctx, const uint8_t* src, const uint64_t* src_off, const uint64_t* dst_off,
+                                const uint32_t* len, int n, uint32_t max_len, uint8_t* dst, b2_stream stream) {
+    B2_REQUIRE(ctx && src && src_off && dst_off && len && dst, "b2_gather_ranges: NULL argument");
+    if (n <= 0) return 0;
+    DeviceGuard g(ctx->device);
+    unsigned gx = (max_len + 256 * 64 - 1) / (256 * 64);
+    if (gx < 1) gx = 1;
+    if (gx > 64) gx = 64;
+    const unsigned gy = (unsigned)(n < 65535 ? n : 65535);
+    gather_ranges_kernel<<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, src_off, dst_off, len, n, dst);
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int b2_lzw_encode(b2_ctx* ctx, const uint8_t* raw, const b2_enc_desc* descs, int n, uint8_t* out,
                              uint32_t* out_len, b2_stream stream) {

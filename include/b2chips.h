@@ -406,6 +406,11 @@ int b2_jpeg_encode_scan(b2_ctx* ctx, const uint8_t* pixels_dev, const b2_jpeg_en
                         const b2_jpeg_enc_job* jobs_host, int n, int quality, int16_t* coef_dev, uint64_t coef_count,
                         uint8_t* out_dev, uint32_t* out_len_dev, b2_stream stream);
 
+/* n byte ranges src[src_off[i] .. +len[i]) -> dst[dst_off[i] ..): the GeoTIFF writer packs the code streams of a batch
+ * (each in a capacity-sized slot) into one dense buffer on the device before the single copy to the host.  All device. */
+int b2_gather_ranges(b2_ctx* ctx, const uint8_t* src, const uint64_t* src_off, const uint64_t* dst_off, const uint32_t* len,
+                     int n, uint32_t max_len, uint8_t* dst, b2_stream stream);
+
 /* ------------------------------------------------------------------ label rasterisation
  * Replaces gdal.RasterizeLayer(mem_ds, [1], layer, options=['ALL_TOUCHED=TRUE'[, 'ATTRIBUTE=...']]) over a raster filled with
  * background_value, create_label_array_for_tile (_descartes_img_chips.py:633-689): polygons (any number of rings each:
