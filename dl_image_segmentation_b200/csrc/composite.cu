@@ -383,6 +383,204 @@ mosaic_kernel(const void* const* __restrict__ stacks, const uint8_t* const* __re
     }
 }
 
+// The same selection for 8-byte pixels (4 bands of uint16: BASELINE configs[4]) with FOUR ADJACENT pixels per thread and
+// two such groups in flight: one 32-bit load brings the validity of a group for one scene (a warp covers 128 contiguous
+// bytes instead of 32), the four pixels leave as two 16-byte stores, their mask as one 32-bit store.  The per-thread
+// statistics are 32-bit sums folded into 64 bits once per chip (a thread sees at most hw / 256 pixels of 16 bits).
+constexpr int kStatSlots = 256;
+
+template <int kStats>   // 0: no statistics; 2: exact integer band statistics of uint16 pixels
+__global__ void __launch_bounds__(256, kStats ? 4 : 2)   // the statistics variant must stay within 64 registers: 4 CTAs / SM
+mosaic_vec8_kernel(const void* const* __restrict__ stacks, const uint8_t* const* __restrict__ valids,
+                   const int32_t* __restrict__ scene_day, const float* __restrict__ scene_cf, int32_t ref_day, int32_t min_day,
+                   int32_t max_day, float max_cf, int T, uint32_t hw, uint8_t* __restrict__ out, uint8_t* __restrict__ out_mask,
+                   int16_t* __restrict__ src_index, int32_t* __restrict__ n_eligible, unsigned long long* __restrict__ stats) {
+    extern __shared__ int32_t sm[];  // key[T], order[T]
+    int32_t* key = sm;
+    int32_t* order = sm + T;
+    __shared__ int32_t n_el;
+    const int chip = blockIdx.y;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const int32_t d = scene_day[(size_t)chip * T + t];
+        const float cf = scene_cf[(size_t)chip * T + t];
+        bool ok = d >= min_day && d < max_day;
+        if (!isnan(max_cf)) ok = ok && (cf < max_cf);
+        const int64_t diff = (int64_t)d - (int64_t)ref_day;
+        const int64_t ad = diff < 0 ? -diff : diff;
+        key[t] = ok ? (int32_t)(ad > 0x7FFFFFFE ? 0x7FFFFFFE : ad) : -1;
+    }
+    if (threadIdx.x == 0) n_el = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const int32_t k = key[t];
+        if (k >= 0) {
+            int r = 0;
+            for (int u = 0; u < T; u++) {
+                const int32_t ku = key[u];
+                r += (ku >= 0) && (ku < k || (ku == k && u > t));
+            }
+            order[r] = t;
+            atomicAdd(&n_el, 1);
+        }
+    }
+    __syncthreads();
+    const int ne = n_el;
+    if (n_eligible && blockIdx.x == 0 && threadIdx.x == 0) n_eligible[chip] = ne;
+    const uint8_t* vchip = valids[chip];
+    const uint2* schip = static_cast<const uint2*>(stacks[chip]);
+    const bool v4 = (reinterpret_cast<uintptr_t>(vchip) & 3u) == 0;    // validity planes readable as 32-bit words
+    uint32_t st_n = 0, st_s[4] = {0, 0, 0, 0};
+    unsigned long long st_q[4] = {0, 0, 0, 0};
+    constexpr int kG = 2;                                              // groups of 4 pixels in flight per thread
+    const uint32_t groups = hw >> 2, stride = gridDim.x * blockDim.x;
+    // validity word of one group for scene t
+    auto vload = [&](int t, uint32_t g) -> uint32_t {
+        const uint8_t* a = vchip + (size_t)t * hw + 4u * g;
+        return v4 ? __ldg(reinterpret_cast<const uint32_t*>(a))
+                  : ((uint32_t)__ldg(a) | ((uint32_t)__ldg(a + 1) << 8) | ((uint32_t)__ldg(a + 2) << 16) | ((uint32_t)__ldg(a + 3) << 24));
+    };
+    // the probes of the best scene for the NEXT round of groups are requested before this round's statistics are worked
+    // out, so that the arithmetic hides behind them instead of delaying them
+    uint32_t vfirst[kG];
+#pragma unroll
+    for (int u = 0; u < kG; u++) {
+        const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x + u * stride;
+        vfirst[u] = (ne > 0 && g < groups) ? vload(order[0], g) : 0u;
+    }
+    for (uint32_t g0 = blockIdx.x * blockDim.x + threadIdx.x; g0 < groups; g0 += kG * stride) {
+        int sel[kG][4];
+        uint32_t open[kG];                                             // bit j: pixel j of the group still unresolved
+#pragma unroll
+        for (int u = 0; u < kG; u++) {
+            open[u] = (g0 + u * stride < groups) ? 0xFu : 0u;
+#pragma unroll
+            for (int j = 0; j < 4; j++) sel[u][j] = -1;
+        }
+        for (int k = 0; k < ne; k++) {
+            uint32_t any_open = 0;
+#pragma unroll
+            for (int u = 0; u < kG; u++) any_open |= open[u];
+            if (!any_open) break;
+            const int t = order[k];
+            uint32_t v[kG];
+#pragma unroll
+            for (int u = 0; u < kG; u++) {
+                v[u] = 0;
+                if (open[u]) v[u] = k == 0 ? vfirst[u] : vload(t, g0 + u * stride);
+            }
+#pragma unroll
+            for (int u = 0; u < kG; u++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (((open[u] >> j) & 1u) && ((v[u] >> (8 * j)) & 0xFFu)) {
+                        sel[u][j] = t;
+                        open[u] &= ~(1u << j);
+                    }
+        }
+        uint2 w[kG][4];
+#pragma unroll
+        for (int u = 0; u < kG; u++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                w[u][j] = make_uint2(0u, 0u);
+                if (g0 + u * stride < groups && sel[u][j] >= 0)
+                    w[u][j] = __ldg(schip + (size_t)sel[u][j] * hw + 4u * (g0 + u * stride) + j);
+            }
+#pragma unroll
+        for (int u = 0; u < kG; u++) {
+            const uint32_t gn = g0 + (kG + u) * stride;
+            vfirst[u] = (ne > 0 && gn < groups) ? vload(order[0], gn) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kG; u++) {
+            const uint32_t g = g0 + u * stride;
+            if (g >= groups) continue;
+            const size_t p = (size_t)chip * hw + 4u * g;
+            uint4* o = reinterpret_cast<uint4*>(out + p * 8);
+            o[0] = make_uint4(w[u][0].x, w[u][0].y, w[u][1].x, w[u][1].y);
+            o[1] = make_uint4(w[u][2].x, w[u][2].y, w[u][3].x, w[u][3].y);
+            uint32_t m = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) m |= (sel[u][j] < 0 ? 1u : 0u) << (8 * j);
+            *reinterpret_cast<uint32_t*>(out_mask + p) = m;
+            if (src_index) {
+                *reinterpret_cast<uint2*>(src_index + p) =
+                    make_uint2(((uint32_t)sel[u][0] & 0xFFFFu) | ((uint32_t)sel[u][1] << 16), ((uint32_t)sel[u][2] & 0xFFFFu) | ((uint32_t)sel[u][3] << 16));
+            }
+            if (kStats) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (sel[u][j] < 0) continue;
+                    st_n++;
+                    const uint32_t x0 = w[u][j].x & 0xFFFFu, x1 = w[u][j].x >> 16, x2 = w[u][j].y & 0xFFFFu, x3 = w[u][j].y >> 16;
+                    st_s[0] += x0; st_s[1] += x1; st_s[2] += x2; st_s[3] += x3;
+                    st_q[0] += x0 * x0; st_q[1] += x1 * x1; st_q[2] += x2 * x2; st_q[3] += x3 * x3;
+                }
+            }
+        }
+    }
+    if (kStats) {   // warp shuffle -> shared memory -> one 64-bit atomic per (CTA, band, counter)
+        __shared__ unsigned long long red[8][9];
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        unsigned long long nn = st_n;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+        if (lane == 0) red[wid][8] = nn;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            unsigned long long sv = st_s[b], qv = st_q[b];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                sv += __shfl_xor_sync(0xffffffffu, sv, o);
+                qv += __shfl_xor_sync(0xffffffffu, qv, o);
+            }
+            if (lane == 0) {
+                red[wid][b] = sv;
+                red[wid][4 + b] = qv;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            const int b = threadIdx.x;
+            unsigned long long n = 0, sv = 0, qv = 0;
+            for (int k = 0; k < 8; k++) {
+                n += red[k][8];
+                sv += red[k][b];
+                qv += red[k][4 + b];
+            }
+            if (n) {   // thousands of CTAs adding to the same 16 words serialise in L2: each chip adds to one of kStatSlots copies
+                unsigned long long* slot = stats + (size_t)(chip & (kStatSlots - 1)) * 12 + 3 * b;
+                atomicAdd(slot + 0, n);
+                atomicAdd(slot + 1, sv);
+                atomicAdd(slot + 2, qv);
+            }
+        }
+    }
+}
+
+// fold the slot copies into the caller's accumulators {n, sum x, sum x^2 & 0xFFFF, sum x^2 >> 16} per band
+__global__ void stats_fold_kernel(const unsigned long long* __restrict__ slots, unsigned long long* __restrict__ stats) {
+    const int b = threadIdx.x >> 5, lane = threadIdx.x & 31;       // one warp per band
+    unsigned long long n = 0, sv = 0, qv = 0;
+    for (int k = lane; k < kStatSlots; k += 32) {
+        n += slots[(size_t)k * 12 + 3 * b + 0];
+        sv += slots[(size_t)k * 12 + 3 * b + 1];
+        qv += slots[(size_t)k * 12 + 3 * b + 2];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        qv += __shfl_xor_sync(0xffffffffu, qv, o);
+    }
+    if (lane == 0 && n) {
+        atomicAdd(stats + 4 * b + 0, n);
+        atomicAdd(stats + 4 * b + 1, sv);
+        atomicAdd(stats + 4 * b + 2, qv & 0xFFFFull);
+        atomicAdd(stats + 4 * b + 3, qv >> 16);
+    }
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -439,6 +637,23 @@ extern "C" int b2_nearest_date_mosaic(b2_ctx* ctx, const void* const* stacks, co
     mosaic_kernel<PBV, EB><<<grid, 256, smem, s>>>(stacks, valids, scene_day, scene_cf, ref_day, min_day, max_day,  \
                                                    max_cf, T, hw, pb, static_cast<uint8_t*>(out), out_mask, src_index, \
                                                    n_eligible, reinterpret_cast<unsigned long long*>(stats_acc))
+    const bool vec8 = al && pb == 8 && (hw & 3u) == 0 && reinterpret_cast<uintptr_t>(out_mask) % 4 == 0 &&
+                      (!src_index || reinterpret_cast<uintptr_t>(src_index) % 8 == 0) && (!stats_acc || elem_bytes == 2) &&
+                      hw / 256 < 60000;                                // 32-bit per-thread sums of 16-bit values
+    if (vec8) {
+        if (stats_acc) {
+            const size_t slot_bytes = (size_t)kStatSlots * 12 * sizeof(unsigned long long);
+            if (int e = ws_reserve(ctx, slot_bytes, s)) return e;
+            B2_CUDA(cudaMemsetAsync(ctx->ws, 0, slot_bytes, s));
+            unsigned long long* slots = static_cast<unsigned long long*>(ctx->ws);
+            mosaic_vec8_kernel<2><<<grid, 256, smem, s>>>(stacks, valids, scene_day, scene_cf, ref_day, min_day, max_day, max_cf, T, hw,
+                                                          static_cast<uint8_t*>(out), out_mask, src_index, n_eligible, slots);
+            stats_fold_kernel<<<1, 128, 0, s>>>(slots, reinterpret_cast<unsigned long long*>(stats_acc));
+            ctx->launches++;
+        } else
+            mosaic_vec8_kernel<0><<<grid, 256, smem, s>>>(stacks, valids, scene_day, scene_cf, ref_day, min_day, max_day, max_cf, T, hw,
+                                                          static_cast<uint8_t*>(out), out_mask, src_index, n_eligible, nullptr);
+    } else
     if (stats_acc) {
         B2_REQUIRE(al && (elem_bytes == 1 || elem_bytes == 2) && B <= 4 && (pb == 2 || pb == 4 || pb == 8),
                    "b2_nearest_date_mosaic: fused statistics need uint8 / uint16 chips of at most 4 bands, 2-, 4- or "
