@@ -562,6 +562,17 @@ def translate_e2e(dev, rank, world, kind, store_as_array):
             k += 1
         res["byte_identical_with_cpu_restatement"] = bool(got[:len(want)] == want)
         res["records_compared"] = len(otfr.scan(want, verify=False)[0])
+        if world > 1:
+            # the other end of the partition too: the head of the LAST rank's first shard, record by record
+            imgs, lbls = opart.find_image_files(root, ext)
+            plan = opart.shard_plan(len(imgs), shards, world)
+            sh, lo, hi = plan[(world - 1) * cfg["shards_per_gpu"]]
+            k = min(32, hi - lo)
+            want2 = b"".join(otfr.frame(otr.build_record(imgs[i], lbls[i], True, store_as_array)) for i in range(lo, lo + k))
+            with open(os.path.join(out, opart.shard_name("bench", sh, shards)), "rb") as f:
+                got2 = f.read(len(want2))
+            res["last_rank_first_shard_head_identical"] = bool(got2 == want2)
+            res["records_compared"] += k
     if world > 1:
         dist.barrier()
     if rank == 0:

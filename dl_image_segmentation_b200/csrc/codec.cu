@@ -1535,6 +1535,7 @@ extern "C" int b2_decode_streams(b2_ctx* ctx, const uint8_t* blob, const b2_stre
         unsigned ctas = (unsigned)n_streams;
         const unsigned resident = (unsigned)(ctx->sm_count * per_sm);
         if (ctas > resident) ctas = resident;
+        WsLock ws_lock(ctx);
         if (int e = ws_reserve(ctx, 256, s)) return e;
         unsigned int* counter = reinterpret_cast<unsigned int*>(ctx->ws);
         B2_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));

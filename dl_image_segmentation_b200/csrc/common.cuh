@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include <string>
 
 #include "../../include/b2chips.h"
@@ -29,8 +30,12 @@ struct b2_ctx {
     b2::CrcTables* crc_dev;  // device copy
     b2::CrcTables* crc_host;
     unsigned long long* prof_dev;  // 8 phase counters (b2_debug_parse_phases)
-    void* ws;                // grow-on-demand workspace
+    void* ws;                // grow-on-demand workspace, shared by the entry points that need scratch (see WsLock)
     size_t ws_bytes;
+    std::mutex* ws_mutex;    // one workspace user at a time on the host ...
+    cudaStream_t ws_stream;  // ... and on the device: the stream of the last user,
+    cudaEvent_t ws_event;    //     which the next user's stream waits for when it is a different one
+    bool ws_used;
 };
 
 namespace b2 {
@@ -39,6 +44,14 @@ void set_error(const std::string& msg);
 int fail(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
 int ws_reserve(b2_ctx* ctx, size_t bytes, cudaStream_t s);
+
+// Entry points that use the context workspace hold this for their whole body: calls on one context from several host
+// threads take turns, and ws_reserve orders a call behind the previous user's work when that ran on another stream, so two
+// streams never have kernels in flight on the same scratch (the rule used to be a comment).
+struct WsLock {
+    std::lock_guard<std::mutex> g;
+    explicit WsLock(b2_ctx* ctx) : g(*ctx->ws_mutex) {}
+};
 
 #define B2_CUDA(expr)                                            \
     do {                                                         \

@@ -643,6 +643,7 @@ extern "C" int b2_nearest_date_mosaic(b2_ctx* ctx, const void* const* stacks, co
     if (vec8) {
         if (stats_acc) {
             const size_t slot_bytes = (size_t)kStatSlots * 12 * sizeof(unsigned long long);
+            WsLock ws_lock(ctx);
             if (int e = ws_reserve(ctx, slot_bytes, s)) return e;
             B2_CUDA(cudaMemsetAsync(ctx->ws, 0, slot_bytes, s));
             unsigned long long* slots = static_cast<unsigned long long*>(ctx->ws);

@@ -20,6 +20,12 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 int ws_reserve(b2_ctx* ctx, size_t bytes, cudaStream_t s) {
+    if (ctx->ws_used && ctx->ws_stream != s) {     // the previous user ran on another stream: wait for everything queued there
+        B2_CUDA(cudaEventRecord(ctx->ws_event, ctx->ws_stream));
+        B2_CUDA(cudaStreamWaitEvent(s, ctx->ws_event, 0));
+    }
+    ctx->ws_stream = s;
+    ctx->ws_used = true;
     if (bytes <= ctx->ws_bytes) return 0;
     // growing is rare (first calls only); stream-ordered so in-flight users of the old block finish first
     if (ctx->ws) B2_CUDA(cudaFreeAsync(ctx->ws, s));
@@ -110,6 +116,10 @@ int b2_ctx_create(int device, b2_ctx** out) {
     c->launches = 0;
     c->ws = nullptr;
     c->ws_bytes = 0;
+    c->ws_mutex = new std::mutex();
+    c->ws_stream = nullptr;
+    c->ws_used = false;
+    B2_CUDA(cudaEventCreateWithFlags(&c->ws_event, cudaEventDisableTiming));
     c->crc_host = new CrcTables();
     build_tables(c->crc_host);
     B2_CUDA(cudaMalloc(&c->crc_dev, sizeof(CrcTables)));
@@ -125,6 +135,8 @@ int b2_ctx_destroy(b2_ctx* ctx) {
     DeviceGuard g(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->ws) cudaFree(ctx->ws);
+    cudaEventDestroy(ctx->ws_event);
+    delete ctx->ws_mutex;
     if (ctx->crc_dev) cudaFree(ctx->crc_dev);
     if (ctx->prof_dev) cudaFree(ctx->prof_dev);
     delete ctx->crc_host;

@@ -247,6 +247,7 @@ extern "C" int b2_lzw_encode(b2_ctx* ctx, const uint8_t* raw, const b2_enc_desc*
     unsigned ctas = (unsigned)n;
     const unsigned resident = (unsigned)ctx->sm_count * 9;     // 25 KiB of shared memory per CTA
     if (ctas > resident) ctas = resident;
+    WsLock ws_lock(ctx);
     if (int e = ws_reserve(ctx, 256, s)) return e;
     unsigned int* counter = static_cast<unsigned int*>(ctx->ws);
     B2_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), s));

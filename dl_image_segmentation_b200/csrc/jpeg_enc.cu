@@ -526,6 +526,7 @@ extern "C" int b2_jpeg_encode_scan(b2_ctx* ctx, const uint8_t* pixels_dev, const
     const uint64_t n_blocks_all = coef_count / 64;
     const uint64_t bits_bytes = (n_blocks_all + (uint64_t)n) * sizeof(uint64_t);
     const uint64_t raw_bytes = ((out_end / 2 + 64) + 15) & ~15ull;
+    WsLock ws_lock(ctx);
     if (ws_reserve(ctx, bits_bytes + raw_bytes, s)) return 1;
     uint64_t* bits = static_cast<uint64_t*>(ctx->ws);
     uint64_t* total = bits + n_blocks_all;

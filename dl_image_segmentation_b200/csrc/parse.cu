@@ -761,6 +761,7 @@ extern "C" int b2_tfrecord_parse(b2_ctx* ctx, const uint8_t* shard, uint64_t nby
     if (!tx) tx = 1;
     B2_REQUIRE(tx * (uint64_t)n < (1ull << 32), "b2_tfrecord_parse: too many tiles for one call");
     // per-record accumulators live in the context workspace: calls on one context must be stream-ordered
+    WsLock ws_lock(ctx);
     if (int e = ws_reserve(ctx, (size_t)n * 8 + 8, s)) return e;
     B2_CUDA(cudaMemsetAsync(ctx->ws, 0, (size_t)n * 8 + 8, s));
     uint32_t* acc = static_cast<uint32_t*>(ctx->ws);
@@ -795,6 +796,7 @@ extern "C" int b2_crc32c(b2_ctx* ctx, const uint8_t* data, const uint64_t* offse
     uint64_t tx = (max_len + 15 + kTile - 1) / kTile;
     if (!tx) tx = 1;
     B2_REQUIRE(tx * (uint64_t)n < (1ull << 32), "b2_crc32c: too many tiles for one call");
+    WsLock ws_lock(ctx);
     if (int e = ws_reserve(ctx, (size_t)n * 8 + 8, s)) return e;
     B2_CUDA(cudaMemsetAsync(ctx->ws, 0, (size_t)n * 8 + 8, s));
     uint32_t* acc = static_cast<uint32_t*>(ctx->ws);

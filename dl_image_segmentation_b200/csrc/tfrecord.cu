@@ -769,6 +769,7 @@ extern "C" int b2_tfrecord_build(b2_ctx* ctx, const b2_build_desc* descs, int n,
     uint32_t tx = (uint32_t)((max_record_bytes + 15 + kTile - 1) / kTile);
     if (!tx) tx = 1;
     // per-record accumulators live in the context workspace: calls on one context must be stream-ordered
+    WsLock ws_lock(ctx);
     if (int e = ws_reserve(ctx, (size_t)n * sizeof(unsigned long long), s)) return e;
     B2_CUDA(cudaMemsetAsync(ctx->ws, 0, (size_t)n * sizeof(unsigned long long), s));
     BuildArgs ba{descs, scaffold, out, ctx->crc_dev, static_cast<unsigned long long*>(ctx->ws), tx, n};

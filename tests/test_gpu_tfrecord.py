@@ -547,3 +547,54 @@ def test_index_fuzz_against_oracle_parser(dev):
         else:
             assert np.array_equal(np.frombuffer(shard[o:o + l], "<f4"), np.asarray(f["image/image_data"][1], np.float32))
         assert shard[int(ix["id_off"]):int(ix["id_off"]) + int(ix["id_len"])] == key.encode("utf-8")
+
+
+@pytest.mark.gpu
+def test_context_workspace_is_safe_across_streams_and_host_threads(dev):
+    """b2_crc32c / b2_tfrecord_parse / b2_tfrecord_build share one per-context scratch.  Calls on different
+    streams, from different host threads, must not corrupt each other: each entry point holds the workspace lock for its
+    body and a call waits (on the device) for the previous user's stream."""
+    import threading
+
+    import torch
+
+    from dl_image_segmentation_b200 import ops
+    rng = np.random.default_rng(17)
+    data = rng.integers(0, 256, 3 << 20, dtype=np.uint8)
+    n = 300
+    offs = np.sort(rng.integers(0, data.size - 20000, n)).astype(np.uint64)
+    lens = rng.integers(1, 20000, n).astype(np.uint64)
+    want = np.array([otfr.crc32c(data[int(o):int(o + l)].tobytes()) for o, l in zip(offs, lens)], dtype=np.uint32)
+    d_dev = torch.from_numpy(data).to(dev)
+    imgs = [rng.integers(0, 256, (40, 40, 3), dtype=np.uint8) for _ in range(40)]
+    labs = [rng.integers(0, 10, (40, 40), dtype=np.uint8) for _ in range(40)]
+    want_rec = b"".join(otfr.frame(oep.convert_to_example(i, l, 40, 40, 3, 40, 40, "k%d" % k).SerializeToString())
+                        for k, (i, l) in enumerate(zip(imgs, labs)))
+    errors = []
+
+    def crc_loop():
+        try:
+            st = torch.cuda.Stream(dev)
+            with torch.cuda.stream(st):
+                for _ in range(30):
+                    assert np.array_equal(ops.crc32c(d_dev, offs, lens, dev), want)
+        except Exception as e:            # noqa: BLE001
+            errors.append(e)
+
+    def build_loop():
+        try:
+            st = torch.cuda.Stream(dev)
+            with torch.cuda.stream(st):
+                items = [dict(img=torch.from_numpy(i).to(dev).reshape(-1), tgt=torch.from_numpy(l).to(dev).reshape(-1), kind=1,
+                              h=40, w=40, c=3, th=40, tw=40, identifier=("k%d" % k).encode()) for k, (i, l) in enumerate(zip(imgs, labs))]
+                for _ in range(30):
+                    buf, _, total = ops.build_records(items, dev)
+                    assert bytes(buf[:total].cpu().numpy()) == want_rec
+        except Exception as e:            # noqa: BLE001
+            errors.append(e)
+    ts = [threading.Thread(target=crc_loop), threading.Thread(target=build_loop), threading.Thread(target=crc_loop)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors[0]
