@@ -204,7 +204,7 @@ def reserve_staging(device, nbytes):
         pool.stage_hwm = max(pool.stage_hwm, int(nbytes))
 
 
-def plan_blobs(blobs, device=None, png_as_tf=False, inplace=None):
+def plan_blobs(blobs, device=None, png_as_tf=False, inplace=None, threads=0):
     """Host half of decode_blobs: header parse, descriptor tables and the gather of all compressed bytes into one pinned
     buffer, in ONE native multi-threaded call.  Touches no GPU state besides pinned host memory, so the translators run
     it on their read-ahead thread while the GPU works on the previous batch.
@@ -237,7 +237,7 @@ def plan_blobs(blobs, device=None, png_as_tf=False, inplace=None):
     for _ in range(2):
         check(lib().b2_decode_plan_batch(ptrs, sizes.ctypes.data, n, pb.infos, pb.status.ctypes.data, pb.images.ctypes.data,
                                          hs.streams.data_ptr(), hs.streams.numel() // ssz, hs.stage.data_ptr(),
-                                         hs.stage.numel(), 0, flags, ctypes.byref(pb.plan)))
+                                         hs.stage.numel(), int(threads), flags, ctypes.byref(pb.plan)))
         if pb.plan.filled:
             break
         if hs.stage.numel() < pb.plan.stage_bytes:

@@ -314,6 +314,12 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
     num_files = ranges[worker_index][1] - ranges[worker_index][0]
     ctx = get_ctx(device)
     os.makedirs(output_directory, exist_ok=True)
+    # host threads: this worker's share of the box's cores (one worker per GPU runs beside it, in this process or under
+    # torchrun); more threads than cores only adds context switches — an 8-GPU box here has 4 cores per GPU
+    share = max(1, (os.cpu_count() or 1) // max(1, _workers_on_this_host()))
+    io_threads = max(2, min(io_threads, share))
+    plan_threads = max(2, min(16, share))
+    write_threads = max(2, min(16, 2 * share))
     try:
         pair_bytes = os.path.getsize(img_filenames[ranges[worker_index][0]]) + os.path.getsize(lbl_filenames[ranges[worker_index][0]])
     except (OSError, IndexError):
@@ -360,10 +366,11 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
         sys.stdout.flush()
 
     with ThreadPoolExecutor(max_workers=2) as pool, ThreadPoolExecutor(max_workers=1) as writer, \
-            ThreadPoolExecutor(max_workers=max(8, io_threads)) as wpool:
+            ThreadPoolExecutor(max_workers=write_threads) as wpool:
         reader = cache["reader"]
         if reader is None:
             reader = cache["reader"] = FileBatchReader(depth=5, threads=io_threads)
+        reader.threads = io_threads
 
         def write_back(buf, total, pieces):
             """Device buffer -> pinned slot -> files.  pieces: [(shard, byte lo, byte hi)] of buf."""
@@ -405,14 +412,15 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                 blobs = reader.read(paths)                                  # one native call; the GIL is free meanwhile
                 planned = None
                 if (store_as_array or validate is not None) and not png_to_jpg:   # host half of the decode, off the main thread
-                    planned = _codec.plan_blobs([b"" if isinstance(b, Exception) else b for b in blobs], ctx.device, png_as_tf)
+                    planned = _codec.plan_blobs([b"" if isinstance(b, Exception) else b for b in blobs], ctx.device, png_as_tf,
+                                                threads=plan_threads)
                 return dict(fast=False, blobs=blobs, planned=planned)
             hs = _codec.take_staging(ctx.device)
             planned = infos = offs = sizes = None
             try:
                 blobs, offs, sizes, clean = reader.read_into(paths, hs)     # straight into the pinned staging buffer
                 if clean and store_as_array:
-                    planned = _codec.plan_blobs(blobs, ctx.device, png_as_tf, inplace=hs)
+                    planned = _codec.plan_blobs(blobs, ctx.device, png_as_tf, inplace=hs, threads=plan_threads)
                 elif clean:                                                 # raw-bytes records: the header fields only
                     infos = np.frombuffer(_codec.probe_blobs(blobs, png_as_tf=png_as_tf), dtype=_codec.IMAGE_INFO_DTYPE, count=len(paths))
                     clean = not infos["status"].any()
@@ -538,6 +546,17 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
     return state["counter"]
 
 
+_concurrent_workers = [1]      # GPU workers running at the same time in THIS process (set by run_workers)
+
+
+def _workers_on_this_host():
+    """How many GPU workers share this host's cores right now: the ranks of a torchrun job on this node, or the device
+    threads of a single process."""
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    return _concurrent_workers[0]
+
+
 def run_workers(num_workers, fn):
     """Run fn(worker_index, device) for every worker this OS process owns.  Workers on different GPUs run
     concurrently, one host thread per GPU (the C ABI's rule is one context = one device = one thread at a time;
@@ -554,9 +573,11 @@ def run_workers(num_workers, fn):
         for p in by_dev[dev]:
             results[p] = fn(p, dev)
     if len(by_dev) <= 1 or os.environ.get("B2_WORKER_THREADS", "1") == "0":
+        _concurrent_workers[0] = 1
         for dev in by_dev:
             on_device(dev)
     else:
+        _concurrent_workers[0] = len(by_dev)
         from concurrent.futures import ThreadPoolExecutor
         for dev in by_dev:
             get_ctx(dev)                                                   # contexts are created on the calling thread
