@@ -251,7 +251,7 @@ def run_ours(args, rank, world):
     traffic = args.traffic
     if traffic is None:                                     # dram bytes per launch from the committed ncu --set full capture
         try:
-            traffic = float(json.load(open(os.path.join(ROOT, "profiles", "r01_parse_traffic.json")))["dram_bytes_per_launch"])
+            traffic = float(json.load(open(os.path.join(ROOT, "profiles", "r02_parse_traffic.json")))["dram_bytes_per_launch"])
         except Exception:
             traffic = None
     kms = [a.elapsed_time(b) for a, b in kern_events]
@@ -277,7 +277,7 @@ def run_ours(args, rank, world):
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                      "launch_ms": k_avg_ms, "launch_timing": "CUDA events around each launch, un-pipelined pass on one stream",
                      "algorithmic_bytes_per_launch": algo, "traffic": traffic,
-                     "traffic_source": "ncu --set full capture of this kernel, profiles/r01_parse_traffic.json (dram read + write per launch)",
+                     "traffic_source": "ncu --set full capture of this kernel, profiles/r02_parse_traffic.json (dram read + write per launch)",
                      "in_graph": {"ms_per_launch_upper_bound": in_graph_ms, "achieved": algo / (in_graph_ms / 1e3) / 1e9,
                                   "frac": algo / (in_graph_ms / 1e3) / 1e9 / peak,
                                   "note": "ms_per_step / 24 launches: inside the timed graph consecutive passes overlap on 3 streams"}},

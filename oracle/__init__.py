@@ -22,19 +22,24 @@ What it restates (reference = harry-gibson/dl_image_segmentation, paths under
                        byte-identical to libjpeg-turbo's files
 ``composite``          ``_descartes_img_chips.py:562-567`` (np.ma median) and ``:461-469,603-626``
                        (date/cloud filter, stable descending sort, painter's mosaic), ``:516`` dstack
+``rasterize``          ``create_label_array_for_tile`` ``_descartes_img_chips.py:633-689`` (GDAL RasterizeLayer, ALL_TOUCHED)
+``refrun``             runs the unmodified reference under ``refstubs/`` (fixture generator, live checks)
 ``normalise``          north-star row A17 (cast, per-band normalise, one-hot, integer band statistics)
 ``translate``          the whole worker loop ``_img_to_tf_mp.py:78-157`` on top of the pieces above
 =====================  ==========================================================================
 
-PARITY STATUS — **parity unpinned by the reference**: the reference ships no tests, golden
-vectors or fixtures and none of its dependencies (tensorflow, rasterio/GDAL,
-descarteslabs) can be imported in the build container, so it cannot be executed to make
-fixtures either.  The arithmetic it delegates lives in un-pinned third-party libraries
-(conda_env_cpu.yml:5-12).  The oracle is therefore pinned from the outside instead:
-RFC 3720 B.4 CRC-32C vectors; ``google.protobuf`` (dynamic ``tensorflow.Example`` descriptor,
-deterministic serialisation); ``zlib``; libtiff 4.7.1 through ``cv2`` and ``Pillow``; libpng through
-``Pillow``; libjpeg-turbo through ``cv2`` and ``Pillow`` (decoded pixels bit for bit, encoded files byte for byte); and ``numpy.ma.median`` itself (NumPy is the real implementation the reference calls).
-Those checks live in ``tests/test_oracle_*.py`` and the committed vectors in ``tests/golden/``.
+PARITY STATUS — pinned on the reference's own code: ``oracle/refrun.py`` imports the UNMODIFIED
+``/root/reference/dl_segmentation_utils`` under the stub dependencies of ``oracle/refstubs/`` (tensorflow, rasterio,
+descarteslabs, geopandas, osgeo are not installable here; the stubs delegate their arithmetic to google.protobuf, NumPy,
+Pillow/libpng, OpenCV/libtiff and libjpeg-turbo, never to this package).  ``tests/golden/gen_golden_reference.py`` ran the
+reference's translators, ``convert_to_example``, its five parsers, its compositors and ``create_chips_for_tile`` and
+committed the outputs (``tests/golden/ref_*``); ``tests/test_reference_parity.py`` checks that every module here reproduces
+them byte for byte and re-runs the reference live where ``/root/reference`` exists.  Unpinned remain only the two things
+for which no code exists in this image: the Descartes Labs service's search / mosaic semantics (restated from its
+documentation) and GDAL's ``RasterizeLayer`` (``rasterize``: restated from GDAL's public algorithm, pinned on the exact
+square-meets-polygon set).  Beneath that the codecs stay pinned from the outside: RFC 3720 B.4 CRC-32C vectors;
+``google.protobuf``; ``zlib``; libtiff 4.7.1 through ``cv2`` and ``Pillow``; libpng; libjpeg-turbo (decoded pixels bit for
+bit, encoded files byte for byte); ``numpy.ma.median`` (``tests/test_oracle_*.py``, ``tests/golden/``).
 """
 import ctypes
 import os
