@@ -222,3 +222,96 @@ def test_probe_header_only(dev):
     i3 = _codec.probe(syn.png_bytes(syn.cfg1_chip(0, size=40)[0]))
     assert (i3.height, i3.width, i3.samples, i3.format) == (40, 40, 3, 2)
     assert _codec.probe(b"garbage").status != 0
+
+
+# ------------------------------------------------------------------------------------------------ round-2 decoders: fuzz
+def _grey_png_from_zlib(rows, width, zstream):
+    """A grey 8-bit PNG whose IDAT is the given zlib stream over `rows` x (1 + width) filtered bytes."""
+    return syn.png_bytes_raw_zlib(width, rows, 1, zstream)
+
+
+def test_inflate_chunk_parallel_decode_against_zlib_fuzz(dev):
+    """The chunk-parallel symbol decode (self-synchronising restart rounds, staged literals, dependency-ordered matches,
+    serial fallback for match-dense blocks) on streams of every character: incompressible, runs, short and long matches,
+    all zlib strategies / levels (fixed Huffman, Huffman-only, RLE, stored), several blocks, sizes around the chunk
+    boundaries — decoded bytes must equal what zlib itself returns (filter type 0 rows make the PNG's pixels = the data)."""
+    import zlib
+    rng = np.random.default_rng(2024)
+    blobs, want = [], []
+
+    def add(data, level, strategy=zlib.Z_DEFAULT_STRATEGY, wbits=15, width=None):
+        width = width or 255
+        rows = (len(data) + width - 1) // width
+        data = data + bytes(rows * width - len(data))
+        arr = np.frombuffer(data, np.uint8).reshape(rows, width)
+        filtered = np.concatenate([np.zeros((rows, 1), np.uint8), arr], axis=1).tobytes()        # filter type 0 on every row
+        co = zlib.compressobj(level, zlib.DEFLATED, wbits, 8, strategy)
+        z = co.compress(filtered) + co.flush()
+        assert zlib.decompress(z) == filtered
+        blobs.append(_grey_png_from_zlib(rows, width, z))
+        want.append(arr[:, :, None])
+    for n in (1, 7, 79, 80, 81, 639, 640, 641, 5000, 70000, 200000):
+        add(rng.integers(0, 256, n, dtype=np.uint8).tobytes(), 6)                                  # incompressible: all literals
+    for level in (1, 6, 9):
+        noise = rng.integers(0, 4, 150000, dtype=np.uint8).tobytes()                               # short codes, few matches
+        add(noise, level)
+        add(noise, level, zlib.Z_HUFFMAN_ONLY)
+        text = bytes(rng.choice(np.frombuffer(b"abcdefgh \n", np.uint8), 120000))                  # many short matches
+        add(text, level)
+        add(text, level, zlib.Z_FIXED)
+        runs = np.repeat(rng.integers(0, 256, 3000, dtype=np.uint8), rng.integers(1, 300, 3000)).tobytes()   # long runs: dist 1
+        add(runs, level)
+        add(runs, level, zlib.Z_RLE)
+    add(rng.integers(0, 256, 90000, dtype=np.uint8).tobytes(), 0)                                  # stored blocks only
+    mixed = b"".join([rng.integers(0, 256, 30000, dtype=np.uint8).tobytes(), bytes(40000), rng.integers(0, 3, 50000, dtype=np.uint8).tobytes(),
+                      b"xyz" * 20000])                                                             # the character changes block by block
+    add(mixed, 6)
+    add(mixed, 6, wbits=9)                                                                         # 512-byte window: short distances only
+    co = zlib.compressobj(6)
+    parts = b""
+    src = rng.integers(0, 16, 100000, dtype=np.uint8).tobytes()
+    rows = len(src) // 250
+    filt = np.concatenate([np.zeros((rows, 1), np.uint8), np.frombuffer(src[:rows * 250], np.uint8).reshape(rows, 250)], axis=1).tobytes()
+    for k in range(0, len(filt), 7001):                                                            # Z_FULL_FLUSH: many small blocks + empty stored blocks
+        parts += co.compress(filt[k:k + 7001]) + co.flush(zlib.Z_FULL_FLUSH)
+    parts += co.flush()
+    blobs.append(_grey_png_from_zlib(rows, 250, parts))
+    want.append(np.frombuffer(src[:rows * 250], np.uint8).reshape(rows, 250, 1))
+    got, status = _decode(dev, blobs)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert status[i] == 0, (i, status[i])
+        assert np.array_equal(g, w), i
+    # damaged streams: a flipped bit anywhere must never be silently accepted with the same bytes AND a valid check
+    bad = []
+    for i in [k for k, b in enumerate(blobs) if len(b) > 4000][::5][:4]:
+        b = bytearray(blobs[i])
+        pos = b.find(b"IDAT") + 4 + 10 + (i * 37) % 200
+        b[pos] ^= 0x10
+        bad.append(bytes(b))
+    _, st = _decode(dev, bad)
+    assert all(s != 0 for s in st), list(st)
+
+
+def test_lzw_segment_parallel_decode_fuzz(dev):
+    """The segment-parallel LZW decoder on tiles of every character (incompressible: strings of 1-2 bytes; constant and
+    run-length data: strings hundreds of bytes long, several output windows per segment; text-like; tiny tiles; tiles that
+    end in mid-string; strips instead of tiles) against the oracle's sequential table decoder."""
+    rng = np.random.default_rng(77)
+    blobs = []
+    S = 96
+    imgs = [rng.integers(0, 65536, (S, S, 4)).astype(np.uint16),                                  # incompressible
+            np.zeros((S, S, 4), np.uint16), np.full((S, S, 4), 0xABCD, np.uint16),                 # one very long string chain
+            np.repeat(rng.integers(0, 256, (S, S // 8, 1)), 8, axis=1).astype(np.uint8).repeat(3, axis=2),      # runs
+            (np.arange(S * S * 2).reshape(S, S, 2) % 251).astype(np.uint8),                       # periodic
+            rng.integers(0, 3, (S, S, 1)).astype(np.uint8),                                        # tiny alphabet: deep forests
+            rng.integers(0, 256, (5, 7, 1)).astype(np.uint8), rng.integers(0, 256, (1, 1, 1)).astype(np.uint8)]
+    for im in imgs:
+        blobs += [syn.tiff_bytes(im, tile=32), syn.tiff_bytes(im, tile=256), syn.tiff_bytes(im, tile=None, rows_per_strip=3),
+                  syn.tiff_bytes(im, tile=64, predictor=2)]
+    big = np.zeros((512, 512), np.uint8)
+    big[100:300, 50:400] = 9
+    blobs.append(syn.tiff_bytes(big, tile=256))                                                   # label-like: segments of > 12 KiB output
+    got, status = _decode(dev, blobs)
+    for i, b in enumerate(blobs):
+        assert status[i] == 0, (i, status[i])
+        assert np.array_equal(got[i], oic.decode_image(b)), i
