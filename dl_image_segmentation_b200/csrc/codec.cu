@@ -334,11 +334,13 @@ constexpr int kLitRoot = 10, kDistRoot = 8;
 constexpr int kLitSub = 320, kDistSub = 256;     // second-level entries; a code set needing more decodes bit by bit
 constexpr int kWinWords = 128;
 constexpr int kInfStage = 256;
-// chunk-parallel decode: 32 lanes x kParSub bits per chunk.  160 bits = 5 words: lanes in lock-step hit 32 different banks
+// chunk-parallel decode: 32 lanes x kParSub bits per chunk.  160 bits = 5 words, an odd stride: lanes in lock-step hit 32
+// different banks.  The per-warp shared memory (13.9 KB) keeps 16 streams resident per SM, which a 1024-pair batch needs
+// (13.8 streams per SM): larger stages / match lists cost a second wave (measured: 5.5 ms instead of 3.65 ms per batch)
 constexpr int kParSub = 160;
 constexpr int kParWords = 32 * kParSub / 32 + 8;     // chunk + alignment + the longest symbol (48 bits) + the words fetched ahead
 constexpr int kParPre = 6;                           // words per lane requested ahead for the next chunk
-constexpr int kParMatches = 128;
+constexpr int kParMatches = 128;                     // > the most matches one sub-chunk can hold (2 bits each: 80)
 constexpr int kParStage = 2048;
 
 // table entry: [15:0] value | [23:16] code bits to drop | [27:24] extra bits (BASE) or index bits (SUB) | [31:28] kind.
@@ -790,7 +792,7 @@ __device__ __forceinline__ int inflate_par_chunk(InfWarpSmem* sm, const ParTable
         if (lane >= d) { mincl += a; oincl += b; }
     }
     const uint32_t fits = __ballot_sync(kFull, lane < valid && mincl <= (uint32_t)kParMatches);
-    const int keep = fits == kFull ? 32 : __ffs(~fits) - 1;            // a sub-chunk holds at most 80 matches: keep >= 1
+    const int keep = fits == kFull ? 32 : __ffs(~fits) - 1;            // a sub-chunk holds at most kParSub / 2 matches: keep >= 1
     bool stopped = first_stop < 32;
     if (keep < valid) { valid = keep; stopped = false; }
     const uint32_t total_out = __shfl_sync(kFull, oincl, valid - 1), total_m = __shfl_sync(kFull, mincl, valid - 1);
