@@ -310,6 +310,17 @@ def run_ours(args, rank, world):
         print(json.dumps(line))
 
 
+def _mosaic_traffic(chips_per_s, peak):
+    """DRAM bytes per chip of the mosaic kernel from the committed ncu --set full capture, and the rate they imply."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_mosaic_traffic.json")))
+        b = float(t["dram_bytes_per_chip"])
+        return {"bytes_per_chip_ncu": b, "GB/s": chips_per_s * b / 1e9, "frac_of_measured_hbm": round(chips_per_s * b / 1e9 / peak, 4),
+                "source": "profiles/r02_mosaic_traffic.json (dram__bytes_read + write of one launch / 4096 chips)"}
+    except Exception:
+        return None
+
+
 def other_configs(dev):
     """The other configurations of BASELINE.json's compound metric, device-resident kernel rates on this GPU (CUDA
     events, inputs >> L2, same code as tools/kbench.py): cloud-masked median (configs[3]), nearest-date mosaic with
@@ -331,6 +342,7 @@ def other_configs(dev):
     out["cfg5_mosaic_T32_256x256x4_u16_with_band_stats"] = {
         "ms": d["ms"], "chips_per_s": d["chips_per_s"], "min_touched_GB/s": d["GB/s_min_touched"],
         "frac_of_measured_hbm_min_touched": round(d["GB/s_min_touched"] / kbench.PEAK, 4), "dense_equivalent_GB/s": d["GB/s"],
+        "dram_traffic": _mosaic_traffic(d["chips_per_s"], kbench.PEAK),
         "note": "SURVEY 8(d): 331 k chips/s is the dense-definition roofline; the kernel skips filtered / occluded scenes, so the "
                 "dense-equivalent rate exceeds HBM bandwidth and the fraction is quoted on the bytes it must touch"}
     torch.cuda.empty_cache()
