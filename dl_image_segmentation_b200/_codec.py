@@ -134,7 +134,7 @@ class _StagingPool:
     """A few pinned staging sets per device, handed out in rotation: a batch can be planned (host work, any thread) while
     the previous one is still being uploaded and decoded."""
 
-    def __init__(self, n=4):
+    def __init__(self, n=6):
         self.sets = [_HostStaging() for _ in range(n)]
         self.k = 0
         self.lock = threading.Lock()

@@ -339,17 +339,43 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
     lo_all, hi_all = int(shard_ranges[0]), int(shard_ranges[-1])
     # the first batches are small (1/8, 1/4, 1/2 of the full size): the pipeline's start-up latency is the time the first
     # batch takes to go through read -> plan -> decode -> build -> write
-    batches, b0, size = [], lo_all, max(32, batch_pairs // 8)
-    while b0 < hi_all:
-        b1 = min(b0 + size, hi_all)
-        batches.append((b0, b1))
-        b0, size = b1, min(batch_pairs, size * 2)
+    # ... and the last ones taper off again (1/2, 1/4, 1/4): what follows the last read — decode, serialise, copy back,
+    # write — is the pipeline's tail, and it is as long as the last batch is large
+    sizes, left, size = [], hi_all - lo_all, max(32, batch_pairs // 8)
+    while left > 0 and size < batch_pairs:
+        sizes.append(min(size, left))
+        left -= sizes[-1]
+        size *= 2
+    tail = []
+    if left > batch_pairs:
+        for frac in (4, 4, 2):
+            t = min(left, max(32, batch_pairs // frac))
+            tail.insert(0, t)
+            left -= t
+    while left > 0:
+        sizes.append(min(batch_pairs, left))
+        left -= sizes[-1]
+    sizes += tail                                                           # e.g. ..., 1024, 512, 256, 256
+    batches, b0 = [], lo_all
+    for sz in sizes:
+        if sz > 0:
+            batches.append((b0, b0 + sz))
+            b0 += sz
+    assert b0 == hi_all
     files = [open(os.path.join(output_directory, "%s-%.5d-of-%.5d" % (name, worker_index * per + s, num_shards)), "w+b")
              for s in range(per)]
     shard_off = [0] * per
     shard_count = [0] * per
+    kAhead = 3                                                              # batches being read / planned ahead of the GPU
     state = {"counter": 0, "seq": 0}
     copy_stream = torch.cuda.Stream(ctx.device)
+    trace = [] if os.environ.get("B2_TRANSLATE_TRACE") else None      # development aid: (seconds, event) per pipeline step
+    import time as _time
+    t_start = _time.perf_counter()
+
+    def mark(ev):
+        if trace is not None:
+            trace.append((round(_time.perf_counter() - t_start, 4), ev))
 
     def count_records(s, k):
         """k more records in shard s: the reference's progress line at every multiple of progress_every."""
@@ -365,7 +391,7 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
         print("%s [%s %d]: Wrote %d images to %s" % (datetime.now(), label, worker_index, shard_count[s], files[s].name))
         sys.stdout.flush()
 
-    with ThreadPoolExecutor(max_workers=2) as pool, ThreadPoolExecutor(max_workers=1) as writer, \
+    with ThreadPoolExecutor(max_workers=kAhead) as pool, ThreadPoolExecutor(max_workers=1) as writer, \
             ThreadPoolExecutor(max_workers=write_threads) as wpool:
         reader = cache["reader"]
         if reader is None:
@@ -405,6 +431,13 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
             slot_futs[slot].append(writer.submit(_write))
 
         def read_and_plan(rng):
+            mark("thread read start %d" % rng[0])
+            try:
+                return _read_and_plan(rng)
+            finally:
+                mark("thread read end %d" % rng[0])
+
+        def _read_and_plan(rng):
             paths = []
             for i in range(*rng):
                 paths += [img_filenames[i], lbl_filenames[i]]
@@ -436,9 +469,11 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
 
         def stage1(bi):
             """Batch bi: wait for its files + plan, queue its upload and decode (nothing synchronised)."""
+            mark("wait read %d" % bi)
             b = pending.pop(0).result()
-            if bi + 2 < len(batches):
-                pending.append(pool.submit(read_and_plan, batches[bi + 2]))  # two batches ahead, on two threads
+            mark("got read %d" % bi)
+            if bi + kAhead < len(batches):
+                pending.append(pool.submit(read_and_plan, batches[bi + kAhead]))  # kAhead batches ahead, one thread each
             b["range"] = batches[bi]
             if b["fast"] and store_as_array:
                 b["job"] = _codec.decode_enqueue(b["planned"], ctx.device)
@@ -481,7 +516,9 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                 keys = b["keys"]
                 if store_as_array:
                     job = b["job"]
+                    mark("wait status")
                     st = job.status()                                       # waits for this batch's decode only
+                    mark("got status")
                     infos = job.infos_array()
                     ok = not st.any() and not infos["status"].any()
                 else:
@@ -503,14 +540,16 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                         count_records(s, hi - lo)
                         if hi == int(shard_ranges[s + 1]):
                             done.append(s)
+                    mark("built")
                     write_back(rec.out, rec.total, pieces)
+                    mark("queued write")
                     for s in done:
                         shard_done(s)
                     return
                 b = dict(blobs=None, planned=None)                          # an irregular batch: chip by chip, from the files
             slow_batch(b0, b1, b.get("blobs"), b.get("planned"))
 
-        pending = [pool.submit(read_and_plan, batches[k]) for k in range(min(2, len(batches)))]
+        pending = [pool.submit(read_and_plan, batches[k]) for k in range(min(kAhead, len(batches)))]
         prev = None
         try:
             for bi in range(len(batches)):
@@ -535,10 +574,14 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
         for s in range(per):                                                # shards that received no file at all
             if int(shard_ranges[s]) == int(shard_ranges[s + 1]):
                 shard_done(s)
+        mark("drain writes")
         for fl in slot_futs:
             for x in fl:
                 for y in x.result():
                     y.result()
+        mark("done")
+    if trace is not None:
+        sys.stderr.write("translate trace (worker %d): %s\n" % (worker_index, trace))
     for f in files:
         f.close()
     print("%s [%s %d]: Wrote %d images to %d shards." % (datetime.now(), label, worker_index, state["counter"], per))
