@@ -112,3 +112,32 @@ def test_images_to_tfrecords_mt_png(dev, tmp_path, store_as_array):
         pkg.images_to_tfrecords_mt("m", str(tmp_path), out_g, 2, num_threads=2, store_as_array=store_as_array)
     otr.images_to_tfrecords("m", str(tmp_path), out_c, 2, num_proc=2, file_ext="png", store_as_array=store_as_array, n_jobs=1)
     _same_shards(out_g, out_c)
+
+
+@pytest.mark.parametrize("kind,store_as_array", [("png", True), ("tif", True), ("tif", False)])
+def test_pipelined_worker_mixes_clean_and_irregular_batches(dev, tmp_path, kind, store_as_array):
+    """The worker pipeline with many small decode batches: clean batches take the vectorised path (one plan call, one build
+    launch per batch), a batch with a damaged chip or a key mismatch falls back to the chip-by-chip path, and batches
+    straddle shard boundaries — the shard files must still be the oracle's, byte for byte, with the reference's progress
+    and SKIPPED lines."""
+    from dl_image_segmentation_b200 import _translate
+    n = 61
+    ext = _write_dataset(tmp_path, kind, n, 40 if kind == "png" else 48, corrupt=(20,), mismatch=(33, 34))
+    imgs, lbls = opart.find_image_files(str(tmp_path), ext)
+    out_g, out_c = str(tmp_path / "g"), str(tmp_path / "c")
+    ranges = _translate.worker_ranges(n, 1)
+    key = lambda p, info=None: _translate.tile_key_from_path(p, True)
+    with contextlib.redirect_stdout(io.StringIO()) as log:
+        wrote = _translate.run_worker(0, ranges, "t", imgs, lbls, out_g, 5, key, store_as_array, progress_every=10,
+                                      batch_pairs=8, path_key=lambda p: _translate.tile_key_from_path(p, True))
+    want = otr.images_to_tfrecords("t", str(tmp_path), out_c, 5, num_proc=1, file_ext=ext, store_as_array=store_as_array, n_jobs=1)
+    _same_shards(out_g, out_c)
+    assert wrote == want
+    text = log.getvalue()
+    assert text.count("SKIPPED: Unexpected eror while decoding") == n - want
+    assert text.count("Processed ") == want // 10 and text.count("Wrote ") == 5 + 1
+    # and again straight away: the pinned staging sets, write-back buffers and the reader are reused
+    with contextlib.redirect_stdout(io.StringIO()):
+        assert _translate.run_worker(0, ranges, "t", imgs, lbls, str(tmp_path / "g2"), 5, key, store_as_array, batch_pairs=16,
+                                     path_key=lambda p: _translate.tile_key_from_path(p, True)) == want
+    _same_shards(str(tmp_path / "g2"), out_c)
