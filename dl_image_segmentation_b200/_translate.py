@@ -20,6 +20,8 @@ from . import _codec, ops
 from . import _lib as _lib_mod
 from ._lib import check, get_ctx, lib
 
+_MAPPED_WRITE_MIN = 32 << 20     # pieces this large are written pwrite-head + mapped-rest (see run_worker.write_back)
+
 
 def tile_key_from_path(path, parse_dltile_filename=True):
     base = os.path.basename(path)
@@ -290,6 +292,68 @@ class BatchRecords:
         return int(self.rec_off[lo]), (int(self.rec_off[hi]) if hi < len(self.rec_off) else self.total)
 
 
+def batch_schedule(shard_ranges, batch_pairs, interleave=8):
+    """Decode batches of one worker: a list of batches, each a list of runs (shard, lo, hi) over the file list.  Every file of
+    [shard_ranges[0], shard_ranges[-1]) appears once, and each shard's files in order."""
+    per = len(shard_ranges) - 1
+    lo_all, hi_all = int(shard_ranges[0]), int(shard_ranges[-1])
+    # the first batches are small (1/8, 1/4, 1/2 of the full size): the pipeline's start-up latency is the time the first
+    # batch takes to go through read -> plan -> decode -> build -> write
+    # ... and the last ones taper off again (1/2, 1/4, 1/4): what follows the last read — decode, serialise, copy back,
+    # write — is the pipeline's tail, and it is as long as the last batch is large
+    sizes, left, size = [], hi_all - lo_all, max(32, batch_pairs // 8)
+    while left > 0 and size < batch_pairs:
+        sizes.append(min(size, left))
+        left -= sizes[-1]
+        size *= 2
+    tail = []
+    if left > batch_pairs:
+        for frac in (4, 4, 2):
+            t = min(left, max(32, batch_pairs // frac))
+            tail.insert(0, t)
+            left -= t
+    while left > 0:
+        sizes.append(min(batch_pairs, left))
+        left -= sizes[-1]
+    sizes += tail                                                           # e.g. ..., 1024, 512, 256, 256
+    # a batch is a list of runs (shard, lo, hi): the same number of pairs from each of up to interleave shards, so that every
+    # batch's records go to that many files at once — writes to ONE file serialise in the kernel (see write_back), and with
+    # multi-megabyte records a batch of consecutive pairs would touch two or three files only
+    batches = []
+    for g0 in range(0, per, interleave):
+        group = list(range(g0, min(per, g0 + interleave)))
+        cursor = {s: int(shard_ranges[s]) for s in group}
+        left_g = sum(int(shard_ranges[s + 1]) - cursor[s] for s in group)
+        while left_g > 0:
+            want = min(sizes.pop(0) if sizes else batch_pairs, left_g)
+            if want <= 0:
+                continue
+            runs, got = [], 0
+            while got < want:
+                active = [s for s in group if cursor[s] < int(shard_ranges[s + 1])]
+                quota = -(-(want - got) // len(active))
+                for s in active:
+                    k = min(quota, int(shard_ranges[s + 1]) - cursor[s], want - got)
+                    if k > 0:
+                        if runs and runs[-1][0] == s:
+                            runs[-1] = (s, runs[-1][1], cursor[s] + k)
+                        else:
+                            runs.append((s, cursor[s], cursor[s] + k))
+                        cursor[s] += k
+                        got += k
+            runs.sort()
+            merged = []
+            for r in runs:                                                  # a second helping from the same shard joins its run
+                if merged and merged[-1][0] == r[0] and merged[-1][2] == r[1]:
+                    merged[-1] = (r[0], merged[-1][1], r[2])
+                else:
+                    merged.append(r)
+            batches.append(merged)
+            left_g -= got
+    assert sum(hi - lo for runs in batches for _, lo, hi in runs) == hi_all - lo_all
+    return batches
+
+
 def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_directory, num_shards, key_fn,
                store_as_array, label="process", progress_every=100, validate=None, device=None, batch_pairs=None,
                io_threads=8, png_as_tf=False, png_to_jpg=False, path_key=None, fast_validate=None):
@@ -336,32 +400,7 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
     cache = _worker_buffers.setdefault(ctx.device.index, {"pinned": [None] * n_slots, "reader": None})
     pinned = cache["pinned"]
     slot_futs = [[] for _ in range(n_slots)]                                # writes still reading a buffer
-    lo_all, hi_all = int(shard_ranges[0]), int(shard_ranges[-1])
-    # the first batches are small (1/8, 1/4, 1/2 of the full size): the pipeline's start-up latency is the time the first
-    # batch takes to go through read -> plan -> decode -> build -> write
-    # ... and the last ones taper off again (1/2, 1/4, 1/4): what follows the last read — decode, serialise, copy back,
-    # write — is the pipeline's tail, and it is as long as the last batch is large
-    sizes, left, size = [], hi_all - lo_all, max(32, batch_pairs // 8)
-    while left > 0 and size < batch_pairs:
-        sizes.append(min(size, left))
-        left -= sizes[-1]
-        size *= 2
-    tail = []
-    if left > batch_pairs:
-        for frac in (4, 4, 2):
-            t = min(left, max(32, batch_pairs // frac))
-            tail.insert(0, t)
-            left -= t
-    while left > 0:
-        sizes.append(min(batch_pairs, left))
-        left -= sizes[-1]
-    sizes += tail                                                           # e.g. ..., 1024, 512, 256, 256
-    batches, b0 = [], lo_all
-    for sz in sizes:
-        if sz > 0:
-            batches.append((b0, b0 + sz))
-            b0 += sz
-    assert b0 == hi_all
+    batches = batch_schedule(shard_ranges, batch_pairs)
     files = [open(os.path.join(output_directory, "%s-%.5d-of-%.5d" % (name, worker_index * per + s, num_shards)), "w+b")
              for s in range(per)]
     shard_off = [0] * per
@@ -423,24 +462,47 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
 
             def _write(h=host, ev=done, jobs=jobs):
                 ev.synchronize()                                             # the records have arrived in pinned memory
-                mv = memoryview(h.numpy())
+                src = h.numpy()
+                mv = memoryview(src)
                 # write(2) on ONE file serialises on its inode lock (3.3 GB/s on tmpfs whatever the thread count), writes to
-                # different files do not (28 GB/s over 8 files, 46 GB/s over 16: tools/shm_write_probe.py): one pwrite per
-                # shard file and batch
-                return [wpool.submit(os.pwrite, fd, mv[lo:hi], off) for fd, lo, hi, off in jobs]
+                # different files do not (30 GB/s over 8 files, 35-46 GB/s over 16: tools/shm_write_probe.py): one pwrite per
+                # shard file and batch.  When a batch touches only a few files (large records), the idle threads copy the
+                # rest of each piece into a shared mapping of the file — page faults do not take the inode lock — which
+                # nearly doubles the rate (4 files: 12.9 -> 23 GB/s)
+                futs = []
+                spare = write_threads // max(1, len(jobs)) - 1
+                for fd, lo, hi, off in jobs:
+                    n = hi - lo
+                    k = min(3, spare) if n >= _MAPPED_WRITE_MIN else 0
+                    head = n if k <= 0 else (int(n * 0.4) & ~4095)
+                    if k > 0:
+                        try:
+                            os.ftruncate(fd, max(os.fstat(fd).st_size, off + n))
+                            a0 = (off + head) & ~(mmap.ALLOCATIONGRANULARITY - 1)
+                            mm = mmap.mmap(fd, off + n - a0, offset=a0)
+                            dst = np.frombuffer(mm, dtype=np.uint8)[off + head - a0:]
+                            step = ((n - head + k - 1) // k + 4095) & ~4095
+                            for o in range(0, n - head, step):
+                                e = min(o + step, n - head)
+                                futs.append(wpool.submit(np.copyto, dst[o:e], src[lo + head + o:lo + head + e]))
+                        except (OSError, ValueError):                       # a file system without shared mappings
+                            head = n
+                    futs.append(wpool.submit(os.pwrite, fd, mv[lo:lo + head], off))
+                return futs
             slot_futs[slot].append(writer.submit(_write))
 
         def read_and_plan(rng):
-            mark("thread read start %d" % rng[0])
+            mark("thread read start %d" % rng[0][1])
             try:
                 return _read_and_plan(rng)
             finally:
-                mark("thread read end %d" % rng[0])
+                mark("thread read end %d" % rng[0][1])
 
         def _read_and_plan(rng):
             paths = []
-            for i in range(*rng):
-                paths += [img_filenames[i], lbl_filenames[i]]
+            for _, lo, hi in rng:
+                for i in range(lo, hi):
+                    paths += [img_filenames[i], lbl_filenames[i]]
             if not fast:
                 blobs = reader.read(paths)                                  # one native call; the GIL is free meanwhile
                 planned = None
@@ -474,7 +536,7 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
             mark("got read %d" % bi)
             if bi + kAhead < len(batches):
                 pending.append(pool.submit(read_and_plan, batches[bi + kAhead]))  # kAhead batches ahead, one thread each
-            b["range"] = batches[bi]
+            b["runs"] = batches[bi]
             if b["fast"] and store_as_array:
                 b["job"] = _codec.decode_enqueue(b["planned"], ctx.device)
             elif b["fast"]:                                                 # the files as they are: one upload of the staging buffer
@@ -486,24 +548,23 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                 hs.pending = False
             return b
 
-        def slow_batch(b0, b1, blobs, planned):
-            idx = list(range(b0, b1))
+        def slow_batch(runs, blobs, planned):
+            idx = [i for _, lo, hi in runs for i in range(lo, hi)]
             pairs = load_pairs([img_filenames[i] for i in idx], [lbl_filenames[i] for i in idx], store_as_array,
                                key_fn, validate, ctx.device, blobs=blobs, png_as_tf=png_as_tf, planned=planned,
                                png_to_jpg=png_to_jpg)
-            for s in range(per):
-                lo, hi = max(b0, int(shard_ranges[s])), min(b1, int(shard_ranges[s + 1]))
-                if lo >= hi:
-                    continue
+            pos = 0
+            for s, lo, hi in runs:
                 items = []
                 for i in range(lo, hi):
-                    p = pairs[i - b0]
+                    p = pairs[pos + i - lo]
                     if isinstance(p, Exception):
                         print(p)
                         print("SKIPPED: Unexpected eror while decoding %s." % img_filenames[i])
                         continue
                     items.append(p)
                     count_records(s, 1)
+                pos += hi - lo
                 if items:
                     buf, _, total = ops.build_records(items, ctx.device)
                     write_back(buf, total, [(s, 0, total)])
@@ -511,7 +572,7 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                     shard_done(s)
 
         def finish(b):
-            b0, b1 = b["range"]
+            runs = b["runs"]
             if b["fast"]:
                 keys = b["keys"]
                 if store_as_array:
@@ -530,13 +591,10 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                     ids = [k.encode("utf-8") for k in keys[0::2]]
                     rec = BatchRecords.from_decode(job, ids, ctx) if store_as_array else \
                         BatchRecords.from_files(b["dev"], b["offs"], b["sizes"], infos, ids, ctx)
-                    pieces = []
-                    done = []
-                    for s in range(per):
-                        lo, hi = max(b0, int(shard_ranges[s])), min(b1, int(shard_ranges[s + 1]))
-                        if lo >= hi:
-                            continue
-                        pieces.append((s,) + rec.byte_range(lo - b0, hi - b0))
+                    pieces, done, pos = [], [], 0
+                    for s, lo, hi in runs:
+                        pieces.append((s,) + rec.byte_range(pos, pos + hi - lo))
+                        pos += hi - lo
                         count_records(s, hi - lo)
                         if hi == int(shard_ranges[s + 1]):
                             done.append(s)
@@ -547,7 +605,7 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                         shard_done(s)
                     return
                 b = dict(blobs=None, planned=None)                          # an irregular batch: chip by chip, from the files
-            slow_batch(b0, b1, b.get("blobs"), b.get("planned"))
+            slow_batch(runs, b.get("blobs"), b.get("planned"))
 
         pending = [pool.submit(read_and_plan, batches[k]) for k in range(min(kAhead, len(batches)))]
         prev = None

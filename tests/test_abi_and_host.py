@@ -270,3 +270,25 @@ def test_native_batch_file_reader(tmp_path):
         assert isinstance(got[-2], FileNotFoundError) and isinstance(got[-1], IsADirectoryError)
         assert got[-2].filename == paths[-2]
     assert rd.read([]) == []
+
+
+def test_batch_schedule_covers_every_file_once_in_shard_order():
+    """The translators' decode batches take pairs from up to 8 shards at a time (so that each batch's records go to that
+    many files at once): whatever the shard sizes and batch size, every file index appears exactly once, each shard's
+    files in order, and no batch is empty."""
+    import random
+    from dl_image_segmentation_b200._translate import batch_schedule
+    rng = random.Random(7)
+    for _ in range(200):
+        per = rng.choice([1, 2, 3, 5, 8, 9, 24])
+        n, lo = rng.randint(0, 3000), rng.randint(0, 50)
+        shard_ranges = np.linspace(lo, lo + n, per + 1).astype(int)
+        batches = batch_schedule(shard_ranges, rng.choice([1, 8, 32, 100, 227, 1024]))
+        seen = {s: int(shard_ranges[s]) for s in range(per)}
+        for runs in batches:
+            assert runs and [r[0] for r in runs] == sorted({r[0] for r in runs})
+            assert len(runs) <= 8
+            for s, a, b in runs:
+                assert a == seen[s] and a < b <= int(shard_ranges[s + 1])
+                seen[s] = b
+        assert all(seen[s] == int(shard_ranges[s + 1]) for s in range(per))

@@ -141,3 +141,23 @@ def test_pipelined_worker_mixes_clean_and_irregular_batches(dev, tmp_path, kind,
         assert _translate.run_worker(0, ranges, "t", imgs, lbls, str(tmp_path / "g2"), 5, key, store_as_array, batch_pairs=16,
                                      path_key=lambda p: _translate.tile_key_from_path(p, True)) == want
     _same_shards(str(tmp_path / "g2"), out_c)
+
+
+@pytest.mark.gpu
+def test_large_pieces_written_through_shared_mapping(dev, tmp_path, monkeypatch):
+    """Pieces above _MAPPED_WRITE_MIN are written as a pwrite head plus mapped copies of the rest (run_worker.write_back);
+    with the threshold lowered every piece of this small job takes that path, over several batches per shard file, and the
+    shards must not change by a byte."""
+    from dl_image_segmentation_b200 import _translate
+    monkeypatch.setattr(_translate, "_MAPPED_WRITE_MIN", 4096)
+    n = 40
+    ext = _write_dataset(tmp_path, "tif", n, 48)
+    imgs, lbls = opart.find_image_files(str(tmp_path), ext)
+    out_g, out_c = str(tmp_path / "g"), str(tmp_path / "c")
+    key = lambda p, info=None: _translate.tile_key_from_path(p, True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        wrote = _translate.run_worker(0, _translate.worker_ranges(n, 1), "t", imgs, lbls, out_g, 2, key, True, batch_pairs=6,
+                                      path_key=lambda p: _translate.tile_key_from_path(p, True))
+    want = otr.images_to_tfrecords("t", str(tmp_path), out_c, 2, num_proc=1, file_ext=ext, store_as_array=True, n_jobs=1)
+    assert wrote == want == n
+    _same_shards(out_g, out_c)
