@@ -22,9 +22,14 @@ ENC_DESC_DTYPE = np.dtype([("src_off", "<u8"), ("dst_off", "<u8"), ("src_len", "
 _vp, _i = ctypes.c_void_p, ctypes.c_int
 _lib.register_signatures({
     "b2_lzw_encode": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "b2_lzw_encode_restart": (_i, [_vp, _vp, _vp, _i, ctypes.c_uint32, _vp, _vp, _vp]),
     "b2_tile_split": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "b2_gather_ranges": (_i, [_vp, _vp, _vp, _vp, _vp, _i, ctypes.c_uint32, _vp, _vp]),
 })
+
+# A Clear code every LZW_RESTART input bytes (0: only when the 4094-entry table is full, as libtiff does).  Every TIFF reader
+# accepts either; with the restarts a tile is hundreds of independent pieces for the encoder instead of one serial walk.
+LZW_RESTART = 1024
 
 _pinned = {}      # device index -> pinned host buffer the packed code streams land in (grown on demand)
 
@@ -36,10 +41,11 @@ for _n, _t in (("uint16", np.uint16), ("uint32", np.uint32)):
         _NP_OF_TORCH[getattr(torch, _n)] = _t
 
 
-def _encode_compact(raw, lengths, device=None):
+def _encode_compact(raw, lengths, device=None, restart=None):
     """TIFF-LZW encode consecutive byte ranges of one device buffer (back to back, each padded to 16 bytes).
     Returns (host uint8 array holding all code streams back to back, numpy array of their lengths)."""
     ctx = get_ctx(device)
+    restart = LZW_RESTART if restart is None else int(restart)
     n = len(lengths)
     ln = np.asarray(lengths, dtype=np.int64)
     cap = (ln * 3) // 2 + 64
@@ -50,8 +56,11 @@ def _encode_compact(raw, lengths, device=None):
     descs["dst_off"] = np.concatenate(([0], np.cumsum(dcap)[:-1]))
     out = torch.empty((max(int(dcap.sum()), 16),), dtype=torch.uint8, device=ctx.device)
     out_len = torch.empty((n,), dtype=torch.int32, device=ctx.device)
-    d_dev = torch.from_numpy(descs.view(np.uint8).reshape(-1)).to(ctx.device)
-    check(lib().b2_lzw_encode(ctx.handle, ptr(raw), ptr(d_dev), n, ptr(out), ptr(out_len), ctx.stream()))
+    if restart:
+        check(lib().b2_lzw_encode_restart(ctx.handle, ptr(raw), descs.ctypes.data, n, restart, ptr(out), ptr(out_len), ctx.stream()))
+    else:
+        d_dev = torch.from_numpy(descs.view(np.uint8).reshape(-1)).to(ctx.device)
+        check(lib().b2_lzw_encode(ctx.handle, ptr(raw), ptr(d_dev), n, ptr(out), ptr(out_len), ctx.stream()))
     lens = out_len.cpu().numpy().view(np.uint32).astype(np.int64)          # small read-back; waits for the encoder
     if (lens == 0xFFFFFFFF).any():
         raise B2Error("b2_lzw_encode: output capacity exceeded")
@@ -72,9 +81,9 @@ def _encode_compact(raw, lengths, device=None):
     return host[:total].numpy(), lens
 
 
-def lzw_encode_tiles(raw, lengths, device=None):
+def lzw_encode_tiles(raw, lengths, device=None, restart=None):
     """As _encode_compact, returning one bytes object per stream."""
-    host, lens = _encode_compact(raw, lengths, device)
+    host, lens = _encode_compact(raw, lengths, device, restart)
     ends = np.cumsum(lens)
     return [host[int(e - l):int(e)].tobytes() for e, l in zip(ends, lens)]
 
@@ -147,7 +156,7 @@ def _ifd(width, height, bands, np_dtype, tile, block_lens, block_data, nodata, g
 
 
 def encode_geotiffs(arrays, nodata=None, geotransform=(499980.0, 10.0, 0.0, 5300040.0, 0.0, -10.0), epsg=32643, tile=256,
-                    device=None, as_parts=False):
+                    device=None, as_parts=False, lzw_restart=None):
     """A batch of (H,W,bands) / (H,W) rasters (CUDA tensors or numpy arrays, any TIFF sample type) -> list of GeoTIFF
     file bytes.  nodata: one value for all, or a list (None entries = no GDAL_NODATA tag).  All tiles of the batch are
     compressed in ONE b2_lzw_encode launch.  as_parts: return (header bytes, tile data view) per file instead of joined
@@ -175,7 +184,7 @@ def encode_geotiffs(arrays, nodata=None, geotransform=(499980.0, 10.0, 0.0, 5300
         lengths += [tb] * (across * down)
         metas.append((W, H, B, _NP_OF_TORCH[t.dtype], across * down))
     raw = torch.cat(parts) if len(parts) > 1 else parts[0]                  # tile sizes are multiples of 16
-    host, lens = _encode_compact(raw, lengths, ctx.device)
+    host, lens = _encode_compact(raw, lengths, ctx.device, lzw_restart)  # None: LZW_RESTART
     mv = memoryview(host)
     files, k, pos = [], 0, 0
     for (W, H, B, dt, nb), nd in zip(metas, nod):
@@ -190,12 +199,13 @@ def encode_geotiffs(arrays, nodata=None, geotransform=(499980.0, 10.0, 0.0, 5300
 
 
 def write_geotiffs(arrays, paths, nodata=None, geotransform=(499980.0, 10.0, 0.0, 5300040.0, 0.0, -10.0), epsg=32643, tile=256,
-                   device=None, io_threads=16):
+                   device=None, io_threads=16, lzw_restart=None):
     """Encode a batch of rasters and write each to its path (the save step of create_chips_for_tile for many tiles at
     once): one encode launch, one packed device -> pinned host copy, then header + tile data of every file written by a
     pool of threads straight from the pinned buffer.  Returns the paths."""
     from concurrent.futures import ThreadPoolExecutor
-    parts = encode_geotiffs(arrays, nodata=nodata, geotransform=geotransform, epsg=epsg, tile=tile, device=device, as_parts=True)
+    parts = encode_geotiffs(arrays, nodata=nodata, geotransform=geotransform, epsg=epsg, tile=tile, device=device, as_parts=True,
+                            lzw_restart=lzw_restart)
 
     def write(job):
         path, (head, data) = job

@@ -17,6 +17,9 @@
 // CTA, so every address is "register + immediate").  With the table in global memory (L2) a byte cost ~1000 cycles
 // and a 512 KiB tile 275 ms; nine resident warps per SM instead of sixty-four is a good trade for a 5x shorter chain
 // (59 ms per tile, ~210 cycles per byte on chips whose noisy low bytes make nearly every step a dictionary miss).
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 namespace b2 {
@@ -176,6 +179,216 @@ lzw_encode_kernel(const uint8_t* __restrict__ raw, const b2_enc_desc* __restrict
     }
 }
 
+// ---------------------------------------------------------------- restart-interval encoder
+// TIFF-LZW allows a Clear code anywhere.  With a Clear every R input bytes (R <= 1024) the pieces of a tile between two
+// Clears are independent LZW streams: a tile of 512 KiB is 512 of them instead of one serial walk, the dictionary of a
+// piece has at most R entries, so its hash table is 8 KiB instead of 24 (28 of them per SM, each owned by ONE thread —
+// the serial walk has nothing for the other 31 lanes of a warp to do), and codes stay 9-11 bits wide.  Two kernels:
+// lzw_segment_kernel encodes every piece into a scratch slot (bit-packed 32-bit words, MSB first) and records its length
+// in bits; lzw_concat_kernel scans the lengths of a tile and shifts the pieces together into the final byte stream.
+constexpr int kSegSlots = 2048;         // hash slots per piece: load <= 0.5
+constexpr int kSegLanes = 7;            // active lanes per warp ...
+constexpr int kSegWarps = 4;            // ... times warps = 28 private tables = 224 KiB of shared memory
+constexpr int kSegMaxRestart = 1024;
+
+struct SegArgs {
+    const uint8_t* raw;
+    const b2_enc_desc* descs;           // device copy, all n tiles
+    const uint32_t* seg_start;          // [n + 1] first piece of every tile (global numbering)
+    uint32_t tile0, tile1;              // this launch covers the pieces of tiles [tile0, tile1)
+    uint32_t seg0, seg1;                // = seg_start[tile0], seg_start[tile1]
+    uint32_t restart, slot_words;
+    uint32_t* scratch;                  // (seg1 - seg0) slots
+    uint32_t* seg_bits;                 // bits produced per piece
+    uint32_t* seg_pos;                  // exclusive scan of seg_bits inside every tile
+    unsigned int* counter;
+    uint8_t* out;
+    uint32_t* out_len;
+};
+
+__global__ void __launch_bounds__(kSegWarps * 32, 1)
+lzw_segment_kernel(const SegArgs a) {
+    extern __shared__ __align__(16) uint32_t seg_tables[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane >= kSegLanes) return;
+    uint32_t* tab = seg_tables + (size_t)(warp * kSegLanes + lane) * kSegSlots;
+    enum { CLEAR = 256, EOI = 257, FIRST = 258 };
+    for (;;) {
+        const uint32_t seg = a.seg0 + atomicAdd(a.counter, 1u);
+        if (seg >= a.seg1) return;
+        // the tile owning this piece: last t in [tile0, tile1) with seg_start[t] <= seg
+        uint32_t lo_t = a.tile0, hi_t = a.tile1;
+        while (hi_t - lo_t > 1) {
+            const uint32_t mid = (lo_t + hi_t) >> 1;
+            if (__ldg(&a.seg_start[mid]) <= seg) lo_t = mid; else hi_t = mid;
+        }
+        const uint32_t k = seg - __ldg(&a.seg_start[lo_t]);
+        const bool last = seg + 1 == __ldg(&a.seg_start[lo_t + 1]);
+        const b2_enc_desc d = a.descs[lo_t];
+        const uint32_t lo = k * a.restart;
+        const uint32_t cnt = d.src_len > lo ? min(a.restart, d.src_len - lo) : 0u;
+        const uint8_t* p = a.raw + d.src_off + lo;
+        uint32_t* slot = a.scratch + (size_t)(seg - a.seg0) * a.slot_words;
+        for (int q = 0; q < kSegSlots / 4; q++) reinterpret_cast<uint4*>(tab)[q] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+        uint64_t acc = 0;
+        int nacc = 0;
+        uint32_t o = 0;
+        auto put = [&](uint32_t code, int nb) {
+            acc = (acc << nb) | code;
+            nacc += nb;
+            if (nacc >= 32) {
+                slot[o++] = (uint32_t)(acc >> (nacc - 32));
+                nacc -= 32;
+            }
+        };
+        int nbits = 9;
+        uint32_t next = FIRST, cur = 0;
+        if (k == 0) put(CLEAR, 9);
+        const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+        auto load16 = [&](uint32_t off) {
+            if (aligned && off + 16 <= cnt) return ld_nc(reinterpret_cast<const uint4*>(p + off));
+            uint32_t t[4] = {0, 0, 0, 0};
+            for (uint32_t q = off; q < cnt && q < off + 16; q++) t[(q - off) >> 2] |= (uint32_t)p[q] << (8 * ((q - off) & 3));
+            return make_uint4(t[0], t[1], t[2], t[3]);
+        };
+        auto step = [&](uint32_t c) {
+            const uint32_t key = (cur << 8) | c;
+            uint32_t h = (key * 2654435761u) >> 21;                 // top 11 bits: 0 .. kSegSlots - 1
+            uint32_t e = tab[h];
+            while (e != kEmpty && (e >> 11) != key) {
+                h = (h + 1) & (kSegSlots - 1);
+                e = tab[h];
+            }
+            if (e != kEmpty) {
+                cur = e & 0x7FFu;
+                return;
+            }
+            put(cur, nbits);
+            tab[h] = (key << 11) | next;
+            next++;
+            cur = c;
+            if (next > (1u << nbits) - 1) nbits++;
+        };
+        if (cnt) {
+            uint4 nxt = load16(0);
+            for (uint32_t off = 0; off < cnt; off += 16) {
+                const uint4 v = nxt;
+                if (off + 16 < cnt) nxt = load16(off + 16);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                if (off != 0 && off + 16 <= cnt) {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) step((w[q >> 2] >> (8 * (q & 3))) & 0xFFu);
+                } else {
+                    const uint32_t m = min(16u, cnt - off);
+                    for (uint32_t q = 0; q < m; q++) {
+                        const uint32_t c = (w[q >> 2] >> (8 * (q & 3))) & 0xFFu;
+                        if (off + q == 0) cur = c;
+                        else step(c);
+                    }
+                }
+            }
+            put(cur, nbits);
+            next++;                                                    // the entry the decoder adds after this code
+            if (next > (1u << nbits) - 1 && nbits < 12) nbits++;
+        }
+        put(last ? EOI : CLEAR, nbits);
+        const uint32_t bits = o * 32 + nacc;
+        if (nacc) slot[o] = (uint32_t)(acc << (32 - nacc));
+        a.seg_bits[seg - a.seg0] = bits;
+    }
+}
+
+// bits [b, b + take) (take <= 32) of a piece stored as MSB-first 32-bit words
+__device__ __forceinline__ uint32_t seg_extract(const uint32_t* slot, uint32_t b, uint32_t take) {
+    const uint32_t w = b >> 5, sh = b & 31;
+    const uint32_t hi = slot[w], lo = sh ? slot[w + 1] : 0u;          // the slot has one spare word
+    const uint32_t v = __funnelshift_l(lo, hi, sh);
+    return take == 32 ? v : v >> (32 - take);
+}
+
+constexpr int kCatThreads = 256;
+constexpr int kCatWords = 8;            // consecutive output words per thread (one 32-byte sector)
+
+__global__ void __launch_bounds__(kCatThreads)
+lzw_concat_kernel(const SegArgs a) {
+    __shared__ uint32_t warp_sum[kCatThreads / 32];
+    __shared__ uint32_t carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t t = a.tile0 + blockIdx.x; t < a.tile1; t += gridDim.x) {
+        const uint32_t s0 = a.seg_start[t] - a.seg0, nseg = a.seg_start[t + 1] - a.seg_start[t];
+        const uint32_t* bits = a.seg_bits + s0;
+        uint32_t* pos = a.seg_pos + s0;
+        __syncthreads();
+        if (tid == 0) carry = 0;
+        __syncthreads();
+        for (uint32_t base = 0; base < nseg; base += kCatThreads) {      // exclusive scan, 256 pieces at a time
+            const uint32_t i = base + tid;
+            const uint32_t v = i < nseg ? bits[i] : 0u;
+            uint32_t x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (lane == 31) warp_sum[warp] = x;
+            __syncthreads();
+            uint32_t before = carry;
+            for (int q = 0; q < warp; q++) before += warp_sum[q];
+            if (i < nseg) pos[i] = before + x - v;
+            __syncthreads();
+            if (tid == kCatThreads - 1) carry = before + x;
+            __syncthreads();
+        }
+        const uint32_t total = carry;
+        const b2_enc_desc d = a.descs[t];
+        const uint32_t nbytes = (total + 7) >> 3;
+        if (nbytes > d.dst_cap) {
+            if (tid == 0) a.out_len[t] = 0xFFFFFFFFu;
+            continue;
+        }
+        if (tid == 0) a.out_len[t] = nbytes;
+        uint8_t* dst = a.out + d.dst_off;
+        const uint32_t nwords = (total + 31) >> 5;
+        for (uint32_t j0 = (uint32_t)tid * kCatWords; j0 < nwords; j0 += kCatThreads * kCatWords) {
+            // the piece holding bit 32 * j0: last k with pos[k] <= bit
+            uint32_t b = j0 << 5, lo = 0, hi = nseg;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (pos[mid] <= b) lo = mid; else hi = mid;
+            }
+            uint32_t k = lo, k_pos = pos[k], k_len = bits[k];
+            uint32_t vals[kCatWords];
+#pragma unroll
+            for (int q = 0; q < kCatWords; q++) {
+                uint32_t val = 0, need = 32;
+                while (need && k < nseg) {
+                    const uint32_t off = b - k_pos, avail = k_len - off;
+                    if (avail == 0) {
+                        k++;
+                        if (k < nseg) { k_pos = pos[k]; k_len = bits[k]; }
+                        continue;
+                    }
+                    const uint32_t take = min(need, avail);
+                    const uint32_t piece = seg_extract(a.scratch + (size_t)(s0 + k) * a.slot_words, off, take);
+                    val |= take == 32 ? piece : piece << (need - take);
+                    need -= take;
+                    b += take;
+                }
+                b += need;                                              // past the end of the stream: zero padding
+                vals[q] = __byte_perm(val, 0, 0x0123);                  // big-endian bit stream
+            }
+#pragma unroll
+            for (int q = 0; q < kCatWords; q++) {
+                const uint32_t j = j0 + q;
+                if (j >= nwords) break;
+                if (4 * j + 4 <= d.dst_cap) *reinterpret_cast<uint32_t*>(dst + 4 * (size_t)j) = vals[q];
+                else
+                    for (uint32_t z = 4 * j; z < nbytes; z++) dst[z] = (uint8_t)(vals[q] >> (8 * (z - 4 * j)));
+            }
+        }
+    }
+}
+
 // (H,W) raster of `pb`-byte pixels -> padded tiles of tw x th pixels, tile-major (row of tiles by row of tiles), zero
 // padding on the right / bottom edge: exactly what a tiled, pixel-interleaved TIFF stores per block.
 __global__ void __launch_bounds__(256)
@@ -254,6 +467,78 @@ extern "C" int b2_lzw_encode(b2_ctx* ctx, const uint8_t* raw, const b2_enc_desc*
     lzw_encode_kernel<<<ctas, 32, 0, s>>>(raw, descs, n, out, out_len, counter);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b2_lzw_encode_restart(b2_ctx* ctx, const uint8_t* raw, const b2_enc_desc* descs_host, int n, uint32_t restart_bytes,
+                                     uint8_t* out, uint32_t* out_len, b2_stream stream) {
+    B2_REQUIRE(ctx && raw && descs_host && out && out_len, "b2_lzw_encode_restart: NULL argument");
+    B2_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "b2_lzw_encode_restart: out must be 16-byte aligned (and every dst_off a multiple of 4)");
+    B2_REQUIRE(restart_bytes >= 16 && restart_bytes <= (uint32_t)kSegMaxRestart && restart_bytes % 16 == 0,
+               "b2_lzw_encode_restart: restart_bytes must be a multiple of 16 in [16, 1024]");
+    if (n <= 0) return 0;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    std::vector<uint32_t> seg_start((size_t)n + 1);
+    uint64_t segs = 0;
+    for (int i = 0; i < n; i++) {
+        B2_REQUIRE(descs_host[i].dst_off % 4 == 0, "b2_lzw_encode_restart: dst_off must be a multiple of 4");
+        B2_REQUIRE(descs_host[i].src_len < (1u << 28), "b2_lzw_encode_restart: src_len must be below 2^28");
+        seg_start[i] = (uint32_t)segs;
+        const uint64_t k = ((uint64_t)descs_host[i].src_len + restart_bytes - 1) / restart_bytes;
+        segs += k ? k : 1;
+        B2_REQUIRE(segs < (1ull << 31), "b2_lzw_encode_restart: too many pieces for one call");
+    }
+    seg_start[n] = (uint32_t)segs;
+    // every code is at most 12 bits and a piece has at most restart + 1 codes besides the leading Clear; + one spare word
+    const uint32_t slot_words = ((restart_bytes + 3) * 12 + 31) / 32 + 1;
+    // tiles are encoded in groups whose scratch stays under 256 MiB
+    const uint64_t budget_segs = std::max<uint64_t>(1, (256ull << 20) / (slot_words * 4ull));
+    uint64_t group_max = 0;
+    for (int t0 = 0; t0 < n;) {
+        int t1 = t0 + 1;
+        while (t1 < n && seg_start[t1 + 1] - seg_start[t0] <= budget_segs) t1++;
+        group_max = std::max<uint64_t>(group_max, seg_start[t1] - seg_start[t0]);
+        t0 = t1;
+    }
+    const size_t off_descs = 256, off_start = off_descs + (((size_t)n * sizeof(b2_enc_desc) + 255) & ~(size_t)255);
+    const size_t off_bits = off_start + (((size_t)(n + 1) * 4 + 255) & ~(size_t)255);
+    const size_t off_pos = off_bits + ((group_max * 4 + 255) & ~(size_t)255);
+    const size_t off_scratch = off_pos + ((group_max * 4 + 255) & ~(size_t)255);
+    WsLock ws_lock(ctx);
+    if (int e = ws_reserve(ctx, off_scratch + group_max * slot_words * 4ull + 256, s)) return e;
+    uint8_t* ws = static_cast<uint8_t*>(ctx->ws);
+    B2_CUDA(cudaMemcpyAsync(ws + off_descs, descs_host, (size_t)n * sizeof(b2_enc_desc), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(ws + off_start, seg_start.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaStreamSynchronize(s));                                  // the host arrays are read by the copies above
+    static bool attr_done = false;
+    const int smem = kSegWarps * kSegLanes * kSegSlots * 4;
+    if (!attr_done) {
+        B2_CUDA(cudaFuncSetAttribute(lzw_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    SegArgs a{raw, reinterpret_cast<const b2_enc_desc*>(ws + off_descs), reinterpret_cast<const uint32_t*>(ws + off_start), 0, 0, 0, 0,
+              restart_bytes, slot_words, reinterpret_cast<uint32_t*>(ws + off_scratch), reinterpret_cast<uint32_t*>(ws + off_bits),
+              reinterpret_cast<uint32_t*>(ws + off_pos), reinterpret_cast<unsigned int*>(ws), out, out_len};
+    for (int t0 = 0; t0 < n;) {
+        int t1 = t0 + 1;
+        while (t1 < n && seg_start[t1 + 1] - seg_start[t0] <= budget_segs) t1++;
+        a.tile0 = (uint32_t)t0;
+        a.tile1 = (uint32_t)t1;
+        a.seg0 = seg_start[t0];
+        a.seg1 = seg_start[t1];
+        B2_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), s));
+        const uint32_t pieces = a.seg1 - a.seg0;
+        unsigned ctas = (pieces + kSegWarps * kSegLanes - 1) / (kSegWarps * kSegLanes);
+        if (ctas > (unsigned)ctx->sm_count) ctas = (unsigned)ctx->sm_count;
+        lzw_segment_kernel<<<ctas, kSegWarps * 32, smem, s>>>(a);
+        unsigned cat = (unsigned)(t1 - t0);
+        if (cat > (unsigned)ctx->sm_count * 8) cat = (unsigned)ctx->sm_count * 8;
+        lzw_concat_kernel<<<cat, kCatThreads, 0, s>>>(a);
+        ctx->launches += 2;
+        B2_CUDA(cudaGetLastError());
+        t0 = t1;
+    }
     return 0;
 }
 

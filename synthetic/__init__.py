@@ -36,19 +36,20 @@ def _clib():
     global _lib
     if _lib is None:
         L = ctypes.CDLL(build())
-        L.syn_lzw_encode.restype = ctypes.c_int64
-        L.syn_lzw_encode.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+        L.syn_lzw_encode_restart.restype = ctypes.c_int64
+        L.syn_lzw_encode_restart.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t]
         L.syn_hdiff.restype = None
         L.syn_hdiff.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
         _lib = L
     return _lib
 
 
-def lzw_encode(data: bytes) -> bytes:
+def lzw_encode(data: bytes, restart: int = 0) -> bytes:
+    """TIFF-LZW (MSB first, early change, Clear at 4094 entries); restart > 0: a Clear every `restart` input bytes too."""
     s = np.frombuffer(data, dtype=np.uint8)
     cap = 2 * s.size + 64
     out = np.empty(cap, dtype=np.uint8)
-    n = _clib().syn_lzw_encode(s.ctypes.data, s.size, out.ctypes.data, cap)
+    n = _clib().syn_lzw_encode_restart(s.ctypes.data, s.size, out.ctypes.data, cap, int(restart))
     assert n >= 0
     return out[:n].tobytes()
 
@@ -58,7 +59,7 @@ _SF = {"u": 1, "i": 2, "f": 3}
 
 
 def tiff_bytes(arr, tile=256, compression="lzw", predictor=1, planar=1, big_endian=False,
-               rows_per_strip=None, nodata=None, geo=True, zlevel=6, photometric=None):
+               rows_per_strip=None, nodata=None, geo=True, zlevel=6, photometric=None, lzw_restart=0):
     """(H,W,B) or (H,W) array -> TIFF file bytes.  tile=None -> strips."""
     arr = np.asarray(arr)
     if arr.ndim == 2:
@@ -89,7 +90,7 @@ def tiff_bytes(arr, tile=256, compression="lzw", predictor=1, planar=1, big_endi
                     _clib().syn_hdiff(blk.ctypes.data, rows, bw * spb, spb, dt.itemsize)
                 raw = blk.astype(dt.newbyteorder(bo)).tobytes()
                 if comp == 5:
-                    raw = lzw_encode(raw)
+                    raw = lzw_encode(raw, lzw_restart)
                 elif comp == 8:
                     raw = zlib.compress(raw, zlevel)
                 blocks.append(raw)

@@ -19,7 +19,8 @@ static void put(bitw* w, uint32_t code, int nb) {
     }
 }
 
-int64_t syn_lzw_encode(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) {
+/* restart > 0: an additional Clear code every `restart` input bytes (any TIFF-LZW reader accepts a Clear anywhere) */
+int64_t syn_lzw_encode_restart(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t restart) {
     enum { CLEAR = 256, EOI = 257, FIRST = 258, LIMIT = 4094 };
     static __thread int16_t child[4096], sib[4096];
     static __thread uint8_t ch[4096];
@@ -27,9 +28,11 @@ int64_t syn_lzw_encode(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) {
     int nbits = 9, next = FIRST;
     memset(child, 0xff, sizeof child);
     put(&w, CLEAR, nbits);
-    if (n) {
-        int cur = src[0];
-        for (size_t i = 1; i < n; i++) {
+    size_t pos = 0;
+    while (pos < n) {
+        const size_t end = restart && n - pos > restart ? pos + restart : n;
+        int cur = src[pos];
+        for (size_t i = pos + 1; i < end; i++) {
             uint8_t c = src[i];
             int k = child[cur];
             while (k >= 0 && ch[k] != c) k = sib[k];
@@ -50,10 +53,20 @@ int64_t syn_lzw_encode(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) {
         next++;
         if (next == LIMIT) { put(&w, CLEAR, nbits); nbits = 9; }
         else if (next > (1 << nbits) - 1 && nbits < 12) nbits++;
+        pos = end;
+        if (pos < n) {                                   /* a restart: Clear in the current width, fresh table */
+            put(&w, CLEAR, nbits);
+            memset(child, 0xff, sizeof child);
+            nbits = 9; next = FIRST;
+        }
     }
     put(&w, EOI, nbits);
     if (w.nacc) put(&w, 0, 8 - w.nacc);
     return w.fail ? -1 : (int64_t)w.o;
+}
+
+int64_t syn_lzw_encode(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) {
+    return syn_lzw_encode_restart(src, n, dst, cap, 0);
 }
 
 /* horizontal differencing (predictor 2), in place, host-order words */

@@ -26,19 +26,36 @@ def _cases():
     yield lab.tobytes()
 
 
-def test_lzw_encode_is_byte_identical_with_the_cpu_encoder_and_round_trips(dev):
+@pytest.mark.parametrize("restart", [0, 1024, 16, 400])
+def test_lzw_encode_is_byte_identical_with_the_cpu_encoder_and_round_trips(dev, restart):
+    """restart 0: the classic stream (Clear only when the table is full); otherwise a Clear every `restart` input bytes —
+    the pieces are encoded independently on the device and shifted together; 1024 is what the writer uses."""
     import torch
 
     from dl_image_segmentation_b200 import _geotiff
     msgs = list(_cases())
+    if restart:
+        rng = np.random.default_rng(restart)
+        msgs += [bytes(restart), bytes(restart + 1), bytes(restart - 1), rng.integers(0, 256, 3 * restart, dtype=np.uint8).tobytes()]
     buf = bytearray()
     for m in msgs:
         buf += m + bytes((-len(m)) % 16)
     raw = torch.from_numpy(np.frombuffer(bytes(buf) or b"\0" * 16, np.uint8).copy()).to(dev)
-    got = _geotiff.lzw_encode_tiles(raw, [len(m) for m in msgs], dev)
+    got = _geotiff.lzw_encode_tiles(raw, [len(m) for m in msgs], dev, restart=restart)
     for m, g in zip(msgs, got):
-        assert g == syn.lzw_encode(m), len(m)
+        assert g == syn.lzw_encode(m, restart), len(m)
         assert oic.lzw_decode(g, len(m)) == m                              # oracle decoder (TIFF 6.0 section 13)
+
+
+def test_lzw_restart_rejects_bad_intervals(dev):
+    import torch
+
+    from dl_image_segmentation_b200 import _geotiff
+    from dl_image_segmentation_b200._lib import B2Error
+    raw = torch.zeros(64, dtype=torch.uint8, device=dev)
+    for bad in (8, 1000, 2048):
+        with pytest.raises(B2Error):
+            _geotiff.lzw_encode_tiles(raw, [40], dev, restart=bad)
 
 
 @pytest.mark.parametrize("shape,dtype,nodata", [((512, 512, 4), np.uint16, None), ((512, 512), np.uint8, 255),
@@ -59,7 +76,7 @@ def test_geotiff_files_match_the_fixture_writer_and_libtiff_reads_them(dev, shap
         arr = arr.reshape(shape)
     (blob,) = _geotiff.encode_geotiffs([torch.from_numpy(arr).to(dev) if dtype != np.uint16 else torch.from_numpy(arr.view(np.int16)).to(dev).view(torch.uint16)],
                                        nodata=nodata, device=dev)
-    want = syn.tiff_bytes(arr, tile=256, nodata=nodata)
+    want = syn.tiff_bytes(arr, tile=256, nodata=nodata, lzw_restart=_geotiff.LZW_RESTART)
     assert blob == want                                                    # same bytes as the fixture writer
     a3 = arr if arr.ndim == 3 else arr[:, :, None]
     np.testing.assert_array_equal(oic.decode_image(blob), a3)              # oracle decoder
@@ -101,3 +118,20 @@ def test_write_chip_pair_feeds_the_translator(dev, tmp_path):
     assert sorted(oep.parse_example(r)["identifier"][1][0].decode() for r in recs) == sorted(keys)
     f = oep.parse_example(recs[0])
     assert f["image/channels"][1] == [4] and f["image/image_data"][0] == "float"
+
+
+def test_lzw_restart_large_batch_spans_several_scratch_groups(dev):
+    """More pieces than one 256 MiB scratch group holds (the library encodes the tiles group by group): every stream must
+    still be the fixture encoder's, including tiles of different lengths side by side."""
+    import torch
+
+    from dl_image_segmentation_b200 import _geotiff
+    rng = np.random.default_rng(5)
+    base = [rng.integers(0, 256, 524288, dtype=np.uint8).tobytes(), bytes(65536), rng.integers(0, 3, 70001, dtype=np.uint8).tobytes()]
+    want = [syn.lzw_encode(m, 1024) for m in base]
+    n = 720                                                                # 240 x (512 + 64 + 69) pieces x 1.5 KiB > 256 MiB
+    msgs = [base[i % 3] for i in range(n)]
+    raw = torch.from_numpy(np.frombuffer(b"".join(m + bytes((-len(m)) % 16) for m in msgs), np.uint8).copy()).to(dev)
+    got = _geotiff.lzw_encode_tiles(raw, [len(m) for m in msgs], dev, restart=1024)
+    for i, g in enumerate(got):
+        assert g == want[i % 3], i

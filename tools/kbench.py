@@ -123,6 +123,9 @@ def bench_decode(dev, kind, n_distinct=16, reps=None):
         if kind == "lzw":
             img, lab, _ = syn.cfg3_chip(i)
             blobs += [syn.tiff_bytes(img, tile=256), syn.tiff_bytes(lab, tile=256, nodata=255)]
+        elif kind == "lzw_restart":                  # what the GeoTIFF writer produces: a Clear every 1024 input bytes
+            img, lab, _ = syn.cfg3_chip(i)
+            blobs += [syn.tiff_bytes(img, tile=256, lzw_restart=1024), syn.tiff_bytes(lab, tile=256, nodata=255, lzw_restart=1024)]
         elif kind == "lzw_strips_pred2":
             img, lab, _ = syn.cfg3_chip(i)
             blobs += [syn.tiff_bytes(img, tile=None, predictor=2, photometric=2), syn.tiff_bytes(lab, tile=None, predictor=2)]
@@ -378,6 +381,14 @@ def bench_encode_kernel(dev):
 
         def fn(i):
             check(lib().b2_lzw_encode(ctx.handle, ptr(raw), ptr(d_dev), n, ptr(out), ptr(out_len), ctx.stream()))
+        def fn_r(i):
+            check(lib().b2_lzw_encode_restart(ctx.handle, ptr(raw), descs.ctypes.data, n, 1024, ptr(out), ptr(out_len), ctx.stream()))
+        ms = timeit(fn_r, 3, warmup=1)
+        comp = int(out_len.cpu().numpy().view(np.uint32).astype(np.int64).sum())
+        report("lzw restart-1024 encode (segment + concat kernels) %d tiles of 512 KiB" % n, ms, n * tb + comp,
+               {"raw_GB/s": round(n * tb / ms / 1e6, 2), "tiles_per_s": round(n / ms * 1e3, 1),
+                "cycles_per_byte_per_thread_at_1.9GHz": round(ms * 1e-3 * 1.9e9 / (n * tb / min(n * 512, 148 * 28)), 1),
+                "compressed_fraction": round(comp / (n * tb), 3)})
         ms = timeit(fn, 2, warmup=1)
         comp = int(out_len.cpu().numpy().view(np.uint32).astype(np.int64).sum())
         report("lzw_encode_kernel %d tiles of 512 KiB" % n, ms, n * tb + comp,
@@ -433,7 +444,7 @@ def main():
         bench_jpeg(dev)
     if "jpeg_encode" in which:
         bench_jpeg_encode(dev)
-    for kind in ("lzw", "lzw_strips_pred2", "deflate", "png", "png_images", "png_labels"):
+    for kind in ("lzw", "lzw_restart", "lzw_strips_pred2", "deflate", "png", "png_images", "png_labels"):
         if kind in which or "decode" in which:
             bench_decode(dev, kind)
 
