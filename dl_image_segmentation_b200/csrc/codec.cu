@@ -18,6 +18,9 @@
 //   DEFLATE: every lane decodes the same Huffman symbols (uniform control flow, no broadcasts), literals are
 //            gathered 32 at a time into one coalesced store, and LZ77 matches are copied by the whole warp.
 //   PNG    : anti-diagonal wavefront, one lane per scanline of a 32-row band (left / up / up-left dependencies).
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <cstring>
 #include <vector>
 
@@ -1756,6 +1759,55 @@ const int kAdam7[7][4] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}
 
 // CRC-32 (IEEE 802.3, the PNG chunk CRC), slice-by-8.  libpng treats a CRC mismatch in a critical chunk (IHDR, IDAT)
 // as a fatal error, so tf.image.decode_png / GDAL fail on such a file and the reference skips it: so do we.
+#if defined(__x86_64__)
+// CRC-32 (zlib polynomial, reflected) of n bytes (n >= 64, n % 16 == 0) continuing state c: four 128-bit lanes folded 64
+// bytes at a time with PCLMULQDQ, then into one lane, 128 -> 64 -> 32 bits by Barrett reduction.  Constants: x^(512+64),
+// x^512, x^(128+64), x^128, x^64 mod P in the reflected domain, then mu and P (Gopal et al., "Fast CRC computation for
+// generic polynomials using PCLMULQDQ").  Checked against the table version for every length in tests/.
+__attribute__((target("pclmul,sse4.1")))
+uint32_t crc32_clmul(uint32_t c, const uint8_t* p, uint64_t n) {
+    const __m128i k1k2 = _mm_set_epi64x(0x01c6e41596ll, 0x0154442bd4ll);
+    const __m128i k3k4 = _mm_set_epi64x(0x00ccaa009ell, 0x01751997d0ll);
+    const __m128i k5k0 = _mm_set_epi64x(0, 0x0163cd6124ll);
+    const __m128i poly = _mm_set_epi64x(0x01f7011641ll, 0x01db710641ll);
+#define B2_LD128(q) _mm_loadu_si128(reinterpret_cast<const __m128i*>(q))
+#define B2_FOLD128(a, b) _mm_xor_si128(_mm_xor_si128(_mm_clmulepi64_si128((a), k3k4, 0x11), (b)), _mm_clmulepi64_si128((a), k3k4, 0x00))
+    __m128i x1 = _mm_xor_si128(B2_LD128(p), _mm_cvtsi32_si128((int)c)), x2 = B2_LD128(p + 16), x3 = B2_LD128(p + 32), x4 = B2_LD128(p + 48);
+    p += 64;
+    n -= 64;
+    while (n >= 64) {
+        const __m128i l1 = _mm_clmulepi64_si128(x1, k1k2, 0x00), l2 = _mm_clmulepi64_si128(x2, k1k2, 0x00);
+        const __m128i l3 = _mm_clmulepi64_si128(x3, k1k2, 0x00), l4 = _mm_clmulepi64_si128(x4, k1k2, 0x00);
+        x1 = _mm_xor_si128(_mm_xor_si128(_mm_clmulepi64_si128(x1, k1k2, 0x11), l1), B2_LD128(p));
+        x2 = _mm_xor_si128(_mm_xor_si128(_mm_clmulepi64_si128(x2, k1k2, 0x11), l2), B2_LD128(p + 16));
+        x3 = _mm_xor_si128(_mm_xor_si128(_mm_clmulepi64_si128(x3, k1k2, 0x11), l3), B2_LD128(p + 32));
+        x4 = _mm_xor_si128(_mm_xor_si128(_mm_clmulepi64_si128(x4, k1k2, 0x11), l4), B2_LD128(p + 48));
+        p += 64;
+        n -= 64;
+    }
+    x1 = B2_FOLD128(x1, x2);
+    x1 = B2_FOLD128(x1, x3);
+    x1 = B2_FOLD128(x1, x4);
+    while (n >= 16) {
+        x2 = B2_LD128(p);
+        x1 = B2_FOLD128(x1, x2);
+        p += 16;
+        n -= 16;
+    }
+    const __m128i lo32 = _mm_setr_epi32(~0, 0, ~0, 0);
+    x2 = _mm_clmulepi64_si128(x1, k3k4, 0x10);                            // 128 -> 64 bits
+    x1 = _mm_xor_si128(_mm_srli_si128(x1, 8), x2);
+    x2 = _mm_srli_si128(x1, 4);
+    x1 = _mm_xor_si128(_mm_clmulepi64_si128(_mm_and_si128(x1, lo32), k5k0, 0x00), x2);
+    x2 = _mm_clmulepi64_si128(_mm_and_si128(x1, lo32), poly, 0x10);      // Barrett
+    x2 = _mm_clmulepi64_si128(_mm_and_si128(x2, lo32), poly, 0x00);
+    x1 = _mm_xor_si128(x1, x2);
+    return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+#undef B2_LD128
+#undef B2_FOLD128
+#endif
+
 struct PngCrc {
     uint32_t t[8][256];
     PngCrc() {
@@ -1767,8 +1819,7 @@ struct PngCrc {
         for (uint32_t i = 0; i < 256; i++)
             for (int s = 1; s < 8; s++) t[s][i] = (t[s - 1][i] >> 8) ^ t[0][t[s - 1][i] & 0xFF];
     }
-    uint32_t run(const uint8_t* p, uint64_t n) const {
-        uint32_t c = 0xFFFFFFFFu;
+    uint32_t update(uint32_t c, const uint8_t* p, uint64_t n) const {       // c = running state (inverted CRC)
         while (n >= 8) {
             uint32_t a, b;
             memcpy(&a, p, 4);
@@ -1780,7 +1831,22 @@ struct PngCrc {
             n -= 8;
         }
         while (n--) c = (c >> 8) ^ t[0][(c ^ *p++) & 0xFF];
-        return ~c;
+        return c;
+    }
+    uint32_t run(const uint8_t* p, uint64_t n) const {
+        uint32_t c = 0xFFFFFFFFu;
+#if defined(__x86_64__)
+        // the IDAT checksums are the largest item of the PNG planner's host time (1.4 GB/s per core through the tables):
+        // carry-less multiplication folds 64 bytes per step (6 GB/s)
+        static const bool clmul = __builtin_cpu_supports("pclmul") && __builtin_cpu_supports("sse4.1");
+        if (clmul && n >= 64) {
+            const uint64_t m = n & ~15ull;
+            c = crc32_clmul(c, p, m);
+            p += m;
+            n -= m;
+        }
+#endif
+        return ~update(c, p, n);
     }
 };
 const PngCrc kPngCrc;

@@ -368,7 +368,8 @@ def bench_encode_kernel(dev):
             for tx in range(2):
                 tiles.append(np.ascontiguousarray(img[ty * 256:(ty + 1) * 256, tx * 256:(tx + 1) * 256]).view(np.uint8).reshape(-1))
     tb = tiles[0].size
-    for n in (8, 64, 1024, 4096):
+    only = os.environ.get("B2_KBENCH_ENC_N")                         # e.g. "64": one batch size, restart encoder only (for ncu)
+    for n in ((int(only),) if only else (8, 64, 1024, 4096)):
         raw = torch.from_numpy(np.concatenate([tiles[i % len(tiles)] for i in range(n)])).to(dev)
         cap = tb * 3 // 2 + 64
         descs = np.zeros(n, _geotiff.ENC_DESC_DTYPE)
@@ -389,6 +390,8 @@ def bench_encode_kernel(dev):
                {"raw_GB/s": round(n * tb / ms / 1e6, 2), "tiles_per_s": round(n / ms * 1e3, 1),
                 "cycles_per_byte_per_thread_at_1.9GHz": round(ms * 1e-3 * 1.9e9 / (n * tb / min(n * 512, 148 * 28)), 1),
                 "compressed_fraction": round(comp / (n * tb), 3)})
+        if only:
+            continue
         ms = timeit(fn, 2, warmup=1)
         comp = int(out_len.cpu().numpy().view(np.uint32).astype(np.int64).sum())
         report("lzw_encode_kernel %d tiles of 512 KiB" % n, ms, n * tb + comp,
