@@ -183,12 +183,19 @@ lzw_encode_kernel(const uint8_t* __restrict__ raw, const b2_enc_desc* __restrict
 // TIFF-LZW allows a Clear code anywhere.  With a Clear every R input bytes (R <= 1024) the pieces of a tile between two
 // Clears are independent LZW streams: a tile of 512 KiB is 512 of them instead of one serial walk, the dictionary of a
 // piece has at most R entries, so its hash table is 8 KiB instead of 24 (28 of them per SM, each owned by ONE thread —
-// the serial walk has nothing for the other 31 lanes of a warp to do), and codes stay 9-11 bits wide.  Two kernels:
-// lzw_segment_kernel encodes every piece into a scratch slot (bit-packed 32-bit words, MSB first) and records its length
-// in bits; lzw_concat_kernel scans the lengths of a tile and shifts the pieces together into the final byte stream.
+// the serial walk has nothing for the other lanes of a warp to do), and codes stay 9-11 bits wide.  Two kernels:
+//   lzw_segment_kernel  the serial part, as short as it gets: probe, and on a miss store the code as a 16-bit number and
+//                       insert.  No bit packing here: the width of the i-th code of a piece depends on i alone.
+//   lzw_pack_kernel     per tile: bit lengths of the pieces from their code counts (closed form), exclusive scan, then every
+//                       thread packs eight consecutive 32-bit words of the final stream from the 16-bit codes.
+// Two lanes per warp run a piece each (14 warps per CTA).  The walk is a chain of dependent instructions, ~35 per input byte
+// on noisy imagery (96 % of the steps are misses): with 7 lanes in each of 4 warps the lanes execute each other's probe
+// loops and miss paths and one warp per scheduler hides nothing (latency-bound, 410 cycles per byte-step, 19 GB/s); with
+// one lane in each of 28 warps the chains overlap but every instruction serves one byte (issue-bound at 79 %, 21 GB/s);
+// 2 x 14 measured best (26 GB/s; 4 x 7: 24.7).
 constexpr int kSegSlots = 2048;         // hash slots per piece: load <= 0.5
-constexpr int kSegLanes = 7;            // active lanes per warp ...
-constexpr int kSegWarps = 4;            // ... times warps = 28 private tables = 224 KiB of shared memory
+constexpr int kSegLanes = 2;            // active lanes per warp ...
+constexpr int kSegWarps = 14;           // ... times warps = 28 private tables = 224 KiB of shared memory
 constexpr int kSegMaxRestart = 1024;
 
 struct SegArgs {
@@ -197,10 +204,10 @@ struct SegArgs {
     const uint32_t* seg_start;          // [n + 1] first piece of every tile (global numbering)
     uint32_t tile0, tile1;              // this launch covers the pieces of tiles [tile0, tile1)
     uint32_t seg0, seg1;                // = seg_start[tile0], seg_start[tile1]
-    uint32_t restart, slot_words;
-    uint32_t* scratch;                  // (seg1 - seg0) slots
-    uint32_t* seg_bits;                 // bits produced per piece
-    uint32_t* seg_pos;                  // exclusive scan of seg_bits inside every tile
+    uint32_t restart, slot_codes;
+    uint16_t* scratch;                  // (seg1 - seg0) slots of slot_codes codes
+    uint32_t* seg_count;                // codes per piece
+    uint32_t* seg_pos;                  // exclusive scan of the pieces' bit lengths inside every tile
     unsigned int* counter;
     uint8_t* out;
     uint32_t* out_len;
@@ -209,10 +216,8 @@ struct SegArgs {
 __global__ void __launch_bounds__(kSegWarps * 32, 1)
 lzw_segment_kernel(const SegArgs a) {
     extern __shared__ __align__(16) uint32_t seg_tables[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane >= kSegLanes) return;
-    uint32_t* tab = seg_tables + (size_t)(warp * kSegLanes + lane) * kSegSlots;
-    enum { CLEAR = 256, EOI = 257, FIRST = 258 };
+    if ((threadIdx.x & 31) >= kSegLanes) return;
+    uint32_t* tab = seg_tables + (size_t)((threadIdx.x >> 5) * kSegLanes + (threadIdx.x & 31)) * kSegSlots;
     for (;;) {
         const uint32_t seg = a.seg0 + atomicAdd(a.counter, 1u);
         if (seg >= a.seg1) return;
@@ -223,27 +228,14 @@ lzw_segment_kernel(const SegArgs a) {
             if (__ldg(&a.seg_start[mid]) <= seg) lo_t = mid; else hi_t = mid;
         }
         const uint32_t k = seg - __ldg(&a.seg_start[lo_t]);
-        const bool last = seg + 1 == __ldg(&a.seg_start[lo_t + 1]);
         const b2_enc_desc d = a.descs[lo_t];
         const uint32_t lo = k * a.restart;
         const uint32_t cnt = d.src_len > lo ? min(a.restart, d.src_len - lo) : 0u;
         const uint8_t* p = a.raw + d.src_off + lo;
-        uint32_t* slot = a.scratch + (size_t)(seg - a.seg0) * a.slot_words;
+        uint16_t* codes = a.scratch + (size_t)(seg - a.seg0) * a.slot_codes;
         for (int q = 0; q < kSegSlots / 4; q++) reinterpret_cast<uint4*>(tab)[q] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-        uint64_t acc = 0;
-        int nacc = 0;
-        uint32_t o = 0;
-        auto put = [&](uint32_t code, int nb) {
-            acc = (acc << nb) | code;
-            nacc += nb;
-            if (nacc >= 32) {
-                slot[o++] = (uint32_t)(acc >> (nacc - 32));
-                nacc -= 32;
-            }
-        };
-        int nbits = 9;
-        uint32_t next = FIRST, cur = 0;
-        if (k == 0) put(CLEAR, 9);
+        uint32_t next = 258, cur = 0;                                   // next dictionary code = 258 + codes emitted
+        uint16_t* cp = codes;
         const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
         auto load16 = [&](uint32_t off) {
             if (aligned && off + 16 <= cnt) return ld_nc(reinterpret_cast<const uint4*>(p + off));
@@ -253,7 +245,7 @@ lzw_segment_kernel(const SegArgs a) {
         };
         auto step = [&](uint32_t c) {
             const uint32_t key = (cur << 8) | c;
-            uint32_t h = (key * 2654435761u) >> 21;                 // top 11 bits: 0 .. kSegSlots - 1
+            uint32_t h = (key * 2654435761u) >> 21;                     // top 11 bits: 0 .. kSegSlots - 1
             uint32_t e = tab[h];
             while (e != kEmpty && (e >> 11) != key) {
                 h = (h + 1) & (kSegSlots - 1);
@@ -261,13 +253,12 @@ lzw_segment_kernel(const SegArgs a) {
             }
             if (e != kEmpty) {
                 cur = e & 0x7FFu;
-                return;
+            } else {
+                *cp++ = (uint16_t)cur;
+                tab[h] = (key << 11) | next;
+                next++;
+                cur = c;
             }
-            put(cur, nbits);
-            tab[h] = (key << 11) | next;
-            next++;
-            cur = c;
-            if (next > (1u << nbits) - 1) nbits++;
         };
         if (cnt) {
             uint4 nxt = load16(0);
@@ -287,43 +278,44 @@ lzw_segment_kernel(const SegArgs a) {
                     }
                 }
             }
-            put(cur, nbits);
-            next++;                                                    // the entry the decoder adds after this code
-            if (next > (1u << nbits) - 1 && nbits < 12) nbits++;
+            *cp++ = (uint16_t)cur;
         }
-        put(last ? EOI : CLEAR, nbits);
-        const uint32_t bits = o * 32 + nacc;
-        if (nacc) slot[o] = (uint32_t)(acc << (32 - nacc));
-        a.seg_bits[seg - a.seg0] = bits;
+        a.seg_count[seg - a.seg0] = (uint32_t)(cp - codes);
     }
 }
 
-// bits [b, b + take) (take <= 32) of a piece stored as MSB-first 32-bit words
-__device__ __forceinline__ uint32_t seg_extract(const uint32_t* slot, uint32_t b, uint32_t take) {
-    const uint32_t w = b >> 5, sh = b & 31;
-    const uint32_t hi = slot[w], lo = sh ? slot[w + 1] : 0u;          // the slot has one spare word
-    const uint32_t v = __funnelshift_l(lo, hi, sh);
-    return take == 32 ? v : v >> (32 - take);
+// Widths inside a piece: the dictionary holds 258 + i codes when code i goes out, and the width grows one code early
+// ("early change"): codes 0..253 have 9 bits, 254..765 ten, from 766 eleven (a piece has at most 1025 codes).
+__device__ __forceinline__ uint32_t seg_code_bits(uint32_t i) { return i < 254 ? 9u : (i < 766 ? 10u : 11u); }
+__device__ __forceinline__ uint32_t seg_bits_before(uint32_t i) {      // bits of codes 0 .. i-1
+    return i <= 254 ? 9u * i : (i <= 766 ? 2286u + 10u * (i - 254) : 7406u + 11u * (i - 766));
+}
+__device__ __forceinline__ uint32_t seg_code_at(uint32_t x) {          // index of the code holding bit x
+    return x < 2286u ? x / 9u : (x < 7406u ? 254u + (x - 2286u) / 10u : 766u + (x - 7406u) / 11u);
+}
+// a piece in the final stream: [Clear, 9 bits, first piece of a tile only] codes [Clear | EOI in the width code n would have]
+__device__ __forceinline__ uint32_t seg_total_bits(uint32_t n, bool first) {
+    return (first ? 9u : 0u) + seg_bits_before(n) + seg_code_bits(n);
 }
 
 constexpr int kCatThreads = 256;
 constexpr int kCatWords = 8;            // consecutive output words per thread (one 32-byte sector)
 
 __global__ void __launch_bounds__(kCatThreads)
-lzw_concat_kernel(const SegArgs a) {
+lzw_pack_kernel(const SegArgs a) {
     __shared__ uint32_t warp_sum[kCatThreads / 32];
     __shared__ uint32_t carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t t = a.tile0 + blockIdx.x; t < a.tile1; t += gridDim.x) {
         const uint32_t s0 = a.seg_start[t] - a.seg0, nseg = a.seg_start[t + 1] - a.seg_start[t];
-        const uint32_t* bits = a.seg_bits + s0;
+        const uint32_t* count = a.seg_count + s0;
         uint32_t* pos = a.seg_pos + s0;
         __syncthreads();
         if (tid == 0) carry = 0;
         __syncthreads();
         for (uint32_t base = 0; base < nseg; base += kCatThreads) {      // exclusive scan, 256 pieces at a time
             const uint32_t i = base + tid;
-            const uint32_t v = i < nseg ? bits[i] : 0u;
+            const uint32_t v = i < nseg ? seg_total_bits(count[i], i == 0) : 0u;
             uint32_t x = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -351,39 +343,78 @@ lzw_concat_kernel(const SegArgs a) {
         const uint32_t nwords = (total + 31) >> 5;
         for (uint32_t j0 = (uint32_t)tid * kCatWords; j0 < nwords; j0 += kCatThreads * kCatWords) {
             // the piece holding bit 32 * j0: last k with pos[k] <= bit
-            uint32_t b = j0 << 5, lo = 0, hi = nseg;
+            const uint32_t b0 = j0 << 5;
+            uint32_t lo = 0, hi = nseg;
             while (hi - lo > 1) {
                 const uint32_t mid = (lo + hi) >> 1;
-                if (pos[mid] <= b) lo = mid; else hi = mid;
+                if (pos[mid] <= b0) lo = mid; else hi = mid;
             }
-            uint32_t k = lo, k_pos = pos[k], k_len = bits[k];
+            uint32_t k = lo, n = count[k];
+            const uint16_t* codes = a.scratch + (size_t)(s0 + k) * a.slot_codes;
+            // virtual code index inside the piece: -1 = the tile's leading Clear, 0 .. n-1 the stored codes, n the Clear / EOI
+            int i;
+            uint32_t skip;                                              // bits of that code already in earlier words
+            {
+                uint32_t off = b0 - pos[k];
+                if (k == 0) {
+                    if (off < 9) { i = -1; skip = off; }
+                    else { off -= 9; i = (int)min(seg_code_at(off), n); skip = off - seg_bits_before((uint32_t)i); }
+                } else {
+                    i = (int)min(seg_code_at(off), n);
+                    skip = off - seg_bits_before((uint32_t)i);
+                }
+            }
+            unsigned long long acc = 0;
+            uint32_t nacc = 0, made = 0;
             uint32_t vals[kCatWords];
 #pragma unroll
-            for (int q = 0; q < kCatWords; q++) {
-                uint32_t val = 0, need = 32;
-                while (need && k < nseg) {
-                    const uint32_t off = b - k_pos, avail = k_len - off;
-                    if (avail == 0) {
-                        k++;
-                        if (k < nseg) { k_pos = pos[k]; k_len = bits[k]; }
-                        continue;
-                    }
-                    const uint32_t take = min(need, avail);
-                    const uint32_t piece = seg_extract(a.scratch + (size_t)(s0 + k) * a.slot_words, off, take);
-                    val |= take == 32 ? piece : piece << (need - take);
-                    need -= take;
-                    b += take;
+            for (int q = 0; q < kCatWords; q++) vals[q] = 0;
+            while (made < kCatWords && k < nseg) {
+                uint32_t val, width;
+                if (i < 0) { val = 256; width = 9; }
+                else if ((uint32_t)i < n) { val = codes[i]; width = seg_code_bits((uint32_t)i); }
+                else { val = k + 1 == nseg ? 257u : 256u; width = seg_code_bits(n); }
+                if (skip) {
+                    width -= skip;
+                    val &= (1u << width) - 1u;
+                    skip = 0;
                 }
-                b += need;                                              // past the end of the stream: zero padding
-                vals[q] = __byte_perm(val, 0, 0x0123);                  // big-endian bit stream
+                acc = (acc << width) | val;
+                nacc += width;
+                if (nacc >= 32) {
+                    const uint32_t wv = (uint32_t)(acc >> (nacc - 32));
+#pragma unroll
+                    for (int q = 0; q < kCatWords; q++)
+                        if (q == (int)made) vals[q] = wv;
+                    made++;
+                    nacc -= 32;
+                }
+                if (i >= 0 && (uint32_t)i >= n) {                       // past this piece's last code: the next piece
+                    k++;
+                    if (k < nseg) {
+                        n = count[k];
+                        codes += a.slot_codes;
+                        i = 0;
+                    }
+                } else {
+                    i++;
+                }
+            }
+            if (made < kCatWords && nacc) {                             // the end of the stream: zero padding
+                const uint32_t wv = (uint32_t)(acc << (32 - nacc));
+#pragma unroll
+                for (int q = 0; q < kCatWords; q++)
+                    if (q == (int)made) vals[q] = wv;
+                made++;
             }
 #pragma unroll
             for (int q = 0; q < kCatWords; q++) {
                 const uint32_t j = j0 + q;
-                if (j >= nwords) break;
-                if (4 * j + 4 <= d.dst_cap) *reinterpret_cast<uint32_t*>(dst + 4 * (size_t)j) = vals[q];
+                if (q >= (int)made || j >= nwords) break;
+                const uint32_t be = __byte_perm(vals[q], 0, 0x0123);    // big-endian bit stream
+                if (4 * j + 4 <= d.dst_cap) *reinterpret_cast<uint32_t*>(dst + 4 * (size_t)j) = be;
                 else
-                    for (uint32_t z = 4 * j; z < nbytes; z++) dst[z] = (uint8_t)(vals[q] >> (8 * (z - 4 * j)));
+                    for (uint32_t z = 4 * j; z < nbytes; z++) dst[z] = (uint8_t)(be >> (8 * (z - 4 * j)));
             }
         }
     }
@@ -490,10 +521,10 @@ extern "C" int b2_lzw_encode_restart(b2_ctx* ctx, const uint8_t* raw, const b2_e
         B2_REQUIRE(segs < (1ull << 31), "b2_lzw_encode_restart: too many pieces for one call");
     }
     seg_start[n] = (uint32_t)segs;
-    // every code is at most 12 bits and a piece has at most restart + 1 codes besides the leading Clear; + one spare word
-    const uint32_t slot_words = ((restart_bytes + 3) * 12 + 31) / 32 + 1;
+    // a piece has at most restart codes (one per input byte), stored as 16-bit numbers; slots stay 16-byte aligned
+    const uint32_t slot_codes = restart_bytes + 8;
     // tiles are encoded in groups whose scratch stays under 256 MiB
-    const uint64_t budget_segs = std::max<uint64_t>(1, (256ull << 20) / (slot_words * 4ull));
+    const uint64_t budget_segs = std::max<uint64_t>(1, (256ull << 20) / (slot_codes * 2ull));
     uint64_t group_max = 0;
     for (int t0 = 0; t0 < n;) {
         int t1 = t0 + 1;
@@ -506,7 +537,7 @@ extern "C" int b2_lzw_encode_restart(b2_ctx* ctx, const uint8_t* raw, const b2_e
     const size_t off_pos = off_bits + ((group_max * 4 + 255) & ~(size_t)255);
     const size_t off_scratch = off_pos + ((group_max * 4 + 255) & ~(size_t)255);
     WsLock ws_lock(ctx);
-    if (int e = ws_reserve(ctx, off_scratch + group_max * slot_words * 4ull + 256, s)) return e;
+    if (int e = ws_reserve(ctx, off_scratch + group_max * slot_codes * 2ull + 256, s)) return e;
     uint8_t* ws = static_cast<uint8_t*>(ctx->ws);
     B2_CUDA(cudaMemcpyAsync(ws + off_descs, descs_host, (size_t)n * sizeof(b2_enc_desc), cudaMemcpyHostToDevice, s));
     B2_CUDA(cudaMemcpyAsync(ws + off_start, seg_start.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s));
@@ -518,7 +549,7 @@ extern "C" int b2_lzw_encode_restart(b2_ctx* ctx, const uint8_t* raw, const b2_e
         attr_done = true;
     }
     SegArgs a{raw, reinterpret_cast<const b2_enc_desc*>(ws + off_descs), reinterpret_cast<const uint32_t*>(ws + off_start), 0, 0, 0, 0,
-              restart_bytes, slot_words, reinterpret_cast<uint32_t*>(ws + off_scratch), reinterpret_cast<uint32_t*>(ws + off_bits),
+              restart_bytes, slot_codes, reinterpret_cast<uint16_t*>(ws + off_scratch), reinterpret_cast<uint32_t*>(ws + off_bits),
               reinterpret_cast<uint32_t*>(ws + off_pos), reinterpret_cast<unsigned int*>(ws), out, out_len};
     for (int t0 = 0; t0 < n;) {
         int t1 = t0 + 1;
@@ -534,7 +565,7 @@ extern "C" int b2_lzw_encode_restart(b2_ctx* ctx, const uint8_t* raw, const b2_e
         lzw_segment_kernel<<<ctas, kSegWarps * 32, smem, s>>>(a);
         unsigned cat = (unsigned)(t1 - t0);
         if (cat > (unsigned)ctx->sm_count * 8) cat = (unsigned)ctx->sm_count * 8;
-        lzw_concat_kernel<<<cat, kCatThreads, 0, s>>>(a);
+        lzw_pack_kernel<<<cat, kCatThreads, 0, s>>>(a);
         ctx->launches += 2;
         B2_CUDA(cudaGetLastError());
         t0 = t1;
