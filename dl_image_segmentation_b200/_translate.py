@@ -380,7 +380,11 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
     os.makedirs(output_directory, exist_ok=True)
     # host threads: this worker's share of the box's cores (one worker per GPU runs beside it, in this process or under
     # torchrun); more threads than cores only adds context switches — an 8-GPU box here has 4 cores per GPU
-    share = max(1, (os.cpu_count() or 1) // max(1, _workers_on_this_host()))
+    try:
+        cores = len(os.sched_getaffinity(0))                               # the cores this process may run on (taskset, cgroups)
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 1
+    share = max(1, cores // max(1, _workers_on_this_host()))
     io_threads = max(2, min(io_threads, share))
     plan_threads = max(2, min(16, share))
     write_threads = max(2, min(16, 2 * share))
