@@ -188,15 +188,18 @@ def take_staging(device=None):
     return pool.take()
 
 
-def reserve_staging(device, nbytes):
+def reserve_staging(device, nbytes, sets=6):
     """Grow every free staging set of the device to nbytes now (a worker calls this once, before its pipeline starts:
-    pinning memory later would stall every CUDA call of the process for the duration of the cudaHostAlloc)."""
+    pinning memory later would stall every CUDA call of the process for the duration of the cudaHostAlloc).  sets: how
+    many sets the caller's pipeline can hold at once (the pool only ever grows)."""
     ctx = get_ctx(device)
     with _pool_lock:
         pool = _staging.get(ctx.device.index)
         if pool is None:
             pool = _staging[ctx.device.index] = _StagingPool()
     with pool.lock:
+        while len(pool.sets) < sets:
+            pool.sets.append(_HostStaging())
         for hs in pool.sets:
             if not hs.pending and hs.stage.numel() < nbytes:
                 hs.wait()

@@ -397,9 +397,14 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
         # (pinned staging) — sized from the first pair
         batch_pairs = int(max(32, min(1024, (512 << 20) // max(1, pair_bytes))))
     # clean batches of decoded-array records, or of raw-file records that need no decode to be validated, skip per-chip Python
-    fast = bool(not png_to_jpg and path_key is not None and (store_as_array or validate is None))
+    fast = bool(not png_to_jpg and path_key is not None and (store_as_array or validate is None or fast_validate is not None))
+    # file-bytes records whose chips must decode before they are accepted (the threaded translator, :94-105): the files go up
+    # as they are for the records AND a planned copy of their compressed streams goes through the decoders for the verdict
+    check_decode = bool(fast and not store_as_array and validate is not None)
+    kAhead = 3                                                              # batches being read / planned ahead of the GPU
     if fast:
-        _codec.reserve_staging(ctx.device, int(pair_bytes * batch_pairs * 1.25) + (1 << 20))
+        _codec.reserve_staging(ctx.device, int(pair_bytes * batch_pairs * 1.25) + (1 << 20),
+                               sets=(kAhead + 2) * (2 if check_decode else 1))
     n_slots = 4                                                             # rotating pinned write-back buffers, kept per device
     cache = _worker_buffers.setdefault(ctx.device.index, {"pinned": [None] * n_slots, "reader": None})
     pinned = cache["pinned"]
@@ -409,7 +414,6 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
              for s in range(per)]
     shard_off = [0] * per
     shard_count = [0] * per
-    kAhead = 3                                                              # batches being read / planned ahead of the GPU
     state = {"counter": 0, "seq": 0}
     copy_stream = torch.cuda.Stream(ctx.device)
     trace = [] if os.environ.get("B2_TRANSLATE_TRACE") else None      # development aid: (seconds, event) per pipeline step
@@ -520,12 +524,14 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                 blobs, offs, sizes, clean = reader.read_into(paths, hs)     # straight into the pinned staging buffer
                 if clean and store_as_array:
                     planned = _codec.plan_blobs(blobs, ctx.device, png_as_tf, inplace=hs, threads=plan_threads)
+                elif clean and check_decode:                                # into a staging set of its own: hs keeps the files
+                    planned = _codec.plan_blobs(blobs, ctx.device, png_as_tf, threads=plan_threads)
                 elif clean:                                                 # raw-bytes records: the header fields only
                     infos = np.frombuffer(_codec.probe_blobs(blobs, png_as_tf=png_as_tf), dtype=_codec.IMAGE_INFO_DTYPE, count=len(paths))
                     clean = not infos["status"].any()
             except Exception:
                 planned, clean = None, False
-            if not clean or (store_as_array and planned is None):
+            if not clean or ((store_as_array or check_decode) and planned is None):
                 if planned is not None:
                     planned.release()
                 hs.pending = False
@@ -541,9 +547,9 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
             if bi + kAhead < len(batches):
                 pending.append(pool.submit(read_and_plan, batches[bi + kAhead]))  # kAhead batches ahead, one thread each
             b["runs"] = batches[bi]
-            if b["fast"] and store_as_array:
+            if b["fast"] and b["planned"] is not None:
                 b["job"] = _codec.decode_enqueue(b["planned"], ctx.device)
-            elif b["fast"]:                                                 # the files as they are: one upload of the staging buffer
+            if b["fast"] and not store_as_array:                            # the files as they are: one upload of the staging buffer
                 hs = b["hs"]
                 used = int(b["offs"][-1] + b["sizes"][-1]) + 16
                 b["dev"] = hs.stage[:used].to(ctx.device, non_blocking=True)
@@ -579,7 +585,7 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
             runs = b["runs"]
             if b["fast"]:
                 keys = b["keys"]
-                if store_as_array:
+                if b["planned"] is not None:
                     job = b["job"]
                     mark("wait status")
                     st = job.status()                                       # waits for this batch's decode only
@@ -626,9 +632,12 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
             for leftover in pending:
                 if leftover is not None:                                    # aborted with a read-ahead in flight: hand its
                     try:                                                    # pinned staging set back
-                        dropped = leftover.result().get("planned")
+                        res = leftover.result()
+                        dropped = res.get("planned")
                         if dropped is not None:
                             dropped.release()
+                        if res.get("hs") is not None and not store_as_array:
+                            res["hs"].pending = False                       # the set that holds the files themselves
                     except Exception:
                         pass
             if prev is not None and prev.get("planned") is not None:
