@@ -544,6 +544,7 @@ TF_JPEG_DENSITY = (1, 300, 300)    # tf.image.encode_jpeg's defaults: density_un
 _lib.register_signatures({
     "b2_jpeg_header": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _u64, ctypes.POINTER(_u64)]),
     "b2_jpeg_encode_sizes": (_i, [_i, _i, _i, ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
+    "b2_gather_ranges": (_i, [_vp, _vp, _vp, _vp, _vp, _i, ctypes.c_uint32, _vp, _vp]),
     "b2_jpeg_encode_scan": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _u64, _vp, _vp, _vp]),
 })
 
@@ -556,6 +557,70 @@ def jpeg_header(height, width, components, quality=100, density=TF_JPEG_DENSITY)
     return bytes(buf[:ln.value])
 
 
+def encode_jpeg_device(pixels, src_off, height, width, components, quality=100, density=TF_JPEG_DENSITY, device=None,
+                       timings=None):
+    """Baseline JPEG files of n uint8 images that already lie in ONE device buffer (image j: (height[j], width[j],
+    components[j]) pixels at pixels[src_off[j]:], components 1 or 3), assembled on the device: header + scan + EOI of every
+    file back to back (16-byte aligned) in one device buffer.  Returns (files buffer, offsets, sizes).  One small
+    device -> host read (the scan lengths) is the only synchronisation."""
+    ctx = get_ctx(device)
+    n = len(src_off)
+    shapes = np.stack([np.asarray(height, np.int64), np.asarray(width, np.int64), np.asarray(components, np.int64)], axis=1)
+    uniq, inv = np.unique(shapes, axis=0, return_inverse=True)
+    inv = inv.reshape(-1)
+    cc_u, cap_u, hdr_off, hdr_len, front = [], [], [], [], bytearray(b"\xff\xd9" + bytes(14))
+    cc, cap = _u64(), _u64()
+    for h, w, c in uniq:
+        if c not in (1, 3):
+            raise B2Error("encode_jpeg: (H,W,1) or (H,W,3) uint8 images only (tf.image.encode_jpeg, format='')")
+        check(lib().b2_jpeg_encode_sizes(int(h), int(w), int(c), ctypes.byref(cc), ctypes.byref(cap)))
+        cc_u.append(cc.value)
+        cap_u.append(cap.value)
+        hd = jpeg_header(int(h), int(w), int(c), quality, density)
+        hdr_off.append(len(front))
+        hdr_len.append(len(hd))
+        front += hd + bytes((-len(hd)) % 16)
+    cc_u, cap_u, hdr_off, hdr_len = (np.asarray(x, np.int64) for x in (cc_u, cap_u, hdr_off, hdr_len))
+    caps = (cap_u[inv] + 15) & ~15
+    jobs = np.zeros(n, JPEG_ENC_JOB_DTYPE)
+    jobs["src_off"] = np.asarray(src_off, np.uint64)
+    jobs["coef_off"] = np.concatenate(([0], np.cumsum(cc_u[inv])[:-1]))
+    jobs["out_off"] = np.concatenate(([0], np.cumsum(caps)[:-1]))
+    jobs["out_cap"] = cap_u[inv]
+    jobs["height"], jobs["width"], jobs["components"] = shapes[:, 0], shapes[:, 1], shapes[:, 2]
+    coef, nfront = int(cc_u[inv].sum()), len(front)
+    buf = torch.empty((nfront + int(caps.sum()) + 16,), dtype=torch.uint8, device=ctx.device)
+    buf[:nfront].copy_(torch.from_numpy(np.frombuffer(bytes(front), np.uint8).copy()), non_blocking=True)
+    jobs_d = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(ctx.device)
+    coef_d = torch.empty((max(coef, 1),), dtype=torch.int16, device=ctx.device)
+    len_d = torch.zeros((n,), dtype=torch.int32, device=ctx.device)
+    if timings is not None:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+    check(lib().b2_jpeg_encode_scan(ctx.handle, ptr(pixels), ptr(jobs_d), jobs.ctypes.data, n, int(quality), ptr(coef_d), coef,
+                                    ctypes.c_void_p(buf.data_ptr() + nfront), ptr(len_d), ctx.stream()))
+    if timings is not None:
+        ev[1].record()
+        torch.cuda.synchronize()
+        timings.update(encode_ms=ev[0].elapsed_time(ev[1]))
+    lens = len_d.cpu().numpy().view(np.uint32).astype(np.int64)
+    if (lens == 0xFFFFFFFF).any():
+        raise B2Error("b2_jpeg_encode_scan: scan buffer too small (its own bound)")
+    # header, scan (far shorter than its bound) and EOI of every file packed by ONE gather launch
+    sizes = hdr_len[inv] + lens + 2
+    offs = np.concatenate(([0], np.cumsum((sizes + 15) & ~15)[:-1]))
+    g_src = np.stack([hdr_off[inv], nfront + jobs["out_off"].astype(np.int64), np.zeros(n, np.int64)], axis=1).reshape(-1)
+    g_len = np.stack([hdr_len[inv], lens, np.full(n, 2, np.int64)], axis=1)
+    g_dst = (offs[:, None] + np.concatenate((np.zeros((n, 1), np.int64), np.cumsum(g_len, axis=1)[:, :2]), axis=1)).reshape(-1)
+    files = torch.empty((int(offs[-1] + ((sizes[-1] + 15) & ~15)) + 16,), dtype=torch.uint8, device=ctx.device)
+    so_d = torch.from_numpy(g_src.astype(np.uint64)).to(ctx.device)
+    do_d = torch.from_numpy(g_dst.astype(np.uint64)).to(ctx.device)
+    ln_d = torch.from_numpy(g_len.reshape(-1).astype(np.uint32)).to(ctx.device)
+    check(lib().b2_gather_ranges(ctx.handle, ptr(buf), ptr(so_d), ptr(do_d), ptr(ln_d), 3 * n, int(g_len.max()), ptr(files), ctx.stream()))
+    files.record_stream(torch.cuda.current_stream(ctx.device))
+    return files, offs.astype(np.uint64), sizes.astype(np.uint64)
+
+
 def encode_jpeg_arrays(arrays, quality=100, density=TF_JPEG_DENSITY, device=None, timings=None):
     """Encode a batch of (H,W,1) / (H,W,3) uint8 images (CUDA tensors or host arrays) as baseline JPEG files on the GPU
     -> list of bytes.  Replaces tf.image.encode_jpeg(image, format='', quality=100) behind ImageCoder.png_to_jpeg
@@ -564,51 +629,24 @@ def encode_jpeg_arrays(arrays, quality=100, density=TF_JPEG_DENSITY, device=None
     n = len(arrays)
     if n == 0:
         return []
-    jobs = np.zeros(n, JPEG_ENC_JOB_DTYPE)
-    flat = []
-    src = coef = out = 0
-    cc, cap = _u64(), _u64()
-    for j, a in enumerate(arrays):
+    flat, src_off, hs, ws, cs, src = [], [], [], [], [], 0
+    for a in arrays:
         t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
         if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] not in (1, 3):
             raise B2Error("encode_jpeg_arrays: (H,W,1) or (H,W,3) uint8 images only (tf.image.encode_jpeg, format='')")
         h, w, c = (int(x) for x in t.shape)
-        check(lib().b2_jpeg_encode_sizes(h, w, c, ctypes.byref(cc), ctypes.byref(cap)))
-        jobs[j] = (src, coef, out, cap.value, w, h, c)
         flat.append(t.to(ctx.device, non_blocking=True).contiguous().reshape(-1))
-        pad = (-t.numel()) % 16
-        if pad:
-            flat.append(torch.zeros((pad,), dtype=torch.uint8, device=ctx.device))
-        src += t.numel() + pad
-        coef += cc.value
-        out = _align(out + cap.value, 16)
+        src_off.append(src)
+        hs.append(h)
+        ws.append(w)
+        cs.append(c)
+        src += t.numel()
     pixels = torch.cat(flat)
-    jobs_d = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(ctx.device)
-    coef_d = torch.empty((coef,), dtype=torch.int16, device=ctx.device)
-    out_d = torch.empty((out,), dtype=torch.uint8, device=ctx.device)
-    len_d = torch.zeros((n,), dtype=torch.int32, device=ctx.device)
+    files, offs, sizes = encode_jpeg_device(pixels, src_off, hs, ws, cs, quality, density, ctx.device, timings)
     if timings is not None:
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        ev[0].record()
-    check(lib().b2_jpeg_encode_scan(ctx.handle, ptr(pixels), ptr(jobs_d), jobs.ctypes.data, n, int(quality), ptr(coef_d), coef,
-                                    ptr(out_d), ptr(len_d), ctx.stream()))
-    if timings is not None:
-        ev[1].record()
-        torch.cuda.synchronize()
-        timings.update(encode_ms=ev[0].elapsed_time(ev[1]), pixel_bytes=int(src))
-    lens = len_d.cpu().numpy().view(np.uint32)
-    if (lens == 0xFFFFFFFF).any():
-        raise B2Error("b2_jpeg_encode_scan: scan buffer too small (its own bound)")
-    # the scans are far shorter than their bound: pack them on the device, one copy to the host
-    packed = torch.cat([out_d[int(jobs[j]["out_off"]):int(jobs[j]["out_off"]) + int(lens[j])] for j in range(n)]).cpu().numpy()
-    files, o, headers = [], 0, {}
-    for j in range(n):
-        key = (int(jobs[j]["height"]), int(jobs[j]["width"]), int(jobs[j]["components"]))
-        if key not in headers:
-            headers[key] = jpeg_header(key[0], key[1], key[2], quality, density)
-        files.append(headers[key] + packed[o:o + int(lens[j])].tobytes() + b"\xff\xd9")
-        o += int(lens[j])
-    return files
+        timings.update(pixel_bytes=int(src))
+    host = files.cpu().numpy()
+    return [host[int(o):int(o + z)].tobytes() for o, z in zip(offs, sizes)]
 
 
 def to_float32(t):

@@ -397,10 +397,14 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
         # (pinned staging) — sized from the first pair
         batch_pairs = int(max(32, min(1024, (512 << 20) // max(1, pair_bytes))))
     # clean batches of decoded-array records, or of raw-file records that need no decode to be validated, skip per-chip Python
-    fast = bool(not png_to_jpg and path_key is not None and (store_as_array or validate is None or fast_validate is not None))
+    # convert_png_to_jpg with file-bytes records: decode, encode and assemble the JPEG files on the device; with array
+    # records (the pixels of the JPEG decoded again) the chip-by-chip path stays
+    to_jpg = bool(png_to_jpg and not store_as_array)
+    fast = bool((not png_to_jpg or to_jpg) and path_key is not None and
+                (store_as_array or validate is None or fast_validate is not None))
     # file-bytes records whose chips must decode before they are accepted (the threaded translator, :94-105): the files go up
     # as they are for the records AND a planned copy of their compressed streams goes through the decoders for the verdict
-    check_decode = bool(fast and not store_as_array and validate is not None)
+    check_decode = bool(fast and not store_as_array and validate is not None and not to_jpg)
     kAhead = 3                                                              # batches being read / planned ahead of the GPU
     if fast:
         _codec.reserve_staging(ctx.device, int(pair_bytes * batch_pairs * 1.25) + (1 << 20),
@@ -522,7 +526,7 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
             planned = infos = offs = sizes = None
             try:
                 blobs, offs, sizes, clean = reader.read_into(paths, hs)     # straight into the pinned staging buffer
-                if clean and store_as_array:
+                if clean and (store_as_array or to_jpg):
                     planned = _codec.plan_blobs(blobs, ctx.device, png_as_tf, inplace=hs, threads=plan_threads)
                 elif clean and check_decode:                                # into a staging set of its own: hs keeps the files
                     planned = _codec.plan_blobs(blobs, ctx.device, png_as_tf, threads=plan_threads)
@@ -531,7 +535,7 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                     clean = not infos["status"].any()
             except Exception:
                 planned, clean = None, False
-            if not clean or ((store_as_array or check_decode) and planned is None):
+            if not clean or ((store_as_array or check_decode or to_jpg) and planned is None):
                 if planned is not None:
                     planned.release()
                 hs.pending = False
@@ -549,7 +553,7 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
             b["runs"] = batches[bi]
             if b["fast"] and b["planned"] is not None:
                 b["job"] = _codec.decode_enqueue(b["planned"], ctx.device)
-            if b["fast"] and not store_as_array:                            # the files as they are: one upload of the staging buffer
+            if b["fast"] and not store_as_array and not to_jpg:             # the files as they are: one upload of the staging buffer
                 hs = b["hs"]
                 used = int(b["offs"][-1] + b["sizes"][-1]) + 16
                 b["dev"] = hs.stage[:used].to(ctx.device, non_blocking=True)
@@ -597,10 +601,21 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                 ok = ok and keys[0::2] == keys[1::2]
                 if ok and fast_validate is not None:
                     ok = bool(np.all(fast_validate(infos)))
+                if ok and to_jpg:                                           # tf.image.encode_jpeg takes 1 or 3 channels of uint8
+                    ok = bool(np.all((infos["samples"] != 2) & (infos["dtype"] == _lib_mod.B2_U8)))
                 if ok:
                     ids = [k.encode("utf-8") for k in keys[0::2]]
-                    rec = BatchRecords.from_decode(job, ids, ctx) if store_as_array else \
-                        BatchRecords.from_files(b["dev"], b["offs"], b["sizes"], infos, ids, ctx)
+                    if to_jpg:
+                        for _, lo, hi in runs:
+                            for i in range(lo, hi):
+                                print("Converting PNG to JPEG for %s" % img_filenames[i])
+                                print("Converting PNG to JPEG for %s" % lbl_filenames[i])
+                        files, foffs, fsizes = _codec.encode_jpeg_device(job.out, job.images["out_off"], infos["height"], infos["width"],
+                                                                         infos["samples"], quality=100, device=ctx.device)
+                        rec = BatchRecords.from_files(files, foffs, fsizes, infos, ids, ctx)
+                    else:
+                        rec = BatchRecords.from_decode(job, ids, ctx) if store_as_array else \
+                            BatchRecords.from_files(b["dev"], b["offs"], b["sizes"], infos, ids, ctx)
                     pieces, done, pos = [], [], 0
                     for s, lo, hi in runs:
                         pieces.append((s,) + rec.byte_range(pos, pos + hi - lo))
