@@ -11,7 +11,7 @@ from ._descartes_img_chips import (DLTileJobConfig, MaskedResult, SceneStack, Sy
 from ._tfrecord_image_translation import (convert_to_example, featuretemplate_bytestring_imagechip,  # noqa: F401
                                           featuretemplate_ndarray_imagechip, parse_8bit_array_proto,
                                           parse_encoded_gdal_proto_eager, parse_encoded_gdal_proto_wrapped,
-                                          parse_encoded_rgb_img_proto, parse_higher_dtype_array_proto)
+                                          parse_encoded_rgb_img_proto, parse_encoded_shard, parse_higher_dtype_array_proto)
 
 from ._geotiff import encode_geotiffs, write_chip_pair  # noqa: F401
 

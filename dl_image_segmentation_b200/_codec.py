@@ -119,7 +119,59 @@ class _HostStaging:
 
 
 _staging = {}
+_shard_staging = {}     # device index -> [two pinned sets, next]: whole shards on their way to the device (parse_encoded_shard)
 _pool_lock = threading.Lock()
+
+
+def shard_staging(device=None):
+    """One of two pinned staging sets kept for whole shards (alternating, so that the next shard can be read while the
+    previous one is still being uploaded); waits until its last upload has left it."""
+    ctx = get_ctx(device)
+    with _pool_lock:
+        ent = _shard_staging.setdefault(ctx.device.index, [[_HostStaging(), _HostStaging()], 0])
+        hs = ent[0][ent[1] & 1]
+        ent[1] += 1
+    hs.wait()
+    return hs
+
+
+def fill_pinned(hs, src, threads=8, spare=64):
+    """A file (path) or host bytes into hs.stage with a few threads (one core copies ~5 GB/s).  Returns the byte count."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    fd = None
+    if isinstance(src, (str, os.PathLike)):
+        fd = os.open(src, os.O_RDONLY)
+        n = os.fstat(fd).st_size
+    else:
+        src = _host_bytes(src)
+        n = int(src.size)
+    try:
+        dst = hs.ensure_stage(n + spare).numpy()
+        step = max(1 << 22, ((n + threads - 1) // max(1, threads) + 4095) & ~4095)
+        spans = [(o, min(n, o + step)) for o in range(0, n, step)]
+
+        def one(span):
+            o, e = span
+            if fd is None:
+                np.copyto(dst[o:e], src[o:e])
+            else:
+                mv = memoryview(dst)
+                while o < e:
+                    got = os.preadv(fd, [mv[o:e]], o)
+                    if got <= 0:
+                        raise OSError("short read")
+                    o += got
+        if len(spans) <= 1:
+            for sp in spans:
+                one(sp)
+        else:
+            with ThreadPoolExecutor(max_workers=threads) as pool:
+                list(pool.map(one, spans))
+    finally:
+        if fd is not None:
+            os.close(fd)
+    return n
 
 
 def _ptr_of(blob):
@@ -291,8 +343,10 @@ class DecodeJob:
         return np.frombuffer(self.infos, dtype=IMAGE_INFO_DTYPE, count=self.n)
 
 
-def decode_enqueue(pb, device=None, timings=None):
-    """Device half of decode_blobs without the wait: upload, decode kernels, assembly — all queued, nothing synchronised."""
+def decode_enqueue(pb, device=None, timings=None, blob_dev=None):
+    """Device half of decode_blobs without the wait: upload, decode kernels, assembly — all queued, nothing synchronised.
+    blob_dev: a device copy of the planned staging buffer that already exists (an in-place plan over an uploaded shard
+    whose blobs the planner did not have to compact): the bytes are not uploaded a second time."""
     ctx = get_ctx(device)
     job = DecodeJob()
     job.n, job.plan, job.infos, job.images = pb.n, pb.plan, pb.infos, pb.images
@@ -304,7 +358,9 @@ def decode_enqueue(pb, device=None, timings=None):
         return job
     hs = pb.hs
     ssz = STREAM_DESC_DTYPE.itemsize
-    blob_d = hs.stage[:plan.stage_bytes].to(ctx.device, non_blocking=True)
+    if blob_dev is not None and blob_dev.numel() < plan.stage_bytes:
+        raise B2Error("decode_enqueue: blob_dev is shorter than the planned staging buffer")
+    blob_d = blob_dev if blob_dev is not None else hs.stage[:plan.stage_bytes].to(ctx.device, non_blocking=True)
     sd_d = hs.streams[:plan.n_streams * ssz].to(ctx.device, non_blocking=True)
     im_d = torch.from_numpy(images.view(np.uint8).reshape(-1)).to(ctx.device, non_blocking=True)
     st_d = torch.from_numpy(pb.status).to(ctx.device, non_blocking=True)
@@ -340,13 +396,10 @@ def decode_enqueue(pb, device=None, timings=None):
     return job
 
 
-def decode_planned(pb, device=None, timings=None, want_infos=False):
-    """Device half of decode_blobs: upload, decode kernels, assembly.  Returns what decode_blobs returns."""
-    n, infos, images = pb.n, pb.infos, pb.images
+def job_arrays(job):
+    """(arrays, status) of a queued decode: waits for its status words; arrays[i] is a view of the job's output buffer."""
+    n, infos, images = job.n, job.infos, job.images
     arrays = [None] * n
-    if n == 0:
-        return (arrays, np.zeros(0, np.int32), []) if want_infos else (arrays, np.zeros(0, np.int32))
-    job = decode_enqueue(pb, device, timings)
     status = job.status()
     out = job.out
     for i in range(n):
@@ -357,7 +410,15 @@ def decode_planned(pb, device=None, timings=None, want_infos=False):
         nbytes = info.width * info.height * info.samples * bs
         o = int(images[i]["out_off"])
         arrays[i] = out[o:o + nbytes].view(_B2_TO_TORCH[info.dtype]).view(info.height, info.width, info.samples)
-    return (arrays, status, infos) if want_infos else (arrays, status)
+    return arrays, status
+
+
+def decode_planned(pb, device=None, timings=None, want_infos=False):
+    """Device half of decode_blobs: upload, decode kernels, assembly.  Returns what decode_blobs returns."""
+    if pb.n == 0:
+        return ([], np.zeros(0, np.int32), []) if want_infos else ([], np.zeros(0, np.int32))
+    arrays, status = job_arrays(decode_enqueue(pb, device, timings))
+    return (arrays, status, pb.infos) if want_infos else (arrays, status)
 
 
 def decode_blobs(blobs, device=None, timings=None, want_infos=False, png_as_tf=False):

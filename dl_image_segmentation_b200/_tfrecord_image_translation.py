@@ -231,3 +231,85 @@ def parse_encoded_gdal_proto_wrapped(example_proto, device=None):
     ib, _, tb, _, ident = _parse_byteslist_proto(example_proto, device)
     img, tgt = _decode_pair(ib, tb, device)
     return _codec.to_float32(img), _codec.to_float32(tgt), ident
+
+
+_ENCODED_PARSERS = {"rgb": "parse_encoded_rgb_img_proto", "gdal_eager": "parse_encoded_gdal_proto_eager",
+                    "gdal_wrapped": "parse_encoded_gdal_proto_wrapped"}
+
+
+def parse_encoded_shard(shard, parser="gdal_eager", verify_crc=True, device=None):
+    """All records of one shard of encoded-blob records (``store_as_array=False``) at once: what
+    ``TFRecordDataset(shard).map(parse_encoded_*_proto)`` yields record by record (reference :269-293, :319-386 — whose
+    docstring :122-126 names the per-record GDAL decode under the GIL as the input pipeline's bottleneck), with ONE frame
+    scan + feature index, ONE data-CRC pass and ONE batched decode of the 2n blobs.
+
+    shard: path, bytes or a host uint8 array.  parser: 'rgb' | 'gdal_eager' | 'gdal_wrapped' (the parse function it stands
+    for).  Returns a list of (img, target, identifier) exactly as the per-record function returns them; errors are the
+    per-record function's (DataLossError for a CRC mismatch, InvalidArgumentError for a record that does not fit the
+    template or a blob that does not decode)."""
+    import os
+
+    from . import _codec
+    if parser not in _ENCODED_PARSERS:
+        raise ValueError("parser must be one of %s" % sorted(_ENCODED_PARSERS))
+    ctx = ops.get_ctx(device)
+    # the shard goes into pinned memory once (a few threads), up to the device once, and — unless the planner has to move
+    # bytes (PNG IDAT payloads are compacted) — the decoders read the blobs where the uploaded shard has them
+    hs = _codec.shard_staging(ctx.device)
+    n_bytes = _codec.fill_pinned(hs, shard if isinstance(shard, (str, os.PathLike)) else
+                                 (np.frombuffer(shard, dtype=np.uint8) if isinstance(shard, (bytes, bytearray, memoryview)) else shard))
+    if n_bytes == 0:
+        return []
+    shard_d = hs.stage[:n_bytes + 64].to(ctx.device, non_blocking=True)      # + the decoders' look-ahead past the last blob
+    hs.busy = torch.cuda.Event()
+    hs.busy.record(torch.cuda.current_stream(ctx.device))
+    host = hs.stage.numpy()[:n_bytes]
+    si = ops.open_shard(shard_d, ctx.device, nbytes=n_bytes)
+    if si.n == 0:
+        return []
+    idx = si.index
+    check_index(idx, 1)
+    if verify_crc:
+        _, _, status = ops.parse_shard(si, "none", verify_crc=True)
+        st = status.cpu().numpy()
+        if (st == 1).any():
+            raise ops.DataLossError("corrupted record #%d (data CRC mismatch)" % int(np.nonzero(st == 1)[0][0]))
+    ids = si.identifiers(shard_host=host)
+    blobs = []
+    for r in idx:
+        blobs.append(host[int(r["img_off"]):int(r["img_off"]) + int(r["img_len"])])
+        blobs.append(host[int(r["tgt_off"]):int(r["tgt_off"]) + int(r["tgt_len"])])
+    as_tf = parser == "rgb"
+    hs.wait()                                                                # the upload has left the pinned buffer: it may change now
+    try:
+        pb = _codec.plan_blobs(blobs, ctx.device, as_tf, inplace=hs)
+        infos = np.frombuffer(pb.infos, dtype=_codec.IMAGE_INFO_DTYPE, count=pb.n)
+        untouched = not (infos["format"] == 2).any()
+    except B2Error:                                                          # palette PNGs: the gathering planner
+        pb, untouched = _codec.plan_blobs(blobs, ctx.device, as_tf), False
+    job = _codec.decode_enqueue(pb, ctx.device, blob_dev=shard_d if untouched else None)
+    arrays, status = _codec.job_arrays(job)
+    arrays, status, _ = _codec.merge_jpeg(blobs, arrays, status, pb.infos, ctx.device, candidates=np.nonzero(status)[0])   # .jpg blobs
+    bad = np.nonzero(np.asarray(status) != 0)[0]
+    if len(bad):
+        raise InvalidArgumentError("record %d: could not decode %s data (codec status %d)" %
+                                   (bad[0] // 2, ("image", "target")[bad[0] % 2], int(status[bad[0]])))
+    if parser == "gdal_eager":
+        for k, r in enumerate(idx):
+            img, tgt = arrays[2 * k], arrays[2 * k + 1]
+            assert tuple(img.shape) == (int(r["height"]), int(r["width"]), int(r["channels"]))             # reference :377
+            assert tgt.shape[0] == int(r["tgt_height"]) and tgt.shape[1] == int(r["tgt_width"])           # reference :383-384
+    elif parser == "gdal_wrapped":
+        # .astype(float32) of everything (reference :328-329): one cast launch per group of equal shape and dtype
+        groups = {}
+        for k, a in enumerate(arrays):
+            groups.setdefault((tuple(a.shape), a.dtype), []).append(k)
+        for ks in groups.values():
+            dt = arrays[ks[0]].dtype
+            signed = {getattr(torch, "uint16", None): torch.int16, getattr(torch, "uint32", None): torch.int32}.get(dt)
+            stacked = torch.stack([arrays[k] if signed is None else arrays[k].view(signed) for k in ks])   # plain copies
+            cast = _codec.to_float32(stacked if signed is None else stacked.view(dt))
+            for j, k in enumerate(ks):
+                arrays[k] = cast[j]
+    return [(arrays[2 * k], arrays[2 * k + 1], ids[k]) for k in range(si.n)]
+

@@ -2125,8 +2125,8 @@ extern "C" int b2_decode_plan_batch(const uint8_t* const* blobs, const uint64_t*
         b2_image_probe(blobs[i], sizes[i], flags, &info);
         if (info.status != 0) { status[i] = info.status; continue; }
         if (inplace) {
-            B2_REQUIRE(blobs[i] >= stage && blobs[i] + sizes[i] <= stage + stage_cap && ((blobs[i] - stage) & 15) == 0,
-                       "b2_decode_plan_batch: B2_PLAN_INPLACE blob outside the buffer or not 16-byte aligned in it");
+            B2_REQUIRE(blobs[i] >= stage && blobs[i] + sizes[i] <= stage + stage_cap,
+                       "b2_decode_plan_batch: B2_PLAN_INPLACE blob outside the buffer");
             B2_REQUIRE(!(info.format == 2 && info.png_color_type == 3), "b2_decode_plan_batch: palette PNGs need the gathering mode");
             stage_pos = (uint64_t)(blobs[i] - stage);
         }

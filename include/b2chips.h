@@ -232,8 +232,9 @@ typedef struct {
  * 8-bit grey, grey+alpha, RGB and RGBA are the same in both.  Adam7-interlaced files are decoded for bit depths 8 and
  * 16; interlaced 1/2/4-bit files are out of scope (status 3). */
 #define B2_PNG_AS_TF 1u
-/* b2_decode_plan_batch only: the blobs already lie (16-byte aligned) inside the staging buffer — b2_read_files put them
- * there — so nothing is gathered: the stream table points at the files in place and the whole buffer is uploaded. */
+/* b2_decode_plan_batch only: the blobs already lie inside the staging buffer (b2_read_files put them there 16-byte
+ * aligned; the blobs of the records of a shard lie wherever the shard has them) — so nothing is gathered: the stream
+ * table points at the files in place and the whole buffer is uploaded. */
 #define B2_PLAN_INPLACE 0x1000u
 
 /* Host-side header parse (TIFF IFD / PNG chunks); never touches the GPU. */

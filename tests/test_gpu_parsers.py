@@ -152,3 +152,69 @@ def test_uint16_mosaic_filled_and_noncontiguous_date_filter(dev):
     got = pkg.create_cloudmasked_s2_array("c", min_date=lo, max_date=hi, scene_source=src).to_masked_array()
     ref = ocomp.create_cloudmasked_s2_array(shuffled, st, va, None, lo, hi)
     assert np.array_equal(np.ma.getmaskarray(got), np.ma.getmaskarray(ref)) and np.array_equal(got.filled(0), ref.filled(0))
+
+
+def _shard_of(records):
+    from oracle import tfrecord as otfr
+    return b"".join(otfr.frame(r) for r in records)
+
+
+@pytest.mark.parametrize("parser", ["gdal_eager", "gdal_wrapped", "rgb"])
+def test_parse_encoded_shard_equals_the_per_record_parsers(dev, parser):
+    """The whole-shard form (one scan + index, one CRC pass, one batched decode) returns, record for record, what the
+    per-record parse function returns — and that is checked against the oracle's restatement of the reference parser."""
+    import dl_image_segmentation_b200 as pkg
+    recs = []
+    for i in range(7):
+        if parser == "rgb":
+            img, lab, key = syn.cfg1_chip(i, size=64 + 8 * (i % 2))          # two shapes in one shard
+            ib, lb = syn.png_bytes(img), syn.png_bytes(lab)
+            h, w, c = img.shape
+        else:
+            img, lab, key = syn.cfg3_chip(i, size=96)
+            kw = (dict(tile=32), dict(tile=None, predictor=2), dict(tile=32, compression="deflate"))[i % 3]
+            ib, lb = syn.tiff_bytes(img, **kw), syn.tiff_bytes(lab, nodata=255, **kw)
+            h, w, c = img.shape
+        recs.append(oep.convert_to_example(ib, lb, h, w, c, h, w, key).SerializeToString())
+    one = getattr(pkg, {"gdal_eager": "parse_encoded_gdal_proto_eager", "gdal_wrapped": "parse_encoded_gdal_proto_wrapped",
+                        "rgb": "parse_encoded_rgb_img_proto"}[parser])
+    ref = getattr(oep, one.__name__)
+    got = pkg.parse_encoded_shard(_shard_of(recs), parser=parser)
+    assert len(got) == len(recs)
+    for rec, (gi, gt, gid) in zip(recs, got):
+        si, st, sid = one(rec)
+        wi, wt, wid = ref(rec)
+        assert gid == sid == wid
+        assert gi.dtype == si.dtype and gt.dtype == st.dtype
+        _same(gi, wi)
+        _same(gt, wt)
+        _same(si, wi)
+
+
+def test_parse_encoded_shard_errors_are_the_per_record_ones(dev, tmp_path):
+    import dl_image_segmentation_b200 as pkg
+    from dl_image_segmentation_b200 import ops
+    from dl_image_segmentation_b200._tfrecord_image_translation import InvalidArgumentError
+    img, lab, key = syn.cfg3_chip(1, size=64)
+    ib, lb = syn.tiff_bytes(img, tile=32), syn.tiff_bytes(lab, tile=32)
+    good = oep.convert_to_example(ib, lb, 64, 64, 4, 64, 64, key).SerializeToString()
+    shard = bytearray(_shard_of([good, good]))
+    assert pkg.parse_encoded_shard(b"") == []
+    path = tmp_path / "s"
+    path.write_bytes(bytes(shard))
+    assert len(pkg.parse_encoded_shard(str(path))) == 2                       # a path works like the bytes
+    shard[len(shard) // 2 + 40] ^= 1                                          # inside the second record's payload
+    with pytest.raises(ops.DataLossError):
+        pkg.parse_encoded_shard(bytes(shard))
+    broken = oep.convert_to_example(ib[:len(ib) // 2], lb, 64, 64, 4, 64, 64, key).SerializeToString()   # truncated TIFF
+    with pytest.raises(InvalidArgumentError):
+        pkg.parse_encoded_shard(_shard_of([good, broken]))
+    wrong = oep.convert_to_example(ib, lb, 64, 60, 4, 64, 64, key).SerializeToString()
+    with pytest.raises(AssertionError):
+        pkg.parse_encoded_shard(_shard_of([wrong]), parser="gdal_eager")
+    assert len(pkg.parse_encoded_shard(_shard_of([wrong]), parser="gdal_wrapped")) == 1
+    arr = oep.convert_to_example(img[..., :3].astype(np.uint8), lab, 64, 64, 3, 64, 64, key).SerializeToString()
+    with pytest.raises(InvalidArgumentError):                                 # FloatList / array records do not fit the template
+        pkg.parse_encoded_shard(_shard_of([oep.convert_to_example(img.astype(np.float32), lab.astype(np.float32), 64, 64, 4, 64, 64,
+                                                                  key).SerializeToString()]))
+    del arr

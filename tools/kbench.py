@@ -425,6 +425,41 @@ def bench_build(dev, n_shards=8):
     return res
 
 
+def bench_parse_encoded(dev):
+    """parse_encoded_shard: whole shards of encoded-blob records (configs[2] raw-bytes records; configs[0] PNG pairs) ->
+    decoded tensors; wall clock from host shard bytes, i.e. what replaces dataset.map(parse_encoded_*_proto)."""
+    import time
+
+    import synthetic as syn
+    import dl_image_segmentation_b200 as pkg
+    from oracle import example_proto as oep
+    from oracle import tfrecord as otfr
+    for name, parser, n, make in (
+            ("cfg3 LZW GeoTIFF blobs, gdal_wrapped (float32)", "gdal_wrapped", 128,
+             lambda i: (lambda img, lab, key: (syn.tiff_bytes(img, tile=256), syn.tiff_bytes(lab, tile=256, nodata=255), img.shape, key))(*syn.cfg3_chip(i))),
+            ("cfg3 LZW GeoTIFF blobs, gdal_eager (native dtype)", "gdal_eager", 128,
+             lambda i: (lambda img, lab, key: (syn.tiff_bytes(img, tile=256), syn.tiff_bytes(lab, tile=256, nodata=255), img.shape, key))(*syn.cfg3_chip(i))),
+            ("cfg1 PNG blobs, rgb", "rgb", 1024,
+             lambda i: (lambda img, lab, key: (syn.png_bytes(img), syn.png_bytes(lab), img.shape, key))(*syn.cfg1_chip(i)))):
+        distinct = [make(i) for i in range(16)]
+        recs = []
+        for i in range(n):
+            ib, lb, (h, w, c), key = distinct[i % 16]
+            recs.append(otfr.frame(oep.convert_to_example(ib, lb, h, w, c, h, w, key + "_%d" % i).SerializeToString()))
+        shard = np.frombuffer(b"".join(recs), np.uint8)
+        best = None
+        for _ in range(4):
+            torch.cuda.synchronize()
+            t0 = time.time()
+            out = pkg.parse_encoded_shard(shard, parser=parser)
+            torch.cuda.synchronize()
+            dt = (time.time() - t0) * 1e3
+            best = dt if best is None or dt < best else best
+        decoded = sum(int(a.numel()) * a.element_size() + int(b.numel()) * b.element_size() for a, b, _ in out)
+        report("parse_encoded_shard %s: %d records" % (name, n), best, shard.size + decoded,
+               {"records_per_s": round(n / best * 1e3, 1), "shard_MB": round(shard.size / 1e6, 1), "decoded_MB": round(decoded / 1e6, 1)})
+
+
 def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -443,6 +478,8 @@ def main():
         bench_encode(dev)
     if "encode_kernel" in which:
         bench_encode_kernel(dev)
+    if "parse_encoded" in which:
+        bench_parse_encoded(dev)
     if "jpeg" in which:
         bench_jpeg(dev)
     if "jpeg_encode" in which:
