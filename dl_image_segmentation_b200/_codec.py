@@ -573,6 +573,99 @@ def decode_jpeg_blobs(blobs, device=None, timings=None):
     return arrays, status, infos
 
 
+JPEG_DIMS_DTYPE = np.dtype([("height", "<i4"), ("width", "<i4"), ("samples", "<i4")])
+
+
+class JpegBatch:
+    """A batch of .jpg chips planned on the host (plan_jpeg_batch) and, after jpeg_decode_enqueue, queued on the device:
+    the translators' pipelined form of decode_jpeg_blobs (nothing synchronised until status())."""
+    __slots__ = ("n", "m", "hs", "jinfos", "jobs", "plan", "host_status", "out", "status_dev", "keep", "consumed")
+
+    def release(self):
+        hs = getattr(self, "hs", None)
+        if hs is not None and not getattr(self, "consumed", True):
+            hs.pending = False
+        self.consumed = True
+
+    def status(self):
+        """Per-file status (0 = decoded); waits for the device."""
+        if self.status_dev is None:
+            return self.host_status
+        return np.where(self.host_status != 0, self.host_status, self.status_dev.cpu().numpy())
+
+    def dims(self):
+        """(height, width, samples) per file as a structured array (zeros where the header was refused)."""
+        d = np.zeros(self.n, JPEG_DIMS_DTYPE)
+        for j in range(self.m):
+            i = int(self.jobs[j]["image"])
+            fi = self.jinfos[j]
+            d[i] = (fi.height, fi.width, fi.components)
+        return d
+
+    def out_offsets(self):
+        """Byte offset of every file's pixels in self.out (valid where status() == 0)."""
+        o = np.zeros(self.n, np.int64)
+        o[self.jobs["image"][:self.m]] = self.jobs["out_off"][:self.m].astype(np.int64)
+        return o
+
+
+def plan_jpeg_batch(blobs, device=None, threads=0):
+    """Host half of a batched JPEG decode: marker walk, job table and the gather of the entropy-coded data into a pinned
+    staging set of the device's pool (held until jpeg_decode_enqueue has queued its upload, or release())."""
+    ctx = get_ctx(device)
+    n = len(blobs)
+    jb = JpegBatch()
+    jb.n, jb.m, jb.hs, jb.out, jb.status_dev, jb.keep, jb.consumed = n, 0, None, None, None, None, True
+    jb.host_status = np.zeros(n, np.int32)
+    jb.jinfos = (JpegInfo * max(n, 1))()
+    jb.jobs = np.zeros(n, JPEG_JOB_DTYPE)
+    jb.plan = JpegPlan()
+    if n == 0:
+        return jb
+    ptrs = (ctypes.c_void_p * n)()
+    sizes = np.zeros(n, np.uint64)
+    keep = []
+    for i, b in enumerate(blobs):
+        p, sz, k = _ptr_of(b)
+        ptrs[i], sizes[i] = p, sz
+        keep.append(k)
+    hs = jb.hs = take_staging(ctx.device)
+    jb.consumed = False
+    stage = hs.ensure_stage(int(sizes.sum()) + 16 * n + 64)        # an upper bound of stage_bytes: one call suffices
+    check(lib().b2_jpeg_plan_batch(ptrs, sizes.ctypes.data, n, jb.jinfos, jb.host_status.ctypes.data, jb.jobs.ctypes.data,
+                                   stage.data_ptr(), stage.numel(), int(threads), ctypes.byref(jb.plan)))
+    del keep
+    jb.m = int(jb.plan.n_jobs)
+    if jb.m and not jb.plan.filled:
+        jb.release()
+        raise B2Error("b2_jpeg_plan_batch: staging buffer smaller than its own bound")
+    return jb
+
+
+def jpeg_decode_enqueue(jb, device=None):
+    """Upload and queue the decode kernels of a planned JPEG batch; no synchronisation."""
+    ctx = get_ctx(device)
+    if jb.m == 0:
+        jb.release()
+        return jb
+    hs, plan, m = jb.hs, jb.plan, jb.m
+    blob_d = hs.stage[:plan.stage_bytes].to(ctx.device, non_blocking=True)
+    hs.busy = torch.cuda.Event()
+    hs.busy.record(torch.cuda.current_stream(ctx.device))
+    jb.release()
+    isz = ctypes.sizeof(JpegInfo)
+    info_d = torch.from_numpy(np.frombuffer(jb.jinfos, dtype=np.uint8, count=m * isz).copy()).to(ctx.device, non_blocking=True)
+    jobs_d = torch.from_numpy(jb.jobs[:m].view(np.uint8).reshape(-1).copy()).to(ctx.device, non_blocking=True)
+    coef_d = torch.empty((max(int(plan.coef_count), 1),), dtype=torch.int16, device=ctx.device)
+    planes_d = torch.empty((max(int(plan.plane_bytes), 1),), dtype=torch.uint8, device=ctx.device)
+    jb.out = torch.empty((max(int(plan.out_bytes), 1),), dtype=torch.uint8, device=ctx.device)
+    jb.status_dev = torch.zeros((jb.n,), dtype=torch.int32, device=ctx.device)
+    check(lib().b2_jpeg_decode(ctx.handle, ptr(blob_d), ptr(info_d), ctypes.addressof(jb.jinfos), ptr(jobs_d), jb.jobs.ctypes.data, m,
+                               ptr(coef_d), int(plan.coef_count), ptr(planes_d), ptr(jb.out), ptr(jb.status_dev), ctx.stream()))
+    jb.keep = (blob_d, info_d, jobs_d, coef_d, planes_d)
+    return jb
+
+
 def merge_jpeg(blobs, arrays, status, infos, device=None, candidates=None):
     """The TIFF / PNG planner reports a .jpg chip as an unknown format; decode those through the JPEG path and put their
     results in place (arrays / status / infos as decode_planned returns them).  candidates: the indices worth a look

@@ -287,6 +287,19 @@ class BatchRecords:
         return cls(ctx, keys, np.ones(n, np.int32), sizes[0::2], sizes[1::2], dims, u8, u8, base + offs[0::2], base + offs[1::2],
                    sizes[0::2], sizes[1::2], dev_buf)
 
+    @classmethod
+    def from_jpeg(cls, jb, keys, ctx):
+        """Decoded .jpg chips (store_as_array=True): uint8 pixels, BytesList records."""
+        d, off = jb.dims(), jb.out_offsets()
+        ii, li = d[0::2], d[1::2]
+        n = len(keys)
+        inum = ii["width"].astype(np.int64) * ii["height"] * ii["samples"]
+        lnum = li["width"].astype(np.int64) * li["height"] * li["samples"]
+        dims = np.stack([ii["height"], ii["width"], ii["samples"], li["height"], li["width"]], axis=1)
+        base = jb.out.data_ptr()
+        u8 = np.full(n, _lib_mod.B2_U8, np.int32)
+        return cls(ctx, keys, np.ones(n, np.int32), inum, lnum, dims, u8, u8, base + off[0::2], base + off[1::2], inum, lnum, jb)
+
     def byte_range(self, lo, hi):
         """Bytes of records [lo, hi) of the batch."""
         return int(self.rec_off[lo]), (int(self.rec_off[hi]) if hi < len(self.rec_off) else self.total)
@@ -407,8 +420,12 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
     check_decode = bool(fast and not store_as_array and validate is not None and not to_jpg)
     kAhead = 3                                                              # batches being read / planned ahead of the GPU
     if fast:
+        try:                                                                # .jpg chips are planned into a second set as well
+            two_sets = check_decode or str(img_filenames[ranges[worker_index][0]]).lower().endswith((".jpg", ".jpeg"))
+        except IndexError:
+            two_sets = check_decode
         _codec.reserve_staging(ctx.device, int(pair_bytes * batch_pairs * 1.25) + (1 << 20),
-                               sets=(kAhead + 2) * (2 if check_decode else 1))
+                               sets=(kAhead + 2) * (2 if two_sets else 1))
     n_slots = 4                                                             # rotating pinned write-back buffers, kept per device
     cache = _worker_buffers.setdefault(ctx.device.index, {"pinned": [None] * n_slots, "reader": None})
     pinned = cache["pinned"]
@@ -523,10 +540,19 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                                                 threads=plan_threads)
                 return dict(fast=False, blobs=blobs, planned=planned)
             hs = _codec.take_staging(ctx.device)
-            planned = infos = offs = sizes = None
+            planned = infos = offs = sizes = jpeg = None
             try:
                 blobs, offs, sizes, clean = reader.read_into(paths, hs)     # straight into the pinned staging buffer
-                if clean and (store_as_array or to_jpg):
+                if clean and not to_jpg and sizes.min() >= 3:               # a batch of .jpg chips (SOI marker FF D8 FF)
+                    st_np, o64 = hs.stage.numpy(), offs.astype(np.int64)
+                    if bool(np.all((st_np[o64] == 0xFF) & (st_np[o64 + 1] == 0xD8) & (st_np[o64 + 2] == 0xFF))):
+                        _codec.reserve_staging(ctx.device, 0, sets=(kAhead + 2) * 2)   # a second set per batch in flight
+                        jpeg = _codec.plan_jpeg_batch(blobs, ctx.device, threads=plan_threads)
+                if jpeg is not None:
+                    if jpeg.host_status.any():                              # a file the marker walk refuses: chip by chip
+                        jpeg.release()
+                        jpeg, clean = None, False
+                elif clean and (store_as_array or to_jpg):
                     planned = _codec.plan_blobs(blobs, ctx.device, png_as_tf, inplace=hs, threads=plan_threads)
                 elif clean and check_decode:                                # into a staging set of its own: hs keeps the files
                     planned = _codec.plan_blobs(blobs, ctx.device, png_as_tf, threads=plan_threads)
@@ -535,13 +561,15 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                     clean = not infos["status"].any()
             except Exception:
                 planned, clean = None, False
-            if not clean or ((store_as_array or check_decode or to_jpg) and planned is None):
+            if not clean or ((store_as_array or check_decode or to_jpg) and planned is None and jpeg is None):
                 if planned is not None:
                     planned.release()
+                if jpeg is not None:
+                    jpeg.release()
                 hs.pending = False
                 return dict(fast=False, blobs=None, planned=None)           # the chip-by-chip path re-reads the files
             keys = [path_key(p) for p in paths]
-            return dict(fast=True, planned=planned, keys=keys, hs=hs, infos=infos, offs=offs, sizes=sizes)
+            return dict(fast=True, planned=planned, keys=keys, hs=hs, infos=infos, offs=offs, sizes=sizes, jpeg=jpeg)
 
         def stage1(bi):
             """Batch bi: wait for its files + plan, queue its upload and decode (nothing synchronised)."""
@@ -553,7 +581,11 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
             b["runs"] = batches[bi]
             if b["fast"] and b["planned"] is not None:
                 b["job"] = _codec.decode_enqueue(b["planned"], ctx.device)
-            if b["fast"] and not store_as_array and not to_jpg:             # the files as they are: one upload of the staging buffer
+            if b["fast"] and b.get("jpeg") is not None:                     # the reference decodes a .jpg chip whatever it stores
+                _codec.jpeg_decode_enqueue(b["jpeg"], ctx.device)
+            if b["fast"] and store_as_array and b.get("jpeg") is not None:
+                b["hs"].pending = False                                     # .jpg pixels come from the JPEG plan's own set
+            if b["fast"] and not to_jpg and not store_as_array:            # the files as they are: one upload of the staging buffer
                 hs = b["hs"]
                 used = int(b["offs"][-1] + b["sizes"][-1]) + 16
                 b["dev"] = hs.stage[:used].to(ctx.device, non_blocking=True)
@@ -589,7 +621,13 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
             runs = b["runs"]
             if b["fast"]:
                 keys = b["keys"]
-                if b["planned"] is not None:
+                jpeg = b.get("jpeg")
+                if jpeg is not None:
+                    mark("wait status")
+                    ok = not jpeg.status().any()
+                    mark("got status")
+                    infos = jpeg.dims()
+                elif b["planned"] is not None:
                     job = b["job"]
                     mark("wait status")
                     st = job.status()                                       # waits for this batch's decode only
@@ -599,7 +637,7 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                 else:
                     infos, ok = b["infos"], True
                 ok = ok and keys[0::2] == keys[1::2]
-                if ok and fast_validate is not None:
+                if ok and fast_validate is not None and jpeg is None:        # (a baseline JPEG has 1 or 3 components: always valid)
                     ok = bool(np.all(fast_validate(infos)))
                 if ok and to_jpg:                                           # tf.image.encode_jpeg takes 1 or 3 channels of uint8
                     ok = bool(np.all((infos["samples"] != 2) & (infos["dtype"] == _lib_mod.B2_U8)))
@@ -613,6 +651,8 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                         files, foffs, fsizes = _codec.encode_jpeg_device(job.out, job.images["out_off"], infos["height"], infos["width"],
                                                                          infos["samples"], quality=100, device=ctx.device)
                         rec = BatchRecords.from_files(files, foffs, fsizes, infos, ids, ctx)
+                    elif jpeg is not None and store_as_array:
+                        rec = BatchRecords.from_jpeg(jpeg, ids, ctx)
                     else:
                         rec = BatchRecords.from_decode(job, ids, ctx) if store_as_array else \
                             BatchRecords.from_files(b["dev"], b["offs"], b["sizes"], infos, ids, ctx)
@@ -651,7 +691,9 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                         dropped = res.get("planned")
                         if dropped is not None:
                             dropped.release()
-                        if res.get("hs") is not None and not store_as_array:
+                        if res.get("jpeg") is not None:
+                            res["jpeg"].release()
+                        if res.get("hs") is not None and (not store_as_array or res.get("jpeg") is not None):
                             res["hs"].pending = False                       # the set that holds the files themselves
                     except Exception:
                         pass
