@@ -72,14 +72,20 @@ struct LzwSmem {
     } u;
     uint32_t in[2][kLzwInWords];       // the segment's input words as they lie in memory; the next segment's arrive meanwhile
     uint32_t warp_sum[kLzwThreads / 32];
-    int m;                             // position of the first control code
+    int m[2];                          // position of the first control code: [0] of a full pass, [1] of a short one (a short
+                                       // pass that gives up is followed at once, without a barrier, by a full pass)
     int stream;                        // next stream drawn from the counter
+    // the stream being decoded (written once per stream; kept out of the registers of the segment pass)
+    const uint32_t* wsrc;              // its words (aligned down); stream bit 0 = bit 8 * mis of word 0
+    uint8_t* dst;
+    uint32_t n_words, mis, src_bits, dst_len;
 };
 static_assert(sizeof(LzwSmem) <= 48 * 1024, "lzw_kernel uses static shared memory");
 
-// stage words [w0, w0 + kLzwInWords) of the stream (zeros beyond its last word) with asynchronous 4-byte copies
-__device__ __forceinline__ void lzw_stage(uint32_t* sdst, const uint32_t* __restrict__ wsrc, uint32_t w0, uint32_t n_words, int tid) {
-    for (int j = tid; j < kLzwInWords; j += kLzwThreads) {
+// stage words [w0 + j0, w0 + j1) of the stream into sdst[j0 .. j1) (zeros beyond its last word) with asynchronous 4-byte copies
+__device__ __forceinline__ void lzw_stage(uint32_t* sdst, const uint32_t* __restrict__ wsrc, uint32_t w0, uint32_t n_words, int tid,
+                                          int j0, int j1) {
+    for (int j = j0 + tid; j < j1; j += kLzwThreads) {
         const uint32_t w = w0 + (uint32_t)j;
         const uint32_t ok = w < n_words ? 4u : 0u;
         const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sdst + j);
@@ -88,16 +94,16 @@ __device__ __forceinline__ void lzw_stage(uint32_t* sdst, const uint32_t* __rest
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-// codes 15 t .. 15 t + 14 of the segment from a sliding two-word window; kCheck: the input may end inside this span
-template <bool kCheck>
+// codes kPer t .. kPer t + kPer - 1 of the segment from a sliding two-word window; kCheck: the input may end inside this span
+template <int kPer, bool kCheck>
 __device__ __forceinline__ uint32_t lzw_extract(const uint32_t* __restrict__ in, uint32_t bit0, uint32_t wd0, int step_at,
-                                                uint32_t lim, uint32_t (&code)[kLzwPer], uint32_t* tcode) {
+                                                uint32_t lim, uint32_t (&code)[kPer], uint32_t* tcode) {
     uint32_t widx = bit0 >> 5, sh = bit0 & 31u;
     uint32_t hi = __byte_perm(in[widx], 0u, 0x0123), lo = __byte_perm(in[widx + 1], 0u, 0x0123);
     widx += 2;
     uint32_t ctl = 0, used = 0;
 #pragma unroll
-    for (int i = 0; i < kLzwPer; i++) {
+    for (int i = 0; i < kPer; i++) {
         const uint32_t wd = wd0 + (i >= step_at ? 1u : 0u);
         uint32_t c = __funnelshift_l(lo, hi, sh) >> (32u - wd);
         sh += wd;
@@ -113,19 +119,219 @@ __device__ __forceinline__ uint32_t lzw_extract(const uint32_t* __restrict__ in,
     return ctl;
 }
 
-__global__ void __launch_bounds__(kLzwThreads, 4)
-lzw_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ streams, const int* __restrict__ order,
-           int n_streams, uint8_t* scratch, int32_t* __restrict__ status, unsigned int* next_stream) {
-    __shared__ LzwSmem sm;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k0 = tid * kLzwPer;
-    uint8_t* const sout = reinterpret_cast<uint8_t*>(sm.u.out16);
-    // code width of this thread's positions: 9 bits, one more from positions 254, 766 and 1790 on; a thread's 15 positions
+// Segments come in two sizes.  A full dictionary ends a segment after 3838 codes (15 per thread); a writer that restarts
+// the dictionary every 1024 input bytes (b2_lzw_encode_restart, the GeoTIFF writer of this package) makes segments of at
+// most 1026 codes, and a pass costs about the same whatever the segment holds — so there is a second instantiation of the
+// pass with 5 codes per thread (1280 positions), tried first and again after every segment that would have fitted it.
+constexpr int kLzwPerShort = 5;
+constexpr int kLzwShortWords = 512;                  // 1280 codes x 12 bits + alignment
+
+struct LzwStream {
+    uint32_t bitpos, out;                            // consumed input bits, produced output bytes
+    int err, buf;
+    int staged;                                      // words of the current segment staged in sm.in[buf]
+    bool next_short;                                 // the pass to try on the next segment
+};
+
+// One segment.  Returns 0: done, the next segment follows; 1: the stream ends here (EOI, end of input, error: st.err);
+// 2 (short pass only): no control code among the first 1280 codes — nothing was consumed, the long pass must take it.
+template <int kPer>
+__device__ __forceinline__ int lzw_pass(LzwSmem& sm, LzwStream& st, const int tid, const int lane, const int warp) {
+    constexpr int kMax = kPer * kLzwThreads;
+    const int k0 = tid * kPer;
+    // code width of this thread's positions: 9 bits, one more from positions 254, 766 and 1790 on; a thread's positions
     // cross at most one of the three steps
     const uint32_t wd0 = lzw_width((uint32_t)k0);
     const int next_step = k0 < 254 ? 254 : (k0 < 766 ? 766 : (k0 < 1790 ? 1790 : (1 << 30)));
     const int step_at = next_step - k0;
     const uint32_t rel0 = lzw_cum_bits((uint32_t)k0);                  // bits from the segment start to this thread's first code
+    uint8_t* const sout = reinterpret_cast<uint8_t*>(sm.u.out16);
+    const uint32_t mis = sm.mis, bitpos = st.bitpos, src_bits = sm.src_bits;
+    const int buf = st.buf;
+    // ---- A: all codes of the segment (its input was staged while the previous segment was being written out)
+    const uint32_t r0 = (8u * mis + bitpos) & 31u;
+    int* const first_ctl = &sm.m[kPer == kLzwPerShort ? 1 : 0];
+    if (tid == 0) *first_ctl = kMax;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    uint32_t code[kPer];
+    {
+        const uint32_t remaining = src_bits - bitpos;              // bits of the stream from the segment start on
+        const uint32_t lim = remaining > rel0 ? remaining - rel0 : 0u;
+        const uint32_t ctl = (lim >= 12u * kPer)
+            ? lzw_extract<kPer, false>(sm.in[buf], r0 + rel0, wd0, step_at, lim, code, sm.tcode + k0)
+            : lzw_extract<kPer, true>(sm.in[buf], r0 + rel0, wd0, step_at, lim, code, sm.tcode + k0);
+        if (ctl) atomicMin(first_ctl, k0 + __ffs(ctl) - 1);
+    }
+    __syncthreads();
+    const int m = *first_ctl;
+    if (kPer == kLzwPerShort && m == kMax) return 2;
+    {   // the next segment starts right after this one's Clear: fetch its input now
+        const uint32_t nb = bitpos + lzw_cum_bits((uint32_t)m) + lzw_width((uint32_t)m);
+        st.next_short = m < kLzwPerShort * kLzwThreads - 2;
+        st.staged = st.next_short ? kLzwShortWords : kLzwInWords;
+        if (m < kMax && nb < src_bits) lzw_stage(sm.in[buf ^ 1], sm.wsrc, (8u * mis + nb) >> 5, sm.n_words, tid, 0, st.staged);
+    }
+    // ---- B: forest over the code positions -> depth and root by pointer jumping (own nodes in registers)
+    uint32_t node[kPer];
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < kPer; i++) {
+        const uint32_t k = (uint32_t)(k0 + i), c = code[i];
+        uint32_t nd = k;                                           // literal / beyond the segment: a root
+        if ((int)k < m && c >= 256u) {
+            const uint32_t e = c - 258u;
+            if (e >= k) bad = true;                                // entry not defined yet (k == 0: the first code must be a literal)
+            else nd = e | (1u << 16);
+        }
+        node[i] = nd;
+        sm.u.tnode[k] = nd;
+    }
+    if (__syncthreads_or(bad)) { st.err = 2; return 1; }
+    for (;;) {
+        bool changed = false;
+#pragma unroll
+        for (int i = 0; i < kPer; i++) {
+            const uint32_t j = node[i] & 0xFFFFu, par = sm.u.tnode[j];
+            if (par != j) {                                        // the ancestor is not a root yet: hop over it
+                node[i] = ((node[i] & 0xFFFF0000u) + (par & 0xFFFF0000u)) | (par & 0xFFFFu);
+                changed = true;
+            }
+        }
+        if (!__syncthreads_or(changed)) break;                     // every ancestor is a root: depths are final
+#pragma unroll
+        for (int i = 0; i < kPer; i++) sm.u.tnode[k0 + i] = node[i];
+        __syncthreads();
+    }
+    // ---- C: first bytes, lengths, offsets
+    uint32_t run = 0;
+#pragma unroll
+    for (int i = 0; i < kPer; i++) {
+        if (k0 + i < m) {
+            if (code[i] >= 256u) {
+                const uint32_t fb = sm.tcode[node[i] & 0xFFFFu] & 0xFFu;   // the root is a literal; its low byte never changes
+                sm.tcode[k0 + i] = code[i] | (fb << 16);
+            } else {
+                sm.tcode[k0 + i] = code[i] * 0x10001u;
+            }
+            run += (node[i] >> 16) + 1u;
+        }
+    }
+    uint32_t incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) sm.warp_sum[warp] = incl;
+    __syncthreads();                                               // also: tnode is dead, its space becomes the output window
+    uint32_t my_off = incl - run, total = 0;
+#pragma unroll
+    for (int w = 0; w < kLzwThreads / 32; w++) {
+        const uint32_t v = sm.warp_sum[w];
+        if (w < warp) my_off += v;
+        total += v;
+    }
+    // ---- D: every string, back to front, through an output window that shares the destination's 16-byte alignment.
+    // libtiff truncates the last string of a tile: bytes past dst_len are dropped
+    const uint32_t room = sm.dst_len - st.out;
+    const uint32_t emit = total < room ? total : room;
+    uint8_t* const gseg = sm.dst + st.out;
+    if (emit == total && total <= (uint32_t)kLzwWindow) {
+        // the whole segment fits one window and the tile (the common case): no range checks on the way
+        const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(gseg) & 15u);
+        uint8_t* ptr = sout + shift + my_off;
+#pragma unroll
+        for (int i = 0; i < kPer; i++) {
+            if (k0 + i < m) {
+                uint32_t c = code[i];
+                if (c < 256u) {
+                    *ptr++ = (uint8_t)c;
+                } else {
+                    ptr += (node[i] >> 16) + 1u;
+                    uint8_t* q = ptr;
+                    do {
+                        *--q = (uint8_t)(sm.tcode[c - 257u] >> 16);
+                        c = sm.tcode[c - 258u] & 0xFFFFu;
+                    } while (c >= 256u);
+                    *--q = (uint8_t)c;
+                }
+            }
+        }
+        __syncthreads();
+        uint8_t* const g16 = gseg - shift;                         // 16-byte aligned
+        const uint32_t lo = shift, hi = shift + total;             // valid bytes of the window buffer
+        for (uint32_t c16 = (uint32_t)tid; c16 * 16u < hi; c16 += kLzwThreads) {
+            const uint32_t b0 = c16 * 16u;
+            if (b0 >= lo && b0 + 16u <= hi) {
+                *reinterpret_cast<uint4*>(g16 + b0) = sm.u.out16[c16];
+            } else {
+                for (uint32_t q = (b0 > lo ? b0 : lo); q < b0 + 16u && q < hi; q++) g16[q] = sout[q];
+            }
+        }
+        __syncthreads();
+    } else
+    for (uint32_t wv = 0; wv < emit; wv += kLzwWindow) {
+        const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(gseg + wv) & 15u);
+        const uint32_t wend = (wv + kLzwWindow < emit) ? wv + kLzwWindow : emit;
+        uint8_t* const sbase = sout + shift - wv;                  // window byte of segment byte p: sbase[p]
+        uint32_t o = my_off;
+#pragma unroll
+        for (int i = 0; i < kPer; i++) {
+            if (k0 + i < m) {
+                const uint32_t c0 = code[i];
+                if (c0 < 256u) {                                   // a literal: one byte
+                    if (o >= wv && o < wend) sbase[o] = (uint8_t)c0;
+                    o += 1u;
+                } else {
+                    const uint32_t len = (node[i] >> 16) + 1u;
+                    if (o < wend && o + len > wv) {
+                        uint32_t p = o + len - 1u, c = c0;
+                        for (;;) {
+                            uint32_t byte = c;
+                            if (c >= 256u) {
+                                byte = (sm.tcode[c - 257u] >> 16) & 0xFFu;
+                                c = sm.tcode[c - 258u] & 0xFFFFu;
+                            } else {
+                                c = 0xFFFFFFFFu;
+                            }
+                            if (p < wend) sbase[p] = (uint8_t)byte;
+                            if (c == 0xFFFFFFFFu || p <= wv) break;
+                            p--;
+                        }
+                    }
+                    o += len;
+                }
+            }
+        }
+        __syncthreads();
+        {
+            uint8_t* const g16 = gseg + wv - shift;                // 16-byte aligned
+            const uint32_t lo = shift, hi = shift + (wend - wv);   // valid bytes of the window buffer
+            for (uint32_t c16 = (uint32_t)tid; c16 * 16u < hi; c16 += kLzwThreads) {
+                const uint32_t b0 = c16 * 16u;
+                if (b0 >= lo && b0 + 16u <= hi) {
+                    *reinterpret_cast<uint4*>(g16 + b0) = sm.u.out16[c16];
+                } else {
+                    for (uint32_t q = (b0 > lo ? b0 : lo); q < b0 + 16u && q < hi; q++) g16[q] = sout[q];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    st.out += emit;
+    const uint32_t ctl = (m < kMax) ? (sm.tcode[m] & 0xFFFFu) : 257u;   // no control code within a full table: overflow, stop
+    if (ctl != 256u) return 1;
+    st.bitpos += lzw_cum_bits((uint32_t)m) + lzw_width((uint32_t)m);
+    st.buf ^= 1;
+    return 0;
+}
+
+__global__ void __launch_bounds__(kLzwThreads, 4)
+lzw_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ streams, const int* __restrict__ order,
+           int n_streams, uint8_t* scratch, int32_t* __restrict__ status, unsigned int* next_stream) {
+    __shared__ LzwSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (;;) {                                                           // persistent CTAs draw streams from a counter
     __syncthreads();
     if (tid == 0) sm.stream = (int)atomicAdd(next_stream, 1u);
@@ -139,190 +345,39 @@ lzw_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restrict__ 
     if (sd.codec != CODEC_LZW || (sd.dst_len >= (1u << 17)) != (draw < n_streams)) continue;
     const uint8_t* src = blob + sd.src_off;
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
-    const uint32_t* __restrict__ wsrc = reinterpret_cast<const uint32_t*>(src - mis);   // aligned words; stream bit 0 = bit 8*mis
+    const uint32_t* const wsrc = reinterpret_cast<const uint32_t*>(src - mis);
     const uint32_t n_words = (mis + sd.src_len + 3u) >> 2;
-    uint8_t* dst = scratch + sd.dst_off;
-    const uint32_t src_bits = sd.src_len * 8u, dst_len = sd.dst_len;
-    uint32_t bitpos = 0, out = 0;
-    int err = 0, buf = 0;
-    lzw_stage(sm.in[0], wsrc, (8u * mis) >> 5, n_words, tid);
-    while (out < dst_len) {
-        // ---- A: all codes of the segment (its input was staged while the previous segment was being written out)
-        const uint32_t r0 = (8u * mis + bitpos) & 31u;
-        if (tid == 0) sm.m = kLzwMaxCodes;
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncthreads();
-        uint32_t code[kLzwPer];
-        {
-            const uint32_t remaining = src_bits - bitpos;              // bits of the stream from the segment start on
-            const uint32_t lim = remaining > rel0 ? remaining - rel0 : 0u;
-            const uint32_t ctl = (lim >= 12u * kLzwPer)
-                ? lzw_extract<false>(sm.in[buf], r0 + rel0, wd0, step_at, lim, code, sm.tcode + k0)
-                : lzw_extract<true>(sm.in[buf], r0 + rel0, wd0, step_at, lim, code, sm.tcode + k0);
-            if (ctl) atomicMin(&sm.m, k0 + __ffs(ctl) - 1);
-        }
-        __syncthreads();
-        const int m = sm.m;
-        {   // the next segment starts right after this one's Clear: fetch its input now
-            const uint32_t nb = bitpos + lzw_cum_bits((uint32_t)m) + lzw_width((uint32_t)m);
-            if (m < kLzwMaxCodes && nb < src_bits) lzw_stage(sm.in[buf ^ 1], wsrc, (8u * mis + nb) >> 5, n_words, tid);
-        }
-        // ---- B: forest over the code positions -> depth and root by pointer jumping (own nodes in registers)
-        uint32_t node[kLzwPer];
-        bool bad = false;
-#pragma unroll
-        for (int i = 0; i < kLzwPer; i++) {
-            const uint32_t k = (uint32_t)(k0 + i), c = code[i];
-            uint32_t nd = k;                                           // literal / beyond the segment: a root
-            if ((int)k < m && c >= 256u) {
-                const uint32_t e = c - 258u;
-                if (e >= k) bad = true;                                // entry not defined yet (k == 0: the first code must be a literal)
-                else nd = e | (1u << 16);
+    if (tid == 0) {
+        sm.wsrc = wsrc;
+        sm.dst = scratch + sd.dst_off;
+        sm.n_words = n_words;
+        sm.mis = mis;
+        sm.src_bits = sd.src_len * 8u;
+        sm.dst_len = sd.dst_len;
+    }
+    const uint32_t dst_len = sd.dst_len;
+    LzwStream st;
+    st.bitpos = st.out = 0;
+    st.err = st.buf = 0;
+    st.next_short = true;
+    st.staged = kLzwShortWords;
+    lzw_stage(sm.in[0], wsrc, (8u * mis) >> 5, n_words, tid, 0, st.staged);
+    __syncthreads();                                                   // the stream's parameters are in shared memory
+    while (st.out < dst_len) {
+        int r = 2;
+        if (st.next_short) r = lzw_pass<kLzwPerShort>(sm, st, tid, lane, warp);
+        if (r == 2) {
+            if (st.staged < kLzwInWords) {                             // the rest of a full segment's input
+                lzw_stage(sm.in[st.buf], wsrc, (8u * mis + st.bitpos) >> 5, n_words, tid, st.staged, kLzwInWords);
+                st.staged = kLzwInWords;
             }
-            node[i] = nd;
-            sm.u.tnode[k] = nd;
+            r = lzw_pass<kLzwPer>(sm, st, tid, lane, warp);
         }
-        if (__syncthreads_or(bad)) { err = 2; break; }
-        for (;;) {
-            bool changed = false;
-#pragma unroll
-            for (int i = 0; i < kLzwPer; i++) {
-                const uint32_t j = node[i] & 0xFFFFu, par = sm.u.tnode[j];
-                if (par != j) {                                        // the ancestor is not a root yet: hop over it
-                    node[i] = ((node[i] & 0xFFFF0000u) + (par & 0xFFFF0000u)) | (par & 0xFFFFu);
-                    changed = true;
-                }
-            }
-            if (!__syncthreads_or(changed)) break;                     // every ancestor is a root: depths are final
-#pragma unroll
-            for (int i = 0; i < kLzwPer; i++) sm.u.tnode[k0 + i] = node[i];
-            __syncthreads();
-        }
-        // ---- C: first bytes, lengths, offsets
-        uint32_t run = 0;
-#pragma unroll
-        for (int i = 0; i < kLzwPer; i++) {
-            if (k0 + i < m) {
-                if (code[i] >= 256u) {
-                    const uint32_t fb = sm.tcode[node[i] & 0xFFFFu] & 0xFFu;   // the root is a literal; its low byte never changes
-                    sm.tcode[k0 + i] = code[i] | (fb << 16);
-                } else {
-                    sm.tcode[k0 + i] = code[i] * 0x10001u;
-                }
-                run += (node[i] >> 16) + 1u;
-            }
-        }
-        uint32_t incl = run;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) sm.warp_sum[warp] = incl;
-        __syncthreads();                                               // also: tnode is dead, its space becomes the output window
-        uint32_t my_off = incl - run, total = 0;
-#pragma unroll
-        for (int w = 0; w < kLzwThreads / 32; w++) {
-            const uint32_t v = sm.warp_sum[w];
-            if (w < warp) my_off += v;
-            total += v;
-        }
-        // ---- D: every string, back to front, through an output window that shares the destination's 16-byte alignment.
-        // libtiff truncates the last string of a tile: bytes past dst_len are dropped
-        const uint32_t room = dst_len - out;
-        const uint32_t emit = total < room ? total : room;
-        uint8_t* const gseg = dst + out;
-        if (emit == total && total <= (uint32_t)kLzwWindow) {
-            // the whole segment fits one window and the tile (the common case): no range checks on the way
-            const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(gseg) & 15u);
-            uint8_t* ptr = sout + shift + my_off;
-#pragma unroll
-            for (int i = 0; i < kLzwPer; i++) {
-                if (k0 + i < m) {
-                    uint32_t c = code[i];
-                    if (c < 256u) {
-                        *ptr++ = (uint8_t)c;
-                    } else {
-                        ptr += (node[i] >> 16) + 1u;
-                        uint8_t* q = ptr;
-                        do {
-                            *--q = (uint8_t)(sm.tcode[c - 257u] >> 16);
-                            c = sm.tcode[c - 258u] & 0xFFFFu;
-                        } while (c >= 256u);
-                        *--q = (uint8_t)c;
-                    }
-                }
-            }
-            __syncthreads();
-            uint8_t* const g16 = gseg - shift;                         // 16-byte aligned
-            const uint32_t lo = shift, hi = shift + total;             // valid bytes of the window buffer
-            for (uint32_t c16 = (uint32_t)tid; c16 * 16u < hi; c16 += kLzwThreads) {
-                const uint32_t b0 = c16 * 16u;
-                if (b0 >= lo && b0 + 16u <= hi) {
-                    *reinterpret_cast<uint4*>(g16 + b0) = sm.u.out16[c16];
-                } else {
-                    for (uint32_t q = (b0 > lo ? b0 : lo); q < b0 + 16u && q < hi; q++) g16[q] = sout[q];
-                }
-            }
-            __syncthreads();
-        } else
-        for (uint32_t wv = 0; wv < emit; wv += kLzwWindow) {
-            const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(gseg + wv) & 15u);
-            const uint32_t wend = (wv + kLzwWindow < emit) ? wv + kLzwWindow : emit;
-            uint8_t* const sbase = sout + shift - wv;                  // window byte of segment byte p: sbase[p]
-            uint32_t o = my_off;
-#pragma unroll
-            for (int i = 0; i < kLzwPer; i++) {
-                if (k0 + i < m) {
-                    const uint32_t c0 = code[i];
-                    if (c0 < 256u) {                                   // a literal: one byte
-                        if (o >= wv && o < wend) sbase[o] = (uint8_t)c0;
-                        o += 1u;
-                    } else {
-                        const uint32_t len = (node[i] >> 16) + 1u;
-                        if (o < wend && o + len > wv) {
-                            uint32_t p = o + len - 1u, c = c0;
-                            for (;;) {
-                                uint32_t byte = c;
-                                if (c >= 256u) {
-                                    byte = (sm.tcode[c - 257u] >> 16) & 0xFFu;
-                                    c = sm.tcode[c - 258u] & 0xFFFFu;
-                                } else {
-                                    c = 0xFFFFFFFFu;
-                                }
-                                if (p < wend) sbase[p] = (uint8_t)byte;
-                                if (c == 0xFFFFFFFFu || p <= wv) break;
-                                p--;
-                            }
-                        }
-                        o += len;
-                    }
-                }
-            }
-            __syncthreads();
-            {
-                uint8_t* const g16 = gseg + wv - shift;                // 16-byte aligned
-                const uint32_t lo = shift, hi = shift + (wend - wv);   // valid bytes of the window buffer
-                for (uint32_t c16 = (uint32_t)tid; c16 * 16u < hi; c16 += kLzwThreads) {
-                    const uint32_t b0 = c16 * 16u;
-                    if (b0 >= lo && b0 + 16u <= hi) {
-                        *reinterpret_cast<uint4*>(g16 + b0) = sm.u.out16[c16];
-                    } else {
-                        for (uint32_t q = (b0 > lo ? b0 : lo); q < b0 + 16u && q < hi; q++) g16[q] = sout[q];
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        out += emit;
-        const uint32_t ctl = (m < kLzwMaxCodes) ? (sm.tcode[m] & 0xFFFFu) : 257u;   // no control code within a full table: overflow, stop
-        if (ctl != 256u) break;
-        bitpos += lzw_cum_bits((uint32_t)m) + lzw_width((uint32_t)m);
-        buf ^= 1;
+        if (r) break;
     }
     asm volatile("cp.async.wait_all;" ::: "memory");                   // nothing may still be landing when the next stream starts
-    if (err == 0 && out < dst_len) err = 1;                            // stream ended early / table overflow
-    if (err && tid == 0) set_status(status, sd.image, 10 + err);
+    if (st.err == 0 && st.out < dst_len) st.err = 1;                   // stream ended early / table overflow
+    if (st.err && tid == 0) set_status(status, sd.image, 10 + st.err);
   }
 }
 

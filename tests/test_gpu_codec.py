@@ -315,3 +315,19 @@ def test_lzw_segment_parallel_decode_fuzz(dev):
     for i, b in enumerate(blobs):
         assert status[i] == 0, (i, status[i])
         assert np.array_equal(got[i], oic.decode_image(b)), i
+
+
+def test_lzw_streams_that_alternate_full_and_short_segments(dev):
+    """Strips of noisy 16-bit chips: every stream is one full-table segment (3838 codes) followed by a short one, thousands
+    of streams per batch — the decoder tries its 5-codes-per-thread pass first, gives up without a barrier and runs the
+    15-codes-per-thread pass on the same segment (the two passes once shared the word that holds the segment's end: a
+    late warp of the short pass read the full pass's initial value and went its own way).  Restart streams
+    (a Clear every 1024 input bytes, what this package's GeoTIFF writer emits) are all short segments."""
+    blobs, wants = [], []
+    for i in range(6):
+        img, lab, _ = syn.cfg3_chip(20 + i)
+        blobs += [syn.tiff_bytes(img, tile=None, predictor=2, photometric=2), syn.tiff_bytes(lab, tile=None, predictor=2),
+                  syn.tiff_bytes(img, tile=256, lzw_restart=1024), syn.tiff_bytes(img, tile=256, lzw_restart=48)]
+        wants += [img, lab[:, :, None], img, img]
+    for _ in range(3):
+        _check(dev, blobs, wants)
