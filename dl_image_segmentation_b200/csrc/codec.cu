@@ -1244,6 +1244,16 @@ rawcopy_kernel(const uint8_t* __restrict__ blob, const b2_stream_desc* __restric
 // one complete pixel, at least one (1..8).  8-bit grey / grey+alpha / RGB / RGBA land in the output directly;
 // the other flavours (palette, 1/2/4-bit, 16-bit) are un-filtered into scratch and expanded by the same warp the way
 // the replaced decoder presents them (b2chips.h: B2_PNG_AS_TF or GDAL).
+constexpr int kUfWarps = 8;                 // warps per image of the wide kernel
+constexpr int kUfRowMax = 4096;             // longest row (bytes) it takes: the last row of a band is handed on through shared memory
+
+// 8-bit grey / grey+alpha / RGB / RGBA, progressive, at least three bands of rows: png_unfilter_wide_kernel's share
+__host__ __device__ __forceinline__ bool png_wide_eligible(const b2_image_desc& im) {
+    const int depth = im.png_bit_depth ? im.png_bit_depth : 8;
+    return im.format == 2 && !im.png_converted && depth == 8 && (im.png_flags & 0x100) == 0 && im.height >= 96 &&
+           (size_t)im.width * im.samples <= (size_t)kUfRowMax;
+}
+
 __global__ void __launch_bounds__(128)
 png_unfilter_kernel(uint8_t* __restrict__ scratch, const b2_image_desc* __restrict__ imgs, int n_images,
                     uint8_t* __restrict__ out, int32_t* __restrict__ status) {
@@ -1253,6 +1263,7 @@ png_unfilter_kernel(uint8_t* __restrict__ scratch, const b2_image_desc* __restri
     const b2_image_desc im = imgs[wi];
     if (im.format != 2) return;
     if (status && status[wi] != 0) return;
+    if (png_wide_eligible(im)) return;
     const int depth = im.png_bit_depth ? im.png_bit_depth : 8, ct = im.png_color_type;
     const int src_ch = im.png_converted ? (ct == 0 || ct == 3 ? 1 : (ct == 2 ? 3 : (ct == 4 ? 2 : 4))) : im.samples;
     const int bpp = max(1, src_ch * depth / 8), h = im.height;
@@ -1372,6 +1383,114 @@ png_unfilter_kernel(uint8_t* __restrict__ scratch, const b2_image_desc* __restri
             o[i] = (uint8_t)(ct == 0 && tf ? v * scale : v);
         }
     }
+}
+
+// The same wavefront with EIGHT warps per image: warp w takes the bands of 32 rows w, w + 8, ... and runs each exactly as the
+// one-warp kernel does, except that the row above a band (the last row of the band before, another warp's work) arrives
+// through shared memory: the producer's lane 31 leaves every byte it finishes in its warp's row buffer and publishes,
+// every eight steps, how far it has come ((band << 13) + steps done, monotonic per warp); the consumer's lane 0 needs
+// pixel x at its step x, which the producer finished at step x + 31, and polls only when the value it last saw is too
+// small.  Band b + 8 reuses band b's buffer: it cannot get to pixel x before band b + 1 has read it (the chain of seven
+// bands in between each waits for its predecessor to pass x).  One warp per image left the SMs at 14 warps; this fills them
+// and shortens an image's critical path from 8 x (w + 31) steps to (w + 31) + 7 x ~40.
+__global__ void __launch_bounds__(kUfWarps * 32)
+png_unfilter_wide_kernel(uint8_t* __restrict__ scratch, const b2_image_desc* __restrict__ imgs, int n_images,
+                         uint8_t* __restrict__ out, int32_t* __restrict__ status) {
+    __shared__ uint8_t lastrow[kUfWarps][kUfRowMax];
+    __shared__ unsigned int progress[kUfWarps];
+    __shared__ int any_bad;
+    const int wi = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (wi >= n_images) return;
+    const b2_image_desc im = imgs[wi];
+    if (!png_wide_eligible(im)) return;
+    if (status && status[wi] != 0) return;
+    const int bpp = im.samples, h = im.height, w = im.width;
+    const size_t rb = (size_t)w * bpp;
+    const uint8_t* src = scratch + im.scratch_off;
+    uint8_t* dst = out + im.out_off;
+    if (threadIdx.x < kUfWarps) progress[threadIdx.x] = 0;
+    if (threadIdx.x == 0) any_bad = 0;
+    __syncthreads();
+    const bool word_out = (rb & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0;
+    const int prod = (warp + kUfWarps - 1) % kUfWarps;                     // the warp that owns the band above
+    volatile unsigned int* const vprog = progress;
+    volatile uint8_t* const above = lastrow[prod];
+    uint8_t* const mine = lastrow[warp];
+    bool bad = false;
+    unsigned int seen = 0;
+    for (int band = warp; band * 32 < h; band += kUfWarps) {
+        const int row = band * 32 + lane;
+        const bool live = row < h;
+        const uint8_t* srow = src + (size_t)(live ? row : 0) * (rb + 1);
+        const int ft = live ? srow[0] : 0;
+        if (live && ft > 4) bad = true;
+        uint32_t left[4] = {0, 0, 0, 0}, upl[4] = {0, 0, 0, 0}, cur[4] = {0, 0, 0, 0};
+        // the filtered bytes are fetched an aligned 32-bit word at a time: byte k of the row is byte (a0 + k) of rowwords[]
+        const uintptr_t in0 = reinterpret_cast<uintptr_t>(srow) + 1;        // first filtered byte
+        const uint32_t a0 = (uint32_t)(in0 & 3);
+        const uint32_t* const rowwords = reinterpret_cast<const uint32_t*>(in0 - a0);
+        const bool f_sub = ft == 1, f_up = ft == 2, f_avg = ft == 3, f_paeth = ft == 4;
+        uint32_t rword = 0, wword = 0;
+        uint8_t* const orow = dst + (size_t)row * rb;
+        const unsigned int base = (unsigned int)band << 13, need0 = ((unsigned int)(band - 1) << 13) + 32u;
+        for (int step = 0; step < w + 31; step++) {
+            const int x = step - lane;
+            const bool act = live && x >= 0 && x < w;
+            if (band > 0 && step < w) {                                     // lane 0 is about to read pixel `step` of the row above
+                const unsigned int need = need0 + (unsigned int)step;
+                if (seen < need) {
+                    do { seen = vprog[prod]; } while (seen < need);         // (a back-off or a single polling lane measured no better)
+                    __threadfence_block();
+                }
+            }
+            const uint32_t kx = (uint32_t)x * (uint32_t)bpp;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if (c >= bpp) break;
+                uint32_t up = __shfl_up_sync(0xffffffffu, cur[c], 1);       // lane L-1's pixel x (computed last step)
+                if (lane == 0) up = (band > 0 && act) ? above[kx + c] : 0;
+                if (act) {
+                    const uint32_t k = kx + c, pos = a0 + k;                // byte index in the row / in rowwords
+                    if ((pos & 3) == 0 || k == 0) rword = rowwords[pos >> 2];   // (fetching words ahead of use measured slower: the pass is issue-bound)
+                    const uint32_t raw = (rword >> (8 * (pos & 3))) & 0xFFu;
+                    const uint32_t a = left[c], b = up, cc = upl[c];
+                    // every predictor, then a select on the row's filter type (the lanes of a warp hold rows of different
+                    // types: branches would run one after the other)
+                    const int pa = abs((int)b - (int)cc), pb = abs((int)a - (int)cc), pc = abs((int)a + (int)b - 2 * (int)cc);
+                    const uint32_t paeth = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : cc);
+                    uint32_t pred = f_sub ? a : 0u;
+                    pred = f_up ? b : pred;
+                    pred = f_avg ? (a + b) >> 1 : pred;
+                    pred = f_paeth ? paeth : pred;
+                    const uint32_t v = (raw + pred) & 0xFFu;
+                    if (word_out) {
+                        wword |= v << (8 * (k & 3));
+                        if ((k & 3) == 3) {
+                            *reinterpret_cast<uint32_t*>(orow + (k & ~3u)) = wword;
+                            wword = 0;
+                        }
+                    } else {
+                        orow[k] = (uint8_t)v;
+                    }
+                    if (lane == 31) mine[k] = (uint8_t)v;                   // the row the next band starts from
+                    left[c] = v;
+                    upl[c] = b;
+                    cur[c] = v;
+                }
+            }
+            if ((step & 7) == 7 || step == w + 30) {                        // publish: `step + 1` steps of this band are done
+                __syncwarp();
+                if (lane == 31) {
+                    __threadfence_block();
+                    vprog[warp] = base + (unsigned int)step + 1u;
+                }
+            }
+        }
+    }
+    if (__ballot_sync(0xffffffffu, bad) && lane == 0) atomicOr(&any_bad, 1);
+    __syncthreads();
+    if (threadIdx.x == 0 && any_bad) set_status(status, wi, 41);
 }
 
 // ================================================================================================ TIFF assembly
@@ -1629,12 +1748,14 @@ extern "C" int b2_assemble_images(b2_ctx* ctx, uint8_t* scratch, const b2_image_
     DeviceGuard g(ctx->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     bool any_png = false, any_tiff = false;
+    int wide_row = 0;                               // longest row among the PNGs the eight-warp un-filter takes
     uint64_t max_bytes = 0;
     long long max_rows[5] = {0, 0, 0, 0, 0};       // predictor-2 rows of the largest image, per sample size
     unsigned spb_mask[5] = {0, 0, 0, 0, 0};        // interleave factors present (bit 0: images that need the generic walk)
     for (int i = 0; i < n_images; i++) {
         const b2_image_desc& im = imgs_host[i];
         if (im.format == 2) any_png = true;
+        if (png_wide_eligible(im) && im.width * im.samples > wide_row) wide_row = im.width * im.samples;
         if (im.format == 1) {
             any_tiff = true;
             const uint64_t nb = (uint64_t)im.width * im.height * im.samples * im.bytes_per_sample;
@@ -1685,6 +1806,10 @@ extern "C" int b2_assemble_images(b2_ctx* ctx, uint8_t* scratch, const b2_image_
     if (any_png) {
         png_unfilter_kernel<<<(n_images * 32 + 127) / 128, 128, 0, s>>>(scratch, imgs_dev, n_images, out, status);   // (+ expand pass)
         ctx->launches++;
+        if (wide_row) {                                                    // its share of the images
+            png_unfilter_wide_kernel<<<n_images, kUfWarps * 32, 0, s>>>(scratch, imgs_dev, n_images, out, status);
+            ctx->launches++;
+        }
         B2_CUDA(cudaGetLastError());
     }
     return 0;

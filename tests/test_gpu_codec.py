@@ -331,3 +331,24 @@ def test_lzw_streams_that_alternate_full_and_short_segments(dev):
         wants += [img, lab[:, :, None], img, img]
     for _ in range(3):
         _check(dev, blobs, wants)
+
+
+@pytest.mark.parametrize("channels", [1, 2, 3, 4])
+def test_png_unfilter_with_eight_warps_per_image(dev, channels):
+    """Images of 96 rows and more (8-bit, progressive, rows of at most 4096 bytes) are un-filtered by eight warps that hand
+    the last row of every band of 32 rows on through shared memory: every filter type and mixes of them, heights that end
+    in a partial band, one band per warp and several, the longest row taken and the first one left to the one-warp kernel,
+    many images at once so that the CTAs of several waves overlap."""
+    rng = np.random.default_rng(10 + channels)
+    blobs, wants = [], []
+    shapes = [(96, 33), (97, 64), (256, 256), (300, 130), (129, 4096 // channels), (128, 4096 // channels + 1), (700, 40)]
+    for j, (h, w) in enumerate(shapes):
+        img = rng.integers(0, 256, (h, w, channels), dtype=np.uint8)
+        img[h // 3:h // 2] = (syn.smooth_field(rng, h // 2 - h // 3, w)[..., None] * 255).astype(np.uint8)
+        for filters in ((4,), (3,), (2,), (1, 0), (0, 1, 2, 3, 4), (4, 3, 2)):
+            if j >= 4 and filters != (0, 1, 2, 3, 4):
+                continue
+            blobs.append(syn.png_bytes_manual(img, filter_types=filters, zlevel=1))
+            wants.append(img)
+    blobs, wants = blobs * 6, wants * 6
+    _check(dev, blobs, wants)
