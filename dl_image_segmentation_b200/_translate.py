@@ -18,7 +18,7 @@ import torch
 
 from . import _codec, ops
 from . import _lib as _lib_mod
-from ._lib import check, get_ctx, lib
+from ._lib import B2Error, check, get_ctx, lib
 
 _MAPPED_WRITE_MIN = 32 << 20     # pieces this large are written pwrite-head + mapped-rest (see run_worker.write_back)
 
@@ -410,11 +410,10 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
         # (pinned staging) — sized from the first pair
         batch_pairs = int(max(32, min(1024, (512 << 20) // max(1, pair_bytes))))
     # clean batches of decoded-array records, or of raw-file records that need no decode to be validated, skip per-chip Python
-    # convert_png_to_jpg with file-bytes records: decode, encode and assemble the JPEG files on the device; with array
-    # records (the pixels of the JPEG decoded again) the chip-by-chip path stays
-    to_jpg = bool(png_to_jpg and not store_as_array)
-    fast = bool((not png_to_jpg or to_jpg) and path_key is not None and
-                (store_as_array or validate is None or fast_validate is not None))
+    # convert_png_to_jpg: decode, encode and assemble the JPEG files on the device; array records carry the pixels of those
+    # files decoded again (the files cross to the host once for the JPEG planner's marker walk)
+    to_jpg = bool(png_to_jpg)
+    fast = bool(path_key is not None and (store_as_array or validate is None or fast_validate is not None))
     # file-bytes records whose chips must decode before they are accepted (the threaded translator, :94-105): the files go up
     # as they are for the records AND a planned copy of their compressed streams goes through the decoders for the verdict
     check_decode = bool(fast and not store_as_array and validate is not None and not to_jpg)
@@ -650,7 +649,23 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                                 print("Converting PNG to JPEG for %s" % lbl_filenames[i])
                         files, foffs, fsizes = _codec.encode_jpeg_device(job.out, job.images["out_off"], infos["height"], infos["width"],
                                                                          infos["samples"], quality=100, device=ctx.device)
-                        rec = BatchRecords.from_files(files, foffs, fsizes, infos, ids, ctx)
+                        if store_as_array:
+                            used = int(foffs[-1] + fsizes[-1])
+                            hbuf = cache.get("jpg_host")
+                            if hbuf is None or hbuf.numel() < used:
+                                hbuf = cache["jpg_host"] = torch.empty((int(used * 1.25) + 4096,), dtype=torch.uint8).pin_memory()
+                            hbuf[:used].copy_(files[:used], non_blocking=True)
+                            torch.cuda.current_stream(ctx.device).synchronize()
+                            hnp = hbuf.numpy()
+                            _codec.reserve_staging(ctx.device, 0, sets=(kAhead + 2) * 2)
+                            jb = _codec.plan_jpeg_batch([hnp[int(o):int(o + z)] for o, z in zip(foffs, fsizes)], ctx.device,
+                                                        threads=plan_threads)
+                            _codec.jpeg_decode_enqueue(jb, ctx.device)
+                            if jb.status().any():
+                                raise B2Error("convert_png_to_jpg: a JPEG file this package encoded does not decode")
+                            rec = BatchRecords.from_jpeg(jb, ids, ctx)
+                        else:
+                            rec = BatchRecords.from_files(files, foffs, fsizes, infos, ids, ctx)
                     elif jpeg is not None and store_as_array:
                         rec = BatchRecords.from_jpeg(jpeg, ids, ctx)
                     else:
