@@ -12,6 +12,7 @@ from ._tfrecord_image_translation import (convert_to_example, featuretemplate_by
                                           featuretemplate_ndarray_imagechip, parse_8bit_array_proto,
                                           parse_encoded_gdal_proto_eager, parse_encoded_gdal_proto_wrapped,
                                           parse_encoded_rgb_img_proto, parse_encoded_shard, parse_higher_dtype_array_proto)
+from ._tfrecord_image_translation import iter_parse_encoded_shards  # noqa: F401,E402
 
 from ._geotiff import encode_geotiffs, write_chip_pair  # noqa: F401
 

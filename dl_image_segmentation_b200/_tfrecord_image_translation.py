@@ -247,17 +247,47 @@ def parse_encoded_shard(shard, parser="gdal_eager", verify_crc=True, device=None
     for).  Returns a list of (img, target, identifier) exactly as the per-record function returns them; errors are the
     per-record function's (DataLossError for a CRC mismatch, InvalidArgumentError for a record that does not fit the
     template or a blob that does not decode)."""
-    import os
-
-    from . import _codec
     if parser not in _ENCODED_PARSERS:
         raise ValueError("parser must be one of %s" % sorted(_ENCODED_PARSERS))
     ctx = ops.get_ctx(device)
-    # the shard goes into pinned memory once (a few threads), up to the device once, and — unless the planner has to move
-    # bytes (PNG IDAT payloads are compacted) — the decoders read the blobs where the uploaded shard has them
+    return _parse_staged_shard(*_stage_shard(shard, ctx), parser, verify_crc, ctx)
+
+
+def iter_parse_encoded_shards(shards, parser="gdal_eager", verify_crc=True, device=None):
+    """parse_encoded_shard over a sequence of shards, yielding one list of (img, target, identifier) per shard; the next
+    shard is read into pinned memory on a helper thread while the current one is uploaded and decoded (the host copy is half
+    of a shard's wall time)."""
+    from concurrent.futures import ThreadPoolExecutor
+    if parser not in _ENCODED_PARSERS:
+        raise ValueError("parser must be one of %s" % sorted(_ENCODED_PARSERS))
+    ctx = ops.get_ctx(device)
+    shards = list(shards)
+    if not shards:
+        return
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        nxt = pool.submit(_stage_shard, shards[0], ctx)
+        for i in range(len(shards)):
+            staged = nxt.result()
+            if i + 1 < len(shards):
+                nxt = pool.submit(_stage_shard, shards[i + 1], ctx)     # the OTHER of the two staging sets
+            yield _parse_staged_shard(*staged, parser, verify_crc, ctx)
+
+
+def _stage_shard(shard, ctx):
+    """The shard's bytes into one of the device's two pinned shard buffers (a few threads).  Returns (staging set, bytes)."""
+    import os
+
+    from . import _codec
     hs = _codec.shard_staging(ctx.device)
     n_bytes = _codec.fill_pinned(hs, shard if isinstance(shard, (str, os.PathLike)) else
                                  (np.frombuffer(shard, dtype=np.uint8) if isinstance(shard, (bytes, bytearray, memoryview)) else shard))
+    return hs, n_bytes
+
+
+def _parse_staged_shard(hs, n_bytes, parser, verify_crc, ctx):
+    # the shard goes into pinned memory once, up to the device once, and — unless the planner has to move bytes (PNG IDAT
+    # payloads are compacted) — the decoders read the blobs where the uploaded shard has them
+    from . import _codec
     if n_bytes == 0:
         return []
     shard_d = hs.stage[:n_bytes + 64].to(ctx.device, non_blocking=True)      # + the decoders' look-ahead past the last blob

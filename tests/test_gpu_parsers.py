@@ -218,3 +218,31 @@ def test_parse_encoded_shard_errors_are_the_per_record_ones(dev, tmp_path):
         pkg.parse_encoded_shard(_shard_of([oep.convert_to_example(img.astype(np.float32), lab.astype(np.float32), 64, 64, 4, 64, 64,
                                                                   key).SerializeToString()]))
     del arr
+
+
+def test_iter_parse_encoded_shards_prefetches_and_equals_shard_by_shard(dev, tmp_path):
+    """The generator form reads shard k+1 into the other pinned buffer while shard k is decoded: same results as calling
+    parse_encoded_shard on each, for paths and bytes, for more shards than staging buffers, and with an empty shard between."""
+    import dl_image_segmentation_b200 as pkg
+    shards = []
+    for s in range(5):
+        recs = []
+        for i in range(3 + s % 2):
+            img, lab, key = syn.cfg3_chip(10 * s + i, size=64)
+            ib, lb = syn.tiff_bytes(img, tile=32), syn.tiff_bytes(lab, tile=32, nodata=255)
+            recs.append(oep.convert_to_example(ib, lb, 64, 64, 4, 64, 64, key).SerializeToString())
+        shards.append(_shard_of(recs))
+    shards.insert(2, b"")
+    paths = []
+    for k, b in enumerate(shards):
+        p = tmp_path / ("s%d" % k)
+        p.write_bytes(b)
+        paths.append(str(p))
+    want = [pkg.parse_encoded_shard(b, parser="gdal_wrapped") for b in shards]
+    for source in (shards, paths):
+        got = list(pkg.iter_parse_encoded_shards(source, parser="gdal_wrapped"))
+        assert [len(g) for g in got] == [len(w) for w in want]
+        for g, w in zip(got, want):
+            for (gi, gt, gid), (wi, wt, wid) in zip(g, w):
+                assert gid == wid and torch.equal(gi, wi) and torch.equal(gt, wt)
+    assert list(pkg.iter_parse_encoded_shards([])) == []

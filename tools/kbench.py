@@ -458,6 +458,20 @@ def bench_parse_encoded(dev):
         decoded = sum(int(a.numel()) * a.element_size() + int(b.numel()) * b.element_size() for a, b, _ in out)
         report("parse_encoded_shard %s: %d records" % (name, n), best, shard.size + decoded,
                {"records_per_s": round(n / best * 1e3, 1), "shard_MB": round(shard.size / 1e6, 1), "decoded_MB": round(decoded / 1e6, 1)})
+        del out
+        k = 6                                                          # the generator form: the next shard is staged meanwhile
+        best = None
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.time()
+            for out in pkg.iter_parse_encoded_shards([shard] * k, parser=parser):
+                pass
+            torch.cuda.synchronize()
+            dt = (time.time() - t0) * 1e3
+            best = dt if best is None or dt < best else best
+        del out
+        report("iter_parse_encoded_shards %s: %d shards x %d records" % (name, k, n), best, k * (shard.size + decoded),
+               {"records_per_s": round(k * n / best * 1e3, 1)})
 
 
 def main():
