@@ -46,7 +46,8 @@ def _process_image_files_mp_worker(proc_index, ranges, name, img_filenames, lbl_
         return "|".join((os.path.basename(p), gt, crs))
     path_key = (lambda p: _translate.tile_key_from_path(p, True)) if dltile_from_filename else None
     return _translate.run_worker(proc_index, ranges, name, img_filenames, lbl_filenames, output_directory, num_shards,
-                                 key_fn, store_as_array, label="process", progress_every=100, device=device, path_key=path_key)
+                                 key_fn, store_as_array, label="process", progress_every=100, device=device, path_key=path_key,
+                                 info_keys=not dltile_from_filename)
 
 
 def _process_image_files_mp(name, img_files, lbl_files, out_folder, num_shards, num_proc, dltile_from_filename,

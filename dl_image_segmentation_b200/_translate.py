@@ -369,7 +369,7 @@ def batch_schedule(shard_ranges, batch_pairs, interleave=8):
 
 def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_directory, num_shards, key_fn,
                store_as_array, label="process", progress_every=100, validate=None, device=None, batch_pairs=None,
-               io_threads=8, png_as_tf=False, png_to_jpg=False, path_key=None, fast_validate=None):
+               io_threads=8, png_as_tf=False, png_to_jpg=False, path_key=None, fast_validate=None, info_keys=False):
     """The reference's worker loop as a pipeline over decode batches:
 
         read-ahead thread : files of batch k+2 -> pinned staging (one native call), header parse + stream tables in place
@@ -381,8 +381,9 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
     irregularity (unreadable / undecodable chip, key mismatch, .jpg chips, convert_png_to_jpg, raw-bytes records, identifiers
     from the georeferencing) goes through load_pairs, which reproduces the reference's skip-and-continue chip by chip.
 
-    path_key(path) -> identifier (when it depends on the file name only); fast_validate(infos) -> boolean array, False where
-    the reference's shape asserts would fail."""
+    path_key(path) -> identifier (when it depends on the file name only); info_keys: the identifier needs the file's header
+    as well (georeferencing) — key_fn(path, info) is then called per file on the read-ahead thread with the planner's
+    ImageInfo; fast_validate(infos) -> boolean array, False where the reference's shape asserts would fail."""
     from concurrent.futures import ThreadPoolExecutor
     num_workers = len(ranges)
     assert not num_shards % num_workers
@@ -413,7 +414,7 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
     # convert_png_to_jpg: decode, encode and assemble the JPEG files on the device; array records carry the pixels of those
     # files decoded again (the files cross to the host once for the JPEG planner's marker walk)
     to_jpg = bool(png_to_jpg)
-    fast = bool(path_key is not None and (store_as_array or validate is None or fast_validate is not None))
+    fast = bool((path_key is not None or info_keys) and (store_as_array or validate is None or fast_validate is not None))
     # file-bytes records whose chips must decode before they are accepted (the threaded translator, :94-105): the files go up
     # as they are for the records AND a planned copy of their compressed streams goes through the decoders for the verdict
     check_decode = bool(fast and not store_as_array and validate is not None and not to_jpg)
@@ -539,10 +540,10 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                                                 threads=plan_threads)
                 return dict(fast=False, blobs=blobs, planned=planned)
             hs = _codec.take_staging(ctx.device)
-            planned = infos = offs = sizes = jpeg = None
+            planned = infos = offs = sizes = jpeg = probed = None
             try:
                 blobs, offs, sizes, clean = reader.read_into(paths, hs)     # straight into the pinned staging buffer
-                if clean and not to_jpg and sizes.min() >= 3:               # a batch of .jpg chips (SOI marker FF D8 FF)
+                if clean and not to_jpg and path_key is not None and sizes.min() >= 3:   # a batch of .jpg chips (SOI marker FF D8 FF)
                     st_np, o64 = hs.stage.numpy(), offs.astype(np.int64)
                     if bool(np.all((st_np[o64] == 0xFF) & (st_np[o64 + 1] == 0xD8) & (st_np[o64 + 2] == 0xFF))):
                         _codec.reserve_staging(ctx.device, 0, sets=(kAhead + 2) * 2)   # a second set per batch in flight
@@ -556,7 +557,8 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                 elif clean and check_decode:                                # into a staging set of its own: hs keeps the files
                     planned = _codec.plan_blobs(blobs, ctx.device, png_as_tf, threads=plan_threads)
                 elif clean:                                                 # raw-bytes records: the header fields only
-                    infos = np.frombuffer(_codec.probe_blobs(blobs, png_as_tf=png_as_tf), dtype=_codec.IMAGE_INFO_DTYPE, count=len(paths))
+                    probed = _codec.probe_blobs(blobs, png_as_tf=png_as_tf)
+                    infos = np.frombuffer(probed, dtype=_codec.IMAGE_INFO_DTYPE, count=len(paths))
                     clean = not infos["status"].any()
             except Exception:
                 planned, clean = None, False
@@ -567,7 +569,11 @@ def run_worker(worker_index, ranges, name, img_filenames, lbl_filenames, output_
                     jpeg.release()
                 hs.pending = False
                 return dict(fast=False, blobs=None, planned=None)           # the chip-by-chip path re-reads the files
-            keys = [path_key(p) for p in paths]
+            if path_key is not None:
+                keys = [path_key(p) for p in paths]
+            else:                                                           # identifiers from the header (georeferencing)
+                ci = planned.infos if planned is not None else probed
+                keys = [key_fn(p, ci[i]) for i, p in enumerate(paths)]
             return dict(fast=True, planned=planned, keys=keys, hs=hs, infos=infos, offs=offs, sizes=sizes, jpeg=jpeg)
 
         def stage1(bi):
