@@ -246,3 +246,37 @@ def test_iter_parse_encoded_shards_prefetches_and_equals_shard_by_shard(dev, tmp
             for (gi, gt, gid), (wi, wt, wid) in zip(g, w):
                 assert gid == wid and torch.equal(gi, wi) and torch.equal(gt, wt)
     assert list(pkg.iter_parse_encoded_shards([])) == []
+
+
+def test_parse_encoded_shard_mixed_blob_formats(dev):
+    """parser='rgb' stands for tf.io.decode_image: PNG of any flavour and JPEG blobs in one shard.  A palette PNG makes the
+    in-place planner give way to the gathering one; the .jpg blobs are the ones the TIFF / PNG planner refuses and go
+    through the JPEG path; every record must equal the per-record parser's result."""
+    import cv2
+    import dl_image_segmentation_b200 as pkg
+    rng = np.random.default_rng(3)
+    recs = []
+    for i in range(6):
+        img, lab, key = syn.cfg1_chip(i, size=64)
+        if i % 3 == 0:                                                       # palette image, 2-bit grey label
+            idx = rng.integers(0, 16, (64, 64))
+            ib = syn.png_bytes_flavour(idx, 8, 3, palette=rng.integers(0, 256, (16, 3)))
+            lb = syn.png_bytes_flavour(rng.integers(0, 4, (64, 64)), 2, 0)
+        elif i % 3 == 1:                                                     # baseline JPEG image, PNG label
+            ib = cv2.imencode(".jpg", np.ascontiguousarray(img[..., ::-1]), [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes()
+            lb = syn.png_bytes(lab)
+        else:
+            ib, lb = syn.png_bytes(img), syn.png_bytes(lab)
+        recs.append(oep.convert_to_example(ib, lb, 64, 64, 3, 64, 64, key).SerializeToString())
+    got = pkg.parse_encoded_shard(_shard_of(recs), parser="rgb")
+    assert len(got) == len(recs)
+    for rec, (gi, gt, gid) in zip(recs, got):
+        si, st, sid = pkg.parse_encoded_rgb_img_proto(rec)
+        assert gid == sid and gi.dtype == si.dtype and gt.dtype == st.dtype
+        assert tuple(gi.shape) == tuple(si.shape) and tuple(gt.shape) == tuple(st.shape)
+        assert torch.equal(gi, si) and torch.equal(gt, st)
+    # and without the palette record the in-place plan is kept: same answers
+    plain = [r for k, r in enumerate(recs) if k % 3 != 0]
+    for rec, (gi, gt, gid) in zip(plain, pkg.parse_encoded_shard(_shard_of(plain), parser="rgb")):
+        si, st, sid = pkg.parse_encoded_rgb_img_proto(rec)
+        assert gid == sid and torch.equal(gi, si) and torch.equal(gt, st)
