@@ -161,3 +161,37 @@ def test_large_pieces_written_through_shared_mapping(dev, tmp_path, monkeypatch)
     want = otr.images_to_tfrecords("t", str(tmp_path), out_c, 2, num_proc=1, file_ext=ext, store_as_array=True, n_jobs=1)
     assert wrote == want == n
     _same_shards(out_g, out_c)
+
+
+@pytest.mark.parametrize("store_as_array", [False, True])
+@pytest.mark.parametrize("convert", [False, True])
+def test_threaded_translator_modes_against_the_oracle_loop(dev, tmp_path, store_as_array, convert):
+    """images_to_tfrecords_mt in its four modes on a clean folder (every batch takes the batched path: decode-to-validate
+    beside the upload of the files; device-side JPEG encode and file assembly; records from the re-decoded JPEG files) and on
+    a clean folder of .jpg chips (JPEG plan on the read-ahead thread): shards byte-identical with the oracle's restatement of
+    the reference's worker loop, which decodes and encodes with libjpeg-turbo itself."""
+    import cv2
+    import dl_image_segmentation_b200 as pkg
+    os.environ["B2_ORACLE_JPEG"] = "libjpeg"
+    try:
+        _write_dataset(tmp_path / "png", "png", 23, 48)
+        jd = tmp_path / "jpg"
+        os.makedirs(jd / "images")
+        os.makedirs(jd / "labels")
+        for i in range(23):
+            img, lab, key = syn.cfg1_chip(i, size=48)
+            for sub, arr in (("images", np.ascontiguousarray(img[..., ::-1])), ("labels", lab)):
+                (jd / sub / (key.replace(":", "#") + ".jpg")).write_bytes(cv2.imencode(".jpg", arr, [cv2.IMWRITE_JPEG_QUALITY, 92])[1].tobytes())
+        for folder in ("png", "jpg"):
+            if folder == "jpg" and convert:
+                continue                                                     # convert_png_to_jpg leaves .jpg chips alone: same job
+            root = str(tmp_path / folder)
+            out_g, out_c = os.path.join(root, "g"), os.path.join(root, "c")
+            with contextlib.redirect_stdout(io.StringIO()):
+                pkg.images_to_tfrecords_mt("m", root, out_g, 3, num_threads=1, store_as_array=store_as_array, convert_png_to_jpg=convert)
+                want = otr.images_to_tfrecords_mt("m", root, out_c, 3, num_threads=1, store_as_array=store_as_array,
+                                                  convert_png_to_jpg=convert)
+            assert want == 23
+            _same_shards(out_g, out_c)
+    finally:
+        os.environ.pop("B2_ORACLE_JPEG", None)
