@@ -542,12 +542,9 @@ extern "C" int b2_lzw_encode_restart(b2_ctx* ctx, const uint8_t* raw, const b2_e
     B2_CUDA(cudaMemcpyAsync(ws + off_descs, descs_host, (size_t)n * sizeof(b2_enc_desc), cudaMemcpyHostToDevice, s));
     B2_CUDA(cudaMemcpyAsync(ws + off_start, seg_start.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s));
     B2_CUDA(cudaStreamSynchronize(s));                                  // the host arrays are read by the copies above
-    static bool attr_done = false;
     const int smem = kSegWarps * kSegLanes * kSegSlots * 4;
-    if (!attr_done) {
-        B2_CUDA(cudaFuncSetAttribute(lzw_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
-    }
+    // (per device: a process may hold one context per GPU, so no "done once" flag)
+    B2_CUDA(cudaFuncSetAttribute(lzw_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     SegArgs a{raw, reinterpret_cast<const b2_enc_desc*>(ws + off_descs), reinterpret_cast<const uint32_t*>(ws + off_start), 0, 0, 0, 0,
               restart_bytes, slot_codes, reinterpret_cast<uint16_t*>(ws + off_scratch), reinterpret_cast<uint32_t*>(ws + off_bits),
               reinterpret_cast<uint32_t*>(ws + off_pos), reinterpret_cast<unsigned int*>(ws), out, out_len};

@@ -135,3 +135,19 @@ def test_lzw_restart_large_batch_spans_several_scratch_groups(dev):
     got = _geotiff.lzw_encode_tiles(raw, [len(m) for m in msgs], dev, restart=1024)
     for i, g in enumerate(got):
         assert g == want[i % 3], i
+
+
+def test_writer_on_a_second_device(dev):
+    """The restart encoder opts in to 224 KiB of dynamic shared memory per DEVICE: a process that encodes on GPU 0 and then
+    on GPU 1 (one context per GPU, as run_workers does) must not rely on a once-per-process setting."""
+    import torch
+
+    from dl_image_segmentation_b200 import _geotiff
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    img, _, _ = syn.cfg3_chip(5, size=256)
+    want = syn.tiff_bytes(img, tile=256, lzw_restart=_geotiff.LZW_RESTART)
+    for d in (0, 1, 0):
+        t = torch.from_numpy(img.view(np.int16)).to("cuda:%d" % d).view(torch.uint16)
+        (blob,) = _geotiff.encode_geotiffs([t], device=torch.device("cuda", d))
+        assert blob == want, d
