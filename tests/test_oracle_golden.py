@@ -318,3 +318,25 @@ def test_normalise_onehot_and_stats_definitions():
     m, s = onorm.mean_std_from_stats(st)
     np.testing.assert_allclose(m, flat.mean(0), rtol=1e-6)
     np.testing.assert_allclose(s, flat.std(0), rtol=1e-6)
+
+
+def test_fixture_lzw_encoder_with_restarts_round_trips_and_is_read_by_libtiff():
+    """The fixture encoder the GPU writer is compared with byte for byte (synthetic/csrc/lzwenc.c): with a Clear every R input
+    bytes its streams must decode back through the oracle's TIFF 6.0 decoder for any R and any data, restart 0 must be the
+    classic stream, and libtiff (through OpenCV) must read a tiled file made of such streams."""
+    import cv2
+    import synthetic as syn
+    from oracle import imagecodecs as oic
+    rng = np.random.default_rng(21)
+    msgs = [b"", b"x", bytes(3000), bytes(range(256)) * 9, rng.integers(0, 256, 5000, dtype=np.uint8).tobytes(),
+            rng.integers(0, 3, 20000, dtype=np.uint8).tobytes(), rng.integers(0, 256, 1024, dtype=np.uint8).tobytes(),
+            rng.integers(0, 256, 1025, dtype=np.uint8).tobytes()]
+    for m in msgs:
+        assert syn.lzw_encode(m, 0) == syn.lzw_encode(m)
+        for restart in (16, 48, 400, 1024):
+            enc = syn.lzw_encode(m, restart)
+            assert oic.lzw_decode(enc, len(m)) == m, (len(m), restart)
+    arr = rng.integers(0, 60000, (300, 500), dtype=np.uint16)
+    blob = syn.tiff_bytes(arr, tile=256, lzw_restart=1024)
+    assert np.array_equal(cv2.imdecode(np.frombuffer(blob, np.uint8), cv2.IMREAD_UNCHANGED), arr)
+    assert np.array_equal(oic.decode_image(blob)[..., 0], arr)
